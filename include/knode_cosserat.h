@@ -1,0 +1,140 @@
+/* knode_cosserat.h — C ABI of libknode_cosserat_b200.so (hand-written sm_100a kernels).
+ *
+ * This is the drop-in boundary for the one hot path of hsiehScalAR/KNODE-Cosserat: batched Cosserat-rod ODE
+ * evaluations, shooting marches, time rollouts and the KNODE (physics + MLP residual) teacher-forced training
+ * step.  The reference has no FFI of its own — its boundary is the Python surface of
+ * knode_cosserat/cosserat_ode_torch.py, cosserat_ode.py and knode.py — so every entry point below names the
+ * reference function (file:line, relative to the reference repo root) whose arithmetic it replaces.  The
+ * Python classes in knode-cosserat_b200/ bind these with ctypes (see INTEGRATION.md for the stub).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every data pointer is a DEVICE pointer unless its name ends in _host;
+ *   - `dtype` selects the arithmetic type of every data pointer of the call: KC_F32 or KC_F64;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); calls are asynchronous and
+ *     never allocate: scratch is caller-provided (`workspace`, sized by the matching *_workspace_bytes call);
+ *   - return value 0 = launched; <0 = error (KC_E*), text via kc_last_error() (thread-local);
+ *   - state layout (cosserat_ode_torch.py:141-152): y[19] = p(0:3) h(3:7,wxyz) n(7:10) m(10:13) q(13:16)
+ *     w(16:19); z[6] = v(0:3) u(3:6); a rod is [25][N] row-major (rows = y then z, columns = nodes).
+ */
+#ifndef KNODE_COSSERAT_H
+#define KNODE_COSSERAT_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KC_F32 0
+#define KC_F64 1
+
+#define KC_OK 0
+#define KC_EINVAL (-1)   /* bad argument (NULL pointer, size, dtype, N < 2, unsupported MLP shape) */
+#define KC_ECUDA (-2)    /* CUDA runtime error at launch */
+#define KC_ENOSPACE (-3) /* workspace too small */
+
+#define KC_MARCH_EULER 0
+#define KC_MARCH_RK4 1
+
+/* Derived rod constants, exactly the attributes CosseratRodTorch.compute_intermediate_terms() produces
+ * (cosserat_ode_torch.py:108-129 == cosserat_ode.py:58-78), plus boundary conditions and tendon geometry
+ * (cosserat_ode_torch.py:25-45).  Always double; converted once per call to the arithmetic type. Matrices are
+ * row-major 3x3.  The host side refreshes this struct from the Python attributes on every call because callers
+ * mutate them (knode.setup_robot, knode.py:11-53). */
+typedef struct kc_rod_params {
+    int32_t N;        /* number of nodes (robot.N) */
+    int32_t reserved; /* must be 0 */
+    double ds, c0, c1, c2, rhoA;
+    double Kse_c0Bse_inv[9]; /* (Kse + c0*Bse)^-1 */
+    double Kbt_c0Bbt_inv[9]; /* (Kbt + c0*Bbt)^-1 */
+    double Bse[9], Bbt[9], rhoJ[9];
+    double Kse_vstar[3], rhoAg[3], C[3], F_tip[3], M_tip[3];
+    double p0[3], h0[4], q0[3], w0[3];
+    double tendon_dirs[12]; /* [4][3]; tendon_force = tensions[4] @ tendon_dirs (cosserat_ode_torch.py:334) */
+} kc_rod_params;
+
+/* The KNODE residual MLP: Linear(in_dim,hidden) -> ELU -> Linear(hidden,25) (cosserat_ode_torch.py:60-62).
+ * Weights in torch's nn.Linear layout, dtype of the call.  in_dim 28 = [y;z;tf], 53 = [y;yh;z;zh;tf]
+ * (nn_input_history, :194-197).  Pass a NULL kc_mlp* for physics only (use_nn == False). */
+typedef struct kc_mlp {
+    int32_t in_dim, hidden, out_dim, reserved;
+    const void *W1, *b1, *W2, *b2; /* W1[hidden][in_dim], b1[hidden], W2[25][hidden], b2[25] */
+} kc_mlp;
+
+int kc_version(void);
+const char *kc_last_error(void);
+
+/* CosseratRodTorch.ODE_parallel (cosserat_ode_torch.py:217-322), CosseratRodTorch.ODE (:137-214) and
+ * CosseratRod.ODE (cosserat_ode.py:114-186): Q independent node evaluations.
+ * y[Q][19], yh[Q][19], zh[Q][6], tf[Q][3] -> ys[Q][19], z[Q][6]. */
+int kc_ode_fwd(int dtype, const kc_rod_params *P, const kc_mlp *mlp, int64_t Q, const void *y, const void *yh,
+               const void *zh, const void *tf, void *ys, void *z, void *stream);
+
+/* Reverse mode of kc_ode_fwd (what torch.autograd does through ODE_parallel): cotangents g_ys[Q][19], g_z[Q][6]
+ * -> g_y[Q][19], g_yh[Q][19], g_zh[Q][6], g_tf[Q][3] (each may be NULL = not wanted) and, when mlp != NULL,
+ * parameter cotangents gW1[hidden][in], gb1[hidden], gW2[25][hidden], gb2[25] which are OVERWRITTEN (may be
+ * NULL).  workspace: kc_ode_bwd_workspace_bytes(). */
+int64_t kc_ode_bwd_workspace_bytes(int dtype, const kc_mlp *mlp, int64_t Q);
+int kc_ode_bwd(int dtype, const kc_rod_params *P, const kc_mlp *mlp, int64_t Q, const void *y, const void *yh,
+               const void *zh, const void *tf, const void *g_ys, const void *g_z, void *g_y, void *g_yh,
+               void *g_zh, void *g_tf, void *gW1, void *gb1, void *gW2, void *gb2, void *workspace,
+               int64_t workspace_bytes, void *stream);
+
+/* Shooting residual + spatial march for B rods: CosseratRod.getResidualEuler (cosserat_ode.py:188-213),
+ * CosseratRod.getResidualRK4 (:215-255), CosseratRodTorch.getResidualEuler (cosserat_ode_torch.py:325-367).
+ * G[B][6], y[B][19][N] and z[B][6][N] are updated IN PLACE like the numpy reference does (column 0 of y is
+ * replaced by [p0,h0,G,q0,w0]; z[:, N-1] is left untouched), yh[B][19][N], zh[B][6][N], tensions[B][4]
+ * -> res[B][6] = [F_tip - n(L), M_tip - m(L)]. */
+int kc_march(int dtype, const kc_rod_params *P, const kc_mlp *mlp, int method, int64_t B, const void *G, void *y,
+             void *z, const void *yh, const void *zh, const void *tensions, void *res, void *stream);
+
+/* Teacher-forced one-step prediction: CosseratRodTorch.parallelGetNextSegmentEuler (cosserat_ode_torch.py:401-437)
+ * when K > 0 (key_idx_host[K] = node indices k, the ODE is evaluated at node k-1), and
+ * CosseratRodTorch.getNextSegmentEuler (:370-399) when K == 0 (all nodes; out column 0 = Gs column 0).
+ * Gs[S][25][N], yh[S][19][N], zh[S][6][N], tensions[S][4] -> out[S][25][K] (K>0) or out[S][25][N] (K==0). */
+int kc_segment_fwd(int dtype, const kc_rod_params *P, const kc_mlp *mlp, int64_t S, int32_t K,
+                   const int32_t *key_idx_host, const void *Gs, const void *yh, const void *zh,
+                   const void *tensions, void *out, void *stream);
+
+/* Time rollout of B independent rods: knode.simulate (knode.py:55-102) = BDF2 history (:74-77) + shooting solve
+ * of the 6 base reactions (:88-89, here quasi-Newton instead of MINPACK hybrd, converged to `tol`) + Euler march.
+ * tensions[B][T][4]; y0[B][19][N], z0[B][6][N] initial state or NULL for the straight rod of knode.py:58-64.
+ * traj[B][T][rows][N], rows = 25 ([y;z]) or 50 ([y;z;yh;zh], the reference's layout); index 0 is the initial
+ * state and the step driven by tensions[:, T-1] is not computed (knode.py:102 drops it).
+ * G_out[B][T][6] (may be NULL): converged base reactions; iters[B][T] int32 (may be NULL): marches used, negative
+ * if the solve did not reach tol in max_iter marches.
+ * tol <= 0 selects the default (1e-12 fp64, 2e-6 fp32; relative to max(1,|G|)). */
+int64_t kc_rollout_workspace_bytes(int dtype, const kc_rod_params *P, const kc_mlp *mlp, int64_t B, int64_t T);
+int kc_rollout_fwd(int dtype, const kc_rod_params *P, const kc_mlp *mlp, int64_t B, int64_t T,
+                   const void *tensions, const void *y0, const void *z0, double tol, int32_t max_iter,
+                   int32_t rows, void *traj, void *G_out, int32_t *iters, void *workspace,
+                   int64_t workspace_bytes, void *stream);
+
+/* One teacher-forced training step of physics_train.py's fast path (:313-368) == slow path (:215-267) restricted
+ * to its key nodes == train_segment.py:140-185: for every trajectory b, step t in [0, T-2] and key node k:
+ * ODE+MLP at node k-1 of the NEXT ground-truth state, Euler step, 4-term MSE loss (p | n,m,q,w | euler(h) | z,
+ * physics_train.py:345-352, Utils/transformations.py:3-31), summed and divided by (T-1); reverse mode to the four
+ * MLP tensors.  traj[B][T][25][N], controls[B][T][4], key_idx_host[K]
+ * -> loss[1] (float64 always), gW1[hidden][in], gb1[hidden], gW2[25][hidden], gb2[25] (OVERWRITTEN), and
+ * pred[B][T-1][25][K] if pred != NULL. */
+int64_t kc_train_step_workspace_bytes(int dtype, const kc_mlp *mlp, int64_t B, int64_t T, int32_t K);
+int kc_train_step(int dtype, const kc_rod_params *P, const kc_mlp *mlp, int64_t B, int64_t T, int32_t K,
+                  const int32_t *key_idx_host, const void *traj, const void *controls, double *loss, void *gW1,
+                  void *gb1, void *gW2, void *gb2, void *pred, void *workspace, int64_t workspace_bytes,
+                  void *stream);
+
+/* torch.optim.Adam step (L2 weight decay folded into the gradient) followed by the reference's non-negative clamp of
+ * the Linear weights (physics_train.py:199,296-304): n elements of param/grad/exp_avg/exp_avg_sq, step >= 1. */
+int kc_adam_clamp(int dtype, int64_t n, void *param, const void *grad, void *exp_avg, void *exp_avg_sq,
+                  int32_t step, double lr, double beta1, double beta2, double eps, double weight_decay,
+                  int32_t clamp_min_zero, void *stream);
+
+/* FMA-pipe micro-benchmark used as the compute-roofline denominator by bench.py: runs `iters` dependent-chain
+ * FMAs x 8 chains per thread on a full grid and returns the number of FLOPs executed in *flops_host; time it with
+ * CUDA events on `stream`. */
+int kc_fma_peak(int dtype, int64_t iters, double *flops_host, void *scratch, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KNODE_COSSERAT_H */

@@ -1,0 +1,244 @@
+"""Tensor-level wrappers over the C ABI (include/knode_cosserat.h).
+
+Every function takes CUDA torch tensors, allocates the outputs / workspace with torch (device memory plumbing only),
+and launches the hand-written kernels on torch's current CUDA stream.  There is deliberately no CPU path: a CPU
+tensor, a missing library or a missing GPU raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+import _kc
+
+_DT = {torch.float32: _kc.KC_F32, torch.float64: _kc.KC_F64}
+
+
+def _dtype_code(t: torch.Tensor) -> int:
+    if t.dtype not in _DT:
+        raise TypeError(f"knode-cosserat_b200 kernels compute in float32 or float64, got {t.dtype}")
+    return _DT[t.dtype]
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("knode-cosserat_b200 has no CPU fallback: tensors must live on a CUDA device "
+                               "(construct the robot with device='cuda')")
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _c(t, dtype=None):
+    """contiguous (and optionally cast) view/copy"""
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    return t.contiguous()
+
+
+class Mlp:
+    """Borrowed view of the four nn.Linear tensors in the layout kc_mlp wants."""
+
+    def __init__(self, W1, b1, W2, b2):
+        self.W1, self.b1, self.W2, self.b2 = (_c(W1.detach()), _c(b1.detach()), _c(W2.detach()), _c(b2.detach()))
+        self.hidden, self.in_dim = self.W1.shape
+        if self.W2.shape != (25, self.hidden):
+            raise ValueError(f"second Linear must be [25,{self.hidden}], got {tuple(self.W2.shape)}")
+        self.c = _kc.kc_mlp(self.in_dim, self.hidden, 25, 0, self.W1.data_ptr(), self.b1.data_ptr(),
+                            self.W2.data_ptr(), self.b2.data_ptr())
+
+    def cast(self, dtype):
+        if self.W1.dtype == dtype:
+            return self
+        return Mlp(self.W1.to(dtype), self.b1.to(dtype), self.W2.to(dtype), self.b2.to(dtype))
+
+    def ref(self):
+        return C.byref(self.c)
+
+
+def _mlp_ref(mlp, dtype):
+    if mlp is None:
+        return None, None
+    m = mlp.cast(dtype)
+    return m, m.ref()
+
+
+def ode_fwd(P: _kc.kc_rod_params, mlp, y, yh, zh, tf):
+    """kc_ode_fwd: y[Q,19], yh[Q,19], zh[Q,6], tf[Q,3] -> ys[Q,19], z[Q,6]."""
+    _require_cuda(y, yh, zh, tf)
+    dt = y.dtype
+    y, yh, zh, tf = _c(y), _c(yh, dt), _c(zh, dt), _c(tf, dt)
+    Q = y.shape[0]
+    ys = torch.empty((Q, 19), dtype=dt, device=y.device)
+    z = torch.empty((Q, 6), dtype=dt, device=y.device)
+    keep, mref = _mlp_ref(mlp, dt)
+    with torch.cuda.device(y.device):
+        rc = _kc.lib().kc_ode_fwd(_dtype_code(y), C.byref(P), mref, Q, _ptr(y), _ptr(yh), _ptr(zh), _ptr(tf), _ptr(ys),
+                                  _ptr(z), _stream(y.device))
+    _kc.check(rc, "kc_ode_fwd")
+    return ys, z
+
+
+def ode_bwd(P, mlp, y, yh, zh, tf, g_ys, g_z, need_inputs=True, need_params=True):
+    """kc_ode_bwd -> (g_y, g_yh, g_zh, g_tf, gW1, gb1, gW2, gb2) (None where not requested)."""
+    _require_cuda(y, yh, zh, tf, g_ys, g_z)
+    dt = y.dtype
+    dev = y.device
+    y, yh, zh, tf, g_ys, g_z = _c(y), _c(yh, dt), _c(zh, dt), _c(tf, dt), _c(g_ys, dt), _c(g_z, dt)
+    Q = y.shape[0]
+    gi = [torch.empty_like(t) for t in (y, yh, zh, tf)] if need_inputs else [None] * 4
+    keep, mref = _mlp_ref(mlp, dt)
+    gp = [None] * 4
+    if mlp is not None and need_params:
+        gp = [torch.empty_like(t) for t in (keep.W1, keep.b1, keep.W2, keep.b2)]
+    with torch.cuda.device(dev):
+        nbytes = _kc.lib().kc_ode_bwd_workspace_bytes(_dtype_code(y), mref, Q)
+        ws = torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=dev)
+        rc = _kc.lib().kc_ode_bwd(_dtype_code(y), C.byref(P), mref, Q, _ptr(y), _ptr(yh), _ptr(zh), _ptr(tf),
+                                  _ptr(g_ys), _ptr(g_z), *[_ptr(t) for t in gi], *[_ptr(t) for t in gp], _ptr(ws),
+                                  int(nbytes), _stream(dev))
+    _kc.check(rc, "kc_ode_bwd")
+    return (*gi, *gp)
+
+
+def march(P, mlp, G, y, z, yh, zh, tensions, method=_kc.KC_MARCH_EULER):
+    """kc_march, IN PLACE on y[B,19,N], z[B,6,N]; returns res[B,6]."""
+    _require_cuda(G, y, z, yh, zh, tensions)
+    dt = y.dtype
+    if not (y.is_contiguous() and z.is_contiguous()):
+        raise ValueError("y and z must be contiguous (they are updated in place)")
+    G, yh, zh, tensions = _c(G, dt), _c(yh, dt), _c(zh, dt), _c(tensions, dt)
+    B = y.shape[0]
+    res = torch.empty((B, 6), dtype=dt, device=y.device)
+    keep, mref = _mlp_ref(mlp, dt)
+    with torch.cuda.device(y.device):
+        rc = _kc.lib().kc_march(_dtype_code(y), C.byref(P), mref, method, B, _ptr(G), _ptr(y), _ptr(z), _ptr(yh),
+                                _ptr(zh), _ptr(tensions), _ptr(res), _stream(y.device))
+    _kc.check(rc, "kc_march")
+    return res
+
+
+def segment_fwd(P, mlp, Gs, key_idx, yh, zh, tensions):
+    """kc_segment_fwd: Gs[S,25,N] -> [S,25,K] (key_idx given) or [S,25,N] (key_idx None)."""
+    _require_cuda(Gs, yh, zh, tensions)
+    dt = Gs.dtype
+    Gs, yh, zh, tensions = _c(Gs), _c(yh, dt), _c(zh, dt), _c(tensions, dt)
+    S, _, N = Gs.shape
+    if key_idx is None:
+        K, keys, cols = 0, None, N
+    else:
+        ki = np.ascontiguousarray(np.asarray(key_idx).reshape(-1), dtype=np.int32)
+        K, cols = int(ki.size), int(ki.size)
+        keys = ki.ctypes.data_as(C.POINTER(C.c_int32))
+    out = torch.empty((S, 25, cols), dtype=dt, device=Gs.device)
+    keep, mref = _mlp_ref(mlp, dt)
+    with torch.cuda.device(Gs.device):
+        rc = _kc.lib().kc_segment_fwd(_dtype_code(Gs), C.byref(P), mref, S, K, keys, _ptr(Gs), _ptr(yh), _ptr(zh),
+                                      _ptr(tensions), _ptr(out), _stream(Gs.device))
+    _kc.check(rc, "kc_segment_fwd")
+    return out
+
+
+class RolloutPlan:
+    """Pre-allocated outputs + workspace for repeated rollouts of one shape (what bench.py times)."""
+
+    def __init__(self, P, mlp, B, T, dtype, device, rows=25, want_G=False, want_iters=True):
+        self.P, self.B, self.T, self.rows, self.dtype, self.device = P, B, T, rows, dtype, device
+        self.mlp, self.mref = _mlp_ref(mlp, dtype)
+        self.code = _DT[dtype]
+        with torch.cuda.device(device):
+            nbytes = _kc.lib().kc_rollout_workspace_bytes(self.code, C.byref(P), self.mref, B, T)
+        if nbytes < 0:
+            raise ValueError("kc_rollout_workspace_bytes: bad arguments")
+        self.nbytes = int(nbytes)
+        self.ws = torch.empty(max(self.nbytes, 1), dtype=torch.uint8, device=device)
+        self.traj = torch.empty((B, T, rows, int(P.N)), dtype=dtype, device=device)
+        self.G = torch.empty((B, T, 6), dtype=dtype, device=device) if want_G else None
+        self.iters = torch.empty((B, T), dtype=torch.int32, device=device) if want_iters else None
+
+    def run(self, tensions, y0=None, z0=None, tol=0.0, max_iter=0):
+        _require_cuda(tensions, y0, z0)
+        tensions = _c(tensions, self.dtype)
+        if tuple(tensions.shape) != (self.B, self.T, 4):
+            raise ValueError(f"tensions must be [{self.B},{self.T},4], got {tuple(tensions.shape)}")
+        if y0 is not None:
+            y0, z0 = _c(y0, self.dtype), _c(z0, self.dtype)
+        with torch.cuda.device(self.device):
+            rc = _kc.lib().kc_rollout_fwd(self.code, C.byref(self.P), self.mref, self.B, self.T, _ptr(tensions),
+                                          _ptr(y0), _ptr(z0), float(tol), int(max_iter), self.rows, _ptr(self.traj),
+                                          _ptr(self.G), _ptr(self.iters), _ptr(self.ws), self.nbytes,
+                                          _stream(self.device))
+        _kc.check(rc, "kc_rollout_fwd")
+        return self.traj
+
+
+def rollout(P, mlp, tensions, y0=None, z0=None, tol=0.0, max_iter=0, rows=25, want_G=False):
+    """kc_rollout_fwd: tensions[B,T,4] -> traj[B,T,rows,N] (+ G[B,T,6]) and iters[B,T]."""
+    _require_cuda(tensions)
+    B, T, _ = tensions.shape
+    plan = RolloutPlan(P, mlp, B, T, tensions.dtype, tensions.device, rows, want_G)
+    plan.run(tensions, y0, z0, tol, max_iter)
+    return plan.traj, plan.G, plan.iters
+
+
+def train_step(P, mlp, traj, controls, key_idx, want_pred=False):
+    """kc_train_step: traj[B,T,25,N], controls[B,T,4] -> (loss float64[1] tensor, (gW1,gb1,gW2,gb2), pred|None)."""
+    _require_cuda(traj, controls)
+    dt = traj.dtype
+    dev = traj.device
+    traj, controls = _c(traj), _c(controls, dt)
+    B, T, _, N = traj.shape
+    ki = np.ascontiguousarray(np.asarray(key_idx).reshape(-1), dtype=np.int32)
+    K = int(ki.size)
+    keep, mref = _mlp_ref(mlp, dt)
+    grads = [torch.empty_like(t) for t in (keep.W1, keep.b1, keep.W2, keep.b2)]
+    loss = torch.empty(1, dtype=torch.float64, device=dev)
+    pred = torch.empty((B, T - 1, 25, K), dtype=dt, device=dev) if want_pred else None
+    with torch.cuda.device(dev):
+        nbytes = int(_kc.lib().kc_train_step_workspace_bytes(_dtype_code(traj), mref, B, T, K))
+        ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=dev)
+        rc = _kc.lib().kc_train_step(_dtype_code(traj), C.byref(P), mref, B, T, K,
+                                     ki.ctypes.data_as(C.POINTER(C.c_int32)), _ptr(traj), _ptr(controls),
+                                     _ptr(loss), *[_ptr(g) for g in grads], _ptr(pred), _ptr(ws), nbytes, _stream(dev))
+    _kc.check(rc, "kc_train_step")
+    return loss, tuple(grads), pred
+
+
+def adam_clamp(param, grad, exp_avg, exp_avg_sq, step, lr=1e-2, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0,
+               clamp=True):
+    """kc_adam_clamp, in place on param / exp_avg / exp_avg_sq (flat or any contiguous shape)."""
+    _require_cuda(param, grad, exp_avg, exp_avg_sq)
+    for t in (param, exp_avg, exp_avg_sq):
+        if not t.is_contiguous():
+            raise ValueError("adam_clamp updates in place: tensors must be contiguous")
+    grad = _c(grad, param.dtype)
+    with torch.cuda.device(param.device):
+        rc = _kc.lib().kc_adam_clamp(_dtype_code(param), param.numel(), _ptr(param), _ptr(grad), _ptr(exp_avg),
+                                     _ptr(exp_avg_sq), int(step), float(lr), float(betas[0]), float(betas[1]),
+                                     float(eps), float(weight_decay), 1 if clamp else 0, _stream(param.device))
+    _kc.check(rc, "kc_adam_clamp")
+
+
+def fma_peak(dtype, iters, device):
+    """Measured FP32/FP64 FMA-pipe throughput in FLOP/s (CUDA-event timed), used as the rollout's roofline peak."""
+    code = _DT[dtype]
+    scratch = torch.empty(148 * 8 * 256 * 2, dtype=dtype, device=device)
+    flops = C.c_double(0.0)
+    with torch.cuda.device(device):
+        st = _stream(device)
+        for _ in range(2):
+            _kc.check(_kc.lib().kc_fma_peak(code, int(iters), C.byref(flops), _ptr(scratch), st), "kc_fma_peak")
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _kc.check(_kc.lib().kc_fma_peak(code, int(iters), C.byref(flops), _ptr(scratch), st), "kc_fma_peak")
+        e1.record()
+        e1.synchronize()
+    return flops.value / (e0.elapsed_time(e1) * 1e-3)

@@ -1,0 +1,227 @@
+// kc_rollout.cu — batched time rollout of the Cosserat rod / KNODE model (knode.simulate, knode.py:55-102).
+//
+// Mapping: ONE ROD PER THREAD.  The 19 state values of the node being marched, the 6 base reactions, the 6x6 inverse
+// shooting Jacobian and every temporary of the node ODE live in registers; the BDF2 history of the step being solved
+// (12 values per node: qh, wh, vh, uh — the only history rows the physics reads) lives in shared memory laid out
+// [slot][lane] so every access is conflict-free; the trajectory goes to HBM in a rod-fastest "device layout"
+// [T][25*N][Bpad] so that each of a warp's stores is one full 128-byte line, and is read back (L2 hits) to form the
+// next step's history.  A second kernel transposes the device layout into the reference's [B][T][rows][N] through a
+// padded shared-memory tile (coalesced on both sides) and synthesises rows 25:50 (yh, zh) when asked.
+//
+// Roofline: the rollout is FP32/FP64-pipe and latency bound, not HBM bound: per rod-node-step it moves
+// 100 B (fp32) to HBM against several kFLOP of dependent arithmetic.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include "kc_rollout_core.cuh"
+
+template <typename T, bool DIAG, int IN, int NH>
+__global__ void kc_rollout_kernel(const __grid_constant__ RodC<T> P, const MlpC<T> M, int64_t B, int T_,
+                                  const T* __restrict__ tensions, const T* __restrict__ y0,
+                                  const T* __restrict__ z0, T* trajD, size_t Bpad, T* state, int t_begin, int t_end,
+                                  T tol, int max_iter, T fd_eps, T* Gout, int32_t* iters) {
+    extern __shared__ __align__(16) unsigned char kc_smem[];
+    const int N = P.N;
+    const int hs = blockDim.x;
+    // shared memory: [NH*(N-1)][blockDim] history, then [KC_SHOOT_SLOTS][blockDim] solver state
+    T* Hs = reinterpret_cast<T*>(kc_smem) + threadIdx.x;
+    const ShootMem<T> st{reinterpret_cast<T*>(kc_smem) + (size_t)NH * (N - 1) * hs + threadIdx.x, hs};
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    T* trajD_b = trajD + b;
+    T* sb = state + b;  // state workspace is [KC_SHOOT_SLOTS][Bpad]
+    if (t_begin == 0) {
+        st.reset();
+        rollout_init<T>(P, y0 ? y0 + (size_t)b * 19 * N : nullptr, z0 ? z0 + (size_t)b * 6 * N : nullptr, trajD_b, Bpad);
+        if (Gout) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) Gout[(size_t)b * T_ * 6 + i] = T(0);
+        }
+        if (iters) iters[(size_t)b * T_] = 0;
+    } else {
+        for (int i = 0; i < KC_SHOOT_SLOTS; ++i) st.p[(size_t)i * hs] = sb[(size_t)i * Bpad];
+    }
+    rollout_rod<T, DIAG, IN, NH>(P, M, st, tensions + (size_t)b * T_ * 4, trajD_b, Bpad, Hs, hs, t_begin, t_end, tol,
+                                 max_iter, fd_eps, Gout ? Gout + (size_t)b * T_ * 6 : nullptr,
+                                 iters ? iters + (size_t)b * T_ : nullptr);
+    for (int i = 0; i < KC_SHOOT_SLOTS; ++i) sb[(size_t)i * Bpad] = st.p[(size_t)i * hs];
+}
+
+// trajD[T][K][Bpad] -> traj[B][T][rows][N] (K = 25*N).  One CTA = one time index x 32 rods.
+// rows == 50 adds yh,zh = c1*state[t-1] + c2*state[t-2] (state[-1] := state[0]); index 0 repeats [y;z] (knode.py:68).
+template <typename T>
+__global__ void kc_traj_transpose_kernel(const T* __restrict__ trajD, T* __restrict__ traj, int64_t B, int T_, int K,
+                                         size_t Bpad, int rows, int N, T c1, T c2, int t_begin, int t_end) {
+    extern __shared__ __align__(16) unsigned char kc_smem[];
+    T* tile = reinterpret_cast<T*>(kc_smem);  // [K][33]
+    const int t = t_begin + blockIdx.y;
+    if (t >= t_end) return;
+    const int64_t b0 = (int64_t)blockIdx.x * 32;
+    const int lane = threadIdx.x, wy = threadIdx.y, nwy = blockDim.y;
+    const int passes = rows == 50 ? 2 : 1;
+    for (int pass = 0; pass < passes; ++pass) {
+        if (b0 + lane < B) {
+            for (int k = wy; k < K; k += nwy) {
+                T v;
+                if (pass == 0) {
+                    v = trajD[((size_t)t * K + k) * Bpad + b0 + lane];
+                } else if (t == 0) {
+                    v = trajD[((size_t)k) * Bpad + b0 + lane];
+                } else {
+                    const int tm1 = t - 1, tm2 = t >= 2 ? t - 2 : 0;
+                    v = c1 * trajD[((size_t)tm1 * K + k) * Bpad + b0 + lane] + c2 * trajD[((size_t)tm2 * K + k) * Bpad + b0 + lane];
+                }
+                tile[k * 33 + lane] = v;
+            }
+        }
+        __syncthreads();
+        for (int r = wy; r < 32; r += nwy) {
+            if (b0 + r < B) {
+                T* dst = traj + (((size_t)(b0 + r) * T_ + t) * rows + (size_t)pass * 25) * N;
+                for (int k = lane; k < K; k += 32) dst[k] = tile[k * 33 + r];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// W1[H][in], b1[H], W2[25][H] -> packed rows (see MlpC).
+template <typename T>
+__global__ void kc_pack_mlp_kernel(const T* __restrict__ W1, const T* __restrict__ b1, const T* __restrict__ W2, T* Wp,
+                                   int in_dim, int inP, int hidden, int stride) {
+    const int i = blockIdx.x;
+    for (int k = threadIdx.x; k < stride; k += blockDim.x) {
+        T v = T(0);
+        if (k < in_dim) v = W1[(size_t)i * in_dim + k];
+        else if (k == inP) v = b1[i];
+        else if (k >= inP + 4 && k < inP + 4 + 25) v = W2[(size_t)(k - inP - 4) * hidden + i];
+        Wp[(size_t)i * stride + k] = v;
+    }
+}
+
+template <typename T>
+int kc_pack_mlp(const kc_mlp* mlp, T* Wp, MlpC<T>& M, cudaStream_t st) {
+    M.in_dim = mlp->in_dim;
+    M.inP = (mlp->in_dim + 3) & ~3;
+    M.hidden = mlp->hidden;
+    M.stride = M.inP + 32;
+    M.Wp = Wp;
+    M.b2 = (const T*)mlp->b2;
+    kc_pack_mlp_kernel<T><<<mlp->hidden, 64, 0, st>>>((const T*)mlp->W1, (const T*)mlp->b1, (const T*)mlp->W2, Wp,
+                                                       M.in_dim, M.inP, M.hidden, M.stride);
+    KC_CHECK_LAUNCH("kc_pack_mlp");
+    return KC_OK;
+}
+template int kc_pack_mlp<float>(const kc_mlp*, float*, MlpC<float>&, cudaStream_t);
+template int kc_pack_mlp<double>(const kc_mlp*, double*, MlpC<double>&, cudaStream_t);
+
+int kc_check_mlp(const kc_mlp* mlp) {
+    if (!mlp) return KC_OK;
+    KC_CHECK_ARG(mlp->in_dim == 28 || mlp->in_dim == 53, "kc_mlp.in_dim must be 28 or 53 (got %d)", mlp->in_dim);
+    KC_CHECK_ARG(mlp->out_dim == 25, "kc_mlp.out_dim must be 25 (got %d)", mlp->out_dim);
+    KC_CHECK_ARG(mlp->hidden >= 1, "kc_mlp.hidden must be >= 1");
+    KC_CHECK_ARG(mlp->W1 && mlp->b1 && mlp->W2 && mlp->b2, "kc_mlp has a NULL weight pointer");
+    return KC_OK;
+}
+
+static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+struct RolloutWs {
+    size_t trajD, wp, state, total;
+    size_t Bpad;
+};
+static RolloutWs rollout_ws(int dtype, int N, const kc_mlp* mlp, int64_t B, int64_t T_) {
+    const size_t sz = dtype == KC_F32 ? 4 : 8;
+    RolloutWs w;
+    w.Bpad = (size_t)((B + 31) / 32) * 32;
+    w.trajD = 0;
+    size_t off = align256((size_t)T_ * 25 * N * w.Bpad * sz);
+    w.wp = off;
+    if (mlp) off += align256((size_t)mlp->hidden * (((mlp->in_dim + 3) & ~3) + 32) * sz);
+    w.state = off;
+    off += align256((size_t)KC_SHOOT_SLOTS * w.Bpad * sz);
+    w.total = off;
+    return w;
+}
+
+extern "C" int64_t kc_rollout_workspace_bytes(int dtype, const kc_rod_params* P, const kc_mlp* mlp, int64_t B, int64_t T_) {
+    if (!P || P->N < 2 || B < 0 || T_ < 1 || (dtype != KC_F32 && dtype != KC_F64)) return KC_EINVAL;
+    return (int64_t)rollout_ws(dtype, P->N, mlp, B, T_).total;
+}
+
+template <typename T>
+static int rollout_typed(const kc_rod_params* Pp, const kc_mlp* mlp, int64_t B, int64_t T_, const void* tensions,
+                         const void* y0, const void* z0, double tol, int max_iter, int rows, void* traj, void* G_out,
+                         int32_t* iters, void* workspace, cudaStream_t st) {
+    const RodC<T> P = make_rodc<T>(*Pp);
+    const int N = P.N;
+    const RolloutWs w = rollout_ws(sizeof(T) == 4 ? KC_F32 : KC_F64, N, mlp, B, T_);
+    unsigned char* ws = (unsigned char*)workspace;
+    T* trajD = (T*)(ws + w.trajD);
+    T* state = (T*)(ws + w.state);
+    MlpC<T> M{};
+    int in_dim = 0;
+    if (mlp) {
+        int rc = kc_pack_mlp<T>(mlp, (T*)(ws + w.wp), M, st);
+        if (rc) return rc;
+        in_dim = mlp->in_dim;
+    }
+    const T tl = tol > 0 ? (T)tol : (sizeof(T) == 4 ? T(2e-6) : T(1e-11));
+    const T fd_eps = sizeof(T) == 4 ? T(1e-2) : T(1e-6);
+    if (max_iter <= 0) max_iter = 60;
+    const int NH = in_dim == 53 ? 25 : 12;
+    const int threads = 32;
+    const size_t smem = ((size_t)NH * (N - 1) + KC_SHOOT_SLOTS) * threads * sizeof(T);
+    KC_CHECK_ARG(smem <= 227 * 1024, "N=%d too large for the shared-memory history (%zu B)", N, smem);
+    const unsigned grid = (unsigned)((B + threads - 1) / threads);
+    if (B > 0) {
+#define KC_LAUNCH_ROLL(D, I, H)                                                                                        \
+    do {                                                                                                               \
+        auto kern = kc_rollout_kernel<T, D, I, H>;                                                                     \
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
+        kern<<<grid, threads, smem, st>>>(P, M, B, (int)T_, (const T*)tensions, (const T*)y0, (const T*)z0, trajD,     \
+                                          w.Bpad, state, 0, (int)T_ - 1, tl, max_iter, fd_eps, (T*)G_out, iters);      \
+    } while (0)
+        if (P.diag) {
+            if (in_dim == 0) KC_LAUNCH_ROLL(true, 0, 12);
+            else if (in_dim == 28) KC_LAUNCH_ROLL(true, 28, 12);
+            else KC_LAUNCH_ROLL(true, 53, 25);
+        } else {
+            if (in_dim == 0) KC_LAUNCH_ROLL(false, 0, 12);
+            else if (in_dim == 28) KC_LAUNCH_ROLL(false, 28, 12);
+            else KC_LAUNCH_ROLL(false, 53, 25);
+        }
+#undef KC_LAUNCH_ROLL
+        KC_CHECK_LAUNCH("kc_rollout_kernel");
+        const int K = 25 * N;
+        const size_t tsmem = (size_t)K * 33 * sizeof(T);
+        auto tk = kc_traj_transpose_kernel<T>;
+        if (tsmem > 48 * 1024) cudaFuncSetAttribute(tk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem);
+        dim3 tgrid((unsigned)((B + 31) / 32), (unsigned)T_);
+        tk<<<tgrid, dim3(32, 8), tsmem, st>>>(trajD, (T*)traj, B, (int)T_, K, w.Bpad, rows, N, P.c1, P.c2, 0, (int)T_);
+        KC_CHECK_LAUNCH("kc_traj_transpose_kernel");
+    }
+    return KC_OK;
+}
+
+extern "C" int kc_rollout_fwd(int dtype, const kc_rod_params* P, const kc_mlp* mlp, int64_t B, int64_t T_,
+                              const void* tensions, const void* y0, const void* z0, double tol, int32_t max_iter,
+                              int32_t rows, void* traj, void* G_out, int32_t* iters, void* workspace,
+                              int64_t workspace_bytes, void* stream) {
+    KC_CHECK_ARG(dtype == KC_F32 || dtype == KC_F64, "dtype must be KC_F32 or KC_F64");
+    KC_CHECK_ARG(P && P->N >= 2, "rod params missing or N < 2");
+    KC_CHECK_ARG(B >= 0 && T_ >= 1, "B must be >= 0 and T >= 1");
+    KC_CHECK_ARG(rows == 25 || rows == 50, "rows must be 25 or 50");
+    KC_CHECK_ARG(B == 0 || (tensions && traj && workspace), "NULL tensions/traj/workspace");
+    KC_CHECK_ARG((y0 == nullptr) == (z0 == nullptr), "y0 and z0 must be given together");
+    int rc = kc_check_mlp(mlp);
+    if (rc) return rc;
+    const int64_t need = kc_rollout_workspace_bytes(dtype, P, mlp, B, T_);
+    if (workspace_bytes < need) {
+        kc_set_error("workspace too small: %lld < %lld", (long long)workspace_bytes, (long long)need);
+        return KC_ENOSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == KC_F32)
+        return rollout_typed<float>(P, mlp, B, T_, tensions, y0, z0, tol, max_iter, rows, traj, G_out, iters, workspace, st);
+    return rollout_typed<double>(P, mlp, B, T_, tensions, y0, z0, tol, max_iter, rows, traj, G_out, iters, workspace, st);
+}

@@ -1,0 +1,65 @@
+// kc_emul.cpp — TEST-ONLY host harness: compiles the per-rod solver headers of knode-cosserat_b200/csrc with g++ and
+// runs them one rod at a time on the CPU, so the quasi-Newton / history / layout logic of the rollout kernel can be
+// checked against the oracle in the GPU-less build container.  Not linked into the product library, not reachable
+// from the Python drop-ins.
+#include <vector>
+#include <cstring>
+#include "../../knode-cosserat_b200/csrc/kc_rollout_core.cuh"
+
+void kc_set_error(const char*, ...) {}
+
+template <typename T>
+static void pack_mlp(const T* W1, const T* b1, const T* W2, int in_dim, int hidden, std::vector<T>& Wp, int& inP, int& stride) {
+    inP = (in_dim + 3) & ~3;
+    stride = inP + 32;
+    Wp.assign((size_t)hidden * stride, T(0));
+    for (int i = 0; i < hidden; ++i) {
+        for (int k = 0; k < in_dim; ++k) Wp[(size_t)i * stride + k] = W1[(size_t)i * in_dim + k];
+        Wp[(size_t)i * stride + inP] = b1[i];
+        for (int c = 0; c < 25; ++c) Wp[(size_t)i * stride + inP + 4 + c] = W2[(size_t)c * hidden + i];
+    }
+}
+
+template <typename T, bool DIAG, int IN, int NH>
+static void run(const RodC<T>& P, const MlpC<T>& M, int64_t B, int64_t T_, const T* ten, T* traj, int32_t* iters,
+                T* Gout, T tol, int max_iter, T fd_eps) {
+    const int N = P.N;
+    std::vector<T> trajD((size_t)T_ * 25 * N), Hs((size_t)NH * (N - 1));
+    for (int64_t b = 0; b < B; ++b) {
+        T stmem[KC_SHOOT_SLOTS];
+        ShootMem<T> st{stmem, 1};
+        st.reset();
+        rollout_init<T>(P, nullptr, nullptr, trajD.data(), 1);
+        if (iters) iters[b * T_] = 0;
+        rollout_rod<T, DIAG, IN, NH>(P, M, st, ten + b * T_ * 4, trajD.data(), 1, Hs.data(), 1, 0, (int)T_ - 1, tol,
+                                     max_iter, fd_eps, Gout ? Gout + b * T_ * 6 : nullptr, iters ? iters + b * T_ : nullptr);
+        std::memcpy(traj + (size_t)b * T_ * 25 * N, trajD.data(), sizeof(T) * trajD.size());
+    }
+}
+
+template <typename T>
+static int emul(const kc_rod_params* p, int in_dim, int hidden, const void* W1, const void* b1, const void* W2,
+                const void* b2, int64_t B, int64_t T_, const void* ten, void* traj, int32_t* iters, void* Gout,
+                double tol, int max_iter) {
+    RodC<T> P = make_rodc<T>(*p);
+    MlpC<T> M{};
+    std::vector<T> Wp;
+    if (in_dim) {
+        int inP, stride;
+        pack_mlp<T>((const T*)W1, (const T*)b1, (const T*)W2, in_dim, hidden, Wp, inP, stride);
+        M.Wp = Wp.data(); M.b2 = (const T*)b2; M.in_dim = in_dim; M.inP = inP; M.hidden = hidden; M.stride = stride;
+    }
+    const T fd_eps = sizeof(T) == 4 ? T(1e-2) : T(1e-6);
+    const T tl = tol > 0 ? T(tol) : (sizeof(T) == 4 ? T(2e-6) : T(1e-12));
+#define GO(D, I, H) run<T, D, I, H>(P, M, B, T_, (const T*)ten, (T*)traj, iters, (T*)Gout, tl, max_iter, fd_eps)
+    if (P.diag) { if (in_dim == 0) GO(true, 0, 12); else if (in_dim == 28) GO(true, 28, 12); else GO(true, 53, 25); }
+    else        { if (in_dim == 0) GO(false, 0, 12); else if (in_dim == 28) GO(false, 28, 12); else GO(false, 53, 25); }
+    return 0;
+}
+
+extern "C" int kc_emul_rollout(int dtype, const kc_rod_params* p, int in_dim, int hidden, const void* W1, const void* b1,
+                               const void* W2, const void* b2, int64_t B, int64_t T_, const void* ten, void* traj,
+                               int32_t* iters, void* Gout, double tol, int max_iter) {
+    if (dtype == KC_F32) return emul<float>(p, in_dim, hidden, W1, b1, W2, b2, B, T_, ten, traj, iters, Gout, tol, max_iter);
+    return emul<double>(p, in_dim, hidden, W1, b1, W2, b2, B, T_, ten, traj, iters, Gout, tol, max_iter);
+}

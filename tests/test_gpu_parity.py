@@ -1,0 +1,207 @@
+"""GPU parity: the CUDA path, called through the C ABI (knode-cosserat_b200/_ops.py -> libknode_cosserat_b200.so),
+against the golden vectors of the reference and against the numpy oracle on seeded inputs.
+Tolerances: fp64 1e-9 relative to each field's scale, fp32 1e-4 (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import rod_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+FIELDS = [(0, 3), (3, 7), (7, 10), (10, 13), (13, 16), (16, 19), (19, 22), (22, 25)]
+TOL = {torch.float64: 1e-9, torch.float32: 1e-4}
+
+
+def field_err(a, b):
+    """max over fields of |a-b| / scale_field for [...,25,N] arrays (several fields pass through zero)."""
+    worst = 0.0
+    for lo, hi in FIELDS:
+        if lo >= a.shape[-2]:
+            break
+        scale = max(float(np.abs(b[..., lo:hi, :]).max()), 1e-30)
+        worst = max(worst, float(np.abs(a[..., lo:hi, :] - b[..., lo:hi, :]).max()) / scale)
+    return worst
+
+
+def col_err(a, b, floor=1e-3):
+    scale = np.abs(b).reshape(-1, b.shape[-1]).max(0) + floor
+    return float(np.max(np.abs(a - b) / scale))
+
+
+@pytest.fixture(scope="module")
+def ops():
+    import _kc
+    import _ops
+    assert torch.cuda.is_available()
+    _kc.lib()
+    return _ops
+
+
+def params(P):
+    import _kc
+    return _kc.rod_params(P)
+
+
+def P_setup(mod=None):
+    return O.setup_params(O.RodParams(), mod)
+
+
+def dev(a, dt):
+    return torch.tensor(np.asarray(a), dtype=dt, device="cuda")
+
+
+def mlp_of(ops, d, tag, dt):
+    return ops.Mlp(*[dev(d[f"{tag}_{k}"], dt) for k in ("W1", "b1", "W2", "b2")])
+
+
+@pytest.mark.parametrize("dt", [torch.float64, torch.float32])
+@pytest.mark.parametrize("mod", [None, "noair", "nsw", "short", "damping", "dampstiff", "lengthstiff", "youngs"])
+def test_ode_fwd_physics(ops, golden, dt, mod):
+    d = golden["ode"]
+    tag = "none" if mod is None else mod
+    ys, z = ops.ode_fwd(params(P_setup(mod)), None, dev(d["y"], dt), dev(d["yh"], dt), dev(d["zh"], dt), dev(d["tf"], dt))
+    assert col_err(ys.cpu().numpy().astype(np.float64), d[f"np_{tag}_ys"]) < TOL[dt]
+    assert col_err(z.cpu().numpy().astype(np.float64), d[f"np_{tag}_z"]) < TOL[dt]
+
+
+@pytest.mark.parametrize("dt", [torch.float64, torch.float32])
+@pytest.mark.parametrize("tag", ["h512", "h64hist"])
+def test_ode_fwd_knode(ops, golden, dt, tag):
+    d = golden["ode"]
+    ys, z = ops.ode_fwd(params(P_setup()), mlp_of(ops, d, tag, dt), dev(d["y"], dt), dev(d["yh"], dt), dev(d["zh"], dt),
+                        dev(d["tf"], dt))
+    assert col_err(ys.cpu().numpy().astype(np.float64), d[f"{tag}_par64_ys"]) < TOL[dt]
+    assert col_err(z.cpu().numpy().astype(np.float64), d[f"{tag}_par64_z"]) < TOL[dt]
+
+
+def test_ode_fwd_dense_matrices_and_empty(ops):
+    """Users may set dense Kse/Kbt/Bbt/Bse/J (the diagonal fast path must not be assumed) — and Q = 0 is legal."""
+    rng = np.random.default_rng(4)
+    P = P_setup()
+    P.Bse = 1e-3 * rng.standard_normal((3, 3))
+    P.Bbt = P.Bbt + 1e-3 * rng.standard_normal((3, 3))
+    P.compute_intermediate_terms()
+    P.rhoJ = P.rhoJ + 1e-7 * rng.standard_normal((3, 3))
+    y = rng.standard_normal((77, 19))
+    y[:, 3] += 3.0
+    yh, zh, tf = rng.standard_normal((77, 19)), rng.standard_normal((77, 6)), rng.standard_normal((77, 3))
+    ys_o, z_o = O.ode(P, y, yh, zh, tf)
+    ys, z = ops.ode_fwd(params(P), None, *[dev(a, torch.float64) for a in (y, yh, zh, tf)])
+    assert col_err(ys.cpu().numpy(), ys_o) < 1e-9 and col_err(z.cpu().numpy(), z_o) < 1e-9
+    e = torch.empty((0, 19), dtype=torch.float64, device="cuda")
+    ys, z = ops.ode_fwd(params(P), None, e, e, e[:, :6], e[:, :3])
+    assert ys.shape == (0, 19) and z.shape == (0, 6)
+
+
+@pytest.mark.parametrize("dt", [torch.float64, torch.float32])
+def test_march_euler_and_rk4(ops, golden, dt):
+    import _kc
+    d = golden["ode"]
+    P = params(P_setup())
+    for method, pre in ((_kc.KC_MARCH_EULER, "march"), (_kc.KC_MARCH_RK4, "rk4")):
+        y, z = dev(d["march_y0"][None], dt), dev(d["march_z0"][None], dt)
+        res = ops.march(P, None, dev(d["march_G"][None], dt), y, z, dev(d["march_yh"][None], dt),
+                        dev(d["march_zh"][None], dt), dev(d["march_tensions"][None], dt), method)
+        full = np.concatenate([y.cpu().numpy()[0], z.cpu().numpy()[0]]).astype(np.float64)
+        ref = np.concatenate([d[pre + "_y"], d[pre + "_z"]])
+        assert field_err(full, ref) < TOL[dt]
+        assert np.max(np.abs(res.cpu().numpy()[0] - d[pre + "_res"])) < TOL[dt] * 10
+
+
+@pytest.mark.parametrize("dt", [torch.float64, torch.float32])
+def test_segment_fwd(ops, golden, dt):
+    d = golden["train"]
+    P = P_setup()
+    traj = d["traj"].astype(np.float32).astype(np.float64)
+    ctl = d["controls"].astype(np.float32).astype(np.float64)
+    mlp_np = {k: d[f"none_init_{k}"].astype(np.float64) for k in ("W1", "b1", "W2", "b2")}
+    mlp = ops.Mlp(*[dev(mlp_np[k], dt) for k in ("W1", "b1", "W2", "b2")])
+    key = np.array([3, 5, 7, 9])
+    ys, zs = traj[0, :29, :19], traj[0, :29, 19:]
+    yh = P.c1 * ys + P.c2 * np.concatenate([ys[:1], ys[:-1]])
+    zh = P.c1 * zs + P.c2 * np.concatenate([zs[:1], zs[:-1]])
+    want = O.parallel_next_segment_euler(P, traj[0, 1:30], key, yh, zh, ctl[0, :29], mlp_np)
+    got = ops.segment_fwd(params(P), mlp, dev(traj[0, 1:30], dt), key, dev(yh, dt), dev(zh, dt), dev(ctl[0, :29], dt))
+    assert field_err(got.cpu().numpy().astype(np.float64), want) < TOL[dt]
+    if dt == torch.float32:  # the reference's own fp32 output
+        assert field_err(got.cpu().numpy().astype(np.float64), d["none_fast_grow_trajs0"].astype(np.float64)) < 1e-4
+    want = O.next_segment_euler(P, traj[0, 1:30], yh, zh, ctl[0, :29], mlp_np)
+    got = ops.segment_fwd(params(P), mlp, dev(traj[0, 1:30], dt), None, dev(yh, dt), dev(zh, dt), dev(ctl[0, :29], dt))
+    assert field_err(got.cpu().numpy().astype(np.float64), want) < TOL[dt]
+
+
+ROLLS = [("default_sine", "default", None), ("default_sine200", "default", None), ("setup_sine", "setup", None),
+         ("setup_step", "setup", None), ("setup_random", "setup", None)] + \
+        [(f"mod_{m}", "setup", m) for m in ["noair", "nsw", "short", "damping", "dampstiff", "lengthstiff", "youngs"]]
+
+
+@pytest.mark.parametrize("dt", [torch.float64, torch.float32])
+@pytest.mark.parametrize("name,kind,mod", ROLLS)
+def test_rollout_vs_reference_simulate(ops, golden, dt, name, kind, mod):
+    d = golden["rollouts"]
+    P = O.RodParams() if kind == "default" else P_setup(mod)
+    ctl = d[name + "_ctl"]
+    traj, G, iters = ops.rollout(params(P), None, dev(ctl[None], dt), rows=50, want_G=True)
+    got = traj.cpu().numpy()[0].astype(np.float64)
+    ref = d[name + "_traj"]
+    assert int(iters.min()) >= 0, "a rod failed to converge"
+    assert field_err(got[:, :25], ref[:, :25]) < TOL[dt]
+    # rows 25:50 are the BDF2 histories (state differences scaled by 1/dt): same bar relative to their own scale
+    assert field_err(got[:, 25:], ref[:, 25:]) < TOL[dt] * 10
+    np.testing.assert_allclose(G.cpu().numpy()[0, 1:].astype(np.float64), ref[1:, 7:13, 0], rtol=0,
+                               atol=TOL[dt] * max(1.0, np.abs(ref[:, 7:13, 0]).max()))
+
+
+@pytest.mark.parametrize("dt", [torch.float64, torch.float32])
+@pytest.mark.parametrize("tag", ["h64", "h512", "h32hist"])
+def test_knode_rollout_vs_reference(ops, golden, dt, tag):
+    d = golden["knode_rollouts"]
+    P = P_setup("youngs")
+    traj, _, iters = ops.rollout(params(P), mlp_of(ops, d, tag, dt), dev(d[tag + "_ctl"][None], dt))
+    assert int(iters.min()) >= 0
+    assert field_err(traj.cpu().numpy()[0].astype(np.float64), d[tag + "_traj"][:, :25]) < TOL[dt]
+
+
+@pytest.mark.parametrize("dt", [torch.float64, torch.float32])
+def test_rollout_batch_ragged_and_edge_sizes(ops, dt):
+    """B not a multiple of the warp, mixed tension families, T = 1 and B = 0."""
+    rng = np.random.default_rng(7)
+    P = P_setup()
+    B, T = 37, 14
+    ctl = np.stack([np.array(O.calc_controls("sine", 0.5 + 0.1 * b, P.del_t, T)) if b % 2 == 0
+                    else 5 + 5 * rng.random((T, 4)) for b in range(B)])
+    want = O.rollout_newton(P, ctl, rows=25)
+    traj, _, iters = ops.rollout(params(P), None, dev(ctl, dt))
+    assert int(iters.min()) >= 0
+    assert field_err(traj.cpu().numpy().astype(np.float64), want) < TOL[dt]
+    t1, _, _ = ops.rollout(params(P), None, dev(ctl[:, :1], dt))
+    assert field_err(t1.cpu().numpy().astype(np.float64), want[:, :1]) < 1e-6
+    t0, _, _ = ops.rollout(params(P), None, dev(ctl[:0], dt))
+    assert t0.shape == (0, T, 25, P.N)
+
+
+def test_rollout_full_size_properties(ops):
+    """BASELINE config 2 (4096 rods x 100 steps, fp32): size-independent properties — every solve converged, the tip
+    residual (free-end boundary condition) is ~0 at every step, duplicated inputs give bitwise-identical rods, and a
+    sample of rods matches the fp64 oracle."""
+    rng = np.random.default_rng(0)
+    P = P_setup()
+    B, T = 4096, 100
+    ctl = np.empty((B, T, 4))
+    i = np.arange(1, T + 1)[None, :, None]
+    per = rng.uniform(0.5, 3.0, (B // 2, 1, 1)) / P.del_t
+    ph = rng.uniform(0, 2 * np.pi, (B // 2, 1, 1))
+    ctl[:B // 2] = 6 + np.sin(2 * np.pi * i / per + ph + np.arange(4)[None, None, :] * np.pi / 2)
+    ctl[B // 2:] = 5 + 5 * rng.random((B // 2, T, 4))
+    ctl[1] = ctl[0]
+    ctl[-1] = ctl[-2]
+    traj, _, iters = ops.rollout(params(P), None, dev(ctl, torch.float32))
+    assert int(iters.min()) >= 0
+    tr = traj.cpu().numpy()
+    assert np.isfinite(tr).all()
+    assert np.abs(tr[:, 1:, 7:13, -1]).max() < 5e-5          # n(L) = F_tip = 0, m(L) = M_tip = 0
+    assert np.array_equal(tr[0], tr[1]) and np.array_equal(tr[-1], tr[-2])
+    sel = [0, 5, B // 2 - 1, B // 2, B - 3]
+    want = O.rollout_newton(P, ctl[sel], rows=25)
+    assert field_err(tr[sel].astype(np.float64), want) < 1e-4
