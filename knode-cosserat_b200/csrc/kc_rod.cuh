@@ -259,19 +259,19 @@ template <typename T> KC_HD T norm_inf6(const T v[6]) {
 //   slots 0..5 G (base reactions of the last solved step, warm start, knode.py:67,89), 6..11 the step before (linear
 //   predictor), 12..47 inverse shooting Jacobian (row-major 6x6, Broyden-maintained across steps), 48 have_J flag.
 constexpr int KC_SHOOT_SLOTS = 49;
-template <typename T> struct ShootMem {
-    T* p; int s;
-    KC_HD T& G(int i) const { return p[(size_t)i * s]; }
-    KC_HD T& Gm1(int i) const { return p[(size_t)(6 + i) * s]; }
-    KC_HD T& J(int i, int j) const { return p[(size_t)(12 + i * 6 + j) * s]; }
-    KC_HD T& haveJ() const { return p[(size_t)48 * s]; }
+template <typename T, int LS> struct ShootMem {
+    T* p;
+    KC_HD T& G(int i) const { return p[i * LS]; }
+    KC_HD T& Gm1(int i) const { return p[(6 + i) * LS]; }
+    KC_HD T& J(int i, int j) const { return p[(12 + i * 6 + j) * LS]; }
+    KC_HD T& haveJ() const { return p[48 * LS]; }
     KC_HD void reset() const {
-        for (int i = 0; i < KC_SHOOT_SLOTS; ++i) p[(size_t)i * s] = T(0);
+        for (int i = 0; i < KC_SHOOT_SLOTS; ++i) p[i * LS] = T(0);
     }
 };
 
 // "Good" Broyden update applied to the inverse (Sherman–Morrison): Jinv += (s - Jinv yv)(s^T Jinv) / (s^T Jinv yv).
-template <typename T> KC_HD void broyden_update(const ShootMem<T>& st, const T sv[6], const T yv[6]) {
+template <typename T, int LS> KC_HD void broyden_update(const ShootMem<T, LS>& st, const T sv[6], const T yv[6]) {
     T Jy[6], sJ[6];
 #pragma unroll
     for (int i = 0; i < 6; ++i) { Jy[i] = T(0); sJ[i] = T(0); }
@@ -304,8 +304,8 @@ template <typename T> KC_HD void broyden_update(const ShootMem<T>& st, const T s
 // whenever two consecutive iterations fail to halve the residual.  Written as a small state machine around ONE march
 // call site so lanes in different phases (predictor / FD column / Broyden iterate) still execute the march together.
 // Returns the number of marches (negative: tol not reached within max_iter, or a NaN / singular Jacobian appeared).
-template <typename T, bool DIAG, int IN, int NH, typename Hist, typename Sink>
-KC_HD int shoot_step(const RodC<T>& P, const MlpC<T>& M, const ShootMem<T>& st, const T tf[3], const Hist& H, Sink& S,
+template <typename T, bool DIAG, int IN, int NH, int LS, typename Hist, typename Sink>
+KC_HD int shoot_step(const RodC<T>& P, const MlpC<T>& M, const ShootMem<T, LS>& st, const T tf[3], const Hist& H, Sink& S,
                      T tol, int max_iter, T fd_eps) {
     enum { PRED = 0, FD = 1, BROY = 2 };
     T G[6], F[6], dG[6];

@@ -12,72 +12,87 @@
 // 100 B (fp32) to HBM against several kFLOP of dependent arithmetic.
 #include <cuda_runtime.h>
 #include <cstdio>
+#include <cstdlib>
 #include "kc_rollout_core.cuh"
 
+constexpr int KC_LS = 32;  // lane stride of every per-rod array (one warp-wide tile)
+
+// A rod's base pointer inside the tiled device layout [tile][T][N][25][32].
+template <typename T>
+__device__ __forceinline__ T* rod_base(T* trajD, int64_t b, int T_, int N) {
+    return trajD + (size_t)(b >> 5) * ((size_t)T_ * N * 25 * KC_LS) + (b & 31);
+}
+
+// One warp per CTA; `rpw` (rods per warp, 1..32) lanes are active.  With few rods the launcher spreads them over more
+// warps (the kernel is latency bound: a half-empty warp costs nothing, a longer per-warp critical path does).
 template <typename T, bool DIAG, int IN, int NH>
-__global__ void kc_rollout_kernel(const __grid_constant__ RodC<T> P, const MlpC<T> M, int64_t B, int T_,
-                                  const T* __restrict__ tensions, const T* __restrict__ y0,
-                                  const T* __restrict__ z0, T* trajD, size_t Bpad, T* state, int t_begin, int t_end,
-                                  T tol, int max_iter, T fd_eps, T* Gout, int32_t* iters) {
+__global__ void __launch_bounds__(32)
+kc_rollout_kernel(const __grid_constant__ RodC<T> P, const MlpC<T> M, int64_t B, int T_, int rpw,
+                  const T* __restrict__ tensions, const T* __restrict__ y0, const T* __restrict__ z0, T* trajD,
+                  size_t Bpad, T* state, int t_begin, int t_end, T tol, int max_iter, T fd_eps, T* Gout,
+                  int32_t* iters) {
     extern __shared__ __align__(16) unsigned char kc_smem[];
     const int N = P.N;
-    const int hs = blockDim.x;
-    // shared memory: [NH*(N-1)][blockDim] history, then [KC_SHOOT_SLOTS][blockDim] solver state
+    // shared memory: [N-1][NH][32] history, then [KC_SHOOT_SLOTS][32] solver state
     T* Hs = reinterpret_cast<T*>(kc_smem) + threadIdx.x;
-    const ShootMem<T> st{reinterpret_cast<T*>(kc_smem) + (size_t)NH * (N - 1) * hs + threadIdx.x, hs};
-    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
-    T* trajD_b = trajD + b;
+    const ShootMem<T, KC_LS> st{reinterpret_cast<T*>(kc_smem) + (size_t)NH * (N - 1) * KC_LS + threadIdx.x};
+    const int64_t b = (int64_t)blockIdx.x * rpw + threadIdx.x;
+    if ((int)threadIdx.x >= rpw || b >= B) return;
+    T* traj_b = rod_base(trajD, b, T_, N);
     T* sb = state + b;  // state workspace is [KC_SHOOT_SLOTS][Bpad]
     if (t_begin == 0) {
         st.reset();
-        rollout_init<T>(P, y0 ? y0 + (size_t)b * 19 * N : nullptr, z0 ? z0 + (size_t)b * 6 * N : nullptr, trajD_b, Bpad);
+        rollout_init<T, KC_LS>(P, y0 ? y0 + (size_t)b * 19 * N : nullptr, z0 ? z0 + (size_t)b * 6 * N : nullptr, traj_b);
         if (Gout) {
 #pragma unroll
             for (int i = 0; i < 6; ++i) Gout[(size_t)b * T_ * 6 + i] = T(0);
         }
         if (iters) iters[(size_t)b * T_] = 0;
     } else {
-        for (int i = 0; i < KC_SHOOT_SLOTS; ++i) st.p[(size_t)i * hs] = sb[(size_t)i * Bpad];
+        for (int i = 0; i < KC_SHOOT_SLOTS; ++i) st.p[i * KC_LS] = sb[(size_t)i * Bpad];
     }
-    rollout_rod<T, DIAG, IN, NH>(P, M, st, tensions + (size_t)b * T_ * 4, trajD_b, Bpad, Hs, hs, t_begin, t_end, tol,
-                                 max_iter, fd_eps, Gout ? Gout + (size_t)b * T_ * 6 : nullptr,
-                                 iters ? iters + (size_t)b * T_ : nullptr);
-    for (int i = 0; i < KC_SHOOT_SLOTS; ++i) sb[(size_t)i * Bpad] = st.p[(size_t)i * hs];
+    rollout_rod<T, DIAG, IN, NH, KC_LS>(P, M, st, tensions + (size_t)b * T_ * 4, traj_b, Hs, t_begin, t_end, tol,
+                                        max_iter, fd_eps, Gout ? Gout + (size_t)b * T_ * 6 : nullptr,
+                                        iters ? iters + (size_t)b * T_ : nullptr);
+    for (int i = 0; i < KC_SHOOT_SLOTS; ++i) sb[(size_t)i * Bpad] = st.p[i * KC_LS];
 }
 
-// trajD[T][K][Bpad] -> traj[B][T][rows][N] (K = 25*N).  One CTA = one time index x 32 rods.
+// trajD[tile][T][N][25][32] -> traj[B][T][rows][N].  One CTA = one (32-rod tile, time index): the slab is contiguous,
+// staged through a padded shared tile so both sides are coalesced.
 // rows == 50 adds yh,zh = c1*state[t-1] + c2*state[t-2] (state[-1] := state[0]); index 0 repeats [y;z] (knode.py:68).
 template <typename T>
-__global__ void kc_traj_transpose_kernel(const T* __restrict__ trajD, T* __restrict__ traj, int64_t B, int T_, int K,
-                                         size_t Bpad, int rows, int N, T c1, T c2, int t_begin, int t_end) {
+__global__ void kc_traj_transpose_kernel(const T* __restrict__ trajD, T* __restrict__ traj, int64_t B, int T_, int N,
+                                         int rows, T c1, T c2) {
     extern __shared__ __align__(16) unsigned char kc_smem[];
-    T* tile = reinterpret_cast<T*>(kc_smem);  // [K][33]
-    const int t = t_begin + blockIdx.y;
-    if (t >= t_end) return;
+    T* tile = reinterpret_cast<T*>(kc_smem);  // [N*25][33], k' = j*25 + r
+    const int K = 25 * N;
+    const int t = blockIdx.y;
     const int64_t b0 = (int64_t)blockIdx.x * 32;
     const int lane = threadIdx.x, wy = threadIdx.y, nwy = blockDim.y;
+    const size_t slab = (size_t)K * KC_LS;
+    const T* base = trajD + (size_t)blockIdx.x * T_ * slab;
     const int passes = rows == 50 ? 2 : 1;
     for (int pass = 0; pass < passes; ++pass) {
-        if (b0 + lane < B) {
-            for (int k = wy; k < K; k += nwy) {
-                T v;
-                if (pass == 0) {
-                    v = trajD[((size_t)t * K + k) * Bpad + b0 + lane];
-                } else if (t == 0) {
-                    v = trajD[((size_t)k) * Bpad + b0 + lane];
-                } else {
-                    const int tm1 = t - 1, tm2 = t >= 2 ? t - 2 : 0;
-                    v = c1 * trajD[((size_t)tm1 * K + k) * Bpad + b0 + lane] + c2 * trajD[((size_t)tm2 * K + k) * Bpad + b0 + lane];
-                }
-                tile[k * 33 + lane] = v;
+        for (int k = wy; k < K; k += nwy) {
+            T v;
+            if (pass == 0) {
+                v = base[(size_t)t * slab + (size_t)k * KC_LS + lane];
+            } else if (t == 0) {
+                v = base[(size_t)k * KC_LS + lane];
+            } else {
+                const int tm1 = t - 1, tm2 = t >= 2 ? t - 2 : 0;
+                v = c1 * base[(size_t)tm1 * slab + (size_t)k * KC_LS + lane] + c2 * base[(size_t)tm2 * slab + (size_t)k * KC_LS + lane];
             }
+            tile[k * 33 + lane] = v;
         }
         __syncthreads();
-        for (int r = wy; r < 32; r += nwy) {
-            if (b0 + r < B) {
-                T* dst = traj + (((size_t)(b0 + r) * T_ + t) * rows + (size_t)pass * 25) * N;
-                for (int k = lane; k < K; k += 32) dst[k] = tile[k * 33 + r];
+        for (int rr = wy; rr < 32; rr += nwy) {
+            if (b0 + rr < B) {
+                T* dst = traj + (((size_t)(b0 + rr) * T_ + t) * rows + (size_t)pass * 25) * N;
+                for (int kk = lane; kk < K; kk += 32) {  // kk = r*N + j in the reference layout
+                    const int r = kk / N, j = kk - r * N;
+                    dst[kk] = tile[(j * 25 + r) * 33 + rr];
+                }
             }
         }
         __syncthreads();
@@ -172,14 +187,27 @@ static int rollout_typed(const kc_rod_params* Pp, const kc_mlp* mlp, int64_t B, 
     const int threads = 32;
     const size_t smem = ((size_t)NH * (N - 1) + KC_SHOOT_SLOTS) * threads * sizeof(T);
     KC_CHECK_ARG(smem <= 227 * 1024, "N=%d too large for the shared-memory history (%zu B)", N, smem);
-    const unsigned grid = (unsigned)((B + threads - 1) / threads);
+    // rods per warp: the kernel is latency bound, so with few rods spread them over the chip's 148 x 4 warp schedulers
+    // (one warp each) before filling the lanes of a warp; never exceed one resident wave.
+    int rpw = 32;
+    {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int64_t slots = (int64_t)sms * 4;
+        while (rpw > 8 && (B + rpw / 2 - 1) / (rpw / 2) <= slots) rpw >>= 1;
+        const char* e = getenv("KC_RPW");  // tuning knob for profiling runs
+        if (e && atoi(e) >= 1 && atoi(e) <= 32) rpw = atoi(e);
+    }
+    const unsigned grid = (unsigned)((B + rpw - 1) / rpw);
     if (B > 0) {
 #define KC_LAUNCH_ROLL(D, I, H)                                                                                        \
     do {                                                                                                               \
         auto kern = kc_rollout_kernel<T, D, I, H>;                                                                     \
         if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
-        kern<<<grid, threads, smem, st>>>(P, M, B, (int)T_, (const T*)tensions, (const T*)y0, (const T*)z0, trajD,     \
-                                          w.Bpad, state, 0, (int)T_ - 1, tl, max_iter, fd_eps, (T*)G_out, iters);      \
+        kern<<<grid, threads, smem, st>>>(P, M, B, (int)T_, rpw, (const T*)tensions, (const T*)y0, (const T*)z0,       \
+                                          trajD, w.Bpad, state, 0, (int)T_ - 1, tl, max_iter, fd_eps, (T*)G_out,       \
+                                          iters);                                                                      \
     } while (0)
         if (P.diag) {
             if (in_dim == 0) KC_LAUNCH_ROLL(true, 0, 12);
@@ -197,7 +225,7 @@ static int rollout_typed(const kc_rod_params* Pp, const kc_mlp* mlp, int64_t B, 
         auto tk = kc_traj_transpose_kernel<T>;
         if (tsmem > 48 * 1024) cudaFuncSetAttribute(tk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem);
         dim3 tgrid((unsigned)((B + 31) / 32), (unsigned)T_);
-        tk<<<tgrid, dim3(32, 8), tsmem, st>>>(trajD, (T*)traj, B, (int)T_, K, w.Bpad, rows, N, P.c1, P.c2, 0, (int)T_);
+        tk<<<tgrid, dim3(32, 8), tsmem, st>>>(trajD, (T*)traj, B, (int)T_, N, rows, P.c1, P.c2);
         KC_CHECK_LAUNCH("kc_traj_transpose_kernel");
     }
     return KC_OK;

@@ -25,15 +25,20 @@ static void run(const RodC<T>& P, const MlpC<T>& M, int64_t B, int64_t T_, const
                 T* Gout, T tol, int max_iter, T fd_eps) {
     const int N = P.N;
     std::vector<T> trajD((size_t)T_ * 25 * N), Hs((size_t)NH * (N - 1));
+    T* out = traj;
     for (int64_t b = 0; b < B; ++b) {
         T stmem[KC_SHOOT_SLOTS];
-        ShootMem<T> st{stmem, 1};
+        ShootMem<T, 1> st{stmem};
         st.reset();
-        rollout_init<T>(P, nullptr, nullptr, trajD.data(), 1);
+        rollout_init<T, 1>(P, nullptr, nullptr, trajD.data());
         if (iters) iters[b * T_] = 0;
-        rollout_rod<T, DIAG, IN, NH>(P, M, st, ten + b * T_ * 4, trajD.data(), 1, Hs.data(), 1, 0, (int)T_ - 1, tol,
-                                     max_iter, fd_eps, Gout ? Gout + b * T_ * 6 : nullptr, iters ? iters + b * T_ : nullptr);
-        std::memcpy(traj + (size_t)b * T_ * 25 * N, trajD.data(), sizeof(T) * trajD.size());
+        rollout_rod<T, DIAG, IN, NH, 1>(P, M, st, ten + b * T_ * 4, trajD.data(), Hs.data(), 0, (int)T_ - 1, tol,
+                                        max_iter, fd_eps, Gout ? Gout + b * T_ * 6 : nullptr, iters ? iters + b * T_ : nullptr);
+        // device layout per rod is [T][N][25] -> reference [T][25][N]
+        for (int64_t t = 0; t < T_; ++t)
+            for (int j = 0; j < N; ++j)
+                for (int r = 0; r < 25; ++r)
+                    out[(((size_t)b * T_ + t) * 25 + r) * N + j] = trajD[((size_t)t * N + j) * 25 + r];
     }
 }
 
