@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""bench.py — the benchmark contract of this repo.
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched under torchrun, one rank per GPU)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[1]): batched forward rollout of the physics-only Cosserat rod,
+4096 rods per GPU x N=10 nodes x T=100 time indices (99 solved steps), setup_robot parameters, fp32, synthetic
+tensions (half sine, half random).  One "step" = one rollout of the whole batch through kc_rollout_fwd (rollout kernel +
+layout transpose), inputs resident in HBM.  metric = rod-node-steps/s, whole job (all ranks).  Rods are independent:
+ranks share nothing on the data path (weak scaling, no collective); the KNODE training step reported under "train" is
+the only path with a collective (NCCL all-reduce of the 27,673 MLP gradients).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "knode-cosserat_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+B_PER_GPU, T_STEPS, N_NODES = 4096, 100, 10
+F_ODE = 449.0                      # FLOP per physics node evaluation + Euler update (SURVEY §8 header)
+E_REF = 15.0                       # nominal residual evaluations per time step (reference fsolve mean)
+FLOP_PER_RNS = E_REF * (N_NODES - 1) / N_NODES * F_ODE   # 6.06 kFLOP per rod-node-step, physics only
+BYTES_PER_RNS = 25 * 4 + 16.0 / N_NODES                  # 101.6 B per rod-node-step (fp32 trajectory + tensions)
+TRAIN_B, TRAIN_T, TRAIN_H, TRAIN_KEYS = 1024, 30, 512, [3, 5, 7, 9]
+FLOP_PER_TRAIN_SAMPLE = F_ODE + 106 * TRAIN_H + 156 * TRAIN_H  # 134.6 kFLOP
+
+
+def _cpu_rollout_worker(args):
+    """One rod of the workload on one host core with the reference's algorithm (oracle port of knode.simulate: numpy
+    march + scipy fsolve)."""
+    ctl, = args
+    from oracle import rod_oracle as O
+    P = O.setup_params(O.RodParams())
+    t0 = time.perf_counter()
+    O.rollout_fsolve(P, ctl)
+    return time.perf_counter() - t0
+
+
+def cpu_reference_sample(ctl_rods, cores):
+    """Roll `len(ctl_rods)` rods out on `cores` host processes; returns (rod-node-steps/s, wall seconds)."""
+    import multiprocessing as mp
+    ctx = mp.get_context("fork")
+    t0 = time.perf_counter()
+    with ctx.Pool(cores) as pool:
+        pool.map(_cpu_rollout_worker, [(c,) for c in ctl_rods], chunksize=1)
+    wall = time.perf_counter() - t0
+    n = sum((c.shape[0] - 1) * N_NODES for c in ctl_rods)
+    return n / wall, wall
+
+
+def host_cores():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi-equivalent clock / throttle-reason samples (NVML) during the timed region."""
+
+    REASONS = {0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown",
+               0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown", 0x10: "sync_boost",
+               0x100: "display_clock_setting"}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.sm, self.reasons, self.max_mhz, self.ok = index, False, [], set(), None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        while self.ok and not self.stop_flag:
+            try:
+                self.sm.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                mask = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def summary(self):
+        if not self.ok or not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml_unavailable"]}
+        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.sm)}
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's own CPU implementation of the path (oracle port: numpy + scipy fsolve, one rod
+    per host process) on a bounded sample of the same workload per step."""
+    if rank != 0:
+        return
+    from oracle import rod_oracle as O
+    from physics_controls import synthetic_tensions
+    P = O.setup_params(O.RodParams())
+    cores = min(host_cores(), 64)
+    t_sample = 26  # 25 solved steps per rod per bench step (~1-2 s of CPU work per core)
+    ctl = synthetic_tensions(B_PER_GPU, T_STEPS, P.del_t, seed=0, dtype=np.float64)
+    pick = np.linspace(0, B_PER_GPU - 1, cores).astype(int)
+    rods = [ctl[i, :t_sample] for i in pick]
+    for _ in range(args.warmup):
+        cpu_reference_sample(rods[:cores], cores)
+    t0 = time.perf_counter()
+    n = 0
+    for _ in range(args.steps):
+        cpu_reference_sample(rods, cores)
+        n += len(rods) * (t_sample - 1) * N_NODES
+    wall = time.perf_counter() - t0
+    val = n / wall
+    sample = f"{len(rods)} rods x {t_sample - 1} solved steps per bench step, one rod per host process"
+    print(json.dumps({
+        "impl": "reference", "metric": "rod-node-steps/sec", "value": val, "unit": "rod-node-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C2 batched forward rollout, physics-only rod, 4096 rods x 10 nodes x 100 time indices "
+                               "(bounded sample of it per step)", "params": "setup_robot", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "rod-node-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "rod-node-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, nargs=2, default=None, help=argparse.SUPPRESS)  # T_sample cores
+    args = ap.parse_args()
+    if args.cpu_sample is not None:  # child process of the cpu_baseline leg (keeps fork() away from the CUDA context)
+        from oracle import rod_oracle as O
+        from physics_controls import synthetic_tensions
+        t_sample, cores = args.cpu_sample
+        P = O.setup_params(O.RodParams())
+        c = synthetic_tensions(B_PER_GPU, T_STEPS, P.del_t, seed=0, dtype=np.float64)
+        pick = np.linspace(0, B_PER_GPU - 1, cores).astype(int)
+        val, wall = cpu_reference_sample([c[i, :t_sample] for i in pick], cores)
+        print(json.dumps({"value": val, "wall": wall, "rods": len(pick)}))
+        return
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    import _kc
+    import _ops
+    from oracle import rod_oracle as O  # constants + cpu_baseline leg only
+    from cosserat_ode import CosseratRod
+    from cosserat_ode_torch import CosseratRodTorch
+    from knode import setup_robot, simulate
+    from physics_controls import synthetic_tensions
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (this repo has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- workload ----------------
+    robot = CosseratRod(use_fsolve=True)
+    setup_robot(robot)
+    P = _kc.rod_params(robot)
+    B, T = B_PER_GPU, T_STEPS
+    ctl_host = synthetic_tensions(B, T, robot.del_t, seed=rank, dtype=np.float32)
+    ctl = torch.tensor(ctl_host, device=dev)
+    plan = _ops.RolloutPlan(P, None, B, T, torch.float32, dev, rows=25)
+    plan_k = _ops.RolloutPlan(P, None, B, T, torch.float32, dev, rows=0)   # rollout kernel alone (roofline)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    for _ in range(args.warmup):
+        plan.run(ctl)
+        plan_k.run(ctl)
+    torch.cuda.synchronize()
+    its = plan.iters.cpu().numpy()
+    assert its.min() >= 0, "a rod failed to converge during warm-up"
+    marches_mean = float(np.abs(its[:, 1:]).mean())
+    rpw = 8
+    marches_warp = float(np.abs(its[:, 1:]).reshape(B // rpw, rpw, T - 1).max(1).mean())
+
+    sampler = ClockSampler(local_rank)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    sampler.start()
+    for i in range(args.steps):
+        flush.zero_()
+        ev[i][0].record()
+        plan.run(ctl)
+        ev[i][1].record()
+    barrier()
+    sampler.stop_flag = True
+    total_ms = sum(a.elapsed_time(b) for a, b in ev)
+    total_ms = max_over_ranks(total_ms)
+    rns_per_step = B * N_NODES * (T - 1)
+    value = world * rns_per_step * args.steps / (total_ms * 1e-3)
+
+    # rollout kernel alone, for the roofline object
+    evk = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for i in range(args.steps):
+        flush.zero_()
+        evk[i][0].record()
+        plan_k.run(ctl)
+        evk[i][1].record()
+    torch.cuda.synchronize()
+    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in evk]))
+    fp32_peak = _ops.fma_peak(torch.float32, 40000, dev)
+    achieved = rns_per_step * FLOP_PER_RNS / (kern_ms * 1e-3)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_achieved = rns_per_step * BYTES_PER_RNS / (kern_ms * 1e-3) / 1e9
+    executed_flop = rns_per_step / N_NODES * (N_NODES - 1) * marches_warp * 337.0  # 120 FFMA*2 + 71 FMUL + 26 FADD per node
+
+    # ---------------- end to end through the public API (host buffers in, host buffers out) ----------------
+    pinned = torch.empty((B, T, 25, N_NODES), dtype=torch.float32).pin_memory()
+    ctl64 = ctl_host.astype(np.float64)
+    for _ in range(2):
+        simulate(robot, ctl64, dtype=np.float32, rows=25, pinned_out=pinned)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        simulate(robot, ctl64, dtype=np.float32, rows=25, pinned_out=pinned)
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = world * rns_per_step * args.steps / e2e_s
+
+    # ---------------- KNODE training step (C3/C4): teacher-forced fwd + loss + bwd + allreduce + Adam + clamp -----------
+    train = None
+    if not args.no_train:
+        torch.manual_seed(0)
+        trobot = CosseratRodTorch(str(dev), TRAIN_H)
+        setup_robot(trobot)
+        nb = TRAIN_B // world                                   # C4: the 1024 trajectories are sharded across ranks
+        ttraj = plan.traj[:nb, :TRAIN_T].contiguous()
+        tctl = ctl[:nb, :TRAIN_T].contiguous()
+        W = [p.data for p in trobot.nn_models.parameters()]
+        m = [torch.zeros_like(w) for w in W]
+        v = [torch.zeros_like(w) for w in W]
+        step_no = [0]
+
+        def train_step():
+            loss, grads, _ = trobot.teacher_forced_step(ttraj, tctl, TRAIN_KEYS)
+            if world > 1:
+                flat = torch.cat([g.reshape(-1) for g in grads])
+                dist.all_reduce(flat)                            # the only collective: 27,673 fp32 gradients
+                off = 0
+                new = []
+                for g in grads:
+                    new.append(flat[off:off + g.numel()].view_as(g))
+                    off += g.numel()
+                grads = new
+            step_no[0] += 1
+            for i, (w, g) in enumerate(zip(W, grads)):
+                _ops.adam_clamp(w, g, m[i], v[i], step_no[0], lr=1e-2, clamp=(i % 2 == 0))
+            return loss
+
+        for _ in range(args.warmup):
+            train_step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            loss = train_step()
+        e1.record()
+        barrier()
+        tms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+        q = TRAIN_B * (TRAIN_T - 1) * len(TRAIN_KEYS)
+        train = {"metric": "KNODE train steps/sec", "value": 1e3 / tms, "unit": "steps/s", "ms_per_step": tms,
+                 "global_batch_trajectories": TRAIN_B, "samples_per_step": q, "scaling": "strong",
+                 "semantics": "teacher-forced (physics_train.py), fwd+loss+bwd+allreduce+Adam+clamp",
+                 "useful_tflops": q * FLOP_PER_TRAIN_SAMPLE / (tms * 1e-3) / 1e12, "hidden": TRAIN_H,
+                 "loss": float(loss.item()), "kernels_per_step": 4 + 4 + 1}
+
+    # ---------------- CPU baseline (rank 0, bounded sample, the reference's algorithm on the host cores) -----------
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        cores = min(host_cores(), 64)
+        t_sample = 51
+        import subprocess
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-sample", str(t_sample), str(cores)],
+                           capture_output=True, text=True, check=True)
+        cj = json.loads(r.stdout.strip().splitlines()[-1])
+        cval, cwall, nrods = cj["value"], cj["wall"], cj["rods"]
+        cpu = {"value": cval, "unit": "rod-node-steps/s", "cores": cores, "kind": "port",
+               "sample": f"{nrods} rods x {t_sample - 1} solved steps of the same workload, oracle port of "
+                         f"knode.simulate (numpy + scipy fsolve), one rod per host process, {cwall:.1f} s wall"}
+
+    if rank == 0:
+        out = {
+            "metric": "rod-node-steps/sec", "value": value, "unit": "rod-node-steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C2 batched forward rollout, physics-only Cosserat rod: 4096 rods/GPU x 10 nodes x "
+                                   "100 time indices (99 solved steps), setup_robot params, half sine / half random "
+                                   "tensions", "rods_per_gpu": B, "nodes": N_NODES, "time_indices": T,
+                       "output": "traj[B,T,25,N] fp32 in the reference layout, resident in HBM",
+                       "l2": "827 MB written per step (> 126 MB L2) plus an explicit 256 MB flush between timed "
+                             "iterations", "parallelism": f"rods sharded over {world} rank(s), no collective",
+                       "solver": {"marches_per_step_mean": marches_mean, "marches_per_step_warp": marches_warp,
+                                  "nominal_evals_per_step": E_REF}},
+            "clocks": sampler.summary(),
+            "e2e": {"value": e2e_value, "unit": "rod-node-steps/s", "h2d_bytes_per_step": int(ctl_host.nbytes),
+                    "d2h_bytes_per_step": int(pinned.numel() * 4), "api": "knode.simulate(robot, ctl[B,T,4], "
+                    "dtype=float32, rows=25) host numpy in -> host numpy out", "ms_per_step": e2e_s / args.steps * 1e3},
+            "gpu_launches": 2 * args.steps,
+            "roofline": {"bound": "fp32", "kernel": "kc_rollout_kernel<float,diag,physics>", "achieved": achieved / 1e12,
+                         "peak": fp32_peak / 1e12, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
+                         "peak_source": "kc_fma_peak micro-benchmark measured live in this run (MEASURED_PEAKS.json has "
+                                        "no FP32-pipe figure)", "normalisation": "6.06 kFLOP per rod-node-step = 15 "
+                         "nominal residual evaluations x 9/10 x 449 FLOP (SURVEY 8d)",
+                         "kernel_ms": kern_ms, "executed_tflops": executed_flop / (kern_ms * 1e-3) / 1e12,
+                         "traffic": 366.6e6,
+                         "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak}},
+            "cpu_baseline": cpu, "train": train}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

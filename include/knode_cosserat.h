@@ -80,6 +80,13 @@ int kc_ode_bwd(int dtype, const kc_rod_params *P, const kc_mlp *mlp, int64_t Q, 
                void *g_zh, void *g_tf, void *gW1, void *gb1, void *gW2, void *gb2, void *workspace,
                int64_t workspace_bytes, void *stream);
 
+/* The KNODE MLP alone: CosseratRodTorch.forward (cosserat_ode_torch.py:131-134) and CosseratRod.get_nn_output
+ * (cosserat_ode.py:90-112): x[Q][in_dim] -> out[Q][25]; kc_mlp_bwd is its reverse mode (g_out[Q][25] -> g_x[Q][in_dim]
+ * and/or OVERWRITTEN parameter cotangents; any of them may be NULL).  workspace: kc_ode_bwd_workspace_bytes(). */
+int kc_mlp_fwd(int dtype, const kc_mlp *mlp, int64_t Q, const void *x, void *out, void *stream);
+int kc_mlp_bwd(int dtype, const kc_mlp *mlp, int64_t Q, const void *x, const void *g_out, void *g_x, void *gW1,
+               void *gb1, void *gW2, void *gb2, void *workspace, int64_t workspace_bytes, void *stream);
+
 /* Shooting residual + spatial march for B rods: CosseratRod.getResidualEuler (cosserat_ode.py:188-213),
  * CosseratRod.getResidualRK4 (:215-255), CosseratRodTorch.getResidualEuler (cosserat_ode_torch.py:325-367).
  * G[B][6], y[B][19][N] and z[B][6][N] are updated IN PLACE like the numpy reference does (column 0 of y is
@@ -103,7 +110,9 @@ int kc_segment_fwd(int dtype, const kc_rod_params *P, const kc_mlp *mlp, int64_t
  * state and the step driven by tensions[:, T-1] is not computed (knode.py:102 drops it).
  * G_out[B][T][6] (may be NULL): converged base reactions; iters[B][T] int32 (may be NULL): marches used, negative
  * if the solve did not reach tol in max_iter marches.
- * tol <= 0 selects the default (1e-12 fp64, 2e-6 fp32; relative to max(1,|G|)). */
+ * rows == 0 skips the reference-layout output (traj may be NULL; the device-layout trajectory stays in the
+ * workspace) — used by bench.py to time the rollout kernel alone.
+ * tol <= 0 selects the default (1e-11 fp64, 2e-6 fp32; relative to max(1,|G|)). */
 int64_t kc_rollout_workspace_bytes(int dtype, const kc_rod_params *P, const kc_mlp *mlp, int64_t B, int64_t T);
 int kc_rollout_fwd(int dtype, const kc_rod_params *P, const kc_mlp *mlp, int64_t B, int64_t T,
                    const void *tensions, const void *y0, const void *z0, double tol, int32_t max_iter,

@@ -42,6 +42,8 @@ _SIGNATURES = {
     "kc_ode_bwd_workspace_bytes": (C.c_int64, [C.c_int, C.POINTER(kc_mlp), C.c_int64]),
     "kc_ode_bwd": (C.c_int, [C.c_int, C.POINTER(kc_rod_params), C.POINTER(kc_mlp), C.c_int64] + [C.c_void_p] * 15
                    + [C.c_int64, C.c_void_p]),
+    "kc_mlp_fwd": (C.c_int, [C.c_int, C.POINTER(kc_mlp), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "kc_mlp_bwd": (C.c_int, [C.c_int, C.POINTER(kc_mlp), C.c_int64] + [C.c_void_p] * 8 + [C.c_int64, C.c_void_p]),
     "kc_march": (C.c_int, [C.c_int, C.POINTER(kc_rod_params), C.POINTER(kc_mlp), C.c_int, C.c_int64]
                  + [C.c_void_p] * 8),
     "kc_segment_fwd": (C.c_int, [C.c_int, C.POINTER(kc_rod_params), C.POINTER(kc_mlp), C.c_int64, C.c_int32,

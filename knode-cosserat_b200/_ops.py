@@ -109,6 +109,36 @@ def ode_bwd(P, mlp, y, yh, zh, tf, g_ys, g_z, need_inputs=True, need_params=True
     return (*gi, *gp)
 
 
+def mlp_fwd(mlp, x):
+    """kc_mlp_fwd: x[Q,in] -> [Q,25]."""
+    _require_cuda(x)
+    x = _c(x)
+    m = mlp.cast(x.dtype)
+    out = torch.empty((x.shape[0], 25), dtype=x.dtype, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = _kc.lib().kc_mlp_fwd(_dtype_code(x), m.ref(), x.shape[0], _ptr(x), _ptr(out), _stream(x.device))
+    _kc.check(rc, "kc_mlp_fwd")
+    return out
+
+
+def mlp_bwd(mlp, x, g_out, need_input=True, need_params=True):
+    """kc_mlp_bwd -> (g_x, gW1, gb1, gW2, gb2) (None where not requested)."""
+    _require_cuda(x, g_out)
+    x = _c(x)
+    g_out = _c(g_out, x.dtype)
+    m = mlp.cast(x.dtype)
+    Q = x.shape[0]
+    gx = torch.empty_like(x) if need_input else None
+    gp = [torch.empty_like(t) for t in (m.W1, m.b1, m.W2, m.b2)] if need_params else [None] * 4
+    with torch.cuda.device(x.device):
+        nbytes = int(_kc.lib().kc_ode_bwd_workspace_bytes(_dtype_code(x), m.ref(), Q))
+        ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=x.device)
+        rc = _kc.lib().kc_mlp_bwd(_dtype_code(x), m.ref(), Q, _ptr(x), _ptr(g_out), _ptr(gx), *[_ptr(t) for t in gp],
+                                  _ptr(ws), nbytes, _stream(x.device))
+    _kc.check(rc, "kc_mlp_bwd")
+    return (gx, *gp)
+
+
 def march(P, mlp, G, y, z, yh, zh, tensions, method=_kc.KC_MARCH_EULER):
     """kc_march, IN PLACE on y[B,19,N], z[B,6,N]; returns res[B,6]."""
     _require_cuda(G, y, z, yh, zh, tensions)
@@ -160,7 +190,7 @@ class RolloutPlan:
             raise ValueError("kc_rollout_workspace_bytes: bad arguments")
         self.nbytes = int(nbytes)
         self.ws = torch.empty(max(self.nbytes, 1), dtype=torch.uint8, device=device)
-        self.traj = torch.empty((B, T, rows, int(P.N)), dtype=dtype, device=device)
+        self.traj = torch.empty((B, T, rows, int(P.N)), dtype=dtype, device=device) if rows else None
         self.G = torch.empty((B, T, 6), dtype=dtype, device=device) if want_G else None
         self.iters = torch.empty((B, T), dtype=torch.int32, device=device) if want_iters else None
 

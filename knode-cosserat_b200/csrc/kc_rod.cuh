@@ -380,3 +380,54 @@ KC_HD int shoot_step(const RodC<T>& P, const MlpC<T>& M, const ShootMem<T, LS>& 
     }
     return (converged && !failed) ? marches : -marches;
 }
+
+// ---- loss helpers: Utils/transformations.py:3-31 (quaternion wxyz -> roll, pitch, yaw) and its reverse mode ---------
+KC_HD float kc_sqrt(float x) { return sqrtf(x); }
+KC_HD double kc_sqrt(double x) { return sqrt(x); }
+KC_HD float kc_atan2(float a, float b) { return atan2f(a, b); }
+KC_HD double kc_atan2(double a, double b) { return atan2(a, b); }
+KC_HD float kc_asin(float a) { return asinf(a); }
+KC_HD double kc_asin(double a) { return asin(a); }
+
+template <typename T> KC_HD void quat_to_euler(const T q[4], T e[3]) {
+    const T inv = T(1) / kc_sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    const T w = q[0] * inv, x = q[1] * inv, y = q[2] * inv, z = q[3] * inv;
+    e[0] = kc_atan2(T(2) * (w * y + x * z), T(1) - T(2) * (y * y + z * z));
+    T s = T(2) * (w * z - x * y);
+    s = s < T(-1) ? T(-1) : (s > T(1) ? T(1) : s);
+    e[1] = kc_asin(s);
+    e[2] = kc_atan2(T(2) * (w * x + y * z), T(1) - T(2) * (x * x + z * z));
+}
+
+// cotangent g[3] of the Euler angles -> cotangent gq[4] of the (unnormalised) quaternion; the clamp passes gradient only
+// strictly inside (-1, 1), as torch.clamp does.
+template <typename T> KC_HD void quat_to_euler_vjp(const T q[4], const T g[3], T gq[4]) {
+    const T n2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+    const T inv = T(1) / kc_sqrt(n2);
+    const T w = q[0] * inv, x = q[1] * inv, y = q[2] * inv, z = q[3] * inv;
+    T gw, gx, gy, gz;
+    {
+        const T a = T(2) * (w * y + x * z), b = T(1) - T(2) * (y * y + z * z);
+        const T r = T(1) / (a * a + b * b);
+        const T da = g[0] * b * r, db = -g[0] * a * r;
+        gw = da * T(2) * y; gx = da * T(2) * z;
+        gy = da * T(2) * w - db * T(4) * y; gz = da * T(2) * x - db * T(4) * z;
+    }
+    {
+        const T s = T(2) * (w * z - x * y);
+        if (s > T(-1) && s < T(1)) {
+            const T d = g[1] / kc_sqrt(T(1) - s * s);
+            gw += d * T(2) * z; gz += d * T(2) * w; gx -= d * T(2) * y; gy -= d * T(2) * x;
+        }
+    }
+    {
+        const T c = T(2) * (w * x + y * z), d = T(1) - T(2) * (x * x + z * z);
+        const T r = T(1) / (c * c + d * d);
+        const T dc = g[2] * d * r, dd = -g[2] * c * r;
+        gw += dc * T(2) * x; gx += dc * T(2) * w - dd * T(4) * x;
+        gy += dc * T(2) * z; gz += dc * T(2) * y - dd * T(4) * z;
+    }
+    const T dot = gw * w + gx * x + gy * y + gz * z;
+    gq[0] = (gw - w * dot) * inv; gq[1] = (gx - x * dot) * inv;
+    gq[2] = (gy - y * dot) * inv; gq[3] = (gz - z * dot) * inv;
+}

@@ -220,6 +220,7 @@ static int rollout_typed(const kc_rod_params* Pp, const kc_mlp* mlp, int64_t B, 
         }
 #undef KC_LAUNCH_ROLL
         KC_CHECK_LAUNCH("kc_rollout_kernel");
+        if (rows == 0) return KC_OK;
         const int K = 25 * N;
         const size_t tsmem = (size_t)K * 33 * sizeof(T);
         auto tk = kc_traj_transpose_kernel<T>;
@@ -238,8 +239,8 @@ extern "C" int kc_rollout_fwd(int dtype, const kc_rod_params* P, const kc_mlp* m
     KC_CHECK_ARG(dtype == KC_F32 || dtype == KC_F64, "dtype must be KC_F32 or KC_F64");
     KC_CHECK_ARG(P && P->N >= 2, "rod params missing or N < 2");
     KC_CHECK_ARG(B >= 0 && T_ >= 1, "B must be >= 0 and T >= 1");
-    KC_CHECK_ARG(rows == 25 || rows == 50, "rows must be 25 or 50");
-    KC_CHECK_ARG(B == 0 || (tensions && traj && workspace), "NULL tensions/traj/workspace");
+    KC_CHECK_ARG(rows == 25 || rows == 50 || rows == 0, "rows must be 25, 50 or 0");
+    KC_CHECK_ARG(B == 0 || (tensions && (traj || rows == 0) && workspace), "NULL tensions/traj/workspace");
     KC_CHECK_ARG((y0 == nullptr) == (z0 == nullptr), "y0 and z0 must be given together");
     int rc = kc_check_mlp(mlp);
     if (rc) return rc;

@@ -1,7 +1,407 @@
-// kc_train.cu — teacher-forced KNODE training step, ODE reverse mode, Adam + clamp.
+// kc_train.cu — teacher-forced KNODE training step (forward + 4-term loss + reverse mode to the MLP weights), the
+// reverse mode of the batched node ODE, and Adam + clamp.
+//
+// Reference: physics_train.py:313-368 (fast path) == :215-267 (slow path at its key nodes) == train_segment.py:140-185;
+// loss terms physics_train.py:345-352 with Utils/transformations.py:3-31.  The physics is a constant offset of the
+// prediction, so the weight gradient needs no physics adjoint:
+//     pred[0:19] = y + ds*(ys_phys + o[0:19]),  pred[19:25] = z_phys + o[19:25],  o = W2 ELU(W1 x + b1) + b2.
+//
+// Kernel plan of one step (SIMT FP32/FP64; Q = B*(T-1)*K samples):
+//   1. kc_train_prep_kernel   : gather (b,t,key) from traj, BDF2 history, physics ODE -> X[Q][XP], PHYS[Q][25], TGT[Q][25]
+//   2. kc_train_fwd_kernel    : one sample per thread, MLP forward with broadcast weights, loss terms, dL/do -> dO[Q][32]
+//   3. kc_train_bwd_kernel    : CTA = (32 hidden units) x (a slice of the samples); recomputes z1/ELU for its units from X,
+//                               forms dz1 = (W2^T dO) * ELU'(z1), accumulates gW1, gb1, gW2 (and gb2) in registers as
+//                               shared-memory-tiled outer products; writes per-slice partials
+//   4. kc_train_reduce_kernel : deterministic sum of the partials into gW1, gb1, gW2, gb2 and of the loss partials
 #include <cuda_runtime.h>
 #include "kc_rod.cuh"
+#include "kc_adjoint.cuh"
 
+template <typename T> int kc_pack_mlp(const kc_mlp* mlp, T* Wp, MlpC<T>& M, cudaStream_t st);
+int kc_check_mlp(const kc_mlp* mlp);
+
+struct KeyIdx64 { int32_t k[64]; };
+static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// 1. prep
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T, bool DIAG, int IN>
+__global__ void __launch_bounds__(128)
+kc_train_prep_kernel(const __grid_constant__ RodC<T> P, const __grid_constant__ KeyIdx64 key, int64_t B, int T_, int K,
+                     const T* __restrict__ traj, const T* __restrict__ controls, T* __restrict__ X, int XP,
+                     T* __restrict__ PHYS, T* __restrict__ TGT) {
+    const int64_t Q = B * (int64_t)(T_ - 1) * K;
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= Q) return;
+    const int N = P.N;
+    const int kk = (int)(q % K);
+    const int64_t bt = q / K;
+    const int t = (int)(bt % (T_ - 1));
+    const int64_t b = bt / (T_ - 1);
+    const int kn = key.k[kk];  // key node (loss is taken there); the ODE runs at node kn-1
+    const int j = kn - 1;
+    const T* nxt = traj + ((size_t)(b * T_ + t + 1) * 25) * N;
+    const T* cur = traj + ((size_t)(b * T_ + t) * 25) * N;
+    const T* prv = traj + ((size_t)(b * T_ + (t > 0 ? t - 1 : 0)) * 25) * N;
+    T y[19], hist[25], tn[4], tf[3], ys[19], z[6];
+#pragma unroll
+    for (int r = 0; r < 19; ++r) y[r] = nxt[r * N + j];
+#pragma unroll
+    for (int r = 0; r < 25; ++r) hist[r] = P.c1 * cur[r * N + j] + P.c2 * prv[r * N + j];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) tn[i] = controls[(size_t)(b * T_ + t) * 4 + i];
+    tendon_force(P, tn, tf);
+    rod_ode<T, DIAG>(P, y, hist + 13, hist + 16, hist + 19, hist + 22, tf, ys, z);
+    T* x = X + (size_t)q * XP;
+    if (IN == 28) {
+#pragma unroll
+        for (int i = 0; i < 19; ++i) x[i] = y[i];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) x[19 + i] = z[i];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) x[25 + i] = tf[i];
+#pragma unroll
+        for (int i = 28; i < 32; ++i) x[i] = T(0);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 19; ++i) { x[i] = y[i]; x[19 + i] = hist[i]; }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) { x[38 + i] = z[i]; x[44 + i] = hist[19 + i]; }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) x[50 + i] = tf[i];
+#pragma unroll
+        for (int i = 53; i < 56; ++i) x[i] = T(0);
+    }
+    T* ph = PHYS + (size_t)q * 25;
+    T* tg = TGT + (size_t)q * 25;
+#pragma unroll
+    for (int r = 0; r < 19; ++r) { ph[r] = y[r] + P.ds * ys[r]; tg[r] = nxt[r * N + kn]; }
+#pragma unroll
+    for (int c = 0; c < 6; ++c) { ph[19 + c] = z[c]; tg[19 + c] = nxt[(19 + c) * N + kn - 1]; }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// 2. forward + loss + dL/do
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int FWD_THREADS = 128;
+template <typename T, int IN>
+__global__ void __launch_bounds__(FWD_THREADS)
+kc_train_fwd_kernel(const MlpC<T> M, T ds, int64_t Q, int T_, int K, const T* __restrict__ X, int XP,
+                    const T* __restrict__ PHYS, const T* __restrict__ TGT, T* __restrict__ dO,
+                    double* __restrict__ loss_part, T* __restrict__ pred_out) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double my = 0.0;
+    if (q < Q) {
+        T x[IN], o[25];
+        const T* xr = X + (size_t)q * XP;
+#pragma unroll
+        for (int i = 0; i < IN; ++i) x[i] = xr[i];
+        mlp_eval<T, IN>(M, x, o);
+        T pred[25], tg[25];
+#pragma unroll
+        for (int r = 0; r < 19; ++r) pred[r] = PHYS[(size_t)q * 25 + r] + ds * o[r];
+#pragma unroll
+        for (int c = 19; c < 25; ++c) pred[c] = PHYS[(size_t)q * 25 + c] + o[c];
+#pragma unroll
+        for (int r = 0; r < 25; ++r) tg[r] = TGT[(size_t)q * 25 + r];
+        const T S = T(T_ - 1);
+        const T wp = T(1) / (T(3 * K) * S), wf = T(1) / (T(12 * K) * S), wz = T(1) / (T(6 * K) * S);
+        T g[25];
+        T acc = T(0);
+#pragma unroll
+        for (int r = 0; r < 3; ++r) { const T e = pred[r] - tg[r]; acc += wp * e * e; g[r] = T(2) * wp * e * ds; }
+#pragma unroll
+        for (int r = 7; r < 19; ++r) { const T e = pred[r] - tg[r]; acc += wf * e * e; g[r] = T(2) * wf * e * ds; }
+#pragma unroll
+        for (int r = 19; r < 25; ++r) { const T e = pred[r] - tg[r]; acc += wz * e * e; g[r] = T(2) * wz * e; }
+        T ep[3], et[3], ge[3], gq[4];
+        quat_to_euler(pred + 3, ep);
+        quat_to_euler(tg + 3, et);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { const T e = ep[i] - et[i]; acc += wp * e * e; ge[i] = T(2) * wp * e; }
+        quat_to_euler_vjp(pred + 3, ge, gq);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) g[3 + i] = gq[i] * ds;
+        T* go = dO + (size_t)q * 32;
+#pragma unroll
+        for (int r = 0; r < 25; ++r) go[r] = g[r];
+#pragma unroll
+        for (int r = 25; r < 32; ++r) go[r] = T(0);
+        my = (double)acc;
+        if (pred_out) {  // pred[B][T-1][25][K]
+            const int kk = (int)(q % K);
+            const int64_t bt = q / K;
+            T* po = pred_out + (size_t)bt * 25 * K + kk;
+#pragma unroll
+            for (int r = 0; r < 25; ++r) po[r * K] = pred[r];
+        }
+    }
+    // block reduction of the loss in double
+    __shared__ double red[FWD_THREADS / 32];
+#pragma unroll
+    for (int o2 = 16; o2 > 0; o2 >>= 1) my += __shfl_down_sync(0xffffffffu, my, o2);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = my;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int i = 0; i < FWD_THREADS / 32; ++i) s += red[i];
+        loss_part[blockIdx.x] = s;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// 3. backward: weight gradients
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int BWD_THREADS = 256;
+constexpr int BWD_TS = 128;  // samples per tile
+constexpr int BWD_HC = 32;   // hidden units per CTA
+
+template <typename T, int IN>
+__global__ void __launch_bounds__(BWD_THREADS)
+kc_train_bwd_kernel(int hidden, const T* __restrict__ W1, const T* __restrict__ b1, const T* __restrict__ W2,
+                    int64_t Q, const T* __restrict__ X, const T* __restrict__ dO, T* __restrict__ partial,
+                    int64_t NP, int64_t tiles_per_split) {
+    constexpr int XP = (IN + 3) & ~3;      // 28 -> 32? no: 28 stays 28; rows of X are padded to XPG in global memory
+    constexpr int XPG = IN == 28 ? 32 : 56;  // global row pitch of X
+    constexpr int NG = XP / 4;             // float4 groups per x row (7 or 14)
+    extern __shared__ __align__(16) unsigned char kc_smem[];
+    T* Xs = reinterpret_cast<T*>(kc_smem);              // [TS][XPG]
+    T* dOs = Xs + BWD_TS * XPG;                          // [TS][32]
+    T* As = dOs + BWD_TS * 32;                           // [TS][HC+1]
+    T* dZs = As + BWD_TS * (BWD_HC + 1);                 // [TS][HC+1]
+    T* W1c = dZs + BWD_TS * (BWD_HC + 1);                // [HC][XP]
+    T* W2c = W1c + BWD_HC * XP;                          // [HC][28] (transposed: unit-major, 25 used)
+    T* b1c = W2c + BWD_HC * 28;                          // [HC]
+    const int tid = threadIdx.x;
+    const int u0 = blockIdx.x * BWD_HC;
+    // stage this CTA's slice of the weights (zero beyond `hidden`)
+    for (int e = tid; e < BWD_HC * XP; e += BWD_THREADS) {
+        const int i = e / XP, k = e - i * XP;
+        W1c[e] = (u0 + i < hidden && k < IN) ? W1[(size_t)(u0 + i) * IN + k] : T(0);
+    }
+    for (int e = tid; e < BWD_HC * 28; e += BWD_THREADS) {
+        const int i = e / 28, c = e - i * 28;
+        W2c[e] = (u0 + i < hidden && c < 25) ? W2[(size_t)c * hidden + u0 + i] : T(0);
+    }
+    for (int e = tid; e < BWD_HC; e += BWD_THREADS) b1c[e] = (u0 + e < hidden) ? b1[u0 + e] : T(0);
+    // accumulator ownership
+    const int wi = tid >> 3, wg = tid & 7;          // gW1: unit wi, float4 groups wg (and wg+8 when NG > 8)
+    const int vi = tid & 31, vc = (tid >> 5) * 4;   // gW2: unit vi, outputs vc..vc+3
+    T aW1a[4] = {0, 0, 0, 0}, aW1b[4] = {0, 0, 0, 0}, aW2[4] = {0, 0, 0, 0}, ab1 = T(0), ab2 = T(0);
+    const int64_t tile0 = (int64_t)blockIdx.y * tiles_per_split;
+    const int64_t ntiles = (Q + BWD_TS - 1) / BWD_TS;
+    for (int64_t tile = tile0; tile < tile0 + tiles_per_split && tile < ntiles; ++tile) {
+        const int64_t q0 = tile * BWD_TS;
+        const int cnt = (int)min((int64_t)BWD_TS, Q - q0);
+        __syncthreads();
+        for (int e = tid; e < BWD_TS * XPG; e += BWD_THREADS) Xs[e] = (e < cnt * XPG) ? X[(size_t)q0 * XPG + e] : T(0);
+        for (int e = tid; e < BWD_TS * 32; e += BWD_THREADS) dOs[e] = (e < cnt * 32) ? dO[(size_t)q0 * 32 + e] : T(0);
+        __syncthreads();
+        {   // phase A: a = ELU(z1), dz = (W2^T dO) ELU'(z1) for (sample s, 16 of the 32 units)
+            const int s = tid & (BWD_TS - 1), ib = (tid >> 7) * 16;
+            T x[IN], g[25];
+#pragma unroll
+            for (int k = 0; k < IN; ++k) x[k] = Xs[s * XPG + k];
+#pragma unroll
+            for (int c = 0; c < 25; ++c) g[c] = dOs[s * 32 + c];
+#pragma unroll 2
+            for (int i = ib; i < ib + 16; ++i) {
+                T z1 = b1c[i];
+#pragma unroll
+                for (int k = 0; k < IN; ++k) z1 += W1c[i * XP + k] * x[k];
+                T da = T(0);
+#pragma unroll
+                for (int c = 0; c < 25; ++c) da += W2c[i * 28 + c] * g[c];
+                As[s * (BWD_HC + 1) + i] = kc_elu(z1);
+                dZs[s * (BWD_HC + 1) + i] = da * kc_elu_grad(z1);
+            }
+        }
+        __syncthreads();
+        // phase B: outer-product accumulation over the tile's samples
+        for (int s = 0; s < BWD_TS; ++s) {
+            const T dz = dZs[s * (BWD_HC + 1) + wi];
+            if (wg < NG) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) aW1a[k] += dz * Xs[s * XPG + wg * 4 + k];
+            }
+            if (NG > 8 && wg + 8 < NG) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) aW1b[k] += dz * Xs[s * XPG + (wg + 8) * 4 + k];
+            }
+            const T a = As[s * (BWD_HC + 1) + vi];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) aW2[c] += dOs[s * 32 + vc + c] * a;
+            if (tid < BWD_HC) ab1 += dZs[s * (BWD_HC + 1) + tid];
+            if (blockIdx.x == 0 && tid >= 32 && tid < 32 + 25) ab2 += dOs[s * 32 + tid - 32];
+        }
+    }
+    // write this CTA's partials: flat parameter order [W1 (hidden x IN) | b1 | W2 (25 x hidden) | b2]
+    T* out = partial + (size_t)blockIdx.y * NP;
+    const int64_t oW1 = 0, ob1 = (int64_t)hidden * IN, oW2 = ob1 + hidden, ob2 = oW2 + (int64_t)25 * hidden;
+    if (u0 + wi < hidden) {
+        if (wg < NG) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) if (wg * 4 + k < IN) out[oW1 + (int64_t)(u0 + wi) * IN + wg * 4 + k] = aW1a[k];
+        }
+        if (NG > 8 && wg + 8 < NG) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) if ((wg + 8) * 4 + k < IN) out[oW1 + (int64_t)(u0 + wi) * IN + (wg + 8) * 4 + k] = aW1b[k];
+        }
+    }
+    if (u0 + vi < hidden) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) if (vc + c < 25) out[oW2 + (int64_t)(vc + c) * hidden + u0 + vi] = aW2[c];
+    }
+    if (tid < BWD_HC && u0 + tid < hidden) out[ob1 + u0 + tid] = ab1;
+    if (blockIdx.x == 0 && tid >= 32 && tid < 32 + 25) out[ob2 + tid - 32] = ab2;
+}
+
+template <typename T>
+__global__ void kc_train_reduce_kernel(const T* __restrict__ partial, int splits, int64_t NP, int hidden, int in_dim,
+                                       T* gW1, T* gb1, T* gW2, T* gb2, const double* __restrict__ loss_part,
+                                       int nloss, double* loss) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < NP) {
+        T s = T(0);
+        for (int k = 0; k < splits; ++k) s += partial[(size_t)k * NP + p];
+        const int64_t ob1 = (int64_t)hidden * in_dim, oW2 = ob1 + hidden, ob2 = oW2 + (int64_t)25 * hidden;
+        if (p < ob1) { if (gW1) gW1[p] = s; }
+        else if (p < oW2) { if (gb1) gb1[p - ob1] = s; }
+        else if (p < ob2) { if (gW2) gW2[p - oW2] = s; }
+        else { if (gb2) gb2[p - ob2] = s; }
+    }
+    if (loss && blockIdx.x == 0 && threadIdx.x < 32) {  // deterministic: fixed lane partition, fixed shuffle tree
+        double s = 0.0;
+        for (int i = threadIdx.x; i < nloss; i += 32) s += loss_part[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+        if (threadIdx.x == 0) *loss = s;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side of the train step
+// ---------------------------------------------------------------------------------------------------------------
+struct TrainWs { size_t X, PHYS, TGT, dO, lossp, part, wp, total; int XPG; int64_t Q, NP; int nfwd; int splits; int64_t tps; int chunks; };
+
+static size_t bwd_smem_bytes(int in_dim, size_t sz) {
+    const int XP = (in_dim + 3) & ~3, XPG = in_dim == 28 ? 32 : 56;
+    return (size_t)(BWD_TS * XPG + BWD_TS * 32 + 2 * BWD_TS * (BWD_HC + 1) + BWD_HC * XP + BWD_HC * 28 + BWD_HC) * sz;
+}
+
+static TrainWs train_ws(int dtype, const kc_mlp* mlp, int64_t Q) {
+    const size_t sz = dtype == KC_F32 ? 4 : 8;
+    TrainWs w;
+    w.Q = Q;
+    w.XPG = mlp->in_dim == 28 ? 32 : 56;
+    w.NP = (int64_t)mlp->hidden * mlp->in_dim + mlp->hidden + 25 * (int64_t)mlp->hidden + 25;
+    w.nfwd = (int)((Q + FWD_THREADS - 1) / FWD_THREADS);
+    w.chunks = (mlp->hidden + BWD_HC - 1) / BWD_HC;
+    const int64_t ntiles = (Q + BWD_TS - 1) / BWD_TS;
+    // one resident wave of bwd CTAs: ~3 (fp32) / 1 (fp64) CTAs per SM on 148 SMs
+    const int resident = 148 * (int)((227 * 1024) / bwd_smem_bytes(mlp->in_dim, sz));
+    int splits = resident / w.chunks;
+    if (splits < 1) splits = 1;
+    if (splits > ntiles) splits = (int)(ntiles > 0 ? ntiles : 1);
+    w.splits = splits;
+    w.tps = (ntiles + splits - 1) / splits;
+    size_t off = 0;
+    w.X = off; off += al256((size_t)Q * w.XPG * sz);
+    w.PHYS = off; off += al256((size_t)Q * 25 * sz);
+    w.TGT = off; off += al256((size_t)Q * 25 * sz);
+    w.dO = off; off += al256((size_t)Q * 32 * sz);
+    w.lossp = off; off += al256((size_t)(w.nfwd > 0 ? w.nfwd : 1) * 8);
+    w.part = off; off += al256((size_t)splits * w.NP * sz);
+    w.wp = off; off += al256((size_t)mlp->hidden * (((mlp->in_dim + 3) & ~3) + 32) * sz);
+    w.total = off;
+    return w;
+}
+
+extern "C" int64_t kc_train_step_workspace_bytes(int dtype, const kc_mlp* mlp, int64_t B, int64_t T_, int32_t K) {
+    if (!mlp || (dtype != KC_F32 && dtype != KC_F64) || B < 0 || T_ < 2 || K < 1) return KC_EINVAL;
+    if (kc_check_mlp(mlp)) return KC_EINVAL;
+    return (int64_t)train_ws(dtype, mlp, B * (T_ - 1) * K).total;
+}
+
+template <typename T>
+static int train_typed(const kc_rod_params* Pp, const kc_mlp* mlp, int64_t B, int64_t T_, int K, const int32_t* key_host,
+                       const void* traj, const void* controls, double* loss, void* gW1, void* gb1, void* gW2, void* gb2,
+                       void* pred, void* workspace, cudaStream_t st) {
+    const RodC<T> P = make_rodc<T>(*Pp);
+    KeyIdx64 key{};
+    for (int i = 0; i < K; ++i) {
+        KC_CHECK_ARG(key_host[i] >= 1 && key_host[i] <= P.N - 1, "key index %d out of range [1, N-1]", key_host[i]);
+        key.k[i] = key_host[i];
+    }
+    const int64_t Q = B * (T_ - 1) * K;
+    const TrainWs w = train_ws(sizeof(T) == 4 ? KC_F32 : KC_F64, mlp, Q);
+    unsigned char* ws = (unsigned char*)workspace;
+    T* X = (T*)(ws + w.X); T* PHYS = (T*)(ws + w.PHYS); T* TGT = (T*)(ws + w.TGT); T* dO = (T*)(ws + w.dO);
+    double* lossp = (double*)(ws + w.lossp); T* part = (T*)(ws + w.part);
+    MlpC<T> M;
+    int rc = kc_pack_mlp<T>(mlp, (T*)(ws + w.wp), M, st);
+    if (rc) return rc;
+    const int in_dim = mlp->in_dim;
+    if (Q > 0) {
+        const unsigned g1 = (unsigned)((Q + 127) / 128);
+#define PREP(D, I) kc_train_prep_kernel<T, D, I><<<g1, 128, 0, st>>>(P, key, B, (int)T_, K, (const T*)traj, (const T*)controls, X, w.XPG, PHYS, TGT)
+        if (P.diag) { if (in_dim == 28) PREP(true, 28); else PREP(true, 53); }
+        else { if (in_dim == 28) PREP(false, 28); else PREP(false, 53); }
+#undef PREP
+        KC_CHECK_LAUNCH("kc_train_prep_kernel");
+        if (in_dim == 28)
+            kc_train_fwd_kernel<T, 28><<<w.nfwd, FWD_THREADS, 0, st>>>(M, P.ds, Q, (int)T_, K, X, w.XPG, PHYS, TGT, dO, lossp, (T*)pred);
+        else
+            kc_train_fwd_kernel<T, 53><<<w.nfwd, FWD_THREADS, 0, st>>>(M, P.ds, Q, (int)T_, K, X, w.XPG, PHYS, TGT, dO, lossp, (T*)pred);
+        KC_CHECK_LAUNCH("kc_train_fwd_kernel");
+        const size_t smem = bwd_smem_bytes(in_dim, sizeof(T));
+        dim3 grid((unsigned)w.chunks, (unsigned)w.splits);
+        if (in_dim == 28) {
+            auto k = kc_train_bwd_kernel<T, 28>;
+            cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            k<<<grid, BWD_THREADS, smem, st>>>(mlp->hidden, (const T*)mlp->W1, (const T*)mlp->b1, (const T*)mlp->W2, Q, X, dO, part, w.NP, w.tps);
+        } else {
+            auto k = kc_train_bwd_kernel<T, 53>;
+            cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            k<<<grid, BWD_THREADS, smem, st>>>(mlp->hidden, (const T*)mlp->W1, (const T*)mlp->b1, (const T*)mlp->W2, Q, X, dO, part, w.NP, w.tps);
+        }
+        KC_CHECK_LAUNCH("kc_train_bwd_kernel");
+    }
+    const int splits = Q > 0 ? w.splits : 0;
+    kc_train_reduce_kernel<T><<<(unsigned)((w.NP + 255) / 256), 256, 0, st>>>(part, splits, w.NP, mlp->hidden, in_dim, (T*)gW1, (T*)gb1,
+                                                                            (T*)gW2, (T*)gb2, lossp, Q > 0 ? w.nfwd : 0, loss);
+    KC_CHECK_LAUNCH("kc_train_reduce_kernel");
+    return KC_OK;
+}
+
+extern "C" int kc_train_step(int dtype, const kc_rod_params* P, const kc_mlp* mlp, int64_t B, int64_t T_, int32_t K,
+                             const int32_t* key_idx_host, const void* traj, const void* controls, double* loss, void* gW1,
+                             void* gb1, void* gW2, void* gb2, void* pred, void* workspace, int64_t workspace_bytes,
+                             void* stream) {
+    KC_CHECK_ARG(dtype == KC_F32 || dtype == KC_F64, "dtype must be KC_F32 or KC_F64");
+    KC_CHECK_ARG(P && P->N >= 2, "rod params missing or N < 2");
+    KC_CHECK_ARG(mlp, "kc_train_step needs the MLP (use_nn)");
+    int rc = kc_check_mlp(mlp);
+    if (rc) return rc;
+    KC_CHECK_ARG(B >= 0 && T_ >= 2, "B must be >= 0 and T >= 2");
+    KC_CHECK_ARG(K >= 1 && K <= 64 && key_idx_host, "1 <= K <= 64 and key_idx_host non-NULL");
+    KC_CHECK_ARG(loss && gW1 && gb1 && gW2 && gb2 && workspace, "NULL output/workspace pointer");
+    KC_CHECK_ARG(B == 0 || (traj && controls), "NULL traj/controls");
+    const int64_t need = kc_train_step_workspace_bytes(dtype, mlp, B, T_, K);
+    if (workspace_bytes < need) {
+        kc_set_error("workspace too small: %lld < %lld", (long long)workspace_bytes, (long long)need);
+        return KC_ENOSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == KC_F32)
+        return train_typed<float>(P, mlp, B, T_, K, key_idx_host, traj, controls, loss, gW1, gb1, gW2, gb2, pred, workspace, st);
+    return train_typed<double>(P, mlp, B, T_, K, key_idx_host, traj, controls, loss, gW1, gb1, gW2, gb2, pred, workspace, st);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Adam + clamp
+// ---------------------------------------------------------------------------------------------------------------
 // torch.optim.Adam semantics (L2 weight decay added to the gradient, bias-corrected moments,
 // denom = sqrt(v)/sqrt(1-beta2^t) + eps) followed by the reference's clamp(min=0) of Linear weights
 // (physics_train.py:199,296-304).
@@ -46,17 +446,4 @@ extern "C" int kc_adam_clamp(int dtype, int64_t n, void* param, const void* grad
     return KC_OK;
 }
 
-// ---- placeholders until the fused kernels land (next commit) ----
-extern "C" int64_t kc_ode_bwd_workspace_bytes(int, const kc_mlp*, int64_t) { return 0; }
-extern "C" int kc_ode_bwd(int, const kc_rod_params*, const kc_mlp*, int64_t, const void*, const void*, const void*,
-                          const void*, const void*, const void*, void*, void*, void*, void*, void*, void*, void*, void*,
-                          void*, int64_t, void*) {
-    kc_set_error("kc_ode_bwd: not built yet");
-    return KC_EINVAL;
-}
-extern "C" int64_t kc_train_step_workspace_bytes(int, const kc_mlp*, int64_t, int64_t, int32_t) { return 0; }
-extern "C" int kc_train_step(int, const kc_rod_params*, const kc_mlp*, int64_t, int64_t, int32_t, const int32_t*,
-                             const void*, const void*, double*, void*, void*, void*, void*, void*, void*, int64_t, void*) {
-    kc_set_error("kc_train_step: not built yet");
-    return KC_EINVAL;
-}
+#include "kc_ode_bwd.inl"

@@ -1,0 +1,114 @@
+"""setup_robot / simulate — drop-in for knode_cosserat/knode.py, with the time rollout on the GPU.
+
+`simulate(robot, ctl)` keeps the reference signature and return layout (float64 [T,50,N]; index 0 = initial state, the
+step driven by the last control is dropped, rows 25:50 = yh, zh — knode.py:55-102) but runs ONE launch of the batched
+rollout kernel instead of T calls of scipy.optimize.fsolve around a Python march; a 3-D `ctl` [B,T,4] rolls out B
+independent rods at once and returns [B,T,50,N].  The shooting solve is a quasi-Newton iteration converged to 1e-11
+(fp64), i.e. tighter than the reference's hybrd default (xtol 1.49e-8); `use_fsolve` is accepted and irrelevant.
+"""
+import numpy as np
+import torch
+
+import _kc
+import _ops
+from cosserat_ode import CosseratRod
+
+
+def setup_robot(robot, mod=None, original=False):
+    """Set up robot based on experimental parameters (knode.py:6-53)."""
+    if original:
+        raise Exception("--original parameter no longer supported")
+    # Measured on the robot (:11-20)
+    robot.del_t = 0.05
+    robot.L = 0.635
+    robot.tendon_offset = 0.04445
+    robot.r = 0.003175
+    robot.rho = 1411.6751
+    robot.E = 2.757903e9
+    Bbt = 3e-2
+    if mod is None:
+        pass
+    elif mod == 'noair':
+        if isinstance(robot, CosseratRod):
+            robot.C = np.array([0, 0, 0])
+        else:
+            robot.C = torch.tensor([0, 0, 0], device=robot.device)
+    elif mod == 'nsw':
+        if isinstance(robot, CosseratRod):
+            robot.g = np.array([0, 0, 0])
+        else:
+            robot.g = torch.tensor([0, 0, 0], device=robot.device)
+    elif mod == 'short':
+        robot.L = 0.4
+    elif mod == 'damping':
+        Bbt = 0.2
+    elif mod == 'dampstiff':
+        Bbt = 0.2
+        robot.E = 10e9
+    elif mod == 'lengthstiff':
+        robot.L = 0.4
+        robot.E = 10e9
+    elif mod == 'youngs':
+        robot.E = 10e9
+    else:
+        raise Exception('Unknown mod ' + mod)
+    if isinstance(robot, CosseratRod):
+        robot.Bbt = np.diag([Bbt, Bbt, Bbt])
+    else:
+        robot.Bbt = torch.diag(torch.tensor([Bbt, Bbt, Bbt], device=robot.device))
+    robot.compute_intermediate_terms()
+
+
+def _initial_state(robot_reference, B):
+    """Straight rod (knode.py:58-64), float64 host arrays [B,19,N], [B,6,N]."""
+    N = robot_reference.N
+    y = np.vstack([np.zeros((2, N)), np.linspace(0, robot_reference.L, N), np.ones((1, N)), np.zeros((15, N))])
+    z = np.vstack([np.zeros((2, N)), np.ones((1, N)), np.zeros((3, N))])
+    return np.broadcast_to(y, (B, 19, N)).copy(), np.broadcast_to(z, (B, 6, N)).copy()
+
+
+def _robot_mlp(robot, dtype):
+    if isinstance(robot, CosseratRod):
+        return robot._mlp(dtype)
+    return robot._mlp()  # CosseratRodTorch
+
+
+def simulate(robot, ctl, robot_reference=None, *, dtype=np.float64, rows=50, tol=0.0, max_iter=0, return_info=False,
+             pinned_out=None):
+    """Roll the rod out under the tendon tensions `ctl` ([T,4] -> [T,rows,N]; [B,T,4] -> [B,T,rows,N]).
+
+    Keyword-only extensions (not in the reference): dtype (np.float64 | np.float32 arithmetic and output), rows (50 =
+    reference layout, 25 = [y;z] only), tol / max_iter of the shooting solve, return_info -> (traj, G[..,T,6],
+    marches[..,T]), pinned_out = a pinned host torch tensor to receive the result (avoids an allocation per call).
+    """
+    if robot_reference is None:
+        robot_reference = robot
+    if not torch.cuda.is_available():
+        raise RuntimeError("knode-cosserat_b200 has no CPU fallback: simulate() needs a CUDA device")
+    dev = torch.device("cuda", torch.cuda.current_device())
+    tdt = torch.float64 if np.dtype(dtype) == np.float64 else torch.float32
+    ctl_np = np.asarray(ctl, dtype=np.float64)
+    single = ctl_np.ndim == 2
+    if single:
+        ctl_np = ctl_np[None]
+    B, T, _ = ctl_np.shape
+    # the reference leaves the last applied tensions on the robot (knode.py:71)
+    robot.tendon_tensions = np.array(ctl_np[-1, -1]).astype(np.float64) if T > 0 else robot.tendon_tensions
+    y0, z0 = _initial_state(robot_reference, B)
+    P = _kc.rod_params(robot)
+    mlp = _robot_mlp(robot, tdt)
+    tens = torch.as_tensor(ctl_np).to(dev, tdt, non_blocking=True)
+    traj, G, iters = _ops.rollout(P, mlp, tens, torch.as_tensor(y0).to(dev, tdt), torch.as_tensor(z0).to(dev, tdt),
+                                  tol=tol, max_iter=max_iter, rows=rows, want_G=return_info)
+    if pinned_out is not None:
+        pinned_out.copy_(traj, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        out = pinned_out.numpy()
+    else:
+        out = traj.cpu().numpy()
+    if single:
+        out = out[0]
+    if return_info:
+        Gn, itn = G.cpu().numpy(), iters.cpu().numpy()
+        return (out, Gn[0], itn[0]) if single else (out, Gn, itn)
+    return out

@@ -1,0 +1,162 @@
+"""GPU parity of the training-step kernels (kc_train_step, kc_adam_clamp, kc_ode_bwd) through the C ABI, against the
+reference's own autograd results (tests/golden/train.npz, ode.npz) and the numpy oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import rod_oracle as O
+
+pytestmark = pytest.mark.gpu
+PK = ("W1", "b1", "W2", "b2")
+
+
+@pytest.fixture(scope="module")
+def ops():
+    import _kc
+    import _ops
+    assert torch.cuda.is_available()
+    _kc.lib()
+    return _ops
+
+
+def params(P):
+    import _kc
+    return _kc.rod_params(P)
+
+
+def P_setup(mod=None):
+    return O.setup_params(O.RodParams(), mod)
+
+
+def dev(a, dt):
+    return torch.tensor(np.asarray(a), dtype=dt, device="cuda")
+
+
+CASES = [("none", None, [3, 5, 7, 9], 3, "none_fast"), ("youngs", "youngs", [3, 5, 7, 9], 3, "youngs_fast"),
+         ("slow", None, [2, 6, 9], 2, "slow"), ("segment", "classdefault", [1, 3, 6, 9], 2, "segment")]
+
+
+@pytest.mark.parametrize("dt", [torch.float64, torch.float32])
+@pytest.mark.parametrize("tag,mod,key,ntraj,prefix", CASES)
+def test_train_step_vs_reference_autograd(ops, golden, dt, tag, mod, key, ntraj, prefix):
+    """loss and dW of one full-batch step: the reference computed them in fp32 with torch.autograd."""
+    d = golden["train"]
+    traj = d["traj"].astype(np.float32)[:ntraj]
+    ctl = d["controls"].astype(np.float32)[:ntraj]
+    P = O.RodParams() if mod == "classdefault" else P_setup(mod)
+    mlp = ops.Mlp(*[dev(d[f"{tag}_init_{k}"], dt) for k in PK])
+    loss, grads, pred = ops.train_step(params(P), mlp, dev(traj, dt), dev(ctl, dt), key, want_pred=True)
+    ref_loss = float(d[f"{prefix}_loss"])
+    assert abs(float(loss.item()) - ref_loss) < 3e-5 * abs(ref_loss)
+    for k, g in zip(PK, grads):
+        ref = d[f"{prefix}_grad_{k}"]
+        assert np.max(np.abs(g.cpu().numpy() - ref)) < 1e-4 * np.abs(ref).max(), k
+    # and against the fp64 oracle on the same fp32-rounded inputs (tight in fp64)
+    mlp_np = {k: d[f"{tag}_init_{k}"].astype(np.float64) for k in PK}
+    o_loss, o_grads, o_pred = O.teacher_forced_loss_and_grads(P, traj.astype(np.float64), ctl.astype(np.float64), key, mlp_np)
+    tol = 1e-9 if dt == torch.float64 else 1e-4
+    assert abs(float(loss.item()) - o_loss) < tol * abs(o_loss)
+    for k, g in zip(PK, grads):
+        assert np.max(np.abs(g.cpu().numpy() - o_grads[k])) < tol * np.abs(o_grads[k]).max(), k
+    pr = pred.cpu().numpy().astype(np.float64)
+    scale = np.abs(o_pred).max((0, 1, 3), keepdims=True) + 1e-6
+    assert np.max(np.abs(pr - o_pred) / scale) < tol
+    if prefix.endswith("fast"):
+        ref = d[f"{tag}_fast_grow_trajs0"].astype(np.float64)
+        assert np.max(np.abs(pr[0] - ref) / scale[0]) < 1e-4
+
+
+@pytest.mark.parametrize("dt", [torch.float64, torch.float32])
+def test_train_step_history_inputs_and_odd_hidden(ops, golden, dt):
+    """nn_input_history (53 inputs) and a hidden width that is not a multiple of the CTA's 32-unit chunk."""
+    rng = np.random.default_rng(3)
+    P = P_setup()
+    d = golden["train"]
+    traj = d["traj"][1:3, :9].astype(np.float32).astype(np.float64)
+    ctl = d["controls"][1:3, :9].astype(np.float32).astype(np.float64)
+    for in_dim, H in ((53, 40), (28, 70)):
+        mlp_np = {"W1": np.abs(rng.normal(0.01, 0.01, (H, in_dim))) * (0.05 if in_dim == 53 else 1.0),
+                  "b1": rng.normal(0, 0.01, H), "W2": np.abs(rng.normal(0.01, 0.01, (25, H))), "b2": rng.normal(0, 0.01, 25)}
+        o_loss, o_grads, _ = O.teacher_forced_loss_and_grads(P, traj, ctl, [1, 4, 9], mlp_np, nn_input_history=in_dim == 53)
+        mlp = ops.Mlp(*[dev(mlp_np[k], dt) for k in PK])
+        loss, grads, _ = ops.train_step(params(P), mlp, dev(traj, dt), dev(ctl, dt), [1, 4, 9])
+        tol = 1e-9 if dt == torch.float64 else 2e-4
+        assert abs(float(loss.item()) - o_loss) < tol * abs(o_loss)
+        for k, g in zip(PK, grads):
+            assert np.max(np.abs(g.cpu().numpy() - o_grads[k])) < tol * np.abs(o_grads[k]).max(), (in_dim, k)
+
+
+def test_adam_clamp_two_steps_vs_torch_optim(ops, golden):
+    """Two optimiser steps of physics_train.py:393-408 (Adam lr 1e-2 + clamp), weights compared with the reference's."""
+    d = golden["train"]
+    dt = torch.float32
+    P = P_setup()
+    traj, ctl = dev(d["traj"].astype(np.float32), dt), dev(d["controls"].astype(np.float32), dt)
+    W = [dev(d[f"none_init_{k}"], dt) for k in PK]
+    m = [torch.zeros_like(w) for w in W]
+    v = [torch.zeros_like(w) for w in W]
+    for step in (1, 2):
+        loss, grads, _ = ops.train_step(params(P), ops.Mlp(*W), traj, ctl, [3, 5, 7, 9])
+        for i, k in enumerate(PK):
+            ops.adam_clamp(W[i], grads[i], m[i], v[i], step, lr=1e-2, clamp=k in ("W1", "W2"))
+        for i, k in enumerate(PK):
+            ref = d[f"none_fast_step{step}_{k}"]
+            assert np.max(np.abs(W[i].cpu().numpy() - ref)) < 2e-4 * max(np.abs(ref).max(), 1e-2), (step, k)
+    assert abs(float(loss.item()) - float(d["none_fast_loss2"])) < 5e-3 * float(d["none_fast_loss2"])
+    # weight decay 0.1 (train_segment.py:118-120)
+    W = [dev(d[f"segment_init_{k}"], dt) for k in PK]
+    m = [torch.zeros_like(w) for w in W]
+    v = [torch.zeros_like(w) for w in W]
+    loss, grads, _ = ops.train_step(params(O.RodParams()), ops.Mlp(*W), traj[:2], ctl[:2], [1, 3, 6, 9])
+    for i, k in enumerate(PK):
+        ops.adam_clamp(W[i], grads[i], m[i], v[i], 1, lr=1e-2, weight_decay=0.1, clamp=k in ("W1", "W2"))
+        ref = d[f"segment_step1_{k}"]
+        assert np.max(np.abs(W[i].cpu().numpy() - ref)) < 2e-4 * max(np.abs(ref).max(), 1e-2), k
+
+
+@pytest.mark.parametrize("dt", [torch.float64, torch.float32])
+@pytest.mark.parametrize("tag", ["h512", "h64hist"])
+def test_ode_bwd_vs_reference_autograd(ops, golden, dt, tag):
+    """kc_ode_bwd against torch.autograd through the reference's ODE_parallel (fp64), inputs and parameters."""
+    d = golden["ode"]
+    mlp = ops.Mlp(*[dev(d[f"{tag}_{k}"], dt) for k in PK])
+    out = ops.ode_bwd(params(P_setup()), mlp, dev(d["y"], dt), dev(d["yh"], dt), dev(d["zh"], dt), dev(d["tf"], dt),
+                      dev(d[f"{tag}_cot_ys"], dt), dev(d[f"{tag}_cot_z"], dt))
+    tol = 1e-9 if dt == torch.float64 else 2e-4
+    for name, g in zip(["y", "yh", "zh", "tf", "W1", "b1", "W2", "b2"], out):
+        ref = d[f"{tag}_grad64_{name}"]
+        g = g.cpu().numpy().astype(np.float64)
+        if ref.ndim == 2 and name in ("y", "yh", "zh", "tf"):
+            scale = np.abs(ref).max(0, keepdims=True) + 1e-6 * np.abs(ref).max()
+            err = np.max(np.abs(g - ref) / scale)
+        else:
+            err = np.max(np.abs(g - ref)) / np.abs(ref).max()
+        assert err < tol, (name, err)
+
+
+def test_ode_bwd_physics_only_finite_difference(ops):
+    """Physics-only adjoint (dense user matrices, so the non-diagonal code path) against central differences."""
+    rng = np.random.default_rng(5)
+    P = P_setup()
+    P.Bse = 1e-3 * rng.standard_normal((3, 3))
+    P.Bbt = P.Bbt + 1e-3 * rng.standard_normal((3, 3))
+    P.compute_intermediate_terms()
+    Q = 9
+    y = rng.standard_normal((Q, 19)); y[:, 3] += 2.0
+    yh, zh, tf = rng.standard_normal((Q, 19)), rng.standard_normal((Q, 6)), rng.standard_normal((Q, 3))
+    cy, cz = rng.standard_normal((Q, 19)), rng.standard_normal((Q, 6))
+    dt = torch.float64
+    g = ops.ode_bwd(params(P), None, dev(y, dt), dev(yh, dt), dev(zh, dt), dev(tf, dt), dev(cy, dt), dev(cz, dt))
+
+    def f(y_, yh_, zh_, tf_):
+        a, b = O.ode(P, y_, yh_, zh_, tf_)
+        return np.sum(a * cy, 1) + np.sum(b * cz, 1)
+    args = [y, yh, zh, tf]
+    for ai, got in enumerate(g[:4]):
+        got = got.cpu().numpy()
+        for k in range(args[ai].shape[1]):
+            e = 1e-6
+            ap = [a.copy() for a in args]; am = [a.copy() for a in args]
+            ap[ai][:, k] += e; am[ai][:, k] -= e
+            fd = (f(*ap) - f(*am)) / (2 * e)
+            assert np.max(np.abs(fd - got[:, k])) < 1e-6 * (1 + np.abs(fd).max()), (ai, k)
