@@ -1,0 +1,126 @@
+"""Shared engine of the drop-in training scripts (physics_train.py, physics_multitrain.py, train_segment.py).
+
+The reference trains with a Python loop over trajectories x time steps x nodes of eager torch ops and autograd
+(physics_train.py:209-304 slow, :306-408 fast; train_segment.py:132-214).  Mathematically every epoch is ONE full-batch
+loss over all (trajectory, step, key node) samples, so here an epoch is: kc_train_step (fused forward + 4-term loss +
+reverse mode to the MLP weights) -> all-reduce of dW across ranks (only if torch.distributed is initialised) ->
+kc_adam_clamp per parameter tensor.  ReduceLROnPlateau and the bookkeeping stay on the host exactly as in the reference.
+"""
+import numpy as np
+import torch
+
+import _dist
+import _ops
+
+
+class PlateauLR:
+    """torch.optim.lr_scheduler.ReduceLROnPlateau('min', patience, factor) with its defaults (threshold 1e-4 rel,
+    cooldown 0, min_lr 0, eps 1e-8) — physics_train.py:206."""
+
+    def __init__(self, lr, patience=80, factor=0.5, threshold=1e-4, eps=1e-8):
+        self.lr, self.patience, self.factor, self.threshold, self.eps = lr, patience, factor, threshold, eps
+        self.best, self.bad = float("inf"), 0
+
+    def step(self, metric):
+        if metric < self.best * (1.0 - self.threshold):
+            self.best, self.bad = metric, 0
+        else:
+            self.bad += 1
+        if self.bad > self.patience:
+            new = self.lr * self.factor
+            if self.lr - new > self.eps:
+                self.lr = new
+            self.bad = 0
+        return self.lr
+
+    def get_last_lr(self):
+        return [self.lr]
+
+
+class TeacherForcedTrainer:
+    """Full-batch teacher-forced KNODE training on the GPU.
+
+    trajs: list of [T,25,N] tensors (or one [B,T,25,N]), controls: list of [T,4] (or [B,T,4]); all trajectories must
+    share T (they do in the reference: train_len).  Under torch.distributed each rank keeps only its shard of the
+    trajectories; weights stay bitwise identical on all ranks because every rank applies the same all-reduced gradient.
+    """
+
+    def __init__(self, robot, trajs, controls, key_pt_idx, lr=1e-2, weight_decay=0.0, clamp_weight=True,
+                 patience=80, factor=0.5):
+        self.robot = robot
+        self.rank, self.world = _dist.world_info()
+        traj = torch.stack(list(trajs)) if not torch.is_tensor(trajs) else trajs
+        ctl = torch.stack(list(controls)) if not torch.is_tensor(controls) else controls
+        self.n_total = traj.shape[0]
+        lo, hi = _dist.shard_range(self.n_total, self.rank, self.world)
+        self.traj = traj[lo:hi].detach().contiguous()
+        self.ctl = ctl[lo:hi].detach().to(self.traj.dtype).contiguous()
+        self.key = np.asarray(key_pt_idx).reshape(-1)
+        self.params = [p for p in robot.nn_models.parameters()]
+        self.exp_avg = [torch.zeros_like(p.data) for p in self.params]
+        self.exp_avg_sq = [torch.zeros_like(p.data) for p in self.params]
+        self.step_no = 0
+        self.weight_decay = weight_decay
+        self.clamp_weight = clamp_weight
+        self.sched = PlateauLR(lr, patience, factor)
+        self.loss_arr = []
+        # physics_train.py:301-304: every parameter whose name contains 'weight' is clamped (both Linear layers)
+        self.is_weight = ['weight' in n and 'layer1' not in n for n, _ in robot.nn_models.named_parameters()]
+
+    def loss_and_grads(self):
+        if self.traj.shape[0] > 0:
+            loss, grads, _ = self.robot.teacher_forced_step(self.traj, self.ctl, self.key)
+            grads = [g for g in grads]
+            loss = loss.to(torch.float32) if self.world > 1 else loss
+        else:  # a rank without trajectories contributes zeros
+            grads = [torch.zeros_like(p.data) for p in self.params]
+            loss = torch.zeros(1, dtype=torch.float32, device=self.params[0].device)
+        if self.world > 1:
+            _dist.allreduce_sum_(grads + [loss])
+        return loss, grads
+
+    def step(self, train=True):
+        """One epoch of the reference loop: loss -> backward -> Adam -> scheduler -> clamp (physics_train.py:266-304)."""
+        loss, grads = self.loss_and_grads()
+        loss_val = float(loss.item())
+        self.loss_arr.append(loss_val)
+        if train:
+            self.step_no += 1
+            lr = self.sched.get_last_lr()[0]
+            for p, g, m, v, isw in zip(self.params, grads, self.exp_avg, self.exp_avg_sq, self.is_weight):
+                _ops.adam_clamp(p.data, g, m, v, self.step_no, lr=lr, weight_decay=self.weight_decay,
+                                clamp=self.clamp_weight and isw)
+                p.grad = g
+            self.sched.step(loss_val)
+        return loss_val
+
+    def optim_state_dict(self):
+        """Same shape as torch.optim.Adam.state_dict() so that checkpoints stay loadable by the reference's tooling."""
+        return {"state": {i: {"step": torch.tensor(float(self.step_no)), "exp_avg": m, "exp_avg_sq": v}
+                          for i, (m, v) in enumerate(zip(self.exp_avg, self.exp_avg_sq))},
+                "param_groups": [{"lr": self.sched.get_last_lr()[0], "betas": (0.9, 0.999), "eps": 1e-8,
+                                  "weight_decay": self.weight_decay, "params": list(range(len(self.params)))}]}
+
+
+def dtw_l1(a, b):
+    """Exact dynamic-time-warping distance with the L1 point distance — what fastdtw(a, b)[0] approximates with its
+    default radius=1 (physics_train.py:159, physics_multitrain.py:211).  a[Ta,d], b[Tb,d]."""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    if a.ndim == 1:
+        a, b = a[:, None], b[:, None]
+    cost = np.abs(a[:, None, :] - b[None, :, :]).sum(-1)
+    Ta, Tb = cost.shape
+    acc = np.full((Ta + 1, Tb + 1), np.inf)
+    acc[0, 0] = 0.0
+    for i in range(1, Ta + 1):
+        for j in range(1, Tb + 1):
+            acc[i, j] = cost[i - 1, j - 1] + min(acc[i - 1, j], acc[i, j - 1], acc[i - 1, j - 1])
+    return float(acc[Ta, Tb])
+
+
+def transplant(np_robot, torch_robot):
+    """Force the numpy-flavoured rod to use the torch MLP (physics_train.py:103-110,137-144)."""
+    nn_model = torch_robot.nn_models
+    np_robot.nn_model = nn_model
+    np_robot.param_ls = [layer.detach().cpu().numpy() for _, layer in nn_model.state_dict().items()]
+    np_robot.nn_path = 'whatever'  # Force the robot to use nn

@@ -1,0 +1,130 @@
+"""Train and evaluate multiple KNODE models — drop-in for knode_cosserat/physics_multitrain.py (same CLI).
+
+The reference fans {dataset} x {mod} x {seed} out as physics_train.py subprocesses, two at a time, and scrapes their
+stdout (physics_multitrain.py:85-157); then rolls every saved model out with numpy + fsolve and prints a DTW / pos+Euler
+MSE table against the physics-only baseline (:169-233).  Here the jobs are independent replicas: under torchrun each
+rank takes every world-th job on its own GPU (no collective); a plain run executes them in-process one after the other.
+The evaluation rollouts of one job (all eval sets) are one batched GPU launch.
+"""
+import argparse
+import os
+
+import numpy as np
+import torch
+
+import _dist
+import physics_train
+from _train import dtw_l1
+from cosserat_ode import CosseratRod
+from knode import setup_robot, simulate
+from physics_controls import calc_controls
+
+MODS = ['nsw', 'short', 'youngs', 'lengthstiff']  # physics_multitrain.py:68-76
+SPACE = 40
+
+
+def build_parser():
+    parser = argparse.ArgumentParser(description='Train and Evaluate Multiple Models.')
+    parser.add_argument('--train', action=argparse.BooleanOptionalAction, default=True)
+    parser.add_argument('--eval', action=argparse.BooleanOptionalAction, default=True)
+    parser.add_argument('--original', action=argparse.BooleanOptionalAction, default=False, help="use original parameters")
+    parser.add_argument('--epochs', type=int, default=1000)
+    parser.add_argument('--fast', action=argparse.BooleanOptionalAction, default=False,
+                        help="use fast but inaccurate training")
+    parser.add_argument('--n_seeds', type=int, default=1)
+    parser.add_argument('--save_dir', type=str, default='saved_models')
+    return parser
+
+
+def split_list(a_list):
+    half = len(a_list) // 2
+    return a_list[:half], a_list[half:]
+
+
+def pct_error(new, old):
+    if old == 0:
+        return 0 if new == 0 else float('inf')
+    return (new - old) / old * 100
+
+
+def quat_to_euler_zyx(q):
+    """scipy Rotation.from_quat(q, scalar_first=True).as_euler('zyx') (physics_multitrain.py:216-217), q[n,4] wxyz."""
+    from scipy.spatial.transform import Rotation
+    return Rotation.from_quat(q[:, [1, 2, 3, 0]]).as_euler('zyx')
+
+
+def main(argv=None):
+    args = build_parser().parse_args(argv)
+    rank, world = _dist.world_info()
+    if 'WORLD_SIZE' in os.environ and int(os.environ['WORLD_SIZE']) > 1:
+        rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
+        torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', '0')))
+    if args.original:
+        raise Exception("--original parameter no longer supported")
+    datas = ['sine sine 0.5 1.0', 'sine sine random 0.5 1.0 0.0']   # physics_multitrain.py:43-46
+    eval_set = ['sine 1.5', 'step 1.5']                                # :62-65
+
+    if args.train:
+        jobs = [(d, m, s) for d in datas for m in MODS for s in range(args.n_seeds)]
+        for i, (data, mod, seed) in enumerate(jobs):
+            if i % world != rank:
+                continue
+            control_type, control_arg = split_list(data.split(' '))
+            argv_job = ['--verbose', '--no-eval', '--epochs', str(args.epochs), '--seed', str(seed), '--mod', mod,
+                        '--save_dir', args.save_dir]
+            if args.fast:
+                argv_job.append('--fast')
+            print(f'[rank {rank}] training {data};{mod};{seed}')
+            physics_train.main(argv_job + [*control_type, *control_arg], distributed=False)
+
+    if args.eval and rank == 0:
+        robot_reference = CosseratRod(use_fsolve=True)
+        setup_robot(robot_reference)
+        ctl_eval = np.array([calc_controls(e.split(' ')[0], float(e.split(' ')[1]), robot_reference.del_t, 100)
+                             for e in eval_set])
+        ref = simulate(robot_reference, ctl_eval)[:, :, :25]  # one batched launch for all eval sets
+        print(' ' * SPACE, end='')
+        for e in eval_set:
+            print((';' + e + ' DTW').ljust(20), end='')
+            print((';' + e + ' PQ MSE').ljust(20), end='')
+        print()
+        os.makedirs('evals', exist_ok=True)
+        baselines = {}
+        for data in [None, *datas]:
+            for mod in MODS:
+                for seed in range(args.n_seeds):
+                    if data is None:
+                        data_short = f'baseline {mod}'
+                        robot = CosseratRod(use_fsolve=True, nn_path=None)
+                    else:
+                        data_short = f'{data} {mod} {seed}'
+                        filename = '_'.join('-'.join(s).replace('.', '_') for s in split_list(data.split(' ')))
+                        nn_path = f'{args.save_dir}/physics_{filename}_{mod}_trainlen_30_{args.epochs}_epoch_{seed}.pth'
+                        robot = CosseratRod(use_fsolve=True, nn_path=nn_path)
+                    setup_robot(robot, mod)
+                    print(data_short.ljust(SPACE), end='')
+                    trajs = simulate(robot, ctl_eval)
+                    for k, evall in enumerate(eval_set):
+                        trajectory, interp = trajs[k], ref[k]
+                        fn = evall.replace(' ', '_') + '+' + data_short.replace(' ', '_')
+                        np.save(f'evals/physics_{fn}_trainlen_30_{args.epochs}_epochs.npy',
+                                {"tensions": ctl_eval[k], "reference": interp, "predicted": trajectory})
+                        dtw = dtw_l1(trajectory[:, :3, 9], interp[:, :3, 9])
+                        se_pos = (trajectory[:, :3] - interp[:, :3]).reshape((-1, 3)) ** 2
+                        eq = trajectory[:, 3:7].transpose((0, 2, 1)).reshape((-1, 4))
+                        rq = interp[:, 3:7].transpose((0, 2, 1)).reshape((-1, 4))
+                        se_euler = (quat_to_euler_zyx(eq) - quat_to_euler_zyx(rq)) ** 2
+                        mse = np.mean(np.concatenate([se_euler, se_pos])) * 1000
+                        if data is None:
+                            baselines[(evall, mod)] = {'dtw': dtw, 'mse': mse}
+                            print(';{0:.2f}'.format(dtw).ljust(20), end='')
+                            print(';{0:.2f}'.format(mse).ljust(20), end='')
+                        else:
+                            base = baselines[(evall, mod)]
+                            print(f';{dtw:.2f} ({pct_error(dtw, base["dtw"]):+.1f}%)'.ljust(20), end='')
+                            print(f';{mse:.2f} ({pct_error(mse, base["mse"]):+.1f}%)'.ljust(20), end='')
+                    print()
+
+
+if __name__ == "__main__":
+    main()

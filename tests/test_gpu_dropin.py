@@ -1,0 +1,231 @@
+"""GPU tests of the reference-shaped Python surface (cosserat_ode_torch, cosserat_ode, knode, physics_train,
+train_segment): the same calls the reference's scripts make, checked against the reference's own outputs."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+pytestmark = pytest.mark.gpu
+PK = ("W1", "b1", "W2", "b2")
+FIELDS = [(0, 3), (3, 7), (7, 10), (10, 13), (13, 16), (16, 19), (19, 22), (22, 25)]
+
+
+def field_err(a, b):
+    w = 0.0
+    for lo, hi in FIELDS:
+        s = max(float(np.abs(b[..., lo:hi, :]).max()), 1e-30)
+        w = max(w, float(np.abs(a[..., lo:hi, :] - b[..., lo:hi, :]).max()) / s)
+    return w
+
+
+def col_err(a, b, floor=1e-3):
+    scale = np.abs(b).reshape(-1, b.shape[-1]).max(0) + floor
+    return float(np.max(np.abs(a - b) / scale))
+
+
+def make_torch_robot(d, tag, H, hist=False, mod=None, setup=True):
+    from cosserat_ode_torch import CosseratRodTorch
+    from knode import setup_robot
+    r = CosseratRodTorch("cuda", H, nn_input_history=hist)
+    if setup:
+        setup_robot(r, mod)
+    sd = {"0.weight": d[f"{tag}_W1"], "0.bias": d[f"{tag}_b1"], "2.weight": d[f"{tag}_W2"], "2.bias": d[f"{tag}_b2"]}
+    r.nn_models.load_state_dict({k: torch.tensor(v) for k, v in sd.items()})
+    return r
+
+
+def cu(a, dt=torch.float32):
+    return torch.tensor(np.asarray(a), dtype=dt, device="cuda")
+
+
+def test_torch_class_ode_and_ode_parallel(golden):
+    d = golden["ode"]
+    r = make_torch_robot(d, "h512", 512)
+    y, yh, zh, tf = cu(d["y"]), cu(d["yh"]), cu(d["zh"]), cu(d["tf"])
+    with torch.no_grad():
+        ys, z = r.ODE_parallel(y, yh, zh, tf)
+        assert col_err(ys.cpu().numpy(), d["h512_par32_ys"]) < 1e-4 and col_err(z.cpu().numpy(), d["h512_par32_z"]) < 1e-4
+        a, b = r.ODE(y[7], yh[7], zh[7], tf[7])
+        assert a.shape == (19,) and b.shape == (6,)
+        assert col_err(a.cpu().numpy()[None], d["h512_ode32_ys"][7:8]) < 1e-4
+        r.use_nn = False
+        ys, z = r.ODE_parallel(y, yh, zh, tf)
+        assert col_err(ys.cpu().numpy(), d["h512_par32_nonn_ys"]) < 1e-4
+        r.use_nn = True
+        o = r.forward(torch.cat([y, z, tf], 1))
+        ref = nn.Sequential(*r.nn_models)(torch.cat([y, z, tf], 1))
+        assert torch.allclose(o, ref, rtol=1e-4, atol=1e-5)
+    # autograd through the custom op, in fp64 (inputs decide the dtype), against torch.autograd through the reference
+    t64 = [cu(d[k], torch.float64).requires_grad_(True) for k in ("y", "yh", "zh", "tf")]
+    ys, z = r.ODE_parallel(*t64)
+    s = (ys * cu(d["h512_cot_ys"], torch.float64)).sum() + (z * cu(d["h512_cot_z"], torch.float64)).sum()
+    gr = torch.autograd.grad(s, t64 + list(r.nn_models.parameters()))
+    for name, g in zip(["y", "yh", "zh", "tf", "W1", "b1", "W2", "b2"], gr):
+        ref = d[f"h512_grad64_{name}"]
+        assert np.max(np.abs(g.double().cpu().numpy() - ref)) / np.abs(ref).max() < 2e-5, name
+
+
+def test_torch_class_residual_and_segments(golden):
+    d, dt = golden["ode"], golden["train"]
+    r = make_torch_robot(d, "h512", 512)
+    r.y, r.z = cu(d["march_y0"]), cu(d["march_z0"])
+    r.residualArgs["yh"], r.residualArgs["zh"] = cu(d["march_yh"]), cu(d["march_zh"])
+    r.tendon_tensions = cu(d["march_tensions"])
+    total, full = r.getResidualEuler(cu(d["march_G"]))
+    assert field_err(full.cpu().numpy().astype(np.float64), d["tres32_full"].astype(np.float64)) < 1e-4
+    assert abs(float(total) - float(d["tres32_total"])) < 1e-4 * max(1.0, float(d["tres32_total"]))
+    assert field_err(np.concatenate([r.y.cpu().numpy(), np.zeros((6, 10))])[None][..., :19, :],
+                     np.concatenate([d["tres32_y"], np.zeros((6, 10))])[None][..., :19, :]) < 1e-4
+    # teacher-forced steps, no-grad (fused kernel) and grad (autograd composition) paths must agree with the reference
+    rs = make_torch_robot(dt, "slow_init", 512)
+    traj, ctl = cu(dt["traj"][0]), cu(dt["controls"][0])
+    t = 3
+    rs.tendon_tensions = ctl[t]
+    rs.residualArgs["yh"] = rs.c1 * traj[t, :19] + rs.c2 * traj[t - 1, :19]
+    rs.residualArgs["zh"] = rs.c1 * traj[t, 19:] + rs.c2 * traj[t - 1, 19:]
+    with torch.no_grad():
+        g0 = rs.getNextSegmentEuler(traj[t + 1])
+    g1 = rs.getNextSegmentEuler(traj[t + 1])
+    assert g1.requires_grad and not g0.requires_grad
+    for g in (g0, g1.detach()):
+        assert field_err(g.cpu().numpy().astype(np.float64), dt["slow_grow_traj_t3"].astype(np.float64)) < 1e-4
+    rf = make_torch_robot(dt, "none_init", 512)
+    ys, zs = traj[:29, :19], traj[:29, 19:]
+    args = {"yh": rf.c1 * ys + rf.c2 * torch.cat((ys[:1], ys[:-1])), "zh": rf.c1 * zs + rf.c2 * torch.cat((zs[:1], zs[:-1])),
+            "tendon_tensions": ctl[:29]}
+    with torch.no_grad():
+        p0 = rf.parallelGetNextSegmentEuler(traj[1:30], np.array([3, 5, 7, 9]), args)
+    p1 = rf.parallelGetNextSegmentEuler(traj[1:30], np.array([3, 5, 7, 9]), args)
+    for p in (p0, p1.detach()):
+        assert p.shape == (29, 25, 4)
+        assert field_err(p.cpu().numpy().astype(np.float64), dt["none_fast_grow_trajs0"].astype(np.float64)) < 1e-4
+
+
+def test_reference_slow_loop_runs_unchanged_on_the_dropin(golden):
+    """The loop body of physics_train.py:215-267, verbatim, against the drop-in class: loss and autograd gradients
+    must equal what the reference produced with its own class."""
+    from Utils.transformations import quaternion_to_euler
+    d = golden["train"]
+    robot = make_torch_robot(d, "slow_init", 512)
+    robot.use_nn = True
+    loss_func = nn.MSELoss()
+    batch_len = train_len = 30
+    trajs = [torch.tensor(t, requires_grad=True).float().to("cuda") for t in d["traj"][:2]]
+    ctls = [torch.tensor(c).float().to("cuda") for c in d["controls"][:2]]
+    epoch, grow_loss = 0, 0
+    for traj, controls in zip(trajs, ctls):
+        for stp_idx in range(batch_len - 1):
+            batch_idx = ((epoch % batch_len - 1) * batch_len + stp_idx + batch_len) % train_len
+            if batch_idx >= train_len - 1:
+                break
+            y, z = traj[batch_idx, 0:19, :], traj[batch_idx, 19:, :]
+            if stp_idx == 0:
+                y_prev, z_prev = y.clone().requires_grad_(True), z.clone().requires_grad_(True)
+            else:
+                y_prev, z_prev = traj[batch_idx - 1, 0:19, :], traj[batch_idx - 1, 19:, :]
+            robot.y, robot.z = y, z
+            G = torch.cat((traj[batch_idx + 1, :19, :], traj[batch_idx + 1, 19:, :])).clone().requires_grad_(True)
+            robot.tendon_tensions = controls[batch_idx]
+            robot.residualArgs["yh"] = robot.c1 * robot.y + robot.c2 * y_prev
+            robot.residualArgs["zh"] = robot.c1 * robot.z + robot.c2 * z_prev
+            grow_traj = robot.getNextSegmentEuler(G)
+            k = torch.tensor([2, 6, 9]).to("cuda")
+            grow_loss = grow_loss + loss_func(grow_traj[:3, k], traj[batch_idx + 1][:3, k]) + \
+                loss_func(grow_traj[7:19, k], traj[batch_idx + 1][7:19, k]) + \
+                loss_func(quaternion_to_euler(grow_traj[3:7, k]), quaternion_to_euler(traj[batch_idx + 1][3:7, k])) + \
+                loss_func(grow_traj[19:, k], traj[batch_idx + 1][19:, k - 1])
+    total_loss = grow_loss / (batch_len - 1)
+    total_loss.backward()
+    assert abs(total_loss.item() - float(d["slow_loss"])) < 3e-5 * float(d["slow_loss"])
+    for nm, p in zip(PK, robot.nn_models.parameters()):
+        ref = d[f"slow_grad_{nm}"]
+        assert np.max(np.abs(p.grad.cpu().numpy() - ref)) < 1e-4 * np.abs(ref).max(), nm
+
+
+def test_numpy_class_methods(golden):
+    from cosserat_ode import CosseratRod
+    from knode import setup_robot
+    d = golden["ode"]
+    r = CosseratRod(use_fsolve=True)
+    setup_robot(r)
+    ys, z = r.ODE(d["y"][3], d["yh"][3], d["zh"][3], d["tf"][3])
+    assert col_err(ys[None], d["np_none_ys"][3:4]) < 1e-9 and col_err(z[None], d["np_none_z"][3:4]) < 1e-9
+    r.tendon_tensions = d["march_tensions"]
+    y, z = d["march_y0"].copy(), d["march_z0"].copy()
+    res = r.getResidualEuler(d["march_G"], y, z, d["march_yh"], None, d["march_zh"], None)
+    np.testing.assert_allclose(res, d["march_res"], rtol=0, atol=1e-10)
+    assert field_err(np.concatenate([y, z])[None], np.concatenate([d["march_y"], d["march_z"]])[None]) < 1e-9  # in place
+    r.use_fsolve = False
+    y, z = d["march_y0"].copy(), d["march_z0"].copy()
+    assert abs(r.getResidualEuler(d["march_G"], y, z, d["march_yh"], None, d["march_zh"], None)
+               - float(np.sum(d["march_res"] ** 2))) < 1e-10
+    r.use_fsolve = True
+    y, z = d["march_y0"].copy(), d["march_z0"].copy()
+    np.testing.assert_allclose(r.getResidualRK4(d["march_G"], y, z, d["march_yh"], None, d["march_zh"], None),
+                               d["rk4_res"], rtol=0, atol=1e-10)
+    tr = make_torch_robot(d, "h512", 512)
+    x = np.random.default_rng(0).standard_normal(28)
+    out = r.get_nn_output(x, tr.nn_models, [d[f"h512_{k}"] for k in PK])
+    ref = nn.Sequential(*tr.nn_models).double()(torch.tensor(x, device="cuda")).detach().cpu().numpy()
+    np.testing.assert_allclose(out, ref, rtol=1e-9, atol=1e-11)
+
+
+def test_simulate_dropin(golden):
+    from _train import transplant
+    from cosserat_ode import CosseratRod
+    from knode import setup_robot, simulate
+    from physics_controls import calc_controls
+    d = golden["rollouts"]
+    r = CosseratRod(use_fsolve=True)
+    out = simulate(r, calc_controls('sine', 1.0, 0.005, 30))      # list input, class-default params
+    assert out.shape == (30, 50, 10) and out.dtype == np.float64
+    np.testing.assert_allclose(out[29, :3, -1], [-0.00639067, 0.02322316, 0.39909796], atol=5e-9)
+    assert field_err(out[:, :25], d["default_sine_traj"][:, :25]) < 1e-9
+    assert field_err(out[:, 25:], d["default_sine_traj"][:, 25:]) < 1e-8
+    r2 = CosseratRod(use_fsolve=True)
+    setup_robot(r2)
+    both = simulate(r2, np.stack([d["setup_sine_ctl"][:60], d["setup_step_ctl"]]))   # batched extension
+    assert both.shape == (2, 60, 50, 10)
+    np.testing.assert_allclose(both[0][10, :3, -1], [1.78365287e-01, -8.30740524e-05, 6.02770389e-01], atol=5e-9)
+    assert field_err(both[1][:, :25], d["setup_step_traj"][:, :25]) < 1e-9
+    np.testing.assert_allclose(r2.tendon_tensions, d["setup_step_ctl"][-1])
+    # KNODE evaluation path: torch MLP transplanted into the numpy rod (physics_train.py:136-158)
+    dk = golden["knode_rollouts"]
+    tr = make_torch_robot(dk, "h64", 64, mod="youngs")
+    r3 = CosseratRod(use_fsolve=True)
+    setup_robot(r3, "youngs")
+    transplant(r3, tr)
+    out, G, its = simulate(r3, dk["h64_ctl"], return_info=True)
+    assert its.min() >= 0 and field_err(out[:, :25], dk["h64_traj"][:, :25]) < 1e-9
+    f32 = simulate(r3, dk["h64_ctl"], dtype=np.float32, rows=25)
+    assert f32.dtype == np.float32 and field_err(f32.astype(np.float64), dk["h64_traj"][:, :25]) < 1e-4
+
+
+def test_physics_train_script_reproduces_reference_losses(golden, tmp_path, monkeypatch):
+    """python physics_train.py --fast --no-eval --epochs 1 sine sine random 0.5 1.0 0.0: epoch-0 and epoch-1 losses of
+    the reference (same seed, same data, Adam + clamp in between) and a loadable checkpoint."""
+    import physics_train
+    d = golden["train"]
+    monkeypatch.chdir(tmp_path)
+    robot, loss_arr = physics_train.main(["--fast", "--no-eval", "--epochs", "1", "--seed", "0", "sine", "sine",
+                                          "random", "0.5", "1.0", "0.0"], distributed=False)
+    assert abs(loss_arr[0] - float(d["none_fast_loss"])) < 1e-4 * float(d["none_fast_loss"])
+    assert abs(loss_arr[1] - float(d["none_fast_loss2"])) < 1e-2 * float(d["none_fast_loss2"])
+    ck = [f for f in os.listdir(tmp_path / "saved_models") if f.endswith(".pth")]
+    assert ck == ["physics_sine-sine-random_0_5-1_0-0_0_None_trainlen_30_1_epoch_0.pth"]
+    saved = torch.load(tmp_path / "saved_models" / ck[0], weights_only=False)
+    assert set(saved) == {"robot", "dtw", "loss", "optim"} and len(saved["loss"]) == 2
+    assert saved["robot"].nn_models[0].weight.min() >= 0          # clamp applied
+
+
+def test_train_segment_script_synthetic(tmp_path, monkeypatch):
+    import train_segment
+    monkeypatch.chdir(tmp_path)
+    robot, loss_arr = train_segment.main(["--synthetic", "--epochs", "3", "--train_len", "20", "--layers", "64",
+                                          "--save_path", str(tmp_path / "m.pth")])
+    assert len(loss_arr) == 3 and np.isfinite(loss_arr).all() and loss_arr[2] < loss_arr[0]
+    assert os.path.exists(tmp_path / "m.pth")
+    with pytest.raises(FileNotFoundError):
+        train_segment.main(["--epochs", "1"])
