@@ -76,8 +76,8 @@ def test_torch_class_residual_and_segments(golden):
     total, full = r.getResidualEuler(cu(d["march_G"]))
     assert field_err(full.cpu().numpy().astype(np.float64), d["tres32_full"].astype(np.float64)) < 1e-4
     assert abs(float(total) - float(d["tres32_total"])) < 1e-4 * max(1.0, float(d["tres32_total"]))
-    assert field_err(np.concatenate([r.y.cpu().numpy(), np.zeros((6, 10))])[None][..., :19, :],
-                     np.concatenate([d["tres32_y"], np.zeros((6, 10))])[None][..., :19, :]) < 1e-4
+    ynew = np.concatenate([r.y.cpu().numpy().astype(np.float64), np.ones((6, 10))])   # self.y is replaced (:359)
+    assert field_err(ynew, np.concatenate([d["tres32_y"].astype(np.float64), np.ones((6, 10))])) < 1e-4
     # teacher-forced steps, no-grad (fused kernel) and grad (autograd composition) paths must agree with the reference
     rs = make_torch_robot(dt, "slow_init", 512)
     traj, ctl = cu(dt["traj"][0]), cu(dt["controls"][0])
