@@ -44,10 +44,24 @@ template <typename T> KC_HD void kc_mtv(const T M[9], const T x[3], T r[3]) {  /
     r[2] = M[2] * x[0] + M[5] * x[1] + M[8] * x[2];
 }
 
+// 2/x.  fp32 on the device: MUFU.RCP + one Newton step (≈1 ulp) instead of the IEEE division sequence, whose slow-path
+// CALL splits the node evaluation's basic block in two and sits at the head of its critical path.
+KC_HD float kc_two_over(float x) {
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    r = fmaf(r, fmaf(-x, r, 1.0f), r);
+    return r + r;
+#else
+    return 2.0f / x;
+#endif
+}
+KC_HD double kc_two_over(double x) { return 2.0 / x; }
+
 // Eq(10) quaternion (w,x,y,z) -> rotation, NOT normalised (cosserat_ode_torch.py:157-161).
 template <typename T> KC_HD void kc_quat_R(const T h[4], T R[9]) {
     const T a = h[0], b = h[1], c = h[2], d = h[3];
-    const T s = T(2) / (a * a + b * b + c * c + d * d);
+    const T s = kc_two_over(a * a + b * b + c * c + d * d);
     R[0] = T(1) + s * (-c * c - d * d); R[1] = s * (b * c - d * a);        R[2] = s * (b * d + c * a);
     R[3] = s * (b * c + d * a);        R[4] = T(1) + s * (-b * b - d * d); R[5] = s * (c * d - b * a);
     R[6] = s * (b * d - c * a);        R[7] = s * (c * d + b * a);        R[8] = T(1) + s * (-b * b - c * c);

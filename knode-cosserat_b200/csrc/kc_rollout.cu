@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include "kc_rollout_core.cuh"
+#include "kc_rollout_wide.cuh"
 
 constexpr int KC_LS = 32;  // lane stride of every per-rod array (one warp-wide tile)
 
@@ -55,6 +56,125 @@ kc_rollout_kernel(const __grid_constant__ RodC<T> P, const MlpC<T> M, int64_t B,
                                         max_iter, fd_eps, Gout ? Gout + (size_t)b * T_ * 6 : nullptr,
                                         iters ? iters + (size_t)b * T_ : nullptr);
     for (int i = 0; i < KC_SHOOT_SLOTS; ++i) sb[(size_t)i * Bpad] = st.p[i * KC_LS];
+}
+
+// Wide mode: 4 rods per warp, 8 lanes per rod (see kc_rollout_wide.cuh).  Shared memory: history [N-1][NH][4].
+constexpr int KC_WG = 4;  // rods (lane groups) per warp
+template <typename T, bool DIAG, int IN, int NH>
+__global__ void __launch_bounds__(32)
+kc_rollout_wide_kernel(const __grid_constant__ RodC<T> P, const MlpC<T> M, int64_t B, int T_,
+                       const T* __restrict__ tensions, const T* __restrict__ y0, const T* __restrict__ z0, T* trajD,
+                       T tol, int max_iter, T fd_eps, T* Gout, int32_t* iters) {
+    extern __shared__ __align__(16) unsigned char kc_smem[];
+    const int N = P.N;
+    const int lane = threadIdx.x, g = lane >> 3, k = lane & 7;
+    const unsigned full = 0xffffffffu;
+    const int64_t b_raw = (int64_t)blockIdx.x * KC_WG + g;
+    const bool valid = b_raw < B;
+    const int64_t b = valid ? b_raw : B - 1;  // surplus groups shadow the last rod and never store
+    T* Hs = reinterpret_cast<T*>(kc_smem) + g;
+    T* traj_b = rod_base(trajD, b, T_, N);
+    const size_t tstride = (size_t)25 * N * KC_LS;
+    if (k == 0 && valid) {
+        rollout_init<T, KC_LS>(P, y0 ? y0 + (size_t)b * 19 * N : nullptr, z0 ? z0 + (size_t)b * 6 * N : nullptr, traj_b);
+        if (Gout) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) Gout[(size_t)b * T_ * 6 + i] = T(0);
+        }
+        if (iters) iters[(size_t)b * T_] = 0;
+    }
+    __syncwarp();
+    // cooperative history build H = c1*state[t] + c2*state[t-1] from the trajectory just written (L2 hits): the 8 lanes of
+    // a group split the slots; all loads of up to 4 nodes are issued before the first use so their latencies overlap.
+    auto build_hist = [&](const T* cur, const T* prev) {
+        constexpr int SPL = (NH + 7) / 8;  // slots per lane
+        for (int j0 = 0; j0 < N - 1; j0 += 4) {
+            T a[4][SPL], c[4][SPL];
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+#pragma unroll
+                for (int q = 0; q < SPL; ++q) {
+                    const int s = k + 8 * q, j = j0 + jj;
+                    const bool ok = s < NH && j < N - 1;
+                    const size_t o = ((size_t)(ok ? j : 0) * 25 + slot_row<NH>(ok ? s : 0)) * KC_LS;
+                    a[jj][q] = cur[o];
+                    c[jj][q] = prev[o];
+                }
+            }
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+#pragma unroll
+                for (int q = 0; q < SPL; ++q) {
+                    const int s = k + 8 * q, j = j0 + jj;
+                    if (s < NH && j < N - 1) Hs[(size_t)(j * NH + s) * KC_WG] = P.c1 * a[jj][q] + P.c2 * c[jj][q];
+                }
+            }
+        }
+    };
+    build_hist(traj_b, traj_b);
+    T zlast[6];  // z[:, N-1] is never written by the march: constant over the whole rollout (cosserat_ode.py:198-201)
+#pragma unroll
+    for (int c = 0; c < 6; ++c) zlast[c] = traj_b[((size_t)(N - 1) * 25 + 19 + c) * KC_LS];
+    __syncwarp();
+    T G[6], Gm1[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { G[i] = T(0); Gm1[i] = T(0); }
+    const T* ten = tensions + (size_t)b * T_ * 4;
+    T tn[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) tn[i] = ten[i];
+    for (int t = 0; t < T_ - 1; ++t) {
+        T tf[3];
+        tendon_force(P, tn, tf);
+        if (t + 1 < T_ - 1) {  // prefetch the next step's tensions: their latency hides behind this step's marches
+#pragma unroll
+            for (int i = 0; i < 4; ++i) tn[i] = ten[(size_t)(t + 1) * 4 + i];
+        }
+        T* nxt = traj_b + (size_t)(t + 1) * tstride;
+        T Gp[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) { Gp[i] = G[i]; G[i] = G[i] + (G[i] - Gm1[i]); }   // linear predictor
+        bool done = false;
+        int status = 0, marches = 0;
+        HistView<T, NH, KC_WG> H{Hs};
+        while (true) {
+            T eps[6], Ge[6], F[6];
+            wide_eps(G, fd_eps, eps);
+#pragma unroll
+            for (int i = 0; i < 6; ++i) Ge[i] = G[i] + ((k == i + 1) ? eps[i] : T(0));
+            const bool on = k == 0 && !done;
+            TrajSinkPred<T, KC_LS, NH, KC_WG> S{nxt, nullptr, on && valid, N - 1};
+            rod_march<T, DIAG, IN, NH>(P, M, Ge, tf, H, S, F);
+            T Fall[7][6];
+#pragma unroll
+            for (int c = 0; c < 7; ++c) {
+#pragma unroll
+                for (int i = 0; i < 6; ++i) Fall[c][i] = __shfl_sync(full, F[i], (lane & ~7) | c);
+            }
+            if (!done) {
+                ++marches;
+                const int r = wide_decide(Fall, G, eps, tol);
+                if (r != 0) { done = true; status = r; }
+                else if (marches >= max_iter) { done = true; status = -1; }
+            }
+            if (__all_sync(full, done)) break;
+        }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) Gm1[i] = Gp[i];
+        if (k == 0 && valid) {
+            const size_t o = (size_t)(N - 1) * 25 * KC_LS;
+#pragma unroll
+            for (int c = 0; c < 6; ++c) nxt[o + (19 + c) * KC_LS] = zlast[c];
+            if (Gout) {
+#pragma unroll
+                for (int i = 0; i < 6; ++i) Gout[((size_t)b * T_ + t + 1) * 6 + i] = G[i];
+            }
+            if (iters) iters[(size_t)b * T_ + t + 1] = status > 0 ? marches : -marches;
+        }
+        __syncwarp();
+        build_hist(nxt, nxt - tstride);
+        __syncwarp();
+    }
 }
 
 // trajD[tile][T][N][25][32] -> traj[B][T][rows][N].  One CTA = one (32-rod tile, time index): the slab is contiguous,
@@ -200,7 +320,36 @@ static int rollout_typed(const kc_rod_params* Pp, const kc_mlp* mlp, int64_t B, 
         if (e && atoi(e) >= 1 && atoi(e) <= 32) rpw = atoi(e);
     }
     const unsigned grid = (unsigned)((B + rpw - 1) / rpw);
+    // mode: wide (8 lanes per rod, Newton with a fresh FD Jacobian per joint march) while the 8x lanes still fit the
+    // chip's resident warps; narrow (one rod per lane, Broyden) beyond that.  KC_ROLLOUT_MODE=wide|narrow overrides.
+    bool wide = B * 8 <= (int64_t)148 * 4 * 32 * 2;  // <= 2 warps per scheduler (B <= 4736 on 148 SMs)
+    {
+        const char* e = getenv("KC_ROLLOUT_MODE");
+        if (e && e[0] == 'w') wide = true;
+        if (e && e[0] == 'n') wide = false;
+    }
     if (B > 0) {
+        if (wide) {
+            const size_t wsmem = (size_t)NH * (N - 1) * KC_WG * sizeof(T);
+            const unsigned wgrid = (unsigned)((B + KC_WG - 1) / KC_WG);
+#define KC_LAUNCH_WIDE(D, I, H)                                                                                        \
+    do {                                                                                                               \
+        auto kern = kc_rollout_wide_kernel<T, D, I, H>;                                                                \
+        if (wsmem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem);    \
+        kern<<<wgrid, 32, wsmem, st>>>(P, M, B, (int)T_, (const T*)tensions, (const T*)y0, (const T*)z0, trajD, tl,    \
+                                       max_iter, fd_eps, (T*)G_out, iters);                                            \
+    } while (0)
+            if (P.diag) {
+                if (in_dim == 0) KC_LAUNCH_WIDE(true, 0, 12);
+                else if (in_dim == 28) KC_LAUNCH_WIDE(true, 28, 12);
+                else KC_LAUNCH_WIDE(true, 53, 25);
+            } else {
+                if (in_dim == 0) KC_LAUNCH_WIDE(false, 0, 12);
+                else if (in_dim == 28) KC_LAUNCH_WIDE(false, 28, 12);
+                else KC_LAUNCH_WIDE(false, 53, 25);
+            }
+#undef KC_LAUNCH_WIDE
+        } else {
 #define KC_LAUNCH_ROLL(D, I, H)                                                                                        \
     do {                                                                                                               \
         auto kern = kc_rollout_kernel<T, D, I, H>;                                                                     \
@@ -209,16 +358,17 @@ static int rollout_typed(const kc_rod_params* Pp, const kc_mlp* mlp, int64_t B, 
                                           trajD, w.Bpad, state, 0, (int)T_ - 1, tl, max_iter, fd_eps, (T*)G_out,       \
                                           iters);                                                                      \
     } while (0)
-        if (P.diag) {
-            if (in_dim == 0) KC_LAUNCH_ROLL(true, 0, 12);
-            else if (in_dim == 28) KC_LAUNCH_ROLL(true, 28, 12);
-            else KC_LAUNCH_ROLL(true, 53, 25);
-        } else {
-            if (in_dim == 0) KC_LAUNCH_ROLL(false, 0, 12);
-            else if (in_dim == 28) KC_LAUNCH_ROLL(false, 28, 12);
-            else KC_LAUNCH_ROLL(false, 53, 25);
-        }
+            if (P.diag) {
+                if (in_dim == 0) KC_LAUNCH_ROLL(true, 0, 12);
+                else if (in_dim == 28) KC_LAUNCH_ROLL(true, 28, 12);
+                else KC_LAUNCH_ROLL(true, 53, 25);
+            } else {
+                if (in_dim == 0) KC_LAUNCH_ROLL(false, 0, 12);
+                else if (in_dim == 28) KC_LAUNCH_ROLL(false, 28, 12);
+                else KC_LAUNCH_ROLL(false, 53, 25);
+            }
 #undef KC_LAUNCH_ROLL
+        }
         KC_CHECK_LAUNCH("kc_rollout_kernel");
         if (rows == 0) return KC_OK;
         const int K = 25 * N;

@@ -20,7 +20,7 @@ def lib():
         so = os.path.join(HERE, "libkc_emul.so")
         src = os.path.join(HERE, "kc_emul.cpp")
         hdrs = [os.path.join(ROOT, "knode-cosserat_b200", "csrc", h) for h in
-                ("kc_common.cuh", "kc_rod.cuh", "kc_rollout_core.cuh")]
+                ("kc_common.cuh", "kc_rod.cuh", "kc_rollout_core.cuh", "kc_rollout_wide.cuh")]
         if not os.path.exists(so) or any(os.path.getmtime(f) > os.path.getmtime(so) for f in [src] + hdrs):
             subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", so, src])
         _lib = C.CDLL(so)
@@ -28,7 +28,7 @@ def lib():
     return _lib
 
 
-def rollout(P, ctl, dtype=np.float64, mlp=None, tol=0.0, max_iter=60):
+def rollout(P, ctl, dtype=np.float64, mlp=None, tol=0.0, max_iter=60, wide=False):
     """P: object with the derived rod attributes; ctl[B,T,4] -> traj[B,T,25,N], iters[B,T], G[B,T,6]."""
     ctl = np.ascontiguousarray(ctl, dtype=dtype)
     B, T, _ = ctl.shape
@@ -48,7 +48,7 @@ def rollout(P, ctl, dtype=np.float64, mlp=None, tol=0.0, max_iter=60):
     rc = lib().kc_emul_rollout(C.c_int(0 if dtype == np.float32 else 1), C.byref(p), C.c_int(in_dim), C.c_int(hidden),
                                *ptrs, C.c_int64(B), C.c_int64(T), ctl.ctypes.data_as(C.c_void_p),
                                traj.ctypes.data_as(C.c_void_p), iters.ctypes.data_as(C.c_void_p),
-                               G.ctypes.data_as(C.c_void_p), C.c_double(tol), C.c_int(max_iter))
+                               G.ctypes.data_as(C.c_void_p), C.c_double(tol), C.c_int(max_iter), C.c_int(1 if wide else 0))
     assert rc == 0
     # device layout per rod is [T][25*N] with k = row*N + node: already [T,25,N]
     return traj, iters, G

@@ -4,7 +4,7 @@
 // from the Python drop-ins.
 #include <vector>
 #include <cstring>
-#include "../../knode-cosserat_b200/csrc/kc_rollout_core.cuh"
+#include "../../knode-cosserat_b200/csrc/kc_rollout_wide.cuh"
 
 void kc_set_error(const char*, ...) {}
 
@@ -42,10 +42,59 @@ static void run(const RodC<T>& P, const MlpC<T>& M, int64_t B, int64_t T_, const
     }
 }
 
+// wide mode: the 7 lanes of a rod are emulated one after the other; the decision logic (wide_decide) is the kernel's
+template <typename T, bool DIAG, int IN, int NH>
+static void run_wide(const RodC<T>& P, const MlpC<T>& M, int64_t B, int64_t T_, const T* ten, T* traj, int32_t* iters,
+                     T* Gout, T tol, int max_iter, T fd_eps) {
+    const int N = P.N;
+    std::vector<T> trajD((size_t)T_ * 25 * N), Hs((size_t)NH * (N - 1)), scratch((size_t)25 * N);
+    for (int64_t b = 0; b < B; ++b) {
+        rollout_init<T, 1>(P, nullptr, nullptr, trajD.data());
+        if (iters) iters[b * T_] = 0;
+        build_history<T, NH, 1>(P, trajD.data(), trajD.data(), Hs.data());
+        T G[6] = {0, 0, 0, 0, 0, 0}, Gm1[6] = {0, 0, 0, 0, 0, 0};
+        const size_t ts = (size_t)25 * N;
+        for (int t = 0; t < T_ - 1; ++t) {
+            T tn[4], tf[3];
+            for (int i = 0; i < 4; ++i) tn[i] = ten[(b * T_ + t) * 4 + i];
+            tendon_force(P, tn, tf);
+            T* cur = trajD.data() + (size_t)t * ts;
+            T* nxt = cur + ts;
+            T Gp[6];
+            for (int i = 0; i < 6; ++i) { Gp[i] = G[i]; G[i] = G[i] + (G[i] - Gm1[i]); }
+            int marches = 0, status = 0;
+            HistView<T, NH, 1> H{Hs.data()};
+            while (true) {
+                T eps[6], Fall[7][6];
+                wide_eps(G, fd_eps, eps);
+                for (int k = 0; k < 7; ++k) {
+                    T Ge[6];
+                    for (int i = 0; i < 6; ++i) Ge[i] = G[i] + ((k == i + 1) ? eps[i] : T(0));
+                    TrajSinkPred<T, 1, NH, 1> S{nxt, nullptr, k == 0, N - 1};
+                    rod_march<T, DIAG, IN, NH>(P, M, Ge, tf, H, S, Fall[k]);
+                }
+                ++marches;
+                const int r = wide_decide(Fall, G, eps, tol);
+                if (r != 0) { status = r; break; }
+                if (marches >= max_iter) { status = -1; break; }
+            }
+            for (int i = 0; i < 6; ++i) Gm1[i] = Gp[i];
+            for (int c = 0; c < 6; ++c) nxt[((size_t)(N - 1) * 25 + 19 + c)] = cur[((size_t)(N - 1) * 25 + 19 + c)];
+            if (Gout) for (int i = 0; i < 6; ++i) Gout[(b * T_ + t + 1) * 6 + i] = G[i];
+            if (iters) iters[b * T_ + t + 1] = status > 0 ? marches : -marches;
+            build_history<T, NH, 1>(P, nxt, cur, Hs.data());
+        }
+        for (int64_t t = 0; t < T_; ++t)
+            for (int j = 0; j < N; ++j)
+                for (int r = 0; r < 25; ++r)
+                    traj[(((size_t)b * T_ + t) * 25 + r) * N + j] = trajD[((size_t)t * N + j) * 25 + r];
+    }
+}
+
 template <typename T>
 static int emul(const kc_rod_params* p, int in_dim, int hidden, const void* W1, const void* b1, const void* W2,
                 const void* b2, int64_t B, int64_t T_, const void* ten, void* traj, int32_t* iters, void* Gout,
-                double tol, int max_iter) {
+                double tol, int max_iter, int wide) {
     RodC<T> P = make_rodc<T>(*p);
     MlpC<T> M{};
     std::vector<T> Wp;
@@ -55,8 +104,12 @@ static int emul(const kc_rod_params* p, int in_dim, int hidden, const void* W1, 
         M.Wp = Wp.data(); M.b2 = (const T*)b2; M.in_dim = in_dim; M.inP = inP; M.hidden = hidden; M.stride = stride;
     }
     const T fd_eps = sizeof(T) == 4 ? T(1e-2) : T(1e-6);
-    const T tl = tol > 0 ? T(tol) : (sizeof(T) == 4 ? T(2e-6) : T(1e-12));
-#define GO(D, I, H) run<T, D, I, H>(P, M, B, T_, (const T*)ten, (T*)traj, iters, (T*)Gout, tl, max_iter, fd_eps)
+    const T tl = tol > 0 ? T(tol) : (sizeof(T) == 4 ? T(2e-6) : T(1e-11));
+#define GO(D, I, H)                                                                                             \
+    do {                                                                                                        \
+        if (wide) run_wide<T, D, I, H>(P, M, B, T_, (const T*)ten, (T*)traj, iters, (T*)Gout, tl, max_iter, fd_eps); \
+        else run<T, D, I, H>(P, M, B, T_, (const T*)ten, (T*)traj, iters, (T*)Gout, tl, max_iter, fd_eps);      \
+    } while (0)
     if (P.diag) { if (in_dim == 0) GO(true, 0, 12); else if (in_dim == 28) GO(true, 28, 12); else GO(true, 53, 25); }
     else        { if (in_dim == 0) GO(false, 0, 12); else if (in_dim == 28) GO(false, 28, 12); else GO(false, 53, 25); }
     return 0;
@@ -64,7 +117,7 @@ static int emul(const kc_rod_params* p, int in_dim, int hidden, const void* W1, 
 
 extern "C" int kc_emul_rollout(int dtype, const kc_rod_params* p, int in_dim, int hidden, const void* W1, const void* b1,
                                const void* W2, const void* b2, int64_t B, int64_t T_, const void* ten, void* traj,
-                               int32_t* iters, void* Gout, double tol, int max_iter) {
-    if (dtype == KC_F32) return emul<float>(p, in_dim, hidden, W1, b1, W2, b2, B, T_, ten, traj, iters, Gout, tol, max_iter);
-    return emul<double>(p, in_dim, hidden, W1, b1, W2, b2, B, T_, ten, traj, iters, Gout, tol, max_iter);
+                               int32_t* iters, void* Gout, double tol, int max_iter, int wide) {
+    if (dtype == KC_F32) return emul<float>(p, in_dim, hidden, W1, b1, W2, b2, B, T_, ten, traj, iters, Gout, tol, max_iter, wide);
+    return emul<double>(p, in_dim, hidden, W1, b1, W2, b2, B, T_, ten, traj, iters, Gout, tol, max_iter, wide);
 }

@@ -131,6 +131,15 @@ def test_segment_fwd(ops, golden, dt):
     assert field_err(got.cpu().numpy().astype(np.float64), want) < TOL[dt]
 
 
+@pytest.fixture(params=["narrow", "wide"])
+def mode(request, monkeypatch):
+    """Both rollout kernels: one rod per lane + Broyden ("narrow", large batches) and 8 lanes per rod + Newton with a
+    finite-difference Jacobian per joint march ("wide", small batches).  The launcher picks by batch size; the
+    environment knob forces one."""
+    monkeypatch.setenv("KC_ROLLOUT_MODE", request.param)
+    return request.param
+
+
 ROLLS = [("default_sine", "default", None), ("default_sine200", "default", None), ("setup_sine", "setup", None),
          ("setup_step", "setup", None), ("setup_random", "setup", None)] + \
         [(f"mod_{m}", "setup", m) for m in ["noair", "nsw", "short", "damping", "dampstiff", "lengthstiff", "youngs"]]
@@ -138,7 +147,7 @@ ROLLS = [("default_sine", "default", None), ("default_sine200", "default", None)
 
 @pytest.mark.parametrize("dt", [torch.float64, torch.float32])
 @pytest.mark.parametrize("name,kind,mod", ROLLS)
-def test_rollout_vs_reference_simulate(ops, golden, dt, name, kind, mod):
+def test_rollout_vs_reference_simulate(ops, golden, mode, dt, name, kind, mod):
     d = golden["rollouts"]
     P = O.RodParams() if kind == "default" else P_setup(mod)
     ctl = d[name + "_ctl"]
@@ -155,7 +164,7 @@ def test_rollout_vs_reference_simulate(ops, golden, dt, name, kind, mod):
 
 @pytest.mark.parametrize("dt", [torch.float64, torch.float32])
 @pytest.mark.parametrize("tag", ["h64", "h512", "h32hist"])
-def test_knode_rollout_vs_reference(ops, golden, dt, tag):
+def test_knode_rollout_vs_reference(ops, golden, mode, dt, tag):
     d = golden["knode_rollouts"]
     P = P_setup("youngs")
     traj, _, iters = ops.rollout(params(P), mlp_of(ops, d, tag, dt), dev(d[tag + "_ctl"][None], dt))
@@ -164,7 +173,7 @@ def test_knode_rollout_vs_reference(ops, golden, dt, tag):
 
 
 @pytest.mark.parametrize("dt", [torch.float64, torch.float32])
-def test_rollout_batch_ragged_and_edge_sizes(ops, dt):
+def test_rollout_batch_ragged_and_edge_sizes(ops, mode, dt):
     """B not a multiple of the warp, mixed tension families, T = 1 and B = 0."""
     rng = np.random.default_rng(7)
     P = P_setup()
@@ -181,7 +190,7 @@ def test_rollout_batch_ragged_and_edge_sizes(ops, dt):
     assert t0.shape == (0, T, 25, P.N)
 
 
-def test_rollout_full_size_properties(ops):
+def test_rollout_full_size_properties(ops, mode):
     """BASELINE config 2 (4096 rods x 100 steps, fp32): size-independent properties — every solve converged, the tip
     residual (free-end boundary condition) is ~0 at every step, duplicated inputs give bitwise-identical rods, and a
     sample of rods matches the fp64 oracle."""
