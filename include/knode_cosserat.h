@@ -143,6 +143,11 @@ int kc_adam_clamp(int dtype, int64_t n, void *param, const void *grad, void *exp
  * CUDA events on `stream`. */
 int kc_fma_peak(int dtype, int64_t iters, double *flops_host, void *scratch, void *stream);
 
+/* Tensor-core self-test (tcgen05.mma kind::tf32, accumulators in TMEM): D[128][N] = A[128][K] * B[N][K]^T in fp32 storage,
+ * one CTA.  Pins the operand layout / descriptor / TMEM read-back conventions that the fused KNODE MLP kernels rely on.
+ * N % 16 == 0 in [16, 256], K % 8 == 0. */
+int kc_umma_selftest(const void *A, const void *B, void *D, int32_t N, int32_t K, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

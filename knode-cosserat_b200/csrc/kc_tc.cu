@@ -1,0 +1,66 @@
+// kc_tc.cu — tensor-core (tcgen05 / TMEM) kernels.  Step 1: a self-test GEMM that pins down the operand layout,
+// descriptors and TMEM read-back used by the fused KNODE MLP kernels: D[128][N] = A[128][K] * B[N][K]^T (tf32, fp32 acc).
+#include <cuda_runtime.h>
+#include "kc_common.cuh"
+#include "kc_umma.cuh"
+
+__global__ void __launch_bounds__(128)
+kc_umma_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ D, int N, int K) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ uint32_t tmem_slot;
+    __shared__ __align__(8) uint64_t bar;
+    float* sA = reinterpret_cast<float*>(smem);                       // 128 x K, K-major interleaved
+    float* sB = reinterpret_cast<float*>(smem + (size_t)128 * K * 4);  // N x K
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint32_t ncols = 32;
+    while ((int)ncols < N) ncols <<= 1;
+    if (warp == 0) umma::tmem_alloc(&tmem_slot, ncols);
+    if (tid == 0) umma::mbar_init(&bar, 1);
+    for (int e = tid; e < 128 * K; e += 128) {
+        const int r = e / K, k = e - r * K;
+        *reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(sA) + umma::kmajor_off(r, k, K)) = A[e];
+    }
+    for (int e = tid; e < N * K; e += 128) {
+        const int r = e / K, k = e - r * K;
+        *reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(sB) + umma::kmajor_off(r, k, K)) = B[e];
+    }
+    umma::fence_async_smem();
+    umma::fence_before();
+    __syncthreads();
+    umma::fence_after();
+    const uint32_t tbase = tmem_slot;
+    if (tid == 0) {
+        const uint32_t idesc = umma::make_idesc_tf32(128, N);
+        const uint32_t sbo = (uint32_t)(K / 4) * 128;
+        for (int kk = 0; kk < K / 8; ++kk) {
+            const uint64_t da = umma::make_desc(umma::smem_u32(sA) + kk * 256, 128, sbo);
+            const uint64_t db = umma::make_desc(umma::smem_u32(sB) + kk * 256, 128, sbo);
+            umma::mma_tf32(tbase, da, db, idesc, kk > 0 ? 1u : 0u);
+        }
+        umma::commit(&bar);
+    }
+    umma::mbar_wait(&bar, 0);
+    umma::fence_after();
+    for (int c0 = 0; c0 < N; c0 += 32) {
+        uint32_t v[32];
+        umma::ld32(tbase + ((uint32_t)(warp * 32) << 16) + c0, v);
+        umma::wait_ld();
+        const int row = warp * 32 + lane;
+        for (int c = 0; c < 32 && c0 + c < N; ++c) D[(size_t)row * N + c0 + c] = __uint_as_float(v[c]);
+    }
+    umma::fence_before();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(tbase, ncols);
+}
+
+// D[128][N] = A[128][K] B[N][K]^T on the tensor cores; N % 16 == 0, 16 <= N <= 256, K % 8 == 0, (128+N)*K*4 <= 200 KB.
+extern "C" int kc_umma_selftest(const void* A, const void* B, void* D, int32_t N, int32_t K, void* stream) {
+    KC_CHECK_ARG(A && B && D, "NULL pointer");
+    KC_CHECK_ARG(N % 16 == 0 && N >= 16 && N <= 256 && K % 8 == 0 && K >= 8, "need N %% 16 == 0 in [16,256], K %% 8 == 0");
+    const size_t smem = (size_t)(128 + N) * K * 4;
+    KC_CHECK_ARG(smem <= 200 * 1024, "tile too large for shared memory");
+    cudaFuncSetAttribute(kc_umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kc_umma_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>((const float*)A, (const float*)B, (float*)D, N, K);
+    KC_CHECK_LAUNCH("kc_umma_selftest_kernel");
+    return KC_OK;
+}
