@@ -11,15 +11,16 @@ KC_HD void mlp_input_vjp(const MlpC<T>& M, const T* __restrict__ x, const T* __r
     for (int k = 0; k < IN; ++k) gx[k] = T(0);
     for (int i = 0; i < M.hidden; ++i) {
         const T* __restrict__ wrow = M.Wp + (size_t)i * M.stride;
-        T z1 = wrow[inP];
-#pragma unroll
-        for (int k = 0; k < IN; ++k) z1 += wrow[k] * x[k];
-        T da = T(0);
-#pragma unroll
-        for (int c = 0; c < 25; ++c) da += wrow[inP + 4 + c] * go[c];
+        const T z1 = mlp_unit_dot<T, IN>(wrow, x, wrow[inP]);
+        const T da = mlp_unit_dot<T, 25>(wrow + inP + 4, go, T(0));
         const T dz = da * kc_elu_grad(z1);
 #pragma unroll
-        for (int k = 0; k < IN; ++k) gx[k] += dz * wrow[k];
+        for (int k = 0; k < IN; k += 4) {
+            T w[4];
+            kc_ld4(wrow + k, w);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if (k + j < IN) gx[k + j] += dz * w[j];
+        }
     }
 }
 

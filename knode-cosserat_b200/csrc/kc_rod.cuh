@@ -148,20 +148,62 @@ KC_HD void rod_ode(const RodC<T>& P, const T* __restrict__ y, const T qh[3], con
     for (int i = 0; i < 3; ++i) { z[i] = v[i]; z[3 + i] = u[i]; }
 }
 
-// KNODE residual, SIMT form: o[25] = W2 ELU(W1 x + b1) + b2 with the packed weights of MlpC (uniform broadcast loads).
+// KNODE residual, SIMT form: o[25] = W2 ELU(W1 x + b1) + b2 with the packed weights of MlpC (uniform broadcast loads,
+// 16-byte vectors).  The 28/53-term dot product of a hidden unit is split over 4 partial sums so that it is not one serial
+// FMA chain, and two hidden units are in flight per iteration.
+// 4 consecutive values from a 16-byte aligned address as ONE 128-bit load (fp32) / two (fp64)
+KC_HD void kc_ld4(const float* __restrict__ p, float v[4]) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+KC_HD void kc_ld4(const double* __restrict__ p, double v[4]) {
+    const double2 a = *reinterpret_cast<const double2*>(p);
+    const double2 b = *reinterpret_cast<const double2*>(p + 2);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+// bias + sum_k wrow[k] x[k], wrow 16-byte aligned and readable up to the next multiple of 4 (padding is zero-filled or
+// multiplied by nothing: only k < IN is used); 4 partial sums break the serial FMA chain.
+template <typename T, int IN>
+KC_HD T mlp_unit_dot(const T* __restrict__ wrow, const T* __restrict__ x, T bias) {
+    T p[4] = {bias, T(0), T(0), T(0)};
+#pragma unroll
+    for (int k = 0; k < IN; k += 4) {
+        T w[4];
+        kc_ld4(wrow + k, w);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (k + j < IN) p[j] += w[j] * x[k + j];
+    }
+    return (p[0] + p[1]) + (p[2] + p[3]);
+}
+// o[0..25) += wcol[0..25) * a with 128-bit loads (wcol 16-byte aligned, 28 readable)
+template <typename T>
+KC_HD void mlp_unit_axpy(const T* __restrict__ wcol, T a, T* __restrict__ o) {
+#pragma unroll
+    for (int c = 0; c < 28; c += 4) {
+        T w[4];
+        kc_ld4(wcol + c, w);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (c + j < 25) o[c + j] += w[j] * a;
+    }
+}
 template <typename T, int IN>
 KC_HD void mlp_eval(const MlpC<T>& M, const T* __restrict__ x, T* __restrict__ o) {
 #pragma unroll
     for (int c = 0; c < 25; ++c) o[c] = M.b2[c];
     const int inP = (IN + 3) & ~3;
-    for (int i = 0; i < M.hidden; ++i) {
-        const T* __restrict__ wrow = M.Wp + (size_t)i * M.stride;
-        T acc = wrow[inP];
-#pragma unroll
-        for (int k = 0; k < IN; ++k) acc += wrow[k] * x[k];
-        const T a = kc_elu(acc);
-#pragma unroll
-        for (int c = 0; c < 25; ++c) o[c] += wrow[inP + 4 + c] * a;
+    int i = 0;
+    for (; i + 1 < M.hidden; i += 2) {
+        const T* __restrict__ w0 = M.Wp + (size_t)i * M.stride;
+        const T* __restrict__ w1 = w0 + M.stride;
+        const T a0 = kc_elu(mlp_unit_dot<T, IN>(w0, x, w0[inP]));
+        const T a1 = kc_elu(mlp_unit_dot<T, IN>(w1, x, w1[inP]));
+        mlp_unit_axpy<T>(w0 + inP + 4, a0, o);
+        mlp_unit_axpy<T>(w1 + inP + 4, a1, o);
+    }
+    for (; i < M.hidden; ++i) {
+        const T* __restrict__ w0 = M.Wp + (size_t)i * M.stride;
+        const T a0 = kc_elu(mlp_unit_dot<T, IN>(w0, x, w0[inP]));
+        mlp_unit_axpy<T>(w0 + inP + 4, a0, o);
     }
 }
 

@@ -14,6 +14,7 @@
 //                               shared-memory-tiled outer products; writes per-slice partials
 //   4. kc_train_reduce_kernel : deterministic sum of the partials into gW1, gb1, gW2, gb2 and of the loss partials
 #include <cuda_runtime.h>
+#include <algorithm>
 #include "kc_rod.cuh"
 #include "kc_adjoint.cuh"
 
@@ -84,15 +85,24 @@ kc_train_prep_kernel(const __grid_constant__ RodC<T> P, const __grid_constant__ 
 // ---------------------------------------------------------------------------------------------------------------
 // 2. forward + loss + dL/do
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int FWD_THREADS = 128;
+constexpr int FWD_THREADS = 512;
+// One sample per thread; the packed weights are staged in shared memory once per CTA (when they fit: 123 KB in fp32 at
+// H = 512) and read as 16-byte broadcasts; CTAs are persistent over tiles of FWD_THREADS samples.
 template <typename T, int IN>
-__global__ void __launch_bounds__(FWD_THREADS)
-kc_train_fwd_kernel(const MlpC<T> M, T ds, int64_t Q, int T_, int K, const T* __restrict__ X, int XP,
+__global__ void __launch_bounds__(FWD_THREADS, 1)
+kc_train_fwd_kernel(MlpC<T> M, int wp_in_smem, T ds, int64_t Q, int T_, int K, const T* __restrict__ X, int XP,
                     const T* __restrict__ PHYS, const T* __restrict__ TGT, T* __restrict__ dO,
                     double* __restrict__ loss_part, T* __restrict__ pred_out) {
-    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    extern __shared__ __align__(16) unsigned char kc_smem[];
+    if (wp_in_smem) {
+        T* sw = reinterpret_cast<T*>(kc_smem);
+        const int n = M.hidden * M.stride;
+        for (int e = threadIdx.x; e < n; e += FWD_THREADS) sw[e] = M.Wp[e];
+        __syncthreads();
+        M.Wp = sw;
+    }
     double my = 0.0;
-    if (q < Q) {
+    for (int64_t q = (int64_t)blockIdx.x * FWD_THREADS + threadIdx.x; q < Q; q += (int64_t)gridDim.x * FWD_THREADS) {
         T x[IN], o[25];
         const T* xr = X + (size_t)q * XP;
 #pragma unroll
@@ -128,7 +138,7 @@ kc_train_fwd_kernel(const MlpC<T> M, T ds, int64_t Q, int T_, int K, const T* __
         for (int r = 0; r < 25; ++r) go[r] = g[r];
 #pragma unroll
         for (int r = 25; r < 32; ++r) go[r] = T(0);
-        my = (double)acc;
+        my += (double)acc;
         if (pred_out) {  // pred[B][T-1][25][K]
             const int kk = (int)(q % K);
             const int64_t bt = q / K;
@@ -207,12 +217,8 @@ kc_train_bwd_kernel(int hidden, const T* __restrict__ W1, const T* __restrict__ 
             for (int c = 0; c < 25; ++c) g[c] = dOs[s * 32 + c];
 #pragma unroll 2
             for (int i = ib; i < ib + 16; ++i) {
-                T z1 = b1c[i];
-#pragma unroll
-                for (int k = 0; k < IN; ++k) z1 += W1c[i * XP + k] * x[k];
-                T da = T(0);
-#pragma unroll
-                for (int c = 0; c < 25; ++c) da += W2c[i * 28 + c] * g[c];
+                const T z1 = mlp_unit_dot<T, IN>(W1c + i * XP, x, b1c[i]);
+                const T da = mlp_unit_dot<T, 25>(W2c + i * 28, g, T(0));
                 As[s * (BWD_HC + 1) + i] = kc_elu(z1);
                 dZs[s * (BWD_HC + 1) + i] = da * kc_elu_grad(z1);
             }
@@ -222,16 +228,22 @@ kc_train_bwd_kernel(int hidden, const T* __restrict__ W1, const T* __restrict__ 
         for (int s = 0; s < BWD_TS; ++s) {
             const T dz = dZs[s * (BWD_HC + 1) + wi];
             if (wg < NG) {
+                T xv[4];
+                kc_ld4(Xs + s * XPG + wg * 4, xv);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) aW1a[k] += dz * Xs[s * XPG + wg * 4 + k];
+                for (int k = 0; k < 4; ++k) aW1a[k] += dz * xv[k];
             }
             if (NG > 8 && wg + 8 < NG) {
+                T xv[4];
+                kc_ld4(Xs + s * XPG + (wg + 8) * 4, xv);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) aW1b[k] += dz * Xs[s * XPG + (wg + 8) * 4 + k];
+                for (int k = 0; k < 4; ++k) aW1b[k] += dz * xv[k];
             }
             const T a = As[s * (BWD_HC + 1) + vi];
+            T gv[4];
+            kc_ld4(dOs + s * 32 + vc, gv);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) aW2[c] += dOs[s * 32 + vc + c] * a;
+            for (int c = 0; c < 4; ++c) aW2[c] += gv[c] * a;
             if (tid < BWD_HC) ab1 += dZs[s * (BWD_HC + 1) + tid];
             if (blockIdx.x == 0 && tid >= 32 && tid < 32 + 25) ab2 += dOs[s * 32 + tid - 32];
         }
@@ -296,7 +308,8 @@ static TrainWs train_ws(int dtype, const kc_mlp* mlp, int64_t Q) {
     w.Q = Q;
     w.XPG = mlp->in_dim == 28 ? 32 : 56;
     w.NP = (int64_t)mlp->hidden * mlp->in_dim + mlp->hidden + 25 * (int64_t)mlp->hidden + 25;
-    w.nfwd = (int)((Q + FWD_THREADS - 1) / FWD_THREADS);
+    w.nfwd = (int)std::min<int64_t>((Q + FWD_THREADS - 1) / FWD_THREADS, 148);
+    if (w.nfwd < 1) w.nfwd = 1;
     w.chunks = (mlp->hidden + BWD_HC - 1) / BWD_HC;
     const int64_t ntiles = (Q + BWD_TS - 1) / BWD_TS;
     // one resident wave of bwd CTAs: ~3 (fp32) / 1 (fp64) CTAs per SM on 148 SMs
@@ -350,10 +363,20 @@ static int train_typed(const kc_rod_params* Pp, const kc_mlp* mlp, int64_t B, in
         else { if (in_dim == 28) PREP(false, 28); else PREP(false, 53); }
 #undef PREP
         KC_CHECK_LAUNCH("kc_train_prep_kernel");
-        if (in_dim == 28)
-            kc_train_fwd_kernel<T, 28><<<w.nfwd, FWD_THREADS, 0, st>>>(M, P.ds, Q, (int)T_, K, X, w.XPG, PHYS, TGT, dO, lossp, (T*)pred);
-        else
-            kc_train_fwd_kernel<T, 53><<<w.nfwd, FWD_THREADS, 0, st>>>(M, P.ds, Q, (int)T_, K, X, w.XPG, PHYS, TGT, dO, lossp, (T*)pred);
+        {
+            const size_t wbytes = (size_t)M.hidden * M.stride * sizeof(T);
+            const int in_smem = wbytes <= 200 * 1024 ? 1 : 0;
+            const size_t fsmem = in_smem ? wbytes : 0;
+            if (in_dim == 28) {
+                auto k = kc_train_fwd_kernel<T, 28>;
+                if (fsmem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
+                k<<<w.nfwd, FWD_THREADS, fsmem, st>>>(M, in_smem, P.ds, Q, (int)T_, K, X, w.XPG, PHYS, TGT, dO, lossp, (T*)pred);
+            } else {
+                auto k = kc_train_fwd_kernel<T, 53>;
+                if (fsmem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
+                k<<<w.nfwd, FWD_THREADS, fsmem, st>>>(M, in_smem, P.ds, Q, (int)T_, K, X, w.XPG, PHYS, TGT, dO, lossp, (T*)pred);
+            }
+        }
         KC_CHECK_LAUNCH("kc_train_fwd_kernel");
         const size_t smem = bwd_smem_bytes(in_dim, sizeof(T));
         dim3 grid((unsigned)w.chunks, (unsigned)w.splits);
