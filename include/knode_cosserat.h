@@ -145,8 +145,10 @@ int kc_fma_peak(int dtype, int64_t iters, double *flops_host, void *scratch, voi
 
 /* Tensor-core self-test (tcgen05.mma kind::tf32, accumulators in TMEM): D[128][N] = A[128][K] * B[N][K]^T in fp32 storage,
  * one CTA.  Pins the operand layout / descriptor / TMEM read-back conventions that the fused KNODE MLP kernels rely on.
- * N % 16 == 0 in [16, 256], K % 8 == 0. */
-int kc_umma_selftest(const void *A, const void *B, void *D, int32_t N, int32_t K, void *stream);
+ * N % 16 == 0 in [16, 256], K % 8 == 0.  mode (mn_major) 0: tf32 operands, K-major; 1: tf32, MN-major (not a legal
+ * no-swizzle layout for tf32 - kept to document the failure); 2: bf16 operands, MN-major, K % 16 == 0.  Modes 0 and 2 are
+ * the two shared-memory layouts the fused kernels use. */
+int kc_umma_selftest(const void *A, const void *B, void *D, int32_t N, int32_t K, int32_t mn_major, void *stream);
 
 #ifdef __cplusplus
 }

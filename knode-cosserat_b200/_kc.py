@@ -58,7 +58,7 @@ _SIGNATURES = {
                                 C.POINTER(C.c_int32)] + [C.c_void_p] * 9 + [C.c_int64, C.c_void_p]),
     "kc_adam_clamp": (C.c_int, [C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                 C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int32, C.c_void_p]),
-    "kc_umma_selftest": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    "kc_umma_selftest": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "kc_fma_peak": (C.c_int, [C.c_int, C.c_int64, C.POINTER(C.c_double), C.c_void_p, C.c_void_p]),
 }
 

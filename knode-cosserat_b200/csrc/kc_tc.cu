@@ -3,9 +3,11 @@
 #include <cuda_runtime.h>
 #include "kc_common.cuh"
 #include "kc_umma.cuh"
+#include <cuda_bf16.h>
 
 __global__ void __launch_bounds__(128)
-kc_umma_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ D, int N, int K) {
+kc_umma_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ D, int N, int K,
+                        int mn_major) {
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ uint32_t tmem_slot;
     __shared__ __align__(8) uint64_t bar;
@@ -16,13 +18,17 @@ kc_umma_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B
     while ((int)ncols < N) ncols <<= 1;
     if (warp == 0) umma::tmem_alloc(&tmem_slot, ncols);
     if (tid == 0) umma::mbar_init(&bar, 1);
+    unsigned char* bA = reinterpret_cast<unsigned char*>(sA);
+    unsigned char* bB = bA + (mn_major == 2 ? (size_t)128 * K * 2 : (size_t)128 * K * 4);
     for (int e = tid; e < 128 * K; e += 128) {
         const int r = e / K, k = e - r * K;
-        *reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(sA) + umma::kmajor_off(r, k, K)) = A[e];
+        if (mn_major == 2) *reinterpret_cast<__nv_bfloat16*>(bA + umma::mnmajor_off_b16(r, k, K)) = __float2bfloat16(A[e]);
+        else *reinterpret_cast<float*>(bA + (mn_major ? umma::mnmajor_off(r, k, K) : umma::kmajor_off(r, k, K))) = A[e];
     }
     for (int e = tid; e < N * K; e += 128) {
         const int r = e / K, k = e - r * K;
-        *reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(sB) + umma::kmajor_off(r, k, K)) = B[e];
+        if (mn_major == 2) *reinterpret_cast<__nv_bfloat16*>(bB + umma::mnmajor_off_b16(r, k, K)) = __float2bfloat16(B[e]);
+        else *reinterpret_cast<float*>(bB + (mn_major ? umma::mnmajor_off(r, k, K) : umma::kmajor_off(r, k, K))) = B[e];
     }
     umma::fence_async_smem();
     umma::fence_before();
@@ -30,12 +36,23 @@ kc_umma_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B
     umma::fence_after();
     const uint32_t tbase = tmem_slot;
     if (tid == 0) {
-        const uint32_t idesc = umma::make_idesc_tf32(128, N);
-        const uint32_t sbo = (uint32_t)(K / 4) * 128;
-        for (int kk = 0; kk < K / 8; ++kk) {
-            const uint64_t da = umma::make_desc(umma::smem_u32(sA) + kk * 256, 128, sbo);
-            const uint64_t db = umma::make_desc(umma::smem_u32(sB) + kk * 256, 128, sbo);
-            umma::mma_tf32(tbase, da, db, idesc, kk > 0 ? 1u : 0u);
+        if (mn_major == 2) {  // bf16, both operands MN-major, K = 16 per instruction
+            const uint32_t idesc = umma::make_idesc_bf16(128, N, 1, 1);
+            const uint32_t sbo = (uint32_t)(K / 8) * 128;
+            for (int kk = 0; kk < K / 16; ++kk) {
+                const uint64_t da = umma::make_desc(umma::smem_u32(bA) + kk * 256, 128, sbo);
+                const uint64_t db = umma::make_desc(umma::smem_u32(bB) + kk * 256, 128, sbo);
+                umma::mma_bf16(tbase, da, db, idesc, kk > 0 ? 1u : 0u);
+            }
+        } else {
+            const uint32_t idesc = umma::make_idesc_tf32(128, N, mn_major, mn_major);
+            const uint32_t sbo = mn_major ? (uint32_t)(K / 8) * 128 : (uint32_t)(K / 4) * 128;
+            const uint32_t kstep = mn_major ? 128 : 256;  // bytes per K = 8
+            for (int kk = 0; kk < K / 8; ++kk) {
+                const uint64_t da = umma::make_desc(umma::smem_u32(bA) + kk * kstep, 128, sbo);
+                const uint64_t db = umma::make_desc(umma::smem_u32(bB) + kk * kstep, 128, sbo);
+                umma::mma_tf32(tbase, da, db, idesc, kk > 0 ? 1u : 0u);
+            }
         }
         umma::commit(&bar);
     }
@@ -54,13 +71,13 @@ kc_umma_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B
 }
 
 // D[128][N] = A[128][K] B[N][K]^T on the tensor cores; N % 16 == 0, 16 <= N <= 256, K % 8 == 0, (128+N)*K*4 <= 200 KB.
-extern "C" int kc_umma_selftest(const void* A, const void* B, void* D, int32_t N, int32_t K, void* stream) {
+extern "C" int kc_umma_selftest(const void* A, const void* B, void* D, int32_t N, int32_t K, int32_t mn_major, void* stream) {
     KC_CHECK_ARG(A && B && D, "NULL pointer");
-    KC_CHECK_ARG(N % 16 == 0 && N >= 16 && N <= 256 && K % 8 == 0 && K >= 8, "need N %% 16 == 0 in [16,256], K %% 8 == 0");
+    KC_CHECK_ARG(N % 16 == 0 && N >= 16 && N <= 256 && K % 8 == 0 && K >= 8 && (mn_major != 2 || K % 16 == 0), "need N %% 16 == 0 in [16,256], K %% 8 == 0 (16 for bf16)");
     const size_t smem = (size_t)(128 + N) * K * 4;
     KC_CHECK_ARG(smem <= 200 * 1024, "tile too large for shared memory");
     cudaFuncSetAttribute(kc_umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kc_umma_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>((const float*)A, (const float*)B, (float*)D, N, K);
+    kc_umma_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>((const float*)A, (const float*)B, (float*)D, N, K, mn_major);
     KC_CHECK_LAUNCH("kc_umma_selftest_kernel");
     return KC_OK;
 }

@@ -25,9 +25,29 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
     return d;
 }
 
-// instruction descriptor: D fp32, A/B tf32, both K-major, M x N tile
-__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// instruction descriptor: D fp32, A/B tf32, M x N tile; a_mn / b_mn = 1 selects MN-major for that operand
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, int a_mn = 0, int b_mn = 0) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// MN-major, no swizzle, 4-byte elements: 8 (k) x 16-byte (4 mn elements) core matrices.  Element (mn, k) of a tile with
+// KT k-values lives at (mn/4) * SBO + (k/8) * 128 + (k%8) * 16 + (mn%4) * 4 with LBO = 128 B (next group of 8 k),
+// SBO = (KT/8) * 128 B (next group of 4 mn).  One kind::tf32 instruction consumes K = 8 = one k-group.
+__device__ __forceinline__ uint32_t mnmajor_off(int mn, int k, int KT) {
+    return (uint32_t)((mn >> 2) * ((KT >> 3) * 128) + (k >> 3) * 128 + (k & 7) * 16 + (mn & 3) * 4);
+}
+
+// bf16 operands (kind::f16), D fp32
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn = 0, int b_mn = 0) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// MN-major, no swizzle, 2-byte elements: 8 (k) x 16-byte (8 mn elements) core matrices.  Element (mn, k) of a tile with
+// KT k-values: (mn/8) * SBO + (k/8) * 128 + (k%8) * 16 + (mn%8) * 2, LBO = 128 B, SBO = (KT/8) * 128 B.
+// One kind::f16 instruction consumes K = 16 = two k-groups (256 B).
+__device__ __forceinline__ uint32_t mnmajor_off_b16(int mn, int k, int KT) {
+    return (uint32_t)((mn >> 3) * ((KT >> 3) * 128) + (k >> 3) * 128 + (k & 7) * 16 + (mn & 7) * 2);
 }
 
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot, uint32_t ncols) {  // one full warp
@@ -61,6 +81,12 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint6
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
 // arrive on an mbarrier when all previously issued MMAs of this thread have completed (implies fence::before_thread_sync)
 __device__ __forceinline__ void commit(uint64_t* bar) {
