@@ -15,10 +15,17 @@
 //   4. kc_train_reduce_kernel : deterministic sum of the partials into gW1, gb1, gW2, gb2 and of the loss partials
 #include <cuda_runtime.h>
 #include <algorithm>
+#include <cstdlib>
 #include "kc_rod.cuh"
 #include "kc_adjoint.cuh"
 
 template <typename T> int kc_pack_mlp(const kc_mlp* mlp, T* Wp, MlpC<T>& M, cudaStream_t st);
+int kc_train_tc_grid(int64_t Q);
+int kc_train_tc_launch(const kc_mlp* mlp, float ds, int64_t Q, int T_, int K, const float* X, const float* PHYS,
+                       const float* TGT, float* W1hl, float* W2c, float* partial, int64_t NP, double* loss_part,
+                       float* pred_out, int grid, cudaStream_t st);
+template <typename T> struct kc_is_float { static constexpr bool value = false; };
+template <> struct kc_is_float<float> { static constexpr bool value = true; };
 int kc_check_mlp(const kc_mlp* mlp);
 
 struct KeyIdx64 { int32_t k[64]; };
@@ -295,7 +302,7 @@ __global__ void kc_train_reduce_kernel(const T* __restrict__ partial, int splits
 // ---------------------------------------------------------------------------------------------------------------
 // host side of the train step
 // ---------------------------------------------------------------------------------------------------------------
-struct TrainWs { size_t X, PHYS, TGT, dO, lossp, part, wp, total; int XPG; int64_t Q, NP; int nfwd; int splits; int64_t tps; int chunks; };
+struct TrainWs { size_t X, PHYS, TGT, dO, lossp, part, wp, tcw, total; int XPG; int64_t Q, NP; int nfwd; int splits; int64_t tps; int chunks; };
 
 static size_t bwd_smem_bytes(int in_dim, size_t sz) {
     const int XP = (in_dim + 3) & ~3, XPG = in_dim == 28 ? 32 : 56;
@@ -324,9 +331,10 @@ static TrainWs train_ws(int dtype, const kc_mlp* mlp, int64_t Q) {
     w.PHYS = off; off += al256((size_t)Q * 25 * sz);
     w.TGT = off; off += al256((size_t)Q * 25 * sz);
     w.dO = off; off += al256((size_t)Q * 32 * sz);
-    w.lossp = off; off += al256((size_t)(w.nfwd > 0 ? w.nfwd : 1) * 8);
-    w.part = off; off += al256((size_t)splits * w.NP * sz);
+    w.lossp = off; off += al256((size_t)std::max(w.nfwd, 160) * 8);
+    w.part = off; off += al256((size_t)std::max(splits, 160) * w.NP * sz);   // >= one slice per SM for the tensor-core path
     w.wp = off; off += al256((size_t)mlp->hidden * (((mlp->in_dim + 3) & ~3) + 32) * sz);
+    w.tcw = off; off += al256((size_t)4 * (2 * 128 * 32 + 128 * 28) * 4);   // tensor-core path: split / transposed weights
     w.total = off;
     return w;
 }
@@ -356,6 +364,7 @@ static int train_typed(const kc_rod_params* Pp, const kc_mlp* mlp, int64_t B, in
     int rc = kc_pack_mlp<T>(mlp, (T*)(ws + w.wp), M, st);
     if (rc) return rc;
     const int in_dim = mlp->in_dim;
+    int tc_slices = 0;
     if (Q > 0) {
         const unsigned g1 = (unsigned)((Q + 127) / 128);
 #define PREP(D, I) kc_train_prep_kernel<T, D, I><<<g1, 128, 0, st>>>(P, key, B, (int)T_, K, (const T*)traj, (const T*)controls, X, w.XPG, PHYS, TGT)
@@ -363,6 +372,19 @@ static int train_typed(const kc_rod_params* Pp, const kc_mlp* mlp, int64_t B, in
         else { if (in_dim == 28) PREP(false, 28); else PREP(false, 53); }
 #undef PREP
         KC_CHECK_LAUNCH("kc_train_prep_kernel");
+        // tensor-core path (tcgen05): fp32 model, 28 inputs, hidden <= 512; KC_TRAIN_MODE=simt forces the SIMT kernels
+        bool use_tc = kc_is_float<T>::value && in_dim == 28 && mlp->hidden <= 512;
+        {
+            const char* e = getenv("KC_TRAIN_MODE");
+            if (e && e[0] == 's') use_tc = false;
+        }
+        if (use_tc) {
+            float* tcw = (float*)(ws + w.tcw);
+            tc_slices = kc_train_tc_grid(Q);
+            int rc2 = kc_train_tc_launch(mlp, (float)P.ds, Q, (int)T_, K, (const float*)X, (const float*)PHYS, (const float*)TGT,
+                                         tcw, tcw + 4 * 2 * 128 * 32, (float*)part, w.NP, lossp, (float*)pred, tc_slices, st);
+            if (rc2) return rc2;
+        } else {
         {
             const size_t wbytes = (size_t)M.hidden * M.stride * sizeof(T);
             const int in_smem = wbytes <= 200 * 1024 ? 1 : 0;
@@ -390,10 +412,11 @@ static int train_typed(const kc_rod_params* Pp, const kc_mlp* mlp, int64_t B, in
             k<<<grid, BWD_THREADS, smem, st>>>(mlp->hidden, (const T*)mlp->W1, (const T*)mlp->b1, (const T*)mlp->W2, Q, X, dO, part, w.NP, w.tps);
         }
         KC_CHECK_LAUNCH("kc_train_bwd_kernel");
+        }
     }
-    const int splits = Q > 0 ? w.splits : 0;
+    const int splits = Q > 0 ? (tc_slices > 0 ? tc_slices : w.splits) : 0;
     kc_train_reduce_kernel<T><<<(unsigned)((w.NP + 255) / 256), 256, 0, st>>>(part, splits, w.NP, mlp->hidden, in_dim, (T*)gW1, (T*)gb1,
-                                                                            (T*)gW2, (T*)gb2, lossp, Q > 0 ? w.nfwd : 0, loss);
+                                                                            (T*)gW2, (T*)gb2, lossp, Q > 0 ? (tc_slices > 0 ? tc_slices : w.nfwd) : 0, loss);
     KC_CHECK_LAUNCH("kc_train_reduce_kernel");
     return KC_OK;
 }

@@ -1,0 +1,394 @@
+// kc_train_tc.cu — tensor-core (tcgen05 / TMEM) version of the teacher-forced KNODE training step, fp32 model, 28 inputs,
+// hidden <= 512.  Replaces kc_train_fwd_kernel + kc_train_bwd_kernel (kc_train.cu), which stay as the SIMT reference path
+// (other dtypes / shapes, and KC_TRAIN_MODE=simt).  Same maths (physics_train.py:313-368), see kc_train.cu header.
+//
+// One persistent CTA per SM, 256 threads, tiles of 128 samples (TMEM lane = sample row for the activations, = hidden unit
+// for the gradient accumulators).  Per tile and per chunk of 128 hidden units:
+//   forward : Z = X W1c^T            tcgen05.mma kind::tf32, 3-pass split (hi*hi + lo*hi + hi*lo: fp32-accurate), K = 32
+//             (column 28 of X is 1 and carries b1) -> TMEM; epilogue: a = ELU(z), o += W2c a (SIMT, 25 wide)
+//   loss    : pred, 4-term loss, dL/do per sample row (same code as the SIMT kernel)
+//   backward: Z again (recompute), epilogue: dz = (W2c^T dO) ELU'(z); a and dz are written to shared memory as bf16 hi/lo
+//             pairs, MN-major; gW1c += dZ^T X and gW2c^T += A^T dO on tcgen05.mma kind::f16 (bf16 3-pass split), K = the
+//             tile's 128 samples, accumulating in TMEM across all tiles of the CTA.
+// At the end the accumulators are written as one partial-gradient slice per CTA; kc_train_reduce_kernel sums the slices.
+// Operand layouts / descriptors are the ones pinned by kc_umma_selftest (tests/test_gpu_tensorcore.py).
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include "kc_rod.cuh"
+#include "kc_umma.cuh"
+
+namespace tc {
+constexpr int TS = 128, HC = 128, THREADS = 256;
+constexpr int OFF_XH = 0;        // X hi  [128 x 32] tf32 K-major                      16384
+constexpr int OFF_XL = 16384;    // X lo                                               16384
+constexpr int OFF_W2 = 32768;    // W2 chunk [128 units][28] fp32 (SIMT broadcasts)     14336
+constexpr int OFF_DZ = 47104;    // dZ^T hi | lo, bf16 MN-major [128 units x 128 samples] 2 x 32768;
+                                 // W1 chunk hi | lo (tf32 K-major [128 x 32], 2 x 16384) ALIASES the first half
+constexpr int OFF_A = 112640;    // A^T hi | lo, bf16 MN-major                           2 x 32768; sO [128][32] fp32 aliases
+constexpr int OFF_XT = 178176;   // X^T hi | lo, bf16 MN-major [32 inputs x 128 samples]  2 x 8192
+constexpr int OFF_DO = 194560;   // dO^T hi | lo, bf16 MN-major [32 outputs x 128 samples] 2 x 8192
+constexpr int OFF_MISC = 210944; // tmem slot, mbarriers, reduction scratch
+constexpr int SMEM_BYTES = OFF_MISC + 1024;
+constexpr int W1_TILE_FLOATS = 128 * 32;          // one hi or lo tile
+constexpr int W2_TILE_FLOATS = 128 * 28;
+}  // namespace tc
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+    const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&v);
+}
+// x = hi + lo with hi, lo bf16 (about 16 mantissa bits together)
+__device__ __forceinline__ void split_bf16(float x, float& hi, float& lo) {
+    hi = __bfloat162float(__float2bfloat16_rn(x));
+    lo = x - hi;
+}
+
+// W1[H][28], b1[H], W2[25][H] -> per chunk c: W1hl[c] = {hi tile, lo tile} (tf32 values, K-major interleaved, column 28
+// = b1, rows >= H zero) and W2c[c][128][28] (W2 transposed, zero padded).
+__global__ void kc_tc_prep_weights_kernel(const float* __restrict__ W1, const float* __restrict__ b1,
+                                          const float* __restrict__ W2, int hidden, float* __restrict__ W1hl,
+                                          float* __restrict__ W2c) {
+    const int c = blockIdx.x;
+    for (int e = threadIdx.x; e < 128 * 32; e += blockDim.x) {
+        const int ul = e >> 5, k = e & 31, u = c * 128 + ul;
+        float v = 0.f;
+        if (u < hidden) v = k < 28 ? W1[(size_t)u * 28 + k] : (k == 28 ? b1[u] : 0.f);
+        const float hi = umma::to_tf32_rn(v), lo = umma::to_tf32_rn(v - hi);
+        const uint32_t o = umma::kmajor_off(ul, k, 32) >> 2;
+        W1hl[(size_t)c * 2 * tc::W1_TILE_FLOATS + o] = hi;
+        W1hl[(size_t)c * 2 * tc::W1_TILE_FLOATS + tc::W1_TILE_FLOATS + o] = lo;
+    }
+    for (int e = threadIdx.x; e < 128 * 28; e += blockDim.x) {
+        const int ul = e / 28, co = e - ul * 28, u = c * 128 + ul;
+        W2c[(size_t)c * tc::W2_TILE_FLOATS + e] = (u < hidden && co < 25) ? W2[(size_t)co * hidden + u] : 0.f;
+    }
+}
+
+__global__ void __launch_bounds__(tc::THREADS, 1)
+kc_train_tc_kernel(int hidden, int nch, const float* __restrict__ W1hl, const float* __restrict__ W2c,
+                   const float* __restrict__ b2, float ds, int64_t Q, int T_, int K, const float* __restrict__ X,
+                   const float* __restrict__ PHYS, const float* __restrict__ TGT, float* __restrict__ partial,
+                   int64_t NP, double* __restrict__ loss_part, float* __restrict__ pred_out) {
+    extern __shared__ __align__(1024) unsigned char sm[];
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + tc::OFF_MISC);
+    uint64_t* barZ = reinterpret_cast<uint64_t*>(sm + tc::OFF_MISC + 8);
+    uint64_t* barG = reinterpret_cast<uint64_t*>(sm + tc::OFF_MISC + 16);
+    double* redd = reinterpret_cast<double*>(sm + tc::OFF_MISC + 32);    // [8]
+    float* redb = reinterpret_cast<float*>(sm + tc::OFF_MISC + 128);     // [4][25]
+    float* sW2 = reinterpret_cast<float*>(sm + tc::OFF_W2);
+    float* sO = reinterpret_cast<float*>(sm + tc::OFF_A);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int row = tid & 127, half = tid >> 7;
+    const uint32_t laneblk = (uint32_t)((warp & 3) * 32) << 16;
+    if (warp == 0) umma::tmem_alloc(tmem_slot, 512);
+    if (tid == 0) {
+        umma::mbar_init(barZ, 1);
+        umma::mbar_init(barG, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    umma::fence_async_smem();
+    umma::fence_before();
+    __syncthreads();
+    umma::fence_after();
+    const uint32_t tbase = *tmem_slot;
+    uint32_t phZ = 0, phG = 0;
+    const uint32_t idescZ = umma::make_idesc_tf32(128, 128);
+    const uint32_t idescG = umma::make_idesc_bf16(128, 32, 1, 1);
+    const uint32_t aXh = umma::smem_u32(sm + tc::OFF_XH), aXl = umma::smem_u32(sm + tc::OFF_XL);
+    const uint32_t aW1h = umma::smem_u32(sm + tc::OFF_DZ), aW1l = aW1h + 16384;
+    const uint32_t aDZh = umma::smem_u32(sm + tc::OFF_DZ), aDZl = aDZh + 32768;
+    const uint32_t aAh = umma::smem_u32(sm + tc::OFF_A), aAl = aAh + 32768;
+    const uint32_t aXth = umma::smem_u32(sm + tc::OFF_XT), aXtl = aXth + 8192;
+    const uint32_t aDOh = umma::smem_u32(sm + tc::OFF_DO), aDOl = aDOh + 8192;
+
+    auto load_weights = [&](int c) {   // W1 chunk hi|lo -> OFF_DZ (32 KB), W2 chunk -> OFF_W2 (14 KB)
+        const float4* src = reinterpret_cast<const float4*>(W1hl + (size_t)c * 2 * tc::W1_TILE_FLOATS);
+        float4* dst = reinterpret_cast<float4*>(sm + tc::OFF_DZ);
+        for (int e = tid; e < 2 * tc::W1_TILE_FLOATS / 4; e += tc::THREADS) dst[e] = src[e];
+        const float4* src2 = reinterpret_cast<const float4*>(W2c + (size_t)c * tc::W2_TILE_FLOATS);
+        float4* dst2 = reinterpret_cast<float4*>(sm + tc::OFF_W2);
+        for (int e = tid; e < tc::W2_TILE_FLOATS / 4; e += tc::THREADS) dst2[e] = src2[e];
+    };
+    auto issue_gemm1 = [&]() {  // Z[128 samples x 128 units] = X W1c^T, 3-pass tf32 split, K = 32 (4 x K8)
+        uint32_t acc = 0;
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+            const uint32_t a = (p == 1) ? aXl : aXh, b = (p == 2) ? aW1l : aW1h;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                umma::mma_tf32(tbase, umma::make_desc(a + kk * 256, 128, 1024), umma::make_desc(b + kk * 256, 128, 1024), idescZ, acc);
+                acc = 1;
+            }
+        }
+        umma::commit(barZ);
+    };
+    auto issue_grads = [&](int c, bool first_tile) {  // gW1c += dZ^T X ; gW2c^T += A^T dO ; K = 128 samples (8 x K16)
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+            const uint32_t d = tbase + (g == 0 ? 128 : 256) + 32 * c;
+            uint32_t acc = first_tile ? 0u : 1u;
+#pragma unroll
+            for (int p = 0; p < 3; ++p) {
+                const uint32_t a = g == 0 ? ((p == 1) ? aDZl : aDZh) : ((p == 1) ? aAl : aAh);
+                const uint32_t b = g == 0 ? ((p == 2) ? aXtl : aXth) : ((p == 2) ? aDOl : aDOh);
+                for (int kk = 0; kk < 8; ++kk) {
+                    umma::mma_bf16(d, umma::make_desc(a + kk * 256, 128, 2048), umma::make_desc(b + kk * 256, 128, 2048), idescG, acc);
+                    acc = 1;
+                }
+            }
+        }
+        umma::commit(barG);
+    };
+
+    float gb2acc[25];
+#pragma unroll
+    for (int c = 0; c < 25; ++c) gb2acc[c] = 0.f;
+    double lossacc = 0.0;
+    const int64_t ntiles = (Q + tc::TS - 1) / tc::TS;
+    bool first_tile = true;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t q = tile * tc::TS + row;
+        const bool valid = q < Q;
+        // ---- stage the X tile: tf32 hi/lo K-major (A of GEMM1) and bf16 hi/lo MN-major (B of the gW1 GEMM) ----
+        {
+            float xv[16];
+            const float4* xs = reinterpret_cast<const float4*>(X + (size_t)(valid ? q : 0) * 32 + half * 16);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                float4 t = valid ? xs[g] : make_float4(0.f, 0.f, 0.f, 0.f);
+                xv[4 * g] = t.x; xv[4 * g + 1] = t.y; xv[4 * g + 2] = t.z; xv[4 * g + 3] = t.w;
+            }
+            if (half == 1) xv[12] = valid ? 1.f : 0.f;  // column 28: carries b1 in GEMM1 and yields gb1 in the gW1 GEMM
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                float4 h, l;
+                h.x = umma::to_tf32_rn(xv[4 * g]);     l.x = umma::to_tf32_rn(xv[4 * g] - h.x);
+                h.y = umma::to_tf32_rn(xv[4 * g + 1]); l.y = umma::to_tf32_rn(xv[4 * g + 1] - h.y);
+                h.z = umma::to_tf32_rn(xv[4 * g + 2]); l.z = umma::to_tf32_rn(xv[4 * g + 2] - h.z);
+                h.w = umma::to_tf32_rn(xv[4 * g + 3]); l.w = umma::to_tf32_rn(xv[4 * g + 3] - h.w);
+                const uint32_t o = umma::kmajor_off(row, half * 16 + 4 * g, 32);
+                *reinterpret_cast<float4*>(sm + tc::OFF_XH + o) = h;
+                *reinterpret_cast<float4*>(sm + tc::OFF_XL + o) = l;
+            }
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+                float hi[8], lo[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) split_bf16(xv[8 * g + j], hi[j], lo[j]);
+                const uint32_t o = umma::mnmajor_off_b16(half * 16 + 8 * g, row, 128);
+                *reinterpret_cast<uint4*>(sm + tc::OFF_XT + o) =
+                    make_uint4(pack_bf16x2(hi[0], hi[1]), pack_bf16x2(hi[2], hi[3]), pack_bf16x2(hi[4], hi[5]), pack_bf16x2(hi[6], hi[7]));
+                *reinterpret_cast<uint4*>(sm + tc::OFF_XT + 8192 + o) =
+                    make_uint4(pack_bf16x2(lo[0], lo[1]), pack_bf16x2(lo[2], lo[3]), pack_bf16x2(lo[4], lo[5]), pack_bf16x2(lo[6], lo[7]));
+            }
+        }
+        float o[25];
+#pragma unroll
+        for (int c = 0; c < 25; ++c) o[c] = 0.f;
+        // ---- pass 1: forward ----
+        for (int c = 0; c < nch; ++c) {
+            load_weights(c);
+            umma::fence_async_smem();
+            umma::fence_before();
+            __syncthreads();
+            if (tid == 0) { umma::fence_after(); issue_gemm1(); }
+            umma::mbar_wait(barZ, phZ); phZ ^= 1;
+            umma::fence_after();
+#pragma unroll 1
+            for (int cc = 0; cc < 2; ++cc) {
+                uint32_t v[32];
+                umma::ld32(tbase + laneblk + half * 64 + cc * 32, v);
+                umma::wait_ld();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float a = kc_elu(__uint_as_float(v[j]));
+                    mlp_unit_axpy<float>(sW2 + (half * 64 + cc * 32 + j) * 28, a, o);
+                }
+            }
+            umma::fence_before();
+            __syncthreads();
+        }
+        // ---- loss and dL/do (rows of half 0 own the sample) ----
+        if (half == 1) {
+#pragma unroll
+            for (int c = 0; c < 25; ++c) sO[row * 32 + c] = o[c];
+        }
+        __syncthreads();
+        if (half == 0) {
+            float g[25];
+#pragma unroll
+            for (int c = 0; c < 25; ++c) { o[c] += sO[row * 32 + c] + b2[c]; g[c] = 0.f; }
+            if (valid) {
+                float pred[25], tg[25];
+#pragma unroll
+                for (int r = 0; r < 19; ++r) pred[r] = PHYS[(size_t)q * 25 + r] + ds * o[r];
+#pragma unroll
+                for (int c = 19; c < 25; ++c) pred[c] = PHYS[(size_t)q * 25 + c] + o[c];
+#pragma unroll
+                for (int r = 0; r < 25; ++r) tg[r] = TGT[(size_t)q * 25 + r];
+                const float S = float(T_ - 1);
+                const float wp = 1.f / (float(3 * K) * S), wf = 1.f / (float(12 * K) * S), wz = 1.f / (float(6 * K) * S);
+                float acc = 0.f;
+#pragma unroll
+                for (int r = 0; r < 3; ++r) { const float e = pred[r] - tg[r]; acc += wp * e * e; g[r] = 2.f * wp * e * ds; }
+#pragma unroll
+                for (int r = 7; r < 19; ++r) { const float e = pred[r] - tg[r]; acc += wf * e * e; g[r] = 2.f * wf * e * ds; }
+#pragma unroll
+                for (int r = 19; r < 25; ++r) { const float e = pred[r] - tg[r]; acc += wz * e * e; g[r] = 2.f * wz * e; }
+                float ep[3], et[3], ge[3], gq[4];
+                quat_to_euler(pred + 3, ep);
+                quat_to_euler(tg + 3, et);
+#pragma unroll
+                for (int i = 0; i < 3; ++i) { const float e = ep[i] - et[i]; acc += wp * e * e; ge[i] = 2.f * wp * e; }
+                quat_to_euler_vjp(pred + 3, ge, gq);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) g[3 + i] = gq[i] * ds;
+                lossacc += (double)acc;
+                if (pred_out) {
+                    const int kk = (int)(q % K);
+                    const int64_t bt = q / K;
+                    float* po = pred_out + (size_t)bt * 25 * K + kk;
+#pragma unroll
+                    for (int r = 0; r < 25; ++r) po[r * K] = pred[r];
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 25; ++c) { gb2acc[c] += g[c]; sO[row * 32 + c] = g[c]; o[c] = g[c]; }
+            // dO^T as bf16 hi/lo, MN-major [32 outputs x 128 samples] (B operand of the gW2 GEMM)
+#pragma unroll
+            for (int gi = 0; gi < 4; ++gi) {
+                float hi[8], lo[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int c = gi * 8 + j;
+                    split_bf16(c < 25 ? g[c < 25 ? c : 0] : 0.f, hi[j], lo[j]);
+                }
+                const uint32_t off = umma::mnmajor_off_b16(gi * 8, row, 128);
+                *reinterpret_cast<uint4*>(sm + tc::OFF_DO + off) =
+                    make_uint4(pack_bf16x2(hi[0], hi[1]), pack_bf16x2(hi[2], hi[3]), pack_bf16x2(hi[4], hi[5]), pack_bf16x2(hi[6], hi[7]));
+                *reinterpret_cast<uint4*>(sm + tc::OFF_DO + 8192 + off) =
+                    make_uint4(pack_bf16x2(lo[0], lo[1]), pack_bf16x2(lo[2], lo[3]), pack_bf16x2(lo[4], lo[5]), pack_bf16x2(lo[6], lo[7]));
+            }
+        }
+        __syncthreads();
+        if (half == 1) {
+#pragma unroll
+            for (int c = 0; c < 25; ++c) o[c] = sO[row * 32 + c];   // o now holds dL/do of this row in both halves
+        }
+        __syncthreads();
+        // ---- pass 2: backward ----
+        for (int c = 0; c < nch; ++c) {
+            if (c > 0) { umma::mbar_wait(barG, phG); phG ^= 1; umma::fence_after(); }  // chunk c-1's gradient MMAs done
+            load_weights(c);
+            umma::fence_async_smem();
+            umma::fence_before();
+            __syncthreads();
+            if (tid == 0) { umma::fence_after(); issue_gemm1(); }
+            umma::mbar_wait(barZ, phZ); phZ ^= 1;
+            umma::fence_after();
+#pragma unroll 1
+            for (int cc = 0; cc < 2; ++cc) {
+                uint32_t v[32];
+                umma::ld32(tbase + laneblk + half * 64 + cc * 32, v);
+                umma::wait_ld();
+#pragma unroll
+                for (int g8 = 0; g8 < 4; ++g8) {
+                    float ah[8], al[8], dh[8], dl[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int u = half * 64 + cc * 32 + g8 * 8 + j;
+                        const float z = __uint_as_float(v[g8 * 8 + j]);
+                        const float a = kc_elu(z), e = kc_elu_grad(z);
+                        const float da = mlp_unit_dot<float, 25>(sW2 + u * 28, o, 0.f);
+                        split_bf16(a, ah[j], al[j]);
+                        split_bf16(da * e, dh[j], dl[j]);
+                    }
+                    const uint32_t off = umma::mnmajor_off_b16(half * 64 + cc * 32 + g8 * 8, row, 128);
+                    *reinterpret_cast<uint4*>(sm + tc::OFF_A + off) =
+                        make_uint4(pack_bf16x2(ah[0], ah[1]), pack_bf16x2(ah[2], ah[3]), pack_bf16x2(ah[4], ah[5]), pack_bf16x2(ah[6], ah[7]));
+                    *reinterpret_cast<uint4*>(sm + tc::OFF_A + 32768 + off) =
+                        make_uint4(pack_bf16x2(al[0], al[1]), pack_bf16x2(al[2], al[3]), pack_bf16x2(al[4], al[5]), pack_bf16x2(al[6], al[7]));
+                    *reinterpret_cast<uint4*>(sm + tc::OFF_DZ + off) =
+                        make_uint4(pack_bf16x2(dh[0], dh[1]), pack_bf16x2(dh[2], dh[3]), pack_bf16x2(dh[4], dh[5]), pack_bf16x2(dh[6], dh[7]));
+                    *reinterpret_cast<uint4*>(sm + tc::OFF_DZ + 32768 + off) =
+                        make_uint4(pack_bf16x2(dl[0], dl[1]), pack_bf16x2(dl[2], dl[3]), pack_bf16x2(dl[4], dl[5]), pack_bf16x2(dl[6], dl[7]));
+                }
+            }
+            umma::fence_async_smem();
+            umma::fence_before();
+            __syncthreads();
+            if (tid == 0) { umma::fence_after(); issue_grads(c, first_tile); }
+        }
+        umma::mbar_wait(barG, phG); phG ^= 1;   // last chunk's gradient MMAs: they read X^T / dO^T which the next tile overwrites
+        umma::fence_after();
+        first_tile = false;
+    }
+    // ---- write this CTA's partial gradients ----
+    umma::fence_before();
+    __syncthreads();
+    umma::fence_after();
+    float* out = partial + (size_t)blockIdx.x * NP;
+    const int64_t ob1 = (int64_t)hidden * 28, oW2 = ob1 + hidden, ob2 = oW2 + (int64_t)25 * hidden;
+    if (half == 0) {
+        for (int c = 0; c < nch; ++c) {
+            const int u = c * tc::HC + row;
+            uint32_t v[32];
+            umma::ld32(tbase + laneblk + 128 + 32 * c, v);
+            umma::wait_ld();
+            if (u < hidden) {
+#pragma unroll
+                for (int k = 0; k < 28; ++k) out[(size_t)u * 28 + k] = __uint_as_float(v[k]);
+                out[ob1 + u] = __uint_as_float(v[28]);
+            }
+            umma::ld32(tbase + laneblk + 256 + 32 * c, v);
+            umma::wait_ld();
+            if (u < hidden) {
+#pragma unroll
+                for (int co = 0; co < 25; ++co) out[oW2 + (size_t)co * hidden + u] = __uint_as_float(v[co]);
+            }
+        }
+    }
+    // gb2 and loss: block reductions (fixed order: deterministic)
+#pragma unroll
+    for (int c = 0; c < 25; ++c) {
+        float s = gb2acc[c];
+#pragma unroll
+        for (int o2 = 16; o2 > 0; o2 >>= 1) s += __shfl_down_sync(0xffffffffu, s, o2);
+        if (lane == 0 && warp < 4) redb[warp * 25 + c] = s;
+    }
+    {
+        double s = lossacc;
+#pragma unroll
+        for (int o2 = 16; o2 > 0; o2 >>= 1) s += __shfl_down_sync(0xffffffffu, s, o2);
+        if (lane == 0) redd[warp] = s;
+    }
+    umma::fence_before();
+    __syncthreads();
+    if (tid < 25) out[ob2 + tid] = redb[tid] + redb[25 + tid] + redb[50 + tid] + redb[75 + tid];
+    if (tid == 0) loss_part[blockIdx.x] = redd[0] + redd[1] + redd[2] + redd[3];
+    if (warp == 0) umma::tmem_dealloc(tbase, 512);
+}
+
+// Host side: called by kc_train_step (kc_train.cu) when the shape is eligible.  W1hl: nch*2*4096 floats, W2c: nch*3584
+// floats (workspace), partial: grid*NP floats, loss_part: grid doubles.  Returns the grid size used (= number of slices).
+int kc_train_tc_grid(int64_t Q) {
+    const int64_t ntiles = (Q + tc::TS - 1) / tc::TS;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return (int)(ntiles < sms ? (ntiles > 0 ? ntiles : 1) : sms);
+}
+
+int kc_train_tc_launch(const kc_mlp* mlp, float ds, int64_t Q, int T_, int K, const float* X, const float* PHYS,
+                       const float* TGT, float* W1hl, float* W2c, float* partial, int64_t NP, double* loss_part,
+                       float* pred_out, int grid, cudaStream_t st) {
+    const int nch = (mlp->hidden + tc::HC - 1) / tc::HC;
+    kc_tc_prep_weights_kernel<<<nch, 256, 0, st>>>((const float*)mlp->W1, (const float*)mlp->b1, (const float*)mlp->W2,
+                                                  mlp->hidden, W1hl, W2c);
+    KC_CHECK_LAUNCH("kc_tc_prep_weights_kernel");
+    cudaFuncSetAttribute(kc_train_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
+    kc_train_tc_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(mlp->hidden, nch, W1hl, W2c, (const float*)mlp->b2, ds, Q,
+                                                                  T_, K, X, PHYS, TGT, partial, NP, loss_part, pred_out);
+    KC_CHECK_LAUNCH("kc_train_tc_kernel");
+    return KC_OK;
+}
