@@ -5,11 +5,15 @@
 // One persistent CTA per SM, 256 threads, tiles of 128 samples (TMEM lane = sample row for the activations, = hidden unit
 // for the gradient accumulators).  Per tile and per chunk of 128 hidden units:
 //   forward : Z = X W1c^T            tcgen05.mma kind::tf32, 3-pass split (hi*hi + lo*hi + hi*lo: fp32-accurate), K = 32
-//             (column 28 of X is 1 and carries b1) -> TMEM; epilogue: a = ELU(z), o += W2c a (SIMT, 25 wide)
+//             (column 28 of X is 1 and carries b1) -> TMEM; epilogue: a = ELU(z) -> shared memory as bf16 hi/lo pairs;
+//             O += A W2c^T            kind::f16 (bf16 3-pass split), K = 128 units, accumulated in TMEM over the chunks
 //   loss    : pred, 4-term loss, dL/do per sample row (same code as the SIMT kernel)
-//   backward: Z again (recompute), epilogue: dz = (W2c^T dO) ELU'(z); a and dz are written to shared memory as bf16 hi/lo
-//             pairs, MN-major; gW1c += dZ^T X and gW2c^T += A^T dO on tcgen05.mma kind::f16 (bf16 3-pass split), K = the
-//             tile's 128 samples, accumulating in TMEM across all tiles of the CTA.
+//   backward: Z again (recompute) and dA = dO W2c (bf16 3-pass, K = 32); epilogue: dz = dA * ELU'(z); a and dz go to
+//             shared memory as bf16 hi/lo; gW1c += dZ^T X and gW2c^T += A^T dO (bf16 3-pass), K = the tile's 128
+//             samples, accumulating in TMEM across all tiles of the CTA.
+// The activation tile A is written ONCE per chunk, thread = sample row, 8 units per 16-byte store; the same bytes are the
+// K-major A operand of the forward GEMM (K = units) and the MN-major A operand of the gradient GEMM (K = samples) - only
+// LBO/SBO swap in the descriptor.  The same holds for dO (A of the dA GEMM, B of the gW2 GEMM).
 // At the end the accumulators are written as one partial-gradient slice per CTA; kc_train_reduce_kernel sums the slices.
 // Operand layouts / descriptors are the ones pinned by kc_umma_selftest (tests/test_gpu_tensorcore.py).
 #include <cuda_runtime.h>
@@ -21,16 +25,19 @@ namespace tc {
 constexpr int TS = 128, HC = 128, THREADS = 256;
 constexpr int OFF_XH = 0;        // X hi  [128 x 32] tf32 K-major                      16384
 constexpr int OFF_XL = 16384;    // X lo                                               16384
-constexpr int OFF_W2 = 32768;    // W2 chunk [128 units][28] fp32 (SIMT broadcasts)     14336
-constexpr int OFF_DZ = 47104;    // dZ^T hi | lo, bf16 MN-major [128 units x 128 samples] 2 x 32768;
+constexpr int OFF_W2 = 32768;    // W2 chunk as a bf16 B operand, hi | lo (2 x 8192): pass 1 [32 outs x 128 units] K-major,
+                                 // pass 2 [128 units x 32 outs] K-major                                      16384
+constexpr int OFF_DZ = 49152;    // dZ^T hi | lo, bf16 MN-major [128 units x 128 samples] 2 x 32768;
                                  // W1 chunk hi | lo (tf32 K-major [128 x 32], 2 x 16384) ALIASES the first half
-constexpr int OFF_A = 112640;    // A^T hi | lo, bf16 MN-major                           2 x 32768; sO [128][32] fp32 aliases
-constexpr int OFF_XT = 178176;   // X^T hi | lo, bf16 MN-major [32 inputs x 128 samples]  2 x 8192
-constexpr int OFF_DO = 194560;   // dO^T hi | lo, bf16 MN-major [32 outputs x 128 samples] 2 x 8192
-constexpr int OFF_MISC = 210944; // tmem slot, mbarriers, reduction scratch
+constexpr int OFF_A = 114688;    // A^T hi | lo, bf16 MN-major                           2 x 32768
+constexpr int OFF_XT = 180224;   // X^T hi | lo, bf16 MN-major [32 inputs x 128 samples]  2 x 8192
+constexpr int OFF_DO = 196608;   // dO^T hi | lo, bf16 MN-major [32 outputs x 128 samples] 2 x 8192
+constexpr int OFF_MISC = 212992; // tmem slot, mbarriers, reduction scratch
 constexpr int SMEM_BYTES = OFF_MISC + 1024;
 constexpr int W1_TILE_FLOATS = 128 * 32;          // one hi or lo tile
-constexpr int W2_TILE_FLOATS = 128 * 28;
+constexpr int W2B_CHUNK_BYTES = 32768;            // per chunk: W2 fwd image hi|lo (16 KB) then W2^T bwd image hi|lo (16 KB)
+// TMEM columns
+constexpr int COL_Z = 0, COL_GW1 = 128, COL_GW2 = 256, COL_O = 384;
 }  // namespace tc
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
@@ -43,11 +50,17 @@ __device__ __forceinline__ void split_bf16(float x, float& hi, float& lo) {
     lo = x - hi;
 }
 
+// K-major, no swizzle, 2-byte elements: element (r, k) of a tile with KT k-values per row
+__device__ __forceinline__ uint32_t kmajor_off_b16(int r, int k, int KT) {
+    return (uint32_t)(((r >> 3) * (KT >> 3) + (k >> 3)) * 128 + (r & 7) * 16 + (k & 7) * 2);
+}
+
 // W1[H][28], b1[H], W2[25][H] -> per chunk c: W1hl[c] = {hi tile, lo tile} (tf32 values, K-major interleaved, column 28
-// = b1, rows >= H zero) and W2c[c][128][28] (W2 transposed, zero padded).
+// = b1, rows >= H zero); W2b[c] = bf16 hi|lo images of W2 as the B operand of the forward GEMM ([32 outs][128 units],
+// K-major) followed by hi|lo images of W2^T as the B operand of the dA GEMM ([128 units][32 outs], K-major).
 __global__ void kc_tc_prep_weights_kernel(const float* __restrict__ W1, const float* __restrict__ b1,
                                           const float* __restrict__ W2, int hidden, float* __restrict__ W1hl,
-                                          float* __restrict__ W2c) {
+                                          unsigned char* __restrict__ W2b) {
     const int c = blockIdx.x;
     for (int e = threadIdx.x; e < 128 * 32; e += blockDim.x) {
         const int ul = e >> 5, k = e & 31, u = c * 128 + ul;
@@ -57,15 +70,23 @@ __global__ void kc_tc_prep_weights_kernel(const float* __restrict__ W1, const fl
         const uint32_t o = umma::kmajor_off(ul, k, 32) >> 2;
         W1hl[(size_t)c * 2 * tc::W1_TILE_FLOATS + o] = hi;
         W1hl[(size_t)c * 2 * tc::W1_TILE_FLOATS + tc::W1_TILE_FLOATS + o] = lo;
-    }
-    for (int e = threadIdx.x; e < 128 * 28; e += blockDim.x) {
-        const int ul = e / 28, co = e - ul * 28, u = c * 128 + ul;
-        W2c[(size_t)c * tc::W2_TILE_FLOATS + e] = (u < hidden && co < 25) ? W2[(size_t)co * hidden + u] : 0.f;
+        // the same (unit ul, output co = k) pair feeds both W2 images
+        const int co = k;
+        const float w = (u < hidden && co < 25) ? W2[(size_t)co * hidden + u] : 0.f;
+        float wh, wl;
+        split_bf16(w, wh, wl);
+        unsigned char* base = W2b + (size_t)c * tc::W2B_CHUNK_BYTES;
+        const uint32_t of = kmajor_off_b16(co, ul, 128);   // forward: rows = outputs, k = units
+        *reinterpret_cast<__nv_bfloat16*>(base + of) = __float2bfloat16_rn(wh);
+        *reinterpret_cast<__nv_bfloat16*>(base + 8192 + of) = __float2bfloat16_rn(wl);
+        const uint32_t ob = kmajor_off_b16(ul, co, 32);    // backward: rows = units, k = outputs
+        *reinterpret_cast<__nv_bfloat16*>(base + 16384 + ob) = __float2bfloat16_rn(wh);
+        *reinterpret_cast<__nv_bfloat16*>(base + 16384 + 8192 + ob) = __float2bfloat16_rn(wl);
     }
 }
 
 __global__ void __launch_bounds__(tc::THREADS, 1)
-kc_train_tc_kernel(int hidden, int nch, const float* __restrict__ W1hl, const float* __restrict__ W2c,
+kc_train_tc_kernel(int hidden, int nch, const float* __restrict__ W1hl, const unsigned char* __restrict__ W2b,
                    const float* __restrict__ b2, float ds, int64_t Q, int T_, int K, const float* __restrict__ X,
                    const float* __restrict__ PHYS, const float* __restrict__ TGT, float* __restrict__ partial,
                    int64_t NP, double* __restrict__ loss_part, float* __restrict__ pred_out) {
@@ -73,10 +94,11 @@ kc_train_tc_kernel(int hidden, int nch, const float* __restrict__ W1hl, const fl
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + tc::OFF_MISC);
     uint64_t* barZ = reinterpret_cast<uint64_t*>(sm + tc::OFF_MISC + 8);
     uint64_t* barG = reinterpret_cast<uint64_t*>(sm + tc::OFF_MISC + 16);
+    uint64_t* barO = reinterpret_cast<uint64_t*>(sm + tc::OFF_MISC + 24);
     double* redd = reinterpret_cast<double*>(sm + tc::OFF_MISC + 32);    // [8]
     float* redb = reinterpret_cast<float*>(sm + tc::OFF_MISC + 128);     // [4][25]
-    float* sW2 = reinterpret_cast<float*>(sm + tc::OFF_W2);
-    float* sO = reinterpret_cast<float*>(sm + tc::OFF_A);
+    float* sO = reinterpret_cast<float*>(sm + tc::OFF_MISC + 640);       // unused now (kept for layout stability)
+    (void)sO;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int row = tid & 127, half = tid >> 7;
     const uint32_t laneblk = (uint32_t)((warp & 3) * 32) << 16;
@@ -84,6 +106,7 @@ kc_train_tc_kernel(int hidden, int nch, const float* __restrict__ W1hl, const fl
     if (tid == 0) {
         umma::mbar_init(barZ, 1);
         umma::mbar_init(barG, 1);
+        umma::mbar_init(barO, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     umma::fence_async_smem();
@@ -91,9 +114,12 @@ kc_train_tc_kernel(int hidden, int nch, const float* __restrict__ W1hl, const fl
     __syncthreads();
     umma::fence_after();
     const uint32_t tbase = *tmem_slot;
-    uint32_t phZ = 0, phG = 0;
+    uint32_t phZ = 0, phG = 0, phO = 0;
     const uint32_t idescZ = umma::make_idesc_tf32(128, 128);
-    const uint32_t idescG = umma::make_idesc_bf16(128, 32, 1, 1);
+    const uint32_t idescG = umma::make_idesc_bf16(128, 32, 1, 1);   // gradient GEMMs: both operands MN-major
+    const uint32_t idescO = umma::make_idesc_bf16(128, 32, 0, 0);   // O  = A W2c^T   (K-major views)
+    const uint32_t idescD = umma::make_idesc_bf16(128, 128, 0, 0);  // dA = dO W2c    (K-major views)
+    const uint32_t aWB = umma::smem_u32(sm + tc::OFF_W2);
     const uint32_t aXh = umma::smem_u32(sm + tc::OFF_XH), aXl = umma::smem_u32(sm + tc::OFF_XL);
     const uint32_t aW1h = umma::smem_u32(sm + tc::OFF_DZ), aW1l = aW1h + 16384;
     const uint32_t aDZh = umma::smem_u32(sm + tc::OFF_DZ), aDZl = aDZh + 32768;
@@ -101,13 +127,13 @@ kc_train_tc_kernel(int hidden, int nch, const float* __restrict__ W1hl, const fl
     const uint32_t aXth = umma::smem_u32(sm + tc::OFF_XT), aXtl = aXth + 8192;
     const uint32_t aDOh = umma::smem_u32(sm + tc::OFF_DO), aDOl = aDOh + 8192;
 
-    auto load_weights = [&](int c) {   // W1 chunk hi|lo -> OFF_DZ (32 KB), W2 chunk -> OFF_W2 (14 KB)
+    auto load_weights = [&](int c, int pass) {   // W1 chunk hi|lo -> OFF_DZ (32 KB); W2 bf16 image of this pass -> OFF_W2 (16 KB)
         const float4* src = reinterpret_cast<const float4*>(W1hl + (size_t)c * 2 * tc::W1_TILE_FLOATS);
         float4* dst = reinterpret_cast<float4*>(sm + tc::OFF_DZ);
         for (int e = tid; e < 2 * tc::W1_TILE_FLOATS / 4; e += tc::THREADS) dst[e] = src[e];
-        const float4* src2 = reinterpret_cast<const float4*>(W2c + (size_t)c * tc::W2_TILE_FLOATS);
+        const float4* src2 = reinterpret_cast<const float4*>(W2b + (size_t)c * tc::W2B_CHUNK_BYTES + (pass == 2 ? 16384 : 0));
         float4* dst2 = reinterpret_cast<float4*>(sm + tc::OFF_W2);
-        for (int e = tid; e < tc::W2_TILE_FLOATS / 4; e += tc::THREADS) dst2[e] = src2[e];
+        for (int e = tid; e < 16384 / 16; e += tc::THREADS) dst2[e] = src2[e];
     };
     auto issue_gemm1 = [&]() {  // Z[128 samples x 128 units] = X W1c^T, 3-pass tf32 split, K = 32 (4 x K8)
         uint32_t acc = 0;
@@ -116,16 +142,43 @@ kc_train_tc_kernel(int hidden, int nch, const float* __restrict__ W1hl, const fl
             const uint32_t a = (p == 1) ? aXl : aXh, b = (p == 2) ? aW1l : aW1h;
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
-                umma::mma_tf32(tbase, umma::make_desc(a + kk * 256, 128, 1024), umma::make_desc(b + kk * 256, 128, 1024), idescZ, acc);
+                umma::mma_tf32(tbase + tc::COL_Z, umma::make_desc(a + kk * 256, 128, 1024), umma::make_desc(b + kk * 256, 128, 1024), idescZ, acc);
                 acc = 1;
             }
         }
-        umma::commit(barZ);
+    };
+    // O[128 samples x 32 outs] (+)= A[samples x 128 units] W2c^T: A = the activation tile viewed K-major (LBO 2048, SBO 128),
+    // B = W2 image [32 outs x 128 units] K-major (LBO 128, SBO 2048); K = 128 units = 8 x K16
+    auto issue_gemm2 = [&](bool first_chunk) {
+        uint32_t acc = first_chunk ? 0u : 1u;
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+            const uint32_t a = (p == 1) ? aAl : aAh, b = (p == 2) ? aWB + 8192 : aWB;
+            for (int kk = 0; kk < 8; ++kk) {
+                umma::mma_bf16(tbase + tc::COL_O, umma::make_desc(a + kk * 4096, 2048, 128), umma::make_desc(b + kk * 256, 128, 2048), idescO, acc);
+                acc = 1;
+            }
+        }
+        umma::commit(barO);
+    };
+    // dA[128 samples x 128 units] = dO[samples x 32 outs] W2c: A = the dO tile viewed K-major (LBO 2048, SBO 128),
+    // B = W2^T image [128 units x 32 outs] K-major (LBO 128, SBO 512); K = 32 = 2 x K16
+    auto issue_gemm3 = [&]() {
+        uint32_t acc = 0;
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+            const uint32_t a = (p == 1) ? aDOl : aDOh, b = (p == 2) ? aWB + 8192 : aWB;
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk) {
+                umma::mma_bf16(tbase + tc::COL_O, umma::make_desc(a + kk * 4096, 2048, 128), umma::make_desc(b + kk * 256, 128, 512), idescD, acc);
+                acc = 1;
+            }
+        }
     };
     auto issue_grads = [&](int c, bool first_tile) {  // gW1c += dZ^T X ; gW2c^T += A^T dO ; K = 128 samples (8 x K16)
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
-            const uint32_t d = tbase + (g == 0 ? 128 : 256) + 32 * c;
+            const uint32_t d = tbase + (g == 0 ? tc::COL_GW1 : tc::COL_GW2) + 32 * c;
             uint32_t acc = first_tile ? 0u : 1u;
 #pragma unroll
             for (int p = 0; p < 3; ++p) {
@@ -182,42 +235,50 @@ kc_train_tc_kernel(int hidden, int nch, const float* __restrict__ W1hl, const fl
                     make_uint4(pack_bf16x2(lo[0], lo[1]), pack_bf16x2(lo[2], lo[3]), pack_bf16x2(lo[4], lo[5]), pack_bf16x2(lo[6], lo[7]));
             }
         }
-        float o[25];
-#pragma unroll
-        for (int c = 0; c < 25; ++c) o[c] = 0.f;
         // ---- pass 1: forward ----
         for (int c = 0; c < nch; ++c) {
-            load_weights(c);
+            if (c > 0) { umma::mbar_wait(barO, phO); phO ^= 1; umma::fence_after(); }  // chunk c-1's O GEMM done: sA, OFF_W2 free
+            load_weights(c, 1);
             umma::fence_async_smem();
             umma::fence_before();
             __syncthreads();
-            if (tid == 0) { umma::fence_after(); issue_gemm1(); }
+            if (tid == 0) { umma::fence_after(); issue_gemm1(); umma::commit(barZ); }
             umma::mbar_wait(barZ, phZ); phZ ^= 1;
             umma::fence_after();
 #pragma unroll 1
             for (int cc = 0; cc < 2; ++cc) {
                 uint32_t v[32];
-                umma::ld32(tbase + laneblk + half * 64 + cc * 32, v);
+                umma::ld32(tbase + laneblk + tc::COL_Z + half * 64 + cc * 32, v);
                 umma::wait_ld();
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float a = kc_elu(__uint_as_float(v[j]));
-                    mlp_unit_axpy<float>(sW2 + (half * 64 + cc * 32 + j) * 28, a, o);
+                for (int g8 = 0; g8 < 4; ++g8) {
+                    float ah[8], al[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) split_bf16(kc_elu(__uint_as_float(v[g8 * 8 + j])), ah[j], al[j]);
+                    const uint32_t off = umma::mnmajor_off_b16(half * 64 + cc * 32 + g8 * 8, row, 128);
+                    *reinterpret_cast<uint4*>(sm + tc::OFF_A + off) =
+                        make_uint4(pack_bf16x2(ah[0], ah[1]), pack_bf16x2(ah[2], ah[3]), pack_bf16x2(ah[4], ah[5]), pack_bf16x2(ah[6], ah[7]));
+                    *reinterpret_cast<uint4*>(sm + tc::OFF_A + 32768 + off) =
+                        make_uint4(pack_bf16x2(al[0], al[1]), pack_bf16x2(al[2], al[3]), pack_bf16x2(al[4], al[5]), pack_bf16x2(al[6], al[7]));
                 }
             }
+            umma::fence_async_smem();
             umma::fence_before();
             __syncthreads();
+            if (tid == 0) { umma::fence_after(); issue_gemm2(c == 0); }
         }
+        umma::mbar_wait(barO, phO); phO ^= 1;
+        umma::fence_after();
         // ---- loss and dL/do (rows of half 0 own the sample) ----
-        if (half == 1) {
-#pragma unroll
-            for (int c = 0; c < 25; ++c) sO[row * 32 + c] = o[c];
-        }
-        __syncthreads();
         if (half == 0) {
-            float g[25];
+            float o[25], g[25];
+            {
+                uint32_t v[32];
+                umma::ld32(tbase + laneblk + tc::COL_O, v);
+                umma::wait_ld();
 #pragma unroll
-            for (int c = 0; c < 25; ++c) { o[c] += sO[row * 32 + c] + b2[c]; g[c] = 0.f; }
+                for (int c = 0; c < 25; ++c) { o[c] = __uint_as_float(v[c]) + b2[c]; g[c] = 0.f; }
+            }
             if (valid) {
                 float pred[25], tg[25];
 #pragma unroll
@@ -253,7 +314,7 @@ kc_train_tc_kernel(int hidden, int nch, const float* __restrict__ W1hl, const fl
                 }
             }
 #pragma unroll
-            for (int c = 0; c < 25; ++c) { gb2acc[c] += g[c]; sO[row * 32 + c] = g[c]; o[c] = g[c]; }
+            for (int c = 0; c < 25; ++c) gb2acc[c] += g[c];
             // dO^T as bf16 hi/lo, MN-major [32 outputs x 128 samples] (B operand of the gW2 GEMM)
 #pragma unroll
             for (int gi = 0; gi < 4; ++gi) {
@@ -270,38 +331,32 @@ kc_train_tc_kernel(int hidden, int nch, const float* __restrict__ W1hl, const fl
                     make_uint4(pack_bf16x2(lo[0], lo[1]), pack_bf16x2(lo[2], lo[3]), pack_bf16x2(lo[4], lo[5]), pack_bf16x2(lo[6], lo[7]));
             }
         }
-        __syncthreads();
-        if (half == 1) {
-#pragma unroll
-            for (int c = 0; c < 25; ++c) o[c] = sO[row * 32 + c];   // o now holds dL/do of this row in both halves
-        }
+        umma::fence_before();
         __syncthreads();
         // ---- pass 2: backward ----
         for (int c = 0; c < nch; ++c) {
             if (c > 0) { umma::mbar_wait(barG, phG); phG ^= 1; umma::fence_after(); }  // chunk c-1's gradient MMAs done
-            load_weights(c);
+            load_weights(c, 2);
             umma::fence_async_smem();
             umma::fence_before();
             __syncthreads();
-            if (tid == 0) { umma::fence_after(); issue_gemm1(); }
+            if (tid == 0) { umma::fence_after(); issue_gemm1(); issue_gemm3(); umma::commit(barZ); }
             umma::mbar_wait(barZ, phZ); phZ ^= 1;
             umma::fence_after();
 #pragma unroll 1
             for (int cc = 0; cc < 2; ++cc) {
-                uint32_t v[32];
-                umma::ld32(tbase + laneblk + half * 64 + cc * 32, v);
+                uint32_t v[32], d[32];
+                umma::ld32(tbase + laneblk + tc::COL_Z + half * 64 + cc * 32, v);
+                umma::ld32(tbase + laneblk + tc::COL_O + half * 64 + cc * 32, d);
                 umma::wait_ld();
 #pragma unroll
                 for (int g8 = 0; g8 < 4; ++g8) {
                     float ah[8], al[8], dh[8], dl[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        const int u = half * 64 + cc * 32 + g8 * 8 + j;
                         const float z = __uint_as_float(v[g8 * 8 + j]);
-                        const float a = kc_elu(z), e = kc_elu_grad(z);
-                        const float da = mlp_unit_dot<float, 25>(sW2 + u * 28, o, 0.f);
-                        split_bf16(a, ah[j], al[j]);
-                        split_bf16(da * e, dh[j], dl[j]);
+                        split_bf16(kc_elu(z), ah[j], al[j]);
+                        split_bf16(__uint_as_float(d[g8 * 8 + j]) * kc_elu_grad(z), dh[j], dl[j]);
                     }
                     const uint32_t off = umma::mnmajor_off_b16(half * 64 + cc * 32 + g8 * 8, row, 128);
                     *reinterpret_cast<uint4*>(sm + tc::OFF_A + off) =
@@ -333,14 +388,14 @@ kc_train_tc_kernel(int hidden, int nch, const float* __restrict__ W1hl, const fl
         for (int c = 0; c < nch; ++c) {
             const int u = c * tc::HC + row;
             uint32_t v[32];
-            umma::ld32(tbase + laneblk + 128 + 32 * c, v);
+            umma::ld32(tbase + laneblk + tc::COL_GW1 + 32 * c, v);
             umma::wait_ld();
             if (u < hidden) {
 #pragma unroll
                 for (int k = 0; k < 28; ++k) out[(size_t)u * 28 + k] = __uint_as_float(v[k]);
                 out[ob1 + u] = __uint_as_float(v[28]);
             }
-            umma::ld32(tbase + laneblk + 256 + 32 * c, v);
+            umma::ld32(tbase + laneblk + tc::COL_GW2 + 32 * c, v);
             umma::wait_ld();
             if (u < hidden) {
 #pragma unroll
@@ -369,8 +424,8 @@ kc_train_tc_kernel(int hidden, int nch, const float* __restrict__ W1hl, const fl
     if (warp == 0) umma::tmem_dealloc(tbase, 512);
 }
 
-// Host side: called by kc_train_step (kc_train.cu) when the shape is eligible.  W1hl: nch*2*4096 floats, W2c: nch*3584
-// floats (workspace), partial: grid*NP floats, loss_part: grid doubles.  Returns the grid size used (= number of slices).
+// Host side: called by kc_train_step (kc_train.cu) when the shape is eligible.  W1hl: nch*2*4096 floats, W2b: nch*32768
+// bytes (workspace), partial: grid*NP floats, loss_part: grid doubles.
 int kc_train_tc_grid(int64_t Q) {
     const int64_t ntiles = (Q + tc::TS - 1) / tc::TS;
     int dev = 0, sms = 148;
@@ -380,14 +435,15 @@ int kc_train_tc_grid(int64_t Q) {
 }
 
 int kc_train_tc_launch(const kc_mlp* mlp, float ds, int64_t Q, int T_, int K, const float* X, const float* PHYS,
-                       const float* TGT, float* W1hl, float* W2c, float* partial, int64_t NP, double* loss_part,
+                       const float* TGT, float* W1hl, float* W2c_, float* partial, int64_t NP, double* loss_part,
                        float* pred_out, int grid, cudaStream_t st) {
     const int nch = (mlp->hidden + tc::HC - 1) / tc::HC;
+    unsigned char* W2b = reinterpret_cast<unsigned char*>(W2c_);
     kc_tc_prep_weights_kernel<<<nch, 256, 0, st>>>((const float*)mlp->W1, (const float*)mlp->b1, (const float*)mlp->W2,
-                                                  mlp->hidden, W1hl, W2c);
+                                                  mlp->hidden, W1hl, W2b);
     KC_CHECK_LAUNCH("kc_tc_prep_weights_kernel");
     cudaFuncSetAttribute(kc_train_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
-    kc_train_tc_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(mlp->hidden, nch, W1hl, W2c, (const float*)mlp->b2, ds, Q,
+    kc_train_tc_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(mlp->hidden, nch, W1hl, W2b, (const float*)mlp->b2, ds, Q,
                                                                   T_, K, X, PHYS, TGT, partial, NP, loss_part, pred_out);
     KC_CHECK_LAUNCH("kc_train_tc_kernel");
     return KC_OK;
