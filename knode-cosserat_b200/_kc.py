@@ -99,22 +99,51 @@ def _f64(x):
     return np.asarray(x, dtype=np.float64).reshape(-1)
 
 
+_ATTRS = [("Kse_c0Bse_inv", "Kse_plus_c0_Bse_inv", 9), ("Kbt_c0Bbt_inv", "Kbt_plus_c0_Bbt_inv", 9),
+          ("Bse", "Bse", 9), ("Bbt", "Bbt", 9), ("rhoJ", "rhoJ", 9), ("Kse_vstar", "Kse_vstar", 3),
+          ("rhoAg", "rhoAg", 3), ("C", "C", 3), ("F_tip", "F_tip", 3), ("M_tip", "M_tip", 3),
+          ("p0", "p0", 3), ("h0", "h0", 4), ("q0", "q0", 3), ("w0", "w0", 3), ("tendon_dirs", "tendon_dirs", 12)]
+_SCALARS = ["N", "ds", "c0", "c1", "c2", "rhoA"]
+
+
+def _fingerprint(robot):
+    """Cheap identity of every attribute the struct depends on: object id + in-place version counter for tensors,
+    id + bytes for numpy arrays, value for python scalars.  No device synchronisation."""
+    fp = []
+    for name in _SCALARS:
+        fp.append(float(getattr(robot, name)))
+    for _, attr, _n in _ATTRS:
+        v = getattr(robot, attr)
+        if hasattr(v, "_version"):
+            fp.append((id(v), v._version))
+        elif isinstance(v, np.ndarray):
+            fp.append((id(v), v.tobytes()))
+        else:
+            fp.append(repr(v))
+    return tuple(fp)
+
+
 def rod_params(robot) -> kc_rod_params:
     """Snapshot the derived constants of a CosseratRodTorch / CosseratRod-shaped object
-    (cosserat_ode_torch.py:108-129).  Re-read on every call: callers mutate attributes and then call
-    compute_intermediate_terms() (knode.py:11-53)."""
+    (cosserat_ode_torch.py:108-129).  Callers mutate attributes and then call compute_intermediate_terms()
+    (knode.py:11-53), so the struct is rebuilt whenever any attribute object, its in-place version or a scalar changed;
+    otherwise the cached struct is reused (reading device tensors back costs a synchronisation per attribute)."""
+    fp = _fingerprint(robot)
+    cache = robot.__dict__.get("_kc_params_cache") if hasattr(robot, "__dict__") else None
+    if cache is not None and cache[0] == fp:
+        return cache[1]
     p = kc_rod_params()
     p.N = int(robot.N)
     p.reserved = 0
     p.ds, p.c0, p.c1, p.c2, p.rhoA = (float(robot.ds), float(robot.c0), float(robot.c1), float(robot.c2),
                                       float(robot.rhoA))
-    for name, attr, n in [("Kse_c0Bse_inv", "Kse_plus_c0_Bse_inv", 9), ("Kbt_c0Bbt_inv", "Kbt_plus_c0_Bbt_inv", 9),
-                          ("Bse", "Bse", 9), ("Bbt", "Bbt", 9), ("rhoJ", "rhoJ", 9), ("Kse_vstar", "Kse_vstar", 3),
-                          ("rhoAg", "rhoAg", 3), ("C", "C", 3), ("F_tip", "F_tip", 3), ("M_tip", "M_tip", 3),
-                          ("p0", "p0", 3), ("h0", "h0", 4), ("q0", "q0", 3), ("w0", "w0", 3),
-                          ("tendon_dirs", "tendon_dirs", 12)]:
+    for name, attr, n in _ATTRS:
         v = _f64(getattr(robot, attr))
         if v.size != n:
             raise ValueError(f"robot.{attr} has {v.size} elements, expected {n}")
         getattr(p, name)[:] = v.tolist()
+    if hasattr(robot, "__dict__"):
+        # keep the fingerprinted objects alive: a freed tensor's id() could otherwise be reused by its replacement
+        keep = [getattr(robot, attr) for _, attr, _n in _ATTRS]
+        robot.__dict__["_kc_params_cache"] = (fp, p, keep)
     return p

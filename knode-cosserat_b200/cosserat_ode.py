@@ -63,6 +63,12 @@ class CosseratRod:
         if self.nn_path is not None:
             self.nn_model, self.param_ls = self.get_nn_from_file()
 
+    def __getstate__(self):
+        """Checkpoints pickle the whole object (physics_train.py:284-288): keep it picklable (drop the ctypes cache)."""
+        d = dict(self.__dict__)
+        d.pop("_kc_params_cache", None)
+        return d
+
     def compute_intermediate_terms(self):
         """cosserat_ode.py:58-78 (host-side scalar / 3x3 setup, passed to the kernels through kc_rod_params)."""
         self.A = np.pi * self.r ** 2

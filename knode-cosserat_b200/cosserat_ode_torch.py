@@ -126,6 +126,12 @@ class CosseratRodTorch:
             with torch.no_grad():
                 m.weight.data.normal_(mean, std).abs_()
 
+    def __getstate__(self):
+        """Checkpoints pickle the whole object (physics_train.py:284-288): keep it picklable (drop the ctypes cache)."""
+        d = dict(self.__dict__)
+        d.pop("_kc_params_cache", None)
+        return d
+
     def compute_intermediate_terms(self):
         """Dependent parameters (cosserat_ode_torch.py:108-129).  One-off host-side scalar/3x3 setup: the kernels
         receive these through kc_rod_params, refreshed on every call."""
