@@ -181,7 +181,18 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner on stdout during initialisation; keep stdout for the ONE JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     def barrier():
         if world > 1:
@@ -213,7 +224,7 @@ def main():
     its = plan.iters.cpu().numpy()
     assert its.min() >= 0, "a rod failed to converge during warm-up"
     marches_mean = float(np.abs(its[:, 1:]).mean())
-    rpw = 8
+    rpw = 4   # the wide kernel (B <= 4736 per GPU) packs 4 rods per warp
     marches_warp = float(np.abs(its[:, 1:]).reshape(B // rpw, rpw, T - 1).max(1).mean())
 
     sampler = ClockSampler(local_rank)
@@ -250,7 +261,7 @@ def main():
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     hbm_achieved = rns_per_step * BYTES_PER_RNS / (kern_ms * 1e-3) / 1e9
-    executed_flop = rns_per_step / N_NODES * (N_NODES - 1) * marches_warp * 337.0  # 120 FFMA*2 + 71 FMUL + 26 FADD per node
+    executed_flop = rns_per_step / N_NODES * (N_NODES - 1) * marches_warp * 7 * 337.0  # 7 lanes x (120 FFMA*2 + 71 FMUL + 26 FADD) per node
 
     # ---------------- end to end through the public API (host buffers in, host buffers out) ----------------
     pinned = torch.empty((B, T, 25, N_NODES), dtype=torch.float32).pin_memory()
@@ -344,13 +355,14 @@ def main():
                     "d2h_bytes_per_step": int(pinned.numel() * 4), "api": "knode.simulate(robot, ctl[B,T,4], "
                     "dtype=float32, rows=25) host numpy in -> host numpy out", "ms_per_step": e2e_s / args.steps * 1e3},
             "gpu_launches": 2 * args.steps,
-            "roofline": {"bound": "fp32", "kernel": "kc_rollout_kernel<float,diag,physics>", "achieved": achieved / 1e12,
+            "roofline": {"bound": "fp32", "kernel": "kc_rollout_wide_kernel<float,diag,physics> (8 lanes per rod, Newton + per-march FD Jacobian)", "achieved": achieved / 1e12,
                          "peak": fp32_peak / 1e12, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
                          "peak_source": "kc_fma_peak micro-benchmark measured live in this run (MEASURED_PEAKS.json has "
                                         "no FP32-pipe figure)", "normalisation": "6.06 kFLOP per rod-node-step = 15 "
                          "nominal residual evaluations x 9/10 x 449 FLOP (SURVEY 8d)",
                          "kernel_ms": kern_ms, "executed_tflops": executed_flop / (kern_ms * 1e-3) / 1e12,
-                         "traffic": 366.6e6,
+                         "traffic": 516.3e6, "traffic_source": "ncu dram__bytes_read+write per launch, profiles/r01_ncu_prof_rollout_wide_r1c.csv "
+                         "(algorithmic 416 MB: the trajectory is written once, 106 MB read back for the BDF2 history)",
                          "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak}},
             "cpu_baseline": cpu, "train": train}
         print(json.dumps(out))

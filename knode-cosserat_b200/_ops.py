@@ -194,6 +194,11 @@ class RolloutPlan:
         self.G = torch.empty((B, T, 6), dtype=dtype, device=device) if want_G else None
         self.iters = torch.empty((B, T), dtype=torch.int32, device=device) if want_iters else None
 
+    def rebind(self, P, mlp):
+        """Point a cached plan at the current rod constants / weights (same shapes)."""
+        self.P = P
+        self.mlp, self.mref = _mlp_ref(mlp, self.dtype)
+
     def run(self, tensions, y0=None, z0=None, tol=0.0, max_iter=0):
         _require_cuda(tensions, y0, z0)
         tensions = _c(tensions, self.dtype)

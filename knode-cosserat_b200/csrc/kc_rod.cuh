@@ -152,6 +152,7 @@ KC_HD void rod_ode(const RodC<T>& P, const T* __restrict__ y, const T qh[3], con
 // 16-byte vectors).  The 28/53-term dot product of a hidden unit is split over 4 partial sums so that it is not one serial
 // FMA chain, and two hidden units are in flight per iteration.
 // 4 consecutive values from a 16-byte aligned address as ONE 128-bit load (fp32) / two (fp64)
+#if defined(__CUDACC__)
 KC_HD void kc_ld4(const float* __restrict__ p, float v[4]) {
     const float4 t = *reinterpret_cast<const float4*>(p);
     v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
@@ -161,6 +162,9 @@ KC_HD void kc_ld4(const double* __restrict__ p, double v[4]) {
     const double2 b = *reinterpret_cast<const double2*>(p + 2);
     v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
 }
+#else   // host build of the test harness (tests/emul): no CUDA vector types
+template <typename T> inline void kc_ld4(const T* p, T v[4]) { v[0] = p[0]; v[1] = p[1]; v[2] = p[2]; v[3] = p[3]; }
+#endif
 // bias + sum_k wrow[k] x[k], wrow 16-byte aligned and readable up to the next multiple of 4 (padding is zero-filled or
 // multiplied by nothing: only k < IN is used); 4 partial sums break the serial FMA chain.
 template <typename T, int IN>

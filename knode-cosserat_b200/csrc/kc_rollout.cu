@@ -177,6 +177,141 @@ kc_rollout_wide_kernel(const __grid_constant__ RodC<T> P, const MlpC<T> M, int64
     }
 }
 
+// Wide mode with the linearised final correction (kc_rollout_wide.cuh): the 7 marched states of a rod live in shared
+// memory ([N][25][28 slots] per warp), the accepted state is written to the trajectory by the 8 lanes of the group
+// cooperatively, and the next history is formed from shared memory (no read-back).
+constexpr int KC_WS = 28;  // state slots per warp: 4 rods x 7 points
+template <typename T, bool DIAG, int IN, int NH>
+__global__ void __launch_bounds__(32)
+kc_rollout_wide_lin_kernel(const __grid_constant__ RodC<T> P, const MlpC<T> M, int64_t B, int T_,
+                           const T* __restrict__ tensions, const T* __restrict__ y0, const T* __restrict__ z0,
+                           T* trajD, T tol, int max_iter, T fd_eps, T* Gout, int32_t* iters) {
+    extern __shared__ __align__(16) unsigned char kc_smem[];
+    const int N = P.N;
+    const int lane = threadIdx.x, g = lane >> 3, k = lane & 7;
+    const unsigned full = 0xffffffffu;
+    const int64_t b_raw = (int64_t)blockIdx.x * KC_WG + g;
+    const bool valid = b_raw < B;
+    const int64_t b = valid ? b_raw : B - 1;
+    // shared memory: S [N][25][28] marched states, H [N-1][NH][4] history, A [N-1][NH][4] history rows of the previous state
+    T* Sall = reinterpret_cast<T*>(kc_smem);
+    T* Hs = Sall + (size_t)N * 25 * KC_WS + g;
+    T* As = Sall + (size_t)N * 25 * KC_WS + (size_t)(N - 1) * NH * KC_WG + g;
+    T* Sg = Sall + g * 7;                       // this rod's 7 slots
+    T* traj_b = rod_base(trajD, b, T_, N);
+    const size_t tstride = (size_t)25 * N * KC_LS;
+    const int NV = 25 * N;
+    // initial state -> trajectory index 0 and As
+    for (int e = k; e < NV; e += 8) {
+        const int j = e / 25, r = e - j * 25;
+        T v;
+        if (r < 19) v = y0 ? y0[(size_t)b * 19 * N + r * N + j] : ((r == 2) ? P.ds * T(j) : (r == 3 ? T(1) : T(0)));
+        else v = z0 ? z0[(size_t)b * 6 * N + (r - 19) * N + j] : ((r == 21) ? T(1) : T(0));
+        if (j < N - 1) {
+            const int sl = (NH == 12) ? r - 13 : r;
+            if (sl >= 0) {
+                As[(size_t)(j * NH + sl) * KC_WG] = v;
+                Hs[(size_t)(j * NH + sl) * KC_WG] = (P.c1 + P.c2) * v;   // state[-1] := state[0] (knode.py:65-66)
+            }
+        }
+        if (valid) traj_b[(size_t)e * KC_LS] = v;
+    }
+    if (k == 0 && valid) {
+        if (Gout) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) Gout[(size_t)b * T_ * 6 + i] = T(0);
+        }
+        if (iters) iters[(size_t)b * T_] = 0;
+    }
+    T zlast[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) zlast[c] = z0 ? z0[(size_t)b * 6 * N + c * N + (N - 1)] : ((c == 2) ? T(1) : T(0));
+    __syncwarp();
+    T G[6], Gm1[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { G[i] = T(0); Gm1[i] = T(0); }
+    T Cest = T(0);
+    const T* ten = tensions + (size_t)b * T_ * 4;
+    T tn[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) tn[i] = ten[i];
+    for (int t = 0; t < T_ - 1; ++t) {
+        T tf[3];
+        tendon_force(P, tn, tf);
+        if (t + 1 < T_ - 1) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) tn[i] = ten[(size_t)(t + 1) * 4 + i];
+        }
+        T* nxt = traj_b + (size_t)(t + 1) * tstride;
+        T Gp[6], w[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) { Gp[i] = G[i]; G[i] = G[i] + (G[i] - Gm1[i]); w[i] = T(0); }
+        bool done = false;
+        int status = 0, marches = 0;
+        T sprev = T(0);
+        Cest = T(0);      // the curvature estimate must come from THIS step's own iterations (inputs may jump between steps)
+        HistView<T, NH, KC_WG> H{Hs};
+        while (true) {
+            T eps[6], Ge[6], F[6];
+            wide_eps(G, fd_eps, eps);
+#pragma unroll
+            for (int i = 0; i < 6; ++i) Ge[i] = G[i] + ((k == i + 1) ? eps[i] : T(0));
+            SmemStateSink<T, KC_WS> S{Sg + (k < 7 ? k : 0), k < 7 && !done};
+            rod_march<T, DIAG, IN, NH>(P, M, Ge, tf, H, S, F);
+            T Fall[7][6];
+#pragma unroll
+            for (int c = 0; c < 7; ++c) {
+#pragma unroll
+                for (int i = 0; i < 6; ++i) Fall[c][i] = __shfl_sync(full, F[i], (lane & ~7) | c);
+            }
+            if (!done) {
+                ++marches;
+                const int r = wide_decide_lin(Fall, G, eps, tol, Cest, sprev, w);
+                if (r != 0) { done = true; status = r; }
+                else if (marches >= max_iter) { done = true; status = -1; }
+            }
+            if (__all_sync(full, done)) break;
+        }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) Gm1[i] = Gp[i];
+        __syncwarp();
+        // accepted state = base state (+ first-order correction when status == 2); lane k of the group handles rows
+        // k, k+8, k+16, k+24 of every node (no index arithmetic in the loop)
+        const bool lin = status == 2;
+        for (int j = 0; j < N; ++j) {
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+                const int r = k + 8 * rr;
+                if (r < 25) {
+                    const T* sp = Sg + (size_t)(j * 25 + r) * KC_WS;
+                    T v = sp[0];
+                    if (lin) {
+                        const T v0 = v;
+#pragma unroll
+                        for (int c = 0; c < 6; ++c) v += (sp[c + 1] - v0) * w[c];
+                    }
+                    if (j == N - 1 && r >= 19) v = zlast[r - 19];   // z[:, N-1] is never written by the march
+                    if (valid) nxt[(size_t)(j * 25 + r) * KC_LS] = v;
+                    const int sl = (NH == 12) ? r - 13 : r;          // history for the next step; A <- accepted
+                    if (j < N - 1 && sl >= 0) {
+                        const size_t hi = (size_t)(j * NH + sl) * KC_WG;
+                        Hs[hi] = P.c1 * v + P.c2 * As[hi];
+                        As[hi] = v;
+                    }
+                }
+            }
+        }
+        if (k == 0 && valid) {
+            if (Gout) {
+#pragma unroll
+                for (int i = 0; i < 6; ++i) Gout[((size_t)b * T_ + t + 1) * 6 + i] = G[i];
+            }
+            if (iters) iters[(size_t)b * T_ + t + 1] = status > 0 ? marches : -marches;
+        }
+        __syncwarp();
+    }
+}
+
 // trajD[tile][T][N][25][32] -> traj[B][T][rows][N].  One CTA = one (32-rod tile, time index): the slab is contiguous,
 // staged through a padded shared tile so both sides are coalesced.
 // rows == 50 adds yh,zh = c1*state[t-1] + c2*state[t-2] (state[-1] := state[0]); index 0 repeats [y;z] (knode.py:68).
@@ -328,8 +463,39 @@ static int rollout_typed(const kc_rod_params* Pp, const kc_mlp* mlp, int64_t B, 
         if (e && e[0] == 'w') wide = true;
         if (e && e[0] == 'n') wide = false;
     }
+    if (in_dim != 0) {   // with the MLP in the march every finite-difference lane would pay a full MLP: one rod per lane
+        const char* e = getenv("KC_ROLLOUT_MODE");
+        if (!(e && e[0] == 'w')) wide = false;
+    }
+    // linearised final correction (saves the last verification march) when its shared-memory state fits 7 warps per SM
+    const size_t lsmem = ((size_t)N * 25 * KC_WS + (size_t)2 * (N - 1) * NH * KC_WG) * sizeof(T);
+    bool lin = wide && lsmem <= 32 * 1024;
+    {
+        const char* e = getenv("KC_ROLLOUT_LIN");
+        if (e && e[0] == '0') lin = false;
+        if (e && e[0] == '1' && lsmem <= 200 * 1024) lin = wide;
+    }
     if (B > 0) {
-        if (wide) {
+        if (wide && lin) {
+            const unsigned wgrid = (unsigned)((B + KC_WG - 1) / KC_WG);
+#define KC_LAUNCH_WLIN(D, I, H)                                                                                        \
+    do {                                                                                                               \
+        auto kern = kc_rollout_wide_lin_kernel<T, D, I, H>;                                                            \
+        if (lsmem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem);    \
+        kern<<<wgrid, 32, lsmem, st>>>(P, M, B, (int)T_, (const T*)tensions, (const T*)y0, (const T*)z0, trajD, tl,    \
+                                       max_iter, fd_eps, (T*)G_out, iters);                                            \
+    } while (0)
+            if (P.diag) {
+                if (in_dim == 0) KC_LAUNCH_WLIN(true, 0, 12);
+                else if (in_dim == 28) KC_LAUNCH_WLIN(true, 28, 12);
+                else KC_LAUNCH_WLIN(true, 53, 25);
+            } else {
+                if (in_dim == 0) KC_LAUNCH_WLIN(false, 0, 12);
+                else if (in_dim == 28) KC_LAUNCH_WLIN(false, 28, 12);
+                else KC_LAUNCH_WLIN(false, 53, 25);
+            }
+#undef KC_LAUNCH_WLIN
+        } else if (wide) {
             const size_t wsmem = (size_t)NH * (N - 1) * KC_WG * sizeof(T);
             const unsigned wgrid = (unsigned)((B + KC_WG - 1) / KC_WG);
 #define KC_LAUNCH_WIDE(D, I, H)                                                                                        \

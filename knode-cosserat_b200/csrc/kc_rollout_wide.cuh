@@ -90,3 +90,54 @@ template <typename T, int LS, int NH, int CS> struct TrajSinkPred {
         }
     }
 };
+
+// ---- wide mode with a linearised final correction ------------------------------------------------------------------
+// Every joint march leaves the marched states of all 7 points in shared memory.  Once the Newton step dG is so small that
+// the second-order remainder C*|dG|^2 is below the tolerance, the state at G + dG is formed as
+//     state(G) + sum_c (state(G + eps_c e_c) - state(G)) * dG_c / eps_c
+// instead of marching once more — the same first-order model Newton itself uses, applied to the whole rod.  C (the
+// curvature of the residual map) is estimated from THIS step's own iterations: after a Newton step of size s the new
+// residual is ~ C s^2 (so the correction can be used from the second joint march of a step on, never on stale data).  Returns 1 = converged at G (state = base lane's), 2 = accepted G + dG with the linearised state (w[c] =
+// dG_c/eps_c returned), 0 = G advanced, keep marching, -1 = failure.
+template <typename T>
+KC_HD int wide_decide_lin(const T Fall[7][6], T G[6], const T eps[6], T tol, T& Cest, T& sprev, T w[6]) {
+    const T fn = norm_inf6(Fall[0]);
+    if (!(fn == fn)) return -1;
+    const T scale = kc_max(T(1), norm_inf6(G));
+    if (sprev > T(0)) Cest = kc_max(Cest, fn / (sprev * sprev));   // this residual is what the last step left behind
+    if (fn <= tol * scale) return 1;
+    T Gn[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) Gn[i] = G[i];
+    const int r = wide_decide(Fall, Gn, eps, T(-1));   // tol < 0: always take the Newton step
+    if (r < 0) return -1;
+    T dG[6], s = T(0);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { dG[i] = Gn[i] - G[i]; s = kc_max(s, kc_abs(dG[i])); G[i] = Gn[i]; }
+    sprev = s;
+    if (Cest > T(0) && T(4) * Cest * s * s <= tol * scale) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) w[i] = dG[i] / eps[i];
+        return 2;
+    }
+    return 0;
+}
+
+// Sink that keeps the marched state of one lane in shared memory: [node][row][slot stride SS]
+template <typename T, int SS> struct SmemStateSink {
+    T* p; bool on;
+    KC_HD void put(int j, const T y[19]) {
+        if (on) {
+            T* pn = p + (size_t)j * 25 * SS;
+#pragma unroll
+            for (int r = 0; r < 19; ++r) pn[r * SS] = y[r];
+        }
+    }
+    KC_HD void putz(int j, const T z[6]) {
+        if (on) {
+            T* pn = p + (size_t)j * 25 * SS;
+#pragma unroll
+            for (int c = 0; c < 6; ++c) pn[(19 + c) * SS] = z[c];
+        }
+    }
+};

@@ -59,6 +59,9 @@ def setup_robot(robot, mod=None, original=False):
     robot.compute_intermediate_terms()
 
 
+_PLANS = {}   # output/workspace buffers reused across calls of the same shape (they are overwritten by every call)
+
+
 def _initial_state(robot_reference, B):
     """Straight rod (knode.py:58-64), float64 host arrays [B,19,N], [B,6,N]."""
     N = robot_reference.N
@@ -87,25 +90,44 @@ def simulate(robot, ctl, robot_reference=None, *, dtype=np.float64, rows=50, tol
         raise RuntimeError("knode-cosserat_b200 has no CPU fallback: simulate() needs a CUDA device")
     dev = torch.device("cuda", torch.cuda.current_device())
     tdt = torch.float64 if np.dtype(dtype) == np.float64 else torch.float32
-    ctl_np = np.asarray(ctl, dtype=np.float64)
-    single = ctl_np.ndim == 2
+    if torch.is_tensor(ctl):
+        tens = ctl.to(dev, tdt)
+    else:
+        ctl_np = np.asarray(ctl)
+        if ctl_np.dtype != np.dtype(dtype):
+            ctl_np = ctl_np.astype(np.float64).astype(dtype)   # lists / ints go through float64 like knode.py:71
+        tens = torch.from_numpy(np.ascontiguousarray(ctl_np)).to(dev, non_blocking=True)
+    single = tens.ndim == 2
     if single:
-        ctl_np = ctl_np[None]
-    B, T, _ = ctl_np.shape
+        tens = tens[None]
+    B, T, _ = tens.shape
     # the reference leaves the last applied tensions on the robot (knode.py:71)
-    robot.tendon_tensions = np.array(ctl_np[-1, -1]).astype(np.float64) if T > 0 else robot.tendon_tensions
-    y0, z0 = _initial_state(robot_reference, B)
+    if T > 0 and B > 0:
+        last = ctl[-1] if single else ctl[-1][-1]
+        robot.tendon_tensions = np.array(last.detach().cpu() if torch.is_tensor(last) else last).astype(np.float64)
     P = _kc.rod_params(robot)
     mlp = _robot_mlp(robot, tdt)
-    tens = torch.as_tensor(ctl_np).to(dev, tdt, non_blocking=True)
-    traj, G, iters = _ops.rollout(P, mlp, tens, torch.as_tensor(y0).to(dev, tdt), torch.as_tensor(z0).to(dev, tdt),
-                                  tol=tol, max_iter=max_iter, rows=rows, want_G=return_info)
+    # initial state: the kernel builds the straight rod of knode.py:58-64 itself; an explicit y0/z0 is only needed when
+    # another robot defines the geometry (robot_reference) or in fp64, where linspace's exact end point is reproduced
+    y0 = z0 = None
+    if robot_reference is not robot or tdt == torch.float64:
+        y0n, z0n = _initial_state(robot_reference, B)
+        y0, z0 = torch.as_tensor(y0n).to(dev, tdt), torch.as_tensor(z0n).to(dev, tdt)
+    key = (B, T, rows, tdt, dev, int(P.N), None if mlp is None else (mlp.in_dim, mlp.hidden), bool(return_info))
+    plan = _PLANS.get(key)
+    if plan is None:
+        if len(_PLANS) >= 4:
+            _PLANS.clear()
+        plan = _PLANS[key] = _ops.RolloutPlan(P, mlp, B, T, tdt, dev, rows, want_G=return_info)
+    plan.rebind(P, mlp)
+    plan.run(tens, y0, z0, tol=tol, max_iter=max_iter)
+    traj, G, iters = plan.traj, plan.G, plan.iters
     if pinned_out is not None:
         pinned_out.copy_(traj, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         out = pinned_out.numpy()
     else:
-        out = traj.cpu().numpy()
+        out = traj.cpu().numpy()   # a fresh host array: the device buffers of the cached plan are reused by later calls
     if single:
         out = out[0]
     if return_info:

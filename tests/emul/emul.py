@@ -48,7 +48,7 @@ def rollout(P, ctl, dtype=np.float64, mlp=None, tol=0.0, max_iter=60, wide=False
     rc = lib().kc_emul_rollout(C.c_int(0 if dtype == np.float32 else 1), C.byref(p), C.c_int(in_dim), C.c_int(hidden),
                                *ptrs, C.c_int64(B), C.c_int64(T), ctl.ctypes.data_as(C.c_void_p),
                                traj.ctypes.data_as(C.c_void_p), iters.ctypes.data_as(C.c_void_p),
-                               G.ctypes.data_as(C.c_void_p), C.c_double(tol), C.c_int(max_iter), C.c_int(1 if wide else 0))
+                               G.ctypes.data_as(C.c_void_p), C.c_double(tol), C.c_int(max_iter), C.c_int(int(wide)))
     assert rc == 0
     # device layout per rod is [T][25*N] with k = row*N + node: already [T,25,N]
     return traj, iters, G

@@ -91,6 +91,65 @@ static void run_wide(const RodC<T>& P, const MlpC<T>& M, int64_t B, int64_t T_, 
     }
 }
 
+// wide mode with the linearised final correction (wide_decide_lin), emulated lane by lane
+template <typename T, bool DIAG, int IN, int NH>
+static void run_wide_lin(const RodC<T>& P, const MlpC<T>& M, int64_t B, int64_t T_, const T* ten, T* traj, int32_t* iters,
+                         T* Gout, T tol, int max_iter, T fd_eps) {
+    const int N = P.N, NV = 25 * N;
+    std::vector<T> A(NV), Hs((size_t)NH * (N - 1)), S((size_t)7 * NV), out_t(NV);
+    for (int64_t b = 0; b < B; ++b) {
+        rollout_init<T, 1>(P, nullptr, nullptr, A.data());
+        auto emit = [&](int64_t t, const std::vector<T>& st) {
+            for (int j = 0; j < N; ++j)
+                for (int r = 0; r < 25; ++r) traj[(((size_t)b * T_ + t) * 25 + r) * N + j] = st[(size_t)j * 25 + r];
+        };
+        emit(0, A);
+        if (iters) iters[b * T_] = 0;
+        build_history<T, NH, 1>(P, A.data(), A.data(), Hs.data());
+        T zlast[6];
+        for (int c = 0; c < 6; ++c) zlast[c] = A[(size_t)(N - 1) * 25 + 19 + c];
+        T G[6] = {0, 0, 0, 0, 0, 0}, Gm1[6] = {0, 0, 0, 0, 0, 0}, Cest = 0;
+        for (int t = 0; t < T_ - 1; ++t) {
+            T tn[4], tf[3];
+            for (int i = 0; i < 4; ++i) tn[i] = ten[(b * T_ + t) * 4 + i];
+            tendon_force(P, tn, tf);
+            T Gp[6], w[6] = {0, 0, 0, 0, 0, 0};
+            for (int i = 0; i < 6; ++i) { Gp[i] = G[i]; G[i] = G[i] + (G[i] - Gm1[i]); }
+            int marches = 0, status = 0;
+            T sprev = 0;
+            Cest = T(0);
+            HistView<T, NH, 1> H{Hs.data()};
+            while (true) {
+                T eps[6], Fall[7][6];
+                wide_eps(G, fd_eps, eps);
+                for (int k = 0; k < 7; ++k) {
+                    T Ge[6];
+                    for (int i = 0; i < 6; ++i) Ge[i] = G[i] + ((k == i + 1) ? eps[i] : T(0));
+                    SmemStateSink<T, 1> Sk{S.data() + (size_t)k * NV, true};
+                    rod_march<T, DIAG, IN, NH>(P, M, Ge, tf, H, Sk, Fall[k]);
+                }
+                ++marches;
+                const int r = wide_decide_lin(Fall, G, eps, tol, Cest, sprev, w);
+                if (r != 0) { status = r; break; }
+                if (marches >= max_iter) { status = -1; break; }
+            }
+            for (int i = 0; i < 6; ++i) Gm1[i] = Gp[i];
+            for (int e = 0; e < NV; ++e) {
+                T v = S[e];
+                if (status == 2) { const T v0 = v; for (int c = 0; c < 6; ++c) v += (S[(size_t)(c + 1) * NV + e] - v0) * w[c]; }
+                const int j = e / 25, r = e - j * 25;
+                if (j == N - 1 && r >= 19) v = zlast[r - 19];
+                out_t[e] = v;
+            }
+            build_history<T, NH, 1>(P, out_t.data(), A.data(), Hs.data());
+            A = out_t;
+            emit(t + 1, A);
+            if (Gout) for (int i = 0; i < 6; ++i) Gout[(b * T_ + t + 1) * 6 + i] = G[i];
+            if (iters) iters[b * T_ + t + 1] = status > 0 ? marches : -marches;
+        }
+    }
+}
+
 template <typename T>
 static int emul(const kc_rod_params* p, int in_dim, int hidden, const void* W1, const void* b1, const void* W2,
                 const void* b2, int64_t B, int64_t T_, const void* ten, void* traj, int32_t* iters, void* Gout,
@@ -107,7 +166,8 @@ static int emul(const kc_rod_params* p, int in_dim, int hidden, const void* W1, 
     const T tl = tol > 0 ? T(tol) : (sizeof(T) == 4 ? T(2e-6) : T(1e-11));
 #define GO(D, I, H)                                                                                             \
     do {                                                                                                        \
-        if (wide) run_wide<T, D, I, H>(P, M, B, T_, (const T*)ten, (T*)traj, iters, (T*)Gout, tl, max_iter, fd_eps); \
+        if (wide == 2) run_wide_lin<T, D, I, H>(P, M, B, T_, (const T*)ten, (T*)traj, iters, (T*)Gout, tl, max_iter, fd_eps); \
+        else if (wide) run_wide<T, D, I, H>(P, M, B, T_, (const T*)ten, (T*)traj, iters, (T*)Gout, tl, max_iter, fd_eps); \
         else run<T, D, I, H>(P, M, B, T_, (const T*)ten, (T*)traj, iters, (T*)Gout, tl, max_iter, fd_eps);      \
     } while (0)
     if (P.diag) { if (in_dim == 0) GO(true, 0, 12); else if (in_dim == 28) GO(true, 28, 12); else GO(true, 53, 25); }
