@@ -119,6 +119,15 @@ int kc_rollout_fwd(int dtype, const kc_rod_params *P, const kc_mlp *mlp, int64_t
                    int32_t rows, void *traj, void *G_out, int32_t *iters, void *workspace,
                    int64_t workspace_bytes, void *stream);
 
+/* Reverse mode THROUGH kc_rollout_fwd (back-propagation through time; BASELINE.json north_star subsystem 3 — an extension:
+ * the reference never differentiates a rollout).  traj[B][T][25][N] is the forward result (rows = 25),
+ * g_traj[B][T][25][N] = dL/dtraj -> g_tensions[B][T][4] (may be NULL) and, with an MLP, the OVERWRITTEN parameter
+ * cotangents gW1, gb1, gW2, gb2 (may be NULL).  The shooting solve is differentiated by the implicit function theorem. */
+int64_t kc_rollout_bwd_workspace_bytes(int dtype, const kc_rod_params *P, const kc_mlp *mlp, int64_t B, int64_t T);
+int kc_rollout_bwd(int dtype, const kc_rod_params *P, const kc_mlp *mlp, int64_t B, int64_t T, const void *tensions,
+                   const void *traj, const void *g_traj, void *g_tensions, void *gW1, void *gb1, void *gW2, void *gb2,
+                   void *workspace, int64_t workspace_bytes, void *stream);
+
 /* One teacher-forced training step of physics_train.py's fast path (:313-368) == slow path (:215-267) restricted
  * to its key nodes == train_segment.py:140-185: for every trajectory b, step t in [0, T-2] and key node k:
  * ODE+MLP at node k-1 of the NEXT ground-truth state, Euler step, 4-term MSE loss (p | n,m,q,w | euler(h) | z,

@@ -53,6 +53,10 @@ _SIGNATURES = {
     "kc_rollout_fwd": (C.c_int, [C.c_int, C.POINTER(kc_rod_params), C.POINTER(kc_mlp), C.c_int64, C.c_int64,
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int32, C.c_int32, C.c_void_p,
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "kc_rollout_bwd_workspace_bytes": (C.c_int64, [C.c_int, C.POINTER(kc_rod_params), C.POINTER(kc_mlp), C.c_int64,
+                                                   C.c_int64]),
+    "kc_rollout_bwd": (C.c_int, [C.c_int, C.POINTER(kc_rod_params), C.POINTER(kc_mlp), C.c_int64, C.c_int64]
+                       + [C.c_void_p] * 9 + [C.c_int64, C.c_void_p]),
     "kc_train_step_workspace_bytes": (C.c_int64, [C.c_int, C.POINTER(kc_mlp), C.c_int64, C.c_int64, C.c_int32]),
     "kc_train_step": (C.c_int, [C.c_int, C.POINTER(kc_rod_params), C.POINTER(kc_mlp), C.c_int64, C.c_int64, C.c_int32,
                                 C.POINTER(C.c_int32)] + [C.c_void_p] * 9 + [C.c_int64, C.c_void_p]),

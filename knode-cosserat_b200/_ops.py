@@ -224,6 +224,30 @@ def rollout(P, mlp, tensions, y0=None, z0=None, tol=0.0, max_iter=0, rows=25, wa
     return plan.traj, plan.G, plan.iters
 
 
+def rollout_bwd(P, mlp, tensions, traj, g_traj, want_g_tensions=True, want_params=True):
+    """kc_rollout_bwd: reverse mode through the rollout.  tensions[B,T,4], traj[B,T,25,N] (forward result), g_traj
+    (dL/dtraj) -> (g_tensions|None, gW1, gb1, gW2, gb2 | Nones)."""
+    _require_cuda(tensions, traj, g_traj)
+    dt = traj.dtype
+    dev = traj.device
+    tensions, traj, g_traj = _c(tensions, dt), _c(traj), _c(g_traj, dt)
+    B, T, rows, N = traj.shape
+    if rows != 25:
+        raise ValueError("rollout_bwd needs the 25-row trajectory [y;z]")
+    keep, mref = _mlp_ref(mlp, dt)
+    gt = torch.empty_like(tensions) if want_g_tensions else None
+    gp = [None] * 4
+    if mlp is not None and want_params:
+        gp = [torch.empty_like(t) for t in (keep.W1, keep.b1, keep.W2, keep.b2)]
+    with torch.cuda.device(dev):
+        nbytes = int(_kc.lib().kc_rollout_bwd_workspace_bytes(_dtype_code(traj), C.byref(P), mref, B, T))
+        ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=dev)
+        rc = _kc.lib().kc_rollout_bwd(_dtype_code(traj), C.byref(P), mref, B, T, _ptr(tensions), _ptr(traj), _ptr(g_traj),
+                                      _ptr(gt), *[_ptr(g) for g in gp], _ptr(ws), nbytes, _stream(dev))
+    _kc.check(rc, "kc_rollout_bwd")
+    return (gt, *gp)
+
+
 def train_step(P, mlp, traj, controls, key_idx, want_pred=False):
     """kc_train_step: traj[B,T,25,N], controls[B,T,4] -> (loss float64[1] tensor, (gW1,gb1,gW2,gb2), pred|None)."""
     _require_cuda(traj, controls)

@@ -63,6 +63,30 @@ class _MLPFunction(torch.autograd.Function):
         return tuple(g_ if ctx.needs_input_grad[i] else None for i, g_ in enumerate(out))
 
 
+class _RolloutFunction(torch.autograd.Function):
+    """kc_rollout_fwd / kc_rollout_bwd as one differentiable op: (tensions, W1, b1, W2, b2) -> traj[B,T,25,N].
+    Reverse mode = back-propagation through time with the shooting solve differentiated implicitly."""
+
+    @staticmethod
+    def forward(ctx, P, use_nn, tol, tensions, W1, b1, W2, b2):
+        mlp = _ops.Mlp(W1, b1, W2, b2) if use_nn else None
+        traj, _, iters = _ops.rollout(P, mlp, tensions, tol=tol, rows=25)
+        ctx.P, ctx.use_nn = P, use_nn
+        ctx.save_for_backward(tensions, traj, W1, b1, W2, b2)
+        ctx.mark_non_differentiable(iters)
+        return traj, iters
+
+    @staticmethod
+    def backward(ctx, g_traj, _g_iters):
+        tensions, traj, W1, b1, W2, b2 = ctx.saved_tensors
+        mlp = _ops.Mlp(W1, b1, W2, b2) if ctx.use_nn else None
+        out = _ops.rollout_bwd(ctx.P, mlp, tensions, traj, g_traj.contiguous(),
+                               want_g_tensions=ctx.needs_input_grad[3],
+                               want_params=ctx.use_nn and any(ctx.needs_input_grad[4:8]))
+        gp = [g if (g is not None and ctx.needs_input_grad[4 + i]) else None for i, g in enumerate(out[1:])]
+        return (None, None, None, out[0] if ctx.needs_input_grad[3] else None, *gp)
+
+
 class CosseratRodTorch:
     def __init__(self, device, n_layers, nn_input_history=False):
         self.device = device
@@ -242,6 +266,25 @@ class CosseratRodTorch:
         dys, zs_new = self.ODE_parallel(all_ys, all_yh, all_zh, all_tf)
         ys_next = all_ys + self.ds * dys
         return torch.cat([ys_next, zs_new], dim=1).reshape(S, K, 25).transpose(1, 2)
+
+    # ------------------------------------------------------------------------------------------------------------
+    # differentiable time rollout (extension: the reference has no torch rollout and never back-propagates through one)
+    # ------------------------------------------------------------------------------------------------------------
+    def rollout(self, tensions, tol=0.0, return_iters=False):
+        """Roll B rods out under tensions[B,T,4] (or [T,4]) from the straight rod: -> traj[B,T,25,N], same semantics as
+        knode.simulate (index 0 = initial state).  Differentiable w.r.t. the MLP parameters and the tensions
+        (kc_rollout_bwd: BPTT, implicit differentiation of the shooting solve)."""
+        single = tensions.ndim == 2
+        t3 = tensions.unsqueeze(0) if single else tensions
+        dt = t3.dtype
+        if self.use_nn:
+            W = [w if w.dtype == dt else w.to(dt) for w in self._weights()]
+        else:
+            W = [None, None, None, None]
+        traj, iters = _RolloutFunction.apply(self._params(), bool(self.use_nn), float(tol), t3.contiguous(), *W)
+        if single:
+            traj, iters = traj[0], iters[0]
+        return (traj, iters) if return_iters else traj
 
     # ------------------------------------------------------------------------------------------------------------
     # fused training step (what the drop-in training scripts call instead of the Python loops)

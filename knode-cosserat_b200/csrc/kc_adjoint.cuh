@@ -187,3 +187,25 @@ KC_HD void rod_ode_vjp(const RodC<T>& P, const T* __restrict__ y, const T qh[3],
 #pragma unroll
     for (int i = 0; i < 4; ++i) gy[3 + i] = gh[i];
 }
+
+// Reverse mode of the MLP with respect to its INPUT: gx = W1^T ((W2^T go) * ELU'(W1 x + b1)), packed weights (MlpC).
+template <typename T, int IN>
+KC_HD void mlp_input_vjp(const MlpC<T>& M, const T* __restrict__ x, const T* __restrict__ go, T* __restrict__ gx) {
+    const int inP = (IN + 3) & ~3;
+#pragma unroll
+    for (int k = 0; k < IN; ++k) gx[k] = T(0);
+    for (int i = 0; i < M.hidden; ++i) {
+        const T* __restrict__ wrow = M.Wp + (size_t)i * M.stride;
+        const T z1 = mlp_unit_dot<T, IN>(wrow, x, wrow[inP]);
+        const T da = mlp_unit_dot<T, 25>(wrow + inP + 4, go, T(0));
+        const T dz = da * kc_elu_grad(z1);
+#pragma unroll
+        for (int k = 0; k < IN; k += 4) {
+            T w[4];
+            kc_ld4(wrow + k, w);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if (k + j < IN) gx[k + j] += dz * w[j];
+        }
+    }
+}
+

@@ -1,0 +1,124 @@
+// kc_bptt.cu — kc_rollout_bwd: reverse mode through the batched rollout (north-star subsystem 3, SURVEY kernel K5).
+// One rod per thread (kc_bptt_core.cuh); the four history-cotangent arrays of a rod live in shared memory; every node
+// evaluation of the two adjoint marches emits an MLP sample (x, dL/do) and kc_mlp_bwd's tiled reduction kernels turn the
+// B*(T-1)*(N-1)*2 samples into gW1, gb1, gW2, gb2.
+#include <cuda_runtime.h>
+#include <cstdlib>
+#include "kc_bptt_core.cuh"
+
+template <typename T> int kc_pack_mlp(const kc_mlp* mlp, T* Wp, MlpC<T>& M, cudaStream_t st);
+int kc_check_mlp(const kc_mlp* mlp);
+
+template <typename T, bool DIAG, int IN, int NH>
+__global__ void __launch_bounds__(32)
+kc_rollout_bwd_kernel(const __grid_constant__ RodC<T> P, const MlpC<T> M, int64_t B, int T_, int rpw,
+                      const T* __restrict__ tensions, const T* __restrict__ traj, const T* __restrict__ gtraj,
+                      T* __restrict__ gten, T* __restrict__ xs, T* __restrict__ gos, T fd_eps) {
+    extern __shared__ __align__(16) unsigned char kc_smem[];
+    const int N = P.N;
+    const int64_t b = (int64_t)blockIdx.x * rpw + threadIdx.x;
+    if ((int)threadIdx.x >= rpw || b >= B) return;
+    T* Hs = reinterpret_cast<T*>(kc_smem) + threadIdx.x;
+    const size_t per_rod = (size_t)(T_ - 1) * (N - 1) * 2;
+    bptt_rod<T, DIAG, IN, NH, 32>(P, M, traj + (size_t)b * T_ * 25 * N, gtraj + (size_t)b * T_ * 25 * N,
+                                  tensions + (size_t)b * T_ * 4, gten ? gten + (size_t)b * T_ * 4 : nullptr, T_, Hs,
+                                  IN > 0 ? xs + b * per_rod * (IN > 0 ? IN : 1) : nullptr,
+                                  IN > 0 ? gos + b * per_rod * 25 : nullptr, fd_eps);
+}
+
+static inline size_t a256(size_t x) { return (x + 255) & ~(size_t)255; }
+struct BpttWs { size_t xs, gos, wp, mlpws, total; int64_t Qs; int64_t mlp_bytes; };
+static BpttWs bptt_ws(int dtype, int N, const kc_mlp* mlp, int64_t B, int64_t T_) {
+    const size_t sz = dtype == KC_F32 ? 4 : 8;
+    BpttWs w{};
+    w.Qs = mlp ? B * (T_ - 1) * (N - 1) * 2 : 0;
+    size_t off = 0;
+    w.xs = off; off += a256((size_t)w.Qs * (mlp ? mlp->in_dim : 0) * sz);
+    w.gos = off; off += a256((size_t)w.Qs * 25 * sz);
+    w.wp = off; off += mlp ? a256((size_t)mlp->hidden * (((mlp->in_dim + 3) & ~3) + 32) * sz) : 0;
+    w.mlp_bytes = mlp ? kc_ode_bwd_workspace_bytes(dtype, mlp, w.Qs) : 0;
+    w.mlpws = off; off += a256((size_t)w.mlp_bytes);
+    w.total = off + 256;
+    return w;
+}
+
+extern "C" int64_t kc_rollout_bwd_workspace_bytes(int dtype, const kc_rod_params* P, const kc_mlp* mlp, int64_t B, int64_t T_) {
+    if (!P || P->N < 2 || B < 0 || T_ < 1 || (dtype != KC_F32 && dtype != KC_F64)) return KC_EINVAL;
+    if (mlp && kc_check_mlp(mlp)) return KC_EINVAL;
+    return (int64_t)bptt_ws(dtype, P->N, mlp, B, T_).total;
+}
+
+template <typename T>
+static int bwd_typed(const kc_rod_params* Pp, const kc_mlp* mlp, int64_t B, int64_t T_, const void* tensions,
+                     const void* traj, const void* gtraj, void* gten, void* gW1, void* gb1, void* gW2, void* gb2,
+                     void* workspace, cudaStream_t st) {
+    const RodC<T> P = make_rodc<T>(*Pp);
+    const int N = P.N, dtype = sizeof(T) == 4 ? KC_F32 : KC_F64;
+    const BpttWs w = bptt_ws(dtype, N, mlp, B, T_);
+    unsigned char* ws = (unsigned char*)workspace;
+    MlpC<T> M{};
+    const int in_dim = mlp ? mlp->in_dim : 0;
+    if (mlp) {
+        int rc = kc_pack_mlp<T>(mlp, (T*)(ws + w.wp), M, st);
+        if (rc) return rc;
+    }
+    const int NH = in_dim == 53 ? 25 : 12;
+    const size_t smem = (size_t)4 * NH * (N - 1) * 32 * sizeof(T);
+    KC_CHECK_ARG(smem <= 227 * 1024, "N=%d too large for the shared-memory history cotangents (%zu B)", N, smem);
+    int rpw = 32;
+    {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int64_t slots = (int64_t)sms * 4;
+        while (rpw > 8 && (B + rpw / 2 - 1) / (rpw / 2) <= slots) rpw >>= 1;
+    }
+    const T fd_eps = sizeof(T) == 4 ? T(1e-2) : T(1e-6);
+    T* xs = (T*)(ws + w.xs);
+    T* gos = (T*)(ws + w.gos);
+    if (B > 0 && T_ > 1) {
+        const unsigned grid = (unsigned)((B + rpw - 1) / rpw);
+#define KC_LAUNCH_BWD(D, I, H)                                                                                         \
+    do {                                                                                                               \
+        auto kern = kc_rollout_bwd_kernel<T, D, I, H>;                                                                 \
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
+        kern<<<grid, 32, smem, st>>>(P, M, B, (int)T_, rpw, (const T*)tensions, (const T*)traj, (const T*)gtraj,       \
+                                     (T*)gten, xs, gos, fd_eps);                                                       \
+    } while (0)
+        if (P.diag) {
+            if (in_dim == 0) KC_LAUNCH_BWD(true, 0, 12);
+            else if (in_dim == 28) KC_LAUNCH_BWD(true, 28, 12);
+            else KC_LAUNCH_BWD(true, 53, 25);
+        } else {
+            if (in_dim == 0) KC_LAUNCH_BWD(false, 0, 12);
+            else if (in_dim == 28) KC_LAUNCH_BWD(false, 28, 12);
+            else KC_LAUNCH_BWD(false, 53, 25);
+        }
+#undef KC_LAUNCH_BWD
+        KC_CHECK_LAUNCH("kc_rollout_bwd_kernel");
+    }
+    if (mlp && (gW1 || gb1 || gW2 || gb2))
+        return kc_mlp_bwd(dtype, mlp, (B > 0 && T_ > 1) ? w.Qs : 0, xs, gos, nullptr, gW1, gb1, gW2, gb2, ws + w.mlpws,
+                          w.mlp_bytes, (void*)st);
+    return KC_OK;
+}
+
+extern "C" int kc_rollout_bwd(int dtype, const kc_rod_params* P, const kc_mlp* mlp, int64_t B, int64_t T_,
+                              const void* tensions, const void* traj, const void* g_traj, void* g_tensions, void* gW1,
+                              void* gb1, void* gW2, void* gb2, void* workspace, int64_t workspace_bytes, void* stream) {
+    KC_CHECK_ARG(dtype == KC_F32 || dtype == KC_F64, "dtype must be KC_F32 or KC_F64");
+    KC_CHECK_ARG(P && P->N >= 2, "rod params missing or N < 2");
+    KC_CHECK_ARG(B >= 0 && T_ >= 1, "B must be >= 0 and T >= 1");
+    KC_CHECK_ARG(B == 0 || (tensions && traj && g_traj && workspace), "NULL tensions/traj/g_traj/workspace");
+    int rc = kc_check_mlp(mlp);
+    if (rc) return rc;
+    const int64_t need = kc_rollout_bwd_workspace_bytes(dtype, P, mlp, B, T_);
+    if (workspace_bytes < need) {
+        kc_set_error("workspace too small: %lld < %lld", (long long)workspace_bytes, (long long)need);
+        return KC_ENOSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == KC_F32)
+        return bwd_typed<float>(P, mlp, B, T_, tensions, traj, g_traj, g_tensions, gW1, gb1, gW2, gb2, workspace, st);
+    return bwd_typed<double>(P, mlp, B, T_, tensions, traj, g_traj, g_tensions, gW1, gb1, gW2, gb2, workspace, st);
+}

@@ -4,26 +4,6 @@
 // parameter cotangents are wanted, the kernel also emits X[Q][XPG] and dO[Q][32] and the train-step kernels 3+4 reduce
 // them to gW1, gb1, gW2, gb2.
 
-template <typename T, int IN>
-KC_HD void mlp_input_vjp(const MlpC<T>& M, const T* __restrict__ x, const T* __restrict__ go, T* __restrict__ gx) {
-    const int inP = (IN + 3) & ~3;
-#pragma unroll
-    for (int k = 0; k < IN; ++k) gx[k] = T(0);
-    for (int i = 0; i < M.hidden; ++i) {
-        const T* __restrict__ wrow = M.Wp + (size_t)i * M.stride;
-        const T z1 = mlp_unit_dot<T, IN>(wrow, x, wrow[inP]);
-        const T da = mlp_unit_dot<T, 25>(wrow + inP + 4, go, T(0));
-        const T dz = da * kc_elu_grad(z1);
-#pragma unroll
-        for (int k = 0; k < IN; k += 4) {
-            T w[4];
-            kc_ld4(wrow + k, w);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) if (k + j < IN) gx[k + j] += dz * w[j];
-        }
-    }
-}
-
 template <typename T, bool DIAG, int IN>
 __global__ void __launch_bounds__(128)
 kc_ode_bwd_kernel(const __grid_constant__ RodC<T> P, const MlpC<T> M, int64_t Q, const T* __restrict__ y,

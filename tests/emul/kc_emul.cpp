@@ -5,6 +5,7 @@
 #include <vector>
 #include <cstring>
 #include "../../knode-cosserat_b200/csrc/kc_rollout_wide.cuh"
+#include "../../knode-cosserat_b200/csrc/kc_bptt_core.cuh"
 
 void kc_set_error(const char*, ...) {}
 
@@ -180,4 +181,43 @@ extern "C" int kc_emul_rollout(int dtype, const kc_rod_params* p, int in_dim, in
                                int32_t* iters, void* Gout, double tol, int max_iter, int wide) {
     if (dtype == KC_F32) return emul<float>(p, in_dim, hidden, W1, b1, W2, b2, B, T_, ten, traj, iters, Gout, tol, max_iter, wide);
     return emul<double>(p, in_dim, hidden, W1, b1, W2, b2, B, T_, ten, traj, iters, Gout, tol, max_iter, wide);
+}
+
+// ---- BPTT (reverse mode through the rollout), one rod after the other ----------------------------------------------
+template <typename T, bool DIAG, int IN, int NH>
+static void run_bptt(const RodC<T>& P, const MlpC<T>& M, int64_t B, int64_t T_, const T* ten, const T* traj, const T* gtraj,
+                     T* gten, T* xs, T* gos, T fd_eps) {
+    const int N = P.N;
+    std::vector<T> Hs((size_t)4 * NH * (N - 1));
+    const size_t per_rod = (size_t)(T_ - 1) * (N - 1) * 2;
+    for (int64_t b = 0; b < B; ++b)
+        bptt_rod<T, DIAG, IN, NH, 1>(P, M, traj + (size_t)b * T_ * 25 * N, gtraj + (size_t)b * T_ * 25 * N, ten + b * T_ * 4,
+                                     gten ? gten + b * T_ * 4 : nullptr, (int)T_, Hs.data(),
+                                     IN > 0 ? xs + b * per_rod * (IN > 0 ? IN : 1) : nullptr, IN > 0 ? gos + b * per_rod * 25 : nullptr, fd_eps);
+}
+
+template <typename T>
+static int emul_bptt(const kc_rod_params* p, int in_dim, int hidden, const void* W1, const void* b1, const void* W2,
+                     const void* b2, int64_t B, int64_t T_, const void* ten, const void* traj, const void* gtraj, void* gten,
+                     void* xs, void* gos) {
+    RodC<T> P = make_rodc<T>(*p);
+    MlpC<T> M{};
+    std::vector<T> Wp;
+    if (in_dim) {
+        int inP, stride;
+        pack_mlp<T>((const T*)W1, (const T*)b1, (const T*)W2, in_dim, hidden, Wp, inP, stride);
+        M.Wp = Wp.data(); M.b2 = (const T*)b2; M.in_dim = in_dim; M.inP = inP; M.hidden = hidden; M.stride = stride;
+    }
+    const T fd_eps = sizeof(T) == 4 ? T(1e-2) : T(1e-6);
+#define GOB(D, I, H) run_bptt<T, D, I, H>(P, M, B, T_, (const T*)ten, (const T*)traj, (const T*)gtraj, (T*)gten, (T*)xs, (T*)gos, fd_eps)
+    if (P.diag) { if (in_dim == 0) GOB(true, 0, 12); else if (in_dim == 28) GOB(true, 28, 12); else GOB(true, 53, 25); }
+    else        { if (in_dim == 0) GOB(false, 0, 12); else if (in_dim == 28) GOB(false, 28, 12); else GOB(false, 53, 25); }
+    return 0;
+}
+
+extern "C" int kc_emul_bptt(int dtype, const kc_rod_params* p, int in_dim, int hidden, const void* W1, const void* b1,
+                            const void* W2, const void* b2, int64_t B, int64_t T_, const void* ten, const void* traj,
+                            const void* gtraj, void* gten, void* xs, void* gos) {
+    if (dtype == KC_F32) return emul_bptt<float>(p, in_dim, hidden, W1, b1, W2, b2, B, T_, ten, traj, gtraj, gten, xs, gos);
+    return emul_bptt<double>(p, in_dim, hidden, W1, b1, W2, b2, B, T_, ten, traj, gtraj, gten, xs, gos);
 }
