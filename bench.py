@@ -323,6 +323,69 @@ def main():
                  "useful_tflops": q * FLOP_PER_TRAIN_SAMPLE / (tms * 1e-3) / 1e12, "hidden": TRAIN_H,
                  "loss": float(loss.item()), "kernels_per_step": 4 + 4 + 1}
 
+    # ---------------- KNODE rollout training step (C3 ii, north-star extension): rollout + loss + BPTT + Adam ----------
+    bptt = None
+    if not args.no_train:
+        from Utils.transformations import quaternion_to_euler
+        torch.manual_seed(1)
+        brobot = CosseratRodTorch(str(dev), TRAIN_H)
+        setup_robot(brobot, "youngs")
+        with torch.no_grad():   # a trained-size residual (the reference's random init is unstable inside a rollout)
+            brobot.nn_models[2].weight.mul_(0.02)
+            brobot.nn_models[2].bias.mul_(0.02)
+        nb = TRAIN_B // world
+        target = plan.traj[:nb, :TRAIN_T].contiguous()
+        btens = ctl[:nb, :TRAIN_T].contiguous()
+        key = torch.tensor(TRAIN_KEYS, device=dev)
+        BW = [p for p in brobot.nn_models.parameters()]
+        bm = [torch.zeros_like(w.data) for w in BW]
+        bv = [torch.zeros_like(w.data) for w in BW]
+        bstep = [0]
+
+        def bptt_step():
+            traj, its_b = brobot.rollout(btens, return_iters=True)
+            pk, tk = traj[:, 1:, :, key], target[:, 1:, :, key]
+            qp = pk[:, :, 3:7].permute(2, 0, 1, 3).reshape(4, -1)
+            qt = tk[:, :, 3:7].permute(2, 0, 1, 3).reshape(4, -1)
+            loss = ((pk[:, :, :3] - tk[:, :, :3]) ** 2).mean() + ((pk[:, :, 7:19] - tk[:, :, 7:19]) ** 2).mean() + \
+                ((quaternion_to_euler(qp) - quaternion_to_euler(qt)) ** 2).mean() + \
+                ((traj[:, 1:, 19:, key - 1] - target[:, 1:, 19:, key - 1]) ** 2).mean()
+            for w in BW:
+                w.grad = None
+            loss.backward()
+            grads = [w.grad for w in BW]
+            if world > 1:
+                flat = torch.cat([g.reshape(-1) for g in grads])
+                dist.all_reduce(flat)
+                off = 0
+                new = []
+                for g in grads:
+                    new.append(flat[off:off + g.numel()].view_as(g) / world)
+                    off += g.numel()
+                grads = new
+            bstep[0] += 1
+            for i, (w, g) in enumerate(zip(BW, grads)):
+                _ops.adam_clamp(w.data, g, bm[i], bv[i], bstep[0], lr=1e-4, clamp=(i % 2 == 0))
+            return loss, its_b
+
+        nsteps_b = max(2, min(args.steps, 5))
+        for _ in range(2):
+            bptt_step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(nsteps_b):
+            bl, its_b = bptt_step()
+        e1.record()
+        barrier()
+        bms = max_over_ranks(e0.elapsed_time(e1)) / nsteps_b
+        bptt = {"metric": "KNODE rollout-BPTT train steps/sec", "value": 1e3 / bms, "unit": "steps/s", "ms_per_step": bms,
+                "global_batch_trajectories": TRAIN_B, "rollout_steps": TRAIN_T - 1, "hidden": TRAIN_H, "steps": nsteps_b,
+                "semantics": "29-step KNODE rollout from the straight rod + 4-term loss at key nodes + BPTT "
+                             "(kc_rollout_bwd) + all-reduce + Adam + clamp; MLP inside the march on the FP32 SIMT path",
+                "loss": float(bl.item()), "all_converged": bool(int(its_b.min()) >= 0),
+                "rod_node_steps_per_s_fwd_bwd": TRAIN_B * N_NODES * (TRAIN_T - 1) / (bms * 1e-3)}
+
     # ---------------- CPU baseline (rank 0, bounded sample, the reference's algorithm on the host cores) -----------
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
@@ -364,7 +427,7 @@ def main():
                          "traffic": 516.3e6, "traffic_source": "ncu dram__bytes_read+write per launch, profiles/r01_ncu_prof_rollout_wide_r1c.csv "
                          "(algorithmic 416 MB: the trajectory is written once, 106 MB read back for the BDF2 history)",
                          "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak}},
-            "cpu_baseline": cpu, "train": train}
+            "cpu_baseline": cpu, "train": train, "train_bptt": bptt}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
