@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <cstdlib>
 #include "kc_bptt_core.cuh"
+#include "kc_mlp_coop.cuh"
 
 template <typename T> int kc_pack_mlp(const kc_mlp* mlp, T* Wp, MlpC<T>& M, cudaStream_t st);
 int kc_check_mlp(const kc_mlp* mlp);
@@ -26,8 +27,25 @@ kc_rollout_bwd_kernel(const __grid_constant__ RodC<T> P, const MlpC<T> M, int64_
                                   IN > 0 ? gos + b * per_rod * 25 : nullptr, fd_eps);
 }
 
+// warp-cooperative variant: one rod per warp, the MLP (and its input VJP) split over the lanes (kc_mlp_coop.cuh)
+template <typename T, bool DIAG, int IN, int NH>
+__global__ void __launch_bounds__(32)
+kc_rollout_bwd_coop_kernel(const __grid_constant__ RodC<T> P, const MlpCoop<T> M, int64_t B, int T_,
+                           const T* __restrict__ tensions, const T* __restrict__ traj, const T* __restrict__ gtraj,
+                           T* __restrict__ gten, T* __restrict__ xs, T* __restrict__ gos, T fd_eps) {
+    extern __shared__ __align__(16) unsigned char kc_smem[];
+    const int N = P.N;
+    const int64_t b = blockIdx.x;
+    if (b >= B) return;
+    T* Hs = reinterpret_cast<T*>(kc_smem);
+    const size_t per_rod = (size_t)(T_ - 1) * (N - 1) * 2;
+    bptt_rod<T, DIAG, IN, NH, 32>(P, M, traj + (size_t)b * T_ * 25 * N, gtraj + (size_t)b * T_ * 25 * N,
+                                  tensions + (size_t)b * T_ * 4, gten ? gten + (size_t)b * T_ * 4 : nullptr, T_, Hs,
+                                  xs + b * per_rod * IN, gos + b * per_rod * 25, fd_eps);
+}
+
 static inline size_t a256(size_t x) { return (x + 255) & ~(size_t)255; }
-struct BpttWs { size_t xs, gos, wp, mlpws, total; int64_t Qs; int64_t mlp_bytes; };
+struct BpttWs { size_t xs, gos, wp, wc, mlpws, total; int64_t Qs; int64_t mlp_bytes; };
 static BpttWs bptt_ws(int dtype, int N, const kc_mlp* mlp, int64_t B, int64_t T_) {
     const size_t sz = dtype == KC_F32 ? 4 : 8;
     BpttWs w{};
@@ -36,6 +54,7 @@ static BpttWs bptt_ws(int dtype, int N, const kc_mlp* mlp, int64_t B, int64_t T_
     w.xs = off; off += a256((size_t)w.Qs * (mlp ? mlp->in_dim : 0) * sz);
     w.gos = off; off += a256((size_t)w.Qs * 25 * sz);
     w.wp = off; off += mlp ? a256((size_t)mlp->hidden * (((mlp->in_dim + 3) & ~3) + 32) * sz) : 0;
+    w.wc = off; off += mlp ? a256((size_t)(((mlp->in_dim + 3) & ~3) + 26) * (size_t)((mlp->hidden + 31) & ~31) * sz) : 0;
     w.mlp_bytes = mlp ? kc_ode_bwd_workspace_bytes(dtype, mlp, w.Qs) : 0;
     w.mlpws = off; off += a256((size_t)w.mlp_bytes);
     w.total = off + 256;
@@ -76,7 +95,33 @@ static int bwd_typed(const kc_rod_params* Pp, const kc_mlp* mlp, int64_t B, int6
     const T fd_eps = sizeof(T) == 4 ? T(1e-2) : T(1e-6);
     T* xs = (T*)(ws + w.xs);
     T* gos = (T*)(ws + w.gos);
-    if (B > 0 && T_ > 1) {
+    bool coop = in_dim != 0 && B <= 8192;
+    {
+        const char* e = getenv("KC_ROLLOUT_COOP");
+        if (e && e[0] == '0') coop = false;
+        if (e && e[0] == '1' && in_dim != 0) coop = true;
+    }
+    if (B > 0 && T_ > 1 && coop) {
+        MlpCoop<T> MC;
+        static_cast<MlpC<T>&>(MC) = M;
+        MC.Hp = (mlp->hidden + 31) & ~31;
+        T* Wc = (T*)(ws + w.wc);
+        MC.Wc = Wc;
+        kc_pack_mlp_coop_kernel<T><<<64, 256, 0, st>>>((const T*)mlp->W1, (const T*)mlp->b1, (const T*)mlp->W2, Wc, in_dim,
+                                                      (in_dim + 3) & ~3, mlp->hidden, MC.Hp);
+        KC_CHECK_LAUNCH("kc_pack_mlp_coop_kernel");
+#define KC_LAUNCH_BWDC(D, I, H)                                                                                        \
+    do {                                                                                                               \
+        auto kern = kc_rollout_bwd_coop_kernel<T, D, I, H>;                                                            \
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
+        kern<<<(unsigned)B, 32, smem, st>>>(P, MC, B, (int)T_, (const T*)tensions, (const T*)traj, (const T*)gtraj,    \
+                                            (T*)gten, xs, gos, fd_eps);                                                \
+    } while (0)
+        if (P.diag) { if (in_dim == 28) KC_LAUNCH_BWDC(true, 28, 12); else KC_LAUNCH_BWDC(true, 53, 25); }
+        else { if (in_dim == 28) KC_LAUNCH_BWDC(false, 28, 12); else KC_LAUNCH_BWDC(false, 53, 25); }
+#undef KC_LAUNCH_BWDC
+        KC_CHECK_LAUNCH("kc_rollout_bwd_coop_kernel");
+    } else if (B > 0 && T_ > 1) {
         const unsigned grid = (unsigned)((B + rpw - 1) / rpw);
 #define KC_LAUNCH_BWD(D, I, H)                                                                                         \
     do {                                                                                                               \

@@ -17,8 +17,8 @@
 
 // Node evaluation in reverse: cotangents cys[19] (of ys incl. the MLP residual) and cz[6] (of the corrected z).
 // hist layout as in node_eval (NH = 12: qh,wh,vh,uh; NH = 25: yh(19), zh(6)).  xs[IN] / gos[25] receive the MLP sample.
-template <typename T, bool DIAG, int IN, int NH>
-KC_HD void node_vjp(const RodC<T>& P, const MlpC<T>& M, const T* __restrict__ y, const T* __restrict__ hist,
+template <typename T, bool DIAG, int IN, int NH, typename MLP>
+KC_HD void node_vjp(const RodC<T>& P, const MLP& M, const T* __restrict__ y, const T* __restrict__ hist,
                     const T tf[3], const T* __restrict__ cys, const T* __restrict__ cz, T* __restrict__ gy,
                     T* __restrict__ ghist, T gtf[3], T* __restrict__ xs, T* __restrict__ gos) {
     const T* qh = (NH == 12) ? hist : hist + 13;
@@ -101,8 +101,8 @@ struct NullSink {
 //   ten             : tensions [T][4];  gten (may be null): dL/dtensions [T][4]
 //   Hs              : per-rod scratch, 4 arrays of NH*(N-1) values with element stride LS: Hcur | Ha | Hb | Hc
 //   xs, gos         : MLP samples of this rod: [(T-1)*(N-1)*2][IN] and [..][25] (null when IN == 0)
-template <typename T, bool DIAG, int IN, int NH, int LS>
-KC_HD void bptt_rod(const RodC<T>& P, const MlpC<T>& M, const T* __restrict__ traj_b, const T* __restrict__ gtraj_b,
+template <typename T, bool DIAG, int IN, int NH, int LS, typename MLP>
+KC_HD void bptt_rod(const RodC<T>& P, const MLP& M, const T* __restrict__ traj_b, const T* __restrict__ gtraj_b,
                     const T* __restrict__ ten, T* __restrict__ gten, int T_, T* Hs, T* __restrict__ xs,
                     T* __restrict__ gos, T fd_eps) {
     const int N = P.N, Nm1 = N - 1, HN = NH * Nm1;

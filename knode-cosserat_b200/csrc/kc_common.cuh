@@ -58,6 +58,16 @@ struct MlpC {
     int in_dim, inP, hidden, stride;
 };
 
+// Warp-cooperative MLP view (kc_mlp_coop.cuh): the 32 lanes of a warp hold the SAME rod and split the hidden units.
+// Wc: [inP][Hp] W1^T | [Hp] b1 | [25][Hp] W2 with Hp = hidden rounded up to 32 (zero padded), unit index fastest so
+// that a warp's loads are coalesced.  Passing an MlpCoop instead of an MlpC selects the cooperative evaluation by
+// overload resolution; everything else of the per-rod code is unchanged (all lanes compute the physics redundantly).
+template <typename T>
+struct MlpCoop : MlpC<T> {
+    const T* Wc;
+    int Hp;
+};
+
 void kc_set_error(const char* fmt, ...);
 #define KC_CHECK_ARG(cond, ...)          \
     do {                                 \

@@ -165,8 +165,8 @@ template <typename T> struct RefSink {
 };
 
 // RK4 march (cosserat_ode.py:215-255): mid-point histories are linear interpolations (knode.py:80-81); only k1's z is kept.
-template <typename T, bool DIAG, int IN, int NH, typename Hist, typename Sink>
-KC_HD void rod_march_rk4(const RodC<T>& P, const MlpC<T>& M, const T G[6], const T tf[3], const Hist& H, Sink& S, T res[6]) {
+template <typename T, bool DIAG, int IN, int NH, typename Hist, typename Sink, typename MLP>
+KC_HD void rod_march_rk4(const RodC<T>& P, const MLP& M, const T G[6], const T tf[3], const Hist& H, Sink& S, T res[6]) {
     T y[19];
     base_state(P, G, y);
     const int N = P.N;

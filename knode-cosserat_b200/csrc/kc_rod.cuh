@@ -214,8 +214,8 @@ KC_HD void mlp_eval(const MlpC<T>& M, const T* __restrict__ x, T* __restrict__ o
 // Physics + optional MLP residual for one node.  NH = number of history rows carried per node:
 // 12 -> hist = [qh,wh,vh,uh]; 25 -> hist = [yh(19); zh(6)] (needed when the MLP sees the history, IN == 53).
 // The MLP sees the PRE-correction z; z is corrected after ys is formed (cosserat_ode_torch.py:192-212).
-template <typename T, bool DIAG, int IN /*0 = physics only*/, int NH>
-KC_HD void node_eval(const RodC<T>& P, const MlpC<T>& M, const T* __restrict__ y, const T* __restrict__ hist,
+template <typename T, bool DIAG, int IN /*0 = physics only*/, int NH, typename MLP>
+KC_HD void node_eval(const RodC<T>& P, const MLP& M, const T* __restrict__ y, const T* __restrict__ hist,
                      const T tf[3], T* __restrict__ ys, T* __restrict__ z) {
     const T* qh = (NH == 12) ? hist : hist + 13;
     const T* wh = qh + 3;
@@ -264,8 +264,8 @@ template <typename T> KC_HD void base_state(const RodC<T>& P, const T G[6], T y[
 // Explicit-Euler shooting march (cosserat_ode.py:188-213).  Hist::load(j, hist[NH]) supplies node j's history,
 // Sink::put(j, y[19]) receives the state entering node j (j = 0..N-1) and Sink::putz(j, z[6]) the z produced at node j
 // (j = 0..N-2).  Returns res = [F_tip - n(L), M_tip - m(L)].
-template <typename T, bool DIAG, int IN, int NH, typename Hist, typename Sink>
-KC_HD void rod_march(const RodC<T>& P, const MlpC<T>& M, const T G[6], const T tf[3], const Hist& H, Sink& S,
+template <typename T, bool DIAG, int IN, int NH, typename Hist, typename Sink, typename MLP>
+KC_HD void rod_march(const RodC<T>& P, const MLP& M, const T G[6], const T tf[3], const Hist& H, Sink& S,
                      T res[6]) {
     T y[19];
     base_state(P, G, y);
@@ -364,8 +364,8 @@ template <typename T, int LS> KC_HD void broyden_update(const ShootMem<T, LS>& s
 // whenever two consecutive iterations fail to halve the residual.  Written as a small state machine around ONE march
 // call site so lanes in different phases (predictor / FD column / Broyden iterate) still execute the march together.
 // Returns the number of marches (negative: tol not reached within max_iter, or a NaN / singular Jacobian appeared).
-template <typename T, bool DIAG, int IN, int NH, int LS, typename Hist, typename Sink>
-KC_HD int shoot_step(const RodC<T>& P, const MlpC<T>& M, const ShootMem<T, LS>& st, const T tf[3], const Hist& H, Sink& S,
+template <typename T, bool DIAG, int IN, int NH, int LS, typename Hist, typename Sink, typename MLP>
+KC_HD int shoot_step(const RodC<T>& P, const MLP& M, const ShootMem<T, LS>& st, const T tf[3], const Hist& H, Sink& S,
                      T tol, int max_iter, T fd_eps) {
     enum { PRED = 0, FD = 1, BROY = 2 };
     T G[6], F[6], dG[6];

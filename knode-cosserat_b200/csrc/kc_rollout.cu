@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include "kc_rollout_core.cuh"
 #include "kc_rollout_wide.cuh"
+#include "kc_mlp_coop.cuh"
 
 constexpr int KC_LS = 32;  // lane stride of every per-rod array (one warp-wide tile)
 
@@ -56,6 +57,34 @@ kc_rollout_kernel(const __grid_constant__ RodC<T> P, const MlpC<T> M, int64_t B,
                                         max_iter, fd_eps, Gout ? Gout + (size_t)b * T_ * 6 : nullptr,
                                         iters ? iters + (size_t)b * T_ : nullptr);
     for (int i = 0; i < KC_SHOOT_SLOTS; ++i) sb[(size_t)i * Bpad] = st.p[i * KC_LS];
+}
+
+// KNODE rollout, warp-cooperative: ONE ROD PER WARP.  Every lane runs the same per-rod code on the same rod (physics
+// redundantly, shared-memory state at lane-independent addresses, identical stores), the MLP inside each node evaluation
+// is split over the lanes (kc_mlp_coop.cuh).  Chosen when the MLP is in the march and the batch is small.
+template <typename T, bool DIAG, int IN, int NH>
+__global__ void __launch_bounds__(32)
+kc_rollout_coop_kernel(const __grid_constant__ RodC<T> P, const MlpCoop<T> M, int64_t B, int T_,
+                       const T* __restrict__ tensions, const T* __restrict__ y0, const T* __restrict__ z0, T* trajD,
+                       T tol, int max_iter, T fd_eps, T* Gout, int32_t* iters) {
+    extern __shared__ __align__(16) unsigned char kc_smem[];
+    const int N = P.N;
+    const int64_t b = blockIdx.x;
+    if (b >= B) return;
+    T* Hs = reinterpret_cast<T*>(kc_smem);
+    const ShootMem<T, KC_LS> st{reinterpret_cast<T*>(kc_smem) + (size_t)NH * (N - 1) * KC_LS};
+    T* traj_b = rod_base(trajD, b, T_, N);
+    st.reset();
+    rollout_init<T, KC_LS>(P, y0 ? y0 + (size_t)b * 19 * N : nullptr, z0 ? z0 + (size_t)b * 6 * N : nullptr, traj_b);
+    if (Gout) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) Gout[(size_t)b * T_ * 6 + i] = T(0);
+    }
+    if (iters) iters[(size_t)b * T_] = 0;
+    __syncwarp();
+    rollout_rod<T, DIAG, IN, NH, KC_LS>(P, M, st, tensions + (size_t)b * T_ * 4, traj_b, Hs, 0, T_ - 1, tol, max_iter,
+                                        fd_eps, Gout ? Gout + (size_t)b * T_ * 6 : nullptr,
+                                        iters ? iters + (size_t)b * T_ : nullptr);
 }
 
 // Wide mode: 4 rods per warp, 8 lanes per rod (see kc_rollout_wide.cuh).  Shared memory: history [N-1][NH][4].
@@ -396,7 +425,7 @@ int kc_check_mlp(const kc_mlp* mlp) {
 static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct RolloutWs {
-    size_t trajD, wp, state, total;
+    size_t trajD, wp, wc, state, total;
     size_t Bpad;
 };
 static RolloutWs rollout_ws(int dtype, int N, const kc_mlp* mlp, int64_t B, int64_t T_) {
@@ -407,6 +436,8 @@ static RolloutWs rollout_ws(int dtype, int N, const kc_mlp* mlp, int64_t B, int6
     size_t off = align256((size_t)T_ * 25 * N * w.Bpad * sz);
     w.wp = off;
     if (mlp) off += align256((size_t)mlp->hidden * (((mlp->in_dim + 3) & ~3) + 32) * sz);
+    w.wc = off;
+    if (mlp) off += align256((size_t)(((mlp->in_dim + 3) & ~3) + 26) * (size_t)((mlp->hidden + 31) & ~31) * sz);
     w.state = off;
     off += align256((size_t)KC_SHOOT_SLOTS * w.Bpad * sz);
     w.total = off;
@@ -475,8 +506,35 @@ static int rollout_typed(const kc_rod_params* Pp, const kc_mlp* mlp, int64_t B, 
         if (e && e[0] == '0') lin = false;
         if (e && e[0] == '1' && lsmem <= 200 * 1024) lin = wide;
     }
+    // warp-cooperative KNODE rollout: MLP in the march and too few rods to fill the chip with one rod per thread
+    bool coop = in_dim != 0 && !wide && B <= 8192;
+    {
+        const char* e = getenv("KC_ROLLOUT_COOP");
+        if (e && e[0] == '0') coop = false;
+        if (e && e[0] == '1' && in_dim != 0) coop = true;
+    }
     if (B > 0) {
-        if (wide && lin) {
+        if (coop) {
+        MlpCoop<T> MC;
+        static_cast<MlpC<T>&>(MC) = M;
+        MC.Hp = (mlp->hidden + 31) & ~31;
+        T* Wc = (T*)(ws + w.wc);
+        MC.Wc = Wc;
+        const int inP = (in_dim + 3) & ~3;
+        kc_pack_mlp_coop_kernel<T><<<64, 256, 0, st>>>((const T*)mlp->W1, (const T*)mlp->b1, (const T*)mlp->W2, Wc, in_dim, inP,
+                                                      mlp->hidden, MC.Hp);
+        KC_CHECK_LAUNCH("kc_pack_mlp_coop_kernel");
+#define KC_LAUNCH_COOP(D, I, H)                                                                                        \
+    do {                                                                                                               \
+        auto kern = kc_rollout_coop_kernel<T, D, I, H>;                                                                \
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
+        kern<<<(unsigned)B, 32, smem, st>>>(P, MC, B, (int)T_, (const T*)tensions, (const T*)y0, (const T*)z0, trajD,  \
+                                            tl, max_iter, fd_eps, (T*)G_out, iters);                                   \
+    } while (0)
+        if (P.diag) { if (in_dim == 28) KC_LAUNCH_COOP(true, 28, 12); else KC_LAUNCH_COOP(true, 53, 25); }
+        else { if (in_dim == 28) KC_LAUNCH_COOP(false, 28, 12); else KC_LAUNCH_COOP(false, 53, 25); }
+#undef KC_LAUNCH_COOP
+        } else if (wide && lin) {
             const unsigned wgrid = (unsigned)((B + KC_WG - 1) / KC_WG);
 #define KC_LAUNCH_WLIN(D, I, H)                                                                                        \
     do {                                                                                                               \

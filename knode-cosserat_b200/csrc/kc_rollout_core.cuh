@@ -51,8 +51,8 @@ KC_HD void build_history(const RodC<T>& P, const T* cur, const T* prev, T* Hs) {
 //   ten      : this rod's tensions, ten[t*4 + i]
 //   traj_b   : this rod's base in trajD (element t=0, node 0, row 0); time stride is N*25*LS
 //   Gout/iters: this rod's [T][6] / [T] output rows (reference layout) or nullptr
-template <typename T, bool DIAG, int IN, int NH, int LS>
-KC_HD void rollout_rod(const RodC<T>& P, const MlpC<T>& M, const ShootMem<T, LS>& st, const T* __restrict__ ten,
+template <typename T, bool DIAG, int IN, int NH, int LS, typename MLP>
+KC_HD void rollout_rod(const RodC<T>& P, const MLP& M, const ShootMem<T, LS>& st, const T* __restrict__ ten,
                        T* traj_b, T* Hs, int t_begin, int t_end, T tol, int max_iter, T fd_eps, T* Gout,
                        int32_t* iters) {
     const int N = P.N;

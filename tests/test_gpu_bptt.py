@@ -11,6 +11,14 @@ pytestmark = pytest.mark.gpu
 PK = ("W1", "b1", "W2", "b2")
 
 
+@pytest.fixture(params=["coop", "thread"], autouse=True)
+def coop(request, monkeypatch):
+    """Both KNODE kernels: one rod per warp with the MLP split over the lanes ("coop", small batches) and one rod per
+    thread ("thread")."""
+    monkeypatch.setenv("KC_ROLLOUT_COOP", "1" if request.param == "coop" else "0")
+    return request.param
+
+
 def setup_case(H=16, B=2, T=7, in_dim=28, seed=0):
     rng = np.random.default_rng(seed)
     P = O.setup_params(O.RodParams(), "youngs")

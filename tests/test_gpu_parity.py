@@ -164,7 +164,9 @@ def test_rollout_vs_reference_simulate(ops, golden, mode, dt, name, kind, mod):
 
 @pytest.mark.parametrize("dt", [torch.float64, torch.float32])
 @pytest.mark.parametrize("tag", ["h64", "h512", "h32hist"])
-def test_knode_rollout_vs_reference(ops, golden, mode, dt, tag):
+@pytest.mark.parametrize("coop", ["0", "1"])
+def test_knode_rollout_vs_reference(ops, golden, mode, dt, tag, coop, monkeypatch):
+    monkeypatch.setenv("KC_ROLLOUT_COOP", coop)   # 1: one rod per warp, MLP split over the lanes (narrow mode only)
     d = golden["knode_rollouts"]
     P = P_setup("youngs")
     traj, _, iters = ops.rollout(params(P), mlp_of(ops, d, tag, dt), dev(d[tag + "_ctl"][None], dt))
