@@ -58,6 +58,19 @@ KC_HD float kc_two_over(float x) {
 }
 KC_HD double kc_two_over(double x) { return 2.0 / x; }
 
+// 1/x for the small dense solves of the shooting iteration (same MUFU + Newton form; a Newton / Broyden step does not
+// need a correctly rounded quotient and the IEEE sequence serialises the 6x6 elimination).
+KC_HD float kc_rcp(float x) {
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return fmaf(r, fmaf(-x, r, 1.0f), r);
+#else
+    return 1.0f / x;
+#endif
+}
+KC_HD double kc_rcp(double x) { return 1.0 / x; }
+
 // Eq(10) quaternion (w,x,y,z) -> rotation, NOT normalised (cosserat_ode_torch.py:157-161).
 template <typename T> KC_HD void kc_quat_R(const T h[4], T R[9]) {
     const T a = h[0], b = h[1], c = h[2], d = h[3];

@@ -252,9 +252,14 @@ kc_rollout_wide_lin_kernel(const __grid_constant__ RodC<T> P, const MlpC<T> M, i
         }
         if (iters) iters[(size_t)b * T_] = 0;
     }
-    T zlast[6];
+    // z[:, N-1] is never written by the march: it keeps its initial value; zl[rr] = this lane's row of it (rows >= 19)
+    T zl[4];
 #pragma unroll
-    for (int c = 0; c < 6; ++c) zlast[c] = z0 ? z0[(size_t)b * 6 * N + c * N + (N - 1)] : ((c == 2) ? T(1) : T(0));
+    for (int rr = 0; rr < 4; ++rr) {
+        const int r = rr < 3 ? k + 8 * rr : 24;
+        const int c = r >= 19 ? r - 19 : 0;
+        zl[rr] = z0 ? z0[(size_t)b * 6 * N + c * N + (N - 1)] : ((c == 2) ? T(1) : T(0));
+    }
     __syncwarp();
     T G[6], Gm1[6];
 #pragma unroll
@@ -280,12 +285,17 @@ kc_rollout_wide_lin_kernel(const __grid_constant__ RodC<T> P, const MlpC<T> M, i
         T sprev = T(0);
         Cest = T(0);      // the curvature estimate must come from THIS step's own iterations (inputs may jump between steps)
         HistView<T, NH, KC_WG> H{Hs};
+        // Gm: the point the group marches.  It is frozen once the rod is done, so while other rods of the warp still
+        // iterate its re-marches reproduce the marched states bit for bit and the sink stores without a predicate.
+        T Gm[6];
         while (true) {
             T eps[6], Ge[6], F[6];
-            wide_eps(G, fd_eps, eps);
 #pragma unroll
-            for (int i = 0; i < 6; ++i) Ge[i] = G[i] + ((k == i + 1) ? eps[i] : T(0));
-            SmemStateSink<T, KC_WS> S{Sg + (k < 7 ? k : 0), k < 7 && !done};
+            for (int i = 0; i < 6; ++i) Gm[i] = done ? Gm[i] : G[i];
+            wide_eps(Gm, fd_eps, eps);
+#pragma unroll
+            for (int i = 0; i < 6; ++i) Ge[i] = Gm[i] + ((k == i + 1) ? eps[i] : T(0));
+            SmemStateSink<T, KC_WS> S{Sg + (k < 7 ? k : 0)};   // lane 7 repeats lane 0 (same values, same address)
             rod_march<T, DIAG, IN, NH>(P, M, Ge, tf, H, S, F);
             T Fall[7][6];
 #pragma unroll
@@ -302,31 +312,41 @@ kc_rollout_wide_lin_kernel(const __grid_constant__ RodC<T> P, const MlpC<T> M, i
             if (__all_sync(full, done)) break;
         }
 #pragma unroll
-        for (int i = 0; i < 6; ++i) Gm1[i] = Gp[i];
+        for (int i = 0; i < 6; ++i) { Gm1[i] = Gp[i]; w[i] = (status == 2) ? w[i] : T(0); }
         __syncwarp();
-        // accepted state = base state (+ first-order correction when status == 2); lane k of the group handles rows
-        // k, k+8, k+16, k+24 of every node (no index arithmetic in the loop)
-        const bool lin = status == 2;
+        // accepted state = base state + first-order correction (w = 0 unless status == 2).  Lane k of the group handles
+        // rows k, k+8, k+16 and (k == 0 only) 24 of every node: all shared-memory loads of a node are issued before its
+        // stores, so the 32 loads overlap instead of forming 40 serial load-use-store chains per step.
         for (int j = 0; j < N; ++j) {
+            const int jh = j < N - 1 ? j : N - 2;
+            T s0[4], sc[4][6], ap[4];
 #pragma unroll
             for (int rr = 0; rr < 4; ++rr) {
-                const int r = k + 8 * rr;
-                if (r < 25) {
-                    const T* sp = Sg + (size_t)(j * 25 + r) * KC_WS;
-                    T v = sp[0];
-                    if (lin) {
-                        const T v0 = v;
+                const int r = rr < 3 ? k + 8 * rr : 24;
+                const T* sp = Sg + (size_t)(j * 25 + r) * KC_WS;
+                s0[rr] = sp[0];
 #pragma unroll
-                        for (int c = 0; c < 6; ++c) v += (sp[c + 1] - v0) * w[c];
-                    }
-                    if (j == N - 1 && r >= 19) v = zlast[r - 19];   // z[:, N-1] is never written by the march
-                    if (valid) nxt[(size_t)(j * 25 + r) * KC_LS] = v;
-                    const int sl = (NH == 12) ? r - 13 : r;          // history for the next step; A <- accepted
-                    if (j < N - 1 && sl >= 0) {
-                        const size_t hi = (size_t)(j * NH + sl) * KC_WG;
-                        Hs[hi] = P.c1 * v + P.c2 * As[hi];
-                        As[hi] = v;
-                    }
+                for (int c = 0; c < 6; ++c) sc[rr][c] = sp[c + 1];
+                const int sl = (NH == 12) ? (r >= 13 ? r - 13 : 0) : r;
+                ap[rr] = As[(size_t)(jh * NH + sl) * KC_WG];
+            }
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+                const int r = rr < 3 ? k + 8 * rr : 24;
+                const bool act = rr < 3 || k == 0;
+                const T v0 = s0[rr];
+                T va = (sc[rr][0] - v0) * w[0], vb = (sc[rr][1] - v0) * w[1];
+                va += (sc[rr][2] - v0) * w[2]; vb += (sc[rr][3] - v0) * w[3];
+                va += (sc[rr][4] - v0) * w[4]; vb += (sc[rr][5] - v0) * w[5];
+                T v = v0 + (va + vb);
+                if (j == N - 1 && r >= 19) v = zl[rr];   // z[:, N-1] is never written by the march
+                if (act && valid) nxt[(size_t)(j * 25 + r) * KC_LS] = v;
+                const bool hrow = (NH == 12) ? r >= 13 : true;   // history for the next step; A <- accepted
+                if (act && hrow && j < N - 1) {
+                    const int sl = (NH == 12) ? r - 13 : r;
+                    const size_t hi = (size_t)(j * NH + sl) * KC_WG;
+                    Hs[hi] = P.c1 * v + P.c2 * ap[rr];
+                    As[hi] = v;
                 }
             }
         }

@@ -19,36 +19,39 @@ template <typename T> KC_HD int wide_decide(const T Fall[7][6], T G[6], const T 
     const T fn = norm_inf6(Fall[0]);
     if (!(fn == fn)) return -1;
     if (fn <= tol * kc_max(T(1), norm_inf6(G))) return 1;
-    T A[36], rhs[6], ie[6];
+    T A[36], rhs[6], ie[6], ip[6];
 #pragma unroll
-    for (int c = 0; c < 6; ++c) ie[c] = T(1) / eps[c];
+    for (int c = 0; c < 6; ++c) ie[c] = kc_rcp(eps[c]);
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
         rhs[i] = -Fall[0][i];
 #pragma unroll
         for (int c = 0; c < 6; ++c) A[i * 6 + c] = (Fall[c + 1][i] - Fall[0][i]) * ie[c];
     }
-    // Gaussian elimination without pivoting (J = -[[I,0],[X,I]] + small, cond ~ 1.5), then back substitution
+    // Gaussian elimination without pivoting (J = -[[I,0],[X,I]] + small, cond ~ 1.5), then back substitution; branch
+    // free (a bad pivot is only flagged) and with one fast reciprocal per pivot, reused by the back substitution
+    bool bad = false;
 #pragma unroll
     for (int p = 0; p < 6; ++p) {
         const T piv = A[p * 6 + p];
-        if (!(kc_abs(piv) > T(1e-30))) return -1;
-        const T ip = T(1) / piv;
+        bad = bad || !(kc_abs(piv) > T(1e-30));
+        ip[p] = kc_rcp(piv);
 #pragma unroll
         for (int r = p + 1; r < 6; ++r) {
-            const T f = A[r * 6 + p] * ip;
+            const T f = A[r * 6 + p] * ip[p];
 #pragma unroll
             for (int c = p + 1; c < 6; ++c) A[r * 6 + c] -= f * A[p * 6 + c];
             rhs[r] -= f * rhs[p];
         }
     }
+    if (bad) return -1;
     T dG[6];
 #pragma unroll
     for (int r = 5; r >= 0; --r) {
         T s = rhs[r];
 #pragma unroll
         for (int c = r + 1; c < 6; ++c) s -= A[r * 6 + c] * dG[c];
-        dG[r] = s / A[r * 6 + r];
+        dG[r] = s * ip[r];
     }
 #pragma unroll
     for (int i = 0; i < 6; ++i) G[i] += dG[i];
@@ -104,7 +107,7 @@ KC_HD int wide_decide_lin(const T Fall[7][6], T G[6], const T eps[6], T tol, T& 
     const T fn = norm_inf6(Fall[0]);
     if (!(fn == fn)) return -1;
     const T scale = kc_max(T(1), norm_inf6(G));
-    if (sprev > T(0)) Cest = kc_max(Cest, fn / (sprev * sprev));   // this residual is what the last step left behind
+    if (sprev > T(0)) Cest = kc_max(Cest, fn * kc_rcp(sprev * sprev));   // this residual is what the last step left behind
     if (fn <= tol * scale) return 1;
     T Gn[6];
 #pragma unroll
@@ -117,27 +120,24 @@ KC_HD int wide_decide_lin(const T Fall[7][6], T G[6], const T eps[6], T tol, T& 
     sprev = s;
     if (Cest > T(0) && T(4) * Cest * s * s <= tol * scale) {
 #pragma unroll
-        for (int i = 0; i < 6; ++i) w[i] = dG[i] / eps[i];
+        for (int i = 0; i < 6; ++i) w[i] = dG[i] * kc_rcp(eps[i]);
         return 2;
     }
     return 0;
 }
 
-// Sink that keeps the marched state of one lane in shared memory: [node][row][slot stride SS]
+// Sink that keeps the marched state of one lane in shared memory: [node][row][slot stride SS].  Stores are unconditional:
+// the kernel freezes the marched point of a finished rod, so its re-marches rewrite the same values.
 template <typename T, int SS> struct SmemStateSink {
-    T* p; bool on;
+    T* p;
     KC_HD void put(int j, const T y[19]) {
-        if (on) {
-            T* pn = p + (size_t)j * 25 * SS;
+        T* pn = p + (size_t)j * 25 * SS;
 #pragma unroll
-            for (int r = 0; r < 19; ++r) pn[r * SS] = y[r];
-        }
+        for (int r = 0; r < 19; ++r) pn[r * SS] = y[r];
     }
     KC_HD void putz(int j, const T z[6]) {
-        if (on) {
-            T* pn = p + (size_t)j * 25 * SS;
+        T* pn = p + (size_t)j * 25 * SS;
 #pragma unroll
-            for (int c = 0; c < 6; ++c) pn[(19 + c) * SS] = z[c];
-        }
+        for (int c = 0; c < 6; ++c) pn[(19 + c) * SS] = z[c];
     }
 };

@@ -126,7 +126,7 @@ static void run_wide_lin(const RodC<T>& P, const MlpC<T>& M, int64_t B, int64_t 
                 for (int k = 0; k < 7; ++k) {
                     T Ge[6];
                     for (int i = 0; i < 6; ++i) Ge[i] = G[i] + ((k == i + 1) ? eps[i] : T(0));
-                    SmemStateSink<T, 1> Sk{S.data() + (size_t)k * NV, true};
+                    SmemStateSink<T, 1> Sk{S.data() + (size_t)k * NV};
                     rod_march<T, DIAG, IN, NH>(P, M, Ge, tf, H, Sk, Fall[k]);
                 }
                 ++marches;
