@@ -207,43 +207,45 @@ kc_rollout_wide_kernel(const __grid_constant__ RodC<T> P, const MlpC<T> M, int64
 }
 
 // Wide mode with the linearised final correction (kc_rollout_wide.cuh): the 7 marched states of a rod live in shared
-// memory ([N][25][28 slots] per warp), the accepted state is written to the trajectory by the 8 lanes of the group
-// cooperatively, and the next history is formed from shared memory (no read-back).
+// memory, the accepted state is written STRAIGHT into the reference layout traj[B][T][rows][N] by the 8 lanes of the
+// group (no device-layout trajectory, no transpose pass), and the next history is formed in shared memory.
+// Shared memory per warp, all in "output order" e = r*N + j (row r, node j — the order of one [25][N] time slice):
+//   S [25*N][28 slots]  marched states (slot = 7*rod + point)      H, A [NH*N][4 rods]  history / previous accepted state
+// NC = compile-time node count (0: use P.N) — with NC all shared-memory offsets are immediates.
 constexpr int KC_WS = 28;  // state slots per warp: 4 rods x 7 points
-template <typename T, bool DIAG, int IN, int NH>
+template <typename T, bool DIAG, int IN, int NH, int NC>
 __global__ void __launch_bounds__(32)
 kc_rollout_wide_lin_kernel(const __grid_constant__ RodC<T> P, const MlpC<T> M, int64_t B, int T_,
                            const T* __restrict__ tensions, const T* __restrict__ y0, const T* __restrict__ z0,
-                           T* trajD, T tol, int max_iter, T fd_eps, T* Gout, int32_t* iters) {
+                           T* __restrict__ out, int64_t tstride, T tol, int max_iter, T fd_eps, T* Gout, int32_t* iters) {
     extern __shared__ __align__(16) unsigned char kc_smem[];
-    const int N = P.N;
+    const int N = NC ? NC : P.N;
+    const int NV = 25 * N;
+    const int H0 = (NH == 12) ? 13 * N : 0;   // first element that has a history (rows 13..24, or all rows)
     const int lane = threadIdx.x, g = lane >> 3, k = lane & 7;
     const unsigned full = 0xffffffffu;
     const int64_t b_raw = (int64_t)blockIdx.x * KC_WG + g;
     const bool valid = b_raw < B;
     const int64_t b = valid ? b_raw : B - 1;
-    // shared memory: S [N][25][28] marched states, H [N-1][NH][4] history, A [N-1][NH][4] history rows of the previous state
     T* Sall = reinterpret_cast<T*>(kc_smem);
-    T* Hs = Sall + (size_t)N * 25 * KC_WS + g;
-    T* As = Sall + (size_t)N * 25 * KC_WS + (size_t)(N - 1) * NH * KC_WG + g;
     T* Sg = Sall + g * 7;                       // this rod's 7 slots
-    T* traj_b = rod_base(trajD, b, T_, N);
-    const size_t tstride = (size_t)25 * N * KC_LS;
-    const int NV = 25 * N;
-    // initial state -> trajectory index 0 and As
+    T* Hs = Sall + (size_t)NV * KC_WS + g;
+    T* As = Hs + (size_t)NH * N * KC_WG;
+    T* out_b = out + (size_t)b * T_ * tstride;
+    // initial state -> time index 0, A, H and EVERY slot of S (rows 19..24 of the tip node are never written by the
+    // march, cosserat_ode.py:198-201: they keep the initial z for the whole rollout)
     for (int e = k; e < NV; e += 8) {
-        const int j = e / 25, r = e - j * 25;
+        const int r = e / N, j = e - r * N;
         T v;
-        if (r < 19) v = y0 ? y0[(size_t)b * 19 * N + r * N + j] : ((r == 2) ? P.ds * T(j) : (r == 3 ? T(1) : T(0)));
-        else v = z0 ? z0[(size_t)b * 6 * N + (r - 19) * N + j] : ((r == 21) ? T(1) : T(0));
-        if (j < N - 1) {
-            const int sl = (NH == 12) ? r - 13 : r;
-            if (sl >= 0) {
-                As[(size_t)(j * NH + sl) * KC_WG] = v;
-                Hs[(size_t)(j * NH + sl) * KC_WG] = (P.c1 + P.c2) * v;   // state[-1] := state[0] (knode.py:65-66)
-            }
+        if (r < 19) v = y0 ? y0[(size_t)b * 19 * N + e] : ((r == 2) ? P.ds * T(j) : (r == 3 ? T(1) : T(0)));
+        else v = z0 ? z0[(size_t)b * 6 * N + (e - 19 * N)] : ((r == 21) ? T(1) : T(0));
+        if (e >= H0) {
+            As[(size_t)(e - H0) * KC_WG] = v;
+            Hs[(size_t)(e - H0) * KC_WG] = (P.c1 + P.c2) * v;   // state[-1] := state[0] (knode.py:65-66)
         }
-        if (valid) traj_b[(size_t)e * KC_LS] = v;
+#pragma unroll
+        for (int c = 0; c < 7; ++c) Sg[(size_t)e * KC_WS + c] = v;
+        if (valid) out_b[e] = v;
     }
     if (k == 0 && valid) {
         if (Gout) {
@@ -251,14 +253,6 @@ kc_rollout_wide_lin_kernel(const __grid_constant__ RodC<T> P, const MlpC<T> M, i
             for (int i = 0; i < 6; ++i) Gout[(size_t)b * T_ * 6 + i] = T(0);
         }
         if (iters) iters[(size_t)b * T_] = 0;
-    }
-    // z[:, N-1] is never written by the march: it keeps its initial value; zl[rr] = this lane's row of it (rows >= 19)
-    T zl[4];
-#pragma unroll
-    for (int rr = 0; rr < 4; ++rr) {
-        const int r = rr < 3 ? k + 8 * rr : 24;
-        const int c = r >= 19 ? r - 19 : 0;
-        zl[rr] = z0 ? z0[(size_t)b * 6 * N + c * N + (N - 1)] : ((c == 2) ? T(1) : T(0));
     }
     __syncwarp();
     T G[6], Gm1[6];
@@ -276,7 +270,7 @@ kc_rollout_wide_lin_kernel(const __grid_constant__ RodC<T> P, const MlpC<T> M, i
 #pragma unroll
             for (int i = 0; i < 4; ++i) tn[i] = ten[(size_t)(t + 1) * 4 + i];
         }
-        T* nxt = traj_b + (size_t)(t + 1) * tstride;
+        T* nxt = out_b + (size_t)(t + 1) * tstride;
         T Gp[6], w[6];
 #pragma unroll
         for (int i = 0; i < 6; ++i) { Gp[i] = G[i]; G[i] = G[i] + (G[i] - Gm1[i]); w[i] = T(0); }
@@ -284,7 +278,7 @@ kc_rollout_wide_lin_kernel(const __grid_constant__ RodC<T> P, const MlpC<T> M, i
         int status = 0, marches = 0;
         T sprev = T(0);
         Cest = T(0);      // the curvature estimate must come from THIS step's own iterations (inputs may jump between steps)
-        HistView<T, NH, KC_WG> H{Hs};
+        HistViewE<T, NH, KC_WG, NC> H{Hs, N};
         // Gm: the point the group marches.  It is frozen once the rod is done, so while other rods of the warp still
         // iterate its re-marches reproduce the marched states bit for bit and the sink stores without a predicate.
         T Gm[6];
@@ -295,7 +289,7 @@ kc_rollout_wide_lin_kernel(const __grid_constant__ RodC<T> P, const MlpC<T> M, i
             wide_eps(Gm, fd_eps, eps);
 #pragma unroll
             for (int i = 0; i < 6; ++i) Ge[i] = Gm[i] + ((k == i + 1) ? eps[i] : T(0));
-            SmemStateSink<T, KC_WS> S{Sg + (k < 7 ? k : 0)};   // lane 7 repeats lane 0 (same values, same address)
+            SmemStateSinkE<T, KC_WS, NC> S{Sg + (k < 7 ? k : 0), N};   // lane 7 repeats lane 0 (same values, same address)
             rod_march<T, DIAG, IN, NH>(P, M, Ge, tf, H, S, F);
             T Fall[7][6];
 #pragma unroll
@@ -314,41 +308,44 @@ kc_rollout_wide_lin_kernel(const __grid_constant__ RodC<T> P, const MlpC<T> M, i
 #pragma unroll
         for (int i = 0; i < 6; ++i) { Gm1[i] = Gp[i]; w[i] = (status == 2) ? w[i] : T(0); }
         __syncwarp();
-        // accepted state = base state + first-order correction (w = 0 unless status == 2).  Lane k of the group handles
-        // rows k, k+8, k+16 and (k == 0 only) 24 of every node: all shared-memory loads of a node are issued before its
-        // stores, so the 32 loads overlap instead of forming 40 serial load-use-store chains per step.
-        for (int j = 0; j < N; ++j) {
-            const int jh = j < N - 1 ? j : N - 2;
+        // accepted state = base state + first-order correction (w = 0 unless status == 2); lane k of the group handles
+        // elements k, k+8, ... of the time slice: consecutive lanes write consecutive addresses of the reference layout.
+        // Four elements per lane are loaded before any of them is stored so the shared-memory loads overlap.
+        auto emit4 = [&](int e0) {
             T s0[4], sc[4][6], ap[4];
 #pragma unroll
-            for (int rr = 0; rr < 4; ++rr) {
-                const int r = rr < 3 ? k + 8 * rr : 24;
-                const T* sp = Sg + (size_t)(j * 25 + r) * KC_WS;
-                s0[rr] = sp[0];
+            for (int u = 0; u < 4; ++u) {
+                const int e = e0 + 8 * u;
+                const int ec = e < NV ? e : NV - 1;
+                const T* sp = Sg + (size_t)ec * KC_WS;
+                s0[u] = sp[0];
 #pragma unroll
-                for (int c = 0; c < 6; ++c) sc[rr][c] = sp[c + 1];
-                const int sl = (NH == 12) ? (r >= 13 ? r - 13 : 0) : r;
-                ap[rr] = As[(size_t)(jh * NH + sl) * KC_WG];
+                for (int c = 0; c < 6; ++c) sc[u][c] = sp[c + 1];
+                ap[u] = As[(size_t)(ec >= H0 ? ec - H0 : 0) * KC_WG];
             }
 #pragma unroll
-            for (int rr = 0; rr < 4; ++rr) {
-                const int r = rr < 3 ? k + 8 * rr : 24;
-                const bool act = rr < 3 || k == 0;
-                const T v0 = s0[rr];
-                T va = (sc[rr][0] - v0) * w[0], vb = (sc[rr][1] - v0) * w[1];
-                va += (sc[rr][2] - v0) * w[2]; vb += (sc[rr][3] - v0) * w[3];
-                va += (sc[rr][4] - v0) * w[4]; vb += (sc[rr][5] - v0) * w[5];
-                T v = v0 + (va + vb);
-                if (j == N - 1 && r >= 19) v = zl[rr];   // z[:, N-1] is never written by the march
-                if (act && valid) nxt[(size_t)(j * 25 + r) * KC_LS] = v;
-                const bool hrow = (NH == 12) ? r >= 13 : true;   // history for the next step; A <- accepted
-                if (act && hrow && j < N - 1) {
-                    const int sl = (NH == 12) ? r - 13 : r;
-                    const size_t hi = (size_t)(j * NH + sl) * KC_WG;
-                    Hs[hi] = P.c1 * v + P.c2 * ap[rr];
-                    As[hi] = v;
+            for (int u = 0; u < 4; ++u) {
+                const int e = e0 + 8 * u;
+                const T v0 = s0[u];
+                T va = (sc[u][0] - v0) * w[0], vb = (sc[u][1] - v0) * w[1];
+                va += (sc[u][2] - v0) * w[2]; vb += (sc[u][3] - v0) * w[3];
+                va += (sc[u][4] - v0) * w[4]; vb += (sc[u][5] - v0) * w[5];
+                const T v = v0 + (va + vb);
+                if (e < NV) {
+                    if (valid) nxt[e] = v;
+                    if (e >= H0) {   // history for the next step; A <- accepted
+                        const size_t hi = (size_t)(e - H0) * KC_WG;
+                        Hs[hi] = P.c1 * v + P.c2 * ap[u];
+                        As[hi] = v;
+                    }
                 }
             }
+        };
+        if (NC) {
+#pragma unroll
+            for (int i = 0; i < (25 * NC + 31) / 32; ++i) emit4(k + 32 * i);
+        } else {
+            for (int e0 = k; e0 < NV; e0 += 32) emit4(e0);
         }
         if (k == 0 && valid) {
             if (Gout) {
@@ -358,6 +355,27 @@ kc_rollout_wide_lin_kernel(const __grid_constant__ RodC<T> P, const MlpC<T> M, i
             if (iters) iters[(size_t)b * T_ + t + 1] = status > 0 ? marches : -marches;
         }
         __syncwarp();
+    }
+}
+
+// rows == 50 after a direct-layout rollout: rows 25:50 of time index t are yh,zh = c1*state[t-1] + c2*state[t-2]
+// (state[-1] := state[0]); index 0 repeats [y;z] (knode.py:68,74-75).  One thread per element of [B][T][25*N].
+template <typename T>
+__global__ void kc_hist_rows_kernel(T* __restrict__ traj, int64_t B, int T_, int NV, T c1, T c2) {
+    const int64_t total = B * T_ * NV;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int e = (int)(i % NV);
+        const int64_t bt = i / NV;
+        const int t = (int)(bt % T_);
+        T* slice = traj + bt * 2 * NV;
+        T v;
+        if (t == 0) v = slice[e];
+        else {
+            const T a = slice[e - 2 * NV];
+            const T p = t >= 2 ? slice[e - 4 * NV] : a;
+            v = c1 * a + c2 * p;
+        }
+        slice[NV + e] = v;
     }
 }
 
@@ -519,12 +537,13 @@ static int rollout_typed(const kc_rod_params* Pp, const kc_mlp* mlp, int64_t B, 
         if (!(e && e[0] == 'w')) wide = false;
     }
     // linearised final correction (saves the last verification march) when its shared-memory state fits 7 warps per SM
-    const size_t lsmem = ((size_t)N * 25 * KC_WS + (size_t)2 * (N - 1) * NH * KC_WG) * sizeof(T);
-    bool lin = wide && lsmem <= 32 * 1024;
+    // (it writes the reference layout directly, so it needs rows != 0)
+    const size_t lsmem = ((size_t)N * 25 * KC_WS + (size_t)2 * N * NH * KC_WG) * sizeof(T);
+    bool lin = wide && rows != 0 && lsmem <= 32 * 1024;
     {
         const char* e = getenv("KC_ROLLOUT_LIN");
         if (e && e[0] == '0') lin = false;
-        if (e && e[0] == '1' && lsmem <= 200 * 1024) lin = wide;
+        if (e && e[0] == '1' && lsmem <= 200 * 1024) lin = wide && rows != 0;
     }
     // warp-cooperative KNODE rollout: MLP in the march and too few rods to fill the chip with one rod per thread
     bool coop = in_dim != 0 && !wide && B <= 8192;
@@ -555,24 +574,34 @@ static int rollout_typed(const kc_rod_params* Pp, const kc_mlp* mlp, int64_t B, 
         else { if (in_dim == 28) KC_LAUNCH_COOP(false, 28, 12); else KC_LAUNCH_COOP(false, 53, 25); }
 #undef KC_LAUNCH_COOP
         } else if (wide && lin) {
+            // writes the reference layout directly; rows 25:50 (if asked for) are filled by an elementwise pass
             const unsigned wgrid = (unsigned)((B + KC_WG - 1) / KC_WG);
-#define KC_LAUNCH_WLIN(D, I, H)                                                                                        \
+            const int64_t tstride = (int64_t)rows * N;
+#define KC_LAUNCH_WLIN(D, I, H, NC)                                                                                    \
     do {                                                                                                               \
-        auto kern = kc_rollout_wide_lin_kernel<T, D, I, H>;                                                            \
+        auto kern = kc_rollout_wide_lin_kernel<T, D, I, H, NC>;                                                        \
         if (lsmem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem);    \
-        kern<<<wgrid, 32, lsmem, st>>>(P, M, B, (int)T_, (const T*)tensions, (const T*)y0, (const T*)z0, trajD, tl,    \
-                                       max_iter, fd_eps, (T*)G_out, iters);                                            \
+        kern<<<wgrid, 32, lsmem, st>>>(P, M, B, (int)T_, (const T*)tensions, (const T*)y0, (const T*)z0, (T*)traj,     \
+                                       tstride, tl, max_iter, fd_eps, (T*)G_out, iters);                               \
     } while (0)
             if (P.diag) {
-                if (in_dim == 0) KC_LAUNCH_WLIN(true, 0, 12);
-                else if (in_dim == 28) KC_LAUNCH_WLIN(true, 28, 12);
-                else KC_LAUNCH_WLIN(true, 53, 25);
+                if (in_dim == 0) { if (N == 10) KC_LAUNCH_WLIN(true, 0, 12, 10); else KC_LAUNCH_WLIN(true, 0, 12, 0); }
+                else if (in_dim == 28) KC_LAUNCH_WLIN(true, 28, 12, 0);
+                else KC_LAUNCH_WLIN(true, 53, 25, 0);
             } else {
-                if (in_dim == 0) KC_LAUNCH_WLIN(false, 0, 12);
-                else if (in_dim == 28) KC_LAUNCH_WLIN(false, 28, 12);
-                else KC_LAUNCH_WLIN(false, 53, 25);
+                if (in_dim == 0) { if (N == 10) KC_LAUNCH_WLIN(false, 0, 12, 10); else KC_LAUNCH_WLIN(false, 0, 12, 0); }
+                else if (in_dim == 28) KC_LAUNCH_WLIN(false, 28, 12, 0);
+                else KC_LAUNCH_WLIN(false, 53, 25, 0);
             }
 #undef KC_LAUNCH_WLIN
+            KC_CHECK_LAUNCH("kc_rollout_wide_lin_kernel");
+            if (rows == 50) {
+                const int64_t total = B * T_ * 25 * N;
+                const unsigned hgrid = (unsigned)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+                kc_hist_rows_kernel<T><<<hgrid, 256, 0, st>>>((T*)traj, B, (int)T_, 25 * N, P.c1, P.c2);
+                KC_CHECK_LAUNCH("kc_hist_rows_kernel");
+            }
+            return KC_OK;
         } else if (wide) {
             const size_t wsmem = (size_t)NH * (N - 1) * KC_WG * sizeof(T);
             const unsigned wgrid = (unsigned)((B + KC_WG - 1) / KC_WG);

@@ -126,18 +126,32 @@ KC_HD int wide_decide_lin(const T Fall[7][6], T G[6], const T eps[6], T tol, T& 
     return 0;
 }
 
-// Sink that keeps the marched state of one lane in shared memory: [node][row][slot stride SS].  Stores are unconditional:
-// the kernel freezes the marched point of a finished rod, so its re-marches rewrite the same values.
-template <typename T, int SS> struct SmemStateSink {
-    T* p;
-    KC_HD void put(int j, const T y[19]) {
-        T* pn = p + (size_t)j * 25 * SS;
+// Views in "output order" e = r*n + j (row r, node j: the order of one [25][N] slice of the reference trajectory).
+// NC = compile-time node count (0: run-time n).  History element (slot s, node j) sits at s*n + j.
+template <typename T, int NH, int LS, int NC> struct HistViewE {
+    const T* p; int n;
+    KC_HD void load(int j, T hist[NH]) const {
+        const int N = NC ? NC : n;
+        const T* hn = p + (size_t)j * LS;
 #pragma unroll
-        for (int r = 0; r < 19; ++r) pn[r * SS] = y[r];
+        for (int s = 0; s < NH; ++s) hist[s] = hn[(size_t)s * N * LS];
+    }
+};
+
+// Sink that keeps the marched state of one lane in shared memory, [25*n][slot stride SS] in output order.  Stores are
+// unconditional: the kernel freezes the marched point of a finished rod, so its re-marches rewrite the same values.
+template <typename T, int SS, int NC> struct SmemStateSinkE {
+    T* p; int n;
+    KC_HD void put(int j, const T y[19]) {
+        const int N = NC ? NC : n;
+        T* pn = p + (size_t)j * SS;
+#pragma unroll
+        for (int r = 0; r < 19; ++r) pn[(size_t)r * N * SS] = y[r];
     }
     KC_HD void putz(int j, const T z[6]) {
-        T* pn = p + (size_t)j * 25 * SS;
+        const int N = NC ? NC : n;
+        T* pn = p + (size_t)j * SS;
 #pragma unroll
-        for (int c = 0; c < 6; ++c) pn[(19 + c) * SS] = z[c];
+        for (int c = 0; c < 6; ++c) pn[(size_t)(19 + c) * N * SS] = z[c];
     }
 };

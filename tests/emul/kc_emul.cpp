@@ -126,7 +126,7 @@ static void run_wide_lin(const RodC<T>& P, const MlpC<T>& M, int64_t B, int64_t 
                 for (int k = 0; k < 7; ++k) {
                     T Ge[6];
                     for (int i = 0; i < 6; ++i) Ge[i] = G[i] + ((k == i + 1) ? eps[i] : T(0));
-                    SmemStateSink<T, 1> Sk{S.data() + (size_t)k * NV};
+                    SmemStateSinkE<T, 1, 0> Sk{S.data() + (size_t)k * NV, N};   // output order e = r*N + j
                     rod_march<T, DIAG, IN, NH>(P, M, Ge, tf, H, Sk, Fall[k]);
                 }
                 ++marches;
@@ -138,9 +138,9 @@ static void run_wide_lin(const RodC<T>& P, const MlpC<T>& M, int64_t B, int64_t 
             for (int e = 0; e < NV; ++e) {
                 T v = S[e];
                 if (status == 2) { const T v0 = v; for (int c = 0; c < 6; ++c) v += (S[(size_t)(c + 1) * NV + e] - v0) * w[c]; }
-                const int j = e / 25, r = e - j * 25;
+                const int r = e / N, j = e - r * N;
                 if (j == N - 1 && r >= 19) v = zlast[r - 19];
-                out_t[e] = v;
+                out_t[(size_t)j * 25 + r] = v;
             }
             build_history<T, NH, 1>(P, out_t.data(), A.data(), Hs.data());
             A = out_t;
