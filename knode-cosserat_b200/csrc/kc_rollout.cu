@@ -282,6 +282,7 @@ kc_rollout_wide_lin_kernel(const __grid_constant__ RodC<T> P, const MlpC<T> M, i
         // Gm: the point the group marches.  It is frozen once the rod is done, so while other rods of the warp still
         // iterate its re-marches reproduce the marched states bit for bit and the sink stores without a predicate.
         T Gm[6];
+        bool first = true;
         while (true) {
             T eps[6], Ge[6], F[6];
 #pragma unroll
@@ -289,8 +290,14 @@ kc_rollout_wide_lin_kernel(const __grid_constant__ RodC<T> P, const MlpC<T> M, i
             wide_eps(Gm, fd_eps, eps);
 #pragma unroll
             for (int i = 0; i < 6; ++i) Ge[i] = Gm[i] + ((k == i + 1) ? eps[i] : T(0));
-            SmemStateSinkE<T, KC_WS, NC> S{Sg + (k < 7 ? k : 0), N};   // lane 7 repeats lane 0 (same values, same address)
-            rod_march<T, DIAG, IN, NH>(P, M, Ge, tf, H, S, F);
+            if (first) {
+                // the first joint march of a step is never the accepted one (see the loop exit): no state stores
+                WideNoSink S0;
+                rod_march<T, DIAG, IN, NH>(P, M, Ge, tf, H, S0, F);
+            } else {
+                SmemStateSinkE<T, KC_WS, NC> S{Sg + (k < 7 ? k : 0), N};   // lane 7 repeats lane 0 (same values, same address)
+                rod_march<T, DIAG, IN, NH>(P, M, Ge, tf, H, S, F);
+            }
             T Fall[7][6];
 #pragma unroll
             for (int c = 0; c < 7; ++c) {
@@ -303,7 +310,9 @@ kc_rollout_wide_lin_kernel(const __grid_constant__ RodC<T> P, const MlpC<T> M, i
                 if (r != 0) { done = true; status = r; }
                 else if (marches >= max_iter) { done = true; status = -1; }
             }
-            if (__all_sync(full, done)) break;
+            // a rod that converged on the first march is re-marched once at its frozen point so that S holds its state
+            if (!first && __all_sync(full, done)) break;
+            first = false;
         }
 #pragma unroll
         for (int i = 0; i < 6; ++i) { Gm1[i] = Gp[i]; w[i] = (status == 2) ? w[i] : T(0); }

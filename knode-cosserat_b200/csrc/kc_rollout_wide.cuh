@@ -155,3 +155,8 @@ template <typename T, int SS, int NC> struct SmemStateSinkE {
         for (int c = 0; c < 6; ++c) pn[(size_t)(19 + c) * N * SS] = z[c];
     }
 };
+
+struct WideNoSink {
+    template <typename T> KC_HD void put(int, const T*) {}
+    template <typename T> KC_HD void putz(int, const T*) {}
+};
