@@ -214,12 +214,10 @@ def main():
     ctl_host = synthetic_tensions(B, T, robot.del_t, seed=rank, dtype=np.float32)
     ctl = torch.tensor(ctl_host, device=dev)
     plan = _ops.RolloutPlan(P, None, B, T, torch.float32, dev, rows=25)
-    plan_k = _ops.RolloutPlan(P, None, B, T, torch.float32, dev, rows=0)   # rollout kernel alone (roofline)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     for _ in range(args.warmup):
         plan.run(ctl)
-        plan_k.run(ctl)
     torch.cuda.synchronize()
     its = plan.iters.cpu().numpy()
     assert its.min() >= 0, "a rod failed to converge during warm-up"
@@ -243,15 +241,9 @@ def main():
     rns_per_step = B * N_NODES * (T - 1)
     value = world * rns_per_step * args.steps / (total_ms * 1e-3)
 
-    # rollout kernel alone, for the roofline object
-    evk = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    for i in range(args.steps):
-        flush.zero_()
-        evk[i][0].record()
-        plan_k.run(ctl)
-        evk[i][1].record()
-    torch.cuda.synchronize()
-    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in evk]))
+    # a step IS one launch of the rollout kernel (it writes the reference layout itself): the events around the step
+    # bracket exactly that kernel, on this rank
+    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
     fp32_peak = _ops.fma_peak(torch.float32, 40000, dev)
     achieved = rns_per_step * FLOP_PER_RNS / (kern_ms * 1e-3)
     peaks = {}
@@ -409,23 +401,28 @@ def main():
                                    "100 time indices (99 solved steps), setup_robot params, half sine / half random "
                                    "tensions", "rods_per_gpu": B, "nodes": N_NODES, "time_indices": T,
                        "output": "traj[B,T,25,N] fp32 in the reference layout, resident in HBM",
-                       "l2": "827 MB written per step (> 126 MB L2) plus an explicit 256 MB flush between timed "
+                       "l2": "410 MB written per step (> 126 MB L2) plus an explicit 256 MB flush between timed "
                              "iterations", "parallelism": f"rods sharded over {world} rank(s), no collective",
                        "solver": {"marches_per_step_mean": marches_mean, "marches_per_step_warp": marches_warp,
                                   "nominal_evals_per_step": E_REF}},
             "clocks": sampler.summary(),
             "e2e": {"value": e2e_value, "unit": "rod-node-steps/s", "h2d_bytes_per_step": int(ctl_host.nbytes),
                     "d2h_bytes_per_step": int(pinned.numel() * 4), "api": "knode.simulate(robot, ctl[B,T,4], "
-                    "dtype=float32, rows=25) host numpy in -> host numpy out", "ms_per_step": e2e_s / args.steps * 1e3},
-            "gpu_launches": 2 * args.steps,
-            "roofline": {"bound": "fp32", "kernel": "kc_rollout_wide_kernel<float,diag,physics> (8 lanes per rod, Newton + per-march FD Jacobian)", "achieved": achieved / 1e12,
+                    "dtype=float32, rows=25) host numpy in -> host numpy out = one kc_rollout_host C-ABI call (H2D, "
+                    "rollout in time ranges, D2H of each finished range overlapped with the next)",
+                    "ms_per_step": e2e_s / args.steps * 1e3},
+            "gpu_launches": 1 * args.steps,
+            "roofline": {"bound": "fp32", "kernel": "kc_rollout_wide_lin_kernel<float,diag,physics,N=10> (8 lanes per rod: "
+                         "Newton + per-march FD Jacobian + linearised final correction; writes traj[B,T,25,N] directly)",
+                         "achieved": achieved / 1e12,
                          "peak": fp32_peak / 1e12, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
                          "peak_source": "kc_fma_peak micro-benchmark measured live in this run (MEASURED_PEAKS.json has "
                                         "no FP32-pipe figure)", "normalisation": "6.06 kFLOP per rod-node-step = 15 "
                          "nominal residual evaluations x 9/10 x 449 FLOP (SURVEY 8d)",
                          "kernel_ms": kern_ms, "executed_tflops": executed_flop / (kern_ms * 1e-3) / 1e12,
-                         "traffic": 516.3e6, "traffic_source": "ncu dram__bytes_read+write per launch, profiles/r01_ncu_prof_rollout_wide_r1c.csv "
-                         "(algorithmic 416 MB: the trajectory is written once, 106 MB read back for the BDF2 history)",
+                         "traffic": 364.1e6, "traffic_source": "ncu dram__bytes_read+write per launch, "
+                         "profiles/r01_ncu_prof_rollout_lin_r1h.csv (algorithmic 416 MB: 410 MB trajectory written once + "
+                         "6.5 MB tensions read; the tail of the trajectory is still in L2 when the kernel ends)",
                          "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak}},
             "cpu_baseline": cpu, "train": train, "train_bptt": bptt}
         print(json.dumps(out))

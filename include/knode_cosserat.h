@@ -119,6 +119,32 @@ int kc_rollout_fwd(int dtype, const kc_rod_params *P, const kc_mlp *mlp, int64_t
                    int32_t rows, void *traj, void *G_out, int32_t *iters, void *workspace,
                    int64_t workspace_bytes, void *stream);
 
+/* The same rollout in TIME RANGES: solve steps t in [t_begin, t_end) only, i.e. write time indices t_begin+1 .. t_end
+ * (and index 0 when t_begin == 0) of traj / G_out / iters.  Ranges must be issued in order on one stream with the same
+ * buffers and workspace: a later range resumes from the trajectory already written plus the solver state kept in the
+ * workspace.  Used to overlap the device-to-host copy of finished ranges with the solve of the next one.
+ * kc_rollout_resumable() -> 1 if the kernel this (dtype, MLP, B, T, rows) selects can run in ranges (one-rod-per-lane
+ * Broyden and wide-lin do), 0 if only the full range [0, T-1) is accepted, <0 on bad arguments. */
+int kc_rollout_fwd_range(int dtype, const kc_rod_params *P, const kc_mlp *mlp, int64_t B, int64_t T,
+                         const void *tensions, const void *y0, const void *z0, double tol, int32_t max_iter,
+                         int32_t rows, void *traj, void *G_out, int32_t *iters, void *workspace,
+                         int64_t workspace_bytes, int64_t t_begin, int64_t t_end, void *stream);
+int kc_rollout_resumable(int dtype, const kc_rod_params *P, const kc_mlp *mlp, int64_t B, int64_t T, int32_t rows);
+
+/* knode.simulate for HOST callers (knode.py:55-102, batched): tensions_host[B][T][4] in host memory ->
+ * traj_host[B][T][rows][N] (+ G_host[B][T][6], iters_host[B][T] if non-NULL) in host memory (pinned memory makes the
+ * copies asynchronous; pageable memory works, slower).  The call stages the tensions, runs the rollout in `segments`
+ * time ranges (<= 0: chosen from the trajectory size, 1..8) and copies every finished range back on an internal second
+ * stream while the next one is solved; it RETURNS WHEN THE RESULT IS IN HOST MEMORY (it synchronises `stream`).
+ * rows = 25 | 50.  y0/z0 (optional) and the MLP weights are device pointers as everywhere else.  device_buf: device
+ * scratch of kc_rollout_host_device_bytes() bytes (holds the device copies of tensions/traj/G/iters + the workspace). */
+int64_t kc_rollout_host_device_bytes(int dtype, const kc_rod_params *P, const kc_mlp *mlp, int64_t B, int64_t T,
+                                     int32_t rows);
+int kc_rollout_host(int dtype, const kc_rod_params *P, const kc_mlp *mlp, int64_t B, int64_t T,
+                    const void *tensions_host, const void *y0, const void *z0, double tol, int32_t max_iter,
+                    int32_t rows, void *traj_host, void *G_host, int32_t *iters_host, void *device_buf,
+                    int64_t device_buf_bytes, int32_t segments, void *stream);
+
 /* Reverse mode THROUGH kc_rollout_fwd (back-propagation through time; BASELINE.json north_star subsystem 3 — an extension:
  * the reference never differentiates a rollout).  traj[B][T][25][N] is the forward result (rows = 25),
  * g_traj[B][T][25][N] = dL/dtraj -> g_tensions[B][T][4] (may be NULL) and, with an MLP, the OVERWRITTEN parameter

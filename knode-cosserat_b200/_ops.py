@@ -215,6 +215,67 @@ class RolloutPlan:
         return self.traj
 
 
+class HostRolloutPlan:
+    """kc_rollout_host: host tensions in -> host trajectory out, transfers pipelined with the solve inside the call.
+
+    Holds the device scratch and PINNED host buffers for one shape; `run` returns torch CPU tensors that alias the pinned
+    buffers (they are overwritten by the next run) unless `out` is given.
+    """
+
+    def __init__(self, P, mlp, B, T, dtype, device, rows=25, want_G=False, want_iters=True, segments=0):
+        if rows not in (25, 50):
+            raise ValueError("rows must be 25 or 50")
+        self.P, self.B, self.T, self.rows, self.dtype, self.device = P, B, T, rows, dtype, device
+        self.mlp, self.mref = _mlp_ref(mlp, dtype)
+        self.code = _DT[dtype]
+        self.segments = int(segments)
+        with torch.cuda.device(device):
+            nbytes = _kc.lib().kc_rollout_host_device_bytes(self.code, C.byref(P), self.mref, B, T, rows)
+        if nbytes < 0:
+            raise ValueError("kc_rollout_host_device_bytes: bad arguments")
+        self.nbytes = int(nbytes)
+        self.dbuf = torch.empty(max(self.nbytes, 1), dtype=torch.uint8, device=device)
+        self.tens_h = torch.empty((B, T, 4), dtype=dtype).pin_memory()
+        self.traj_h = None
+        self.G_h = torch.empty((B, T, 6), dtype=dtype).pin_memory() if want_G else None
+        self.iters_h = torch.empty((B, T), dtype=torch.int32).pin_memory() if want_iters else None
+
+    def rebind(self, P, mlp):
+        self.P = P
+        self.mlp, self.mref = _mlp_ref(mlp, self.dtype)
+
+    def run(self, tensions_host, y0=None, z0=None, tol=0.0, max_iter=0, out=None):
+        """tensions_host: numpy array or CPU tensor [B,T,4]; out: optional CPU tensor [B,T,rows,N] (ideally pinned)."""
+        th = torch.as_tensor(tensions_host)
+        if th.is_cuda:
+            raise ValueError("kc_rollout_host takes HOST tensions (use RolloutPlan for device tensors)")
+        if tuple(th.shape) != (self.B, self.T, 4):
+            raise ValueError(f"tensions must be [{self.B},{self.T},4], got {tuple(th.shape)}")
+        if th.dtype == self.dtype and th.is_contiguous() and th.is_pinned():
+            src = th
+        else:
+            self.tens_h.copy_(th)          # dtype conversion + staging into pinned memory
+            src = self.tens_h
+        if out is None:
+            if self.traj_h is None:
+                self.traj_h = torch.empty((self.B, self.T, self.rows, int(self.P.N)), dtype=self.dtype).pin_memory()
+            out = self.traj_h
+        if out.is_cuda or out.dtype != self.dtype or not out.is_contiguous() or \
+                tuple(out.shape) != (self.B, self.T, self.rows, int(self.P.N)):
+            raise ValueError("out must be a contiguous CPU tensor [B,T,rows,N] of the plan's dtype")
+        if y0 is not None:
+            _require_cuda(y0, z0)
+            y0, z0 = _c(y0, self.dtype), _c(z0, self.dtype)
+        with torch.cuda.device(self.device):
+            rc = _kc.lib().kc_rollout_host(self.code, C.byref(self.P), self.mref, self.B, self.T, src.data_ptr(),
+                                           _ptr(y0), _ptr(z0), float(tol), int(max_iter), self.rows, out.data_ptr(),
+                                           self.G_h.data_ptr() if self.G_h is not None else None,
+                                           self.iters_h.data_ptr() if self.iters_h is not None else None,
+                                           _ptr(self.dbuf), self.nbytes, self.segments, _stream(self.device))
+        _kc.check(rc, "kc_rollout_host")
+        return out
+
+
 def rollout(P, mlp, tensions, y0=None, z0=None, tol=0.0, max_iter=0, rows=25, want_G=False):
     """kc_rollout_fwd: tensions[B,T,4] -> traj[B,T,rows,N] (+ G[B,T,6]) and iters[B,T]."""
     _require_cuda(tensions)

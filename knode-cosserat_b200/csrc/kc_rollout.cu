@@ -217,7 +217,10 @@ template <typename T, bool DIAG, int IN, int NH, int NC>
 __global__ void __launch_bounds__(32)
 kc_rollout_wide_lin_kernel(const __grid_constant__ RodC<T> P, const MlpC<T> M, int64_t B, int T_,
                            const T* __restrict__ tensions, const T* __restrict__ y0, const T* __restrict__ z0,
-                           T* __restrict__ out, int64_t tstride, T tol, int max_iter, T fd_eps, T* Gout, int32_t* iters) {
+                           T* out, int64_t tstride, T* gstate, size_t Bpad, int t_begin, int t_end, T tol, int max_iter,
+                           T fd_eps, T* Gout, int32_t* iters) {
+    // steps t in [t_begin, t_end) are solved (time indices t_begin+1 .. t_end are written; t_begin == 0 also writes
+    // index 0).  A later launch resumes from the trajectory itself plus gstate[12][Bpad] = the last two roots.
     extern __shared__ __align__(16) unsigned char kc_smem[];
     const int N = NC ? NC : P.N;
     const int NV = 25 * N;
@@ -236,18 +239,24 @@ kc_rollout_wide_lin_kernel(const __grid_constant__ RodC<T> P, const MlpC<T> M, i
     // march, cosserat_ode.py:198-201: they keep the initial z for the whole rollout)
     for (int e = k; e < NV; e += 8) {
         const int r = e / N, j = e - r * N;
-        T v;
-        if (r < 19) v = y0 ? y0[(size_t)b * 19 * N + e] : ((r == 2) ? P.ds * T(j) : (r == 3 ? T(1) : T(0)));
-        else v = z0 ? z0[(size_t)b * 6 * N + (e - 19 * N)] : ((r == 21) ? T(1) : T(0));
+        T v, vp;
+        if (t_begin == 0) {
+            if (r < 19) v = y0 ? y0[(size_t)b * 19 * N + e] : ((r == 2) ? P.ds * T(j) : (r == 3 ? T(1) : T(0)));
+            else v = z0 ? z0[(size_t)b * 6 * N + (e - 19 * N)] : ((r == 21) ? T(1) : T(0));
+            vp = v;                                             // state[-1] := state[0] (knode.py:65-66)
+            if (valid) out_b[e] = v;
+        } else {
+            v = out_b[(size_t)t_begin * tstride + e];
+            vp = out_b[(size_t)(t_begin - 1) * tstride + e];
+        }
         if (e >= H0) {
             As[(size_t)(e - H0) * KC_WG] = v;
-            Hs[(size_t)(e - H0) * KC_WG] = (P.c1 + P.c2) * v;   // state[-1] := state[0] (knode.py:65-66)
+            Hs[(size_t)(e - H0) * KC_WG] = P.c1 * v + P.c2 * vp;
         }
 #pragma unroll
         for (int c = 0; c < 7; ++c) Sg[(size_t)e * KC_WS + c] = v;
-        if (valid) out_b[e] = v;
     }
-    if (k == 0 && valid) {
+    if (k == 0 && valid && t_begin == 0) {
         if (Gout) {
 #pragma unroll
             for (int i = 0; i < 6; ++i) Gout[(size_t)b * T_ * 6 + i] = T(0);
@@ -257,16 +266,19 @@ kc_rollout_wide_lin_kernel(const __grid_constant__ RodC<T> P, const MlpC<T> M, i
     __syncwarp();
     T G[6], Gm1[6];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) { G[i] = T(0); Gm1[i] = T(0); }
+    for (int i = 0; i < 6; ++i) {
+        G[i] = t_begin == 0 ? T(0) : gstate[(size_t)i * Bpad + b];
+        Gm1[i] = t_begin == 0 ? T(0) : gstate[(size_t)(6 + i) * Bpad + b];
+    }
     T Cest = T(0);
     const T* ten = tensions + (size_t)b * T_ * 4;
     T tn[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) tn[i] = ten[i];
-    for (int t = 0; t < T_ - 1; ++t) {
+    for (int i = 0; i < 4; ++i) tn[i] = ten[(size_t)t_begin * 4 + i];
+    for (int t = t_begin; t < t_end; ++t) {
         T tf[3];
         tendon_force(P, tn, tf);
-        if (t + 1 < T_ - 1) {
+        if (t + 1 < t_end) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) tn[i] = ten[(size_t)(t + 1) * 4 + i];
         }
@@ -365,18 +377,23 @@ kc_rollout_wide_lin_kernel(const __grid_constant__ RodC<T> P, const MlpC<T> M, i
         }
         __syncwarp();
     }
+    if (k == 0 && valid) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) { gstate[(size_t)i * Bpad + b] = G[i]; gstate[(size_t)(6 + i) * Bpad + b] = Gm1[i]; }
+    }
 }
 
 // rows == 50 after a direct-layout rollout: rows 25:50 of time index t are yh,zh = c1*state[t-1] + c2*state[t-2]
 // (state[-1] := state[0]); index 0 repeats [y;z] (knode.py:68,74-75).  One thread per element of [B][T][25*N].
 template <typename T>
-__global__ void kc_hist_rows_kernel(T* __restrict__ traj, int64_t B, int T_, int NV, T c1, T c2) {
-    const int64_t total = B * T_ * NV;
+__global__ void kc_hist_rows_kernel(T* __restrict__ traj, int64_t B, int T_, int NV, int t0, int nt, T c1, T c2) {
+    // time indices t0 .. t0+nt-1 of every rod
+    const int64_t total = B * nt * NV;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int e = (int)(i % NV);
         const int64_t bt = i / NV;
-        const int t = (int)(bt % T_);
-        T* slice = traj + bt * 2 * NV;
+        const int t = t0 + (int)(bt % nt);
+        T* slice = traj + ((bt / nt) * T_ + t) * 2 * NV;
         T v;
         if (t == 0) v = slice[e];
         else {
@@ -393,11 +410,11 @@ __global__ void kc_hist_rows_kernel(T* __restrict__ traj, int64_t B, int T_, int
 // rows == 50 adds yh,zh = c1*state[t-1] + c2*state[t-2] (state[-1] := state[0]); index 0 repeats [y;z] (knode.py:68).
 template <typename T>
 __global__ void kc_traj_transpose_kernel(const T* __restrict__ trajD, T* __restrict__ traj, int64_t B, int T_, int N,
-                                         int rows, T c1, T c2) {
+                                         int rows, int t_first, T c1, T c2) {
     extern __shared__ __align__(16) unsigned char kc_smem[];
     T* tile = reinterpret_cast<T*>(kc_smem);  // [N*25][33], k' = j*25 + r
     const int K = 25 * N;
-    const int t = blockIdx.y;
+    const int t = t_first + blockIdx.y;   // grid.y = number of time indices handled by this launch
     const int64_t b0 = (int64_t)blockIdx.x * 32;
     const int lane = threadIdx.x, wy = threadIdx.y, nwy = blockDim.y;
     const size_t slab = (size_t)K * KC_LS;
@@ -499,7 +516,10 @@ extern "C" int64_t kc_rollout_workspace_bytes(int dtype, const kc_rod_params* P,
 template <typename T>
 static int rollout_typed(const kc_rod_params* Pp, const kc_mlp* mlp, int64_t B, int64_t T_, const void* tensions,
                          const void* y0, const void* z0, double tol, int max_iter, int rows, void* traj, void* G_out,
-                         int32_t* iters, void* workspace, cudaStream_t st) {
+                         int32_t* iters, void* workspace, int t_begin, int t_end, bool query_resumable,
+                         cudaStream_t st) {
+    // steps [t_begin, t_end) of the rollout (full: 0 .. T-1).  query_resumable: launch nothing, return 1 if the mode this
+    // call would select can be run in several time ranges (narrow and wide-lin keep their solver state), else 0.
     const RodC<T> P = make_rodc<T>(*Pp);
     const int N = P.N;
     const RolloutWs w = rollout_ws(sizeof(T) == 4 ? KC_F32 : KC_F64, N, mlp, B, T_);
@@ -509,8 +529,10 @@ static int rollout_typed(const kc_rod_params* Pp, const kc_mlp* mlp, int64_t B, 
     MlpC<T> M{};
     int in_dim = 0;
     if (mlp) {
-        int rc = kc_pack_mlp<T>(mlp, (T*)(ws + w.wp), M, st);
-        if (rc) return rc;
+        if (!query_resumable) {
+            int rc = kc_pack_mlp<T>(mlp, (T*)(ws + w.wp), M, st);
+            if (rc) return rc;
+        }
         in_dim = mlp->in_dim;
     }
     const T tl = tol > 0 ? (T)tol : (sizeof(T) == 4 ? T(2e-6) : T(1e-11));
@@ -561,7 +583,12 @@ static int rollout_typed(const kc_rod_params* Pp, const kc_mlp* mlp, int64_t B, 
         if (e && e[0] == '0') coop = false;
         if (e && e[0] == '1' && in_dim != 0) coop = true;
     }
-    if (B > 0) {
+    const bool full_range = t_begin == 0 && t_end == (int)T_ - 1;
+    const bool resumable = !coop && (!wide || lin);
+    if (query_resumable) return resumable ? 1 : 0;
+    KC_CHECK_ARG(full_range || resumable, "this rollout mode cannot be run in time ranges");
+    const int t_first = t_begin == 0 ? 0 : t_begin + 1, n_idx = t_end - t_first + 1;   // time indices this call produces
+    if (B > 0 && n_idx > 0) {
         if (coop) {
         MlpCoop<T> MC;
         static_cast<MlpC<T>&>(MC) = M;
@@ -591,7 +618,7 @@ static int rollout_typed(const kc_rod_params* Pp, const kc_mlp* mlp, int64_t B, 
         auto kern = kc_rollout_wide_lin_kernel<T, D, I, H, NC>;                                                        \
         if (lsmem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem);    \
         kern<<<wgrid, 32, lsmem, st>>>(P, M, B, (int)T_, (const T*)tensions, (const T*)y0, (const T*)z0, (T*)traj,     \
-                                       tstride, tl, max_iter, fd_eps, (T*)G_out, iters);                               \
+                                       tstride, state, w.Bpad, t_begin, t_end, tl, max_iter, fd_eps, (T*)G_out, iters);\
     } while (0)
             if (P.diag) {
                 if (in_dim == 0) { if (N == 10) KC_LAUNCH_WLIN(true, 0, 12, 10); else KC_LAUNCH_WLIN(true, 0, 12, 0); }
@@ -605,9 +632,9 @@ static int rollout_typed(const kc_rod_params* Pp, const kc_mlp* mlp, int64_t B, 
 #undef KC_LAUNCH_WLIN
             KC_CHECK_LAUNCH("kc_rollout_wide_lin_kernel");
             if (rows == 50) {
-                const int64_t total = B * T_ * 25 * N;
+                const int64_t total = B * n_idx * 25 * N;
                 const unsigned hgrid = (unsigned)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
-                kc_hist_rows_kernel<T><<<hgrid, 256, 0, st>>>((T*)traj, B, (int)T_, 25 * N, P.c1, P.c2);
+                kc_hist_rows_kernel<T><<<hgrid, 256, 0, st>>>((T*)traj, B, (int)T_, 25 * N, t_first, n_idx, P.c1, P.c2);
                 KC_CHECK_LAUNCH("kc_hist_rows_kernel");
             }
             return KC_OK;
@@ -637,7 +664,7 @@ static int rollout_typed(const kc_rod_params* Pp, const kc_mlp* mlp, int64_t B, 
         auto kern = kc_rollout_kernel<T, D, I, H>;                                                                     \
         if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
         kern<<<grid, threads, smem, st>>>(P, M, B, (int)T_, rpw, (const T*)tensions, (const T*)y0, (const T*)z0,       \
-                                          trajD, w.Bpad, state, 0, (int)T_ - 1, tl, max_iter, fd_eps, (T*)G_out,       \
+                                          trajD, w.Bpad, state, t_begin, t_end, tl, max_iter, fd_eps, (T*)G_out,       \
                                           iters);                                                                      \
     } while (0)
             if (P.diag) {
@@ -657,32 +684,59 @@ static int rollout_typed(const kc_rod_params* Pp, const kc_mlp* mlp, int64_t B, 
         const size_t tsmem = (size_t)K * 33 * sizeof(T);
         auto tk = kc_traj_transpose_kernel<T>;
         if (tsmem > 48 * 1024) cudaFuncSetAttribute(tk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem);
-        dim3 tgrid((unsigned)((B + 31) / 32), (unsigned)T_);
-        tk<<<tgrid, dim3(32, 8), tsmem, st>>>(trajD, (T*)traj, B, (int)T_, N, rows, P.c1, P.c2);
+        dim3 tgrid((unsigned)((B + 31) / 32), (unsigned)n_idx);
+        tk<<<tgrid, dim3(32, 8), tsmem, st>>>(trajD, (T*)traj, B, (int)T_, N, rows, t_first, P.c1, P.c2);
         KC_CHECK_LAUNCH("kc_traj_transpose_kernel");
     }
     return KC_OK;
+}
+
+static int rollout_checked(int dtype, const kc_rod_params* P, const kc_mlp* mlp, int64_t B, int64_t T_,
+                           const void* tensions, const void* y0, const void* z0, double tol, int32_t max_iter,
+                           int32_t rows, void* traj, void* G_out, int32_t* iters, void* workspace,
+                           int64_t workspace_bytes, int64_t t_begin, int64_t t_end, bool query, void* stream) {
+    KC_CHECK_ARG(dtype == KC_F32 || dtype == KC_F64, "dtype must be KC_F32 or KC_F64");
+    KC_CHECK_ARG(P && P->N >= 2, "rod params missing or N < 2");
+    KC_CHECK_ARG(B >= 0 && T_ >= 1, "B must be >= 0 and T >= 1");
+    KC_CHECK_ARG(rows == 25 || rows == 50 || rows == 0, "rows must be 25, 50 or 0");
+    KC_CHECK_ARG(0 <= t_begin && t_begin <= t_end && t_end <= T_ - 1, "time range must satisfy 0 <= t_begin <= t_end <= T-1");
+    int rc = kc_check_mlp(mlp);
+    if (rc) return rc;
+    if (!query) {
+        KC_CHECK_ARG(B == 0 || (tensions && (traj || rows == 0) && workspace), "NULL tensions/traj/workspace");
+        KC_CHECK_ARG((y0 == nullptr) == (z0 == nullptr), "y0 and z0 must be given together");
+        const int64_t need = kc_rollout_workspace_bytes(dtype, P, mlp, B, T_);
+        if (workspace_bytes < need) {
+            kc_set_error("workspace too small: %lld < %lld", (long long)workspace_bytes, (long long)need);
+            return KC_ENOSPACE;
+        }
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == KC_F32)
+        return rollout_typed<float>(P, mlp, B, T_, tensions, y0, z0, tol, max_iter, rows, traj, G_out, iters, workspace,
+                                    (int)t_begin, (int)t_end, query, st);
+    return rollout_typed<double>(P, mlp, B, T_, tensions, y0, z0, tol, max_iter, rows, traj, G_out, iters, workspace,
+                                 (int)t_begin, (int)t_end, query, st);
 }
 
 extern "C" int kc_rollout_fwd(int dtype, const kc_rod_params* P, const kc_mlp* mlp, int64_t B, int64_t T_,
                               const void* tensions, const void* y0, const void* z0, double tol, int32_t max_iter,
                               int32_t rows, void* traj, void* G_out, int32_t* iters, void* workspace,
                               int64_t workspace_bytes, void* stream) {
-    KC_CHECK_ARG(dtype == KC_F32 || dtype == KC_F64, "dtype must be KC_F32 or KC_F64");
-    KC_CHECK_ARG(P && P->N >= 2, "rod params missing or N < 2");
-    KC_CHECK_ARG(B >= 0 && T_ >= 1, "B must be >= 0 and T >= 1");
-    KC_CHECK_ARG(rows == 25 || rows == 50 || rows == 0, "rows must be 25, 50 or 0");
-    KC_CHECK_ARG(B == 0 || (tensions && (traj || rows == 0) && workspace), "NULL tensions/traj/workspace");
-    KC_CHECK_ARG((y0 == nullptr) == (z0 == nullptr), "y0 and z0 must be given together");
-    int rc = kc_check_mlp(mlp);
-    if (rc) return rc;
-    const int64_t need = kc_rollout_workspace_bytes(dtype, P, mlp, B, T_);
-    if (workspace_bytes < need) {
-        kc_set_error("workspace too small: %lld < %lld", (long long)workspace_bytes, (long long)need);
-        return KC_ENOSPACE;
-    }
-    cudaStream_t st = (cudaStream_t)stream;
-    if (dtype == KC_F32)
-        return rollout_typed<float>(P, mlp, B, T_, tensions, y0, z0, tol, max_iter, rows, traj, G_out, iters, workspace, st);
-    return rollout_typed<double>(P, mlp, B, T_, tensions, y0, z0, tol, max_iter, rows, traj, G_out, iters, workspace, st);
+    return rollout_checked(dtype, P, mlp, B, T_, tensions, y0, z0, tol, max_iter, rows, traj, G_out, iters, workspace,
+                           workspace_bytes, 0, T_ - 1, false, stream);
+}
+
+extern "C" int kc_rollout_fwd_range(int dtype, const kc_rod_params* P, const kc_mlp* mlp, int64_t B, int64_t T_,
+                                    const void* tensions, const void* y0, const void* z0, double tol, int32_t max_iter,
+                                    int32_t rows, void* traj, void* G_out, int32_t* iters, void* workspace,
+                                    int64_t workspace_bytes, int64_t t_begin, int64_t t_end, void* stream) {
+    return rollout_checked(dtype, P, mlp, B, T_, tensions, y0, z0, tol, max_iter, rows, traj, G_out, iters, workspace,
+                           workspace_bytes, t_begin, t_end, false, stream);
+}
+
+extern "C" int kc_rollout_resumable(int dtype, const kc_rod_params* P, const kc_mlp* mlp, int64_t B, int64_t T_,
+                                    int32_t rows) {
+    return rollout_checked(dtype, P, mlp, B, T_, nullptr, nullptr, nullptr, 0.0, 0, rows, nullptr, nullptr, nullptr,
+                           nullptr, 0, 0, T_ - 1, true, nullptr);
 }

@@ -90,13 +90,15 @@ def simulate(robot, ctl, robot_reference=None, *, dtype=np.float64, rows=50, tol
         raise RuntimeError("knode-cosserat_b200 has no CPU fallback: simulate() needs a CUDA device")
     dev = torch.device("cuda", torch.cuda.current_device())
     tdt = torch.float64 if np.dtype(dtype) == np.float64 else torch.float32
-    if torch.is_tensor(ctl):
+    on_device = torch.is_tensor(ctl) and ctl.is_cuda
+    if on_device:
         tens = ctl.to(dev, tdt)
     else:
-        ctl_np = np.asarray(ctl)
-        if ctl_np.dtype != np.dtype(dtype):
-            ctl_np = ctl_np.astype(np.float64).astype(dtype)   # lists / ints go through float64 like knode.py:71
-        tens = torch.from_numpy(np.ascontiguousarray(ctl_np)).to(dev, non_blocking=True)
+        ctl_np = ctl.detach().numpy() if torch.is_tensor(ctl) else np.asarray(ctl)
+        if ctl_np.dtype.kind != 'f':
+            ctl_np = ctl_np.astype(np.float64)                 # lists / ints go through float64 like knode.py:71
+        # the cast to the arithmetic type happens while staging into pinned memory (HostRolloutPlan.run), in one pass
+        tens = torch.from_numpy(np.ascontiguousarray(ctl_np))
     single = tens.ndim == 2
     if single:
         tens = tens[None]
@@ -104,7 +106,8 @@ def simulate(robot, ctl, robot_reference=None, *, dtype=np.float64, rows=50, tol
     # the reference leaves the last applied tensions on the robot (knode.py:71)
     if T > 0 and B > 0:
         last = ctl[-1] if single else ctl[-1][-1]
-        robot.tendon_tensions = np.array(last.detach().cpu() if torch.is_tensor(last) else last).astype(np.float64)
+        robot.tendon_tensions = np.asarray(last.detach().cpu().numpy() if torch.is_tensor(last) else last,
+                                           dtype=np.float64).copy()
     P = _kc.rod_params(robot)
     mlp = _robot_mlp(robot, tdt)
     # initial state: the kernel builds the straight rod of knode.py:58-64 itself; an explicit y0/z0 is only needed when
@@ -113,24 +116,38 @@ def simulate(robot, ctl, robot_reference=None, *, dtype=np.float64, rows=50, tol
     if robot_reference is not robot or tdt == torch.float64:
         y0n, z0n = _initial_state(robot_reference, B)
         y0, z0 = torch.as_tensor(y0n).to(dev, tdt), torch.as_tensor(z0n).to(dev, tdt)
-    key = (B, T, rows, tdt, dev, int(P.N), None if mlp is None else (mlp.in_dim, mlp.hidden), bool(return_info))
+    key = (B, T, rows, tdt, dev, int(P.N), None if mlp is None else (mlp.in_dim, mlp.hidden), bool(return_info),
+           on_device)
     plan = _PLANS.get(key)
     if plan is None:
         if len(_PLANS) >= 4:
             _PLANS.clear()
-        plan = _PLANS[key] = _ops.RolloutPlan(P, mlp, B, T, tdt, dev, rows, want_G=return_info)
+        if on_device:
+            plan = _ops.RolloutPlan(P, mlp, B, T, tdt, dev, rows, want_G=return_info)
+        else:
+            plan = _ops.HostRolloutPlan(P, mlp, B, T, tdt, dev, rows, want_G=return_info)
+        _PLANS[key] = plan
     plan.rebind(P, mlp)
-    plan.run(tens, y0, z0, tol=tol, max_iter=max_iter)
-    traj, G, iters = plan.traj, plan.G, plan.iters
-    if pinned_out is not None:
-        pinned_out.copy_(traj, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        out = pinned_out.numpy()
+    if on_device:
+        plan.run(tens, y0, z0, tol=tol, max_iter=max_iter)
+        traj, G, iters = plan.traj, plan.G, plan.iters
+        if pinned_out is not None:
+            pinned_out.copy_(traj, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            out = pinned_out.numpy()
+        else:
+            out = traj.cpu().numpy()   # a fresh host array: the device buffers of the cached plan are reused by later calls
+        if return_info:
+            Gn, itn = G.cpu().numpy(), iters.cpu().numpy()
     else:
-        out = traj.cpu().numpy()   # a fresh host array: the device buffers of the cached plan are reused by later calls
+        # host data in, host data out: ONE C-ABI call (kc_rollout_host) that stages the tensions, solves the rollout in
+        # time ranges and copies each finished range back while the next one is computed
+        dst = pinned_out if pinned_out is not None else torch.empty((B, T, rows, int(P.N)), dtype=tdt)
+        out = plan.run(tens, y0, z0, tol=tol, max_iter=max_iter, out=dst).numpy()
+        if return_info:
+            Gn, itn = plan.G_h.numpy().copy(), plan.iters_h.numpy().copy()
     if single:
         out = out[0]
     if return_info:
-        Gn, itn = G.cpu().numpy(), iters.cpu().numpy()
         return (out, Gn[0], itn[0]) if single else (out, Gn, itn)
     return out
