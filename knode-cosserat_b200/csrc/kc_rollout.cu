@@ -264,11 +264,13 @@ kc_rollout_wide_lin_kernel(const __grid_constant__ RodC<T> P, const MlpC<T> M, i
         if (iters) iters[(size_t)b * T_] = 0;
     }
     __syncwarp();
-    T G[6], Gm1[6];
+    T G[6], Gm1[6], D[6], Dm1[6];   // D: root change expected from the coming tension change (wide_decide_lin)
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
         G[i] = t_begin == 0 ? T(0) : gstate[(size_t)i * Bpad + b];
         Gm1[i] = t_begin == 0 ? T(0) : gstate[(size_t)(6 + i) * Bpad + b];
+        D[i] = t_begin == 0 ? T(0) : gstate[(size_t)(12 + i) * Bpad + b];
+        Dm1[i] = t_begin == 0 ? T(0) : gstate[(size_t)(18 + i) * Bpad + b];
     }
     T Cest = T(0);
     const T* ten = tensions + (size_t)b * T_ * 4;
@@ -276,16 +278,20 @@ kc_rollout_wide_lin_kernel(const __grid_constant__ RodC<T> P, const MlpC<T> M, i
 #pragma unroll
     for (int i = 0; i < 4; ++i) tn[i] = ten[(size_t)t_begin * 4 + i];
     for (int t = t_begin; t < t_end; ++t) {
-        T tf[3];
+        T tf[3], tfn[3];
         tendon_force(P, tn, tf);
-        if (t + 1 < t_end) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) tn[i] = ten[(size_t)(t + 1) * 4 + i];
-        }
+        for (int i = 0; i < 4; ++i) tn[i] = ten[(size_t)(t + 1) * 4 + i];   // t + 1 <= T - 1: always a valid row
+        tendon_force(P, tn, tfn);
         T* nxt = out_b + (size_t)(t + 1) * tstride;
         T Gp[6], w[6];
 #pragma unroll
-        for (int i = 0; i < 6; ++i) { Gp[i] = G[i]; G[i] = G[i] + (G[i] - Gm1[i]); w[i] = T(0); }
+        for (int i = 0; i < 6; ++i) {
+            Gp[i] = G[i];
+            G[i] = G[i] + ((G[i] - Gm1[i]) + (D[i] - Dm1[i]));   // linear extrapolation + anticipated tension change
+            Dm1[i] = D[i];
+            w[i] = T(0);
+        }
         bool done = false;
         int status = 0, marches = 0;
         T sprev = T(0);
@@ -303,9 +309,13 @@ kc_rollout_wide_lin_kernel(const __grid_constant__ RodC<T> P, const MlpC<T> M, i
 #pragma unroll
             for (int i = 0; i < 6; ++i) Ge[i] = Gm[i] + ((k == i + 1) ? eps[i] : T(0));
             if (first) {
-                // the first joint march of a step is never the accepted one (see the loop exit): no state stores
+                // the first joint march of a step is never the accepted one (see the loop exit): no state stores; its
+                // spare lane 7 marches the base point under the NEXT step's tendon load (tension-aware predictor)
                 WideNoSink S0;
-                rod_march<T, DIAG, IN, NH>(P, M, Ge, tf, H, S0, F);
+                T tfl[3];
+#pragma unroll
+                for (int i = 0; i < 3; ++i) tfl[i] = (k == 7) ? tfn[i] : tf[i];
+                rod_march<T, DIAG, IN, NH>(P, M, Ge, tfl, H, S0, F);
             } else {
                 SmemStateSinkE<T, KC_WS, NC> S{Sg + (k < 7 ? k : 0), N};   // lane 7 repeats lane 0 (same values, same address)
                 rod_march<T, DIAG, IN, NH>(P, M, Ge, tf, H, S, F);
@@ -316,7 +326,15 @@ kc_rollout_wide_lin_kernel(const __grid_constant__ RodC<T> P, const MlpC<T> M, i
 #pragma unroll
                 for (int i = 0; i < 6; ++i) Fall[c][i] = __shfl_sync(full, F[i], (lane & ~7) | c);
             }
-            if (!done) {
+            if (first) {
+                T Fnext[6];
+#pragma unroll
+                for (int i = 0; i < 6; ++i) Fnext[i] = __shfl_sync(full, F[i], lane | 7);
+                ++marches;
+                const int r = wide_decide_lin(Fall, G, eps, tol, Cest, sprev, w, Fnext, D);
+                if (r != 0) { done = true; status = r; }
+                else if (marches >= max_iter) { done = true; status = -1; }
+            } else if (!done) {
                 ++marches;
                 const int r = wide_decide_lin(Fall, G, eps, tol, Cest, sprev, w);
                 if (r != 0) { done = true; status = r; }
@@ -379,7 +397,10 @@ kc_rollout_wide_lin_kernel(const __grid_constant__ RodC<T> P, const MlpC<T> M, i
     }
     if (k == 0 && valid) {
 #pragma unroll
-        for (int i = 0; i < 6; ++i) { gstate[(size_t)i * Bpad + b] = G[i]; gstate[(size_t)(6 + i) * Bpad + b] = Gm1[i]; }
+        for (int i = 0; i < 6; ++i) {
+            gstate[(size_t)i * Bpad + b] = G[i]; gstate[(size_t)(6 + i) * Bpad + b] = Gm1[i];
+            gstate[(size_t)(12 + i) * Bpad + b] = D[i]; gstate[(size_t)(18 + i) * Bpad + b] = Dm1[i];
+        }
     }
 }
 

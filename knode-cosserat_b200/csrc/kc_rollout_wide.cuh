@@ -15,16 +15,19 @@ template <typename T> KC_HD void wide_eps(const T G[6], T fd_eps, T eps[6]) {
 // Fall[k][i]: residual i of lane k (k = 0 base, k = c+1 perturbed in component c).
 // Returns 1 = converged at G (the base lane's march is the accepted state), 0 = G advanced by a Newton step,
 // -1 = failure (NaN or singular Jacobian).
-template <typename T> KC_HD int wide_decide(const T Fall[7][6], T G[6], const T eps[6], T tol) {
+// F2 (optional): a second right-hand side, solved with the same factorisation: X2 = -J^-1 (F2 - F(G)).
+template <typename T>
+KC_HD int wide_decide(const T Fall[7][6], T G[6], const T eps[6], T tol, const T* F2 = nullptr, T* X2 = nullptr) {
     const T fn = norm_inf6(Fall[0]);
     if (!(fn == fn)) return -1;
     if (fn <= tol * kc_max(T(1), norm_inf6(G))) return 1;
-    T A[36], rhs[6], ie[6], ip[6];
+    T A[36], rhs[6], rhs2[6], ie[6], ip[6];
 #pragma unroll
     for (int c = 0; c < 6; ++c) ie[c] = kc_rcp(eps[c]);
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
         rhs[i] = -Fall[0][i];
+        rhs2[i] = F2 ? Fall[0][i] - F2[i] : T(0);
 #pragma unroll
         for (int c = 0; c < 6; ++c) A[i * 6 + c] = (Fall[c + 1][i] - Fall[0][i]) * ie[c];
     }
@@ -42,16 +45,18 @@ template <typename T> KC_HD int wide_decide(const T Fall[7][6], T G[6], const T 
 #pragma unroll
             for (int c = p + 1; c < 6; ++c) A[r * 6 + c] -= f * A[p * 6 + c];
             rhs[r] -= f * rhs[p];
+            if (F2) rhs2[r] -= f * rhs2[p];
         }
     }
     if (bad) return -1;
     T dG[6];
 #pragma unroll
     for (int r = 5; r >= 0; --r) {
-        T s = rhs[r];
+        T s = rhs[r], s2 = rhs2[r];
 #pragma unroll
-        for (int c = r + 1; c < 6; ++c) s -= A[r * 6 + c] * dG[c];
+        for (int c = r + 1; c < 6; ++c) { s -= A[r * 6 + c] * dG[c]; if (F2) s2 -= A[r * 6 + c] * X2[c]; }
         dG[r] = s * ip[r];
+        if (F2) X2[r] = s2 * ip[r];
     }
 #pragma unroll
     for (int i = 0; i < 6; ++i) G[i] += dG[i];
@@ -102,18 +107,26 @@ template <typename T, int LS, int NH, int CS> struct TrajSinkPred {
 // curvature of the residual map) is estimated from THIS step's own iterations: after a Newton step of size s the new
 // residual is ~ C s^2 (so the correction can be used from the second joint march of a step on, never on stale data).  Returns 1 = converged at G (state = base lane's), 2 = accepted G + dG with the linearised state (w[c] =
 // dG_c/eps_c returned), 0 = G advanced, keep marching, -1 = failure.
+//
+// Tension-aware predictor: on the FIRST joint march of a step the spare 8th lane marches the base point under the NEXT
+// step's tendon load; Fnext is its residual.  D = -J^-1 (Fnext - F(G)) is the change of the root that the coming change
+// of the tensions will cause (first order, this step's history) — the caller adds D(t) - D(t-1) to the linear
+// extrapolation of G (a jump of the controls is anticipated instead of being discovered by Newton: 3.2 -> 3.0 joint
+// marches per step on random tensions, 2.2 -> 2.0 on sines).  D is left untouched when Fnext == nullptr.
 template <typename T>
-KC_HD int wide_decide_lin(const T Fall[7][6], T G[6], const T eps[6], T tol, T& Cest, T& sprev, T w[6]) {
+KC_HD int wide_decide_lin(const T Fall[7][6], T G[6], const T eps[6], T tol, T& Cest, T& sprev, T w[6],
+                          const T* Fnext = nullptr, T* D = nullptr) {
     const T fn = norm_inf6(Fall[0]);
     if (!(fn == fn)) return -1;
     const T scale = kc_max(T(1), norm_inf6(G));
     if (sprev > T(0)) Cest = kc_max(Cest, fn * kc_rcp(sprev * sprev));   // this residual is what the last step left behind
-    if (fn <= tol * scale) return 1;
+    if (!Fnext && fn <= tol * scale) return 1;
     T Gn[6];
 #pragma unroll
     for (int i = 0; i < 6; ++i) Gn[i] = G[i];
-    const int r = wide_decide(Fall, Gn, eps, T(-1));   // tol < 0: always take the Newton step
+    const int r = wide_decide(Fall, Gn, eps, T(-1), Fnext, D);   // tol < 0: always factor and take the Newton step
     if (r < 0) return -1;
+    if (fn <= tol * scale) return 1;                            // (first march: D was still wanted)
     T dG[6], s = T(0);
 #pragma unroll
     for (int i = 0; i < 6; ++i) { dG[i] = Gn[i] - G[i]; s = kc_max(s, kc_abs(dG[i])); G[i] = Gn[i]; }

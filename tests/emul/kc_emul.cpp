@@ -110,12 +110,19 @@ static void run_wide_lin(const RodC<T>& P, const MlpC<T>& M, int64_t B, int64_t 
         T zlast[6];
         for (int c = 0; c < 6; ++c) zlast[c] = A[(size_t)(N - 1) * 25 + 19 + c];
         T G[6] = {0, 0, 0, 0, 0, 0}, Gm1[6] = {0, 0, 0, 0, 0, 0}, Cest = 0;
+        T D[6] = {0, 0, 0, 0, 0, 0}, Dm1[6] = {0, 0, 0, 0, 0, 0};
         for (int t = 0; t < T_ - 1; ++t) {
-            T tn[4], tf[3];
+            T tn[4], tf[3], tfn[3];
             for (int i = 0; i < 4; ++i) tn[i] = ten[(b * T_ + t) * 4 + i];
             tendon_force(P, tn, tf);
+            for (int i = 0; i < 4; ++i) tn[i] = ten[(b * T_ + t + 1) * 4 + i];
+            tendon_force(P, tn, tfn);
             T Gp[6], w[6] = {0, 0, 0, 0, 0, 0};
-            for (int i = 0; i < 6; ++i) { Gp[i] = G[i]; G[i] = G[i] + (G[i] - Gm1[i]); }
+            for (int i = 0; i < 6; ++i) {
+                Gp[i] = G[i];
+                G[i] = G[i] + ((G[i] - Gm1[i]) + (D[i] - Dm1[i]));
+                Dm1[i] = D[i];
+            }
             int marches = 0, status = 0;
             T sprev = 0;
             Cest = T(0);
@@ -130,7 +137,15 @@ static void run_wide_lin(const RodC<T>& P, const MlpC<T>& M, int64_t B, int64_t 
                     rod_march<T, DIAG, IN, NH>(P, M, Ge, tf, H, Sk, Fall[k]);
                 }
                 ++marches;
-                const int r = wide_decide_lin(Fall, G, eps, tol, Cest, sprev, w);
+                int r;
+                if (marches == 1) {   // lane 7 of the first joint march: base point under the next step's tendon load
+                    T Fnext[6];
+                    NullSink S0;
+                    rod_march<T, DIAG, IN, NH>(P, M, G, tfn, H, S0, Fnext);
+                    r = wide_decide_lin(Fall, G, eps, tol, Cest, sprev, w, Fnext, D);
+                } else {
+                    r = wide_decide_lin(Fall, G, eps, tol, Cest, sprev, w);
+                }
                 if (r != 0) { status = r; break; }
                 if (marches >= max_iter) { status = -1; break; }
             }
