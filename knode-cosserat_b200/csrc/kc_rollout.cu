@@ -578,7 +578,12 @@ static int rollout_typed(const kc_rod_params* Pp, const kc_mlp* mlp, int64_t B, 
     const unsigned grid = (unsigned)((B + rpw - 1) / rpw);
     // mode: wide (8 lanes per rod, Newton with a fresh FD Jacobian per joint march) while the 8x lanes still fit the
     // chip's resident warps; narrow (one rod per lane, Broyden) beyond that.  KC_ROLLOUT_MODE=wide|narrow overrides.
-    bool wide = B * 8 <= (int64_t)148 * 4 * 32 * 2;  // <= 2 warps per scheduler (B <= 4736 on 148 SMs)
+    // Measured (tools/b_sweep.py, fp32 physics): wide-lin 1.25 ms @ 4096, 2.31 ms @ 8192, 3.51 ms @ 12288 rods against
+    // 3.31 / 3.61 ms for narrow @ 8192 / 12288 -> wide up to three resident waves (7 warps x 4 rods per SM each).
+    // Without the linearised variant (fp64, N > 10: shared memory) the older bound of 2 warps per scheduler stands.
+    const bool lin_fits = rows != 0 &&
+                          ((size_t)N * 25 * KC_WS + (size_t)2 * N * NH * KC_WG) * sizeof(T) <= 32 * 1024;
+    bool wide = lin_fits ? B <= (int64_t)3 * 148 * 7 * KC_WG : B * 8 <= (int64_t)148 * 4 * 32 * 2;
     {
         const char* e = getenv("KC_ROLLOUT_MODE");
         if (e && e[0] == 'w') wide = true;
