@@ -274,29 +274,15 @@ def main():
         torch.manual_seed(0)
         trobot = CosseratRodTorch(str(dev), TRAIN_H)
         setup_robot(trobot)
-        nb = TRAIN_B // world                                   # C4: the 1024 trajectories are sharded across ranks
-        ttraj = plan.traj[:nb, :TRAIN_T].contiguous()
-        tctl = ctl[:nb, :TRAIN_T].contiguous()
-        W = [p.data for p in trobot.nn_models.parameters()]
-        m = [torch.zeros_like(w) for w in W]
-        v = [torch.zeros_like(w) for w in W]
-        step_no = [0]
+        # C4: the 1024 trajectories are sharded across the ranks by the trainer itself (rank r keeps shard r)
+        from _train import TeacherForcedTrainer
+        trainer = TeacherForcedTrainer(trobot, plan.traj[:TRAIN_B, :TRAIN_T].contiguous(),
+                                       ctl[:TRAIN_B, :TRAIN_T].contiguous(), TRAIN_KEYS, lr=1e-2)
 
         def train_step():
-            loss, grads, _ = trobot.teacher_forced_step(ttraj, tctl, TRAIN_KEYS)
-            if world > 1:
-                flat = torch.cat([g.reshape(-1) for g in grads])
-                dist.all_reduce(flat)                            # the only collective: 27,673 fp32 gradients
-                off = 0
-                new = []
-                for g in grads:
-                    new.append(flat[off:off + g.numel()].view_as(g))
-                    off += g.numel()
-                grads = new
-            step_no[0] += 1
-            for i, (w, g) in enumerate(zip(W, grads)):
-                _ops.adam_clamp(w, g, m[i], v[i], step_no[0], lr=1e-2, clamp=(i % 2 == 0))
-            return loss
+            # kc_train_step -> all-reduce of [gradients | loss] -> kc_adam_clamp_multi; one CUDA-graph launch per step
+            # from the third call on; no host read of the loss inside the timed region
+            trainer.fused_step(train=True, sync=False)
 
         for _ in range(args.warmup):
             train_step()
@@ -304,16 +290,17 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(args.steps):
-            loss = train_step()
+            train_step()
         e1.record()
         barrier()
         tms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
         q = TRAIN_B * (TRAIN_T - 1) * len(TRAIN_KEYS)
         train = {"metric": "KNODE train steps/sec", "value": 1e3 / tms, "unit": "steps/s", "ms_per_step": tms,
                  "global_batch_trajectories": TRAIN_B, "samples_per_step": q, "scaling": "strong",
-                 "semantics": "teacher-forced (physics_train.py), fwd+loss+bwd+allreduce+Adam+clamp",
+                 "semantics": "teacher-forced (physics_train.py), fwd+loss+bwd+allreduce+Adam+clamp through "
+                              "_train.TeacherForcedTrainer.fused_step (CUDA graph: %s)" % (trainer.graph is not None),
                  "useful_tflops": q * FLOP_PER_TRAIN_SAMPLE / (tms * 1e-3) / 1e12, "hidden": TRAIN_H,
-                 "loss": float(loss.item()), "kernels_per_step": 4 + 4 + 1}
+                 "loss": float(trainer.plan.flat[-1].item()), "kernels_per_step": 4 + 1 + 1}
 
     # ---------------- KNODE rollout training step (C3 ii, north-star extension): rollout + loss + BPTT + Adam ----------
     bptt = None

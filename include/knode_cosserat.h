@@ -173,6 +173,20 @@ int kc_adam_clamp(int dtype, int64_t n, void *param, const void *grad, void *exp
                   int32_t step, double lr, double beta1, double beta2, double eps, double weight_decay,
                   int32_t clamp_min_zero, void *stream);
 
+/* The same update for ALL parameter tensors in one launch, with the step count and the learning rate resident on the
+ * device — nothing of the launch depends on host state, so a whole training step (kc_train_step, the gradient
+ * all-reduce, this call) can be captured once in a CUDA graph and replayed (physics_train.py:289-304 per epoch).
+ * *step_dev = number of updates applied so far (int64, advanced by the kernel), *lr_dev = learning rate (double,
+ * rewritten by the host when ReduceLROnPlateau fires), ticket_dev = one zero-initialised int32 of scratch. */
+typedef struct kc_adam_tensor {
+    void *param; const void *grad; void *exp_avg, *exp_avg_sq; /* device pointers, dtype of the call */
+    int64_t n;
+    int32_t clamp_min_zero, reserved;
+} kc_adam_tensor;
+int kc_adam_clamp_multi(int dtype, int32_t n_tensors, const kc_adam_tensor *tensors_host, int64_t *step_dev,
+                        const double *lr_dev, double beta1, double beta2, double eps, double weight_decay,
+                        int32_t *ticket_dev, void *stream);
+
 /* FMA-pipe micro-benchmark used as the compute-roofline denominator by bench.py: runs `iters` dependent-chain
  * FMAs x 8 chains per thread on a full grid and returns the number of FLOPs executed in *flops_host; time it with
  * CUDA events on `stream`. */

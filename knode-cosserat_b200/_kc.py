@@ -72,6 +72,8 @@ _SIGNATURES = {
                                 C.POINTER(C.c_int32)] + [C.c_void_p] * 9 + [C.c_int64, C.c_void_p]),
     "kc_adam_clamp": (C.c_int, [C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                 C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int32, C.c_void_p]),
+    "kc_adam_clamp_multi": (C.c_int, [C.c_int, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double,
+                                      C.c_double, C.c_double, C.c_void_p, C.c_void_p]),
     "kc_umma_selftest": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "kc_fma_peak": (C.c_int, [C.c_int, C.c_int64, C.POINTER(C.c_double), C.c_void_p, C.c_void_p]),
 }
@@ -94,6 +96,11 @@ def lib():
             fn.argtypes = args
         _lib = L
     return _lib
+
+
+class kc_adam_tensor(C.Structure):
+    _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+                ("n", C.c_int64), ("clamp_min_zero", C.c_int32), ("reserved", C.c_int32)]
 
 
 def exported_symbols():

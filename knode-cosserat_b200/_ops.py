@@ -347,6 +347,81 @@ def adam_clamp(param, grad, exp_avg, exp_avg_sq, step, lr=1e-2, betas=(0.9, 0.99
     _kc.check(rc, "kc_adam_clamp")
 
 
+class TrainStepPlan:
+    """kc_train_step with every output and the workspace allocated once: `run()` launches kernels only (no allocation, no
+    host synchronisation), so it can be captured in a CUDA graph.  The four gradients are views of ONE flat buffer whose
+    last element receives the loss (cast to the parameter dtype): a single all-reduce covers gradients and loss."""
+
+    def __init__(self, P, weights, traj, controls, key_idx):
+        _require_cuda(traj, controls, *weights)
+        self.P = P
+        self.dt, self.dev = traj.dtype, traj.device
+        self.traj, self.controls = _c(traj), _c(controls, traj.dtype)
+        self.B, self.T, _, self.N = self.traj.shape
+        self.ki = np.ascontiguousarray(np.asarray(key_idx).reshape(-1), dtype=np.int32)
+        self.K = int(self.ki.size)
+        self.mlp = Mlp(*weights)            # borrows the parameter storage: in-place optimiser updates are seen
+        for w, t in zip(weights, (self.mlp.W1, self.mlp.b1, self.mlp.W2, self.mlp.b2)):
+            if w.data_ptr() != t.data_ptr():
+                raise ValueError("parameters must be contiguous tensors of the trajectory dtype")
+        sizes = [t.numel() for t in (self.mlp.W1, self.mlp.b1, self.mlp.W2, self.mlp.b2)]
+        self.flat = torch.zeros(sum(sizes) + 1, dtype=self.dt, device=self.dev)
+        self.grads, off = [], 0
+        for t, n in zip((self.mlp.W1, self.mlp.b1, self.mlp.W2, self.mlp.b2), sizes):
+            self.grads.append(self.flat[off:off + n].view_as(t))
+            off += n
+        self.loss64 = torch.zeros(1, dtype=torch.float64, device=self.dev)
+        with torch.cuda.device(self.dev):
+            self.nbytes = int(_kc.lib().kc_train_step_workspace_bytes(_DT[self.dt], self.mlp.ref(), self.B, self.T, self.K))
+        self.ws = torch.empty(max(self.nbytes, 1), dtype=torch.uint8, device=self.dev)
+
+    def run(self):
+        with torch.cuda.device(self.dev):
+            rc = _kc.lib().kc_train_step(_DT[self.dt], C.byref(self.P), self.mlp.ref(), self.B, self.T, self.K,
+                                         self.ki.ctypes.data_as(C.POINTER(C.c_int32)), _ptr(self.traj),
+                                         _ptr(self.controls), _ptr(self.loss64), *[_ptr(g) for g in self.grads], None,
+                                         _ptr(self.ws), self.nbytes, _stream(self.dev))
+        _kc.check(rc, "kc_train_step")
+        self.flat[-1:].copy_(self.loss64)    # f64 -> parameter dtype, on the stream
+        return self.flat
+
+
+class AdamClampMulti:
+    """kc_adam_clamp_multi: Adam + non-negative clamp of all parameter tensors in one launch; step count and learning
+    rate live on the device (graph-capturable)."""
+
+    def __init__(self, params, grads, clamp_flags, lr=1e-2, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0,
+                 exp_avg=None, exp_avg_sq=None, step=0):
+        _require_cuda(*params, *grads)
+        self.dev, self.dt = params[0].device, params[0].dtype
+        self.params, self.grads = list(params), list(grads)
+        self.exp_avg = exp_avg if exp_avg is not None else [torch.zeros_like(p) for p in params]
+        self.exp_avg_sq = exp_avg_sq if exp_avg_sq is not None else [torch.zeros_like(p) for p in params]
+        self.betas, self.eps, self.weight_decay = betas, eps, weight_decay
+        self.step_dev = torch.full((1,), int(step), dtype=torch.int64, device=self.dev)
+        self.lr_dev = torch.full((1,), float(lr), dtype=torch.float64, device=self.dev)
+        self.ticket = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        n = len(params)
+        self.arr = (_kc.kc_adam_tensor * n)()
+        for i, (p, g, m, v, c) in enumerate(zip(self.params, self.grads, self.exp_avg, self.exp_avg_sq, clamp_flags)):
+            for t in (p, g, m, v):
+                if not t.is_contiguous() or t.dtype != self.dt:
+                    raise ValueError("adam tensors must be contiguous and share one dtype")
+            self.arr[i] = _kc.kc_adam_tensor(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(),
+                                             1 if c else 0, 0)
+
+    def set_lr(self, lr):
+        self.lr_dev.fill_(float(lr))
+
+    def run(self):
+        with torch.cuda.device(self.dev):
+            rc = _kc.lib().kc_adam_clamp_multi(_DT[self.dt], len(self.params), C.cast(self.arr, C.c_void_p),
+                                               _ptr(self.step_dev), _ptr(self.lr_dev), float(self.betas[0]),
+                                               float(self.betas[1]), float(self.eps), float(self.weight_decay),
+                                               _ptr(self.ticket), _stream(self.dev))
+        _kc.check(rc, "kc_adam_clamp_multi")
+
+
 def fma_peak(dtype, iters, device):
     """Measured FP32/FP64 FMA-pipe throughput in FLOP/s (CUDA-event timed), used as the rollout's roofline peak."""
     code = _DT[dtype]

@@ -8,6 +8,7 @@ kc_adam_clamp per parameter tensor.  ReduceLROnPlateau and the bookkeeping stay 
 """
 import numpy as np
 import torch
+import torch.distributed as dist
 
 import _dist
 import _ops
@@ -46,8 +47,9 @@ class TeacherForcedTrainer:
     """
 
     def __init__(self, robot, trajs, controls, key_pt_idx, lr=1e-2, weight_decay=0.0, clamp_weight=True,
-                 patience=80, factor=0.5):
+                 patience=80, factor=0.5, fused=True, use_graph=True):
         self.robot = robot
+        self.fused, self.use_graph = fused, use_graph
         self.rank, self.world = _dist.world_info()
         traj = torch.stack(list(trajs)) if not torch.is_tensor(trajs) else trajs
         ctl = torch.stack(list(controls)) if not torch.is_tensor(controls) else controls
@@ -67,6 +69,74 @@ class TeacherForcedTrainer:
         # physics_train.py:301-304: every parameter whose name contains 'weight' is clamped (both Linear layers)
         self.is_weight = ['weight' in n and 'layer1' not in n for n, _ in robot.nn_models.named_parameters()]
 
+    # -- fused step: kc_train_step -> ONE all-reduce of the flat [gradients | loss] buffer -> kc_adam_clamp_multi --------
+    def _fused_setup(self):
+        weights = [p.data for p in self.params]
+        self.plan = _ops.TrainStepPlan(self.robot._params(), weights, self.traj, self.ctl, self.key)
+        self.adam = _ops.AdamClampMulti(weights, self.plan.grads,
+                                        [self.clamp_weight and isw for isw in self.is_weight],
+                                        lr=self.sched.get_last_lr()[0], weight_decay=self.weight_decay,
+                                        exp_avg=self.exp_avg, exp_avg_sq=self.exp_avg_sq, step=self.step_no)
+        self._lr_on_device = self.sched.get_last_lr()[0]
+        self.graph = None
+        self._eager_fused_steps = 0
+
+    def _fused_body(self, train):
+        self.plan.run()
+        if self.world > 1:
+            dist.all_reduce(self.plan.flat)          # the only collective: gradients + loss, one launch
+        if train:
+            self.adam.run()
+
+    def fused_step(self, train=True, sync=True):
+        """The same epoch as `step` with nothing but kernel launches on the critical path: outputs and workspace are
+        allocated once, Adam runs as one launch with its step count / learning rate on the device, and from the third
+        call on the whole step (kernels + NCCL all-reduce + Adam) is ONE CUDA-graph launch.  sync=False skips the host
+        read of the loss (the plateau scheduler then sees no new value for this epoch)."""
+        if not hasattr(self, "plan"):
+            self._fused_setup()
+        P = self.robot._params()
+        if P is not self.plan.P:                      # rod constants changed (setup_robot ...): a captured graph is stale
+            self.plan.P = P
+            self.graph = None
+            self._eager_fused_steps = 0
+        lr = self.sched.get_last_lr()[0]
+        if lr != self._lr_on_device:
+            self.adam.set_lr(lr)
+            self._lr_on_device = lr
+        if not train:
+            self._fused_body(False)
+        elif self.graph is not None:
+            self.graph.replay()
+        elif self._eager_fused_steps < 2 or not self.use_graph:
+            self._fused_body(True)                   # warm-up (also initialises NCCL) before capturing
+            self._eager_fused_steps += 1
+        else:
+            try:
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._fused_body(True)
+                self.graph = g                        # capture does not execute: run this epoch now
+                self.graph.replay()
+            except Exception as e:                    # e.g. a collective backend that cannot be captured
+                self.use_graph = False
+                self.graph = None
+                torch.cuda.synchronize()
+                print(f"[knode-cosserat_b200] CUDA-graph capture of the training step failed ({e}); running eagerly")
+                self._fused_body(True)
+        if train:
+            self.step_no += 1
+            for p, g in zip(self.params, self.plan.grads):
+                p.grad = g
+        if not sync:
+            return None
+        loss_val = float(self.plan.flat[-1].item())
+        self.loss_arr.append(loss_val)
+        if train:
+            self.sched.step(loss_val)
+        return loss_val
+
     def loss_and_grads(self):
         if self.traj.shape[0] > 0:
             loss, grads, _ = self.robot.teacher_forced_step(self.traj, self.ctl, self.key)
@@ -81,6 +151,8 @@ class TeacherForcedTrainer:
 
     def step(self, train=True):
         """One epoch of the reference loop: loss -> backward -> Adam -> scheduler -> clamp (physics_train.py:266-304)."""
+        if self.fused and self.traj.shape[0] > 0:
+            return self.fused_step(train)
         loss, grads = self.loss_and_grads()
         loss_val = float(loss.item())
         self.loss_arr.append(loss_val)

@@ -492,4 +492,82 @@ extern "C" int kc_adam_clamp(int dtype, int64_t n, void* param, const void* grad
     return KC_OK;
 }
 
+// ---- all parameter tensors in ONE launch, hyper-parameters resident on the device --------------------------------
+// For a training step captured in a CUDA graph: nothing of the launch depends on the host (the step count lives in
+// *step_dev and is advanced by the kernel itself, the learning rate is read from *lr_dev, which the host rewrites when
+// the plateau scheduler fires).  Up to 8 tensors; a block handles 256 consecutive elements of one tensor.
+struct AdamTensors {
+    void* p[8]; const void* g[8]; void* m[8]; void* v[8];
+    int64_t n[8]; int32_t clamp[8]; int32_t first_block[9];
+    int32_t count;
+};
+template <typename T>
+__global__ void __launch_bounds__(256)
+kc_adam_clamp_multi_kernel(const __grid_constant__ AdamTensors A, int64_t* step_dev, const double* lr_dev, double b1d,
+                           double b2d, T eps, T wd, int32_t* ticket) {
+    __shared__ T s_lr1, s_bc2s;
+    if (threadIdx.x == 0) {
+        const double step = (double)(*step_dev + 1);
+        s_lr1 = (T)(*lr_dev / (1.0 - pow(b1d, step)));
+        s_bc2s = (T)sqrt(1.0 - pow(b2d, step));
+    }
+    __syncthreads();
+    int k = 0;
+#pragma unroll
+    for (int i = 1; i < 8; ++i) if (i < A.count && (int)blockIdx.x >= A.first_block[i]) k = i;
+    const int64_t i = (int64_t)((int)blockIdx.x - A.first_block[k]) * 256 + threadIdx.x;
+    if (i < A.n[k]) {
+        T* p = (T*)A.p[k]; const T* g = (const T*)A.g[k]; T* m = (T*)A.m[k]; T* v = (T*)A.v[k];
+        const T b1 = (T)b1d, b2 = (T)b2d;
+        const T gi = g[i] + wd * p[i];
+        const T mi = b1 * m[i] + (T(1) - b1) * gi;
+        const T vi = b2 * v[i] + (T(1) - b2) * gi * gi;
+        m[i] = mi;
+        v[i] = vi;
+        const T denom = sqrt(vi) / s_bc2s + eps;
+        T pi = p[i] - s_lr1 * (mi / denom);
+        if (A.clamp[k] && pi < T(0)) pi = T(0);
+        p[i] = pi;
+    }
+    // the block that finishes last advances the step count (every block has read it by then) and re-arms the ticket
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(ticket, 1) == (int)gridDim.x - 1) {
+            *step_dev += 1;
+            *ticket = 0;
+        }
+    }
+}
+
+extern "C" int kc_adam_clamp_multi(int dtype, int32_t n_tensors, const kc_adam_tensor* t, int64_t* step_dev,
+                                   const double* lr_dev, double beta1, double beta2, double eps, double weight_decay,
+                                   int32_t* ticket_dev, void* stream) {
+    KC_CHECK_ARG(dtype == KC_F32 || dtype == KC_F64, "dtype must be KC_F32 or KC_F64");
+    KC_CHECK_ARG(n_tensors >= 1 && n_tensors <= 8 && t, "1..8 tensors");
+    KC_CHECK_ARG(step_dev && lr_dev && ticket_dev, "NULL step/lr/ticket pointer");
+    AdamTensors A{};
+    A.count = n_tensors;
+    int blocks = 0;
+    for (int i = 0; i < n_tensors; ++i) {
+        KC_CHECK_ARG(t[i].n >= 0 && (t[i].n == 0 || (t[i].param && t[i].grad && t[i].exp_avg && t[i].exp_avg_sq)),
+                     "tensor %d: NULL data pointer or negative size", i);
+        A.p[i] = t[i].param; A.g[i] = t[i].grad; A.m[i] = t[i].exp_avg; A.v[i] = t[i].exp_avg_sq;
+        A.n[i] = t[i].n; A.clamp[i] = t[i].clamp_min_zero;
+        A.first_block[i] = blocks;
+        blocks += (int)((t[i].n + 255) / 256);
+    }
+    A.first_block[n_tensors] = blocks;
+    if (blocks == 0) blocks = 1;   // still advances the step count
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == KC_F32)
+        kc_adam_clamp_multi_kernel<float><<<blocks, 256, 0, st>>>(A, step_dev, lr_dev, beta1, beta2, (float)eps,
+                                                                 (float)weight_decay, ticket_dev);
+    else
+        kc_adam_clamp_multi_kernel<double><<<blocks, 256, 0, st>>>(A, step_dev, lr_dev, beta1, beta2, eps, weight_decay,
+                                                                  ticket_dev);
+    KC_CHECK_LAUNCH("kc_adam_clamp_multi_kernel");
+    return KC_OK;
+}
+
 #include "kc_ode_bwd.inl"

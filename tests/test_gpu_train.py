@@ -160,3 +160,67 @@ def test_ode_bwd_physics_only_finite_difference(ops):
             ap[ai][:, k] += e; am[ai][:, k] -= e
             fd = (f(*ap) - f(*am)) / (2 * e)
             assert np.max(np.abs(fd - got[:, k])) < 1e-6 * (1 + np.abs(fd).max()), (ai, k)
+
+
+def _golden_robot(d, tag="none"):
+    """A CosseratRodTorch whose MLP holds the golden initial weights (hidden size from the fixture)."""
+    from cosserat_ode_torch import CosseratRodTorch
+    from knode import setup_robot
+    W = {k: d[f"{tag}_init_{k}"] for k in PK}
+    robot = CosseratRodTorch("cuda", int(W["W1"].shape[0]))
+    setup_robot(robot)
+    with torch.no_grad():
+        for p, k in zip(robot.nn_models.parameters(), PK):
+            p.copy_(torch.tensor(W[k], device="cuda"))
+    return robot
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_fused_trainer_steps_vs_reference(ops, golden, use_graph):
+    """TeacherForcedTrainer.fused_step (preallocated step + ONE kc_adam_clamp_multi launch, CUDA graph from the third
+    epoch) against the reference's weights after two Adam steps, and against the unfused trainer over six epochs."""
+    from _train import TeacherForcedTrainer
+    d = golden["train"]
+    traj = dev(d["traj"].astype(np.float32), torch.float32)
+    ctl = dev(d["controls"].astype(np.float32), torch.float32)
+    a = TeacherForcedTrainer(_golden_robot(d), traj, ctl, [3, 5, 7, 9], fused=True, use_graph=use_graph)
+    b = TeacherForcedTrainer(_golden_robot(d), traj, ctl, [3, 5, 7, 9], fused=False)
+    la, lb = [], []
+    for epoch in range(6):
+        la.append(a.step())
+        lb.append(b.step())
+        if epoch == 1:
+            for p, k in zip(a.params, PK):
+                ref = d[f"none_fast_step2_{k}"]
+                assert np.max(np.abs(p.detach().cpu().numpy() - ref)) < 2e-4 * max(np.abs(ref).max(), 1e-2), k
+    assert (a.graph is not None) == use_graph
+    assert int(a.adam.step_dev.item()) == 6 and a.step_no == 6
+    np.testing.assert_allclose(la, lb, rtol=2e-5)
+    for pa, pb in zip(a.params, b.params):
+        np.testing.assert_allclose(pa.detach().cpu().numpy(), pb.detach().cpu().numpy(), rtol=1e-4, atol=1e-6)
+    # the learning rate lives on the device: a scheduler change reaches the (captured) update
+    a.sched.lr = 0.0
+    before = [p.detach().clone() for p in a.params]
+    a.step()
+    for p, q in zip(a.params, before):
+        assert torch.equal(p.detach(), q)
+
+
+def test_adam_clamp_multi_matches_single_tensor_kernels(ops):
+    rng = np.random.default_rng(3)
+    shapes = [(17, 28), (17,), (25, 17), (25,)]
+    P1 = [dev(rng.normal(size=s), torch.float64) for s in shapes]
+    P2 = [p.clone() for p in P1]
+    m1 = [torch.zeros_like(p) for p in P1]
+    v1 = [torch.zeros_like(p) for p in P1]
+    grads = [torch.zeros_like(p) for p in P1]
+    multi = ops.AdamClampMulti(P2, grads, [True, False, True, False], lr=3e-3, weight_decay=0.05)
+    for step in (1, 2, 3):
+        for g in grads:
+            g.copy_(dev(rng.normal(size=tuple(g.shape)), torch.float64))
+        for i in range(4):
+            ops.adam_clamp(P1[i], grads[i], m1[i], v1[i], step, lr=3e-3, weight_decay=0.05, clamp=i % 2 == 0)
+        multi.run()
+        for a, b in zip(P1, P2):
+            np.testing.assert_allclose(b.cpu().numpy(), a.cpu().numpy(), rtol=1e-12, atol=1e-14)
+    assert int(multi.step_dev.item()) == 3 and int(multi.ticket.item()) == 0
