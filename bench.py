@@ -413,8 +413,22 @@ def main():
                          "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak}},
             "cpu_baseline": cpu, "train": train, "train_bptt": bptt}
         print(json.dumps(out))
+    sys.stdout.flush()
     if world > 1:
+        # a CUDA graph that captured NCCL kernels must be released before its communicator is torn down (otherwise
+        # destroy_process_group can block forever); a watchdog turns any remaining teardown hang into a clean exit
+        import gc
+        import threading
+        if not args.no_train:
+            trainer.close()
+        gc.collect()
+        torch.cuda.synchronize()
+        wd = threading.Timer(30.0, lambda: os._exit(0))
+        wd.daemon = True
+        wd.start()
+        dist.barrier()
         dist.destroy_process_group()
+        wd.cancel()
 
 
 if __name__ == "__main__":

@@ -137,6 +137,12 @@ class TeacherForcedTrainer:
             self.sched.step(loss_val)
         return loss_val
 
+    def close(self):
+        """Release the captured graph (it holds NCCL kernels: do this before torch.distributed.destroy_process_group)."""
+        if getattr(self, "graph", None) is not None:
+            torch.cuda.synchronize()
+            self.graph = None
+
     def loss_and_grads(self):
         if self.traj.shape[0] > 0:
             loss, grads, _ = self.robot.teacher_forced_step(self.traj, self.ctl, self.key)

@@ -152,6 +152,7 @@ def main(argv=None, distributed=True):
         else:
             torch.save({'robot': robot, 'dtw': dtw_arr, 'loss': loss_arr, 'optim': trainer.optim_state_dict()},
                        MODEL_SAVE_PATH)
+    trainer.close()
     return robot, loss_arr
 
 

@@ -104,6 +104,7 @@ def main(argv=None):
     if args.save_path is not None and TRAIN and rank == 0:
         os.makedirs(os.path.dirname(args.save_path) or '.', exist_ok=True)
         torch.save({'robot': robot, 'loss': trainer.loss_arr, 'optim': trainer.optim_state_dict()}, args.save_path)
+    trainer.close()
     return robot, trainer.loss_arr
 
 
