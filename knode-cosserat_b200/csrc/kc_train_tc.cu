@@ -28,12 +28,15 @@ constexpr int OFF_XL = 16384;    // X lo                                        
 constexpr int OFF_W2 = 32768;    // W2 chunk as a bf16 B operand, hi | lo (2 x 8192): pass 1 [32 outs x 128 units] K-major,
                                  // pass 2 [128 units x 32 outs] K-major                                      16384
 constexpr int OFF_DZ = 49152;    // dZ^T hi | lo, bf16 MN-major [128 units x 128 samples] 2 x 32768;
-                                 // W1 chunk hi | lo (tf32 K-major [128 x 32], 2 x 16384) ALIASES the first half
+                                 // W1 chunk hi | lo (tf32 K-major [128 x 32], 2 x 16384) ALIASES the LO half: the gradient
+                                 // MMAs that read dZ lo are issued (and signalled) first, so the next W1 chunk can land
+                                 // while the remaining gradient MMAs still run
 constexpr int OFF_A = 114688;    // A^T hi | lo, bf16 MN-major                           2 x 32768
 constexpr int OFF_XT = 180224;   // X^T hi | lo, bf16 MN-major [32 inputs x 128 samples]  2 x 8192
 constexpr int OFF_DO = 196608;   // dO^T hi | lo, bf16 MN-major [32 outputs x 128 samples] 2 x 8192
 constexpr int OFF_MISC = 212992; // tmem slot, mbarriers, reduction scratch
-constexpr int SMEM_BYTES = OFF_MISC + 1024;
+constexpr int OFF_W2B = OFF_MISC + 1024;   // second W2 image buffer (the images of consecutive stages alternate)   16384
+constexpr int SMEM_BYTES = OFF_W2B + 16384;
 constexpr int W1_TILE_FLOATS = 128 * 32;          // one hi or lo tile
 constexpr int W2B_CHUNK_BYTES = 32768;            // per chunk: W2 fwd image hi|lo (16 KB) then W2^T bwd image hi|lo (16 KB)
 // TMEM columns
@@ -48,6 +51,15 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
 __device__ __forceinline__ void split_bf16(float x, float& hi, float& lo) {
     hi = __bfloat162float(__float2bfloat16_rn(x));
     lo = x - hi;
+}
+
+// global -> shared bulk copy by the TMA engine (no registers, no threads): completes on an mbarrier by byte count
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(umma::smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(umma::smem_u32(bar)), "r"(bytes) : "memory");
 }
 
 // K-major, no swizzle, 2-byte elements: element (r, k) of a tile with KT k-values per row
@@ -95,6 +107,8 @@ kc_train_tc_kernel(int hidden, int nch, const float* __restrict__ W1hl, const un
     uint64_t* barZ = reinterpret_cast<uint64_t*>(sm + tc::OFF_MISC + 8);
     uint64_t* barG = reinterpret_cast<uint64_t*>(sm + tc::OFF_MISC + 16);
     uint64_t* barO = reinterpret_cast<uint64_t*>(sm + tc::OFF_MISC + 24);
+    uint64_t* barW = reinterpret_cast<uint64_t*>(sm + tc::OFF_MISC + 96);   // weights of the next stage have landed
+    uint64_t* barL = reinterpret_cast<uint64_t*>(sm + tc::OFF_MISC + 104);  // gradient MMAs reading the dZ lo tile done
     double* redd = reinterpret_cast<double*>(sm + tc::OFF_MISC + 32);    // [8]
     float* redb = reinterpret_cast<float*>(sm + tc::OFF_MISC + 128);     // [4][25]
     float* sO = reinterpret_cast<float*>(sm + tc::OFF_MISC + 640);       // unused now (kept for layout stability)
@@ -107,6 +121,8 @@ kc_train_tc_kernel(int hidden, int nch, const float* __restrict__ W1hl, const un
         umma::mbar_init(barZ, 1);
         umma::mbar_init(barG, 1);
         umma::mbar_init(barO, 1);
+        umma::mbar_init(barW, 1);
+        umma::mbar_init(barL, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     umma::fence_async_smem();
@@ -114,26 +130,28 @@ kc_train_tc_kernel(int hidden, int nch, const float* __restrict__ W1hl, const un
     __syncthreads();
     umma::fence_after();
     const uint32_t tbase = *tmem_slot;
-    uint32_t phZ = 0, phG = 0, phO = 0;
+    uint32_t phZ = 0, phG = 0, phO = 0, phW = 0, phL = 0;
     const uint32_t idescZ = umma::make_idesc_tf32(128, 128);
     const uint32_t idescG = umma::make_idesc_bf16(128, 32, 1, 1);   // gradient GEMMs: both operands MN-major
     const uint32_t idescO = umma::make_idesc_bf16(128, 32, 0, 0);   // O  = A W2c^T   (K-major views)
     const uint32_t idescD = umma::make_idesc_bf16(128, 128, 0, 0);  // dA = dO W2c    (K-major views)
-    const uint32_t aWB = umma::smem_u32(sm + tc::OFF_W2);
+    const uint32_t aWB0 = umma::smem_u32(sm + tc::OFF_W2), aWB1 = umma::smem_u32(sm + tc::OFF_W2B);
     const uint32_t aXh = umma::smem_u32(sm + tc::OFF_XH), aXl = umma::smem_u32(sm + tc::OFF_XL);
-    const uint32_t aW1h = umma::smem_u32(sm + tc::OFF_DZ), aW1l = aW1h + 16384;
+    const uint32_t aW1h = umma::smem_u32(sm + tc::OFF_DZ + 32768), aW1l = aW1h + 16384;   // aliases the dZ LO tile
     const uint32_t aDZh = umma::smem_u32(sm + tc::OFF_DZ), aDZl = aDZh + 32768;
     const uint32_t aAh = umma::smem_u32(sm + tc::OFF_A), aAl = aAh + 32768;
     const uint32_t aXth = umma::smem_u32(sm + tc::OFF_XT), aXtl = aXth + 8192;
     const uint32_t aDOh = umma::smem_u32(sm + tc::OFF_DO), aDOl = aDOh + 8192;
 
-    auto load_weights = [&](int c, int pass) {   // W1 chunk hi|lo -> OFF_DZ (32 KB); W2 bf16 image of this pass -> OFF_W2 (16 KB)
-        const float4* src = reinterpret_cast<const float4*>(W1hl + (size_t)c * 2 * tc::W1_TILE_FLOATS);
-        float4* dst = reinterpret_cast<float4*>(sm + tc::OFF_DZ);
-        for (int e = tid; e < 2 * tc::W1_TILE_FLOATS / 4; e += tc::THREADS) dst[e] = src[e];
-        const float4* src2 = reinterpret_cast<const float4*>(W2b + (size_t)c * tc::W2B_CHUNK_BYTES + (pass == 2 ? 16384 : 0));
-        float4* dst2 = reinterpret_cast<float4*>(sm + tc::OFF_W2);
-        for (int e = tid; e < 16384 / 16; e += tc::THREADS) dst2[e] = src2[e];
+    // Stages of a tile: s = 0..nch-1 forward chunks, s = nch..2nch-1 backward chunks.  The weights of a stage arrive by TMA
+    // bulk copies issued by thread 0 as early as their buffers are free (barW counts the bytes):
+    //   W1 chunk hi|lo (32 KB) -> OFF_DZ (free once the previous user of that region has completed),
+    //   W2 image hi|lo (16 KB: forward [outs x units] or backward [units x outs]) -> OFF_W2 / OFF_W2B alternating by stage.
+    auto fetch_w1 = [&](int c) {
+        bulk_g2s(aW1h, W1hl + (size_t)c * 2 * tc::W1_TILE_FLOATS, 2 * tc::W1_TILE_FLOATS * 4, barW);
+    };
+    auto fetch_w2 = [&](int c, int pass, int stage) {
+        bulk_g2s((stage & 1) ? aWB1 : aWB0, W2b + (size_t)c * tc::W2B_CHUNK_BYTES + (pass == 2 ? 16384 : 0), 16384, barW);
     };
     auto issue_gemm1 = [&]() {  // Z[128 samples x 128 units] = X W1c^T, 3-pass tf32 split, K = 32 (4 x K8)
         uint32_t acc = 0;
@@ -149,7 +167,7 @@ kc_train_tc_kernel(int hidden, int nch, const float* __restrict__ W1hl, const un
     };
     // O[128 samples x 32 outs] (+)= A[samples x 128 units] W2c^T: A = the activation tile viewed K-major (LBO 2048, SBO 128),
     // B = W2 image [32 outs x 128 units] K-major (LBO 128, SBO 2048); K = 128 units = 8 x K16
-    auto issue_gemm2 = [&](bool first_chunk) {
+    auto issue_gemm2 = [&](bool first_chunk, uint32_t aWB) {
         uint32_t acc = first_chunk ? 0u : 1u;
 #pragma unroll
         for (int p = 0; p < 3; ++p) {
@@ -163,7 +181,7 @@ kc_train_tc_kernel(int hidden, int nch, const float* __restrict__ W1hl, const un
     };
     // dA[128 samples x 128 units] = dO[samples x 32 outs] W2c: A = the dO tile viewed K-major (LBO 2048, SBO 128),
     // B = W2^T image [128 units x 32 outs] K-major (LBO 128, SBO 512); K = 32 = 2 x K16
-    auto issue_gemm3 = [&]() {
+    auto issue_gemm3 = [&](uint32_t aWB) {
         uint32_t acc = 0;
 #pragma unroll
         for (int p = 0; p < 3; ++p) {
@@ -175,19 +193,29 @@ kc_train_tc_kernel(int hidden, int nch, const float* __restrict__ W1hl, const un
             }
         }
     };
-    auto issue_grads = [&](int c, bool first_tile) {  // gW1c += dZ^T X ; gW2c^T += A^T dO ; K = 128 samples (8 x K16)
+    // gW1c += dZ^T X ; gW2c^T += A^T dO ; K = 128 samples (8 x K16).  The pass that reads the dZ LO tile goes first and is
+    // committed on barL (its shared memory is the landing zone of the next W1 chunk); everything else commits on barG.
+    auto issue_grads = [&](int c, bool first_tile) {
+        const uint32_t d1 = tbase + tc::COL_GW1 + 32 * c, d2 = tbase + tc::COL_GW2 + 32 * c;
+        uint32_t acc = first_tile ? 0u : 1u;
+        for (int kk = 0; kk < 8; ++kk) {   // dZ lo * X hi
+            umma::mma_bf16(d1, umma::make_desc(aDZl + kk * 256, 128, 2048), umma::make_desc(aXth + kk * 256, 128, 2048), idescG, acc);
+            acc = 1;
+        }
+        umma::commit(barL);
 #pragma unroll
-        for (int g = 0; g < 2; ++g) {
-            const uint32_t d = tbase + (g == 0 ? tc::COL_GW1 : tc::COL_GW2) + 32 * c;
-            uint32_t acc = first_tile ? 0u : 1u;
+        for (int p = 0; p < 2; ++p) {      // dZ hi * X hi, dZ hi * X lo
+            const uint32_t b = p == 0 ? aXth : aXtl;
+            for (int kk = 0; kk < 8; ++kk)
+                umma::mma_bf16(d1, umma::make_desc(aDZh + kk * 256, 128, 2048), umma::make_desc(b + kk * 256, 128, 2048), idescG, 1u);
+        }
+        acc = first_tile ? 0u : 1u;
 #pragma unroll
-            for (int p = 0; p < 3; ++p) {
-                const uint32_t a = g == 0 ? ((p == 1) ? aDZl : aDZh) : ((p == 1) ? aAl : aAh);
-                const uint32_t b = g == 0 ? ((p == 2) ? aXtl : aXth) : ((p == 2) ? aDOl : aDOh);
-                for (int kk = 0; kk < 8; ++kk) {
-                    umma::mma_bf16(d, umma::make_desc(a + kk * 256, 128, 2048), umma::make_desc(b + kk * 256, 128, 2048), idescG, acc);
-                    acc = 1;
-                }
+        for (int p = 0; p < 3; ++p) {
+            const uint32_t a = (p == 1) ? aAl : aAh, b = (p == 2) ? aDOl : aDOh;
+            for (int kk = 0; kk < 8; ++kk) {
+                umma::mma_bf16(d2, umma::make_desc(a + kk * 256, 128, 2048), umma::make_desc(b + kk * 256, 128, 2048), idescG, acc);
+                acc = 1;
             }
         }
         umma::commit(barG);
@@ -199,6 +227,11 @@ kc_train_tc_kernel(int hidden, int nch, const float* __restrict__ W1hl, const un
     double lossacc = 0.0;
     const int64_t ntiles = (Q + tc::TS - 1) / tc::TS;
     bool first_tile = true;
+    if (tid == 0 && blockIdx.x < ntiles) {   // stage 0 of the first tile
+        mbar_expect_tx(barW, 32768 + 16384);
+        fetch_w1(0);
+        fetch_w2(0, 1, 0);
+    }
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t q = tile * tc::TS + row;
         const bool valid = q < Q;
@@ -236,15 +269,21 @@ kc_train_tc_kernel(int hidden, int nch, const float* __restrict__ W1hl, const un
             }
         }
         // ---- pass 1: forward ----
+        umma::fence_async_smem();       // the X tile
+        umma::fence_before();
+        __syncthreads();
         for (int c = 0; c < nch; ++c) {
-            if (c > 0) { umma::mbar_wait(barO, phO); phO ^= 1; umma::fence_after(); }  // chunk c-1's O GEMM done: sA, OFF_W2 free
-            load_weights(c, 1);
-            umma::fence_async_smem();
-            umma::fence_before();
-            __syncthreads();
+            const int stage = c;
+            umma::mbar_wait(barW, phW); phW ^= 1;                     // W1(c), W2 fwd image(c) have landed
             if (tid == 0) { umma::fence_after(); issue_gemm1(); umma::commit(barZ); }
+            if (c > 0) { umma::mbar_wait(barO, phO); phO ^= 1; }      // chunk c-1's O GEMM done: A tile and its W2 buffer free
             umma::mbar_wait(barZ, phZ); phZ ^= 1;
             umma::fence_after();
+            if (tid == 0) {   // next stage's weights: W1 region free (GEMM1 done), other W2 buffer free (see above)
+                mbar_expect_tx(barW, 32768 + 16384);
+                if (c + 1 < nch) { fetch_w1(c + 1); fetch_w2(c + 1, 1, stage + 1); }
+                else             { fetch_w1(0);     fetch_w2(0, 2, stage + 1); }
+            }
 #pragma unroll 1
             for (int cc = 0; cc < 2; ++cc) {
                 uint32_t v[32];
@@ -265,7 +304,7 @@ kc_train_tc_kernel(int hidden, int nch, const float* __restrict__ W1hl, const un
             umma::fence_async_smem();
             umma::fence_before();
             __syncthreads();
-            if (tid == 0) { umma::fence_after(); issue_gemm2(c == 0); }
+            if (tid == 0) { umma::fence_after(); issue_gemm2(c == 0, (stage & 1) ? aWB1 : aWB0); }
         }
         umma::mbar_wait(barO, phO); phO ^= 1;
         umma::fence_after();
@@ -331,18 +370,25 @@ kc_train_tc_kernel(int hidden, int nch, const float* __restrict__ W1hl, const un
                     make_uint4(pack_bf16x2(lo[0], lo[1]), pack_bf16x2(lo[2], lo[3]), pack_bf16x2(lo[4], lo[5]), pack_bf16x2(lo[6], lo[7]));
             }
         }
+        umma::fence_async_smem();       // the dO tile
         umma::fence_before();
         __syncthreads();
         // ---- pass 2: backward ----
+        const bool more_tiles = tile + gridDim.x < ntiles;
         for (int c = 0; c < nch; ++c) {
-            if (c > 0) { umma::mbar_wait(barG, phG); phG ^= 1; umma::fence_after(); }  // chunk c-1's gradient MMAs done
-            load_weights(c, 2);
-            umma::fence_async_smem();
-            umma::fence_before();
-            __syncthreads();
-            if (tid == 0) { umma::fence_after(); issue_gemm1(); issue_gemm3(); umma::commit(barZ); }
-            umma::mbar_wait(barZ, phZ); phZ ^= 1;
+            const int stage = nch + c;
+            const uint32_t aWB = (stage & 1) ? aWB1 : aWB0;
+            umma::mbar_wait(barW, phW); phW ^= 1;                     // W1(c), W2 bwd image(c) have landed
+            if (tid == 0) { umma::fence_after(); issue_gemm1(); issue_gemm3(aWB); umma::commit(barZ); }
+            umma::mbar_wait(barZ, phZ); phZ ^= 1;                     // (in-order pipe: chunk c-1's gradient MMAs are done too)
+            if (c > 0) { umma::mbar_wait(barG, phG); phG ^= 1; }      // A and dZ tiles free
             umma::fence_after();
+            const bool prefetch = c + 1 < nch || more_tiles;
+            if (tid == 0 && prefetch) {   // the other W2 buffer is free now; W1 follows once the dZ-lo MMAs of this chunk are done
+                mbar_expect_tx(barW, 32768 + 16384);
+                if (c + 1 < nch) fetch_w2(c + 1, 2, stage + 1);
+                else fetch_w2(0, 1, 0);
+            }
 #pragma unroll 1
             for (int cc = 0; cc < 2; ++cc) {
                 uint32_t v[32], d[32];
@@ -355,8 +401,10 @@ kc_train_tc_kernel(int hidden, int nch, const float* __restrict__ W1hl, const un
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const float z = __uint_as_float(v[g8 * 8 + j]);
-                        split_bf16(kc_elu(z), ah[j], al[j]);
-                        split_bf16(__uint_as_float(d[g8 * 8 + j]) * kc_elu_grad(z), dh[j], dl[j]);
+                        const float a = kc_elu(z);
+                        split_bf16(a, ah[j], al[j]);
+                        // ELU'(z) = 1 (z > 0) or e^z = ELU(z) + 1: no second exponential
+                        split_bf16(__uint_as_float(d[g8 * 8 + j]) * (z > 0.f ? 1.f : a + 1.f), dh[j], dl[j]);
                     }
                     const uint32_t off = umma::mnmajor_off_b16(half * 64 + cc * 32 + g8 * 8, row, 128);
                     *reinterpret_cast<uint4*>(sm + tc::OFF_A + off) =
@@ -372,7 +420,13 @@ kc_train_tc_kernel(int hidden, int nch, const float* __restrict__ W1hl, const un
             umma::fence_async_smem();
             umma::fence_before();
             __syncthreads();
-            if (tid == 0) { umma::fence_after(); issue_grads(c, first_tile); }
+            if (tid == 0) {
+                umma::fence_after();
+                issue_grads(c, first_tile);
+                umma::mbar_wait(barL, phL);                           // dZ lo consumed: its bytes may take the next W1 chunk
+                if (prefetch) fetch_w1(c + 1 < nch ? c + 1 : 0);
+            }
+            phL ^= 1;
         }
         umma::mbar_wait(barG, phG); phG ^= 1;   // last chunk's gradient MMAs: they read X^T / dO^T which the next tile overwrites
         umma::fence_after();
