@@ -10,9 +10,21 @@
 template <typename T> KC_HD T kc_abs(T x) { return x < T(0) ? -x : x; }
 template <typename T> KC_HD T kc_max(T a, T b) { return a > b ? a : b; }
 
+// e^x on the device: ONE multiply and ONE MUFU.EX2 (ex2.approx.ftz, rel. error 2^-22).  __expf without -use_fast_math
+// wraps the same instruction in denormal-range handling (~12 instructions): measured as half of all instructions of the
+// tensor-core training kernel.
+KC_HD float kc_exp_fast(float x) {
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x * 1.4426950408889634f));
+    return r;
+#else
+    return expf(x);
+#endif
+}
 KC_HD float kc_elu(float x) {
 #if defined(__CUDA_ARCH__)
-    return x > 0.f ? x : (__expf(x) - 1.f);
+    return x > 0.f ? x : (kc_exp_fast(x) - 1.f);
 #else
     return x > 0.f ? x : expm1f(x);
 #endif
@@ -21,7 +33,7 @@ KC_HD double kc_elu(double x) { return x > 0.0 ? x : expm1(x); }
 // ELU'(x) given x (pre-activation)
 KC_HD float kc_elu_grad(float x) {
 #if defined(__CUDA_ARCH__)
-    return x > 0.f ? 1.f : __expf(x);
+    return x > 0.f ? 1.f : kc_exp_fast(x);
 #else
     return x > 0.f ? 1.f : expf(x);
 #endif
