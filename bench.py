@@ -300,6 +300,12 @@ def main():
                  "semantics": "teacher-forced (physics_train.py), fwd+loss+bwd+allreduce+Adam+clamp through "
                               "_train.TeacherForcedTrainer.fused_step (CUDA graph: %s)" % (trainer.graph is not None),
                  "useful_tflops": q * FLOP_PER_TRAIN_SAMPLE / (tms * 1e-3) / 1e12, "hidden": TRAIN_H,
+                 "roofline": {"bound": "tensor", "kernel": "kc_train_tc_kernel (tcgen05 + TMEM; 80 % of the step)",
+                              "achieved": q * FLOP_PER_TRAIN_SAMPLE / world / (tms * 1e-3) / 1e12, "unit": "TFLOP/s",
+                              "note": "useful fp32-accurate FLOP/s per GPU of the WHOLE step (134.6 kFLOP per sample, SURVEY "
+                                      "8d); every contraction runs 3 tensor-core passes (tf32 / bf16 hi-lo split) to keep "
+                                      "fp32 accuracy, so the executed tensor FLOP/s are 3x this",
+                              "frac_of_fp32_fma_peak": None, "frac_of_bf16_tensor_peak_executed": None},
                  "loss": float(trainer.plan.flat[-1].item()), "kernels_per_step": 4 + 1 + 1}
 
     # ---------------- KNODE rollout training step (C3 ii, north-star extension): rollout + loss + BPTT + Adam ----------
@@ -379,6 +385,10 @@ def main():
                "sample": f"{nrods} rods x {t_sample - 1} solved steps of the same workload, oracle port of "
                          f"knode.simulate (numpy + scipy fsolve), one rod per host process, {cwall:.1f} s wall"}
 
+    if train is not None:
+        ach = train["roofline"]["achieved"] * 1e12
+        train["roofline"]["frac_of_fp32_fma_peak"] = ach / fp32_peak
+        train["roofline"]["frac_of_bf16_tensor_peak_executed"] = 3.0 * ach / (float(peaks.get("bf16_tflops_sustained", 1397.8)) * 1e12)
     if rank == 0:
         out = {
             "metric": "rod-node-steps/sec", "value": value, "unit": "rod-node-steps/s", "n_gpus": world,

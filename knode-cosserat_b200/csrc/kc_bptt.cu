@@ -39,9 +39,11 @@ kc_rollout_bwd_coop_kernel(const __grid_constant__ RodC<T> P, const MlpCoop<T> M
     if (b >= B) return;
     T* Hs = reinterpret_cast<T*>(kc_smem);
     const size_t per_rod = (size_t)(T_ - 1) * (N - 1) * 2;
-    bptt_rod<T, DIAG, IN, NH, 32>(P, M, traj + (size_t)b * T_ * 25 * N, gtraj + (size_t)b * T_ * 25 * N,
-                                  tensions + (size_t)b * T_ * 4, gten ? gten + (size_t)b * T_ * 4 : nullptr, T_, Hs,
-                                  xs + b * per_rod * IN, gos + b * per_rod * 25, fd_eps);
+    // lane stride 1: the warp holds ONE rod (every lane addresses the same element), so the per-rod arrays take 1/32 of
+    // the one-rod-per-lane footprint — 1.7 KB instead of 55 KB per warp, which used to cap the SM at 4 warps
+    bptt_rod<T, DIAG, IN, NH, 1>(P, M, traj + (size_t)b * T_ * 25 * N, gtraj + (size_t)b * T_ * 25 * N,
+                                 tensions + (size_t)b * T_ * 4, gten ? gten + (size_t)b * T_ * 4 : nullptr, T_, Hs,
+                                 xs + b * per_rod * IN, gos + b * per_rod * 25, fd_eps);
 }
 
 static inline size_t a256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -114,7 +116,7 @@ static int bwd_typed(const kc_rod_params* Pp, const kc_mlp* mlp, int64_t B, int6
     do {                                                                                                               \
         auto kern = kc_rollout_bwd_coop_kernel<T, D, I, H>;                                                            \
         if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
-        kern<<<(unsigned)B, 32, smem, st>>>(P, MC, B, (int)T_, (const T*)tensions, (const T*)traj, (const T*)gtraj,    \
+        kern<<<(unsigned)B, 32, smem / 32, st>>>(P, MC, B, (int)T_, (const T*)tensions, (const T*)traj, (const T*)gtraj,\
                                             (T*)gten, xs, gos, fd_eps);                                                \
     } while (0)
         if (P.diag) { if (in_dim == 28) KC_LAUNCH_BWDC(true, 28, 12); else KC_LAUNCH_BWDC(true, 53, 25); }
