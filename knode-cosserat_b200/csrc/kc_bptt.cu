@@ -28,19 +28,27 @@ kc_rollout_bwd_kernel(const __grid_constant__ RodC<T> P, const MlpC<T> M, int64_
 }
 
 // warp-cooperative variant: one rod per warp, the MLP (and its input VJP) split over the lanes (kc_mlp_coop.cuh)
+constexpr int KC_BCOOP_WARPS = 8;   // rods (warps) per CTA sharing one shared-memory copy of the MLP weights
 template <typename T, bool DIAG, int IN, int NH>
-__global__ void __launch_bounds__(32)
-kc_rollout_bwd_coop_kernel(const __grid_constant__ RodC<T> P, const MlpCoop<T> M, int64_t B, int T_,
+__global__ void __launch_bounds__(32 * KC_BCOOP_WARPS)
+kc_rollout_bwd_coop_kernel(const __grid_constant__ RodC<T> P, MlpCoop<T> M, int64_t B, int T_,
                            const T* __restrict__ tensions, const T* __restrict__ traj, const T* __restrict__ gtraj,
-                           T* __restrict__ gten, T* __restrict__ xs, T* __restrict__ gos, T fd_eps) {
+                           T* __restrict__ gten, T* __restrict__ xs, T* __restrict__ gos, T fd_eps, int wc_elems) {
     extern __shared__ __align__(16) unsigned char kc_smem[];
     const int N = P.N;
-    const int64_t b = blockIdx.x;
+    T* Wsm = reinterpret_cast<T*>(kc_smem);
+    if (wc_elems) {   // stage the packed weights once per CTA (see kc_rollout_coop_kernel)
+        for (int e = threadIdx.x; e < wc_elems; e += blockDim.x) Wsm[e] = M.Wc[e];
+        __syncthreads();
+        M.Wc = Wsm;
+    }
+    const int warp = threadIdx.x >> 5;
+    const int64_t b = (int64_t)blockIdx.x * KC_BCOOP_WARPS + warp;
     if (b >= B) return;
-    T* Hs = reinterpret_cast<T*>(kc_smem);
-    const size_t per_rod = (size_t)(T_ - 1) * (N - 1) * 2;
     // lane stride 1: the warp holds ONE rod (every lane addresses the same element), so the per-rod arrays take 1/32 of
-    // the one-rod-per-lane footprint — 1.7 KB instead of 55 KB per warp, which used to cap the SM at 4 warps
+    // the one-rod-per-lane footprint
+    T* Hs = Wsm + wc_elems + (size_t)warp * 4 * NH * (N - 1);
+    const size_t per_rod = (size_t)(T_ - 1) * (N - 1) * 2;
     bptt_rod<T, DIAG, IN, NH, 1>(P, M, traj + (size_t)b * T_ * 25 * N, gtraj + (size_t)b * T_ * 25 * N,
                                  tensions + (size_t)b * T_ * 4, gten ? gten + (size_t)b * T_ * 4 : nullptr, T_, Hs,
                                  xs + b * per_rod * IN, gos + b * per_rod * 25, fd_eps);
@@ -115,9 +123,14 @@ static int bwd_typed(const kc_rod_params* Pp, const kc_mlp* mlp, int64_t B, int6
 #define KC_LAUNCH_BWDC(D, I, H)                                                                                        \
     do {                                                                                                               \
         auto kern = kc_rollout_bwd_coop_kernel<T, D, I, H>;                                                            \
-        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
-        kern<<<(unsigned)B, 32, smem / 32, st>>>(P, MC, B, (int)T_, (const T*)tensions, (const T*)traj, (const T*)gtraj,\
-                                            (T*)gten, xs, gos, fd_eps);                                                \
+        const size_t state_b = (size_t)KC_BCOOP_WARPS * 4 * H * (N - 1) * sizeof(T);                                   \
+        const size_t wc_b = (size_t)(((in_dim + 3) & ~3) + 26) * MC.Hp * sizeof(T);                                    \
+        const int wc_elems = wc_b + state_b <= 200 * 1024 ? (int)(wc_b / sizeof(T)) : 0;                               \
+        const size_t csmem = state_b + (size_t)wc_elems * sizeof(T);                                                   \
+        if (csmem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem);    \
+        kern<<<(unsigned)((B + KC_BCOOP_WARPS - 1) / KC_BCOOP_WARPS), 32 * KC_BCOOP_WARPS, csmem, st>>>(               \
+            P, MC, B, (int)T_, (const T*)tensions, (const T*)traj, (const T*)gtraj, (T*)gten, xs, gos, fd_eps,         \
+            wc_elems);                                                                                                 \
     } while (0)
         if (P.diag) { if (in_dim == 28) KC_LAUNCH_BWDC(true, 28, 12); else KC_LAUNCH_BWDC(true, 53, 25); }
         else { if (in_dim == 28) KC_LAUNCH_BWDC(false, 28, 12); else KC_LAUNCH_BWDC(false, 53, 25); }

@@ -62,17 +62,28 @@ kc_rollout_kernel(const __grid_constant__ RodC<T> P, const MlpC<T> M, int64_t B,
 // KNODE rollout, warp-cooperative: ONE ROD PER WARP.  Every lane runs the same per-rod code on the same rod (physics
 // redundantly, shared-memory state at lane-independent addresses, identical stores), the MLP inside each node evaluation
 // is split over the lanes (kc_mlp_coop.cuh).  Chosen when the MLP is in the march and the batch is small.
+constexpr int KC_COOP_WARPS = 8;   // rods (warps) per CTA: they share one shared-memory copy of the MLP weights
 template <typename T, bool DIAG, int IN, int NH>
-__global__ void __launch_bounds__(32)
-kc_rollout_coop_kernel(const __grid_constant__ RodC<T> P, const MlpCoop<T> M, int64_t B, int T_,
+__global__ void __launch_bounds__(32 * KC_COOP_WARPS)
+kc_rollout_coop_kernel(const __grid_constant__ RodC<T> P, MlpCoop<T> M, int64_t B, int T_,
                        const T* __restrict__ tensions, const T* __restrict__ y0, const T* __restrict__ z0, T* trajD,
-                       T tol, int max_iter, T fd_eps, T* Gout, int32_t* iters) {
+                       T tol, int max_iter, T fd_eps, T* Gout, int32_t* iters, int wc_elems) {
     extern __shared__ __align__(16) unsigned char kc_smem[];
     const int N = P.N;
-    const int64_t b = blockIdx.x;
+    // the packed weights (110 KB at H = 512, fp32) are staged once per CTA when they fit (wc_elems != 0): every node
+    // evaluation of every march re-reads all of them, and from L1/L2 a quarter of those reads missed L1
+    T* Wsm = reinterpret_cast<T*>(kc_smem);
+    if (wc_elems) {
+        for (int e = threadIdx.x; e < wc_elems; e += blockDim.x) Wsm[e] = M.Wc[e];
+        __syncthreads();
+        M.Wc = Wsm;
+    }
+    const int warp = threadIdx.x >> 5;
+    const int64_t b = (int64_t)blockIdx.x * KC_COOP_WARPS + warp;
     if (b >= B) return;
-    T* Hs = reinterpret_cast<T*>(kc_smem);
-    const ShootMem<T, KC_LS> st{reinterpret_cast<T*>(kc_smem) + (size_t)NH * (N - 1) * KC_LS};
+    const int per_warp = NH * (N - 1) + KC_SHOOT_SLOTS;     // lane stride 1: the warp owns one rod
+    T* Hs = Wsm + wc_elems + (size_t)warp * per_warp;
+    const ShootMem<T, 1> st{Hs + (size_t)NH * (N - 1)};
     T* traj_b = rod_base(trajD, b, T_, N);
     st.reset();
     rollout_init<T, KC_LS>(P, y0 ? y0 + (size_t)b * 19 * N : nullptr, z0 ? z0 + (size_t)b * 6 * N : nullptr, traj_b);
@@ -82,9 +93,9 @@ kc_rollout_coop_kernel(const __grid_constant__ RodC<T> P, const MlpCoop<T> M, in
     }
     if (iters) iters[(size_t)b * T_] = 0;
     __syncwarp();
-    rollout_rod<T, DIAG, IN, NH, KC_LS>(P, M, st, tensions + (size_t)b * T_ * 4, traj_b, Hs, 0, T_ - 1, tol, max_iter,
-                                        fd_eps, Gout ? Gout + (size_t)b * T_ * 6 : nullptr,
-                                        iters ? iters + (size_t)b * T_ : nullptr);
+    rollout_rod<T, DIAG, IN, NH, KC_LS, 1>(P, M, st, tensions + (size_t)b * T_ * 4, traj_b, Hs, 0, T_ - 1, tol, max_iter,
+                                           fd_eps, Gout ? Gout + (size_t)b * T_ * 6 : nullptr,
+                                           iters ? iters + (size_t)b * T_ : nullptr);
 }
 
 // Wide mode: 4 rods per warp, 8 lanes per rod (see kc_rollout_wide.cuh).  Shared memory: history [N-1][NH][4].
@@ -628,9 +639,14 @@ static int rollout_typed(const kc_rod_params* Pp, const kc_mlp* mlp, int64_t B, 
 #define KC_LAUNCH_COOP(D, I, H)                                                                                        \
     do {                                                                                                               \
         auto kern = kc_rollout_coop_kernel<T, D, I, H>;                                                                \
-        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
-        kern<<<(unsigned)B, 32, smem, st>>>(P, MC, B, (int)T_, (const T*)tensions, (const T*)y0, (const T*)z0, trajD,  \
-                                            tl, max_iter, fd_eps, (T*)G_out, iters);                                   \
+        const size_t state_b = (size_t)KC_COOP_WARPS * (H * (N - 1) + KC_SHOOT_SLOTS) * sizeof(T);                     \
+        const size_t wc_b = (size_t)(inP + 26) * MC.Hp * sizeof(T);                                                    \
+        const int wc_elems = wc_b + state_b <= 200 * 1024 ? (int)(wc_b / sizeof(T)) : 0;                               \
+        const size_t csmem = state_b + (size_t)wc_elems * sizeof(T);                                                   \
+        if (csmem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem);    \
+        kern<<<(unsigned)((B + KC_COOP_WARPS - 1) / KC_COOP_WARPS), 32 * KC_COOP_WARPS, csmem, st>>>(                  \
+            P, MC, B, (int)T_, (const T*)tensions, (const T*)y0, (const T*)z0, trajD, tl, max_iter, fd_eps,            \
+            (T*)G_out, iters, wc_elems);                                                                               \
     } while (0)
         if (P.diag) { if (in_dim == 28) KC_LAUNCH_COOP(true, 28, 12); else KC_LAUNCH_COOP(true, 53, 25); }
         else { if (in_dim == 28) KC_LAUNCH_COOP(false, 28, 12); else KC_LAUNCH_COOP(false, 53, 25); }

@@ -35,15 +35,17 @@ template <typename T, int LS> struct TrajSink {
 };
 
 // History for the next step from the two most recent states: H = c1*state[t] + c2*state[t-1] (knode.py:74-75).
-template <typename T, int NH, int LS>
+// LS = element stride of the trajectory, LSM = element stride of the history (they differ in the warp-cooperative kernels,
+// where a warp owns ONE rod: device-layout trajectory, lane stride 32, but private per-warp scratch, stride 1)
+template <typename T, int NH, int LS, int LSM = LS>
 KC_HD void build_history(const RodC<T>& P, const T* cur, const T* prev, T* Hs) {
     const int Nm1 = P.N - 1;
     for (int j = 0; j < Nm1; ++j) {
         const T* cn = cur + (size_t)j * 25 * LS;
         const T* pn = prev + (size_t)j * 25 * LS;
-        T* hn = Hs + (size_t)j * NH * LS;
+        T* hn = Hs + (size_t)j * NH * LSM;
 #pragma unroll
-        for (int s = 0; s < NH; ++s) hn[s * LS] = P.c1 * cn[slot_row<NH>(s) * LS] + P.c2 * pn[slot_row<NH>(s) * LS];
+        for (int s = 0; s < NH; ++s) hn[s * LSM] = P.c1 * cn[slot_row<NH>(s) * LS] + P.c2 * pn[slot_row<NH>(s) * LS];
     }
 }
 
@@ -51,14 +53,14 @@ KC_HD void build_history(const RodC<T>& P, const T* cur, const T* prev, T* Hs) {
 //   ten      : this rod's tensions, ten[t*4 + i]
 //   traj_b   : this rod's base in trajD (element t=0, node 0, row 0); time stride is N*25*LS
 //   Gout/iters: this rod's [T][6] / [T] output rows (reference layout) or nullptr
-template <typename T, bool DIAG, int IN, int NH, int LS, typename MLP>
-KC_HD void rollout_rod(const RodC<T>& P, const MLP& M, const ShootMem<T, LS>& st, const T* __restrict__ ten,
+template <typename T, bool DIAG, int IN, int NH, int LS, int LSM = LS, typename MLP>
+KC_HD void rollout_rod(const RodC<T>& P, const MLP& M, const ShootMem<T, LSM>& st, const T* __restrict__ ten,
                        T* traj_b, T* Hs, int t_begin, int t_end, T tol, int max_iter, T fd_eps, T* Gout,
                        int32_t* iters) {
     const int N = P.N;
     const size_t tstride = (size_t)25 * N * LS;
     // (re)build the history of step t_begin from states t_begin and t_begin-1 (state[-1] := state[0], knode.py:65-66)
-    build_history<T, NH, LS>(P, traj_b + (size_t)t_begin * tstride,
+    build_history<T, NH, LS, LSM>(P, traj_b + (size_t)t_begin * tstride,
                              traj_b + (size_t)(t_begin > 0 ? t_begin - 1 : 0) * tstride, Hs);
     for (int t = t_begin; t < t_end; ++t) {
         T tn[4], tf[3];
@@ -67,9 +69,9 @@ KC_HD void rollout_rod(const RodC<T>& P, const MLP& M, const ShootMem<T, LS>& st
         tendon_force(P, tn, tf);
         T* cur = traj_b + (size_t)t * tstride;
         T* nxt = cur + tstride;
-        HistView<T, NH, LS> H{Hs};
+        HistView<T, NH, LSM> H{Hs};
         TrajSink<T, LS> S{nxt};
-        const int it = shoot_step<T, DIAG, IN, NH, LS>(P, M, st, tf, H, S, tol, max_iter, fd_eps);
+        const int it = shoot_step<T, DIAG, IN, NH, LSM>(P, M, st, tf, H, S, tol, max_iter, fd_eps);
         // z[:, N-1] is never written by the march: it keeps its previous value (cosserat_ode.py:198-201)
         {
             const size_t o = (size_t)(N - 1) * 25 * LS;
@@ -81,7 +83,7 @@ KC_HD void rollout_rod(const RodC<T>& P, const MLP& M, const ShootMem<T, LS>& st
             for (int i = 0; i < 6; ++i) Gout[(size_t)(t + 1) * 6 + i] = st.G(i);
         }
         if (iters) iters[t + 1] = it;
-        build_history<T, NH, LS>(P, nxt, cur, Hs);
+        build_history<T, NH, LS, LSM>(P, nxt, cur, Hs);
     }
 }
 
