@@ -216,3 +216,24 @@ def test_rollout_full_size_properties(ops, mode):
     sel = [0, 5, B // 2 - 1, B // 2, B - 3]
     want = O.rollout_newton(P, ctl[sel], rows=25)
     assert field_err(tr[sel].astype(np.float64), want) < 1e-4
+
+
+@pytest.mark.parametrize("dt", [torch.float64, torch.float32])
+@pytest.mark.parametrize("N,B", [(20, 40), (7, 19), (13, 33)])
+def test_rollout_other_node_counts(ops, mode, dt, N, B):
+    """BASELINE config 5 at reduced size: 2x the default node count (and two odd counts) — the kernels take N at run time;
+    N != 10 leaves the N = 10 specialisation of the wide kernel and, beyond 10 nodes, its shared-memory budget."""
+    P = O.RodParams()
+    P.N = N
+    setup = O.setup_params(P)          # robot of knode.setup_robot with N nodes (ds = L / (N - 1))
+    T = 16
+    rng = np.random.default_rng(N)
+    ctl = np.stack([np.array(O.calc_controls("sine", 0.6 + 0.05 * b, setup.del_t, T)) if b % 3 else
+                    5 + 5 * rng.random((T, 4)) for b in range(B)])
+    want = O.rollout_newton(setup, ctl, rows=50)
+    traj, G, iters = ops.rollout(params(setup), None, dev(ctl, dt), rows=50, want_G=True)
+    assert int(iters.min()) >= 0
+    got = traj.cpu().numpy().astype(np.float64)
+    assert got.shape == (B, T, 50, N)
+    assert field_err(got[:, :, :25], want[:, :, :25]) < TOL[dt]
+    assert field_err(got[:, :, 25:], want[:, :, 25:]) < TOL[dt] * 10     # yh, zh = c1*x[t-1] + c2*x[t-2]: cancellation
