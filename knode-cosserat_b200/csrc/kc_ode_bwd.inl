@@ -161,7 +161,7 @@ static int ode_bwd_typed(const kc_rod_params* Pp, const kc_mlp* mlp, int64_t Q, 
             }
             KC_CHECK_LAUNCH("kc_train_bwd_kernel");
         }
-        kc_train_reduce_kernel<T><<<(unsigned)((w.t.NP + 255) / 256), 256, 0, st>>>(part, Q > 0 ? w.t.splits : 0, w.t.NP, mlp->hidden, in_dim,
+        kc_train_reduce_kernel<T><<<(unsigned)((w.t.NP + 63) / 64), 256, 0, st>>>(part, Q > 0 ? w.t.splits : 0, w.t.NP, mlp->hidden, in_dim,
                                                                                   (T*)gW1, (T*)gb1, (T*)gW2, (T*)gb2, nullptr, 0, nullptr);
         KC_CHECK_LAUNCH("kc_train_reduce_kernel");
     }
@@ -298,7 +298,7 @@ static int mlp_bwd_typed(const kc_mlp* mlp, int64_t Q, const void* x, const void
             }
             KC_CHECK_LAUNCH("kc_train_bwd_kernel");
         }
-        kc_train_reduce_kernel<T><<<(unsigned)((w.t.NP + 255) / 256), 256, 0, st>>>(part, Q > 0 ? w.t.splits : 0, w.t.NP, mlp->hidden, in_dim,
+        kc_train_reduce_kernel<T><<<(unsigned)((w.t.NP + 63) / 64), 256, 0, st>>>(part, Q > 0 ? w.t.splits : 0, w.t.NP, mlp->hidden, in_dim,
                                                                                   (T*)gW1, (T*)gb1, (T*)gW2, (T*)gb2, nullptr, 0, nullptr);
         KC_CHECK_LAUNCH("kc_train_reduce_kernel");
     }

@@ -34,34 +34,20 @@ static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 // ---------------------------------------------------------------------------------------------------------------
 // 1. prep
 // ---------------------------------------------------------------------------------------------------------------
+// One (b, t, key) sample: ODE at node kn-1 of the NEXT ground-truth state -> x[XPG], phys[25], tgt[25] (unit stride).
+// nxt / cur / prv: the [25][N] states t+1, t, t-1 of the trajectory (global or shared memory).
 template <typename T, bool DIAG, int IN>
-__global__ void __launch_bounds__(128)
-kc_train_prep_kernel(const __grid_constant__ RodC<T> P, const __grid_constant__ KeyIdx64 key, int64_t B, int T_, int K,
-                     const T* __restrict__ traj, const T* __restrict__ controls, T* __restrict__ X, int XP,
-                     T* __restrict__ PHYS, T* __restrict__ TGT) {
-    const int64_t Q = B * (int64_t)(T_ - 1) * K;
-    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= Q) return;
-    const int N = P.N;
-    const int kk = (int)(q % K);
-    const int64_t bt = q / K;
-    const int t = (int)(bt % (T_ - 1));
-    const int64_t b = bt / (T_ - 1);
-    const int kn = key.k[kk];  // key node (loss is taken there); the ODE runs at node kn-1
-    const int j = kn - 1;
-    const T* nxt = traj + ((size_t)(b * T_ + t + 1) * 25) * N;
-    const T* cur = traj + ((size_t)(b * T_ + t) * 25) * N;
-    const T* prv = traj + ((size_t)(b * T_ + (t > 0 ? t - 1 : 0)) * 25) * N;
+KC_D void prep_sample(const RodC<T>& P, int kn, const T* nxt, const T* cur, const T* prv, const T* tn4, T* x, T* ph, T* tg) {
+    const int N = P.N, j = kn - 1;
     T y[19], hist[25], tn[4], tf[3], ys[19], z[6];
 #pragma unroll
     for (int r = 0; r < 19; ++r) y[r] = nxt[r * N + j];
 #pragma unroll
     for (int r = 0; r < 25; ++r) hist[r] = P.c1 * cur[r * N + j] + P.c2 * prv[r * N + j];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) tn[i] = controls[(size_t)(b * T_ + t) * 4 + i];
+    for (int i = 0; i < 4; ++i) tn[i] = tn4[i];
     tendon_force(P, tn, tf);
     rod_ode<T, DIAG>(P, y, hist + 13, hist + 16, hist + 19, hist + 22, tf, ys, z);
-    T* x = X + (size_t)q * XP;
     if (IN == 28) {
 #pragma unroll
         for (int i = 0; i < 19; ++i) x[i] = y[i];
@@ -81,12 +67,71 @@ kc_train_prep_kernel(const __grid_constant__ RodC<T> P, const __grid_constant__ 
 #pragma unroll
         for (int i = 53; i < 56; ++i) x[i] = T(0);
     }
-    T* ph = PHYS + (size_t)q * 25;
-    T* tg = TGT + (size_t)q * 25;
 #pragma unroll
     for (int r = 0; r < 19; ++r) { ph[r] = y[r] + P.ds * ys[r]; tg[r] = nxt[r * N + kn]; }
 #pragma unroll
     for (int c = 0; c < 6; ++c) { ph[19 + c] = z[c]; tg[19 + c] = nxt[(19 + c) * N + kn - 1]; }
+}
+
+// thread per sample, straight from global memory (any T): the fallback when a trajectory does not fit shared memory
+template <typename T, bool DIAG, int IN>
+__global__ void __launch_bounds__(128)
+kc_train_prep_kernel(const __grid_constant__ RodC<T> P, const __grid_constant__ KeyIdx64 key, int64_t B, int T_, int K,
+                     const T* __restrict__ traj, const T* __restrict__ controls, T* __restrict__ X, int XP,
+                     T* __restrict__ PHYS, T* __restrict__ TGT) {
+    const int64_t Q = B * (int64_t)(T_ - 1) * K;
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= Q) return;
+    const int N = P.N;
+    const int kk = (int)(q % K);
+    const int64_t bt = q / K;
+    const int t = (int)(bt % (T_ - 1));
+    const int64_t b = bt / (T_ - 1);
+    prep_sample<T, DIAG, IN>(P, key.k[kk], traj + ((size_t)(b * T_ + t + 1) * 25) * N, traj + ((size_t)(b * T_ + t) * 25) * N,
+                             traj + ((size_t)(b * T_ + (t > 0 ? t - 1 : 0)) * 25) * N, controls + (size_t)(b * T_ + t) * 4,
+                             X + (size_t)q * XP, PHYS + (size_t)q * 25, TGT + (size_t)q * 25);
+}
+
+// One CTA per trajectory: the whole [T][25][N] block is loaded once, coalesced, into shared memory (every state is used
+// by three consecutive steps and the per-sample accesses are column gathers), the samples are computed from there,
+// staged in shared memory and written out as contiguous runs.  (56 -> ~25 us at C3; the thread-per-sample kernel moves
+// 4-byte elements at a 40-byte stride in both directions.)
+constexpr int PREP_ROW = 56 + 50;   // staging row: x (<= 56) | phys 25 | tgt 25
+template <typename T, bool DIAG, int IN>
+__global__ void __launch_bounds__(128)
+kc_train_prep_traj_kernel(const __grid_constant__ RodC<T> P, const __grid_constant__ KeyIdx64 key, int64_t B, int T_, int K,
+                          const T* __restrict__ traj, const T* __restrict__ controls, T* __restrict__ X,
+                          T* __restrict__ PHYS, T* __restrict__ TGT) {
+    constexpr int XPG = IN == 28 ? 32 : 56;
+    extern __shared__ __align__(16) unsigned char kc_smem[];
+    T* s_traj = reinterpret_cast<T*>(kc_smem);
+    const int N = P.N, slab = 25 * N, total = T_ * slab;
+    T* s_out = s_traj + total;                      // [128][PREP_ROW]
+    const int64_t b = blockIdx.x;
+    const int tid = threadIdx.x;
+    const T* src = traj + (size_t)b * total;
+    for (int e = tid; e < total; e += 128) s_traj[e] = src[e];
+    __syncthreads();
+    const int S = (T_ - 1) * K;
+    for (int s0 = 0; s0 < S; s0 += 128) {
+        const int s = s0 + tid, n = S - s0 < 128 ? S - s0 : 128;
+        if (s < S) {
+            const int t = s / K, kk = s - t * K;
+            T* row = s_out + (size_t)tid * PREP_ROW;
+            prep_sample<T, DIAG, IN>(P, key.k[kk], s_traj + (size_t)(t + 1) * slab, s_traj + (size_t)t * slab,
+                                     s_traj + (size_t)(t > 0 ? t - 1 : 0) * slab, controls + (size_t)(b * T_ + t) * 4,
+                                     row, row + 56, row + 81);
+        }
+        __syncthreads();
+        const size_t q0 = (size_t)b * S + s0;
+        for (int e = tid; e < n * XPG; e += 128) X[q0 * XPG + e] = s_out[(size_t)(e / XPG) * PREP_ROW + (e % XPG)];
+        for (int e = tid; e < n * 25; e += 128) {
+            const int r = e / 25, c = e - r * 25;
+            PHYS[q0 * 25 + e] = s_out[(size_t)r * PREP_ROW + 56 + c];
+            TGT[q0 * 25 + e] = s_out[(size_t)r * PREP_ROW + 81 + c];
+        }
+        __syncthreads();
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -276,14 +321,31 @@ kc_train_bwd_kernel(int hidden, const T* __restrict__ W1, const T* __restrict__ 
     if (blockIdx.x == 0 && tid >= 32 && tid < 32 + 25) out[ob2 + tid - 32] = ab2;
 }
 
+// 256 threads = 4 slice groups x 64 outputs: group g sums slices g, g+4, ... with four independent accumulators (the
+// loads overlap instead of forming one 148-long dependent chain), the four group sums are combined in a fixed order.
 template <typename T>
-__global__ void kc_train_reduce_kernel(const T* __restrict__ partial, int splits, int64_t NP, int hidden, int in_dim,
-                                       T* gW1, T* gb1, T* gW2, T* gb2, const double* __restrict__ loss_part,
-                                       int nloss, double* loss) {
-    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256)
+kc_train_reduce_kernel(const T* __restrict__ partial, int splits, int64_t NP, int hidden, int in_dim,
+                       T* gW1, T* gb1, T* gW2, T* gb2, const double* __restrict__ loss_part,
+                       int nloss, double* loss) {
+    __shared__ T red[4][64];
+    const int g = threadIdx.x >> 6, pl = threadIdx.x & 63;
+    const int64_t p = (int64_t)blockIdx.x * 64 + pl;
+    T a0 = T(0), a1 = T(0), a2 = T(0), a3 = T(0);
     if (p < NP) {
-        T s = T(0);
-        for (int k = 0; k < splits; ++k) s += partial[(size_t)k * NP + p];
+        int k = g;
+        for (; k + 12 < splits; k += 16) {
+            a0 += partial[(size_t)k * NP + p];
+            a1 += partial[(size_t)(k + 4) * NP + p];
+            a2 += partial[(size_t)(k + 8) * NP + p];
+            a3 += partial[(size_t)(k + 12) * NP + p];
+        }
+        for (; k < splits; k += 4) a0 += partial[(size_t)k * NP + p];
+    }
+    red[g][pl] = (a0 + a1) + (a2 + a3);
+    __syncthreads();
+    if (g == 0 && p < NP) {
+        const T s = (red[0][pl] + red[1][pl]) + (red[2][pl] + red[3][pl]);
         const int64_t ob1 = (int64_t)hidden * in_dim, oW2 = ob1 + hidden, ob2 = oW2 + (int64_t)25 * hidden;
         if (p < ob1) { if (gW1) gW1[p] = s; }
         else if (p < oW2) { if (gb1) gb1[p - ob1] = s; }
@@ -360,14 +422,24 @@ static int train_typed(const kc_rod_params* Pp, const kc_mlp* mlp, int64_t B, in
     unsigned char* ws = (unsigned char*)workspace;
     T* X = (T*)(ws + w.X); T* PHYS = (T*)(ws + w.PHYS); T* TGT = (T*)(ws + w.TGT); T* dO = (T*)(ws + w.dO);
     double* lossp = (double*)(ws + w.lossp); T* part = (T*)(ws + w.part);
-    MlpC<T> M;
-    int rc = kc_pack_mlp<T>(mlp, (T*)(ws + w.wp), M, st);
-    if (rc) return rc;
+    MlpC<T> M{};
     const int in_dim = mlp->in_dim;
     int tc_slices = 0;
     if (Q > 0) {
         const unsigned g1 = (unsigned)((Q + 127) / 128);
-#define PREP(D, I) kc_train_prep_kernel<T, D, I><<<g1, 128, 0, st>>>(P, key, B, (int)T_, K, (const T*)traj, (const T*)controls, X, w.XPG, PHYS, TGT)
+        const size_t psmem = ((size_t)T_ * 25 * P.N + (size_t)128 * PREP_ROW) * sizeof(T);
+        const bool per_traj = psmem <= 100 * 1024;   // >= 2 CTAs per SM
+#define PREP(D, I)                                                                                                     \
+    do {                                                                                                               \
+        if (per_traj) {                                                                                                \
+            auto pk = kc_train_prep_traj_kernel<T, D, I>;                                                              \
+            if (psmem > 48 * 1024) cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem);  \
+            pk<<<(unsigned)B, 128, psmem, st>>>(P, key, B, (int)T_, K, (const T*)traj, (const T*)controls, X, PHYS, TGT); \
+        } else {                                                                                                       \
+            kc_train_prep_kernel<T, D, I><<<g1, 128, 0, st>>>(P, key, B, (int)T_, K, (const T*)traj,                   \
+                                                              (const T*)controls, X, w.XPG, PHYS, TGT);                \
+        }                                                                                                              \
+    } while (0)
         if (P.diag) { if (in_dim == 28) PREP(true, 28); else PREP(true, 53); }
         else { if (in_dim == 28) PREP(false, 28); else PREP(false, 53); }
 #undef PREP
@@ -386,6 +458,8 @@ static int train_typed(const kc_rod_params* Pp, const kc_mlp* mlp, int64_t B, in
             if (rc2) return rc2;
         } else {
         {
+            int rc = kc_pack_mlp<T>(mlp, (T*)(ws + w.wp), M, st);   // SIMT weight image (the tensor-core path has its own)
+            if (rc) return rc;
             const size_t wbytes = (size_t)M.hidden * M.stride * sizeof(T);
             const int in_smem = wbytes <= 200 * 1024 ? 1 : 0;
             const size_t fsmem = in_smem ? wbytes : 0;
@@ -415,7 +489,7 @@ static int train_typed(const kc_rod_params* Pp, const kc_mlp* mlp, int64_t B, in
         }
     }
     const int splits = Q > 0 ? (tc_slices > 0 ? tc_slices : w.splits) : 0;
-    kc_train_reduce_kernel<T><<<(unsigned)((w.NP + 255) / 256), 256, 0, st>>>(part, splits, w.NP, mlp->hidden, in_dim, (T*)gW1, (T*)gb1,
+    kc_train_reduce_kernel<T><<<(unsigned)((w.NP + 63) / 64), 256, 0, st>>>(part, splits, w.NP, mlp->hidden, in_dim, (T*)gW1, (T*)gb1,
                                                                             (T*)gW2, (T*)gb2, lossp, Q > 0 ? (tc_slices > 0 ? tc_slices : w.nfwd) : 0, loss);
     KC_CHECK_LAUNCH("kc_train_reduce_kernel");
     return KC_OK;

@@ -73,8 +73,8 @@ __device__ __forceinline__ uint32_t kmajor_off_b16(int r, int k, int KT) {
 __global__ void kc_tc_prep_weights_kernel(const float* __restrict__ W1, const float* __restrict__ b1,
                                           const float* __restrict__ W2, int hidden, float* __restrict__ W1hl,
                                           unsigned char* __restrict__ W2b) {
-    const int c = blockIdx.x;
-    for (int e = threadIdx.x; e < 128 * 32; e += blockDim.x) {
+    const int c = blockIdx.x;   // grid = (chunks, 8): 8 CTAs share a chunk
+    for (int e = blockIdx.y * blockDim.x + threadIdx.x; e < 128 * 32; e += gridDim.y * blockDim.x) {
         const int ul = e >> 5, k = e & 31, u = c * 128 + ul;
         float v = 0.f;
         if (u < hidden) v = k < 28 ? W1[(size_t)u * 28 + k] : (k == 28 ? b1[u] : 0.f);
@@ -493,7 +493,7 @@ int kc_train_tc_launch(const kc_mlp* mlp, float ds, int64_t Q, int T_, int K, co
                        float* pred_out, int grid, cudaStream_t st) {
     const int nch = (mlp->hidden + tc::HC - 1) / tc::HC;
     unsigned char* W2b = reinterpret_cast<unsigned char*>(W2c_);
-    kc_tc_prep_weights_kernel<<<nch, 256, 0, st>>>((const float*)mlp->W1, (const float*)mlp->b1, (const float*)mlp->W2,
+    kc_tc_prep_weights_kernel<<<dim3(nch, 8), 256, 0, st>>>((const float*)mlp->W1, (const float*)mlp->b1, (const float*)mlp->W2,
                                                   mlp->hidden, W1hl, W2b);
     KC_CHECK_LAUNCH("kc_tc_prep_weights_kernel");
     cudaFuncSetAttribute(kc_train_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
