@@ -90,7 +90,11 @@ extern "C" int kc_rollout_host(int dtype, const kc_rod_params* P, const kc_mlp* 
     cudaEvent_t ev[8] = {};
     int rc = KC_OK;
     for (int s = 0; s < nseg && rc == KC_OK; ++s) {
-        const int64_t t0 = (T_ - 1) * s / nseg, t1 = (T_ - 1) * (s + 1) / nseg;   // steps [t0, t1)
+        // steps [t0, t1): the copy engine is ~6x slower than the solve, so only the FIRST range's solve is exposed — it is
+        // kept short (a quarter of an even share); the other ranges share the rest evenly
+        const int64_t first = nseg > 1 ? ((T_ - 1) / (4 * nseg) > 0 ? (T_ - 1) / (4 * nseg) : 1) : T_ - 1;
+        const int64_t t0 = s == 0 ? 0 : first + (T_ - 1 - first) * (s - 1) / (nseg - 1);
+        const int64_t t1 = s == 0 ? first : first + (T_ - 1 - first) * s / (nseg - 1);
         rc = kc_rollout_fwd_range(dtype, P, mlp, B, T_, tens_d, y0, z0, tol, max_iter, rows, traj_d, G_d, iters_d,
                                   d + h.ws, (int64_t)(h.total - h.ws), t0, t1, stream);
         if (rc != KC_OK) break;
