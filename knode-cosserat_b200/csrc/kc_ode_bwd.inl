@@ -104,6 +104,29 @@ kc_ode_bwd_kernel(const __grid_constant__ RodC<T> P, const MlpC<T> M, int64_t Q,
     }
 }
 
+// Parameter gradients from (X[Q][32], dO[Q][32]) samples on the tensor cores (kc_train_tc_kernel<2>) when the shape is the
+// reference's (fp32, 28 inputs, hidden <= 512) and there are enough samples to fill the chip; returns false to fall back
+// to the SIMT kernel.  slices = number of partial-gradient slices written (< 0: launch error).
+int kc_tc_launch_mode(int mode, const kc_mlp* mlp, float ds, int64_t Q, int T_, int K, const float* X, const float* PHYS,
+                      const float* TGT, float* W1hl, float* W2c_, float* partial, int64_t NP, double* loss_part,
+                      float* pred_out, const float* dOin, int grid, cudaStream_t st);
+template <typename T>
+static bool kc_param_grads_tc(const kc_mlp*, int64_t, const T*, const T*, T*, const TrainWs&, unsigned char*, cudaStream_t,
+                              int&) { return false; }
+template <>
+bool kc_param_grads_tc<float>(const kc_mlp* mlp, int64_t Q, const float* X, const float* dO, float* part, const TrainWs& t,
+                              unsigned char* ws, cudaStream_t st, int& slices) {
+    if (mlp->in_dim != 28 || mlp->hidden > 512 || Q < 4096) return false;
+    const char* e = getenv("KC_TRAIN_MODE");
+    if (e && e[0] == 's') return false;
+    float* tcw = (float*)(ws + t.tcw);
+    slices = kc_train_tc_grid(Q);
+    const int rc = kc_tc_launch_mode(2, mlp, 1.f, Q, 2, 1, X, nullptr, nullptr, tcw, tcw + 4 * 2 * 128 * 32, part, t.NP,
+                                     (double*)(ws + t.lossp), nullptr, dO, slices, st);
+    if (rc) slices = -1;
+    return true;
+}
+
 struct OdeBwdWs { size_t X, dO, part, wp, total; TrainWs t; };
 static OdeBwdWs ode_bwd_ws(int dtype, const kc_mlp* mlp, int64_t Q) {
     OdeBwdWs w{};
@@ -147,7 +170,10 @@ static int ode_bwd_typed(const kc_rod_params* Pp, const kc_mlp* mlp, int64_t Q, 
     }
     if (want_params) {
         T* part = (T*)(ws + w.part);
-        if (Q > 0) {
+        int tc_slices = 0;
+        if (Q > 0 && kc_param_grads_tc<T>(mlp, Q, X, dO, part, w.t, ws, st, tc_slices)) {
+            if (tc_slices < 0) return KC_ECUDA;
+        } else if (Q > 0) {
             const size_t smem = bwd_smem_bytes(in_dim, sizeof(T));
             dim3 grid((unsigned)w.t.chunks, (unsigned)w.t.splits);
             if (in_dim == 28) {
@@ -161,7 +187,7 @@ static int ode_bwd_typed(const kc_rod_params* Pp, const kc_mlp* mlp, int64_t Q, 
             }
             KC_CHECK_LAUNCH("kc_train_bwd_kernel");
         }
-        kc_train_reduce_kernel<T><<<(unsigned)((w.t.NP + 63) / 64), 256, 0, st>>>(part, Q > 0 ? w.t.splits : 0, w.t.NP, mlp->hidden, in_dim,
+        kc_train_reduce_kernel<T><<<(unsigned)((w.t.NP + 63) / 64), 256, 0, st>>>(part, Q > 0 ? (tc_slices > 0 ? tc_slices : w.t.splits) : 0, w.t.NP, mlp->hidden, in_dim,
                                                                                   (T*)gW1, (T*)gb1, (T*)gW2, (T*)gb2, nullptr, 0, nullptr);
         KC_CHECK_LAUNCH("kc_train_reduce_kernel");
     }
@@ -284,7 +310,10 @@ static int mlp_bwd_typed(const kc_mlp* mlp, int64_t Q, const void* x, const void
     }
     if (want_params) {
         T* part = (T*)(ws + w.part);
-        if (Q > 0) {
+        int tc_slices = 0;
+        if (Q > 0 && kc_param_grads_tc<T>(mlp, Q, X, dO, part, w.t, ws, st, tc_slices)) {
+            if (tc_slices < 0) return KC_ECUDA;
+        } else if (Q > 0) {
             const size_t smem = bwd_smem_bytes(in_dim, sizeof(T));
             dim3 grid((unsigned)w.t.chunks, (unsigned)w.t.splits);
             if (in_dim == 28) {
@@ -298,7 +327,7 @@ static int mlp_bwd_typed(const kc_mlp* mlp, int64_t Q, const void* x, const void
             }
             KC_CHECK_LAUNCH("kc_train_bwd_kernel");
         }
-        kc_train_reduce_kernel<T><<<(unsigned)((w.t.NP + 63) / 64), 256, 0, st>>>(part, Q > 0 ? w.t.splits : 0, w.t.NP, mlp->hidden, in_dim,
+        kc_train_reduce_kernel<T><<<(unsigned)((w.t.NP + 63) / 64), 256, 0, st>>>(part, Q > 0 ? (tc_slices > 0 ? tc_slices : w.t.splits) : 0, w.t.NP, mlp->hidden, in_dim,
                                                                                   (T*)gW1, (T*)gb1, (T*)gW2, (T*)gb2, nullptr, 0, nullptr);
         KC_CHECK_LAUNCH("kc_train_reduce_kernel");
     }

@@ -97,11 +97,16 @@ __global__ void kc_tc_prep_weights_kernel(const float* __restrict__ W1, const fl
     }
 }
 
+// MODE 0: the full training step.  MODE 1: forward only — pred_out[Q][25] = PHYS + s*o (s = ds for rows < 19, 1 for the
+// rest; kc_ode_fwd / kc_mlp_fwd pass ds = 1 and PHYS = the physics part or zeros).  MODE 2: parameter gradients only from
+// given samples (X, dOin[Q][32]) — kc_mlp_bwd / kc_ode_bwd and the sample reduction of kc_rollout_bwd.
+template <int MODE>
 __global__ void __launch_bounds__(tc::THREADS, 1)
 kc_train_tc_kernel(int hidden, int nch, const float* __restrict__ W1hl, const unsigned char* __restrict__ W2b,
                    const float* __restrict__ b2, float ds, int64_t Q, int T_, int K, const float* __restrict__ X,
                    const float* __restrict__ PHYS, const float* __restrict__ TGT, float* __restrict__ partial,
-                   int64_t NP, double* __restrict__ loss_part, float* __restrict__ pred_out) {
+                   int64_t NP, double* __restrict__ loss_part, float* __restrict__ pred_out,
+                   const float* __restrict__ dOin) {
     extern __shared__ __align__(1024) unsigned char sm[];
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + tc::OFF_MISC);
     uint64_t* barZ = reinterpret_cast<uint64_t*>(sm + tc::OFF_MISC + 8);
@@ -227,10 +232,11 @@ kc_train_tc_kernel(int hidden, int nch, const float* __restrict__ W1hl, const un
     double lossacc = 0.0;
     const int64_t ntiles = (Q + tc::TS - 1) / tc::TS;
     bool first_tile = true;
+    int gs = 0;   // running stage count: the W2 image buffers alternate by it (any number of stages per tile)
     if (tid == 0 && blockIdx.x < ntiles) {   // stage 0 of the first tile
         mbar_expect_tx(barW, 32768 + 16384);
         fetch_w1(0);
-        fetch_w2(0, 1, 0);
+        fetch_w2(0, MODE == 2 ? 2 : 1, 0);
     }
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t q = tile * tc::TS + row;
@@ -244,7 +250,10 @@ kc_train_tc_kernel(int hidden, int nch, const float* __restrict__ W1hl, const un
                 float4 t = valid ? xs[g] : make_float4(0.f, 0.f, 0.f, 0.f);
                 xv[4 * g] = t.x; xv[4 * g + 1] = t.y; xv[4 * g + 2] = t.z; xv[4 * g + 3] = t.w;
             }
-            if (half == 1) xv[12] = valid ? 1.f : 0.f;  // column 28: carries b1 in GEMM1 and yields gb1 in the gW1 GEMM
+            if (half == 1) {   // column 28: carries b1 in GEMM1 and yields gb1 in the gW1 GEMM; 29..31: padding (must be finite)
+                xv[12] = valid ? 1.f : 0.f;
+                xv[13] = 0.f; xv[14] = 0.f; xv[15] = 0.f;
+            }
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
                 float4 h, l;
@@ -268,21 +277,24 @@ kc_train_tc_kernel(int hidden, int nch, const float* __restrict__ W1hl, const un
                     make_uint4(pack_bf16x2(lo[0], lo[1]), pack_bf16x2(lo[2], lo[3]), pack_bf16x2(lo[4], lo[5]), pack_bf16x2(lo[6], lo[7]));
             }
         }
+        const bool more_tiles = tile + gridDim.x < ntiles;
         // ---- pass 1: forward ----
         umma::fence_async_smem();       // the X tile
         umma::fence_before();
         __syncthreads();
-        for (int c = 0; c < nch; ++c) {
-            const int stage = c;
+        if (MODE != 2) {
+        for (int c = 0; c < nch; ++c, ++gs) {
+            const int stage = gs;
             umma::mbar_wait(barW, phW); phW ^= 1;                     // W1(c), W2 fwd image(c) have landed
             if (tid == 0) { umma::fence_after(); issue_gemm1(); umma::commit(barZ); }
             if (c > 0) { umma::mbar_wait(barO, phO); phO ^= 1; }      // chunk c-1's O GEMM done: A tile and its W2 buffer free
             umma::mbar_wait(barZ, phZ); phZ ^= 1;
             umma::fence_after();
-            if (tid == 0) {   // next stage's weights: W1 region free (GEMM1 done), other W2 buffer free (see above)
+            if (tid == 0 && (MODE == 0 || c + 1 < nch || more_tiles)) {
+                // next stage's weights: W1 region free (GEMM1 done), other W2 buffer free (see above)
                 mbar_expect_tx(barW, 32768 + 16384);
                 if (c + 1 < nch) { fetch_w1(c + 1); fetch_w2(c + 1, 1, stage + 1); }
-                else             { fetch_w1(0);     fetch_w2(0, 2, stage + 1); }
+                else             { fetch_w1(0);     fetch_w2(0, MODE == 0 ? 2 : 1, stage + 1); }
             }
 #pragma unroll 1
             for (int cc = 0; cc < 2; ++cc) {
@@ -308,17 +320,28 @@ kc_train_tc_kernel(int hidden, int nch, const float* __restrict__ W1hl, const un
         }
         umma::mbar_wait(barO, phO); phO ^= 1;
         umma::fence_after();
+        }
         // ---- loss and dL/do (rows of half 0 own the sample) ----
         if (half == 0) {
             float o[25], g[25];
-            {
+            if (MODE != 2) {
                 uint32_t v[32];
                 umma::ld32(tbase + laneblk + tc::COL_O, v);
                 umma::wait_ld();
 #pragma unroll
                 for (int c = 0; c < 25; ++c) { o[c] = __uint_as_float(v[c]) + b2[c]; g[c] = 0.f; }
+            } else {
+#pragma unroll
+                for (int c = 0; c < 25; ++c) { o[c] = 0.f; g[c] = valid ? dOin[(size_t)q * 32 + c] : 0.f; }
             }
-            if (valid) {
+            if (MODE == 1) {
+                if (valid) {
+#pragma unroll
+                    for (int r = 0; r < 25; ++r)
+                        pred_out[(size_t)q * 25 + r] = PHYS[(size_t)q * 25 + r] + (r < 19 ? ds : 1.f) * o[r];
+                }
+            }
+            if (MODE == 0 && valid) {
                 float pred[25], tg[25];
 #pragma unroll
                 for (int r = 0; r < 19; ++r) pred[r] = PHYS[(size_t)q * 25 + r] + ds * o[r];
@@ -374,9 +397,9 @@ kc_train_tc_kernel(int hidden, int nch, const float* __restrict__ W1hl, const un
         umma::fence_before();
         __syncthreads();
         // ---- pass 2: backward ----
-        const bool more_tiles = tile + gridDim.x < ntiles;
-        for (int c = 0; c < nch; ++c) {
-            const int stage = nch + c;
+        if (MODE != 1) {
+        for (int c = 0; c < nch; ++c, ++gs) {
+            const int stage = gs;
             const uint32_t aWB = (stage & 1) ? aWB1 : aWB0;
             umma::mbar_wait(barW, phW); phW ^= 1;                     // W1(c), W2 bwd image(c) have landed
             if (tid == 0) { umma::fence_after(); issue_gemm1(); issue_gemm3(aWB); umma::commit(barZ); }
@@ -387,7 +410,7 @@ kc_train_tc_kernel(int hidden, int nch, const float* __restrict__ W1hl, const un
             if (tid == 0 && prefetch) {   // the other W2 buffer is free now; W1 follows once the dZ-lo MMAs of this chunk are done
                 mbar_expect_tx(barW, 32768 + 16384);
                 if (c + 1 < nch) fetch_w2(c + 1, 2, stage + 1);
-                else fetch_w2(0, 1, 0);
+                else fetch_w2(0, MODE == 2 ? 2 : 1, stage + 1);
             }
 #pragma unroll 1
             for (int cc = 0; cc < 2; ++cc) {
@@ -430,7 +453,14 @@ kc_train_tc_kernel(int hidden, int nch, const float* __restrict__ W1hl, const un
         }
         umma::mbar_wait(barG, phG); phG ^= 1;   // last chunk's gradient MMAs: they read X^T / dO^T which the next tile overwrites
         umma::fence_after();
+        }
         first_tile = false;
+    }
+    if (MODE == 1) {   // forward only: no gradients to write
+        umma::fence_before();
+        __syncthreads();
+        if (warp == 0) umma::tmem_dealloc(tbase, 512);
+        return;
     }
     // ---- write this CTA's partial gradients ----
     umma::fence_before();
@@ -480,6 +510,9 @@ kc_train_tc_kernel(int hidden, int nch, const float* __restrict__ W1hl, const un
 
 // Host side: called by kc_train_step (kc_train.cu) when the shape is eligible.  W1hl: nch*2*4096 floats, W2b: nch*32768
 // bytes (workspace), partial: grid*NP floats, loss_part: grid doubles.
+int kc_tc_launch_mode(int mode, const kc_mlp* mlp, float ds, int64_t Q, int T_, int K, const float* X, const float* PHYS,
+                      const float* TGT, float* W1hl, float* W2c_, float* partial, int64_t NP, double* loss_part,
+                      float* pred_out, const float* dOin, int grid, cudaStream_t st);
 int kc_train_tc_grid(int64_t Q) {
     const int64_t ntiles = (Q + tc::TS - 1) / tc::TS;
     int dev = 0, sms = 148;
@@ -491,14 +524,27 @@ int kc_train_tc_grid(int64_t Q) {
 int kc_train_tc_launch(const kc_mlp* mlp, float ds, int64_t Q, int T_, int K, const float* X, const float* PHYS,
                        const float* TGT, float* W1hl, float* W2c_, float* partial, int64_t NP, double* loss_part,
                        float* pred_out, int grid, cudaStream_t st) {
+    return kc_tc_launch_mode(0, mlp, ds, Q, T_, K, X, PHYS, TGT, W1hl, W2c_, partial, NP, loss_part, pred_out, nullptr,
+                             grid, st);
+}
+
+// mode 0: training step; 1: forward only (pred_out[Q][25] = PHYS + s*o); 2: parameter gradients from (X, dOin) samples
+int kc_tc_launch_mode(int mode, const kc_mlp* mlp, float ds, int64_t Q, int T_, int K, const float* X, const float* PHYS,
+                      const float* TGT, float* W1hl, float* W2c_, float* partial, int64_t NP, double* loss_part,
+                      float* pred_out, const float* dOin, int grid, cudaStream_t st) {
     const int nch = (mlp->hidden + tc::HC - 1) / tc::HC;
     unsigned char* W2b = reinterpret_cast<unsigned char*>(W2c_);
-    kc_tc_prep_weights_kernel<<<dim3(nch, 8), 256, 0, st>>>((const float*)mlp->W1, (const float*)mlp->b1, (const float*)mlp->W2,
-                                                  mlp->hidden, W1hl, W2b);
+    kc_tc_prep_weights_kernel<<<dim3(nch, 8), 256, 0, st>>>((const float*)mlp->W1, (const float*)mlp->b1,
+                                                          (const float*)mlp->W2, mlp->hidden, W1hl, W2b);
     KC_CHECK_LAUNCH("kc_tc_prep_weights_kernel");
-    cudaFuncSetAttribute(kc_train_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
-    kc_train_tc_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(mlp->hidden, nch, W1hl, W2b, (const float*)mlp->b2, ds, Q,
-                                                                  T_, K, X, PHYS, TGT, partial, NP, loss_part, pred_out);
+#define KC_TC_GO(M)                                                                                                    \
+    do {                                                                                                               \
+        cudaFuncSetAttribute(kc_train_tc_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);      \
+        kc_train_tc_kernel<M><<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(mlp->hidden, nch, W1hl, W2b,                  \
+            (const float*)mlp->b2, ds, Q, T_, K, X, PHYS, TGT, partial, NP, loss_part, pred_out, dOin);                \
+    } while (0)
+    if (mode == 0) KC_TC_GO(0); else if (mode == 1) KC_TC_GO(1); else KC_TC_GO(2);
+#undef KC_TC_GO
     KC_CHECK_LAUNCH("kc_train_tc_kernel");
     return KC_OK;
 }

@@ -224,3 +224,31 @@ def test_adam_clamp_multi_matches_single_tensor_kernels(ops):
         for a, b in zip(P1, P2):
             np.testing.assert_allclose(b.cpu().numpy(), a.cpu().numpy(), rtol=1e-12, atol=1e-14)
     assert int(multi.step_dev.item()) == 3 and int(multi.ticket.item()) == 0
+
+
+@pytest.mark.parametrize("H", [512, 200, 64])
+def test_param_grads_tensor_core_vs_simt_and_fp64(ops, monkeypatch, H):
+    """kc_mlp_bwd with enough samples takes the tcgen05 gradient kernel (kc_train_tc_kernel<2>); same numbers as the SIMT
+    kernel and as fp64 (3-pass bf16/tf32 splits keep fp32 accuracy).  H = 200: a partly filled last 128-unit chunk."""
+    rng = np.random.default_rng(H)
+    Q = 6000 + 37                                   # not a multiple of the 128-sample tile
+    W = [rng.normal(0, 0.3, (H, 28)), rng.normal(0, 0.1, H), rng.normal(0, 0.3, (25, H)), rng.normal(0, 0.1, 25)]
+    x = rng.normal(0, 1.0, (Q, 28))
+    go = rng.normal(0, 1.0, (Q, 25))
+
+    def run(dt, mode):
+        if mode:
+            monkeypatch.setenv("KC_TRAIN_MODE", mode)
+        else:
+            monkeypatch.delenv("KC_TRAIN_MODE", raising=False)
+        mlp = ops.Mlp(*[dev(w, dt) for w in W])
+        out = ops.mlp_bwd(mlp, dev(x, dt), dev(go, dt))
+        return [o.cpu().numpy().astype(np.float64) for o in out]
+
+    ref = run(torch.float64, None)
+    simt = run(torch.float32, "simt")
+    tc = run(torch.float32, None)
+    for name, r, a, b in zip(("gx",) + PK, ref, simt, tc):
+        scale = np.abs(r).max()
+        assert np.abs(a - r).max() < 1e-4 * scale, (name, "simt")
+        assert np.abs(b - r).max() < 1e-4 * scale, (name, "tc", np.abs(b - r).max() / scale)
