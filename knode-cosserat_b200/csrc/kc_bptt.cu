@@ -30,7 +30,7 @@ kc_rollout_bwd_kernel(const __grid_constant__ RodC<T> P, const MlpC<T> M, int64_
 // warp-cooperative variant: one rod per warp, the MLP (and its input VJP) split over the lanes (kc_mlp_coop.cuh)
 constexpr int KC_BCOOP_WARPS = 8;   // rods (warps) per CTA sharing one shared-memory copy of the MLP weights
 template <typename T, bool DIAG, int IN, int NH>
-__global__ void __launch_bounds__(32 * KC_BCOOP_WARPS)
+__global__ void __launch_bounds__(32 * KC_BCOOP_WARPS, 1)
 kc_rollout_bwd_coop_kernel(const __grid_constant__ RodC<T> P, MlpCoop<T> M, int64_t B, int T_,
                            const T* __restrict__ tensions, const T* __restrict__ traj, const T* __restrict__ gtraj,
                            T* __restrict__ gten, T* __restrict__ xs, T* __restrict__ gos, T fd_eps, int wc_elems) {

@@ -64,7 +64,7 @@ kc_rollout_kernel(const __grid_constant__ RodC<T> P, const MlpC<T> M, int64_t B,
 // is split over the lanes (kc_mlp_coop.cuh).  Chosen when the MLP is in the march and the batch is small.
 constexpr int KC_COOP_WARPS = 8;   // rods (warps) per CTA: they share one shared-memory copy of the MLP weights
 template <typename T, bool DIAG, int IN, int NH>
-__global__ void __launch_bounds__(32 * KC_COOP_WARPS)
+__global__ void __launch_bounds__(32 * KC_COOP_WARPS, 1)
 kc_rollout_coop_kernel(const __grid_constant__ RodC<T> P, MlpCoop<T> M, int64_t B, int T_,
                        const T* __restrict__ tensions, const T* __restrict__ y0, const T* __restrict__ z0, T* trajD,
                        T tol, int max_iter, T fd_eps, T* Gout, int32_t* iters, int wc_elems) {

@@ -24,4 +24,5 @@ for rep in range(2):
     g = torch.ones_like(traj) * 1e-3
     out = _ops.rollout_bwd(P, mlp, ctl, traj, g)
     e[2].record(); torch.cuda.synchronize()
-print("ok fwd %.2f ms  bwd %.2f ms  converged %s  |gW1| %.3e" % (e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2]), bool((iters >= 0).all()), float(out[1].abs().max())))
+it = iters[:, 1:].abs().float()
+print("ok fwd %.2f ms  bwd %.2f ms  converged %s  |gW1| %.3e  marches/step mean %.2f max %d" % (e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2]), bool((iters >= 0).all()), float(out[1].abs().max()), float(it.mean()), int(it.max())))
