@@ -64,7 +64,7 @@ static BpttWs bptt_ws(int dtype, int N, const kc_mlp* mlp, int64_t B, int64_t T_
     w.xs = off; off += a256((size_t)w.Qs * (mlp ? mlp->in_dim : 0) * sz);
     w.gos = off; off += a256((size_t)w.Qs * 25 * sz);
     w.wp = off; off += mlp ? a256((size_t)mlp->hidden * (((mlp->in_dim + 3) & ~3) + 32) * sz) : 0;
-    w.wc = off; off += mlp ? a256((size_t)(((mlp->in_dim + 3) & ~3) + 26) * (size_t)((mlp->hidden + 31) & ~31) * sz) : 0;
+    w.wc = off; off += mlp ? a256((size_t)kc_coop_row(mlp->in_dim) * (size_t)((mlp->hidden + 31) & ~31) * sz) : 0;
     w.mlp_bytes = mlp ? kc_ode_bwd_workspace_bytes(dtype, mlp, w.Qs) : 0;
     w.mlpws = off; off += a256((size_t)w.mlp_bytes);
     w.total = off + 256;
@@ -124,7 +124,7 @@ static int bwd_typed(const kc_rod_params* Pp, const kc_mlp* mlp, int64_t B, int6
     do {                                                                                                               \
         auto kern = kc_rollout_bwd_coop_kernel<T, D, I, H>;                                                            \
         const size_t state_b = (size_t)KC_BCOOP_WARPS * 4 * H * (N - 1) * sizeof(T);                                   \
-        const size_t wc_b = (size_t)(((in_dim + 3) & ~3) + 26) * MC.Hp * sizeof(T);                                    \
+        const size_t wc_b = (size_t)kc_coop_row(I) * MC.Hp * sizeof(T);                                                \
         const int wc_elems = wc_b + state_b <= 200 * 1024 ? (int)(wc_b / sizeof(T)) : 0;                               \
         const size_t csmem = state_b + (size_t)wc_elems * sizeof(T);                                                   \
         if (csmem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem);    \

@@ -59,9 +59,15 @@ struct MlpC {
 };
 
 // Warp-cooperative MLP view (kc_mlp_coop.cuh): the 32 lanes of a warp hold the SAME rod and split the hidden units.
-// Wc: [inP][Hp] W1^T | [Hp] b1 | [25][Hp] W2 with Hp = hidden rounded up to 32 (zero padded), unit index fastest so
-// that a warp's loads are coalesced.  Passing an MlpCoop instead of an MlpC selects the cooperative evaluation by
+// Wc: one row of KC_COOP_ROW(in_dim) values per hidden unit (Hp = hidden rounded up to 32, zero rows as padding):
+// [0, in_dim) W1[i][:], [inP] b1[i], [inP+1, inP+26) W2[:][i].  A lane reads its unit's row with 16-byte loads; the row
+// length is a multiple of 4 with an ODD number of 16-byte words, so the 8 lanes of a 128-bit shared-memory phase hit
+// distinct banks.  Passing an MlpCoop instead of an MlpC selects the cooperative evaluation by
 // overload resolution; everything else of the per-rod code is unchanged (all lanes compute the physics redundantly).
+constexpr int kc_coop_row(int in_dim) {
+    const int n = ((((in_dim + 3) & ~3) + 26) + 3) & ~3;
+    return ((n / 4) & 1) ? n : n + 4;
+}
 template <typename T>
 struct MlpCoop : MlpC<T> {
     const T* Wc;

@@ -533,7 +533,7 @@ static RolloutWs rollout_ws(int dtype, int N, const kc_mlp* mlp, int64_t B, int6
     w.wp = off;
     if (mlp) off += align256((size_t)mlp->hidden * (((mlp->in_dim + 3) & ~3) + 32) * sz);
     w.wc = off;
-    if (mlp) off += align256((size_t)(((mlp->in_dim + 3) & ~3) + 26) * (size_t)((mlp->hidden + 31) & ~31) * sz);
+    if (mlp) off += align256((size_t)kc_coop_row(mlp->in_dim) * (size_t)((mlp->hidden + 31) & ~31) * sz);
     w.state = off;
     off += align256((size_t)KC_SHOOT_SLOTS * w.Bpad * sz);
     w.total = off;
@@ -640,7 +640,7 @@ static int rollout_typed(const kc_rod_params* Pp, const kc_mlp* mlp, int64_t B, 
     do {                                                                                                               \
         auto kern = kc_rollout_coop_kernel<T, D, I, H>;                                                                \
         const size_t state_b = (size_t)KC_COOP_WARPS * (H * (N - 1) + KC_SHOOT_SLOTS) * sizeof(T);                     \
-        const size_t wc_b = (size_t)(inP + 26) * MC.Hp * sizeof(T);                                                    \
+        const size_t wc_b = (size_t)kc_coop_row(I) * MC.Hp * sizeof(T);                                                \
         const int wc_elems = wc_b + state_b <= 200 * 1024 ? (int)(wc_b / sizeof(T)) : 0;                               \
         const size_t csmem = state_b + (size_t)wc_elems * sizeof(T);                                                   \
         if (csmem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem);    \
