@@ -107,10 +107,92 @@ static int prep_mlp(const kc_mlp* mlp, MlpC<T>& M, cudaStream_t st) {
         else KC_DISPATCH_IN(false, in_dim, CALL);                         \
     } while (0)
 
+// Tensor-core KNODE forward (fp32, 28 inputs, hidden <= 512, >= 4096 samples): the physics of every sample on the SIMT
+// pipes (kc_ode_prep_kernel -> X[Q][32] = [y; z; tf], PHYS[Q][25] = [ys; z]), then the MLP contraction and the residual add
+// on tcgen05 (kc_train_tc_kernel<1>) writing ys[Q][19] and z[Q][6] directly.
+void* kc_tc_scratch(size_t bytes);
+bool kc_tc_forward_ok(const kc_mlp* mlp, int64_t Q);
+int kc_train_tc_grid(int64_t Q);
+int kc_tc_launch_mode(int mode, const kc_mlp* mlp, float ds, int64_t Q, int T_, int K, const float* X, const float* PHYS,
+                      const float* TGT, float* W1hl, float* W2c_, float* partial, int64_t NP, double* loss_part,
+                      float* pred_out, const float* dOin, int grid, cudaStream_t st, int xpitch = 32);
+
+template <typename T, bool DIAG>
+__global__ void __launch_bounds__(ODE_THREADS)
+kc_ode_prep_kernel(const __grid_constant__ RodC<T> P, int64_t Q, const T* __restrict__ y, const T* __restrict__ yh,
+                   const T* __restrict__ zh, const T* __restrict__ tf, T* __restrict__ X, T* __restrict__ PHYS) {
+    __shared__ T s_a[ODE_THREADS * 32], s_b[ODE_THREADS * 25], s_zh[ODE_THREADS * 6], s_tf[ODE_THREADS * 3];
+    const int64_t first = (int64_t)blockIdx.x * ODE_THREADS;
+    const int64_t count = min((int64_t)ODE_THREADS, Q - first);
+    stage_in(s_a, y, first, count, 19);
+    stage_in(s_b, yh, first, count, 19);
+    stage_in(s_zh, zh, first, count, 6);
+    stage_in(s_tf, tf, first, count, 3);
+    __syncthreads();
+    T ry[19], rh[25], rt[3], rys[19], rz[6];
+    const int i = threadIdx.x;
+    if (i < count) {
+#pragma unroll
+        for (int k = 0; k < 19; ++k) { ry[k] = s_a[i * 19 + k]; rh[k] = s_b[i * 19 + k]; }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) rh[19 + k] = s_zh[i * 6 + k];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) rt[k] = s_tf[i * 3 + k];
+        rod_ode<T, DIAG>(P, ry, rh + 13, rh + 16, rh + 19, rh + 22, rt, rys, rz);
+    }
+    __syncthreads();
+    if (i < count) {
+#pragma unroll
+        for (int k = 0; k < 19; ++k) { s_a[i * 32 + k] = ry[k]; s_b[i * 25 + k] = rys[k]; }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) { s_a[i * 32 + 19 + k] = rz[k]; s_b[i * 25 + 19 + k] = rz[k]; }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) s_a[i * 32 + 25 + k] = rt[k];
+#pragma unroll
+        for (int k = 28; k < 32; ++k) s_a[i * 32 + k] = T(0);
+    }
+    __syncthreads();
+    stage_out(s_a, X, first, count, 32);
+    stage_out(s_b, PHYS, first, count, 25);
+}
+
+template <typename T>
+static int ode_fwd_tc(const RodC<T>&, const kc_mlp*, int64_t, const void*, const void*, const void*, const void*, void*, void*,
+                      cudaStream_t) { return 1; }
+template <>
+int ode_fwd_tc<float>(const RodC<float>& P, const kc_mlp* mlp, int64_t Q, const void* y, const void* yh, const void* zh,
+                      const void* tf, void* ys, void* z, cudaStream_t st) {
+    if (!kc_tc_forward_ok(mlp, Q)) return 1;   // 1: not taken
+    if (int rc = kc_check_mlp(mlp)) return rc;
+    const size_t tcw_b = (size_t)4 * (2 * 128 * 32 * 4 + 32768);
+    const size_t xb = ((size_t)Q * 32 * 4 + 255) & ~(size_t)255, pb = ((size_t)Q * 25 * 4 + 255) & ~(size_t)255;
+    unsigned char* buf = (unsigned char*)kc_tc_scratch(tcw_b + 2048 + xb + pb);
+    if (!buf) { kc_set_error("cudaMalloc of the tensor-core scratch failed"); return KC_ECUDA; }
+    float* tcw = (float*)buf;
+    double* lossp = (double*)(buf + tcw_b);
+    float* X = (float*)(buf + tcw_b + 2048);
+    float* PHYS = (float*)(buf + tcw_b + 2048 + xb);
+    const unsigned grid = (unsigned)((Q + ODE_THREADS - 1) / ODE_THREADS);
+    if (P.diag)
+        kc_ode_prep_kernel<float, true><<<grid, ODE_THREADS, 0, st>>>(P, Q, (const float*)y, (const float*)yh, (const float*)zh,
+                                                                      (const float*)tf, X, PHYS);
+    else
+        kc_ode_prep_kernel<float, false><<<grid, ODE_THREADS, 0, st>>>(P, Q, (const float*)y, (const float*)yh, (const float*)zh,
+                                                                       (const float*)tf, X, PHYS);
+    KC_CHECK_LAUNCH("kc_ode_prep_kernel");
+    // ys += o[0:19], z += o[19:25] (cosserat_ode_torch.py:199-212): scale 1 on every row; outputs split (z via `partial`)
+    return kc_tc_launch_mode(1, mlp, 1.f, Q, 2, 1, X, PHYS, nullptr, tcw, tcw + 4 * 2 * 128 * 32, (float*)z, 0, lossp,
+                             (float*)ys, nullptr, kc_train_tc_grid(Q), st, 32);
+}
+
 template <typename T>
 static int ode_fwd_typed(const kc_rod_params* Pp, const kc_mlp* mlp, int64_t Q, const void* y, const void* yh,
                          const void* zh, const void* tf, void* ys, void* z, cudaStream_t st) {
     const RodC<T> P = make_rodc<T>(*Pp);
+    {
+        const int rc = ode_fwd_tc<T>(P, mlp, Q, y, yh, zh, tf, ys, z, st);
+        if (rc <= 0) return rc;
+    }
     MlpC<T> M;
     int rc = prep_mlp<T>(mlp, M, st);
     if (rc) return rc;

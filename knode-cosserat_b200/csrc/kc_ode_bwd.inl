@@ -109,7 +109,7 @@ kc_ode_bwd_kernel(const __grid_constant__ RodC<T> P, const MlpC<T> M, int64_t Q,
 // to the SIMT kernel.  slices = number of partial-gradient slices written (< 0: launch error).
 int kc_tc_launch_mode(int mode, const kc_mlp* mlp, float ds, int64_t Q, int T_, int K, const float* X, const float* PHYS,
                       const float* TGT, float* W1hl, float* W2c_, float* partial, int64_t NP, double* loss_part,
-                      float* pred_out, const float* dOin, int grid, cudaStream_t st);
+                      float* pred_out, const float* dOin, int grid, cudaStream_t st, int xpitch = 32);
 template <typename T>
 static bool kc_param_grads_tc(const kc_mlp*, int64_t, const T*, const T*, T*, const TrainWs&, unsigned char*, cudaStream_t,
                               int&) { return false; }
@@ -258,8 +258,43 @@ kc_mlp_bwd_kernel(const MlpC<T> M, int64_t Q, const T* __restrict__ x, const T* 
     }
 }
 
+// Library-owned scratch for the tensor-core forward of the no-workspace entry points (grown on demand, never shrunk; the
+// consumers run on the caller's stream after the producers).
+void* kc_tc_scratch(size_t bytes) {
+    static void* buf = nullptr;
+    static size_t cap = 0;
+    if (bytes > cap) {
+        if (buf) cudaFree(buf);   // synchronises: safe w.r.t. earlier consumers
+        if (cudaMalloc(&buf, bytes) != cudaSuccess) { buf = nullptr; cap = 0; return nullptr; }
+        cap = bytes;
+    }
+    return buf;
+}
+bool kc_tc_forward_ok(const kc_mlp* mlp, int64_t Q) {
+    if (!mlp || mlp->in_dim != 28 || mlp->hidden > 512 || Q < 4096) return false;
+    const char* e = getenv("KC_TRAIN_MODE");
+    return !(e && e[0] == 's');
+}
+constexpr size_t KC_TCW_BYTES = (size_t)4 * (2 * 128 * 32 * 4 + 32768);   // weight images of kc_tc_prep_weights_kernel
+
+template <typename T>
+static int mlp_fwd_tc(const kc_mlp*, int64_t, const void*, void*, cudaStream_t) { return 1; }
+template <>
+int mlp_fwd_tc<float>(const kc_mlp* mlp, int64_t Q, const void* x, void* out, cudaStream_t st) {
+    if (!kc_tc_forward_ok(mlp, Q)) return 1;   // 1: not taken
+    float* tcw = (float*)kc_tc_scratch(KC_TCW_BYTES + 256 * sizeof(double));
+    if (!tcw) { kc_set_error("cudaMalloc of the tensor-core scratch failed"); return KC_ECUDA; }
+    // forward-only mode: out[Q][25] = W2 ELU(W1 x + b1) + b2, x rows 28 floats apart
+    return kc_tc_launch_mode(1, mlp, 1.f, Q, 2, 1, (const float*)x, nullptr, nullptr, tcw, tcw + 4 * 2 * 128 * 32, nullptr, 0,
+                             (double*)((unsigned char*)tcw + KC_TCW_BYTES), (float*)out, nullptr, kc_train_tc_grid(Q), st, 28);
+}
+
 template <typename T>
 static int mlp_fwd_typed(const kc_mlp* mlp, int64_t Q, const void* x, void* out, cudaStream_t st) {
+    {
+        const int rc = mlp_fwd_tc<T>(mlp, Q, x, out, st);
+        if (rc <= 0) return rc;
+    }
     // packed weights in a scratch buffer owned by the library (this entry point takes no workspace)
     static void* buf = nullptr;
     static size_t cap = 0;

@@ -106,7 +106,7 @@ kc_train_tc_kernel(int hidden, int nch, const float* __restrict__ W1hl, const un
                    const float* __restrict__ b2, float ds, int64_t Q, int T_, int K, const float* __restrict__ X,
                    const float* __restrict__ PHYS, const float* __restrict__ TGT, float* __restrict__ partial,
                    int64_t NP, double* __restrict__ loss_part, float* __restrict__ pred_out,
-                   const float* __restrict__ dOin) {
+                   const float* __restrict__ dOin, int xpitch) {
     extern __shared__ __align__(1024) unsigned char sm[];
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + tc::OFF_MISC);
     uint64_t* barZ = reinterpret_cast<uint64_t*>(sm + tc::OFF_MISC + 8);
@@ -244,10 +244,11 @@ kc_train_tc_kernel(int hidden, int nch, const float* __restrict__ W1hl, const un
         // ---- stage the X tile: tf32 hi/lo K-major (A of GEMM1) and bf16 hi/lo MN-major (B of the gW1 GEMM) ----
         {
             float xv[16];
-            const float4* xs = reinterpret_cast<const float4*>(X + (size_t)(valid ? q : 0) * 32 + half * 16);
+            // rows of X are xpitch floats apart (32, or 28 for an unpadded [Q][28] input); columns 28..31 are never read
+            const float4* xs = reinterpret_cast<const float4*>(X + (size_t)(valid ? q : 0) * xpitch + half * 16);
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
-                float4 t = valid ? xs[g] : make_float4(0.f, 0.f, 0.f, 0.f);
+                float4 t = (valid && !(half == 1 && g == 3)) ? xs[g] : make_float4(0.f, 0.f, 0.f, 0.f);
                 xv[4 * g] = t.x; xv[4 * g + 1] = t.y; xv[4 * g + 2] = t.z; xv[4 * g + 3] = t.w;
             }
             if (half == 1) {   // column 28: carries b1 in GEMM1 and yields gb1 in the gW1 GEMM; 29..31: padding (must be finite)
@@ -334,11 +335,21 @@ kc_train_tc_kernel(int hidden, int nch, const float* __restrict__ W1hl, const un
 #pragma unroll
                 for (int c = 0; c < 25; ++c) { o[c] = 0.f; g[c] = valid ? dOin[(size_t)q * 32 + c] : 0.f; }
             }
-            if (MODE == 1) {
+            if (MODE == 1) {   // pred = PHYS (or 0) + s*o -> pred_out[Q][25], or split as ys[Q][19] | z[Q][6] (z = `partial`)
                 if (valid) {
+                    float pr[25];
 #pragma unroll
                     for (int r = 0; r < 25; ++r)
-                        pred_out[(size_t)q * 25 + r] = PHYS[(size_t)q * 25 + r] + (r < 19 ? ds : 1.f) * o[r];
+                        pr[r] = (PHYS ? PHYS[(size_t)q * 25 + r] : 0.f) + (r < 19 ? ds : 1.f) * o[r];
+                    if (partial) {
+#pragma unroll
+                        for (int r = 0; r < 19; ++r) pred_out[(size_t)q * 19 + r] = pr[r];
+#pragma unroll
+                        for (int c = 0; c < 6; ++c) partial[(size_t)q * 6 + c] = pr[19 + c];
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < 25; ++r) pred_out[(size_t)q * 25 + r] = pr[r];
+                    }
                 }
             }
             if (MODE == 0 && valid) {
@@ -512,7 +523,7 @@ kc_train_tc_kernel(int hidden, int nch, const float* __restrict__ W1hl, const un
 // bytes (workspace), partial: grid*NP floats, loss_part: grid doubles.
 int kc_tc_launch_mode(int mode, const kc_mlp* mlp, float ds, int64_t Q, int T_, int K, const float* X, const float* PHYS,
                       const float* TGT, float* W1hl, float* W2c_, float* partial, int64_t NP, double* loss_part,
-                      float* pred_out, const float* dOin, int grid, cudaStream_t st);
+                      float* pred_out, const float* dOin, int grid, cudaStream_t st, int xpitch = 32);
 int kc_train_tc_grid(int64_t Q) {
     const int64_t ntiles = (Q + tc::TS - 1) / tc::TS;
     int dev = 0, sms = 148;
@@ -525,13 +536,13 @@ int kc_train_tc_launch(const kc_mlp* mlp, float ds, int64_t Q, int T_, int K, co
                        const float* TGT, float* W1hl, float* W2c_, float* partial, int64_t NP, double* loss_part,
                        float* pred_out, int grid, cudaStream_t st) {
     return kc_tc_launch_mode(0, mlp, ds, Q, T_, K, X, PHYS, TGT, W1hl, W2c_, partial, NP, loss_part, pred_out, nullptr,
-                             grid, st);
+                             grid, st, 32);
 }
 
 // mode 0: training step; 1: forward only (pred_out[Q][25] = PHYS + s*o); 2: parameter gradients from (X, dOin) samples
 int kc_tc_launch_mode(int mode, const kc_mlp* mlp, float ds, int64_t Q, int T_, int K, const float* X, const float* PHYS,
                       const float* TGT, float* W1hl, float* W2c_, float* partial, int64_t NP, double* loss_part,
-                      float* pred_out, const float* dOin, int grid, cudaStream_t st) {
+                      float* pred_out, const float* dOin, int grid, cudaStream_t st, int xpitch) {
     const int nch = (mlp->hidden + tc::HC - 1) / tc::HC;
     unsigned char* W2b = reinterpret_cast<unsigned char*>(W2c_);
     kc_tc_prep_weights_kernel<<<dim3(nch, 8), 256, 0, st>>>((const float*)mlp->W1, (const float*)mlp->b1,
@@ -541,7 +552,7 @@ int kc_tc_launch_mode(int mode, const kc_mlp* mlp, float ds, int64_t Q, int T_, 
     do {                                                                                                               \
         cudaFuncSetAttribute(kc_train_tc_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);      \
         kc_train_tc_kernel<M><<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(mlp->hidden, nch, W1hl, W2b,                  \
-            (const float*)mlp->b2, ds, Q, T_, K, X, PHYS, TGT, partial, NP, loss_part, pred_out, dOin);                \
+            (const float*)mlp->b2, ds, Q, T_, K, X, PHYS, TGT, partial, NP, loss_part, pred_out, dOin, xpitch);        \
     } while (0)
     if (mode == 0) KC_TC_GO(0); else if (mode == 1) KC_TC_GO(1); else KC_TC_GO(2);
 #undef KC_TC_GO

@@ -252,3 +252,38 @@ def test_param_grads_tensor_core_vs_simt_and_fp64(ops, monkeypatch, H):
         scale = np.abs(r).max()
         assert np.abs(a - r).max() < 1e-4 * scale, (name, "simt")
         assert np.abs(b - r).max() < 1e-4 * scale, (name, "tc", np.abs(b - r).max() / scale)
+
+
+@pytest.mark.parametrize("H", [512, 200])
+def test_forward_tensor_core_vs_simt_and_fp64(ops, monkeypatch, H):
+    """kc_mlp_fwd / kc_ode_fwd with >= 4096 samples run the MLP contraction on tcgen05 (kc_train_tc_kernel<1>, physics on
+    the SIMT pipes): same numbers as the SIMT kernels and as fp64."""
+    rng = np.random.default_rng(100 + H)
+    Q = 5000 + 61
+    W = [rng.normal(0, 0.3, (H, 28)), rng.normal(0, 0.1, H), rng.normal(0, 0.05, (25, H)), rng.normal(0, 0.1, 25)]
+    x = rng.normal(0, 1.0, (Q, 28))
+    y = rng.normal(0, 1.0, (Q, 19)); y[:, 3] += 2.0
+    yh, zh, tf = rng.normal(0, 1.0, (Q, 19)), rng.normal(0, 1.0, (Q, 6)), rng.normal(0, 1.0, (Q, 3))
+    P = params(P_setup())
+
+    def run(dt, mode):
+        if mode:
+            monkeypatch.setenv("KC_TRAIN_MODE", mode)
+        else:
+            monkeypatch.delenv("KC_TRAIN_MODE", raising=False)
+        mlp = ops.Mlp(*[dev(w, dt) for w in W])
+        o = ops.mlp_fwd(mlp, dev(x, dt))
+        ys, z = ops.ode_fwd(P, mlp, dev(y, dt), dev(yh, dt), dev(zh, dt), dev(tf, dt))
+        return [t.cpu().numpy().astype(np.float64) for t in (o, ys, z)]
+
+    ref = run(torch.float64, None)
+    simt = run(torch.float32, "simt")
+    tc = run(torch.float32, None)
+    for name, r, a, b in zip(("mlp", "ys", "z"), ref, simt, tc):
+        assert col_err(a, r) < 1e-4, (name, "simt")
+        assert col_err(b, r) < 1e-4, (name, "tc", col_err(b, r))
+
+
+def col_err(a, b, floor=1e-3):
+    scale = np.abs(b).reshape(-1, b.shape[-1]).max(0) + floor
+    return float(np.max(np.abs(a - b) / scale))
