@@ -180,6 +180,10 @@ def main():
         raise SystemExit("bench.py: no CUDA device (this repo has no CPU fallback)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_node = None
+    if world > 1:
+        import _dist
+        numa_node = _dist.bind_to_gpu_numa_node(local_rank)   # pinned buffers land on the GPU's own socket
     if world > 1:
         # NCCL prints its version banner on stdout during initialisation; keep stdout for the ONE JSON line
         sys.stdout.flush()
@@ -407,7 +411,7 @@ def main():
                     "d2h_bytes_per_step": int(pinned.numel() * 4), "api": "knode.simulate(robot, ctl[B,T,4], "
                     "dtype=float32, rows=25) pinned host tensions in -> pinned host trajectory out = one kc_rollout_host C-ABI call (H2D, "
                     "rollout in time ranges, D2H of each finished range overlapped with the next)",
-                    "ms_per_step": e2e_s / args.steps * 1e3},
+                    "ms_per_step": e2e_s / args.steps * 1e3, "numa_node_rank0": numa_node},
             "gpu_launches": 1 * args.steps,
             "roofline": {"bound": "fp32", "kernel": "kc_rollout_wide_lin_kernel<float,diag,physics,N=10> (8 lanes per rod: "
                          "Newton + per-march FD Jacobian + linearised final correction; writes traj[B,T,25,N] directly)",

@@ -18,10 +18,36 @@ def init_from_env(device_index=None):
             if device_index is None:
                 device_index = int(os.environ.get("LOCAL_RANK", "0"))
             torch.cuda.set_device(device_index)
+            bind_to_gpu_numa_node(device_index)
             dist.init_process_group("nccl", device_id=torch.device("cuda", device_index))
         else:
             dist.init_process_group("gloo")
     return rank, world
+
+
+def bind_to_gpu_numa_node(device_index):
+    """Pin this process (and therefore its pinned host buffers, first touch) to the CPUs of the NUMA node the GPU hangs
+    off.  With one rank per GPU and 410 MB of trajectory per step coming back over PCIe, ranks that all sit on one socket
+    funnel every device-to-host stream through that socket's memory.  Best effort: returns the node or None."""
+    try:
+        props = torch.cuda.get_device_properties(device_index)
+        bus = "%04x:%02x:%02x.0" % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return node
+    except Exception:
+        pass
+    return None
 
 
 def world_info():
