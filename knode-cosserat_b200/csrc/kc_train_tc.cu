@@ -62,6 +62,24 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(umma::smem_u32(bar)), "r"(bytes) : "memory");
 }
 
+// Eight values -> eight bf16 hi | eight bf16 lo (x = hi + lo to ~16 mantissa bits), ready for one 16-byte store each.
+// hi = the fp32 word rounded to its upper half with integer arithmetic (add half an ulp, mask; a byte permute packs two
+// of them), lo = x - hi exactly, rounded to bf16 by the packing conversion: nothing on the XU pipe (cvt.rn.bf16.f32 is an
+// XU instruction and the kernel's exponentials live there too).  Plain truncation of hi would save one more instruction
+// per value but doubles |lo|; the first Adam step (g / (|g| + eps)) is sensitive enough to see that.
+__device__ __forceinline__ void split_pack8(const float x[8], uint4& hi, uint4& lo) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t a = (__float_as_uint(x[2 * i]) + 0x8000u) & 0xffff0000u;
+        const uint32_t b = (__float_as_uint(x[2 * i + 1]) + 0x8000u) & 0xffff0000u;
+        h[i] = __byte_perm(a, b, 0x7632);
+        l[i] = pack_bf16x2(x[2 * i] - __uint_as_float(a), x[2 * i + 1] - __uint_as_float(b));
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
 // K-major, no swizzle, 2-byte elements: element (r, k) of a tile with KT k-values per row
 __device__ __forceinline__ uint32_t kmajor_off_b16(int r, int k, int KT) {
     return (uint32_t)(((r >> 3) * (KT >> 3) + (k >> 3)) * 128 + (r & 7) * 16 + (k & 7) * 2);
@@ -268,14 +286,11 @@ kc_train_tc_kernel(int hidden, int nch, const float* __restrict__ W1hl, const un
             }
 #pragma unroll
             for (int g = 0; g < 2; ++g) {
-                float hi[8], lo[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) split_bf16(xv[8 * g + j], hi[j], lo[j]);
+                uint4 hi, lo;
+                split_pack8(xv + 8 * g, hi, lo);
                 const uint32_t o = umma::mnmajor_off_b16(half * 16 + 8 * g, row, 128);
-                *reinterpret_cast<uint4*>(sm + tc::OFF_XT + o) =
-                    make_uint4(pack_bf16x2(hi[0], hi[1]), pack_bf16x2(hi[2], hi[3]), pack_bf16x2(hi[4], hi[5]), pack_bf16x2(hi[6], hi[7]));
-                *reinterpret_cast<uint4*>(sm + tc::OFF_XT + 8192 + o) =
-                    make_uint4(pack_bf16x2(lo[0], lo[1]), pack_bf16x2(lo[2], lo[3]), pack_bf16x2(lo[4], lo[5]), pack_bf16x2(lo[6], lo[7]));
+                *reinterpret_cast<uint4*>(sm + tc::OFF_XT + o) = hi;
+                *reinterpret_cast<uint4*>(sm + tc::OFF_XT + 8192 + o) = lo;
             }
         }
         const bool more_tiles = tile + gridDim.x < ntiles;
@@ -304,14 +319,14 @@ kc_train_tc_kernel(int hidden, int nch, const float* __restrict__ W1hl, const un
                 umma::wait_ld();
 #pragma unroll
                 for (int g8 = 0; g8 < 4; ++g8) {
-                    float ah[8], al[8];
+                    float a8[8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) split_bf16(kc_elu(__uint_as_float(v[g8 * 8 + j])), ah[j], al[j]);
+                    for (int j = 0; j < 8; ++j) a8[j] = kc_elu(__uint_as_float(v[g8 * 8 + j]));
+                    uint4 ah, al;
+                    split_pack8(a8, ah, al);
                     const uint32_t off = umma::mnmajor_off_b16(half * 64 + cc * 32 + g8 * 8, row, 128);
-                    *reinterpret_cast<uint4*>(sm + tc::OFF_A + off) =
-                        make_uint4(pack_bf16x2(ah[0], ah[1]), pack_bf16x2(ah[2], ah[3]), pack_bf16x2(ah[4], ah[5]), pack_bf16x2(ah[6], ah[7]));
-                    *reinterpret_cast<uint4*>(sm + tc::OFF_A + 32768 + off) =
-                        make_uint4(pack_bf16x2(al[0], al[1]), pack_bf16x2(al[2], al[3]), pack_bf16x2(al[4], al[5]), pack_bf16x2(al[6], al[7]));
+                    *reinterpret_cast<uint4*>(sm + tc::OFF_A + off) = ah;
+                    *reinterpret_cast<uint4*>(sm + tc::OFF_A + 32768 + off) = al;
                 }
             }
             umma::fence_async_smem();
@@ -391,17 +406,17 @@ kc_train_tc_kernel(int hidden, int nch, const float* __restrict__ W1hl, const un
             // dO^T as bf16 hi/lo, MN-major [32 outputs x 128 samples] (B operand of the gW2 GEMM)
 #pragma unroll
             for (int gi = 0; gi < 4; ++gi) {
-                float hi[8], lo[8];
+                float g8v[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const int c = gi * 8 + j;
-                    split_bf16(c < 25 ? g[c < 25 ? c : 0] : 0.f, hi[j], lo[j]);
+                    g8v[j] = c < 25 ? g[c < 25 ? c : 0] : 0.f;
                 }
+                uint4 hi, lo;
+                split_pack8(g8v, hi, lo);
                 const uint32_t off = umma::mnmajor_off_b16(gi * 8, row, 128);
-                *reinterpret_cast<uint4*>(sm + tc::OFF_DO + off) =
-                    make_uint4(pack_bf16x2(hi[0], hi[1]), pack_bf16x2(hi[2], hi[3]), pack_bf16x2(hi[4], hi[5]), pack_bf16x2(hi[6], hi[7]));
-                *reinterpret_cast<uint4*>(sm + tc::OFF_DO + 8192 + off) =
-                    make_uint4(pack_bf16x2(lo[0], lo[1]), pack_bf16x2(lo[2], lo[3]), pack_bf16x2(lo[4], lo[5]), pack_bf16x2(lo[6], lo[7]));
+                *reinterpret_cast<uint4*>(sm + tc::OFF_DO + off) = hi;
+                *reinterpret_cast<uint4*>(sm + tc::OFF_DO + 8192 + off) = lo;
             }
         }
         umma::fence_async_smem();       // the dO tile
@@ -431,24 +446,23 @@ kc_train_tc_kernel(int hidden, int nch, const float* __restrict__ W1hl, const un
                 umma::wait_ld();
 #pragma unroll
                 for (int g8 = 0; g8 < 4; ++g8) {
-                    float ah[8], al[8], dh[8], dl[8];
+                    float a8[8], d8[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const float z = __uint_as_float(v[g8 * 8 + j]);
                         const float a = kc_elu(z);
-                        split_bf16(a, ah[j], al[j]);
+                        a8[j] = a;
                         // ELU'(z) = 1 (z > 0) or e^z = ELU(z) + 1: no second exponential
-                        split_bf16(__uint_as_float(d[g8 * 8 + j]) * (z > 0.f ? 1.f : a + 1.f), dh[j], dl[j]);
+                        d8[j] = __uint_as_float(d[g8 * 8 + j]) * (z > 0.f ? 1.f : a + 1.f);
                     }
+                    uint4 ah, al, dh, dl;
+                    split_pack8(a8, ah, al);
+                    split_pack8(d8, dh, dl);
                     const uint32_t off = umma::mnmajor_off_b16(half * 64 + cc * 32 + g8 * 8, row, 128);
-                    *reinterpret_cast<uint4*>(sm + tc::OFF_A + off) =
-                        make_uint4(pack_bf16x2(ah[0], ah[1]), pack_bf16x2(ah[2], ah[3]), pack_bf16x2(ah[4], ah[5]), pack_bf16x2(ah[6], ah[7]));
-                    *reinterpret_cast<uint4*>(sm + tc::OFF_A + 32768 + off) =
-                        make_uint4(pack_bf16x2(al[0], al[1]), pack_bf16x2(al[2], al[3]), pack_bf16x2(al[4], al[5]), pack_bf16x2(al[6], al[7]));
-                    *reinterpret_cast<uint4*>(sm + tc::OFF_DZ + off) =
-                        make_uint4(pack_bf16x2(dh[0], dh[1]), pack_bf16x2(dh[2], dh[3]), pack_bf16x2(dh[4], dh[5]), pack_bf16x2(dh[6], dh[7]));
-                    *reinterpret_cast<uint4*>(sm + tc::OFF_DZ + 32768 + off) =
-                        make_uint4(pack_bf16x2(dl[0], dl[1]), pack_bf16x2(dl[2], dl[3]), pack_bf16x2(dl[4], dl[5]), pack_bf16x2(dl[6], dl[7]));
+                    *reinterpret_cast<uint4*>(sm + tc::OFF_A + off) = ah;
+                    *reinterpret_cast<uint4*>(sm + tc::OFF_A + 32768 + off) = al;
+                    *reinterpret_cast<uint4*>(sm + tc::OFF_DZ + off) = dh;
+                    *reinterpret_cast<uint4*>(sm + tc::OFF_DZ + 32768 + off) = dl;
                 }
             }
             umma::fence_async_smem();
