@@ -182,7 +182,9 @@ class TeacherForcedTrainer:
 
 def dtw_l1(a, b):
     """Exact dynamic-time-warping distance with the L1 point distance — what fastdtw(a, b)[0] approximates with its
-    default radius=1 (physics_train.py:159, physics_multitrain.py:211).  a[Ta,d], b[Tb,d]."""
+    default radius=1 (physics_train.py:159, physics_multitrain.py:211).  a[Ta,d], b[Tb,d].
+    The recurrence acc[i,j] = cost[i,j] + min(acc[i-1,j], acc[i,j-1], acc[i-1,j-1]) is evaluated one ANTI-DIAGONAL at a time
+    (all cells of a diagonal depend only on the two previous ones), i.e. Ta+Tb-1 vectorised steps instead of Ta*Tb."""
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
     if a.ndim == 1:
         a, b = a[:, None], b[:, None]
@@ -190,9 +192,10 @@ def dtw_l1(a, b):
     Ta, Tb = cost.shape
     acc = np.full((Ta + 1, Tb + 1), np.inf)
     acc[0, 0] = 0.0
-    for i in range(1, Ta + 1):
-        for j in range(1, Tb + 1):
-            acc[i, j] = cost[i - 1, j - 1] + min(acc[i - 1, j], acc[i, j - 1], acc[i - 1, j - 1])
+    for d in range(2, Ta + Tb + 1):                 # cells (i, j), 1-based, with i + j == d
+        i = np.arange(max(1, d - Tb), min(Ta, d - 1) + 1)
+        j = d - i
+        acc[i, j] = cost[i - 1, j - 1] + np.minimum(np.minimum(acc[i - 1, j], acc[i, j - 1]), acc[i - 1, j - 1])
     return float(acc[Ta, Tb])
 
 
