@@ -608,6 +608,12 @@ static int rollout_typed(const kc_rod_params* Pp, const kc_mlp* mlp, int64_t B, 
     // (it writes the reference layout directly, so it needs rows != 0)
     const size_t lsmem = ((size_t)N * 25 * KC_WS + (size_t)2 * N * NH * KC_WG) * sizeof(T);
     bool lin = wide && rows != 0 && lsmem <= 32 * 1024;
+    // larger states (fp64, N > 10): still worth it while all warps are resident at once (it saves about one joint march
+    // in four); beyond one wave the plain wide kernel, whose footprint is a few KB, wins
+    if (wide && rows != 0 && !lin && lsmem <= 200 * 1024) {
+        const int64_t per_sm = (int64_t)(227 * 1024) / (int64_t)(lsmem + 1024);
+        lin = (B + KC_WG - 1) / KC_WG <= 148 * per_sm;
+    }
     {
         const char* e = getenv("KC_ROLLOUT_LIN");
         if (e && e[0] == '0') lin = false;
