@@ -13,6 +13,10 @@
  *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); calls are asynchronous and
  *     never allocate: scratch is caller-provided (`workspace`, sized by the matching *_workspace_bytes call);
  *   - return value 0 = launched; <0 = error (KC_E*), text via kc_last_error() (thread-local);
+ *   - the entry points that mirror reference methods taking nothing but tensors (kc_ode_fwd, kc_mlp_fwd, kc_march,
+ *     kc_segment_fwd) have no workspace argument: they keep a library-owned device scratch (packed weights, tensor-core
+ *     operand images) that is grown on demand and never shrunk — call them from one host thread at a time, as the
+ *     reference does (physics_train.py:179 pins torch to one thread), and not while a CUDA graph is being captured;
  *   - state layout (cosserat_ode_torch.py:141-152): y[19] = p(0:3) h(3:7,wxyz) n(7:10) m(10:13) q(13:16)
  *     w(16:19); z[6] = v(0:3) u(3:6); a rod is [25][N] row-major (rows = y then z, columns = nodes).
  */
