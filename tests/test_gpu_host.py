@@ -119,3 +119,27 @@ def test_simulate_host_and_device_inputs_agree(ops):
     full, G, it = simulate(robot, ctl, return_info=True)
     np.testing.assert_allclose(full[0], one, rtol=0, atol=0)
     assert G.shape == (9, 15, 6) and it.shape == (9, 15) and (it >= 0).all()
+
+
+def test_host_rollout_edge_sizes_and_knode(ops, golden):
+    """B = 0, T = 1 and a KNODE robot (the warp-cooperative kernel runs the full range in one piece) through the host call."""
+    import _kc
+    P = _kc.rod_params(O.setup_params(O.RodParams()))
+    dev0 = torch.device("cuda", 0)
+    hp = ops.HostRolloutPlan(P, None, 0, 5, torch.float32, dev0, rows=25)
+    assert tuple(hp.run(np.zeros((0, 5, 4), np.float32)).shape) == (0, 5, 25, int(P.N))
+    hp = ops.HostRolloutPlan(P, None, 3, 1, torch.float64, dev0, rows=50)
+    one = hp.run(_ctl(3, 1)).numpy()
+    assert one.shape == (3, 1, 50, int(P.N)) and np.isfinite(one).all()
+    np.testing.assert_array_equal(one[:, 0, :25], one[:, 0, 25:])          # index 0 repeats [y; z] (knode.py:68)
+    # KNODE: transplanted weights of the golden fixture, host call against the device call
+    d = golden["ode"]
+    mlp = ops.Mlp(*[torch.tensor(np.asarray(d[f"h512_{k}"]), dtype=torch.float32, device="cuda") * s
+                    for k, s in (("W1", 1.0), ("b1", 1.0), ("W2", 0.02), ("b2", 0.02))])
+    B, T = 5, 9
+    ctl = _ctl(B, T, seed=11)
+    ref, _, it = ops.rollout(P, mlp, torch.tensor(ctl, dtype=torch.float32, device="cuda"), rows=25)
+    hp = ops.HostRolloutPlan(P, mlp, B, T, torch.float32, dev0, rows=25, segments=4)
+    got = hp.run(ctl)
+    assert int(it.min()) >= 0
+    np.testing.assert_array_equal(got.numpy(), ref.cpu().numpy())
