@@ -37,6 +37,20 @@ def _stream(device):
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
+_SCRATCH = {}
+
+
+def _scratch(device, nbytes, tag):
+    """Grow-only workspace per (device, stream, call site): the backward entry points need hundreds of MB at the training
+    sizes, and a fresh torch.empty per call can fall through the caching allocator to cudaMalloc (tens of ms).  The buffer
+    is only touched by kernels on the stream it is keyed by, so back-to-back calls serialise on it naturally."""
+    key = (str(device), torch.cuda.current_stream(device).cuda_stream, tag)
+    buf = _SCRATCH.get(key)
+    if buf is None or buf.numel() < nbytes:
+        _SCRATCH[key] = buf = torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=device)
+    return buf
+
+
 def _c(t, dtype=None):
     """contiguous (and optionally cast) view/copy"""
     if dtype is not None and t.dtype != dtype:
@@ -101,7 +115,7 @@ def ode_bwd(P, mlp, y, yh, zh, tf, g_ys, g_z, need_inputs=True, need_params=True
         gp = [torch.empty_like(t) for t in (keep.W1, keep.b1, keep.W2, keep.b2)]
     with torch.cuda.device(dev):
         nbytes = _kc.lib().kc_ode_bwd_workspace_bytes(_dtype_code(y), mref, Q)
-        ws = torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=dev)
+        ws = _scratch(dev, nbytes, "ode_bwd")
         rc = _kc.lib().kc_ode_bwd(_dtype_code(y), C.byref(P), mref, Q, _ptr(y), _ptr(yh), _ptr(zh), _ptr(tf),
                                   _ptr(g_ys), _ptr(g_z), *[_ptr(t) for t in gi], *[_ptr(t) for t in gp], _ptr(ws),
                                   int(nbytes), _stream(dev))
@@ -132,7 +146,7 @@ def mlp_bwd(mlp, x, g_out, need_input=True, need_params=True):
     gp = [torch.empty_like(t) for t in (m.W1, m.b1, m.W2, m.b2)] if need_params else [None] * 4
     with torch.cuda.device(x.device):
         nbytes = int(_kc.lib().kc_ode_bwd_workspace_bytes(_dtype_code(x), m.ref(), Q))
-        ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=x.device)
+        ws = _scratch(x.device, nbytes, "mlp_bwd")
         rc = _kc.lib().kc_mlp_bwd(_dtype_code(x), m.ref(), Q, _ptr(x), _ptr(g_out), _ptr(gx), *[_ptr(t) for t in gp],
                                   _ptr(ws), nbytes, _stream(x.device))
     _kc.check(rc, "kc_mlp_bwd")
@@ -302,7 +316,7 @@ def rollout_bwd(P, mlp, tensions, traj, g_traj, want_g_tensions=True, want_param
         gp = [torch.empty_like(t) for t in (keep.W1, keep.b1, keep.W2, keep.b2)]
     with torch.cuda.device(dev):
         nbytes = int(_kc.lib().kc_rollout_bwd_workspace_bytes(_dtype_code(traj), C.byref(P), mref, B, T))
-        ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=dev)
+        ws = _scratch(dev, nbytes, "rollout_bwd")
         rc = _kc.lib().kc_rollout_bwd(_dtype_code(traj), C.byref(P), mref, B, T, _ptr(tensions), _ptr(traj), _ptr(g_traj),
                                       _ptr(gt), *[_ptr(g) for g in gp], _ptr(ws), nbytes, _stream(dev))
     _kc.check(rc, "kc_rollout_bwd")
@@ -324,7 +338,7 @@ def train_step(P, mlp, traj, controls, key_idx, want_pred=False):
     pred = torch.empty((B, T - 1, 25, K), dtype=dt, device=dev) if want_pred else None
     with torch.cuda.device(dev):
         nbytes = int(_kc.lib().kc_train_step_workspace_bytes(_dtype_code(traj), mref, B, T, K))
-        ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=dev)
+        ws = _scratch(dev, nbytes, "train_step")
         rc = _kc.lib().kc_train_step(_dtype_code(traj), C.byref(P), mref, B, T, K,
                                      ki.ctypes.data_as(C.POINTER(C.c_int32)), _ptr(traj), _ptr(controls),
                                      _ptr(loss), *[_ptr(g) for g in grads], _ptr(pred), _ptr(ws), nbytes, _stream(dev))

@@ -115,7 +115,7 @@ bool kc_tc_forward_ok(const kc_mlp* mlp, int64_t Q);
 int kc_train_tc_grid(int64_t Q);
 int kc_tc_launch_mode(int mode, const kc_mlp* mlp, float ds, int64_t Q, int T_, int K, const float* X, const float* PHYS,
                       const float* TGT, float* W1hl, float* W2c_, float* partial, int64_t NP, double* loss_part,
-                      float* pred_out, const float* dOin, int grid, cudaStream_t st, int xpitch = 32);
+                      float* pred_out, const float* dOin, int grid, cudaStream_t st, int xpitch = 32, int dopitch = 32);
 
 template <typename T, bool DIAG>
 __global__ void __launch_bounds__(ODE_THREADS)
@@ -164,7 +164,7 @@ int ode_fwd_tc<float>(const RodC<float>& P, const kc_mlp* mlp, int64_t Q, const 
                       const void* tf, void* ys, void* z, cudaStream_t st) {
     if (!kc_tc_forward_ok(mlp, Q)) return 1;   // 1: not taken
     if (int rc = kc_check_mlp(mlp)) return rc;
-    const size_t tcw_b = (size_t)4 * (2 * 128 * 32 * 4 + 32768);
+    const size_t tcw_b = (size_t)4 * (2 * 128 * 32 * 4 + 32768 + 16384);
     const size_t xb = ((size_t)Q * 32 * 4 + 255) & ~(size_t)255, pb = ((size_t)Q * 25 * 4 + 255) & ~(size_t)255;
     unsigned char* buf = (unsigned char*)kc_tc_scratch(tcw_b + 2048 + xb + pb);
     if (!buf) { kc_set_error("cudaMalloc of the tensor-core scratch failed"); return KC_ECUDA; }

@@ -4,12 +4,16 @@
 // parameter cotangents are wanted, the kernel also emits X[Q][XPG] and dO[Q][32] and the train-step kernels 3+4 reduce
 // them to gW1, gb1, gW2, gb2.
 
-template <typename T, bool DIAG, int IN>
+// PH 0: everything in one kernel (SIMT MLP input VJP).  PH 1 / 2: the tensor-core split — PH 1 only emits X and dO (the
+// samples the tcgen05 kernels consume), PH 2 takes the MLP input cotangent gx from GX[Q][32] (kc_train_tc_kernel<3>) and
+// finishes with the physics adjoint.
+template <typename T, bool DIAG, int IN, int PH = 0>
 __global__ void __launch_bounds__(128)
 kc_ode_bwd_kernel(const __grid_constant__ RodC<T> P, const MlpC<T> M, int64_t Q, const T* __restrict__ y,
                   const T* __restrict__ yh, const T* __restrict__ zh, const T* __restrict__ tf,
                   const T* __restrict__ g_ys, const T* __restrict__ g_z, T* __restrict__ g_y, T* __restrict__ g_yh,
-                  T* __restrict__ g_zh, T* __restrict__ g_tf, T* __restrict__ X, int XPG, T* __restrict__ dO) {
+                  T* __restrict__ g_zh, T* __restrict__ g_tf, T* __restrict__ X, int XPG, T* __restrict__ dO,
+                  const T* __restrict__ GX = nullptr) {
     const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= Q) return;
     T ry[19], rh[25], rt[3], gys[19], gz[6];
@@ -52,7 +56,7 @@ kc_ode_bwd_kernel(const __grid_constant__ RodC<T> P, const MlpC<T> M, int64_t Q,
         for (int i = 0; i < 19; ++i) go[i] = gys[i];
 #pragma unroll
         for (int i = 0; i < 6; ++i) go[19 + i] = gz[i];
-        if (X) {
+        if (X && PH != 2) {
 #pragma unroll
             for (int i = 0; i < INX; ++i) X[(size_t)q * XPG + i] = x[i];
             for (int i = INX; i < XPG; ++i) X[(size_t)q * XPG + i] = T(0);
@@ -61,7 +65,13 @@ kc_ode_bwd_kernel(const __grid_constant__ RodC<T> P, const MlpC<T> M, int64_t Q,
 #pragma unroll
             for (int i = 25; i < 32; ++i) dO[(size_t)q * 32 + i] = T(0);
         }
-        mlp_input_vjp<T, INX>(M, x, go, gx);
+        if (PH == 1) return;
+        if (PH == 2) {
+#pragma unroll
+            for (int i = 0; i < INX; ++i) gx[i] = GX[(size_t)q * 32 + i];
+        } else {
+            mlp_input_vjp<T, INX>(M, x, go, gx);
+        }
         if (IN == 28) {
 #pragma unroll
             for (int i = 0; i < 19; ++i) gy_nn[i] = gx[i];
@@ -109,22 +119,39 @@ kc_ode_bwd_kernel(const __grid_constant__ RodC<T> P, const MlpC<T> M, int64_t Q,
 // to the SIMT kernel.  slices = number of partial-gradient slices written (< 0: launch error).
 int kc_tc_launch_mode(int mode, const kc_mlp* mlp, float ds, int64_t Q, int T_, int K, const float* X, const float* PHYS,
                       const float* TGT, float* W1hl, float* W2c_, float* partial, int64_t NP, double* loss_part,
-                      float* pred_out, const float* dOin, int grid, cudaStream_t st, int xpitch = 32);
+                      float* pred_out, const float* dOin, int grid, cudaStream_t st, int xpitch = 32, int dopitch = 32);
 template <typename T>
 static bool kc_param_grads_tc(const kc_mlp*, int64_t, const T*, const T*, T*, const TrainWs&, unsigned char*, cudaStream_t,
-                              int&) { return false; }
+                              int&, int = 32, int = 32) { return false; }
 template <>
 bool kc_param_grads_tc<float>(const kc_mlp* mlp, int64_t Q, const float* X, const float* dO, float* part, const TrainWs& t,
-                              unsigned char* ws, cudaStream_t st, int& slices) {
+                              unsigned char* ws, cudaStream_t st, int& slices, int xpitch, int dopitch) {
     if (mlp->in_dim != 28 || mlp->hidden > 512 || Q < 4096) return false;
     const char* e = getenv("KC_TRAIN_MODE");
     if (e && e[0] == 's') return false;
     float* tcw = (float*)(ws + t.tcw);
     slices = kc_train_tc_grid(Q);
     const int rc = kc_tc_launch_mode(2, mlp, 1.f, Q, 2, 1, X, nullptr, nullptr, tcw, tcw + 4 * 2 * 128 * 32, part, t.NP,
-                                     (double*)(ws + t.lossp), nullptr, dO, slices, st);
+                                     (double*)(ws + t.lossp), nullptr, dO, slices, st, xpitch, dopitch);
     if (rc) slices = -1;
     return true;
+}
+
+// MLP input gradients on the tensor cores (kc_train_tc_kernel<3>): gx[Q][gxpitch] from x[Q][xpitch], dO[Q][dopitch]
+template <typename T>
+static int kc_input_grads_tc(const kc_mlp*, int64_t, const T*, int, const T*, int, T*, int, const TrainWs&, unsigned char*,
+                             cudaStream_t) { return 1; }
+template <>
+int kc_input_grads_tc<float>(const kc_mlp* mlp, int64_t Q, const float* X, int xpitch, const float* dO, int dopitch,
+                             float* gx, int gxpitch, const TrainWs& t, unsigned char* ws, cudaStream_t st) {
+    float* tcw = (float*)(ws + t.tcw);
+    return kc_tc_launch_mode(3, mlp, 1.f, Q, 2, gxpitch, X, nullptr, nullptr, tcw, tcw + 4 * 2 * 128 * 32, nullptr, 0,
+                             (double*)(ws + t.lossp), gx, dO, kc_train_tc_grid(Q), st, xpitch, dopitch);
+}
+static bool kc_tc_bwd_ok(const kc_mlp* mlp, int64_t Q, bool is_float) {
+    if (!is_float || !mlp || mlp->in_dim != 28 || mlp->hidden > 512 || Q < 4096) return false;
+    const char* e = getenv("KC_TRAIN_MODE");
+    return !(e && e[0] == 's');
 }
 
 struct OdeBwdWs { size_t X, dO, part, wp, total; TrainWs t; };
@@ -154,12 +181,29 @@ static int ode_bwd_typed(const kc_rod_params* Pp, const kc_mlp* mlp, int64_t Q, 
     const int in_dim = mlp ? mlp->in_dim : 0;
     const bool want_params = mlp && (gW1 || gb1 || gW2 || gb2);
     T* X = nullptr; T* dO = nullptr;
+    const bool tc = kc_tc_bwd_ok(mlp, Q, sizeof(T) == 4);
     if (mlp) {
-        int rc = kc_pack_mlp<T>(mlp, (T*)(ws + w.wp), M, st);
-        if (rc) return rc;
-        if (want_params) { X = (T*)(ws + w.X); dO = (T*)(ws + w.dO); }
+        if (!tc) {
+            int rc = kc_pack_mlp<T>(mlp, (T*)(ws + w.wp), M, st);
+            if (rc) return rc;
+        }
+        if (want_params || tc) { X = (T*)(ws + w.X); dO = (T*)(ws + w.dO); }
     }
-    if (Q > 0) {
+    if (Q > 0 && tc) {
+        // tensor-core split: samples -> (parameter gradients below) + input gradients -> physics adjoint
+        const unsigned grid = (unsigned)((Q + 127) / 128);
+        T* GX = (T*)(ws + w.t.PHYS);   // Q x 32 scratch: the PHYS | TGT regions of the training workspace are contiguous
+#define BWD1(D) kc_ode_bwd_kernel<T, D, 28, 1><<<grid, 128, 0, st>>>(P, M, Q, (const T*)y, (const T*)yh, (const T*)zh, (const T*)tf, (const T*)g_ys, (const T*)g_z, nullptr, nullptr, nullptr, nullptr, X, w.t.XPG, dO)
+        if (P.diag) BWD1(true); else BWD1(false);
+#undef BWD1
+        KC_CHECK_LAUNCH("kc_ode_bwd_kernel<1>");
+        const int rc = kc_input_grads_tc<T>(mlp, Q, X, 32, dO, 32, GX, 32, w.t, ws, st);
+        if (rc) return rc < 0 ? rc : KC_ECUDA;
+#define BWD2(D) kc_ode_bwd_kernel<T, D, 28, 2><<<grid, 128, 0, st>>>(P, M, Q, (const T*)y, (const T*)yh, (const T*)zh, (const T*)tf, (const T*)g_ys, (const T*)g_z, (T*)g_y, (T*)g_yh, (T*)g_zh, (T*)g_tf, X, w.t.XPG, dO, GX)
+        if (P.diag) BWD2(true); else BWD2(false);
+#undef BWD2
+        KC_CHECK_LAUNCH("kc_ode_bwd_kernel<2>");
+    } else if (Q > 0) {
         const unsigned grid = (unsigned)((Q + 127) / 128);
         const int XPG = mlp ? w.t.XPG : 0;
 #define BWD(D, I) kc_ode_bwd_kernel<T, D, I><<<grid, 128, 0, st>>>(P, M, Q, (const T*)y, (const T*)yh, (const T*)zh, (const T*)tf, (const T*)g_ys, (const T*)g_z, (T*)g_y, (T*)g_yh, (T*)g_zh, (T*)g_tf, X, XPG, dO)
@@ -275,13 +319,13 @@ bool kc_tc_forward_ok(const kc_mlp* mlp, int64_t Q) {
     const char* e = getenv("KC_TRAIN_MODE");
     return !(e && e[0] == 's');
 }
-constexpr size_t KC_TCW_BYTES = (size_t)4 * (2 * 128 * 32 * 4 + 32768);   // weight images of kc_tc_prep_weights_kernel
+constexpr size_t KC_TCW_BYTES = (size_t)4 * (2 * 128 * 32 * 4 + 32768 + 16384);   // weight images of kc_tc_prep_weights_kernel
 
 template <typename T>
 static int mlp_fwd_tc(const kc_mlp*, int64_t, const void*, void*, cudaStream_t) { return 1; }
 template <>
 int mlp_fwd_tc<float>(const kc_mlp* mlp, int64_t Q, const void* x, void* out, cudaStream_t st) {
-    if (!kc_tc_forward_ok(mlp, Q)) return 1;   // 1: not taken
+    if (!kc_tc_forward_ok(mlp, Q) || ((uintptr_t)x & 15) != 0) return 1;   // 1: not taken
     float* tcw = (float*)kc_tc_scratch(KC_TCW_BYTES + 256 * sizeof(double));
     if (!tcw) { kc_set_error("cudaMalloc of the tensor-core scratch failed"); return KC_ECUDA; }
     // forward-only mode: out[Q][25] = W2 ELU(W1 x + b1) + b2, x rows 28 floats apart
@@ -330,13 +374,30 @@ static int mlp_bwd_typed(const kc_mlp* mlp, int64_t Q, const void* x, const void
                          void* gW2, void* gb2, void* workspace, cudaStream_t st) {
     const OdeBwdWs w = ode_bwd_ws(sizeof(T) == 4 ? KC_F32 : KC_F64, mlp, Q);
     unsigned char* ws = (unsigned char*)workspace;
+    const bool want_params = gW1 || gb1 || gW2 || gb2;
+    const int in_dim = mlp->in_dim;
+    if (Q > 0 && kc_tc_bwd_ok(mlp, Q, sizeof(T) == 4) && ((uintptr_t)x & 15) == 0) {   // (16-byte loads of x rows)
+        // tensor cores straight on the caller's arrays: x rows 28 apart, g_out rows 25 apart, g_x rows 28 apart
+        if (g_x) {
+            const int rc = kc_input_grads_tc<T>(mlp, Q, (const T*)x, 28, (const T*)g_out, 25, (T*)g_x, 28, w.t, ws, st);
+            if (rc) return rc < 0 ? rc : KC_ECUDA;
+        }
+        if (want_params) {
+            T* part = (T*)(ws + w.part);
+            int slices = 0;
+            kc_param_grads_tc<T>(mlp, Q, (const T*)x, (const T*)g_out, part, w.t, ws, st, slices, 28, 25);
+            if (slices <= 0) return KC_ECUDA;
+            kc_train_reduce_kernel<T><<<(unsigned)((w.t.NP + 63) / 64), 256, 0, st>>>(part, slices, w.t.NP, mlp->hidden, in_dim,
+                                                                                      (T*)gW1, (T*)gb1, (T*)gW2, (T*)gb2, nullptr, 0, nullptr);
+            KC_CHECK_LAUNCH("kc_train_reduce_kernel");
+        }
+        return KC_OK;
+    }
     MlpC<T> M;
     int rc = kc_pack_mlp<T>(mlp, (T*)(ws + w.wp), M, st);
     if (rc) return rc;
-    const bool want_params = gW1 || gb1 || gW2 || gb2;
     T* X = want_params ? (T*)(ws + w.X) : nullptr;
     T* dO = want_params ? (T*)(ws + w.dO) : nullptr;
-    const int in_dim = mlp->in_dim;
     if (Q > 0) {
         const unsigned grid = (unsigned)((Q + 127) / 128);
         if (in_dim == 28) kc_mlp_bwd_kernel<T, 28><<<grid, 128, 0, st>>>(M, Q, (const T*)x, (const T*)g_out, (T*)g_x, X, w.t.XPG, dO);

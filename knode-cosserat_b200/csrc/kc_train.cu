@@ -396,7 +396,7 @@ static TrainWs train_ws(int dtype, const kc_mlp* mlp, int64_t Q) {
     w.lossp = off; off += al256((size_t)std::max(w.nfwd, 160) * 8);
     w.part = off; off += al256((size_t)std::max(splits, 160) * w.NP * sz);   // >= one slice per SM for the tensor-core path
     w.wp = off; off += al256((size_t)mlp->hidden * (((mlp->in_dim + 3) & ~3) + 32) * sz);
-    w.tcw = off; off += al256((size_t)4 * (2 * 128 * 32 * 4 + 32768));   // tensor-core path: split / transposed weights
+    w.tcw = off; off += al256((size_t)4 * (2 * 128 * 32 * 4 + 32768 + 16384));   // tensor-core path: split / transposed weights
     w.total = off;
     return w;
 }

@@ -112,9 +112,21 @@ __global__ void kc_tc_prep_weights_kernel(const float* __restrict__ W1, const fl
         const uint32_t ob = kmajor_off_b16(ul, co, 32);    // backward: rows = units, k = outputs
         *reinterpret_cast<__nv_bfloat16*>(base + 16384 + ob) = __float2bfloat16_rn(wh);
         *reinterpret_cast<__nv_bfloat16*>(base + 16384 + 8192 + ob) = __float2bfloat16_rn(wl);
+        // W1 chunk as the B operand of the input-gradient GEMM gX += dZ W1c: [32 inputs x 128 units] K-major (the same
+        // format as the forward W2 image); input columns 28..31 (bias, padding) are zero
+        {
+            const float w1 = (u < hidden && k < 28) ? W1[(size_t)u * 28 + k] : 0.f;
+            float h1, l1;
+            split_bf16(w1, h1, l1);
+            unsigned char* b1t = W2b + (size_t)4 * tc::W2B_CHUNK_BYTES + (size_t)c * 16384;
+            *reinterpret_cast<__nv_bfloat16*>(b1t + of) = __float2bfloat16_rn(h1);
+            *reinterpret_cast<__nv_bfloat16*>(b1t + 8192 + of) = __float2bfloat16_rn(l1);
+        }
     }
 }
 
+// MODE 3: INPUT gradients only, gX[Q][gxpitch] = ((dOin W2) * ELU'(X W1^T + b1)) W1 (gxpitch passed in K, output in
+// pred_out) — the MLP part of kc_ode_bwd / kc_mlp_bwd.
 // MODE 0: the full training step.  MODE 1: forward only — pred_out[Q][25] = PHYS + s*o (s = ds for rows < 19, 1 for the
 // rest; kc_ode_fwd / kc_mlp_fwd pass ds = 1 and PHYS = the physics part or zeros).  MODE 2: parameter gradients only from
 // given samples (X, dOin[Q][32]) — kc_mlp_bwd / kc_ode_bwd and the sample reduction of kc_rollout_bwd.
@@ -124,7 +136,7 @@ kc_train_tc_kernel(int hidden, int nch, const float* __restrict__ W1hl, const un
                    const float* __restrict__ b2, float ds, int64_t Q, int T_, int K, const float* __restrict__ X,
                    const float* __restrict__ PHYS, const float* __restrict__ TGT, float* __restrict__ partial,
                    int64_t NP, double* __restrict__ loss_part, float* __restrict__ pred_out,
-                   const float* __restrict__ dOin, int xpitch) {
+                   const float* __restrict__ dOin, int xpitch, int dopitch) {
     extern __shared__ __align__(1024) unsigned char sm[];
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + tc::OFF_MISC);
     uint64_t* barZ = reinterpret_cast<uint64_t*>(sm + tc::OFF_MISC + 8);
@@ -176,6 +188,10 @@ kc_train_tc_kernel(int hidden, int nch, const float* __restrict__ W1hl, const un
     auto fetch_w2 = [&](int c, int pass, int stage) {
         bulk_g2s((stage & 1) ? aWB1 : aWB0, W2b + (size_t)c * tc::W2B_CHUNK_BYTES + (pass == 2 ? 16384 : 0), 16384, barW);
     };
+    auto fetch_w1t = [&](int c, int stage) {   // MODE 3: W1^T image -> OFF_A (+16 KB for odd stages)
+        bulk_g2s(aAh + ((stage & 1) ? 16384u : 0u), W2b + (size_t)4 * tc::W2B_CHUNK_BYTES + (size_t)c * 16384, 16384, barW);
+    };
+    constexpr uint32_t WBYTES = 32768 + 16384 + (MODE == 3 ? 16384 : 0);   // bytes per stage on barW
     auto issue_gemm1 = [&]() {  // Z[128 samples x 128 units] = X W1c^T, 3-pass tf32 split, K = 32 (4 x K8)
         uint32_t acc = 0;
 #pragma unroll
@@ -244,6 +260,23 @@ kc_train_tc_kernel(int hidden, int nch, const float* __restrict__ W1hl, const un
         umma::commit(barG);
     };
 
+    // MODE 3: gX[128 samples x 32 inputs] += dZ[samples x 128 units] W1c: A = the dZ tile viewed K-major (as the activation
+    // tile in GEMM2), B = the W1^T image; the pass that reads dZ lo goes first and commits barL (its bytes take the next W1)
+    auto issue_gemm4 = [&](bool first_chunk, uint32_t aW1T) {
+        uint32_t acc = first_chunk ? 0u : 1u;
+        for (int kk = 0; kk < 8; ++kk) {
+            umma::mma_bf16(tbase + tc::COL_GW1, umma::make_desc(aDZl + kk * 4096, 2048, 128), umma::make_desc(aW1T + kk * 256, 128, 2048), idescO, acc);
+            acc = 1;
+        }
+        umma::commit(barL);
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            const uint32_t b = p == 0 ? aW1T : aW1T + 8192;
+            for (int kk = 0; kk < 8; ++kk)
+                umma::mma_bf16(tbase + tc::COL_GW1, umma::make_desc(aDZh + kk * 4096, 2048, 128), umma::make_desc(b + kk * 256, 128, 2048), idescO, 1u);
+        }
+        umma::commit(barG);
+    };
     float gb2acc[25];
 #pragma unroll
     for (int c = 0; c < 25; ++c) gb2acc[c] = 0.f;
@@ -252,9 +285,10 @@ kc_train_tc_kernel(int hidden, int nch, const float* __restrict__ W1hl, const un
     bool first_tile = true;
     int gs = 0;   // running stage count: the W2 image buffers alternate by it (any number of stages per tile)
     if (tid == 0 && blockIdx.x < ntiles) {   // stage 0 of the first tile
-        mbar_expect_tx(barW, 32768 + 16384);
+        mbar_expect_tx(barW, WBYTES);
         fetch_w1(0);
-        fetch_w2(0, MODE == 2 ? 2 : 1, 0);
+        fetch_w2(0, MODE >= 2 ? 2 : 1, 0);
+        if (MODE == 3) fetch_w1t(0, 0);
     }
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t q = tile * tc::TS + row;
@@ -298,7 +332,7 @@ kc_train_tc_kernel(int hidden, int nch, const float* __restrict__ W1hl, const un
         umma::fence_async_smem();       // the X tile
         umma::fence_before();
         __syncthreads();
-        if (MODE != 2) {
+        if (MODE < 2) {
         for (int c = 0; c < nch; ++c, ++gs) {
             const int stage = gs;
             umma::mbar_wait(barW, phW); phW ^= 1;                     // W1(c), W2 fwd image(c) have landed
@@ -340,7 +374,7 @@ kc_train_tc_kernel(int hidden, int nch, const float* __restrict__ W1hl, const un
         // ---- loss and dL/do (rows of half 0 own the sample) ----
         if (half == 0) {
             float o[25], g[25];
-            if (MODE != 2) {
+            if (MODE < 2) {
                 uint32_t v[32];
                 umma::ld32(tbase + laneblk + tc::COL_O, v);
                 umma::wait_ld();
@@ -348,7 +382,7 @@ kc_train_tc_kernel(int hidden, int nch, const float* __restrict__ W1hl, const un
                 for (int c = 0; c < 25; ++c) { o[c] = __uint_as_float(v[c]) + b2[c]; g[c] = 0.f; }
             } else {
 #pragma unroll
-                for (int c = 0; c < 25; ++c) { o[c] = 0.f; g[c] = valid ? dOin[(size_t)q * 32 + c] : 0.f; }
+                for (int c = 0; c < 25; ++c) { o[c] = 0.f; g[c] = valid ? dOin[(size_t)q * dopitch + c] : 0.f; }
             }
             if (MODE == 1) {   // pred = PHYS (or 0) + s*o -> pred_out[Q][25], or split as ys[Q][19] | z[Q][6] (z = `partial`)
                 if (valid) {
@@ -434,9 +468,10 @@ kc_train_tc_kernel(int hidden, int nch, const float* __restrict__ W1hl, const un
             umma::fence_after();
             const bool prefetch = c + 1 < nch || more_tiles;
             if (tid == 0 && prefetch) {   // the other W2 buffer is free now; W1 follows once the dZ-lo MMAs of this chunk are done
-                mbar_expect_tx(barW, 32768 + 16384);
+                mbar_expect_tx(barW, WBYTES);
                 if (c + 1 < nch) fetch_w2(c + 1, 2, stage + 1);
-                else fetch_w2(0, MODE == 2 ? 2 : 1, stage + 1);
+                else fetch_w2(0, MODE >= 2 ? 2 : 1, stage + 1);
+                if (MODE == 3) fetch_w1t(c + 1 < nch ? c + 1 : 0, stage + 1);   // (the W1^T buffer of stage-1 is free: barG waited)
             }
 #pragma unroll 1
             for (int cc = 0; cc < 2; ++cc) {
@@ -456,11 +491,13 @@ kc_train_tc_kernel(int hidden, int nch, const float* __restrict__ W1hl, const un
                         d8[j] = __uint_as_float(d[g8 * 8 + j]) * (z > 0.f ? 1.f : a + 1.f);
                     }
                     uint4 ah, al, dh, dl;
-                    split_pack8(a8, ah, al);
                     split_pack8(d8, dh, dl);
                     const uint32_t off = umma::mnmajor_off_b16(half * 64 + cc * 32 + g8 * 8, row, 128);
-                    *reinterpret_cast<uint4*>(sm + tc::OFF_A + off) = ah;
-                    *reinterpret_cast<uint4*>(sm + tc::OFF_A + 32768 + off) = al;
+                    if (MODE != 3) {   // (MODE 3 keeps the W1^T images in the activation-tile region)
+                        split_pack8(a8, ah, al);
+                        *reinterpret_cast<uint4*>(sm + tc::OFF_A + off) = ah;
+                        *reinterpret_cast<uint4*>(sm + tc::OFF_A + 32768 + off) = al;
+                    }
                     *reinterpret_cast<uint4*>(sm + tc::OFF_DZ + off) = dh;
                     *reinterpret_cast<uint4*>(sm + tc::OFF_DZ + 32768 + off) = dl;
                 }
@@ -470,7 +507,8 @@ kc_train_tc_kernel(int hidden, int nch, const float* __restrict__ W1hl, const un
             __syncthreads();
             if (tid == 0) {
                 umma::fence_after();
-                issue_grads(c, first_tile);
+                if (MODE == 3) issue_gemm4(c == 0, aAh + ((stage & 1) ? 16384u : 0u));
+                else issue_grads(c, first_tile);
                 umma::mbar_wait(barL, phL);                           // dZ lo consumed: its bytes may take the next W1 chunk
                 if (prefetch) fetch_w1(c + 1 < nch ? c + 1 : 0);
             }
@@ -478,10 +516,20 @@ kc_train_tc_kernel(int hidden, int nch, const float* __restrict__ W1hl, const un
         }
         umma::mbar_wait(barG, phG); phG ^= 1;   // last chunk's gradient MMAs: they read X^T / dO^T which the next tile overwrites
         umma::fence_after();
+        if (MODE == 3 && half == 0) {   // this tile's input gradients
+            uint32_t v[32];
+            umma::ld32(tbase + laneblk + tc::COL_GW1, v);
+            umma::wait_ld();
+            if (valid) {
+#pragma unroll
+                for (int k = 0; k < 28; ++k) pred_out[(size_t)q * K + k] = __uint_as_float(v[k]);
+            }
+        }
+        if (MODE == 3) { umma::fence_before(); __syncthreads(); umma::fence_after(); }   // gX is overwritten by the next tile
         }
         first_tile = false;
     }
-    if (MODE == 1) {   // forward only: no gradients to write
+    if (MODE == 1 || MODE == 3) {   // no parameter gradients to write
         umma::fence_before();
         __syncthreads();
         if (warp == 0) umma::tmem_dealloc(tbase, 512);
@@ -537,7 +585,7 @@ kc_train_tc_kernel(int hidden, int nch, const float* __restrict__ W1hl, const un
 // bytes (workspace), partial: grid*NP floats, loss_part: grid doubles.
 int kc_tc_launch_mode(int mode, const kc_mlp* mlp, float ds, int64_t Q, int T_, int K, const float* X, const float* PHYS,
                       const float* TGT, float* W1hl, float* W2c_, float* partial, int64_t NP, double* loss_part,
-                      float* pred_out, const float* dOin, int grid, cudaStream_t st, int xpitch = 32);
+                      float* pred_out, const float* dOin, int grid, cudaStream_t st, int xpitch = 32, int dopitch = 32);
 int kc_train_tc_grid(int64_t Q) {
     const int64_t ntiles = (Q + tc::TS - 1) / tc::TS;
     int dev = 0, sms = 148;
@@ -556,7 +604,7 @@ int kc_train_tc_launch(const kc_mlp* mlp, float ds, int64_t Q, int T_, int K, co
 // mode 0: training step; 1: forward only (pred_out[Q][25] = PHYS + s*o); 2: parameter gradients from (X, dOin) samples
 int kc_tc_launch_mode(int mode, const kc_mlp* mlp, float ds, int64_t Q, int T_, int K, const float* X, const float* PHYS,
                       const float* TGT, float* W1hl, float* W2c_, float* partial, int64_t NP, double* loss_part,
-                      float* pred_out, const float* dOin, int grid, cudaStream_t st, int xpitch) {
+                      float* pred_out, const float* dOin, int grid, cudaStream_t st, int xpitch, int dopitch) {
     const int nch = (mlp->hidden + tc::HC - 1) / tc::HC;
     unsigned char* W2b = reinterpret_cast<unsigned char*>(W2c_);
     kc_tc_prep_weights_kernel<<<dim3(nch, 8), 256, 0, st>>>((const float*)mlp->W1, (const float*)mlp->b1,
@@ -566,9 +614,9 @@ int kc_tc_launch_mode(int mode, const kc_mlp* mlp, float ds, int64_t Q, int T_, 
     do {                                                                                                               \
         cudaFuncSetAttribute(kc_train_tc_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);      \
         kc_train_tc_kernel<M><<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(mlp->hidden, nch, W1hl, W2b,                  \
-            (const float*)mlp->b2, ds, Q, T_, K, X, PHYS, TGT, partial, NP, loss_part, pred_out, dOin, xpitch);        \
+            (const float*)mlp->b2, ds, Q, T_, K, X, PHYS, TGT, partial, NP, loss_part, pred_out, dOin, xpitch, dopitch);\
     } while (0)
-    if (mode == 0) KC_TC_GO(0); else if (mode == 1) KC_TC_GO(1); else KC_TC_GO(2);
+    if (mode == 0) KC_TC_GO(0); else if (mode == 1) KC_TC_GO(1); else if (mode == 2) KC_TC_GO(2); else KC_TC_GO(3);
 #undef KC_TC_GO
     KC_CHECK_LAUNCH("kc_train_tc_kernel");
     return KC_OK;

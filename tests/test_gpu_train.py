@@ -287,3 +287,34 @@ def test_forward_tensor_core_vs_simt_and_fp64(ops, monkeypatch, H):
 def col_err(a, b, floor=1e-3):
     scale = np.abs(b).reshape(-1, b.shape[-1]).max(0) + floor
     return float(np.max(np.abs(a - b) / scale))
+
+
+@pytest.mark.parametrize("H", [512, 200])
+def test_ode_bwd_tensor_core_vs_simt_and_fp64(ops, monkeypatch, H):
+    """kc_ode_bwd / kc_mlp_bwd with >= 4096 samples: MLP input gradients (kc_train_tc_kernel<3>) and parameter gradients
+    (<2>) on tcgen05 around the SIMT physics adjoint; same numbers as the all-SIMT path and as fp64."""
+    rng = np.random.default_rng(300 + H)
+    Q = 4500 + 13
+    W = [rng.normal(0, 0.3, (H, 28)), rng.normal(0, 0.1, H), rng.normal(0, 0.05, (25, H)), rng.normal(0, 0.1, 25)]
+    y = rng.normal(0, 1.0, (Q, 19)); y[:, 3] += 2.0
+    yh, zh, tf = rng.normal(0, 1.0, (Q, 19)), rng.normal(0, 1.0, (Q, 6)), rng.normal(0, 1.0, (Q, 3))
+    gys, gz = rng.normal(0, 1.0, (Q, 19)), rng.normal(0, 1.0, (Q, 6))
+    P = params(P_setup())
+
+    def run(dt, mode):
+        if mode:
+            monkeypatch.setenv("KC_TRAIN_MODE", mode)
+        else:
+            monkeypatch.delenv("KC_TRAIN_MODE", raising=False)
+        mlp = ops.Mlp(*[dev(w, dt) for w in W])
+        out = ops.ode_bwd(P, mlp, dev(y, dt), dev(yh, dt), dev(zh, dt), dev(tf, dt), dev(gys, dt), dev(gz, dt))
+        return [t.cpu().numpy().astype(np.float64) for t in out]
+
+    ref = run(torch.float64, None)
+    simt = run(torch.float32, "simt")
+    tc = run(torch.float32, None)
+    names = ("g_y", "g_yh", "g_zh", "g_tf") + PK
+    for name, r, a, b in zip(names, ref, simt, tc):
+        scale = np.abs(r).max() + 1e-30
+        assert np.abs(a - r).max() < 2e-4 * scale, (name, "simt", np.abs(a - r).max() / scale)
+        assert np.abs(b - r).max() < 2e-4 * scale, (name, "tc", np.abs(b - r).max() / scale)

@@ -16,7 +16,7 @@ with torch.no_grad():
     robot.nn_models[2].weight.mul_(0.02); robot.nn_models[2].bias.mul_(0.02)
 ctl = torch.tensor(synthetic_tensions(B, T, robot.del_t, seed=0), device="cuda")
 P = robot._params(); mlp = robot._mlp()
-for rep in range(2):
+for rep in range(int(os.environ.get('REPS', '2'))):
     e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     e[0].record()
     traj, _, iters = _ops.rollout(P, mlp, ctl, rows=25)
@@ -24,5 +24,6 @@ for rep in range(2):
     g = torch.ones_like(traj) * 1e-3
     out = _ops.rollout_bwd(P, mlp, ctl, traj, g)
     e[2].record(); torch.cuda.synchronize()
+    if os.environ.get('VERBOSE'): print('rep %d fwd %.2f bwd %.2f' % (rep, e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2])))
 it = iters[:, 1:].abs().float()
 print("ok fwd %.2f ms  bwd %.2f ms  converged %s  |gW1| %.3e  marches/step mean %.2f max %d" % (e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2]), bool((iters >= 0).all()), float(out[1].abs().max()), float(it.mean()), int(it.max())))
