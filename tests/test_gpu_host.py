@@ -143,3 +143,20 @@ def test_host_rollout_edge_sizes_and_knode(ops, golden):
     got = hp.run(ctl)
     assert int(it.min()) >= 0
     np.testing.assert_array_equal(got.numpy(), ref.cpu().numpy())
+
+
+def test_simulate_500_steps_against_the_reference(ops, golden):
+    """Drop-in call with the reference's own signature (knode.simulate(robot, ctl[T,4]) -> float64 [T,50,N]) over the 500
+    time indices of BASELINE config 5, against the unmodified reference (tests/golden/make_long_rollout.py); the host path
+    solves the rollout in several time ranges, so the range hand-over is crossed repeatedly."""
+    from cosserat_ode import CosseratRod
+    from knode import setup_robot, simulate
+    d = golden["long_rollout"]
+    robot = CosseratRod(use_fsolve=True)
+    setup_robot(robot)
+    for r in range(2):
+        got = simulate(robot, d["controls"][r])
+        assert got.shape == (500, 50, robot.N) and got.dtype == np.float64
+        want = d["traj"][r]
+        scale = np.abs(want).max(axis=(0, 2), keepdims=True) + 1e-12
+        assert float(np.max(np.abs(got[d["keep"], :25] - want) / scale)) < 1e-9

@@ -237,3 +237,15 @@ def test_rollout_other_node_counts(ops, mode, dt, N, B):
     assert got.shape == (B, T, 50, N)
     assert field_err(got[:, :, :25], want[:, :, :25]) < TOL[dt]
     assert field_err(got[:, :, 25:], want[:, :, 25:]) < TOL[dt] * 10     # yh, zh = c1*x[t-1] + c2*x[t-2]: cancellation
+
+
+@pytest.mark.parametrize("dt", [torch.float64, torch.float32])
+def test_rollout_500_steps_vs_reference(ops, golden, mode, dt):
+    """The step count of BASELINE config 5 against the unmodified reference (tests/golden/make_long_rollout.py: two
+    500-index rollouts, sine and random tensions, every 20th index kept): no drift over a long horizon."""
+    d = golden["long_rollout"]
+    traj, _, iters = ops.rollout(params(P_setup()), None, dev(d["controls"], dt))
+    assert int(iters.min()) >= 0, "a rod failed to converge"
+    got = traj.cpu().numpy().astype(np.float64)
+    assert got.shape == (2, 500, 25, 10)
+    assert field_err(got[:, d["keep"]], d["traj"]) < TOL[dt]

@@ -235,3 +235,14 @@ def test_adam_clamp_two_steps(golden):
     for k in new:
         ref = d[f"segment_step1_{k}"]
         assert np.max(np.abs(new[k] - ref)) < 2e-4 * max(np.abs(ref).max(), 1e-2), k
+
+
+def test_rollout_500_steps(golden):
+    """The step count of BASELINE config 5: two 500-index rollouts of the unmodified reference (tests/golden/
+    make_long_rollout.py; sine and random tensions, fsolve xtol 1e-13), every 20th index kept.  Shows that the oracle's
+    Newton variant does not drift from the reference's hybrd over a long horizon."""
+    d = golden["long_rollout"]
+    out = O.rollout_newton(P_setup(), d["controls"], rows=25)
+    assert out.shape == (2, 500, 25, 10)
+    for r in range(2):
+        assert rel_field_err(out[r][d["keep"]], d["traj"][r]) < 1e-9
