@@ -191,6 +191,15 @@ int kc_adam_clamp_multi(int dtype, int32_t n_tensors, const kc_adam_tensor *tens
                         const double *lr_dev, double beta1, double beta2, double eps, double weight_decay,
                         int32_t *ticket_dev, void *stream);
 
+/* State estimation from measurements (replaces estimate_state(data, tensions, robot),
+ * knode_cosserat_realworld/estimate_state.py:158-242 with its helpers :11-156): data[B][T][7][N] (positions 0:3 and
+ * quaternions 3:7 (w,x,y,z) on the full grid), tensions[B][T][4] -> est[B][T][25][N] in the state layout of the path.
+ * L and del_t are robot.L and robot.del_t (the function reads them directly: arc lengths linspace(0, L, N), step L/N of the
+ * n/m recursion, numpy.gradient spacing).  Bug-compatible with the reference for N != 10 (its recursion skips the write at
+ * loop index 9 whatever N is).  T >= 3 (numpy.gradient with edge_order=2 needs three samples).  No workspace. */
+int kc_estimate_state(int dtype, const kc_rod_params *P, double L, double del_t, int64_t B, int64_t T, const void *data,
+                      const void *tensions, void *est, void *stream);
+
 /* FMA-pipe micro-benchmark used as the compute-roofline denominator by bench.py: runs `iters` dependent-chain
  * FMAs x 8 chains per thread on a full grid and returns the number of FLOPs executed in *flops_host; time it with
  * CUDA events on `stream`. */

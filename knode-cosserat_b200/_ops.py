@@ -451,3 +451,20 @@ def fma_peak(dtype, iters, device):
         e1.record()
         e1.synchronize()
     return flops.value / (e0.elapsed_time(e1) * 1e-3)
+
+
+def estimate_state(P, L, del_t, data, tensions):
+    """kc_estimate_state: data[B,T,7,N] (p, h on the full grid), tensions[B,T,4] -> est[B,T,25,N]."""
+    _require_cuda(data, tensions)
+    dt = data.dtype
+    data, tensions = _c(data), _c(tensions, dt)
+    B, T, rows, N = data.shape
+    if rows != 7 or N != int(P.N) or tuple(tensions.shape) != (B, T, 4):
+        raise ValueError(f"estimate_state: data must be [B,T,7,{int(P.N)}] and tensions [B,T,4], got "
+                         f"{tuple(data.shape)} and {tuple(tensions.shape)}")
+    est = torch.empty((B, T, 25, N), dtype=dt, device=data.device)
+    with torch.cuda.device(data.device):
+        rc = _kc.lib().kc_estimate_state(_dtype_code(data), C.byref(P), float(L), float(del_t), B, T, _ptr(data),
+                                         _ptr(tensions), _ptr(est), _stream(data.device))
+    _kc.check(rc, "kc_estimate_state")
+    return est

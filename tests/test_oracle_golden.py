@@ -246,3 +246,31 @@ def test_rollout_500_steps(golden):
     assert out.shape == (2, 500, 25, 10)
     for r in range(2):
         assert rel_field_err(out[r][d["keep"]], d["traj"][r]) < 1e-9
+
+
+EST_CASES = ["default", "damped", "n7_t12", "n20_t12", "n10_t3"]
+
+
+def est_params(case):
+    """The robots of tests/golden/make_estimate_state.py."""
+    if case == "default":
+        return P_default()
+    if case == "damped":
+        P = P_setup()
+        P.Bse = np.diag([2e-2, 3e-2, 5e-2])
+        P.compute_intermediate_terms()
+        return P
+    P = P_default()
+    P.N = int(case.split("_")[0][1:])
+    P.compute_intermediate_terms()
+    return P
+
+
+@pytest.mark.parametrize("case", EST_CASES)
+def test_estimate_state_oracle(golden, case):
+    """oracle/estimate_oracle.py against the unmodified reference's estimate_state (estimate_state.py:158-242), including
+    node counts other than 10 (the reference's hard-coded loop index 9) and the minimum length T = 3."""
+    from oracle import estimate_oracle as E
+    d = golden["estimate_state"]
+    got = E.estimate_state(est_params(case), d[case + "_data"], d[case + "_ctl"])
+    assert rel_field_err(got, d[case + "_est"]) < 1e-11
