@@ -1,16 +1,20 @@
 // kc_estimate.cu — kc_estimate_state: the full 25-row state of a rod from measured positions and quaternions
 // (knode_cosserat_realworld/estimate_state.py:158-242 and its helpers :11-156), batched over recordings.
 //
-// Two kernels.  (A) kc_estimate_kernel: everything that is local in time — finite differences in time (numpy.gradient,
-// edge orders 1 and 2), quaternion -> R, the spatial derivative of R through the rotation vector of the relative
-// rotation (the reference's scipy logm, in closed form from the relative quaternion), the backward recursions for n and
-// m, and the constitutive re-estimate of v, u WITHOUT the previous time step's contribution.  One thread per (time step,
-// node); a CTA owns a tile of consecutive time steps of one recording: the measurement rows t0-3 .. t0+TT+2 are staged
-// in shared memory with contiguous loads, the [TT][25][N] result tile leaves through shared memory with contiguous
-// stores (HBM traffic = algorithmic bytes + the 6-row halo).  (B) kc_estimate_recur_kernel: the one true recurrence of
-// the reference (v_prev, u_prev: x_t = a_t + M x_{t-1}, M = -c2 (K + c0 B)^-1 B), one thread per (recording, node),
-// in place on rows 19:25.
+// ONE kernel, one thread per (time step, node).  A CTA owns a span of consecutive time tiles of one recording and walks
+// them in order; per tile: the measurement rows t0-3 .. t0+TT+2 are staged in shared memory with contiguous loads; every
+// thread computes what is local in time and node (finite differences in time = numpy.gradient with edge orders 1 and 2,
+// quaternion -> R, the spatial derivative of R through the rotation vector of the relative rotation — the reference's
+// scipy logm in closed form from the relative quaternion —, ns and the R-term of ms); each thread then walks the backward
+// recursion for n and m from the tip down to its own node; the constitutive re-estimate of v, u is formed WITHOUT the
+// previous time step's contribution (a_t) and the one true recurrence of the reference (v_prev, u_prev:
+// x_t = a_t + M x_{t-1}, M = -c2 (K + c0 B)^-1 B) is run over the tile in shared memory by 2N threads, its carry kept
+// across the tiles of the span; the [TT][25][N] result tile leaves with contiguous stores.  HBM traffic = algorithmic
+// bytes + the halo rows.  Spans make the recurrence parallel in time: M^w is below rounding after w steps (|M| <= 1/3 for
+// symmetric positive K, B since c2/c0 = 1/3; the host CHECKS ||M^w|| and otherwise uses one span per recording, which is
+// the plain sequential recurrence), so a span starts its carry from zero a few tiles early and discards those tiles.
 #include <cuda_runtime.h>
+#include <math.h>
 #include "kc_common.cuh"
 
 namespace {
@@ -18,8 +22,10 @@ namespace {
 template <typename T>
 struct EstC {
     T inv_dt, inv_ds, L_over_N;
-    T Mv[9], Mu[9];   // recurrence matrices, see kernel B
+    T Mv[9], Mu[9];       // recurrence matrices
+    int rec_v, rec_u;     // 0: the matrix is zero, x_t = a_t
     int T_len, TT, N;
+    int span, warm;       // tiles per span, warm-up tiles before a span (0 for the span that starts at t = 0)
 };
 
 template <typename T> KC_D T t_sqrt(T x);
@@ -70,26 +76,27 @@ KC_D void rel_rotvec(const T* hc, const T* hn, T* phi) {
 // Staged measurements: row r of `in` is time t0 - 3 + r, each row [7][N].
 template <typename T>
 struct Meas {
-    const T* in;
-    int t0, N, Tlen;
+    const T* in;   // already offset by the node index j
+    int t0, N, row, Tlen, j;
     T inv_dt;
-    KC_D T p(int t, int k, int j) const {   // estimate_state.py:174-175: base x, y forced to 0
-        return (j == 0 && k < 2) ? T(0) : in[(size_t)(t - t0 + 3) * 7 * N + k * N + j];
+    KC_D T p(int t, int k) const {   // estimate_state.py:174-175: base x, y forced to 0
+        return (j == 0 && k < 2) ? T(0) : in[(t - t0 + 3) * row + k * N];
     }
-    KC_D T h(int t, int k, int j) const { return in[(size_t)(t - t0 + 3) * 7 * N + (3 + k) * N + j]; }
+    KC_D T h(int t, int k) const { return in[(t - t0 + 3) * row + (3 + k) * N]; }
     // numpy.gradient(p, dt, axis=0, edge_order=1), estimate_state.py:180
-    KC_D void vel(int t, int j, T* v) const {
+    KC_D void vel(int t, T* v) const {
+#pragma unroll
         for (int k = 0; k < 3; ++k) {
-            if (t == 0) v[k] = (p(1, k, j) - p(0, k, j)) * inv_dt;
-            else if (t == Tlen - 1) v[k] = (p(t, k, j) - p(t - 1, k, j)) * inv_dt;
-            else v[k] = (p(t + 1, k, j) - p(t - 1, k, j)) * (T(0.5) * inv_dt);
+            if (t == 0) v[k] = (p(1, k) - p(0, k)) * inv_dt;
+            else if (t == Tlen - 1) v[k] = (p(t, k) - p(t - 1, k)) * inv_dt;
+            else v[k] = (p(t + 1, k) - p(t - 1, k)) * (T(0.5) * inv_dt);
         }
     }
     // compute_angular_velocities, estimate_state.py:97-123: w[t] from the pair (h[t-1], h[t]), w[0] = w[1]
-    KC_D void angvel(int t, int j, T* w) const {
+    KC_D void angvel(int t, T* w) const {
         if (t == 0) t = 1;
-        const T q10 = h(t - 1, 0, j), q11 = h(t - 1, 1, j), q12 = h(t - 1, 2, j), q13 = h(t - 1, 3, j);
-        const T q20 = h(t, 0, j), q21 = h(t, 1, j), q22 = h(t, 2, j), q23 = h(t, 3, j);
+        const T q10 = h(t - 1, 0), q11 = h(t - 1, 1), q12 = h(t - 1, 2), q13 = h(t - 1, 3);
+        const T q20 = h(t, 0), q21 = h(t, 1), q22 = h(t, 2), q23 = h(t, 3);
         const T f = T(2) * inv_dt;
         w[0] = f * (q10 * q21 - q11 * q20 - q12 * q23 + q13 * q22);
         w[1] = f * (q10 * q22 + q11 * q23 - q12 * q20 - q13 * q21);
@@ -103,189 +110,227 @@ KC_D void grad2(int t, int Tlen, T inv_dt, F f, T* out) {
     T a[3], b[3], c[3];
     if (t == 0) {
         f(0, a); f(1, b); f(2, c);
+#pragma unroll
         for (int k = 0; k < 3; ++k) out[k] = (T(-1.5) * a[k] + T(2) * b[k] - T(0.5) * c[k]) * inv_dt;
     } else if (t == Tlen - 1) {
         f(t - 2, a); f(t - 1, b); f(t, c);
+#pragma unroll
         for (int k = 0; k < 3; ++k) out[k] = (T(0.5) * a[k] - T(2) * b[k] + T(1.5) * c[k]) * inv_dt;
     } else {
         f(t + 1, a); f(t - 1, b);
+#pragma unroll
         for (int k = 0; k < 3; ++k) out[k] = (a[k] - b[k]) * (T(0.5) * inv_dt);
     }
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) kc_estimate_kernel(const __grid_constant__ RodC<T> c, const __grid_constant__ EstC<T> e,
-                                                          int ntiles, const T* __restrict__ data,
+__global__ void __launch_bounds__(256, sizeof(T) == 8 ? 2 : 4) kc_estimate_kernel(const __grid_constant__ RodC<T> c, const __grid_constant__ EstC<T> e,
+                                                          int ntiles, int nspans, const T* __restrict__ data,
                                                           const T* __restrict__ tens, T* __restrict__ out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int N = e.N, TT = e.TT, Tlen = e.T_len;
-    T* in_s = reinterpret_cast<T*>(smem_raw);            // [TT+6][7][N]
-    T* out_s = in_s + (size_t)(TT + 6) * 7 * N;          // [TT][25][N]
-    T* ns_s = out_s + (size_t)TT * 25 * N;               // [TT][3][N]  ns, then the R-term of ms
-    T* ps_s = ns_s + (size_t)TT * 3 * N;                 // [TT][3][N]  p_s
-    T* n_s = ps_s + (size_t)TT * 3 * N;                  // [TT][3][N]  n of the recursion (tip entry included)
-    T* m_s = n_s + (size_t)TT * 3 * N;                   // [TT][3][N]
+    const int N = e.N, TT = e.TT, Tlen = e.T_len, row = 7 * N;
+    T* in_s = reinterpret_cast<T*>(smem_raw);   // [TT+6][7][N]
+    T* out_s = in_s + (TT + 6) * row;           // [TT][25][N]
+    T* ns_s = out_s + TT * 25 * N;              // [TT][3][N]  ns
+    T* ps_s = ns_s + TT * 3 * N;                // [TT][3][N]  p_s
+    T* rt_s = ps_s + TT * 3 * N;                // [TT][3][N]  R (w x rhoJ w + rhoJ wt), the R-term of ms
+    T* carry_s = rt_s + TT * 3 * N;             // [2][3][N]   v, u of the last time step of the previous tile
 
-    const int64_t b = blockIdx.x / ntiles;
-    const int t0 = (int)(blockIdx.x % ntiles) * TT;
-    const int nt = min(TT, Tlen - t0);
-    {   // stage rows t0-3 .. t0+nt+2 (clipped to the recording): one contiguous block of the input
-        const int lo = max(t0 - 3, 0), hi = min(t0 + nt + 3, Tlen);
-        const T* src = data + ((size_t)b * Tlen + lo) * 7 * N;
-        T* dst = in_s + (size_t)(lo - (t0 - 3)) * 7 * N;
-        const int cnt = (hi - lo) * 7 * N;
-        for (int i = threadIdx.x; i < cnt; i += blockDim.x) dst[i] = src[i];
-    }
-    __syncthreads();
-
+    const int64_t b = blockIdx.x / nspans;
+    const int tile_first = (int)(blockIdx.x % nspans) * e.span;
+    const int tile_hi = min(tile_first + e.span, ntiles);
+    const int tile_lo = max(tile_first - e.warm, 0);
     const int tl = threadIdx.x / N, j = threadIdx.x - tl * N;
-    const bool active = tl < nt;
-    const int t = t0 + tl;
-    const Meas<T> M{in_s, t0, N, Tlen, e.inv_dt};
-    T R[9], q[3], w[3], vraw[3], uraw[3], hq[4], pp[3];
-    if (active) {
-        for (int k = 0; k < 4; ++k) hq[k] = M.h(t, k, j);
-        for (int k = 0; k < 3; ++k) pp[k] = M.p(t, k, j);
-        quat_R(hq, R);
-        M.vel(t, j, q);
-        M.angvel(t, j, w);
-        T qt[3], wt[3];
-        grad2(t, Tlen, e.inv_dt, [&](int tt, T* o) { M.vel(tt, j, o); }, qt);
-        grad2(t, Tlen, e.inv_dt, [&](int tt, T* o) { M.angvel(tt, j, o); }, wt);
-        // p_s (estimate_state.py:64-68) and the rotation vector to the next node; the last node repeats its neighbour's
-        const int jj = (j < N - 1) ? j : N - 2;
-        T ps[3], hc[4], hn[4], phi[3];
-        for (int k = 0; k < 3; ++k) ps[k] = (M.p(t, k, jj + 1) - M.p(t, k, jj)) * e.inv_ds;
-        for (int k = 0; k < 4; ++k) { hc[k] = M.h(t, k, jj); hn[k] = M.h(t, k, jj + 1); }
-        rel_rotvec(hc, hn, phi);
-        for (int k = 0; k < 3; ++k) phi[k] *= e.inv_ds;
-        if (j < N - 1) {   // u_hat = R^T (R [phi]x / ds) = [phi]x / ds   (:39, :84-87)
-            for (int k = 0; k < 3; ++k) uraw[k] = phi[k];
-        } else {           // R_s[N-1] = R_s[N-2] (:42): u_hat = R_{N-1}^T R_{N-2} [phi]x / ds, entries (2,1), (0,2), (1,0)
-            T Rc[9], A[9], S[9] = {T(0), -phi[2], phi[1], phi[2], T(0), -phi[0], -phi[1], phi[0], T(0)};
-            quat_R(hc, Rc);
-            for (int r = 0; r < 3; ++r)
-                for (int cc = 0; cc < 3; ++cc) A[r * 3 + cc] = Rc[r * 3] * S[cc] + Rc[r * 3 + 1] * S[3 + cc] + Rc[r * 3 + 2] * S[6 + cc];
-            uraw[0] = R[2] * A[1] + R[5] * A[4] + R[8] * A[7];   // (R^T A)[2][1]
-            uraw[1] = R[0] * A[2] + R[3] * A[5] + R[6] * A[8];   // (R^T A)[0][2]
-            uraw[2] = R[1] * A[0] + R[4] * A[3] + R[7] * A[6];   // (R^T A)[1][0]
-        }
-        mtv(R, ps, vraw);                                         // :82
-        if (j == 0) { vraw[0] = T(0); vraw[1] = T(0); vraw[2] = T(1); }   // :90-91
-        // ns and the R-term of ms (estimate_state.py:145-146, :151)
-        const T* tn = tens + ((size_t)b * Tlen + t) * 4;
-        T tf[3], d[3], Rd[3], x[3], Rx[3];
-        for (int k = 0; k < 3; ++k) tf[k] = tn[0] * c.tdirs[k] + tn[1] * c.tdirs[3 + k] + tn[2] * c.tdirs[6 + k] + tn[3] * c.tdirs[9 + k];
-        for (int k = 0; k < 3; ++k) d[k] = c.C[k] * q[k] * fabs(q[k]);
-        mv(R, d, Rd);
-        cross3(w, q, x);
-        for (int k = 0; k < 3; ++k) x[k] += qt[k];
-        mv(R, x, Rx);
-        T Jw[3], Jwt[3], wJw[3];
-        mv(c.rhoJ, w, Jw); mv(c.rhoJ, wt, Jwt);
-        cross3(w, Jw, wJw);
-        for (int k = 0; k < 3; ++k) x[k] = wJw[k] + Jwt[k];
-        T Rm[3];
-        mv(R, x, Rm);
-        for (int k = 0; k < 3; ++k) {
-            const T f = c.rhoAg[k] - Rd[k] + tf[k];
-            ns_s[(tl * 3 + k) * N + j] = c.rhoA * Rx[k] - f;
-            ps_s[(tl * 3 + k) * N + j] = ps[k];
-            m_s[(tl * 3 + k) * N + j] = Rm[k];      // parked here until the m recursion starts
-            n_s[(tl * 3 + k) * N + j] = T(0);
-        }
-    }
-    __syncthreads();
-    if (active && j == 0) {
-        // compute_internal_forces_and_moments (estimate_state.py:144-154) as written: backwards from the tip, step L/N,
-        // the write skipped at loop index 9 whatever N is, and index N-i-2 = -1 wrapping to the tip when i = N-1 != 9.
-        T* nn = n_s + tl * 3 * N; T* mm = m_s + tl * 3 * N; const T* nsv = ns_s + tl * 3 * N; const T* psv = ps_s + tl * 3 * N;
-        for (int i = 0; i < N; ++i) {
-            const int k = N - 1 - i, dst = (k == 0) ? N - 1 : k - 1;
-            if (i != 9)
-                for (int a = 0; a < 3; ++a) nn[a * N + dst] = nn[a * N + k] - nsv[a * N + k] * e.L_over_N;
-        }
-        // m in place: mm[k] holds the R-term of node k until node k is visited; mt carries m[k] down the rod
-        T mt[3] = {T(0), T(0), T(0)};
-        for (int i = 0; i < N; ++i) {
-            const int k = N - 1 - i;
-            const T pk[3] = {psv[k], psv[N + k], psv[2 * N + k]}, nk[3] = {nn[k], nn[N + k], nn[2 * N + k]};
-            T pxn[3];
-            cross3(pk, nk, pxn);
-            for (int a = 0; a < 3; ++a) {
-                const T ms = mm[a * N + k] - pxn[a];
-                mm[a * N + k] = mt[a];                                        // m[k] is final
-                mt[a] = (i != 9) ? mt[a] - ms * e.L_over_N : T(0);            // m[k-1]; stays 0 when the write is skipped
-            }
-        }   // (for N != 10 the last write wraps to the tip entry, which is never read: rows 10:13 of the tip stay 0)
-    }
-    __syncthreads();
-    if (active) {
-        T nj[3], mj[3];
-        for (int k = 0; k < 3; ++k) {   // :226-227: the tip keeps n = m = 0
-            nj[k] = (j < N - 1) ? n_s[(tl * 3 + k) * N + j] : T(0);
-            mj[k] = (j < N - 1) ? m_s[(tl * 3 + k) * N + j] : T(0);
-        }
-        // constitutive re-estimate (:231-234) without the previous step's term; at t = 0 v_prev aliases v (:197-199)
-        const T ch = (t == 0) ? c.c1 + c.c2 : c.c1;
-        T Rn[3], Rmm[3], Bv[3], Bu[3], rv[3], ru[3], av[3], au[3];
-        mtv(R, nj, Rn); mtv(R, mj, Rmm);
-        mv(c.Bse, vraw, Bv); mv(c.Bbt, uraw, Bu);
-        for (int k = 0; k < 3; ++k) { rv[k] = Rn[k] + c.KseVstar[k] - ch * Bv[k]; ru[k] = Rmm[k] - ch * Bu[k]; }
-        mv(c.KseInv, rv, av); mv(c.KbtInv, ru, au);
-        T* o = out_s + (size_t)tl * 25 * N + j;
-        for (int k = 0; k < 3; ++k) o[k * N] = pp[k];
-        o[3 * N] = hq[0];
-        for (int k = 1; k < 4; ++k) o[(3 + k) * N] = (j == 0) ? T(0) : hq[k];   // :238
-        for (int k = 0; k < 3; ++k) {
-            o[(7 + k) * N] = nj[k]; o[(10 + k) * N] = mj[k]; o[(13 + k) * N] = q[k]; o[(16 + k) * N] = w[k];
-            o[(19 + k) * N] = av[k]; o[(22 + k) * N] = au[k];
-        }
-    }
-    __syncthreads();
-    {
-        T* dst = out + ((size_t)b * Tlen + t0) * 25 * N;
-        const int cnt = nt * 25 * N;
-        for (int i = threadIdx.x; i < cnt; i += blockDim.x) dst[i] = out_s[i];
-    }
-}
+    const bool recur = e.rec_v || e.rec_u;
+    for (int i = threadIdx.x; i < 6 * N; i += blockDim.x) carry_s[i] = T(0);
 
-// x_t = a_t + M x_{t-1} for t >= 1, in place on rows 19:22 (v, M = Mv) and 22:25 (u, M = Mu); x_0 is already final.
-template <typename T>
-__global__ void __launch_bounds__(128) kc_estimate_recur_kernel(const __grid_constant__ EstC<T> e, int64_t B, T* __restrict__ out) {
-    const int N = e.N, Tlen = e.T_len;
-    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= B * N) return;
-    const int64_t b = g / N;
-    const int j = (int)(g - b * N);
-    T* base = out + (size_t)b * Tlen * 25 * N + 19 * N + j;
-    const size_t step = (size_t)25 * N;
-    T v[3], u[3];
-    for (int k = 0; k < 3; ++k) { v[k] = base[k * N]; u[k] = base[(3 + k) * N]; }
-    constexpr int U = 8;
-    for (int t = 1; t < Tlen; t += U) {
-        T a[U][6];
+    for (int tile = tile_lo; tile < tile_hi; ++tile) {
+        const int t0 = tile * TT, nt = min(TT, Tlen - t0);
+        {   // stage rows t0-3 .. t0+nt+2 (clipped to the recording): one contiguous block of the input
+            const int lo = max(t0 - 3, 0), hi = min(t0 + nt + 3, Tlen);
+            const T* src = data + ((size_t)b * Tlen + lo) * row;
+            T* dst = in_s + (lo - (t0 - 3)) * row;
+            const int cnt = (hi - lo) * row;
+            for (int i = threadIdx.x; i < cnt; i += blockDim.x) dst[i] = src[i];
+        }
+        __syncthreads();
+
+        const bool active = tl < nt;
+        const int t = t0 + tl;
+        const Meas<T> M{in_s + j, t0, N, row, Tlen, j, e.inv_dt};
+        T R[9], q[3], w[3], vraw[3], uraw[3], hq[4], pp[3];
+        if (active) {
 #pragma unroll
-        for (int s = 0; s < U; ++s)
-            if (t + s < Tlen)
+            for (int k = 0; k < 4; ++k) hq[k] = M.h(t, k);
 #pragma unroll
-                for (int k = 0; k < 6; ++k) a[s][k] = base[(size_t)(t + s) * step + k * N];
+            for (int k = 0; k < 3; ++k) pp[k] = M.p(t, k);
+            quat_R(hq, R);
+            M.vel(t, q);
+            M.angvel(t, w);
+            T qt[3], wt[3];
+            grad2(t, Tlen, e.inv_dt, [&](int tt, T* o) { M.vel(tt, o); }, qt);
+            grad2(t, Tlen, e.inv_dt, [&](int tt, T* o) { M.angvel(tt, o); }, wt);
+            // p_s (estimate_state.py:64-68) and the rotation vector to the next node; the last node repeats its neighbour's
+            const int dj = (j < N - 1) ? 0 : -1;
+            const Meas<T> Mc{in_s + j + dj, t0, N, row, Tlen, j + dj, e.inv_dt}, Mn{in_s + j + dj + 1, t0, N, row, Tlen, j + dj + 1, e.inv_dt};
+            T ps[3], hc[4], hn[4], phi[3];
 #pragma unroll
-        for (int s = 0; s < U; ++s)
-            if (t + s < Tlen) {
-                T nv[3], nu[3];
-                mv(e.Mv, v, nv); mv(e.Mu, u, nu);
+            for (int k = 0; k < 3; ++k) ps[k] = (Mn.p(t, k) - Mc.p(t, k)) * e.inv_ds;
 #pragma unroll
-                for (int k = 0; k < 3; ++k) { v[k] = a[s][k] + nv[k]; u[k] = a[s][3 + k] + nu[k]; }
+            for (int k = 0; k < 4; ++k) { hc[k] = Mc.h(t, k); hn[k] = Mn.h(t, k); }
+            rel_rotvec(hc, hn, phi);
 #pragma unroll
-                for (int k = 0; k < 3; ++k) { base[(size_t)(t + s) * step + k * N] = v[k]; base[(size_t)(t + s) * step + (3 + k) * N] = u[k]; }
+            for (int k = 0; k < 3; ++k) phi[k] *= e.inv_ds;
+            if (j < N - 1) {   // u_hat = R^T (R [phi]x / ds) = [phi]x / ds   (:39, :84-87)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) uraw[k] = phi[k];
+            } else {           // R_s[N-1] = R_s[N-2] (:42): u_hat = R_{N-1}^T R_{N-2} [phi]x / ds, entries (2,1), (0,2), (1,0)
+                T Rc[9], A[9];
+                const T S[9] = {T(0), -phi[2], phi[1], phi[2], T(0), -phi[0], -phi[1], phi[0], T(0)};
+                quat_R(hc, Rc);
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+#pragma unroll
+                    for (int cc = 0; cc < 3; ++cc) A[r * 3 + cc] = Rc[r * 3] * S[cc] + Rc[r * 3 + 1] * S[3 + cc] + Rc[r * 3 + 2] * S[6 + cc];
+                uraw[0] = R[2] * A[1] + R[5] * A[4] + R[8] * A[7];   // (R^T A)[2][1]
+                uraw[1] = R[0] * A[2] + R[3] * A[5] + R[6] * A[8];   // (R^T A)[0][2]
+                uraw[2] = R[1] * A[0] + R[4] * A[3] + R[7] * A[6];   // (R^T A)[1][0]
             }
+            mtv(R, ps, vraw);                                         // :82
+            if (j == 0) { vraw[0] = T(0); vraw[1] = T(0); vraw[2] = T(1); }   // :90-91
+            // ns and the R-term of ms (estimate_state.py:145-146, :151)
+            const T* tn = tens + ((size_t)b * Tlen + t) * 4;
+            T tf[3], d[3], Rd[3], x[3], Rx[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) tf[k] = tn[0] * c.tdirs[k] + tn[1] * c.tdirs[3 + k] + tn[2] * c.tdirs[6 + k] + tn[3] * c.tdirs[9 + k];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) d[k] = c.C[k] * q[k] * fabs(q[k]);
+            mv(R, d, Rd);
+            cross3(w, q, x);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) x[k] += qt[k];
+            mv(R, x, Rx);
+            T Jw[3], Jwt[3], wJw[3], Rm[3];
+            mv(c.rhoJ, w, Jw); mv(c.rhoJ, wt, Jwt);
+            cross3(w, Jw, wJw);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) x[k] = wJw[k] + Jwt[k];
+            mv(R, x, Rm);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const T f = c.rhoAg[k] - Rd[k] + tf[k];
+                ns_s[(tl * 3 + k) * N + j] = c.rhoA * Rx[k] - f;
+                ps_s[(tl * 3 + k) * N + j] = ps[k];
+                rt_s[(tl * 3 + k) * N + j] = Rm[k];
+            }
+        }
+        __syncthreads();
+        if (active) {
+            // compute_internal_forces_and_moments (estimate_state.py:144-154) as written — backwards from the tip, step L/N,
+            // the write skipped at loop index i = 9 whatever N is (the target keeps its initial 0), and for N != 10 the last
+            // write (index N-i-2 = -1) lands on the tip entry of n, which the m recursion then reads at the tip.  Every
+            // thread walks the recursion from the tip down to its own node (no serial section, no second exchange).
+            const T* nsv = ns_s + tl * 3 * N; const T* psv = ps_s + tl * 3 * N; const T* rtv = rt_s + tl * 3 * N;
+            T ntip[3] = {T(0), T(0), T(0)};
+            if (N != 10) {
+                for (int k = N - 1; k >= 0; --k) {
+                    const bool wr = (N - 1 - k) != 9;
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) ntip[a] = wr ? ntip[a] - nsv[a * N + k] * e.L_over_N : T(0);
+                }
+            }
+            T nj[3] = {T(0), T(0), T(0)}, mj[3] = {T(0), T(0), T(0)};
+            for (int k = N - 1; k > j; --k) {
+                const bool wr = (N - 1 - k) != 9;
+                const T pk[3] = {psv[k], psv[N + k], psv[2 * N + k]};
+                T nk[3], pxn[3];
+#pragma unroll
+                for (int a = 0; a < 3; ++a) nk[a] = (k == N - 1) ? ntip[a] : nj[a];
+                cross3(pk, nk, pxn);
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    const T ms = rtv[a * N + k] - pxn[a];
+                    mj[a] = wr ? mj[a] - ms * e.L_over_N : T(0);
+                    nj[a] = wr ? nj[a] - nsv[a * N + k] * e.L_over_N : T(0);
+                }
+            }
+            if (j == N - 1) {   // :226-227: the tip rows keep n = m = 0
+#pragma unroll
+                for (int a = 0; a < 3; ++a) { nj[a] = T(0); mj[a] = T(0); }
+            }
+            // constitutive re-estimate (:231-234) without the previous step's term; at t = 0 v_prev aliases v (:197-199)
+            const T ch = (t == 0) ? c.c1 + c.c2 : c.c1;
+            T Rn[3], Rmm[3], Bv[3], Bu[3], rv[3], ru[3], av[3], au[3];
+            mtv(R, nj, Rn); mtv(R, mj, Rmm);
+            mv(c.Bse, vraw, Bv); mv(c.Bbt, uraw, Bu);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { rv[k] = Rn[k] + c.KseVstar[k] - ch * Bv[k]; ru[k] = Rmm[k] - ch * Bu[k]; }
+            mv(c.KseInv, rv, av); mv(c.KbtInv, ru, au);
+            T* o = out_s + tl * 25 * N + j;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) o[k * N] = pp[k];
+            o[3 * N] = hq[0];
+#pragma unroll
+            for (int k = 1; k < 4; ++k) o[(3 + k) * N] = (j == 0) ? T(0) : hq[k];   // :238
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                o[(7 + k) * N] = nj[k]; o[(10 + k) * N] = mj[k]; o[(13 + k) * N] = q[k]; o[(16 + k) * N] = w[k];
+                o[(19 + k) * N] = av[k]; o[(22 + k) * N] = au[k];
+            }
+        }
+        __syncthreads();
+        if (recur) {
+            // x_t = a_t + M x_{t-1} in place on rows 19:22 (v) and 22:25 (u) of the tile; x_0 = a_0 (t = 0 of the recording)
+            for (int r = threadIdx.x; r < 2 * N; r += blockDim.x) {
+                const int which = r / N, jj = r - which * N;
+                if (which == 0 ? !e.rec_v : !e.rec_u) continue;
+                const T* Mx = which == 0 ? e.Mv : e.Mu;
+                T* cs = carry_s + which * 3 * N + jj;
+                T x0 = cs[0], x1 = cs[N], x2 = cs[2 * N];
+                T* a = out_s + (19 + which * 3) * N + jj;
+                for (int s = 0; s < nt; ++s, a += 25 * N) {
+                    const T a0 = a[0], a1 = a[N], a2 = a[2 * N];
+                    if (t0 + s > 0) {
+                        const T y0 = a0 + Mx[0] * x0 + Mx[1] * x1 + Mx[2] * x2;
+                        const T y1 = a1 + Mx[3] * x0 + Mx[4] * x1 + Mx[5] * x2;
+                        const T y2 = a2 + Mx[6] * x0 + Mx[7] * x1 + Mx[8] * x2;
+                        x0 = y0; x1 = y1; x2 = y2;
+                        a[0] = x0; a[N] = x1; a[2 * N] = x2;
+                    } else { x0 = a0; x1 = a1; x2 = a2; }
+                }
+                cs[0] = x0; cs[N] = x1; cs[2 * N] = x2;
+            }
+            __syncthreads();
+        }
+        if (tile >= tile_first) {
+            T* dst = out + ((size_t)b * Tlen + t0) * 25 * N;
+            const int cnt = nt * 25 * N;
+            for (int i = threadIdx.x; i < cnt; i += blockDim.x) dst[i] = out_s[i];
+        }
     }
 }
 
 void mat3(const double* A, const double* B, double s, double* out) {
     for (int r = 0; r < 3; ++r)
         for (int c = 0; c < 3; ++c) out[r * 3 + c] = s * (A[r * 3] * B[c] + A[r * 3 + 1] * B[3 + c] + A[r * 3 + 2] * B[6 + c]);
+}
+double norm_inf(const double* A) {
+    double m = 0;
+    for (int r = 0; r < 3; ++r) m = fmax(m, fabs(A[r * 3]) + fabs(A[r * 3 + 1]) + fabs(A[r * 3 + 2]));
+    return m;
+}
+// smallest w <= limit with ||M^w||_inf <= tol (0 when M == 0), or -1
+int decay_steps(const double* M, double tol, int limit) {
+    if (norm_inf(M) == 0) return 0;
+    double Pw[9];
+    for (int i = 0; i < 9; ++i) Pw[i] = M[i];
+    for (int w = 1; w <= limit; ++w) {
+        if (norm_inf(Pw) <= tol) return w;
+        double Nx[9];
+        mat3(Pw, M, 1.0, Nx);
+        for (int i = 0; i < 9; ++i) Pw[i] = Nx[i];
+    }
+    return -1;
 }
 
 template <typename T>
@@ -299,27 +344,35 @@ int launch(const kc_rod_params* P, double L, double del_t, int64_t B, int64_t Tl
     double Mv[9], Mu[9];
     mat3(P->Kse_c0Bse_inv, P->Bse, -P->c2, Mv);
     mat3(P->Kbt_c0Bbt_inv, P->Bbt, -P->c2, Mu);
-    bool recur = false;
-    for (int i = 0; i < 9; ++i) { e.Mv[i] = (T)Mv[i]; e.Mu[i] = (T)Mu[i]; recur = recur || Mv[i] != 0 || Mu[i] != 0; }
+    for (int i = 0; i < 9; ++i) { e.Mv[i] = (T)Mv[i]; e.Mu[i] = (T)Mu[i]; }
+    e.rec_v = norm_inf(Mv) != 0; e.rec_u = norm_inf(Mu) != 0;
     e.T_len = (int)Tlen; e.N = N;
     e.TT = 256 / N > 0 ? 256 / N : 1;
     if (e.TT > Tlen) e.TT = (int)Tlen;
-    const int threads = ((e.TT * N + 31) / 32) * 32;
-    const size_t smem = sizeof(T) * (size_t)N * ((size_t)(e.TT + 6) * 7 + (size_t)e.TT * (25 + 12));
     const int ntiles = (int)((Tlen + e.TT - 1) / e.TT);
-    static_assert(sizeof(T) == 4 || sizeof(T) == 8, "fp32 / fp64");
+    // spans: after w steps the influence of the carry is below rounding (checked, not assumed)
+    const double tol = sizeof(T) == 8 ? 1e-18 : 1e-9;
+    const int limit = 8 * e.TT > 64 ? 8 * e.TT : 64;
+    const int wv = decay_steps(Mv, tol, limit), wu = decay_steps(Mu, tol, limit);
+    if (wv < 0 || wu < 0) { e.span = ntiles; e.warm = 0; }                 // slowly decaying recurrence: sequential in time
+    else if (wv == 0 && wu == 0) { e.span = 1; e.warm = 0; }               // no recurrence at all
+    else {
+        const int w = wv > wu ? wv : wu;
+        e.warm = (w + e.TT - 1) / e.TT;
+        e.span = 8 * e.warm;
+        while (e.span > 2 * e.warm && B * ((ntiles + e.span - 1) / e.span) < 600) e.span /= 2;
+        if (e.span >= ntiles) { e.span = ntiles; e.warm = 0; }
+    }
+    const int nspans = (ntiles + e.span - 1) / e.span;
+    const int threads = ((e.TT * N + 31) / 32) * 32;
+    const size_t smem = sizeof(T) * (size_t)N * ((size_t)(e.TT + 6) * 7 + (size_t)e.TT * (25 + 9) + 6);
     if (smem > 48 * 1024) {
         cudaError_t er = cudaFuncSetAttribute(kc_estimate_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (er != cudaSuccess) { kc_set_error("kc_estimate_state: %zu bytes of shared memory: %s", smem, cudaGetErrorString(er)); return KC_ECUDA; }
     }
     const RodC<T> c = make_rodc<T>(*P);
-    kc_estimate_kernel<T><<<(unsigned)(B * ntiles), threads, smem, st>>>(c, e, ntiles, (const T*)data, (const T*)tens, (T*)out);
+    kc_estimate_kernel<T><<<(unsigned)(B * nspans), threads, smem, st>>>(c, e, ntiles, nspans, (const T*)data, (const T*)tens, (T*)out);
     KC_CHECK_LAUNCH("kc_estimate_kernel");
-    if (recur && Tlen > 1) {
-        const int64_t n = B * N;
-        kc_estimate_recur_kernel<T><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(e, B, (T*)out);
-        KC_CHECK_LAUNCH("kc_estimate_recur_kernel");
-    }
     return KC_OK;
 }
 
