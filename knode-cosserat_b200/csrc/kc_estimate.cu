@@ -73,30 +73,31 @@ KC_D void rel_rotvec(const T* hc, const T* hn, T* phi) {
     phi[0] = k * x; phi[1] = k * y; phi[2] = k * z;
 }
 
-// Staged measurements: row r of `in` is time t0 - 3 + r, each row [7][N].
-template <typename T>
+// Staged measurements: row r of `in` is time t0 - 3 + r, each row [7][N].  `at` points at (time t, row 0, node j) of the thread; NN != 0 makes every offset an
+// immediate.  EDGE = false: the tile is at least 3 steps away from both ends of the recording — no boundary tests.
+template <typename T, int NN, bool EDGE>
 struct Meas {
-    const T* in;   // already offset by the node index j
-    int t0, N, row, Tlen, j;
+    const T* at;
+    int t, Tlen, Nrt;
     T inv_dt;
-    KC_D T p(int t, int k) const {   // estimate_state.py:174-175: base x, y forced to 0
-        return (j == 0 && k < 2) ? T(0) : in[(t - t0 + 3) * row + k * N];
-    }
-    KC_D T h(int t, int k) const { return in[(t - t0 + 3) * row + (3 + k) * N]; }
-    // numpy.gradient(p, dt, axis=0, edge_order=1), estimate_state.py:180
-    KC_D void vel(int t, T* v) const {
+    bool base;   // node 0: x and y are pinned to 0 (estimate_state.py:175)
+    KC_D int N() const { return NN ? NN : Nrt; }
+    KC_D T p(int dt, int k) const { return (k < 2 && base) ? T(0) : at[dt * 7 * N() + k * N()]; }
+    KC_D T h(int dt, int k) const { return at[dt * 7 * N() + (3 + k) * N()]; }
+    // numpy.gradient(p, dt, axis=0, edge_order=1) at time t + dt, estimate_state.py:180
+    KC_D void vel(int dt, T* v) const {
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            if (t == 0) v[k] = (p(1, k) - p(0, k)) * inv_dt;
-            else if (t == Tlen - 1) v[k] = (p(t, k) - p(t - 1, k)) * inv_dt;
-            else v[k] = (p(t + 1, k) - p(t - 1, k)) * (T(0.5) * inv_dt);
+            if (EDGE && t + dt == 0) v[k] = (p(dt + 1, k) - p(dt, k)) * inv_dt;
+            else if (EDGE && t + dt == Tlen - 1) v[k] = (p(dt, k) - p(dt - 1, k)) * inv_dt;
+            else v[k] = (p(dt + 1, k) - p(dt - 1, k)) * (T(0.5) * inv_dt);
         }
     }
     // compute_angular_velocities, estimate_state.py:97-123: w[t] from the pair (h[t-1], h[t]), w[0] = w[1]
-    KC_D void angvel(int t, T* w) const {
-        if (t == 0) t = 1;
-        const T q10 = h(t - 1, 0), q11 = h(t - 1, 1), q12 = h(t - 1, 2), q13 = h(t - 1, 3);
-        const T q20 = h(t, 0), q21 = h(t, 1), q22 = h(t, 2), q23 = h(t, 3);
+    KC_D void angvel(int dt, T* w) const {
+        if (EDGE && t + dt == 0) dt += 1;
+        const T q10 = h(dt - 1, 0), q11 = h(dt - 1, 1), q12 = h(dt - 1, 2), q13 = h(dt - 1, 3);
+        const T q20 = h(dt, 0), q21 = h(dt, 1), q22 = h(dt, 2), q23 = h(dt, 3);
         const T f = T(2) * inv_dt;
         w[0] = f * (q10 * q21 - q11 * q20 - q12 * q23 + q13 * q22);
         w[1] = f * (q10 * q22 + q11 * q23 - q12 * q20 - q13 * q21);
@@ -104,33 +105,102 @@ struct Meas {
     }
 };
 
-// numpy.gradient(f, dt, axis=0, edge_order=2) at time t for a quantity f(t') given by a functor (estimate_state.py:186-187)
-template <typename T, typename F>
+// numpy.gradient(f, dt, axis=0, edge_order=2) at time t for a quantity f(t + d) given by a functor (estimate_state.py:186-187)
+template <bool EDGE, typename T, typename F>
 KC_D void grad2(int t, int Tlen, T inv_dt, F f, T* out) {
     T a[3], b[3], c[3];
-    if (t == 0) {
+    if (EDGE && t == 0) {
         f(0, a); f(1, b); f(2, c);
 #pragma unroll
         for (int k = 0; k < 3; ++k) out[k] = (T(-1.5) * a[k] + T(2) * b[k] - T(0.5) * c[k]) * inv_dt;
-    } else if (t == Tlen - 1) {
-        f(t - 2, a); f(t - 1, b); f(t, c);
+    } else if (EDGE && t == Tlen - 1) {
+        f(-2, a); f(-1, b); f(0, c);
 #pragma unroll
         for (int k = 0; k < 3; ++k) out[k] = (T(0.5) * a[k] - T(2) * b[k] + T(1.5) * c[k]) * inv_dt;
     } else {
-        f(t + 1, a); f(t - 1, b);
+        f(1, a); f(-1, b);
 #pragma unroll
         for (int k = 0; k < 3; ++k) out[k] = (a[k] - b[k]) * (T(0.5) * inv_dt);
     }
 }
 
-template <typename T>
+// Everything of one (time step, node) that is local in time and node: fills the thread's registers and ns / p_s / R-term.
+template <typename T, int NN, bool EDGE>
+KC_D void local_terms(const RodC<T>& c, const EstC<T>& e, const T* at, int t, int j, int N, const T* tn,
+                      T* R, T* q, T* w, T* vraw, T* uraw, T* hq, T* pp, T* ns_o, T* ps_o, T* rt_o) {
+    const Meas<T, NN, EDGE> M{at, t, e.T_len, N, e.inv_dt, j == 0};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) hq[k] = M.h(0, k);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) pp[k] = M.p(0, k);
+    quat_R(hq, R);
+    M.vel(0, q);
+    M.angvel(0, w);
+    T qt[3], wt[3];
+    grad2<EDGE>(t, e.T_len, e.inv_dt, [&](int d, T* o) { M.vel(d, o); }, qt);
+    grad2<EDGE>(t, e.T_len, e.inv_dt, [&](int d, T* o) { M.angvel(d, o); }, wt);
+    // p_s (estimate_state.py:64-68) and the rotation vector to the next node; the last node repeats its neighbour's
+    const int jc = (j < N - 1) ? j : N - 2;
+    const T* ac = at + (jc - j);
+    T ps[3], hc[4], hn[4], phi[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) ps[k] = (ac[k * N + 1] - ((k < 2 && jc == 0) ? T(0) : ac[k * N])) * e.inv_ds;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { hc[k] = ac[(3 + k) * N]; hn[k] = ac[(3 + k) * N + 1]; }
+    rel_rotvec(hc, hn, phi);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) phi[k] *= e.inv_ds;
+    if (j < N - 1) {   // u_hat = R^T (R [phi]x / ds) = [phi]x / ds   (:39, :84-87)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) uraw[k] = phi[k];
+    } else {           // R_s[N-1] = R_s[N-2] (:42): u_hat = R_{N-1}^T R_{N-2} [phi]x / ds, entries (2,1), (0,2), (1,0)
+        T Rc[9], A[9];
+        const T S[9] = {T(0), -phi[2], phi[1], phi[2], T(0), -phi[0], -phi[1], phi[0], T(0)};
+        quat_R(hc, Rc);
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int cc = 0; cc < 3; ++cc) A[r * 3 + cc] = Rc[r * 3] * S[cc] + Rc[r * 3 + 1] * S[3 + cc] + Rc[r * 3 + 2] * S[6 + cc];
+        uraw[0] = R[2] * A[1] + R[5] * A[4] + R[8] * A[7];   // (R^T A)[2][1]
+        uraw[1] = R[0] * A[2] + R[3] * A[5] + R[6] * A[8];   // (R^T A)[0][2]
+        uraw[2] = R[1] * A[0] + R[4] * A[3] + R[7] * A[6];   // (R^T A)[1][0]
+    }
+    mtv(R, ps, vraw);                                         // :82
+    if (j == 0) { vraw[0] = T(0); vraw[1] = T(0); vraw[2] = T(1); }   // :90-91
+    // ns and the R-term of ms (estimate_state.py:145-146, :151)
+    T tf[3], d[3], Rd[3], x[3], Rx[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) tf[k] = tn[0] * c.tdirs[k] + tn[1] * c.tdirs[3 + k] + tn[2] * c.tdirs[6 + k] + tn[3] * c.tdirs[9 + k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) d[k] = c.C[k] * q[k] * fabs(q[k]);
+    mv(R, d, Rd);
+    cross3(w, q, x);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) x[k] += qt[k];
+    mv(R, x, Rx);
+    T Jw[3], Jwt[3], wJw[3], Rm[3];
+    mv(c.rhoJ, w, Jw); mv(c.rhoJ, wt, Jwt);
+    cross3(w, Jw, wJw);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) x[k] = wJw[k] + Jwt[k];
+    mv(R, x, Rm);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const T f = c.rhoAg[k] - Rd[k] + tf[k];
+        ns_o[k * N] = c.rhoA * Rx[k] - f;
+        ps_o[k * N] = ps[k];
+        rt_o[k * N] = Rm[k];
+    }
+}
+
+template <typename T, int NN>
 __global__ void __launch_bounds__(256, sizeof(T) == 8 ? 2 : 4) kc_estimate_kernel(const __grid_constant__ RodC<T> c, const __grid_constant__ EstC<T> e,
                                                           int ntiles, int nspans, const T* __restrict__ data,
                                                           const T* __restrict__ tens, T* __restrict__ out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int N = e.N, TT = e.TT, Tlen = e.T_len, row = 7 * N;
-    T* in_s = reinterpret_cast<T*>(smem_raw);   // [TT+6][7][N]
-    T* out_s = in_s + (TT + 6) * row;           // [TT][25][N]
+    const int N = NN ? NN : e.N, TT = e.TT, Tlen = e.T_len, row = 7 * N;
+    T* in_s = reinterpret_cast<T*>(smem_raw);   // [2][TT+6][7][N]  double-buffered: the next tile's rows arrive by cp.async
+    T* out_s = in_s + 2 * (TT + 6) * row;       // [TT][25][N]
     T* ns_s = out_s + TT * 25 * N;              // [TT][3][N]  ns
     T* ps_s = ns_s + TT * 3 * N;                // [TT][3][N]  p_s
     T* rt_s = ps_s + TT * 3 * N;                // [TT][3][N]  R (w x rhoJ w + rhoJ wt), the R-term of ms
@@ -144,85 +214,37 @@ __global__ void __launch_bounds__(256, sizeof(T) == 8 ? 2 : 4) kc_estimate_kerne
     const bool recur = e.rec_v || e.rec_u;
     for (int i = threadIdx.x; i < 6 * N; i += blockDim.x) carry_s[i] = T(0);
 
+    // stage rows t0-3 .. t0+nt+2 of a tile (clipped to the recording): one contiguous block of the input, asynchronously
+    auto stage = [&](int tile, T* buf) {
+        const int t0 = tile * TT, nt = min(TT, Tlen - t0);
+        const int lo = max(t0 - 3, 0), hi = min(t0 + nt + 3, Tlen);
+        const T* src = data + ((size_t)b * Tlen + lo) * row;
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(buf + (lo - (t0 - 3)) * row);
+        const int cnt = (hi - lo) * row;
+        for (int i = threadIdx.x; i < cnt; i += blockDim.x)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(dst + i * (unsigned)sizeof(T)), "l"(src + i), "n"(sizeof(T)) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    stage(tile_lo, in_s);
+
     for (int tile = tile_lo; tile < tile_hi; ++tile) {
         const int t0 = tile * TT, nt = min(TT, Tlen - t0);
-        {   // stage rows t0-3 .. t0+nt+2 (clipped to the recording): one contiguous block of the input
-            const int lo = max(t0 - 3, 0), hi = min(t0 + nt + 3, Tlen);
-            const T* src = data + ((size_t)b * Tlen + lo) * row;
-            T* dst = in_s + (lo - (t0 - 3)) * row;
-            const int cnt = (hi - lo) * row;
-            for (int i = threadIdx.x; i < cnt; i += blockDim.x) dst[i] = src[i];
-        }
-        __syncthreads();
+        T* in_cur = in_s + ((tile - tile_lo) & 1) * (TT + 6) * row;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();   // this tile's rows have landed; every thread is past the previous tile's reads of the other buffer
+        if (tile + 1 < tile_hi) stage(tile + 1, in_s + ((tile + 1 - tile_lo) & 1) * (TT + 6) * row);
 
         const bool active = tl < nt;
         const int t = t0 + tl;
-        const Meas<T> M{in_s + j, t0, N, row, Tlen, j, e.inv_dt};
         T R[9], q[3], w[3], vraw[3], uraw[3], hq[4], pp[3];
         if (active) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) hq[k] = M.h(t, k);
-#pragma unroll
-            for (int k = 0; k < 3; ++k) pp[k] = M.p(t, k);
-            quat_R(hq, R);
-            M.vel(t, q);
-            M.angvel(t, w);
-            T qt[3], wt[3];
-            grad2(t, Tlen, e.inv_dt, [&](int tt, T* o) { M.vel(tt, o); }, qt);
-            grad2(t, Tlen, e.inv_dt, [&](int tt, T* o) { M.angvel(tt, o); }, wt);
-            // p_s (estimate_state.py:64-68) and the rotation vector to the next node; the last node repeats its neighbour's
-            const int dj = (j < N - 1) ? 0 : -1;
-            const Meas<T> Mc{in_s + j + dj, t0, N, row, Tlen, j + dj, e.inv_dt}, Mn{in_s + j + dj + 1, t0, N, row, Tlen, j + dj + 1, e.inv_dt};
-            T ps[3], hc[4], hn[4], phi[3];
-#pragma unroll
-            for (int k = 0; k < 3; ++k) ps[k] = (Mn.p(t, k) - Mc.p(t, k)) * e.inv_ds;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) { hc[k] = Mc.h(t, k); hn[k] = Mn.h(t, k); }
-            rel_rotvec(hc, hn, phi);
-#pragma unroll
-            for (int k = 0; k < 3; ++k) phi[k] *= e.inv_ds;
-            if (j < N - 1) {   // u_hat = R^T (R [phi]x / ds) = [phi]x / ds   (:39, :84-87)
-#pragma unroll
-                for (int k = 0; k < 3; ++k) uraw[k] = phi[k];
-            } else {           // R_s[N-1] = R_s[N-2] (:42): u_hat = R_{N-1}^T R_{N-2} [phi]x / ds, entries (2,1), (0,2), (1,0)
-                T Rc[9], A[9];
-                const T S[9] = {T(0), -phi[2], phi[1], phi[2], T(0), -phi[0], -phi[1], phi[0], T(0)};
-                quat_R(hc, Rc);
-#pragma unroll
-                for (int r = 0; r < 3; ++r)
-#pragma unroll
-                    for (int cc = 0; cc < 3; ++cc) A[r * 3 + cc] = Rc[r * 3] * S[cc] + Rc[r * 3 + 1] * S[3 + cc] + Rc[r * 3 + 2] * S[6 + cc];
-                uraw[0] = R[2] * A[1] + R[5] * A[4] + R[8] * A[7];   // (R^T A)[2][1]
-                uraw[1] = R[0] * A[2] + R[3] * A[5] + R[6] * A[8];   // (R^T A)[0][2]
-                uraw[2] = R[1] * A[0] + R[4] * A[3] + R[7] * A[6];   // (R^T A)[1][0]
-            }
-            mtv(R, ps, vraw);                                         // :82
-            if (j == 0) { vraw[0] = T(0); vraw[1] = T(0); vraw[2] = T(1); }   // :90-91
-            // ns and the R-term of ms (estimate_state.py:145-146, :151)
+            const T* at = in_cur + (tl + 3) * row + j;
             const T* tn = tens + ((size_t)b * Tlen + t) * 4;
-            T tf[3], d[3], Rd[3], x[3], Rx[3];
-#pragma unroll
-            for (int k = 0; k < 3; ++k) tf[k] = tn[0] * c.tdirs[k] + tn[1] * c.tdirs[3 + k] + tn[2] * c.tdirs[6 + k] + tn[3] * c.tdirs[9 + k];
-#pragma unroll
-            for (int k = 0; k < 3; ++k) d[k] = c.C[k] * q[k] * fabs(q[k]);
-            mv(R, d, Rd);
-            cross3(w, q, x);
-#pragma unroll
-            for (int k = 0; k < 3; ++k) x[k] += qt[k];
-            mv(R, x, Rx);
-            T Jw[3], Jwt[3], wJw[3], Rm[3];
-            mv(c.rhoJ, w, Jw); mv(c.rhoJ, wt, Jwt);
-            cross3(w, Jw, wJw);
-#pragma unroll
-            for (int k = 0; k < 3; ++k) x[k] = wJw[k] + Jwt[k];
-            mv(R, x, Rm);
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const T f = c.rhoAg[k] - Rd[k] + tf[k];
-                ns_s[(tl * 3 + k) * N + j] = c.rhoA * Rx[k] - f;
-                ps_s[(tl * 3 + k) * N + j] = ps[k];
-                rt_s[(tl * 3 + k) * N + j] = Rm[k];
-            }
+            T* ns_o = ns_s + tl * 3 * N + j; T* ps_o = ps_s + tl * 3 * N + j; T* rt_o = rt_s + tl * 3 * N + j;
+            if (t0 >= 3 && t0 + nt + 3 <= Tlen)
+                local_terms<T, NN, false>(c, e, at, t, j, N, tn, R, q, w, vraw, uraw, hq, pp, ns_o, ps_o, rt_o);
+            else
+                local_terms<T, NN, true>(c, e, at, t, j, N, tn, R, q, w, vraw, uraw, hq, pp, ns_o, ps_o, rt_o);
         }
         __syncthreads();
         if (active) {
@@ -305,7 +327,15 @@ __global__ void __launch_bounds__(256, sizeof(T) == 8 ? 2 : 4) kc_estimate_kerne
         if (tile >= tile_first) {
             T* dst = out + ((size_t)b * Tlen + t0) * 25 * N;
             const int cnt = nt * 25 * N;
-            for (int i = threadIdx.x; i < cnt; i += blockDim.x) dst[i] = out_s[i];
+            if (sizeof(T) == 4 && (N & 1) == 0) {   // fp32, even N: tile base and size are multiples of 8 bytes
+                const float2* s2 = reinterpret_cast<const float2*>(out_s);
+                float2* d2 = reinterpret_cast<float2*>(dst);
+#pragma unroll 4
+                for (int i = threadIdx.x; i < cnt / 2; i += blockDim.x) d2[i] = s2[i];
+            } else {
+#pragma unroll 4
+                for (int i = threadIdx.x; i < cnt; i += blockDim.x) dst[i] = out_s[i];
+            }
         }
     }
 }
@@ -365,13 +395,17 @@ int launch(const kc_rod_params* P, double L, double del_t, int64_t B, int64_t Tl
     }
     const int nspans = (ntiles + e.span - 1) / e.span;
     const int threads = ((e.TT * N + 31) / 32) * 32;
-    const size_t smem = sizeof(T) * (size_t)N * ((size_t)(e.TT + 6) * 7 + (size_t)e.TT * (25 + 9) + 6);
+    const size_t smem = sizeof(T) * (size_t)N * ((size_t)(e.TT + 6) * 14 + (size_t)e.TT * (25 + 9) + 6);
     if (smem > 48 * 1024) {
-        cudaError_t er = cudaFuncSetAttribute(kc_estimate_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t er = N == 10 ? cudaFuncSetAttribute(kc_estimate_kernel<T, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                                 : cudaFuncSetAttribute(kc_estimate_kernel<T, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (er != cudaSuccess) { kc_set_error("kc_estimate_state: %zu bytes of shared memory: %s", smem, cudaGetErrorString(er)); return KC_ECUDA; }
     }
     const RodC<T> c = make_rodc<T>(*P);
-    kc_estimate_kernel<T><<<(unsigned)(B * nspans), threads, smem, st>>>(c, e, ntiles, nspans, (const T*)data, (const T*)tens, (T*)out);
+    if (N == 10)   // the reference's node count: every shared-memory offset an immediate
+        kc_estimate_kernel<T, 10><<<(unsigned)(B * nspans), threads, smem, st>>>(c, e, ntiles, nspans, (const T*)data, (const T*)tens, (T*)out);
+    else
+        kc_estimate_kernel<T, 0><<<(unsigned)(B * nspans), threads, smem, st>>>(c, e, ntiles, nspans, (const T*)data, (const T*)tens, (T*)out);
     KC_CHECK_LAUNCH("kc_estimate_kernel");
     return KC_OK;
 }
