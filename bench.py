@@ -375,6 +375,43 @@ def main():
                 "loss": float(bl.item()), "all_converged": bool(int(its_b.min()) >= 0),
                 "rod_node_steps_per_s_fwd_bwd": TRAIN_B * N_NODES * (TRAIN_T - 1) / (bms * 1e-3)}
 
+    # ---------------- state estimation: estimate_state on recordings resident in HBM ----------------
+    estimate = None
+    if not args.no_train:
+        EB, ET = 64, 6000                     # recordings per GPU x time steps (60 s at 100 Hz), class-default robot, fp64
+        erobot = CosseratRod()
+        s_ = torch.linspace(0, erobot.L, N_NODES, device=dev, dtype=torch.float64)[None, None, :]
+        t_ = (torch.arange(ET, device=dev, dtype=torch.float64) * erobot.del_t)[None, :, None]
+        om = 2 * np.pi / (torch.rand(EB, 1, 1, device=dev, dtype=torch.float64) * 25 + 15) / erobot.del_t
+        one = torch.ones(EB, ET, N_NODES, device=dev, dtype=torch.float64)
+        meas = torch.stack([0.3 * torch.sin(om * t_) * s_ ** 2, 0.2 * torch.cos(1.3 * om * t_) * s_ ** 2, s_ * one, one,
+                            0.8 * s_ * torch.sin(om * t_), 0.6 * s_ * torch.cos(0.7 * om * t_),
+                            0.3 * s_ * torch.sin(0.4 * om * t_ + 1)], 2).contiguous()
+        etens = 5 + 5 * torch.rand(EB, ET, 4, device=dev, dtype=torch.float64)
+        eP = _kc.rod_params(erobot)
+        for _ in range(3):
+            est = _ops.estimate_state(eP, erobot.L, erobot.del_t, meas, etens)
+        barrier()
+        ems = []
+        for _ in range(max(args.steps, 5)):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            est = _ops.estimate_state(eP, erobot.L, erobot.del_t, meas, etens)
+            e1.record()
+            e1.synchronize()
+            ems.append(e0.elapsed_time(e1))
+        ems_med = max_over_ranks(float(np.median(ems)))
+        ebytes = EB * ET * (32 * N_NODES + 4) * 8     # 7 rows in + 25 rows out per node, 4 tensions per step
+        hbm = float(peaks.get("hbm_gbs", 6544.7))
+        estimate = {"metric": "estimate_state rod-node-steps/sec", "value": world * EB * ET * N_NODES / (ems_med * 1e-3),
+                    "unit": "rod-node-steps/s", "ms_per_call": ems_med, "recordings_per_gpu": EB, "time_steps": ET,
+                    "dtype": "f64", "finite": bool(torch.isfinite(est).all().item()),
+                    "roofline": {"bound": "hbm", "kernel": "kc_estimate_kernel<double,10>", "achieved": ebytes / (ems_med * 1e-3) / 1e9,
+                                 "peak": hbm, "unit": "GB/s", "frac": ebytes / (ems_med * 1e-3) / 1e9 / hbm,
+                                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy bandwidth)",
+                                 "algorithmic_bytes_per_rod_node_step": (32 * N_NODES + 4) * 8 / N_NODES}}
+
     # ---------------- CPU baseline (rank 0, bounded sample, the reference's algorithm on the host cores) -----------
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
@@ -425,7 +462,7 @@ def main():
                          "profiles/r01_ncu_prof_rollout_lin_r1h.csv (algorithmic 416 MB: 410 MB trajectory written once + "
                          "6.5 MB tensions read; the tail of the trajectory is still in L2 when the kernel ends)",
                          "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak}},
-            "cpu_baseline": cpu, "train": train, "train_bptt": bptt}
+            "cpu_baseline": cpu, "train": train, "train_bptt": bptt, "estimate_state": estimate}
         print(json.dumps(out))
     sys.stdout.flush()
     if world > 1:

@@ -3,6 +3,8 @@ estimate_state (knode_cosserat_realworld/estimate_state.py:158-242; tests/golden
 numpy oracle on seeded batches.  fp64: 1e-9 of each field's scale.  fp32: 1e-4 against the oracle evaluated on the SAME
 fp32-rounded measurements (the second time differences amplify the input rounding itself by 1/dt^2, which is a property
 of the data, not of the kernel)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -114,3 +116,31 @@ def test_argument_checks(ops):
     assert call(1, 0.0, 0.005, 1, 4, ops._ptr(x), ops._ptr(c), ops._ptr(o)) == -1      # L
     assert call(1, 0.4, 0.005, 1, 4, None, ops._ptr(c), ops._ptr(o)) == -1             # NULL
     assert call(1, 0.4, 0.005, 0, 4, None, None, None) == 0                            # empty batch
+
+
+def test_pipeline_simulate_estimate_save_train(tmp_path, monkeypatch):
+    """The data path around training, end to end on the GPU and through the reference's on-disk format: rollout ->
+    'measured' p, h -> estimate_state -> datas/<name>_estimated.npy = {"traj", "controls"} (estimate_state.py:279-280) ->
+    train_segment.py loads it (train_segment.py:104-116) and trains."""
+    import train_segment
+    from cosserat_ode import CosseratRod
+    from estimate_state import estimate_state
+    from knode import simulate
+    from physics_controls import calc_controls
+    rod = CosseratRod(use_fsolve=True)
+    T = train_segment.trim_len + 24
+    monkeypatch.chdir(tmp_path)
+    os.makedirs("datas")
+    for name, arg in (("sin_1_0_amp_300", 1.0), ("sin_3_0_amp_300", 3.0)):
+        ctl = np.array(calc_controls("sine", arg, rod.del_t, T))
+        traj = simulate(rod, ctl)
+        est = estimate_state(traj[:, :7, :].copy(), ctl, CosseratRod())
+        assert est.shape == (T, 25, rod.N) and np.isfinite(est).all()
+        # the estimator reproduces the simulated kinematics it differentiates (positions exactly, velocities to O(dt))
+        np.testing.assert_allclose(est[:, :3, 1:], traj[:, :3, 1:], rtol=0, atol=1e-12)
+        assert np.abs(est[5:-5, 13:16] - traj[5:-5, 13:16]).max() < 0.05 * max(np.abs(traj[:, 13:16]).max(), 1e-6) + 1e-6
+        np.save(f"datas/{name}_estimated.npy", {"traj": est, "controls": ctl})
+    robot, loss_arr = train_segment.main(["--data", "sinesine", "--epochs", "3", "--train_len", "20", "--layers", "64",
+                                          "--save_path", str(tmp_path / "m.pth")])
+    assert len(loss_arr) == 3 and np.isfinite(loss_arr).all()
+    assert os.path.exists(tmp_path / "m.pth")

@@ -249,3 +249,40 @@ def test_rollout_500_steps_vs_reference(ops, golden, mode, dt):
     got = traj.cpu().numpy().astype(np.float64)
     assert got.shape == (2, 500, 25, 10)
     assert field_err(got[:, d["keep"]], d["traj"]) < TOL[dt]
+
+
+def test_rollout_config5_shard_properties(ops):
+    """BASELINE config 5, one GPU's shard at full size: 8192 rods x 20 nodes x 500 time indices, class-default parameters
+    (train_segment.py never calls setup_robot; dt = 0.005), fp32, 8.2 GB of trajectory.  Size-independent properties checked
+    on the device — every solve converged, finite, free-end boundary condition met at every step, duplicated inputs give
+    bitwise-identical rods — plus sampled rods against the fp64 oracle (first 100 steps) and against the fp64 kernel
+    (all 500 steps)."""
+    rng = np.random.default_rng(5)
+    P = O.RodParams()
+    P.N = 20
+    P.compute_intermediate_terms()
+    B, T = 8192, 500
+    ctl = np.empty((B, T, 4), dtype=np.float32)
+    i = np.arange(1, T + 1)[None, :, None]
+    per = rng.uniform(0.5, 3.0, (B // 2, 1, 1)) / P.del_t
+    ph = rng.uniform(0, 2 * np.pi, (B // 2, 1, 1))
+    ctl[:B // 2] = 6 + np.sin(2 * np.pi * i / per + ph + np.arange(4)[None, None, :] * np.pi / 2)
+    ctl[B // 2:] = 5 + 5 * rng.random((B // 2, T, 4))
+    ctl[1] = ctl[0]
+    ctl[-1] = ctl[-2]
+    traj, _, iters = ops.rollout(params(P), None, torch.tensor(ctl, device="cuda"))
+    assert tuple(traj.shape) == (B, T, 25, 20)
+    assert int(iters.min()) >= 0, "a rod failed to converge"
+    assert bool(torch.isfinite(traj).all())
+    scale = float(traj[:, :, 7:13].abs().max())
+    assert float(traj[:, 1:, 7:13, -1].abs().max()) < 1e-4 * max(scale, 1.0)      # n(L) = F_tip = 0, m(L) = M_tip = 0
+    assert torch.equal(traj[0], traj[1]) and torch.equal(traj[-1], traj[-2])
+    sel = [0, 7, B // 2 - 1, B // 2, B - 3]
+    got = traj[sel].cpu().numpy().astype(np.float64)
+    want64, _, it64 = ops.rollout(params(P), None, torch.tensor(ctl[sel], device="cuda", dtype=torch.float64))
+    assert int(it64.min()) >= 0
+    w64 = want64.cpu().numpy()
+    assert field_err(got, w64) < 1e-4
+    oracle = O.rollout_newton(P, ctl[sel][:, :100].astype(np.float64), rows=25)
+    assert field_err(w64[:, :100], oracle) < 1e-9
+    assert field_err(got[:, :100], oracle) < 1e-4
