@@ -312,6 +312,32 @@ def main():
                               "frac_of_fp32_fma_peak": None, "frac_of_bf16_tensor_peak_executed": None},
                  "loss": float(trainer.plan.flat[-1].item()), "kernels_per_step": 4 + 1 + 1}
 
+    # ---------------- the same training step, weak scaling: 1024 trajectories PER GPU (global batch grows with N) -------
+    train_weak = None
+    if train is not None and world > 1:
+        torch.manual_seed(0)
+        wrobot = CosseratRodTorch(str(dev), TRAIN_H)
+        setup_robot(wrobot)
+        wtrainer = TeacherForcedTrainer(wrobot, plan.traj[:TRAIN_B, :TRAIN_T].contiguous(),
+                                        ctl[:TRAIN_B, :TRAIN_T].contiguous(), TRAIN_KEYS, lr=1e-2, presharded=True)
+        for _ in range(args.warmup):
+            wtrainer.fused_step(train=True, sync=False)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            wtrainer.fused_step(train=True, sync=False)
+        e1.record()
+        barrier()
+        wms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+        train_weak = {"metric": "KNODE train steps/sec, 1024 trajectories per GPU", "value": 1e3 / wms, "unit": "steps/s",
+                      "ms_per_step": wms, "global_batch_trajectories": TRAIN_B * world, "scaling": "weak",
+                      "trajectory_steps_per_s": TRAIN_B * world * 1e3 / wms,
+                      "useful_tflops": world * q * FLOP_PER_TRAIN_SAMPLE / (wms * 1e-3) / 1e12,
+                      "semantics": "same fused step as `train` (kc_train_step -> one all-reduce -> kc_adam_clamp_multi, CUDA "
+                                   "graph) with every rank holding its own 1024 trajectories; compare trajectory_steps_per_s "
+                                   "with 1024 x train.value at N = 1"}
+
     # ---------------- KNODE rollout training step (C3 ii, north-star extension): rollout + loss + BPTT + Adam ----------
     bptt = None
     if not args.no_train:
@@ -462,7 +488,7 @@ def main():
                          "profiles/r01_ncu_prof_rollout_lin_r1h.csv (algorithmic 416 MB: 410 MB trajectory written once + "
                          "6.5 MB tensions read; the tail of the trajectory is still in L2 when the kernel ends)",
                          "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak}},
-            "cpu_baseline": cpu, "train": train, "train_bptt": bptt, "estimate_state": estimate}
+            "cpu_baseline": cpu, "train": train, "train_weak": train_weak, "train_bptt": bptt, "estimate_state": estimate}
         print(json.dumps(out))
     sys.stdout.flush()
     if world > 1:

@@ -43,18 +43,22 @@ class TeacherForcedTrainer:
 
     trajs: list of [T,25,N] tensors (or one [B,T,25,N]), controls: list of [T,4] (or [B,T,4]); all trajectories must
     share T (they do in the reference: train_len).  Under torch.distributed each rank keeps only its shard of the
-    trajectories; weights stay bitwise identical on all ranks because every rank applies the same all-reduced gradient.
+    trajectories (presharded=True: the trajectories passed ARE this rank's shard); weights stay bitwise identical on all ranks because every rank applies the same all-reduced gradient.
     """
 
     def __init__(self, robot, trajs, controls, key_pt_idx, lr=1e-2, weight_decay=0.0, clamp_weight=True,
-                 patience=80, factor=0.5, fused=True, use_graph=True):
+                 patience=80, factor=0.5, fused=True, use_graph=True, presharded=False):
         self.robot = robot
         self.fused, self.use_graph = fused, use_graph
         self.rank, self.world = _dist.world_info()
         traj = torch.stack(list(trajs)) if not torch.is_tensor(trajs) else trajs
         ctl = torch.stack(list(controls)) if not torch.is_tensor(controls) else controls
-        self.n_total = traj.shape[0]
-        lo, hi = _dist.shard_range(self.n_total, self.rank, self.world)
+        if presharded:   # the caller hands every rank its own trajectories (weak scaling: the global batch grows with the ranks)
+            self.n_total = traj.shape[0] * self.world
+            lo, hi = 0, traj.shape[0]
+        else:
+            self.n_total = traj.shape[0]
+            lo, hi = _dist.shard_range(self.n_total, self.rank, self.world)
         self.traj = traj[lo:hi].detach().contiguous()
         self.ctl = ctl[lo:hi].detach().to(self.traj.dtype).contiguous()
         self.key = np.asarray(key_pt_idx).reshape(-1)

@@ -144,3 +144,38 @@ def test_pipeline_simulate_estimate_save_train(tmp_path, monkeypatch):
                                           "--save_path", str(tmp_path / "m.pth")])
     assert len(loss_arr) == 3 and np.isfinite(loss_arr).all()
     assert os.path.exists(tmp_path / "m.pth")
+
+
+def test_realworld_simulate_script(tmp_path, monkeypatch, golden):
+    """knode_cosserat_realworld/simulate.py as a drop-in script: recorded controls from an `_estimated.npy` dict ->
+    data/<name>.npy = {"traj" [steps,50,N], "controls" [steps-1,4]} with trajectory[i] = state after controls[i]
+    (simulate.py:63-100).  Checked against the oracle's rollout (class-default rod) and, with --model, that a saved
+    whole-object checkpoint (physics_train.py:284-288 format) is picked up."""
+    import simulate as sim_script
+    from cosserat_ode import CosseratRod
+    from cosserat_ode_torch import CosseratRodTorch
+    from physics_controls import calc_controls
+    monkeypatch.chdir(tmp_path)
+    rod = CosseratRod()
+    ctl = np.array(calc_controls("sine", 1.0, rod.del_t, 40))
+    os.makedirs("datas")
+    np.save("datas/rec_estimated.npy", {"traj": np.zeros((40, 25, 10)), "controls": ctl})
+    traj, controls = sim_script.main(["--steps", "30", "--save_name", "out", "--real_data_path", "datas/rec_estimated.npy"])
+    saved = np.load("data/out.npy", allow_pickle=True).item()
+    assert saved["traj"].shape == (30, 50, 10) and saved["traj"].dtype == np.float64
+    np.testing.assert_array_equal(saved["controls"], ctl[1:30])
+    want = O.rollout_newton(O.RodParams(), np.concatenate([ctl[1:30], ctl[29:30]])[None], rows=50)[0]
+    assert field_err(saved["traj"][:, :25], want[:, :25]) < 1e-9
+    # with a KNODE checkpoint
+    torch.manual_seed(0)
+    robot = CosseratRodTorch("cuda", 32)
+    with torch.no_grad():
+        robot.nn_models[2].weight.mul_(0.02)
+        robot.nn_models[2].bias.mul_(0.02)
+    torch.save({"robot": robot}, "m.pth")
+    traj_nn, _ = sim_script.main(["--steps", "12", "--model", "m.pth", "--save_name", "out_nn",
+                                  "--real_data_path", "datas/rec_estimated.npy"])
+    mlp = {k: v.detach().cpu().double().numpy() for k, v in zip(("W1", "b1", "W2", "b2"), robot.nn_models.parameters())}
+    want_nn = O.rollout_newton(O.RodParams(), np.concatenate([ctl[1:12], ctl[11:12]])[None], mlp=mlp, rows=25)[0]
+    assert field_err(traj_nn[:, :25], want_nn) < 1e-9
+    assert np.abs(traj_nn[:, :25] - want[:12, :25]).max() > 1e-6          # the residual changed the rollout
