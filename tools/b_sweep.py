@@ -4,10 +4,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "knode-cosserat_b200"))
 import numpy as np, torch
 import _kc, _ops
-from oracle import rod_oracle as O
+from cosserat_ode import CosseratRod
+from knode import setup_robot
+_robot = CosseratRod(use_fsolve=True); setup_robot(_robot)
 from physics_controls import synthetic_tensions
 T = 100
-P = _kc.rod_params(O.setup_params(O.RodParams()))
+P = _kc.rod_params(_robot)
 for B in [int(a) for a in sys.argv[1:]] or [512, 1024, 2048, 4096, 8192]:
     ctl = torch.tensor(synthetic_tensions(B, T, 0.05, seed=0, dtype=np.float32), device="cuda")
     plan = _ops.RolloutPlan(P, None, B, T, torch.float32, "cuda", rows=25)

@@ -4,10 +4,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "knode-cosserat_b200"))
 import numpy as np, torch
 import _kc, _ops
-from oracle import rod_oracle as O
+from cosserat_ode import CosseratRod
+from knode import setup_robot
+_robot = CosseratRod(use_fsolve=True); setup_robot(_robot)
 from physics_controls import synthetic_tensions
 B, T = 4096, 100
-P = _kc.rod_params(O.setup_params(O.RodParams()))
+P = _kc.rod_params(_robot)
 ctl = torch.tensor(synthetic_tensions(B, T, 0.05, seed=0, dtype=np.float32)).pin_memory()
 out = torch.empty((B, T, 25, 10), dtype=torch.float32).pin_memory()
 dev = torch.device("cuda", 0)

@@ -2,9 +2,11 @@ import sys, os
 sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/knode-cosserat_b200")
 import numpy as np, torch
 import _kc, _ops
-from oracle import rod_oracle as O
+from cosserat_ode import CosseratRod
+from knode import setup_robot
+_robot = CosseratRod(use_fsolve=True); setup_robot(_robot)
 from physics_controls import synthetic_tensions
-P = _kc.rod_params(O.setup_params(O.RodParams()))
+P = _kc.rod_params(_robot)
 for B in (1, 64, 1024, 1776, 4096):
     T = 100
     ctl = torch.tensor(synthetic_tensions(B, T, 0.05, seed=0, dtype=np.float64), device="cuda")

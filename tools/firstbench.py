@@ -4,8 +4,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "knode-cosserat_b200"))
 import numpy as np, torch
 import _kc, _ops
-from oracle import rod_oracle as O
-P = O.setup_params(O.RodParams())
+from cosserat_ode import CosseratRod
+from knode import setup_robot
+_robot = CosseratRod(use_fsolve=True); setup_robot(_robot)
+P = _robot
 pc = _kc.rod_params(P)
 def make_ctl(B, T, seed=0):
     rng = np.random.default_rng(seed)

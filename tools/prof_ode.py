@@ -4,10 +4,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "knode-cosserat_b200"))
 import numpy as np, torch
 import _kc, _ops
-from oracle import rod_oracle as O
+from cosserat_ode import CosseratRod
+from knode import setup_robot
+_robot = CosseratRod(use_fsolve=True); setup_robot(_robot)
 Q = int(sys.argv[1]) if len(sys.argv) > 1 else 118784
 H = int(sys.argv[2]) if len(sys.argv) > 2 else 512
-P = _kc.rod_params(O.setup_params(O.RodParams()))
+P = _kc.rod_params(_robot)
 g = torch.Generator(device="cuda").manual_seed(0)
 r = lambda *s: torch.randn(*s, device="cuda", generator=g)
 mlp = _ops.Mlp(r(H, 28) * 0.1, r(H) * 0.1, r(25, H) * 0.02, r(25) * 0.01)

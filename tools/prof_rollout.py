@@ -4,12 +4,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "knode-cosserat_b200"))
 import numpy as np, torch
 import _kc, _ops
-from oracle import rod_oracle as O
+from cosserat_ode import CosseratRod
+from knode import setup_robot
+_robot = CosseratRod(use_fsolve=True); setup_robot(_robot)
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 T = int(sys.argv[2]) if len(sys.argv) > 2 else 100
 dt = torch.float64 if (len(sys.argv) > 3 and sys.argv[3] == "f64") else torch.float32
 reps = int(sys.argv[4]) if len(sys.argv) > 4 else 2
-P = O.setup_params(O.RodParams())
+P = _robot
 rng = np.random.default_rng(0)
 ctl = np.empty((B, T, 4), np.float32)
 i = np.arange(1, T + 1)[None, :, None]
