@@ -170,7 +170,6 @@ def main():
     import torch.distributed as dist
     import _kc
     import _ops
-    from oracle import rod_oracle as O  # constants + cpu_baseline leg only
     from cosserat_ode import CosseratRod
     from cosserat_ode_torch import CosseratRodTorch
     from knode import setup_robot, simulate
@@ -299,6 +298,13 @@ def main():
         barrier()
         tms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
         q = TRAIN_B * (TRAIN_T - 1) * len(TRAIN_KEYS)
+        identical = None
+        if world > 1:   # C4: every rank applied the same all-reduced gradient -> weights bitwise identical on all ranks
+            wflat = torch.cat([p_.data.reshape(-1) for p_ in trobot.nn_models.parameters()])
+            wlo, whi = wflat.clone(), wflat.clone()
+            dist.all_reduce(wlo, op=dist.ReduceOp.MIN)
+            dist.all_reduce(whi, op=dist.ReduceOp.MAX)
+            identical = bool(torch.equal(wlo, whi))
         train = {"metric": "KNODE train steps/sec", "value": 1e3 / tms, "unit": "steps/s", "ms_per_step": tms,
                  "global_batch_trajectories": TRAIN_B, "samples_per_step": q, "scaling": "strong",
                  "semantics": "teacher-forced (physics_train.py), fwd+loss+bwd+allreduce+Adam+clamp through "
@@ -310,7 +316,8 @@ def main():
                                       "8d); every contraction runs 3 tensor-core passes (tf32 / bf16 hi-lo split) to keep "
                                       "fp32 accuracy, so the executed tensor FLOP/s are 3x this",
                               "frac_of_fp32_fma_peak": None, "frac_of_bf16_tensor_peak_executed": None},
-                 "loss": float(trainer.plan.flat[-1].item()), "kernels_per_step": 4 + 1 + 1}
+                 "loss": float(trainer.plan.flat[-1].item()), "kernels_per_step": 4 + 1 + 1,
+                 "weights_bitwise_identical_across_ranks": identical}
 
     # ---------------- the same training step, weak scaling: 1024 trajectories PER GPU (global batch grows with N) -------
     train_weak = None

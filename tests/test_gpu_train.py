@@ -318,3 +318,59 @@ def test_ode_bwd_tensor_core_vs_simt_and_fp64(ops, monkeypatch, H):
         scale = np.abs(r).max() + 1e-30
         assert np.abs(a - r).max() < 2e-4 * scale, (name, "simt", np.abs(a - r).max() / scale)
         assert np.abs(b - r).max() < 2e-4 * scale, (name, "tc", np.abs(b - r).max() / scale)
+
+
+def test_train_step_config3_full_size_properties(ops, monkeypatch):
+    """BASELINE config 3 at full size (1024 trajectories x 30 time indices, key nodes [3,5,7,9] -> 118 784 samples, H = 512,
+    the reference's weight init): size-independent properties of kc_train_step.  (1) the fp32 tensor-core kernel, the fp32
+    SIMT kernels and the fp64 kernels agree on loss and gradients; (2) loss and gradients are additive over a split of the
+    batch (the loss is a sum over trajectories divided by a global constant, physics_train.py:266-267); (3) two runs are
+    bitwise identical (no atomics); (4) a sampled sub-batch agrees with the numpy oracle."""
+    import physics_controls
+    P = P_setup()
+    B, T, key = 1024, 30, [3, 5, 7, 9]
+    ctl = physics_controls.synthetic_tensions(B, T, P.del_t, seed=3, dtype=np.float32)
+    traj32, _, iters = ops.rollout(params(P), None, dev(ctl, torch.float32))
+    assert int(iters.min()) >= 0
+    g = torch.Generator().manual_seed(0)
+    W = [torch.normal(0.01, 0.01, (512, 28), generator=g).abs(), torch.normal(0.0, 0.01, (512,), generator=g),
+         torch.normal(0.01, 0.01, (25, 512), generator=g).abs(), torch.normal(0.0, 0.01, (25,), generator=g)]
+
+    def run(dt, mode, sl=slice(None)):
+        if mode:
+            monkeypatch.setenv("KC_TRAIN_MODE", mode)
+        else:
+            monkeypatch.delenv("KC_TRAIN_MODE", raising=False)
+        mlp = ops.Mlp(*[w.to("cuda", dt) for w in W])
+        loss, grads, _ = ops.train_step(params(P), mlp, traj32[sl].to(dt), dev(ctl[sl], dt), key)
+        return float(loss.item()), [x.cpu().numpy().astype(np.float64) for x in grads], grads
+
+    l64, g64, _ = run(torch.float64, None)
+    ltc, gtc, raw1 = run(torch.float32, None)
+    lsi, gsi, _ = run(torch.float32, "simt")
+    _, _, raw2 = run(torch.float32, None)
+    assert np.isfinite(l64) and l64 > 0
+    for name, l, gr in (("tc", ltc, gtc), ("simt", lsi, gsi)):
+        assert abs(l - l64) < 1e-5 * l64, name
+        for k, a, r in zip(PK, gr, g64):
+            assert np.abs(a - r).max() < 1e-4 * np.abs(r).max(), (name, k)
+    for a, b in zip(raw1, raw2):
+        assert torch.equal(a, b)                                             # deterministic reduction
+    la, ga, _ = run(torch.float64, None, slice(0, 300))
+    lb, gb, _ = run(torch.float64, None, slice(300, B))
+    assert abs(la + lb - l64) < 1e-11 * l64
+    for k, a, b_, r in zip(PK, ga, gb, g64):
+        assert np.abs(a + b_ - r).max() < 1e-11 * np.abs(r).max(), k
+    lt1, gt1, _ = run(torch.float32, None, slice(0, 300))
+    lt2, gt2, _ = run(torch.float32, None, slice(300, B))
+    assert abs(lt1 + lt2 - ltc) < 1e-5 * ltc
+    for k, a, b_, r in zip(PK, gt1, gt2, gtc):
+        assert np.abs(a + b_ - r).max() < 1e-4 * np.abs(r).max(), k
+    sel = [0, 511, 1023]
+    tr = traj32[sel].cpu().numpy().astype(np.float64)
+    mlp_np = {k: w.numpy().astype(np.float64) for k, w in zip(PK, W)}
+    o_loss, o_grads, _ = O.teacher_forced_loss_and_grads(P, tr, ctl[sel].astype(np.float64), key, mlp_np)
+    ls, gs, _ = run(torch.float32, None, sel)
+    assert abs(ls - o_loss) < 1e-4 * abs(o_loss)
+    for k, a in zip(PK, gs):
+        assert np.abs(a - o_grads[k]).max() < 1e-4 * np.abs(o_grads[k]).max(), k
