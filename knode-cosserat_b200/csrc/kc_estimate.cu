@@ -396,6 +396,7 @@ int launch(const kc_rod_params* P, double L, double del_t, int64_t B, int64_t Tl
     const int nspans = (ntiles + e.span - 1) / e.span;
     const int threads = ((e.TT * N + 31) / 32) * 32;
     const size_t smem = sizeof(T) * (size_t)N * ((size_t)(e.TT + 6) * 14 + (size_t)e.TT * (25 + 9) + 6);
+    KC_CHECK_ARG(smem <= 227 * 1024, "N=%d too large for the shared-memory tiles (%zu B)", N, smem);
     if (smem > 48 * 1024) {
         cudaError_t er = N == 10 ? cudaFuncSetAttribute(kc_estimate_kernel<T, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
                                  : cudaFuncSetAttribute(kc_estimate_kernel<T, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -418,7 +419,7 @@ extern "C" int kc_estimate_state(int dtype, const kc_rod_params* P, double L, do
     KC_CHECK_ARG(P && P->N >= 2 && P->N <= 256, "rod params missing or N outside [2, 256]");
     KC_CHECK_ARG(L > 0 && del_t > 0, "L and del_t must be positive");
     KC_CHECK_ARG(B >= 0 && T >= 3 && T < (1 << 30), "need B >= 0 and T >= 3 (numpy.gradient with edge_order=2, estimate_state.py:186)");
-    KC_CHECK_ARG(B * ((T + 0) / 1) < ((int64_t)1 << 31), "B*T too large for one launch");
+    KC_CHECK_ARG(B * T < ((int64_t)1 << 31), "B*T too large for one launch");
     if (B == 0) return KC_OK;
     KC_CHECK_ARG(data && tensions && est, "NULL data / tensions / est pointer");
     return dtype == KC_F32 ? launch<float>(P, L, del_t, B, T, data, tensions, est, (cudaStream_t)stream)

@@ -45,6 +45,12 @@ def test_argument_validation_needs_no_gpu():
     rc = L.kc_rollout_fwd(0, C.byref(p), None, 4, 10, None, None, None, 0.0, 0, 33, None, None, None, None, 0, None)
     assert rc == -1 and b"rows" in L.kc_last_error()
     assert L.kc_rollout_workspace_bytes(0, C.byref(p), None, 4096, 100) >= 4096 * 100 * 250 * 4
+    one = C.c_void_p(8)
+    rc = L.kc_estimate_state(1, C.byref(p), 0.4, 0.005, 1, 2, one, one, one, None)
+    assert rc == -1 and b"T >= 3" in L.kc_last_error()
+    p.N = 250
+    rc = L.kc_estimate_state(1, C.byref(p), 0.4, 0.005, 1, 5, one, one, one, None)
+    assert rc == -1 and b"too large" in L.kc_last_error()
 
 
 def test_no_cpu_fallback():
@@ -54,3 +60,5 @@ def test_no_cpu_fallback():
     P = _kc.rod_params(O.RodParams())
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         _ops.ode_fwd(P, None, torch.zeros(2, 19), torch.zeros(2, 19), torch.zeros(2, 6), torch.zeros(2, 3))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _ops.estimate_state(P, 0.4, 0.005, torch.zeros(1, 4, 7, 10), torch.zeros(1, 4, 4))
