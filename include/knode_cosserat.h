@@ -123,6 +123,15 @@ int kc_rollout_fwd(int dtype, const kc_rod_params *P, const kc_mlp *mlp, int64_t
                    int32_t rows, void *traj, void *G_out, int32_t *iters, void *workspace,
                    int64_t workspace_bytes, void *stream);
 
+/* The same rollout with the reference's RK4 spatial march (CosseratRod.getResidualRK4, cosserat_ode.py:215-255, with the
+ * mid-point histories of knode.py:80-81) in place of the explicit-Euler march inside the shooting solve — what
+ * knode.simulate computes when its residual is getResidualRK4.  Same arguments, workspace and outputs
+ * as kc_rollout_fwd; one rod per thread (no wide / warp-cooperative mode). */
+int kc_rollout_fwd_rk4(int dtype, const kc_rod_params *P, const kc_mlp *mlp, int64_t B, int64_t T,
+                       const void *tensions, const void *y0, const void *z0, double tol, int32_t max_iter,
+                       int32_t rows, void *traj, void *G_out, int32_t *iters, void *workspace,
+                       int64_t workspace_bytes, void *stream);
+
 /* The same rollout in TIME RANGES: solve steps t in [t_begin, t_end) only, i.e. write time indices t_begin+1 .. t_end
  * (and index 0 when t_begin == 0) of traj / G_out / iters.  Ranges must be issued in order on one stream with the same
  * buffers and workspace: a later range resumes from the trajectory already written plus the solver state kept in the

@@ -53,6 +53,9 @@ _SIGNATURES = {
     "kc_rollout_fwd": (C.c_int, [C.c_int, C.POINTER(kc_rod_params), C.POINTER(kc_mlp), C.c_int64, C.c_int64,
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int32, C.c_int32, C.c_void_p,
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "kc_rollout_fwd_rk4": (C.c_int, [C.c_int, C.POINTER(kc_rod_params), C.POINTER(kc_mlp), C.c_int64, C.c_int64,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int32, C.c_int32, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "kc_rollout_fwd_range": (C.c_int, [C.c_int, C.POINTER(kc_rod_params), C.POINTER(kc_mlp), C.c_int64, C.c_int64,
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int32, C.c_int32, C.c_void_p,
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p]),

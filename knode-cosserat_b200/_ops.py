@@ -194,8 +194,11 @@ def segment_fwd(P, mlp, Gs, key_idx, yh, zh, tensions):
 class RolloutPlan:
     """Pre-allocated outputs + workspace for repeated rollouts of one shape (what bench.py times)."""
 
-    def __init__(self, P, mlp, B, T, dtype, device, rows=25, want_G=False, want_iters=True):
+    def __init__(self, P, mlp, B, T, dtype, device, rows=25, want_G=False, want_iters=True, method="euler"):
         self.P, self.B, self.T, self.rows, self.dtype, self.device = P, B, T, rows, dtype, device
+        if method not in ("euler", "rk4"):
+            raise ValueError(f"method must be 'euler' or 'rk4', got {method!r}")
+        self.method = method          # spatial march inside the shooting solve (getResidualEuler / getResidualRK4)
         self.mlp, self.mref = _mlp_ref(mlp, dtype)
         self.code = _DT[dtype]
         with torch.cuda.device(device):
@@ -220,12 +223,12 @@ class RolloutPlan:
             raise ValueError(f"tensions must be [{self.B},{self.T},4], got {tuple(tensions.shape)}")
         if y0 is not None:
             y0, z0 = _c(y0, self.dtype), _c(z0, self.dtype)
+        fn = _kc.lib().kc_rollout_fwd_rk4 if self.method == "rk4" else _kc.lib().kc_rollout_fwd
         with torch.cuda.device(self.device):
-            rc = _kc.lib().kc_rollout_fwd(self.code, C.byref(self.P), self.mref, self.B, self.T, _ptr(tensions),
-                                          _ptr(y0), _ptr(z0), float(tol), int(max_iter), self.rows, _ptr(self.traj),
-                                          _ptr(self.G), _ptr(self.iters), _ptr(self.ws), self.nbytes,
-                                          _stream(self.device))
-        _kc.check(rc, "kc_rollout_fwd")
+            rc = fn(self.code, C.byref(self.P), self.mref, self.B, self.T, _ptr(tensions), _ptr(y0), _ptr(z0), float(tol),
+                    int(max_iter), self.rows, _ptr(self.traj), _ptr(self.G), _ptr(self.iters), _ptr(self.ws), self.nbytes,
+                    _stream(self.device))
+        _kc.check(rc, "kc_rollout_fwd_rk4" if self.method == "rk4" else "kc_rollout_fwd")
         return self.traj
 
 
@@ -290,11 +293,11 @@ class HostRolloutPlan:
         return out
 
 
-def rollout(P, mlp, tensions, y0=None, z0=None, tol=0.0, max_iter=0, rows=25, want_G=False):
-    """kc_rollout_fwd: tensions[B,T,4] -> traj[B,T,rows,N] (+ G[B,T,6]) and iters[B,T]."""
+def rollout(P, mlp, tensions, y0=None, z0=None, tol=0.0, max_iter=0, rows=25, want_G=False, method="euler"):
+    """kc_rollout_fwd (method="rk4": kc_rollout_fwd_rk4): tensions[B,T,4] -> traj[B,T,rows,N] (+ G[B,T,6]) and iters[B,T]."""
     _require_cuda(tensions)
     B, T, _ = tensions.shape
-    plan = RolloutPlan(P, mlp, B, T, tensions.dtype, tensions.device, rows, want_G)
+    plan = RolloutPlan(P, mlp, B, T, tensions.dtype, tensions.device, rows, want_G, method=method)
     plan.run(tensions, y0, z0, tol, max_iter)
     return plan.traj, plan.G, plan.iters
 

@@ -246,41 +246,6 @@ template <typename T> struct RefSink {
     }
 };
 
-// RK4 march (cosserat_ode.py:215-255): mid-point histories are linear interpolations (knode.py:80-81); only k1's z is kept.
-template <typename T, bool DIAG, int IN, int NH, typename Hist, typename Sink, typename MLP>
-KC_HD void rod_march_rk4(const RodC<T>& P, const MLP& M, const T G[6], const T tf[3], const Hist& H, Sink& S, T res[6]) {
-    T y[19];
-    base_state(P, G, y);
-    const int N = P.N;
-    T h0[NH], h1[NH], hm[NH];
-    H.load(0, h0);
-    for (int j = 0; j < N - 1; ++j) {
-        H.load(j + 1, h1);
-#pragma unroll
-        for (int s = 0; s < NH; ++s) hm[s] = T(0.5) * (h0[s] + h1[s]);
-        T k1[19], k2[19], k3[19], k4[19], z[6], zt[6], yt[19];
-        S.put(j, y);
-        node_eval<T, DIAG, IN, NH>(P, M, y, h0, tf, k1, z);
-        S.putz(j, z);
-#pragma unroll
-        for (int i = 0; i < 19; ++i) yt[i] = y[i] + k1[i] * P.ds / T(2);
-        node_eval<T, DIAG, IN, NH>(P, M, yt, hm, tf, k2, zt);
-#pragma unroll
-        for (int i = 0; i < 19; ++i) yt[i] = y[i] + k2[i] * P.ds / T(2);
-        node_eval<T, DIAG, IN, NH>(P, M, yt, hm, tf, k3, zt);
-#pragma unroll
-        for (int i = 0; i < 19; ++i) yt[i] = y[i] + k3[i] * P.ds;
-        node_eval<T, DIAG, IN, NH>(P, M, yt, h1, tf, k4, zt);
-#pragma unroll
-        for (int i = 0; i < 19; ++i) y[i] = y[i] + P.ds * (k1[i] + T(2) * (k2[i] + k3[i]) + k4[i]) / T(6);
-#pragma unroll
-        for (int s = 0; s < NH; ++s) h0[s] = h1[s];
-    }
-    S.put(N - 1, y);
-#pragma unroll
-    for (int i = 0; i < 3; ++i) { res[i] = P.Ftip[i] - y[7 + i]; res[3 + i] = P.Mtip[i] - y[10 + i]; }
-}
-
 template <typename T, bool DIAG, int IN, int NH, int METHOD>
 __global__ void kc_march_kernel(const __grid_constant__ RodC<T> P, const MlpC<T> M, int64_t B,
                                 const T* __restrict__ G, T* y, T* z, const T* __restrict__ yh,

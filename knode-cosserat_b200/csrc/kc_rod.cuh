@@ -312,6 +312,49 @@ KC_HD void rod_march(const RodC<T>& P, const MLP& M, const T G[6], const T tf[3]
     for (int i = 0; i < 3; ++i) { res[i] = P.Ftip[i] - y[7 + i]; res[3 + i] = P.Mtip[i] - y[10 + i]; }
 }
 
+// RK4 march (cosserat_ode.py:215-255): mid-point histories are linear interpolations (knode.py:80-81); only k1's z is kept.
+// Hist must supply node N-1 as well (k4 of the last interval reads it).
+template <typename T, bool DIAG, int IN, int NH, typename Hist, typename Sink, typename MLP>
+KC_HD void rod_march_rk4(const RodC<T>& P, const MLP& M, const T G[6], const T tf[3], const Hist& H, Sink& S, T res[6]) {
+    T y[19];
+    base_state(P, G, y);
+    const int N = P.N;
+    T h0[NH], h1[NH], hm[NH];
+    H.load(0, h0);
+    for (int j = 0; j < N - 1; ++j) {
+        H.load(j + 1, h1);
+#pragma unroll
+        for (int s = 0; s < NH; ++s) hm[s] = T(0.5) * (h0[s] + h1[s]);
+        T k1[19], k2[19], k3[19], k4[19], z[6], zt[6], yt[19];
+        S.put(j, y);
+        node_eval<T, DIAG, IN, NH>(P, M, y, h0, tf, k1, z);
+        S.putz(j, z);
+#pragma unroll
+        for (int i = 0; i < 19; ++i) yt[i] = y[i] + k1[i] * P.ds / T(2);
+        node_eval<T, DIAG, IN, NH>(P, M, yt, hm, tf, k2, zt);
+#pragma unroll
+        for (int i = 0; i < 19; ++i) yt[i] = y[i] + k2[i] * P.ds / T(2);
+        node_eval<T, DIAG, IN, NH>(P, M, yt, hm, tf, k3, zt);
+#pragma unroll
+        for (int i = 0; i < 19; ++i) yt[i] = y[i] + k3[i] * P.ds;
+        node_eval<T, DIAG, IN, NH>(P, M, yt, h1, tf, k4, zt);
+#pragma unroll
+        for (int i = 0; i < 19; ++i) y[i] = y[i] + P.ds * (k1[i] + T(2) * (k2[i] + k3[i]) + k4[i]) / T(6);
+#pragma unroll
+        for (int s = 0; s < NH; ++s) h0[s] = h1[s];
+    }
+    S.put(N - 1, y);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { res[i] = P.Ftip[i] - y[7 + i]; res[3 + i] = P.Mtip[i] - y[10 + i]; }
+}
+
+// Spatial integrator chosen at compile time (KC_MARCH_EULER | KC_MARCH_RK4).
+template <typename T, bool DIAG, int IN, int NH, int METHOD, typename Hist, typename Sink, typename MLP>
+KC_HD void rod_march_m(const RodC<T>& P, const MLP& M, const T G[6], const T tf[3], const Hist& H, Sink& S, T res[6]) {
+    if (METHOD == KC_MARCH_RK4) rod_march_rk4<T, DIAG, IN, NH>(P, M, G, tf, H, S, res);
+    else rod_march<T, DIAG, IN, NH>(P, M, G, tf, H, S, res);
+}
+
 // ---- 6x6 helpers for the quasi-Newton shooting solve ------------------------------------------------------------
 // In-place Gauss-Jordan inverse without pivoting: the shooting Jacobian is -[[I,0],[X,I]] + small (cond ~ 1.5,
 // SURVEY §4), so pivots stay O(1).  Returns false if a pivot is tiny or not finite (caller flags the rod).
@@ -392,7 +435,7 @@ template <typename T, int LS> KC_HD void broyden_update(const ShootMem<T, LS>& s
 // whenever two consecutive iterations fail to halve the residual.  Written as a small state machine around ONE march
 // call site so lanes in different phases (predictor / FD column / Broyden iterate) still execute the march together.
 // Returns the number of marches (negative: tol not reached within max_iter, or a NaN / singular Jacobian appeared).
-template <typename T, bool DIAG, int IN, int NH, int LS, typename Hist, typename Sink, typename MLP>
+template <typename T, bool DIAG, int IN, int NH, int LS, int METHOD = KC_MARCH_EULER, typename Hist, typename Sink, typename MLP>
 KC_HD int shoot_step(const RodC<T>& P, const MLP& M, const ShootMem<T, LS>& st, const T tf[3], const Hist& H, Sink& S,
                      T tol, int max_iter, T fd_eps) {
     enum { PRED = 0, FD = 1, BROY = 2 };
@@ -414,7 +457,7 @@ KC_HD int shoot_step(const RodC<T>& P, const MLP& M, const ShootMem<T, LS>& st, 
 #pragma unroll
             for (int i = 0; i < 6; ++i) if (i == k) Ge[i] += eps_k;
         }
-        rod_march<T, DIAG, IN, NH>(P, M, Ge, tf, H, S, Fn);
+        rod_march_m<T, DIAG, IN, NH, METHOD>(P, M, Ge, tf, H, S, Fn);
         ++marches;
         if (phase == FD) {
             const T ie = T(1) / eps_k;

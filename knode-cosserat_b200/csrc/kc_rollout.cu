@@ -27,7 +27,7 @@ __device__ __forceinline__ T* rod_base(T* trajD, int64_t b, int T_, int N) {
 
 // One warp per CTA; `rpw` (rods per warp, 1..32) lanes are active.  With few rods the launcher spreads them over more
 // warps (the kernel is latency bound: a half-empty warp costs nothing, a longer per-warp critical path does).
-template <typename T, bool DIAG, int IN, int NH>
+template <typename T, bool DIAG, int IN, int NH, int METHOD = KC_MARCH_EULER>
 __global__ void __launch_bounds__(32)
 kc_rollout_kernel(const __grid_constant__ RodC<T> P, const MlpC<T> M, int64_t B, int T_, int rpw,
                   const T* __restrict__ tensions, const T* __restrict__ y0, const T* __restrict__ z0, T* trajD,
@@ -35,9 +35,10 @@ kc_rollout_kernel(const __grid_constant__ RodC<T> P, const MlpC<T> M, int64_t B,
                   int32_t* iters) {
     extern __shared__ __align__(16) unsigned char kc_smem[];
     const int N = P.N;
-    // shared memory: [N-1][NH][32] history, then [KC_SHOOT_SLOTS][32] solver state
+    // shared memory: [N-1][NH][32] history ([N] for the RK4 march), then [KC_SHOOT_SLOTS][32] solver state
     T* Hs = reinterpret_cast<T*>(kc_smem) + threadIdx.x;
-    const ShootMem<T, KC_LS> st{reinterpret_cast<T*>(kc_smem) + (size_t)NH * (N - 1) * KC_LS + threadIdx.x};
+    const int hn = METHOD == KC_MARCH_RK4 ? N : N - 1;
+    const ShootMem<T, KC_LS> st{reinterpret_cast<T*>(kc_smem) + (size_t)NH * hn * KC_LS + threadIdx.x};
     const int64_t b = (int64_t)blockIdx.x * rpw + threadIdx.x;
     if ((int)threadIdx.x >= rpw || b >= B) return;
     T* traj_b = rod_base(trajD, b, T_, N);
@@ -53,7 +54,7 @@ kc_rollout_kernel(const __grid_constant__ RodC<T> P, const MlpC<T> M, int64_t B,
     } else {
         for (int i = 0; i < KC_SHOOT_SLOTS; ++i) st.p[i * KC_LS] = sb[(size_t)i * Bpad];
     }
-    rollout_rod<T, DIAG, IN, NH, KC_LS>(P, M, st, tensions + (size_t)b * T_ * 4, traj_b, Hs, t_begin, t_end, tol,
+    rollout_rod<T, DIAG, IN, NH, KC_LS, KC_LS, METHOD>(P, M, st, tensions + (size_t)b * T_ * 4, traj_b, Hs, t_begin, t_end, tol,
                                         max_iter, fd_eps, Gout ? Gout + (size_t)b * T_ * 6 : nullptr,
                                         iters ? iters + (size_t)b * T_ : nullptr);
     for (int i = 0; i < KC_SHOOT_SLOTS; ++i) sb[(size_t)i * Bpad] = st.p[i * KC_LS];
@@ -548,7 +549,7 @@ extern "C" int64_t kc_rollout_workspace_bytes(int dtype, const kc_rod_params* P,
 template <typename T>
 static int rollout_typed(const kc_rod_params* Pp, const kc_mlp* mlp, int64_t B, int64_t T_, const void* tensions,
                          const void* y0, const void* z0, double tol, int max_iter, int rows, void* traj, void* G_out,
-                         int32_t* iters, void* workspace, int t_begin, int t_end, bool query_resumable,
+                         int32_t* iters, void* workspace, int t_begin, int t_end, bool query_resumable, int method,
                          cudaStream_t st) {
     // steps [t_begin, t_end) of the rollout (full: 0 .. T-1).  query_resumable: launch nothing, return 1 if the mode this
     // call would select can be run in several time ranges (narrow and wide-lin keep their solver state), else 0.
@@ -572,7 +573,8 @@ static int rollout_typed(const kc_rod_params* Pp, const kc_mlp* mlp, int64_t B, 
     if (max_iter <= 0) max_iter = 60;
     const int NH = in_dim == 53 ? 25 : 12;
     const int threads = 32;
-    const size_t smem = ((size_t)NH * (N - 1) + KC_SHOOT_SLOTS) * threads * sizeof(T);
+    const bool rk4 = method == KC_MARCH_RK4;   // RK4 spatial march: one rod per lane only (narrow kernel)
+    const size_t smem = ((size_t)NH * (rk4 ? N : N - 1) + KC_SHOOT_SLOTS) * threads * sizeof(T);
     KC_CHECK_ARG(smem <= 227 * 1024, "N=%d too large for the shared-memory history (%zu B)", N, smem);
     // rods per warp: the kernel is latency bound, so with few rods spread them over the chip's 148 x 4 warp schedulers
     // (one warp each) before filling the lanes of a warp; never exceed one resident wave.
@@ -619,12 +621,13 @@ static int rollout_typed(const kc_rod_params* Pp, const kc_mlp* mlp, int64_t B, 
         if (e && e[0] == '0') lin = false;
         if (e && e[0] == '1' && lsmem <= 200 * 1024) lin = wide && rows != 0;
     }
+    if (rk4) { wide = false; lin = false; }
     // warp-cooperative KNODE rollout: MLP in the march and too few rods to fill the chip with one rod per thread
-    bool coop = in_dim != 0 && !wide && B <= 8192;
+    bool coop = in_dim != 0 && !wide && B <= 8192 && !rk4;
     {
         const char* e = getenv("KC_ROLLOUT_COOP");
         if (e && e[0] == '0') coop = false;
-        if (e && e[0] == '1' && in_dim != 0) coop = true;
+        if (e && e[0] == '1' && in_dim != 0 && !rk4) coop = true;
     }
     const bool full_range = t_begin == 0 && t_end == (int)T_ - 1;
     const bool resumable = !coop && (!wide || lin);
@@ -709,7 +712,7 @@ static int rollout_typed(const kc_rod_params* Pp, const kc_mlp* mlp, int64_t B, 
         } else {
 #define KC_LAUNCH_ROLL(D, I, H)                                                                                        \
     do {                                                                                                               \
-        auto kern = kc_rollout_kernel<T, D, I, H>;                                                                     \
+        auto kern = rk4 ? kc_rollout_kernel<T, D, I, H, KC_MARCH_RK4> : kc_rollout_kernel<T, D, I, H, KC_MARCH_EULER>; \
         if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
         kern<<<grid, threads, smem, st>>>(P, M, B, (int)T_, rpw, (const T*)tensions, (const T*)y0, (const T*)z0,       \
                                           trajD, w.Bpad, state, t_begin, t_end, tl, max_iter, fd_eps, (T*)G_out,       \
@@ -742,7 +745,8 @@ static int rollout_typed(const kc_rod_params* Pp, const kc_mlp* mlp, int64_t B, 
 static int rollout_checked(int dtype, const kc_rod_params* P, const kc_mlp* mlp, int64_t B, int64_t T_,
                            const void* tensions, const void* y0, const void* z0, double tol, int32_t max_iter,
                            int32_t rows, void* traj, void* G_out, int32_t* iters, void* workspace,
-                           int64_t workspace_bytes, int64_t t_begin, int64_t t_end, bool query, void* stream) {
+                           int64_t workspace_bytes, int64_t t_begin, int64_t t_end, bool query, void* stream,
+                           int method = KC_MARCH_EULER) {
     KC_CHECK_ARG(dtype == KC_F32 || dtype == KC_F64, "dtype must be KC_F32 or KC_F64");
     KC_CHECK_ARG(P && P->N >= 2, "rod params missing or N < 2");
     KC_CHECK_ARG(B >= 0 && T_ >= 1, "B must be >= 0 and T >= 1");
@@ -762,9 +766,9 @@ static int rollout_checked(int dtype, const kc_rod_params* P, const kc_mlp* mlp,
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == KC_F32)
         return rollout_typed<float>(P, mlp, B, T_, tensions, y0, z0, tol, max_iter, rows, traj, G_out, iters, workspace,
-                                    (int)t_begin, (int)t_end, query, st);
+                                    (int)t_begin, (int)t_end, query, method, st);
     return rollout_typed<double>(P, mlp, B, T_, tensions, y0, z0, tol, max_iter, rows, traj, G_out, iters, workspace,
-                                 (int)t_begin, (int)t_end, query, st);
+                                 (int)t_begin, (int)t_end, query, method, st);
 }
 
 extern "C" int kc_rollout_fwd(int dtype, const kc_rod_params* P, const kc_mlp* mlp, int64_t B, int64_t T_,
@@ -773,6 +777,14 @@ extern "C" int kc_rollout_fwd(int dtype, const kc_rod_params* P, const kc_mlp* m
                               int64_t workspace_bytes, void* stream) {
     return rollout_checked(dtype, P, mlp, B, T_, tensions, y0, z0, tol, max_iter, rows, traj, G_out, iters, workspace,
                            workspace_bytes, 0, T_ - 1, false, stream);
+}
+
+extern "C" int kc_rollout_fwd_rk4(int dtype, const kc_rod_params* P, const kc_mlp* mlp, int64_t B, int64_t T_,
+                                  const void* tensions, const void* y0, const void* z0, double tol, int32_t max_iter,
+                                  int32_t rows, void* traj, void* G_out, int32_t* iters, void* workspace,
+                                  int64_t workspace_bytes, void* stream) {
+    return rollout_checked(dtype, P, mlp, B, T_, tensions, y0, z0, tol, max_iter, rows, traj, G_out, iters, workspace,
+                           workspace_bytes, 0, T_ - 1, false, stream, KC_MARCH_RK4);
 }
 
 extern "C" int kc_rollout_fwd_range(int dtype, const kc_rod_params* P, const kc_mlp* mlp, int64_t B, int64_t T_,

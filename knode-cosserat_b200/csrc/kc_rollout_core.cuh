@@ -37,9 +37,10 @@ template <typename T, int LS> struct TrajSink {
 // History for the next step from the two most recent states: H = c1*state[t] + c2*state[t-1] (knode.py:74-75).
 // LS = element stride of the trajectory, LSM = element stride of the history (they differ in the warp-cooperative kernels,
 // where a warp owns ONE rod: device-layout trajectory, lane stride 32, but private per-warp scratch, stride 1)
+// `nodes`: N-1 for the Euler march, N for RK4 (k4 of the last interval reads the history of node N-1).
 template <typename T, int NH, int LS, int LSM = LS>
-KC_HD void build_history(const RodC<T>& P, const T* cur, const T* prev, T* Hs) {
-    const int Nm1 = P.N - 1;
+KC_HD void build_history(const RodC<T>& P, const T* cur, const T* prev, T* Hs, int nodes = -1) {
+    const int Nm1 = nodes < 0 ? P.N - 1 : nodes;
     for (int j = 0; j < Nm1; ++j) {
         const T* cn = cur + (size_t)j * 25 * LS;
         const T* pn = prev + (size_t)j * 25 * LS;
@@ -53,15 +54,16 @@ KC_HD void build_history(const RodC<T>& P, const T* cur, const T* prev, T* Hs) {
 //   ten      : this rod's tensions, ten[t*4 + i]
 //   traj_b   : this rod's base in trajD (element t=0, node 0, row 0); time stride is N*25*LS
 //   Gout/iters: this rod's [T][6] / [T] output rows (reference layout) or nullptr
-template <typename T, bool DIAG, int IN, int NH, int LS, int LSM = LS, typename MLP>
+template <typename T, bool DIAG, int IN, int NH, int LS, int LSM = LS, int METHOD = KC_MARCH_EULER, typename MLP>
 KC_HD void rollout_rod(const RodC<T>& P, const MLP& M, const ShootMem<T, LSM>& st, const T* __restrict__ ten,
                        T* traj_b, T* Hs, int t_begin, int t_end, T tol, int max_iter, T fd_eps, T* Gout,
                        int32_t* iters) {
     const int N = P.N;
+    const int hn = METHOD == KC_MARCH_RK4 ? N : N - 1;   // nodes with a history entry
     const size_t tstride = (size_t)25 * N * LS;
     // (re)build the history of step t_begin from states t_begin and t_begin-1 (state[-1] := state[0], knode.py:65-66)
     build_history<T, NH, LS, LSM>(P, traj_b + (size_t)t_begin * tstride,
-                             traj_b + (size_t)(t_begin > 0 ? t_begin - 1 : 0) * tstride, Hs);
+                             traj_b + (size_t)(t_begin > 0 ? t_begin - 1 : 0) * tstride, Hs, hn);
     for (int t = t_begin; t < t_end; ++t) {
         T tn[4], tf[3];
 #pragma unroll
@@ -71,7 +73,7 @@ KC_HD void rollout_rod(const RodC<T>& P, const MLP& M, const ShootMem<T, LSM>& s
         T* nxt = cur + tstride;
         HistView<T, NH, LSM> H{Hs};
         TrajSink<T, LS> S{nxt};
-        const int it = shoot_step<T, DIAG, IN, NH, LSM>(P, M, st, tf, H, S, tol, max_iter, fd_eps);
+        const int it = shoot_step<T, DIAG, IN, NH, LSM, METHOD>(P, M, st, tf, H, S, tol, max_iter, fd_eps);
         // z[:, N-1] is never written by the march: it keeps its previous value (cosserat_ode.py:198-201)
         {
             const size_t o = (size_t)(N - 1) * 25 * LS;
@@ -83,7 +85,7 @@ KC_HD void rollout_rod(const RodC<T>& P, const MLP& M, const ShootMem<T, LSM>& s
             for (int i = 0; i < 6; ++i) Gout[(size_t)(t + 1) * 6 + i] = st.G(i);
         }
         if (iters) iters[t + 1] = it;
-        build_history<T, NH, LS, LSM>(P, nxt, cur, Hs);
+        build_history<T, NH, LS, LSM>(P, nxt, cur, Hs, hn);
     }
 }
 

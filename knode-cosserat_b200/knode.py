@@ -77,12 +77,14 @@ def _robot_mlp(robot, dtype):
 
 
 def simulate(robot, ctl, robot_reference=None, *, dtype=np.float64, rows=50, tol=0.0, max_iter=0, return_info=False,
-             pinned_out=None):
+             pinned_out=None, method="euler"):
     """Roll the rod out under the tendon tensions `ctl` ([T,4] -> [T,rows,N]; [B,T,4] -> [B,T,rows,N]).
 
     Keyword-only extensions (not in the reference): dtype (np.float64 | np.float32 arithmetic and output), rows (50 =
     reference layout, 25 = [y;z] only), tol / max_iter of the shooting solve, return_info -> (traj, G[..,T,6],
-    marches[..,T]), pinned_out = a pinned host torch tensor to receive the result (avoids an allocation per call).
+    marches[..,T]), pinned_out = a pinned host torch tensor to receive the result (avoids an allocation per call),
+    method = "euler" (getResidualEuler, what the reference's loop calls, knode.py:89) or "rk4" (the reference's
+    getResidualRK4, cosserat_ode.py:215-255, as the residual of the same loop).
     """
     if robot_reference is None:
         robot_reference = robot
@@ -91,6 +93,13 @@ def simulate(robot, ctl, robot_reference=None, *, dtype=np.float64, rows=50, tol
     dev = torch.device("cuda", torch.cuda.current_device())
     tdt = torch.float64 if np.dtype(dtype) == np.float64 else torch.float32
     on_device = torch.is_tensor(ctl) and ctl.is_cuda
+    if method != "euler" and not on_device:     # the pipelined host entry point runs the Euler march only
+        ctl_t = ctl if torch.is_tensor(ctl) else torch.as_tensor(np.asarray(ctl, dtype=np.float64))
+        out = simulate(robot, ctl_t.to(dev), robot_reference, dtype=dtype, rows=rows, tol=tol, max_iter=max_iter,
+                       return_info=return_info, method=method)
+        if pinned_out is not None and not return_info:
+            pinned_out.copy_(torch.from_numpy(out))
+        return out
     if on_device:
         tens = ctl.to(dev, tdt)
     else:
@@ -117,13 +126,13 @@ def simulate(robot, ctl, robot_reference=None, *, dtype=np.float64, rows=50, tol
         y0n, z0n = _initial_state(robot_reference, B)
         y0, z0 = torch.as_tensor(y0n).to(dev, tdt), torch.as_tensor(z0n).to(dev, tdt)
     key = (B, T, rows, tdt, dev, int(P.N), None if mlp is None else (mlp.in_dim, mlp.hidden), bool(return_info),
-           on_device)
+           on_device, method)
     plan = _PLANS.get(key)
     if plan is None:
         if len(_PLANS) >= 4:
             _PLANS.clear()
         if on_device:
-            plan = _ops.RolloutPlan(P, mlp, B, T, tdt, dev, rows, want_G=return_info)
+            plan = _ops.RolloutPlan(P, mlp, B, T, tdt, dev, rows, want_G=return_info, method=method)
         else:
             plan = _ops.HostRolloutPlan(P, mlp, B, T, tdt, dev, rows, want_G=return_info)
         _PLANS[key] = plan

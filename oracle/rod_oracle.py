@@ -326,10 +326,13 @@ def rollout_fsolve(P, ctl, mlp=None, nn_input_history=False, xtol=1.49012e-08):
 
 
 def rollout_newton(P, ctl, mlp=None, nn_input_history=False, tol=1e-13, max_iter=30, rows=50,
-                   return_info=False):
+                   return_info=False, method="euler"):
     """Batched rollout: ctl[B,T,4] -> float64[B,T,rows,N].  Same time loop as knode.simulate (knode.py:70-100) with
     the 6-unknown root found by Newton with a central-difference Jacobian instead of hybrd; agrees with
-    `rollout_fsolve(xtol=1e-13)` to ~1e-13 (tests/test_oracle_golden.py)."""
+    `rollout_fsolve(xtol=1e-13)` to ~1e-13 (tests/test_oracle_golden.py).  method="rk4": the residual of the loop is
+    getResidualRK4 (cosserat_ode.py:215-255; the loop already builds its mid-point histories, knode.py:80-81) — pinned to
+    the reference's simulate run with that residual (tests/golden/make_rk4_rollout.py)."""
+    march_euler = globals()["march_rk4" if method == "rk4" else "march_euler"]   # noqa: F841 — shadows the Euler march below
     ctl = np.asarray(ctl, dtype=np.float64)
     B, T, _ = ctl.shape
     y, z = initial_state(P, (B,))

@@ -286,3 +286,60 @@ def test_rollout_config5_shard_properties(ops):
     oracle = O.rollout_newton(P, ctl[sel][:, :100].astype(np.float64), rows=25)
     assert field_err(w64[:, :100], oracle) < 1e-9
     assert field_err(got[:, :100], oracle) < 1e-4
+
+
+@pytest.mark.parametrize("dt", [torch.float64, torch.float32])
+@pytest.mark.parametrize("name", ["default_sine", "default_sine_slow", "default_random"])
+def test_rollout_rk4_vs_reference(ops, golden, dt, name):
+    """kc_rollout_fwd_rk4 (the reference's getResidualRK4 as the residual of knode.simulate) against the unmodified
+    reference (tests/golden/make_rk4_rollout.py)."""
+    d = golden["rk4_rollouts"]
+    ref = d[name + "_traj"]
+    traj, G, iters = ops.rollout(params(O.RodParams()), None, dev(d[name + "_ctl"][None], dt), rows=50, want_G=True,
+                                 method="rk4")
+    assert int(iters.min()) >= 0, "a rod failed to converge"
+    got = traj.cpu().numpy()[0].astype(np.float64)
+    assert field_err(got[:, :25], ref[:, :25]) < TOL[dt]
+    assert field_err(got[:, 25:], ref[:, 25:]) < TOL[dt] * 10
+    np.testing.assert_allclose(G.cpu().numpy()[0, 1:].astype(np.float64), ref[1:, 7:13, 0], rtol=0,
+                               atol=TOL[dt] * max(1.0, np.abs(ref[:, 7:13, 0]).max()))
+
+
+@pytest.mark.parametrize("dt", [torch.float64, torch.float32])
+def test_rollout_rk4_batch_knode_and_node_counts(ops, golden, dt):
+    """RK4 rollouts of a ragged batch, with the KNODE residual in the march, and at another node count, against the oracle
+    (whose RK4 rollout is pinned to the reference); the drop-in keyword knode.simulate(..., method="rk4")."""
+    rng = np.random.default_rng(11)
+    P = O.RodParams()
+    B, T = 37, 12
+    ctl = np.stack([np.array(O.calc_controls("sine", 0.5 + 0.1 * b, P.del_t, T)) if b % 2 == 0
+                    else 5 + 5 * rng.random((T, 4)) for b in range(B)])
+    want = O.rollout_newton(P, ctl, rows=25, method="rk4")
+    traj, _, iters = ops.rollout(params(P), None, dev(ctl, dt), method="rk4")
+    assert int(iters.min()) >= 0
+    assert field_err(traj.cpu().numpy().astype(np.float64), want) < TOL[dt]
+    # KNODE residual inside the RK4 march (weights of the golden h64 network, scaled to a trained-size correction)
+    d = golden["knode_rollouts"]
+    mlp_np = {k: d[f"h64_{k}"].astype(np.float64) * (0.05 if k in ("W2", "b2") else 1.0) for k in ("W1", "b1", "W2", "b2")}
+    mlp = ops.Mlp(*[dev(mlp_np[k], dt) for k in ("W1", "b1", "W2", "b2")])
+    want_nn = O.rollout_newton(P, ctl[:5], mlp=mlp_np, rows=25, method="rk4")
+    traj_nn, _, it_nn = ops.rollout(params(P), mlp, dev(ctl[:5], dt), method="rk4")
+    assert int(it_nn.min()) >= 0
+    assert field_err(traj_nn.cpu().numpy().astype(np.float64), want_nn) < TOL[dt]
+    assert field_err(want_nn, want[:5]) > 1e-6                       # the residual network changes the rollout
+    # 13 nodes
+    P13 = O.RodParams()
+    P13.N = 13
+    P13.compute_intermediate_terms()
+    want13 = O.rollout_newton(P13, ctl[:6], rows=50, method="rk4")
+    t13, _, it13 = ops.rollout(params(P13), None, dev(ctl[:6], dt), rows=50, method="rk4")
+    assert int(it13.min()) >= 0
+    g13 = t13.cpu().numpy().astype(np.float64)
+    assert field_err(g13[:, :, :25], want13[:, :, :25]) < TOL[dt]
+    assert field_err(g13[:, :, 25:], want13[:, :, 25:]) < TOL[dt] * 10
+    if dt == torch.float64:
+        from cosserat_ode import CosseratRod
+        from knode import simulate
+        one = simulate(CosseratRod(use_fsolve=True), ctl[0], method="rk4")
+        assert one.shape == (T, 50, 10) and one.dtype == np.float64
+        assert field_err(one[:, :25], want[0]) < 1e-9

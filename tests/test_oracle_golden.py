@@ -274,3 +274,17 @@ def test_estimate_state_oracle(golden, case):
     d = golden["estimate_state"]
     got = E.estimate_state(est_params(case), d[case + "_data"], d[case + "_ctl"])
     assert rel_field_err(got, d[case + "_est"]) < 1e-11
+
+
+@pytest.mark.parametrize("name", ["default_sine", "default_sine_slow", "default_random"])
+def test_rollout_rk4_residual(golden, name):
+    """Rollouts whose shooting residual is getResidualRK4 (cosserat_ode.py:215-255): the oracle's method="rk4" against the
+    unmodified reference's simulate run with that residual (tests/golden/make_rk4_rollout.py); the Euler rollout differs
+    from these vectors by ~36 % in the worst field, so the comparison discriminates."""
+    d = golden["rk4_rollouts"]
+    out = O.rollout_newton(P_default(), d[name + "_ctl"][None], method="rk4")[0]
+    assert rel_field_err(out[:, :25], d[name + "_traj"][:, :25]) < 1e-10
+    np.testing.assert_allclose(out[:, 25:], d[name + "_traj"][:, 25:], rtol=1e-8, atol=1e-7)
+    if name == "default_sine":
+        euler = O.rollout_newton(P_default(), d[name + "_ctl"][None])[0]
+        assert rel_field_err(euler[:, :25], d[name + "_traj"][:, :25]) > 0.1
