@@ -15,6 +15,7 @@
 // the plain sequential recurrence), so a span starts its carry from zero a few tiles early and discards those tiles.
 #include <cuda_runtime.h>
 #include <math.h>
+#include <cstdlib>
 #include "kc_common.cuh"
 
 namespace {
@@ -377,7 +378,12 @@ int launch(const kc_rod_params* P, double L, double del_t, int64_t B, int64_t Tl
     for (int i = 0; i < 9; ++i) { e.Mv[i] = (T)Mv[i]; e.Mu[i] = (T)Mu[i]; }
     e.rec_v = norm_inf(Mv) != 0; e.rec_u = norm_inf(Mu) != 0;
     e.T_len = (int)Tlen; e.N = N;
-    e.TT = 256 / N > 0 ? 256 / N : 1;
+    // time steps per tile: 4-warp CTAs (same resident threads as 8-warp ones, cheaper barriers: +14 % at N = 10) unless that
+    // leaves fewer than 12 steps per tile — then the 6-row halo dominates the staging (N = 20: 12 steps, 8 warps)
+    e.TT = 128 / N;
+    if (e.TT < 12) e.TT = 256 / N < 12 ? 256 / N : 12;
+    if (e.TT < 1) e.TT = 1;
+    if (const char* ev = getenv("KC_EST_TT")) { const int v = atoi(ev); if (v >= 1 && v * N <= 256) e.TT = v; }   // tuning knob
     if (e.TT > Tlen) e.TT = (int)Tlen;
     const int ntiles = (int)((Tlen + e.TT - 1) / e.TT);
     // spans: after w steps the influence of the carry is below rounding (checked, not assumed)

@@ -56,7 +56,7 @@ def measurements(P, B, T, seed):
 @pytest.mark.parametrize("dt", [torch.float64, torch.float32])
 @pytest.mark.parametrize("B,T,N", [(3, 77, 10), (2, 1000, 10), (1, 3, 10), (5, 26, 10), (2, 40, 20), (4, 19, 7), (2, 9, 130)])
 def test_estimate_state_batches(ops, dt, B, T, N):
-    """Several recordings, lengths that are not a multiple of the time tile (25 steps at N = 10), other node counts; the
+    """Several recordings, lengths that are not a multiple of the time tile (12 steps at N = 10), other node counts; the
     1000-step case is split into time spans that warm their recurrence carry up from zero (kc_estimate.cu)."""
     P = O.RodParams()
     P.N = N
