@@ -18,6 +18,14 @@
 #include <cstdlib>
 #include "kc_common.cuh"
 
+// resident 256-thread CTAs per SM the register allocation is bounded for (fp64: 128 registers, fp32: 64)
+#ifndef KC_EST_MINB64
+#define KC_EST_MINB64 2
+#endif
+#ifndef KC_EST_MINB32
+#define KC_EST_MINB32 4
+#endif
+
 namespace {
 
 template <typename T>
@@ -195,7 +203,7 @@ KC_D void local_terms(const RodC<T>& c, const EstC<T>& e, const T* at, int t, in
 }
 
 template <typename T, int NN>
-__global__ void __launch_bounds__(256, sizeof(T) == 8 ? 2 : 4) kc_estimate_kernel(const __grid_constant__ RodC<T> c, const __grid_constant__ EstC<T> e,
+__global__ void __launch_bounds__(256, sizeof(T) == 8 ? KC_EST_MINB64 : KC_EST_MINB32) kc_estimate_kernel(const __grid_constant__ RodC<T> c, const __grid_constant__ EstC<T> e,
                                                           int ntiles, int nspans, const T* __restrict__ data,
                                                           const T* __restrict__ tens, T* __restrict__ out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
