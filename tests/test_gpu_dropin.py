@@ -229,3 +229,25 @@ def test_train_segment_script_synthetic(tmp_path, monkeypatch):
     assert os.path.exists(tmp_path / "m.pth")
     with pytest.raises(FileNotFoundError):
         train_segment.main(["--epochs", "1"])
+
+
+def test_physics_multitrain_script_trains_and_writes_evals(tmp_path, monkeypatch, capsys):
+    """physics_multitrain.py as a script (physics_multitrain.py:85-233): {2 datasets} x {4 mods} training jobs, then the
+    evaluation table against the physics-only baselines and the evals/*.npy dicts {"tensions", "reference", "predicted"}
+    (:201-205) — the on-disk format downstream plotting reads."""
+    import physics_multitrain
+    monkeypatch.chdir(tmp_path)
+    physics_multitrain.main(["--epochs", "2", "--fast", "--n_seeds", "1", "--save_dir", str(tmp_path / "saved_models")])
+    out = capsys.readouterr().out
+    models = sorted(os.listdir(tmp_path / "saved_models"))
+    assert len(models) == 8 and all(m.endswith("_trainlen_30_2_epoch_0.pth") for m in models)
+    evals = sorted(os.listdir(tmp_path / "evals"))
+    assert len(evals) == 2 * 3 * 4                         # eval sets x (baseline + 2 datasets) x mods
+    for line_start in ("baseline nsw", "sine sine 0.5 1.0 youngs 0", "sine sine random 0.5 1.0 0.0 lengthstiff 0"):
+        assert any(l.startswith(line_start) for l in out.splitlines()), line_start
+    d = np.load(tmp_path / "evals" / evals[0], allow_pickle=True).item()
+    assert set(d) == {"tensions", "reference", "predicted"}
+    assert d["tensions"].shape == (100, 4) and d["predicted"].shape == (100, 50, 10) and d["reference"].shape == (100, 25, 10)
+    assert np.isfinite(d["predicted"]).all()
+    base = np.load(tmp_path / "evals" / "physics_sine_1_5+baseline_youngs_trainlen_30_2_epochs.npy", allow_pickle=True).item()
+    assert np.abs(base["predicted"][:, :3, 9] - base["reference"][:, :3, 9]).max() > 1e-4   # a modified rod differs
