@@ -249,5 +249,5 @@ def test_physics_multitrain_script_trains_and_writes_evals(tmp_path, monkeypatch
     assert set(d) == {"tensions", "reference", "predicted"}
     assert d["tensions"].shape == (100, 4) and d["predicted"].shape == (100, 50, 10) and d["reference"].shape == (100, 25, 10)
     assert np.isfinite(d["predicted"]).all()
-    base = np.load(tmp_path / "evals" / "physics_sine_1_5+baseline_youngs_trainlen_30_2_epochs.npy", allow_pickle=True).item()
+    base = np.load(tmp_path / "evals" / "physics_sine_1.5+baseline_youngs_trainlen_30_2_epochs.npy", allow_pickle=True).item()
     assert np.abs(base["predicted"][:, :3, 9] - base["reference"][:, :3, 9]).max() > 1e-4   # a modified rod differs
