@@ -405,6 +405,8 @@ int launch(const kc_rod_params* P, double L, double del_t, int64_t B, int64_t Tl
         e.warm = (w + e.TT - 1) / e.TT;
         e.span = 8 * e.warm;
         while (e.span > 2 * e.warm && B * ((ntiles + e.span - 1) / e.span) < 600) e.span /= 2;
+        // a handful of recordings: the call is latency bound by the tiles one CTA walks — trade recompute for parallelism
+        if (B * ((ntiles + e.span - 1) / e.span) < 148 && e.span > e.warm) e.span = e.warm;
         if (e.span >= ntiles) { e.span = ntiles; e.warm = 0; }
     }
     const int nspans = (ntiles + e.span - 1) / e.span;
