@@ -129,6 +129,17 @@ def _gloo_worker(rank, world, port, q):
     lo, hi = _dist.shard_range(5, rank, world)
     mine = [sum(g_all[lo:hi], torch.zeros(4)), torch.full((2, 3), float(hi - lo))]
     _dist.allreduce_sum_(mine)
+    # trainer-side sharding (host logic only: no kernel is launched by the constructor): 5 trajectories split 3 + 2, or,
+    # presharded, every rank keeps what it was given and the global batch is world x local (weak scaling)
+    from _train import TeacherForcedTrainer
+
+    class _Robot:
+        nn_models = torch.nn.ModuleList([torch.nn.Linear(28, 4), torch.nn.ELU(), torch.nn.Linear(4, 25)])
+    traj, ctl = torch.zeros(5, 6, 25, 10), torch.zeros(5, 6, 4)
+    tr = TeacherForcedTrainer(_Robot(), traj, ctl, [3, 5])
+    assert tr.n_total == 5 and tr.traj.shape[0] == hi - lo
+    tw = TeacherForcedTrainer(_Robot(), traj, ctl, [3, 5], presharded=True)
+    assert tw.n_total == 5 * world and tw.traj.shape[0] == 5
     q.put((rank, mine[0].tolist(), mine[1].tolist()))
     dist.barrier()
     dist.destroy_process_group()
