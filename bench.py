@@ -459,6 +459,19 @@ def main():
                "sample": f"{nrods} rods x {t_sample - 1} solved steps of the same workload, oracle port of "
                          f"knode.simulate (numpy + scipy fsolve), one rod per host process, {cwall:.1f} s wall"}
 
+    if cpu is not None and estimate is not None:
+        # the same checker leg for the state estimator: oracle port of estimate_state (numpy, vectorised over time, one
+        # core) on a bounded sample of one recording
+        from oracle import estimate_oracle as EO
+        from oracle import rod_oracle as RO
+        n_s = 1200
+        m_np, c_np = meas[0, :n_s].cpu().numpy(), etens[0, :n_s].cpu().numpy()
+        t0 = time.perf_counter()
+        EO.estimate_state(RO.RodParams(), m_np, c_np)
+        dt_cpu = time.perf_counter() - t0
+        estimate["cpu_baseline"] = {"value": n_s * N_NODES / dt_cpu, "unit": "rod-node-steps/s", "cores": 1, "kind": "port",
+                                    "sample": f"{n_s} time steps of one recording, oracle port of estimate_state (numpy), "
+                                              f"{dt_cpu:.2f} s wall"}
     if train is not None:
         ach = train["roofline"]["achieved"] * 1e12
         train["roofline"]["frac_of_fp32_fma_peak"] = ach / fp32_peak
