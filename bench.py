@@ -443,7 +443,10 @@ def main():
                     "roofline": {"bound": "hbm", "kernel": "kc_estimate_kernel<double,10>", "achieved": ebytes / (ems_med * 1e-3) / 1e9,
                                  "peak": hbm, "unit": "GB/s", "frac": ebytes / (ems_med * 1e-3) / 1e9 / hbm,
                                  "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy bandwidth)",
-                                 "algorithmic_bytes_per_rod_node_step": (32 * N_NODES + 4) * 8 / N_NODES}}
+                                 "algorithmic_bytes_per_rod_node_step": (32 * N_NODES + 4) * 8 / N_NODES,
+                                 "algorithmic_bytes": ebytes, "traffic": 4.042e9 * EB / 256,
+                                 "traffic_source": "ncu dram__bytes_read+write of one launch at 256 recordings (1.03 GB + 3.01 "
+                                                   "GB, profiles/r01_ncu_prof_est64_r1t.csv), scaled to this batch"}}
 
     # ---------------- CPU baseline (rank 0, bounded sample, the reference's algorithm on the host cores) -----------
     cpu = None
