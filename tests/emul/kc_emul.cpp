@@ -21,11 +21,11 @@ static void pack_mlp(const T* W1, const T* b1, const T* W2, int in_dim, int hidd
     }
 }
 
-template <typename T, bool DIAG, int IN, int NH>
+template <typename T, bool DIAG, int IN, int NH, int METHOD = KC_MARCH_EULER>
 static void run(const RodC<T>& P, const MlpC<T>& M, int64_t B, int64_t T_, const T* ten, T* traj, int32_t* iters,
                 T* Gout, T tol, int max_iter, T fd_eps) {
     const int N = P.N;
-    std::vector<T> trajD((size_t)T_ * 25 * N), Hs((size_t)NH * (N - 1));
+    std::vector<T> trajD((size_t)T_ * 25 * N), Hs((size_t)NH * N);   // N history nodes cover the RK4 march too
     T* out = traj;
     for (int64_t b = 0; b < B; ++b) {
         T stmem[KC_SHOOT_SLOTS];
@@ -33,7 +33,7 @@ static void run(const RodC<T>& P, const MlpC<T>& M, int64_t B, int64_t T_, const
         st.reset();
         rollout_init<T, 1>(P, nullptr, nullptr, trajD.data());
         if (iters) iters[b * T_] = 0;
-        rollout_rod<T, DIAG, IN, NH, 1>(P, M, st, ten + b * T_ * 4, trajD.data(), Hs.data(), 0, (int)T_ - 1, tol,
+        rollout_rod<T, DIAG, IN, NH, 1, 1, METHOD>(P, M, st, ten + b * T_ * 4, trajD.data(), Hs.data(), 0, (int)T_ - 1, tol,
                                         max_iter, fd_eps, Gout ? Gout + b * T_ * 6 : nullptr, iters ? iters + b * T_ : nullptr);
         // device layout per rod is [T][N][25] -> reference [T][25][N]
         for (int64_t t = 0; t < T_; ++t)
@@ -182,7 +182,8 @@ static int emul(const kc_rod_params* p, int in_dim, int hidden, const void* W1, 
     const T tl = tol > 0 ? T(tol) : (sizeof(T) == 4 ? T(2e-6) : T(1e-11));
 #define GO(D, I, H)                                                                                             \
     do {                                                                                                        \
-        if (wide == 2) run_wide_lin<T, D, I, H>(P, M, B, T_, (const T*)ten, (T*)traj, iters, (T*)Gout, tl, max_iter, fd_eps); \
+        if (wide == 3) run<T, D, I, H, KC_MARCH_RK4>(P, M, B, T_, (const T*)ten, (T*)traj, iters, (T*)Gout, tl, max_iter, fd_eps); \
+        else if (wide == 2) run_wide_lin<T, D, I, H>(P, M, B, T_, (const T*)ten, (T*)traj, iters, (T*)Gout, tl, max_iter, fd_eps); \
         else if (wide) run_wide<T, D, I, H>(P, M, B, T_, (const T*)ten, (T*)traj, iters, (T*)Gout, tl, max_iter, fd_eps); \
         else run<T, D, I, H>(P, M, B, T_, (const T*)ten, (T*)traj, iters, (T*)Gout, tl, max_iter, fd_eps);      \
     } while (0)
