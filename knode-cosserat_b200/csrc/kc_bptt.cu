@@ -7,7 +7,15 @@
 #include "kc_bptt_core.cuh"
 #include "kc_mlp_coop.cuh"
 
+#include <type_traits>
 template <typename T> int kc_pack_mlp(const kc_mlp* mlp, T* Wp, MlpC<T>& M, cudaStream_t st);
+// kc_knode_tc.cu: joint adjoint march with the MLP input-VJP on tcgen05
+bool kc_knode_tc_eligible(int dtype, const kc_mlp* mlp, int N, int method);
+size_t kc_knode_tc_img_bytes();
+size_t kc_knode_tc_bwd_scratch_bytes(int N, int64_t B);
+int kc_knode_tc_bwd(const RodC<float>& P, const kc_mlp* mlp, int64_t B, int T_, const float* tensions, const float* traj,
+                    const float* gtraj, float* gten, float* xs, float* gos, unsigned char* img, unsigned char* scratch,
+                    cudaStream_t st);
 int kc_check_mlp(const kc_mlp* mlp);
 
 template <typename T, bool DIAG, int IN, int NH>
@@ -55,7 +63,7 @@ kc_rollout_bwd_coop_kernel(const __grid_constant__ RodC<T> P, MlpCoop<T> M, int6
 }
 
 static inline size_t a256(size_t x) { return (x + 255) & ~(size_t)255; }
-struct BpttWs { size_t xs, gos, wp, wc, mlpws, total; int64_t Qs; int64_t mlp_bytes; };
+struct BpttWs { size_t xs, gos, wp, wc, mlpws, tcimg, tcscr, total; int64_t Qs; int64_t mlp_bytes; };
 static BpttWs bptt_ws(int dtype, int N, const kc_mlp* mlp, int64_t B, int64_t T_) {
     const size_t sz = dtype == KC_F32 ? 4 : 8;
     BpttWs w{};
@@ -67,6 +75,8 @@ static BpttWs bptt_ws(int dtype, int N, const kc_mlp* mlp, int64_t B, int64_t T_
     w.wc = off; off += mlp ? a256((size_t)kc_coop_row(mlp->in_dim) * (size_t)((mlp->hidden + 31) & ~31) * sz) : 0;
     w.mlp_bytes = mlp ? kc_ode_bwd_workspace_bytes(dtype, mlp, w.Qs) : 0;
     w.mlpws = off; off += a256((size_t)w.mlp_bytes);
+    w.tcimg = off; off += mlp ? a256(kc_knode_tc_img_bytes()) : 0;
+    w.tcscr = off; off += (mlp && dtype == KC_F32) ? a256(kc_knode_tc_bwd_scratch_bytes(N, B)) : 0;
     w.total = off + 256;
     return w;
 }
@@ -111,7 +121,20 @@ static int bwd_typed(const kc_rod_params* Pp, const kc_mlp* mlp, int64_t B, int6
         if (e && e[0] == '0') coop = false;
         if (e && e[0] == '1' && in_dim != 0) coop = true;
     }
-    if (B > 0 && T_ > 1 && coop) {
+    bool tc = kc_knode_tc_eligible(dtype, mlp, N, KC_MARCH_EULER) && !getenv("KC_ROLLOUT_COOP");
+    {
+        const char* e = getenv("KC_ROLLOUT_TC");
+        if (e && e[0] == '1' && kc_knode_tc_eligible(dtype, mlp, N, KC_MARCH_EULER)) tc = true;
+    }
+    int64_t Qred = w.Qs;   // samples handed to the weight-gradient reduction
+    if (B > 0 && T_ > 1 && tc) {
+        if constexpr (std::is_same<T, float>::value) {
+            int rc = kc_knode_tc_bwd(P, mlp, B, (int)T_, (const float*)tensions, (const float*)traj, (const float*)gtraj,
+                                     (float*)gten, xs, gos, ws + w.tcimg, ws + w.tcscr, st);
+            if (rc) return rc;
+        }
+        Qred = B * (T_ - 1) * (N - 1);   // the joint adjoint march emits ONE (x, dL/do) sample per node
+    } else if (B > 0 && T_ > 1 && coop) {
         MlpCoop<T> MC;
         static_cast<MlpC<T>&>(MC) = M;
         MC.Hp = (mlp->hidden + 31) & ~31;
@@ -158,7 +181,7 @@ static int bwd_typed(const kc_rod_params* Pp, const kc_mlp* mlp, int64_t B, int6
         KC_CHECK_LAUNCH("kc_rollout_bwd_kernel");
     }
     if (mlp && (gW1 || gb1 || gW2 || gb2))
-        return kc_mlp_bwd(dtype, mlp, (B > 0 && T_ > 1) ? w.Qs : 0, xs, gos, nullptr, gW1, gb1, gW2, gb2, ws + w.mlpws,
+        return kc_mlp_bwd(dtype, mlp, (B > 0 && T_ > 1) ? Qred : 0, xs, gos, nullptr, gW1, gb1, gW2, gb2, ws + w.mlpws,
                           w.mlp_bytes, (void*)st);
     return KC_OK;
 }

@@ -1,0 +1,761 @@
+// kc_knode_tc.cu — the KNODE residual MLP INSIDE the shooting march on the Blackwell tensor cores (tcgen05 + TMEM):
+// north-star subsystem 2 for the rollout (knode.simulate with CosseratRod.get_nn_output in the ODE, cosserat_ode.py:169-184,
+// cosserat_ode_torch.py:192-212) and for back-propagation through it (subsystem 3).  fp32 model, 28 inputs, hidden <= 512.
+//
+// One CTA = 128 "rows" = the 128 lanes of TMEM.  A row is one marched point of one rod: 16 rods x 8 points per CTA
+// (forward: base point + 6 finite-difference points of the Newton shooting solve, as kc_rollout_wide_kernel; backward:
+// the loss-seeded adjoint march + 6 unit-seeded adjoint marches, see below).  All 128 rows step through the nodes of the
+// march together, so every node evaluation is ONE [128 x 32] x [32 x H] x [H x 32] MLP for the whole CTA:
+//
+//   warps 0-3  (128 threads) physics of their row on the FP32 pipes, then each writes its 28 inputs (+1 for the bias) as
+//              a bf16 hi/lo row of the X tile in shared memory and arrives on barX;
+//   warp 8     one elected thread issues the MMAs: Z_c = X W1_c^T (kind::f16, 3-pass bf16 hi/lo split = fp32-grade
+//              products: hi*hi + lo*hi + hi*lo) into a ring of TMEM buffers, commits barZ[buf];
+//   warps 0-7  epilogue: tcgen05.ld Z_c -> ELU -> bf16 hi/lo -> tcgen05.st back INTO THE SAME TMEM COLUMNS (the activation
+//              tile never touches shared memory), arrive on barA[buf];
+//   warp 8     O += A_c W2_c^T with the A operand read from TMEM (".ts" MMA), B = the resident W2 image; then the next
+//              Z chunk into the freed buffer; after the last chunk commits barO;
+//   warps 0-3  tcgen05.ld their row of O (25 outputs) and continue the physics (ys += o[0:19], z += o[19:25], Euler).
+//
+// Both weight images (bf16 hi|lo, K-major, no swizzle: the layouts pinned by kc_umma_selftest) stay resident in shared
+// memory for the whole kernel: 128 KB forward, 192 KB backward (W1, W2^T, W1^T).
+//
+// Backward (kc_rollout_bwd for this shape): per time step ONE joint adjoint march.  Row 0 of a rod carries the cotangent of
+// the loss, rows 1..6 carry unit cotangents on the tip's (n, m): their result at the base is the EXACT transposed shooting
+// Jacobian (no finite differences), the implicit-function multiplier mu solves a 6x6 system per rod, and because the
+// adjoint march is linear in its seed the implicit part is the mu-weighted sum of rows 1..6 — combined with warp shuffles
+// afterwards.  The MLP input-VJP per node is three GEMMs: Z = X W1^T (recompute), dA = GO W2, gX = (dA * ELU'(Z)) W1, the
+// last one again with its A operand in TMEM.  Weight gradients: one (x, dL/do) sample per node goes to the tensor-core
+// sample reduction of the training step (kc_mlp_bwd).
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cstdlib>
+#include "kc_rollout_wide.cuh"
+#include "kc_adjoint.cuh"
+#include "kc_umma.cuh"
+
+namespace ktc {
+constexpr int THREADS = 288;          // warps 0-3 physics + epilogue, 4-7 epilogue, 8 MMA issue
+constexpr int RPC = 16;               // rods per CTA (8 rows each)
+constexpr int NBUF = 3;               // TMEM ring: 3 x 128 columns + 32 columns of output
+constexpr int COL_O = 384;
+constexpr int IMG = 32768;            // one bf16 image (hi or lo) of a [512 x 32] / [32 x 512] weight matrix
+// forward shared memory
+constexpr int F_W1 = 0, F_W2 = 2 * IMG, F_X = 4 * IMG, F_MISC = F_X + 16384, F_HIST = F_MISC + 256;
+// backward shared memory
+constexpr int B_W1 = 0, B_W2T = 2 * IMG, B_W1T = 4 * IMG, B_X = 6 * IMG, B_GO = B_X + 16384, B_MISC = B_GO + 16384,
+              B_BYTES = B_MISC + 256;
+constexpr int SV = 37;                // scratch values per row and node in the backward: 12 history + 25 output cotangents
+
+struct Bars {
+    uint64_t X, O, Z[NBUF], A[NBUF];
+    uint32_t tmem_slot;
+    uint32_t exit_flag;
+};
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+    const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&v);
+}
+// two values -> one packed pair of bf16 "hi" (even element in the low half) and one packed pair of bf16 "lo" = x - hi.
+// hi is the fp32 word rounded to its upper half with integer arithmetic (nothing on the XU pipe, cf. kc_train_tc.cu).
+__device__ __forceinline__ void split_pair(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    const uint32_t a = (__float_as_uint(x0) + 0x8000u) & 0xffff0000u;
+    const uint32_t b = (__float_as_uint(x1) + 0x8000u) & 0xffff0000u;
+    hi = __byte_perm(a, b, 0x7632);
+    lo = pack_bf16x2(x0 - __uint_as_float(a), x1 - __uint_as_float(b));
+}
+// 32 values of one row -> the row's bf16 hi/lo entries of a [128 x 32] K-major tile (4 x 16-byte stores each)
+__device__ __forceinline__ void store_row32(unsigned char* tile_hi, int row, const float v[32]) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) split_pair(v[8 * g + 2 * i], v[8 * g + 2 * i + 1], h[i], l[i]);
+        const uint32_t o = umma::kmajor_off_b16(row, 8 * g, 32);
+        *reinterpret_cast<uint4*>(tile_hi + o) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(tile_hi + 8192 + o) = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+}
+// all 128 physics threads (warps 0-3): logical AND of a predicate, named barrier 1
+__device__ __forceinline__ bool all128(bool p) {
+    uint32_t r;
+    asm volatile(
+        "{\n\t.reg .pred q, o;\n\t"
+        "setp.ne.u32 q, %1, 0;\n\t"
+        "bar.red.and.pred o, 1, 128, q;\n\t"
+        "selp.u32 %0, 1, 0, o;\n\t}" : "=r"(r) : "r"((uint32_t)p) : "memory");
+    return r != 0;
+}
+__device__ __forceinline__ void sync128() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// ---- epilogues (warps 0-7; `half` = 0 for warps 0-3, 1 for warps 4-7) -------------------------------------------------
+// forward: a Z chunk is 128 columns; this thread turns its 64 columns into ELU(z) as bf16 hi | lo IN PLACE: the 32 columns
+// [s, s+32) of a sub-block become 16 packed hi columns [s, s+16) and 16 packed lo columns [s+16, s+32).
+__device__ __forceinline__ void fwd_epilogue(uint32_t taddr) {   // taddr -> this thread's lane block, first of its 64 columns
+    uint32_t v0[32], v1[32];
+    umma::ld32(taddr, v0);
+    umma::ld32(taddr + 32, v1);
+    umma::wait_ld();
+    uint32_t hi[16], lo[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+        split_pair(kc_elu(__uint_as_float(v0[2 * i])), kc_elu(__uint_as_float(v0[2 * i + 1])), hi[i], lo[i]);
+    umma::st16(taddr, hi);
+    umma::st16(taddr + 16, lo);
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+        split_pair(kc_elu(__uint_as_float(v1[2 * i])), kc_elu(__uint_as_float(v1[2 * i + 1])), hi[i], lo[i]);
+    umma::st16(taddr + 32, hi);
+    umma::st16(taddr + 48, lo);
+    umma::wait_st();
+}
+// backward: a buffer is Z chunk (64 columns) | dA chunk (64 columns); this thread's 32 units: dz = dA * ELU'(z) as bf16
+// hi | lo over its own 32 Z columns.
+__device__ __forceinline__ void bwd_epilogue(uint32_t taddr) {   // taddr -> lane block, buffer base + half*32
+    uint32_t z[32], d[32];
+    umma::ld32(taddr, z);
+    umma::ld32(taddr + 64, d);
+    umma::wait_ld();
+    uint32_t hi[16], lo[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const float z0 = __uint_as_float(z[2 * i]), z1 = __uint_as_float(z[2 * i + 1]);
+        const float e0 = z0 > 0.f ? 1.f : kc_exp_fast(z0), e1 = z1 > 0.f ? 1.f : kc_exp_fast(z1);
+        split_pair(__uint_as_float(d[2 * i]) * e0, __uint_as_float(d[2 * i + 1]) * e1, hi[i], lo[i]);
+    }
+    umma::st16(taddr, hi);
+    umma::st16(taddr + 16, lo);
+    umma::wait_st();
+}
+}  // namespace ktc
+
+// MLP views handed to node_eval / the adjoint node step: overload resolution on these types selects the CTA-cooperative
+// tensor-core evaluation (as MlpCoop selects the warp-cooperative one).
+struct MlpTCF : MlpC<float> {
+    unsigned char* sm;
+    ktc::Bars* bars;
+    uint32_t tbase, laneblk;
+    int nch, row;
+    mutable uint32_t ph;   // bit b: parity of barZ[b]; bit 3: parity of barO
+};
+
+// forward: o[25] = W2 ELU(W1 x + b1) + b2 for this thread's row; called by all 128 physics threads together
+template <typename T, int IN>
+__device__ __forceinline__ void mlp_eval(const MlpTCF& M, const float* __restrict__ x, float* __restrict__ o) {
+    static_assert(IN == 28, "tensor-core march: 28 inputs");
+    float xv[32];
+#pragma unroll
+    for (int i = 0; i < 28; ++i) xv[i] = x[i];
+    xv[28] = 1.f; xv[29] = 0.f; xv[30] = 0.f; xv[31] = 0.f;      // column 28 carries b1
+    ktc::store_row32(M.sm + ktc::F_X, M.row, xv);
+    umma::fence_async_smem();
+    umma::fence_before();                                         // (orders this thread's last TMEM read of O before the next MMAs)
+    umma::mbar_arrive(&M.bars->X);
+    for (int c = 0; c < M.nch; ++c) {
+        const int buf = c % ktc::NBUF;
+        umma::mbar_wait(&M.bars->Z[buf], (M.ph >> buf) & 1u);
+        M.ph ^= 1u << buf;
+        umma::fence_after();
+        ktc::fwd_epilogue(M.tbase + M.laneblk + buf * 128);
+        umma::fence_before();
+        umma::mbar_arrive(&M.bars->A[buf]);
+    }
+    umma::mbar_wait(&M.bars->O, (M.ph >> 3) & 1u);
+    M.ph ^= 8u;
+    umma::fence_after();
+    uint32_t v[32];
+    umma::ld32(M.tbase + M.laneblk + ktc::COL_O, v);
+    umma::wait_ld();
+#pragma unroll
+    for (int c = 0; c < 25; ++c) o[c] = __uint_as_float(v[c]) + M.b2[c];
+}
+
+struct MlpTCB : MlpTCF {};
+// backward: gx[28] = W1^T ((W2^T go) * ELU'(W1 x + b1)) for this thread's row
+template <typename T, int IN>
+__device__ __forceinline__ void mlp_input_vjp(const MlpTCB& M, const float* __restrict__ x, const float* __restrict__ go,
+                                              float* __restrict__ gx) {
+    static_assert(IN == 28, "tensor-core march: 28 inputs");
+    float xv[32];
+#pragma unroll
+    for (int i = 0; i < 28; ++i) xv[i] = x[i];
+    xv[28] = 1.f; xv[29] = 0.f; xv[30] = 0.f; xv[31] = 0.f;
+    ktc::store_row32(M.sm + ktc::B_X, M.row, xv);
+#pragma unroll
+    for (int i = 0; i < 25; ++i) xv[i] = go[i];
+#pragma unroll
+    for (int i = 25; i < 32; ++i) xv[i] = 0.f;
+    ktc::store_row32(M.sm + ktc::B_GO, M.row, xv);
+    umma::fence_async_smem();
+    umma::fence_before();
+    umma::mbar_arrive(&M.bars->X);
+    for (int c = 0; c < M.nch; ++c) {      // nch = chunks of 64 units here
+        const int buf = c % ktc::NBUF;
+        umma::mbar_wait(&M.bars->Z[buf], (M.ph >> buf) & 1u);
+        M.ph ^= 1u << buf;
+        umma::fence_after();
+        ktc::bwd_epilogue(M.tbase + M.laneblk + buf * 128);
+        umma::fence_before();
+        umma::mbar_arrive(&M.bars->A[buf]);
+    }
+    umma::mbar_wait(&M.bars->O, (M.ph >> 3) & 1u);
+    M.ph ^= 8u;
+    umma::fence_after();
+    uint32_t v[32];
+    umma::ld32(M.tbase + M.laneblk + ktc::COL_O, v);
+    umma::wait_ld();
+#pragma unroll
+    for (int k = 0; k < 28; ++k) gx[k] = __uint_as_float(v[k]);
+}
+
+namespace ktc {
+// ---- the helper warps (4-7): second half of every epilogue, until the exit flag is raised ------------------------------
+template <bool BWD>
+__device__ __forceinline__ void helper_loop(Bars* bars, uint32_t tbase, uint32_t laneblk, int nch) {
+    uint32_t ph = 0;
+    while (true) {
+        for (int c = 0; c < nch; ++c) {
+            const int buf = c % NBUF;
+            umma::mbar_wait(&bars->Z[buf], (ph >> buf) & 1u);
+            ph ^= 1u << buf;
+            if (*reinterpret_cast<volatile uint32_t*>(&bars->exit_flag)) return;
+            umma::fence_after();
+            if (BWD) bwd_epilogue(tbase + laneblk + buf * 128 + 32);
+            else fwd_epilogue(tbase + laneblk + buf * 128 + 64);
+            umma::fence_before();
+            umma::mbar_arrive(&bars->A[buf]);
+        }
+    }
+}
+
+// ---- the MMA thread (warp 8, lane 0) -----------------------------------------------------------------------------------
+// forward: Z chunk c = 128 units.  X: [128 x 32] K-major (LBO 128, SBO 512); W1 image rows = units (chunk c at c*8192);
+// W2 image [32 outs x 512 units] K-major (LBO 128, SBO 8192), 16 units = 256 bytes.
+__device__ __forceinline__ void mma_loop_fwd(unsigned char* sm, Bars* bars, uint32_t tbase, int nch) {
+    const uint32_t idZ = umma::make_idesc_bf16(128, 128), idO = umma::make_idesc_bf16(128, 32);
+    const uint32_t aX = umma::smem_u32(sm + F_X), aW1 = umma::smem_u32(sm + F_W1), aW2 = umma::smem_u32(sm + F_W2);
+    uint32_t phX = 0, phA = 0;
+    auto gemm1 = [&](int c) {
+        const uint32_t d = tbase + (c % NBUF) * 128, w = aW1 + c * 8192;
+        uint32_t acc = 0;
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+            const uint32_t a = p == 1 ? aX + 8192 : aX, b = p == 2 ? w + IMG : w;
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk) {
+                umma::mma_bf16(d, umma::make_desc(a + kk * 256, 128, 512), umma::make_desc(b + kk * 256, 128, 512), idZ, acc);
+                acc = 1;
+            }
+        }
+        umma::commit(&bars->Z[c % NBUF]);
+    };
+    while (true) {
+        umma::mbar_wait(&bars->X, phX);
+        phX ^= 1;
+        if (*reinterpret_cast<volatile uint32_t*>(&bars->exit_flag)) {
+            umma::mbar_arrive(&bars->Z[0]);      // releases the helper warps, which then see the flag
+            return;
+        }
+        umma::fence_after();
+        for (int c = 0; c < nch && c < NBUF; ++c) gemm1(c);
+        for (int c = 0; c < nch; ++c) {
+            const int buf = c % NBUF;
+            umma::mbar_wait(&bars->A[buf], (phA >> buf) & 1u);
+            phA ^= 1u << buf;
+            umma::fence_after();
+            uint32_t acc = c > 0 ? 1u : 0u;
+#pragma unroll
+            for (int p = 0; p < 3; ++p) {
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) {
+                    const uint32_t a = tbase + buf * 128 + (kk >> 2) * 64 + ((kk >> 1) & 1) * 32 + (kk & 1) * 8 + (p == 1 ? 16 : 0);
+                    const uint32_t b = aW2 + (p == 2 ? IMG : 0) + (c * 8 + kk) * 256;
+                    umma::mma_bf16_ts(tbase + COL_O, a, umma::make_desc(b, 128, 8192), idO, acc);
+                    acc = 1;
+                }
+            }
+            if (c + NBUF < nch) gemm1(c + NBUF);
+        }
+        umma::commit(&bars->O);
+    }
+}
+// backward: chunk c = 64 units; buffer = Z (64 columns) | dA (64 columns).  W1 / W2^T images: rows = units (chunk c at
+// c*4096); GO tile as X; W1^T image [32 inputs x 512 units] K-major as the forward W2 image.
+__device__ __forceinline__ void mma_loop_bwd(unsigned char* sm, Bars* bars, uint32_t tbase, int nch) {
+    const uint32_t idZ = umma::make_idesc_bf16(128, 64), idO = umma::make_idesc_bf16(128, 32);
+    const uint32_t aX = umma::smem_u32(sm + B_X), aGO = umma::smem_u32(sm + B_GO), aW1 = umma::smem_u32(sm + B_W1),
+                   aW2T = umma::smem_u32(sm + B_W2T), aW1T = umma::smem_u32(sm + B_W1T);
+    uint32_t phX = 0, phA = 0;
+    auto gemm13 = [&](int c) {
+        const uint32_t d = tbase + (c % NBUF) * 128;
+#pragma unroll
+        for (int which = 0; which < 2; ++which) {
+            const uint32_t at = which ? aGO : aX, w = (which ? aW2T : aW1) + c * 4096;
+            uint32_t acc = 0;
+#pragma unroll
+            for (int p = 0; p < 3; ++p) {
+                const uint32_t a = p == 1 ? at + 8192 : at, b = p == 2 ? w + IMG : w;
+#pragma unroll
+                for (int kk = 0; kk < 2; ++kk) {
+                    umma::mma_bf16(d + which * 64, umma::make_desc(a + kk * 256, 128, 512), umma::make_desc(b + kk * 256, 128, 512), idZ, acc);
+                    acc = 1;
+                }
+            }
+        }
+        umma::commit(&bars->Z[c % NBUF]);
+    };
+    while (true) {
+        umma::mbar_wait(&bars->X, phX);
+        phX ^= 1;
+        if (*reinterpret_cast<volatile uint32_t*>(&bars->exit_flag)) {
+            umma::mbar_arrive(&bars->Z[0]);
+            return;
+        }
+        umma::fence_after();
+        for (int c = 0; c < nch && c < NBUF; ++c) gemm13(c);
+        for (int c = 0; c < nch; ++c) {
+            const int buf = c % NBUF;
+            umma::mbar_wait(&bars->A[buf], (phA >> buf) & 1u);
+            phA ^= 1u << buf;
+            umma::fence_after();
+            uint32_t acc = c > 0 ? 1u : 0u;
+#pragma unroll
+            for (int p = 0; p < 3; ++p) {
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    const uint32_t a = tbase + buf * 128 + (kk >> 1) * 32 + (kk & 1) * 8 + (p == 1 ? 16 : 0);
+                    const uint32_t b = aW1T + (p == 2 ? IMG : 0) + (c * 4 + kk) * 256;
+                    umma::mma_bf16_ts(tbase + COL_O, a, umma::make_desc(b, 128, 8192), idO, acc);
+                    acc = 1;
+                }
+            }
+            if (c + NBUF < nch) gemm13(c + NBUF);
+        }
+        umma::commit(&bars->O);
+    }
+}
+
+// common prologue: TMEM, barriers, resident weight images
+__device__ __forceinline__ Bars* cta_setup(unsigned char* sm, int misc_off, const unsigned char* __restrict__ img, int img_bytes) {
+    Bars* bars = reinterpret_cast<Bars*>(sm + misc_off);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (warp == 0) umma::tmem_alloc(&bars->tmem_slot, 512);
+    if (tid == 32) {
+        umma::mbar_init(&bars->X, 128);
+        umma::mbar_init(&bars->O, 1);
+        for (int i = 0; i < NBUF; ++i) { umma::mbar_init(&bars->Z[i], 1); umma::mbar_init(&bars->A[i], 256); }
+        bars->exit_flag = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    const uint4* src = reinterpret_cast<const uint4*>(img);
+    uint4* dst = reinterpret_cast<uint4*>(sm);
+    for (int e = tid; e < img_bytes / 16; e += THREADS) dst[e] = src[e];
+    umma::fence_async_smem();
+    umma::fence_before();
+    __syncthreads();
+    umma::fence_after();
+    return bars;
+}
+__device__ __forceinline__ void cta_teardown(Bars* bars, uint32_t tbase) {
+    // physics threads: raise the flag, then a last arrival on barX wakes the MMA thread, which releases the helpers
+    const int tid = threadIdx.x;
+    if (tid < 128) {
+        if (tid == 0) *reinterpret_cast<volatile uint32_t*>(&bars->exit_flag) = 1u;
+        sync128();
+        __threadfence_block();
+        umma::fence_before();
+        umma::mbar_arrive(&bars->X);
+    }
+    umma::fence_before();
+    __syncthreads();
+    if ((tid >> 5) == 0) umma::tmem_dealloc(tbase, 512);
+}
+
+template <typename T> __device__ __forceinline__ T* rod_base_tc(T* trajD, int64_t b, int T_, int N) {
+    return trajD + (size_t)(b >> 5) * ((size_t)T_ * N * 25 * 32) + (b & 31);
+}
+}  // namespace ktc
+
+// =========================================================================================================================
+// Forward: KNODE rollout, 16 rods per CTA, Newton shooting solve with a per-march finite-difference Jacobian (the logic of
+// kc_rollout_wide_kernel), MLP on tcgen05.  Trajectory in the device layout [tile][T][N][25][32] (transposed afterwards).
+template <bool DIAG>
+__global__ void __launch_bounds__(ktc::THREADS, 1)
+kc_knode_tc_fwd_kernel(const __grid_constant__ RodC<float> P, const unsigned char* __restrict__ img, const float* __restrict__ b2,
+                       int hidden, int64_t B, int T_, const float* __restrict__ tensions, const float* __restrict__ y0,
+                       const float* __restrict__ z0, float* trajD, float tol, int max_iter, float fd_eps, float* Gout,
+                       int32_t* iters) {
+    extern __shared__ __align__(1024) unsigned char sm[];
+    constexpr int NH = 12, WG = ktc::RPC, LS = 32;
+    const int N = P.N, tid = threadIdx.x, warp = tid >> 5;
+    ktc::Bars* bars = ktc::cta_setup(sm, ktc::F_MISC, img, 4 * ktc::IMG);
+    const uint32_t tbase = bars->tmem_slot;
+    const uint32_t laneblk = (uint32_t)((warp & 3) * 32) << 16;
+    const int nch = (hidden + 127) / 128;
+    if (warp == 8) {
+        if ((tid & 31) == 0) ktc::mma_loop_fwd(sm, bars, tbase, nch);
+        __syncwarp();
+    } else if (warp >= 4) {
+        ktc::helper_loop<false>(bars, tbase, laneblk, nch);
+    } else {
+        MlpTCF M{};
+        M.sm = sm; M.bars = bars; M.tbase = tbase; M.laneblk = laneblk; M.nch = nch; M.row = tid; M.ph = 0; M.b2 = b2;
+        M.hidden = hidden; M.in_dim = 28;
+        const int lane = tid & 31, g = tid >> 3, k = tid & 7;
+        const unsigned full = 0xffffffffu;
+        const int64_t b_raw = (int64_t)blockIdx.x * WG + g;
+        const bool valid = b_raw < B;
+        const int64_t b = valid ? b_raw : B - 1;   // surplus groups shadow the last rod and never store
+        float* Hs = reinterpret_cast<float*>(sm + ktc::F_HIST) + g;
+        float* traj_b = ktc::rod_base_tc(trajD, b, T_, N);
+        const size_t tstride = (size_t)25 * N * LS;
+        if (k == 0 && valid) {
+            rollout_init<float, LS>(P, y0 ? y0 + (size_t)b * 19 * N : nullptr, z0 ? z0 + (size_t)b * 6 * N : nullptr, traj_b);
+            if (Gout) {
+#pragma unroll
+                for (int i = 0; i < 6; ++i) Gout[(size_t)b * T_ * 6 + i] = 0.f;
+            }
+            if (iters) iters[(size_t)b * T_] = 0;
+        }
+        __threadfence_block();
+        ktc::sync128();   // (surplus groups read the last rod's initial state written by another warp)
+        auto build_hist = [&](const float* cur, const float* prev) {
+            for (int e = k; e < (N - 1) * NH; e += 8) {
+                const int j = e / NH, s = e - j * NH;
+                const size_t o = ((size_t)j * 25 + slot_row<NH>(s)) * LS;
+                Hs[(size_t)e * WG] = P.c1 * cur[o] + P.c2 * prev[o];
+            }
+        };
+        build_hist(traj_b, traj_b);
+        float zlast[6];   // z[:, N-1] is never written by the march (cosserat_ode.py:198-201)
+#pragma unroll
+        for (int c = 0; c < 6; ++c) zlast[c] = traj_b[((size_t)(N - 1) * 25 + 19 + c) * LS];
+        __syncwarp();
+        float G[6], Gm1[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) { G[i] = 0.f; Gm1[i] = 0.f; }
+        const float* ten = tensions + (size_t)b * T_ * 4;
+        for (int t = 0; t < T_ - 1; ++t) {
+            float tn[4], tf[3];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) tn[i] = ten[(size_t)t * 4 + i];
+            tendon_force(P, tn, tf);
+            float* nxt = traj_b + (size_t)(t + 1) * tstride;
+            float Gp[6];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) { Gp[i] = G[i]; G[i] = G[i] + (G[i] - Gm1[i]); }   // linear predictor
+            bool done = false;
+            int status = 0, marches = 0;
+            HistView<float, NH, WG> H{Hs};
+            while (true) {
+                float eps[6], Ge[6], F[6];
+                wide_eps(G, fd_eps, eps);
+#pragma unroll
+                for (int i = 0; i < 6; ++i) Ge[i] = G[i] + ((k == i + 1) ? eps[i] : 0.f);
+                TrajSinkPred<float, LS, NH, WG> S{nxt, nullptr, k == 0 && !done && valid, N - 1};
+                rod_march<float, DIAG, 28, NH>(P, M, Ge, tf, H, S, F);
+                float Fall[7][6];
+#pragma unroll
+                for (int c = 0; c < 7; ++c) {
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) Fall[c][i] = __shfl_sync(full, F[i], (lane & ~7) | c);
+                }
+                if (!done) {
+                    ++marches;
+                    const int r = wide_decide(Fall, G, eps, tol);
+                    if (r != 0) { done = true; status = r; }
+                    else if (marches >= max_iter) { done = true; status = -1; }
+                }
+                if (ktc::all128(done)) break;
+            }
+#pragma unroll
+            for (int i = 0; i < 6; ++i) Gm1[i] = Gp[i];
+            if (k == 0 && valid) {
+                const size_t o = (size_t)(N - 1) * 25 * LS;
+#pragma unroll
+                for (int c = 0; c < 6; ++c) nxt[o + (19 + c) * LS] = zlast[c];
+                if (Gout) {
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) Gout[((size_t)b * T_ + t + 1) * 6 + i] = G[i];
+                }
+                if (iters) iters[(size_t)b * T_ + t + 1] = status > 0 ? marches : -marches;
+            }
+            __threadfence_block();
+            ktc::sync128();   // the new state (written by the rod's base lane, maybe of another warp for shadow groups)
+            build_hist(nxt, nxt - tstride);
+            __syncwarp();
+        }
+    }
+    ktc::cta_teardown(bars, tbase);
+}
+
+// =========================================================================================================================
+// Backward through the rollout for the same shape: persistent CTAs over groups of 16 rods, steps in reverse, ONE joint
+// adjoint march per step (see the header).  traj / gtraj in the reference layout [B][T][25][N].
+//   rowscr : per CTA [(N-1)*SV][128] floats — per node and row: 12 history cotangents, 25 output cotangents
+//   hscr   : per CTA [3][(N-1)*12][16] floats — history cotangents of steps t+1, t+2 and the one being built
+template <bool DIAG>
+__global__ void __launch_bounds__(ktc::THREADS, 1)
+kc_knode_tc_bwd_kernel(const __grid_constant__ RodC<float> P, const unsigned char* __restrict__ img, int hidden, int64_t B,
+                       int T_, const float* __restrict__ tensions, const float* __restrict__ traj,
+                       const float* __restrict__ gtraj, float* __restrict__ gten, float* __restrict__ xs,
+                       float* __restrict__ gos, float* __restrict__ rowscr_all, float* __restrict__ hscr_all) {
+    extern __shared__ __align__(1024) unsigned char sm[];
+    constexpr int NH = 12, WG = ktc::RPC, SV = ktc::SV;
+    const int N = P.N, Nm1 = N - 1, tid = threadIdx.x, warp = tid >> 5;
+    ktc::Bars* bars = ktc::cta_setup(sm, ktc::B_MISC, img, 6 * ktc::IMG);
+    const uint32_t tbase = bars->tmem_slot;
+    const uint32_t laneblk = (uint32_t)((warp & 3) * 32) << 16;
+    const int nch = (hidden + 63) / 64;
+    if (warp == 8) {
+        if ((tid & 31) == 0) ktc::mma_loop_bwd(sm, bars, tbase, nch);
+        __syncwarp();
+    } else if (warp >= 4) {
+        ktc::helper_loop<true>(bars, tbase, laneblk, nch);
+    } else {
+        MlpTCB M{};
+        M.sm = sm; M.bars = bars; M.tbase = tbase; M.laneblk = laneblk; M.nch = nch; M.row = tid; M.ph = 0;
+        M.hidden = hidden; M.in_dim = 28;
+        const int lane = tid & 31, g = tid >> 3, k = tid & 7;
+        const unsigned full = 0xffffffffu;
+        float* rowscr = rowscr_all + (size_t)blockIdx.x * Nm1 * SV * 128 + tid;
+        float* hscr = hscr_all + (size_t)blockIdx.x * 3 * Nm1 * NH * WG + g;
+        const size_t harr = (size_t)Nm1 * NH * WG;
+        const size_t ts = (size_t)25 * N;
+        const int64_t ngroups = (B + WG - 1) / WG;
+        for (int64_t grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+            const int64_t b_raw = grp * WG + g;
+            const bool valid = b_raw < B;
+            const int64_t b = valid ? b_raw : B - 1;
+            const float* traj_b = traj + (size_t)b * T_ * ts;
+            const float* gtraj_b = gtraj + (size_t)b * T_ * ts;
+            const float* ten = tensions + (size_t)b * T_ * 4;
+            int ia = 0, ib = 1, ic = 2;   // hscr arrays: g_hist of step t+1, of step t+2, of step t (being built)
+            for (int e = k; e < Nm1 * NH; e += 8) { hscr[ia * harr + (size_t)e * WG] = 0.f; hscr[ib * harr + (size_t)e * WG] = 0.f; }
+            __syncwarp();
+            for (int t = T_ - 2; t >= 0; --t) {
+                const float* s1 = traj_b + (size_t)(t + 1) * ts;
+                const float* s0 = traj_b + (size_t)t * ts;
+                const float* sm1 = traj_b + (size_t)(t > 0 ? t - 1 : 0) * ts;
+                const float* lam = gtraj_b + (size_t)(t + 1) * ts;
+                const float* Ha = hscr + ia * harr;
+                const float* Hb = hscr + ib * harr;
+                float tn[4], tf[3];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) tn[i] = ten[(size_t)t * 4 + i];
+                tendon_force(P, tn, tf);
+                float yb[19], gtf_acc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+                for (int r = 0; r < 19; ++r) yb[r] = k == 0 ? lam[r * N + (N - 1)] : ((k >= 1 && k <= 6 && r == 6 + k) ? 1.f : 0.f);
+                for (int j = Nm1 - 1; j >= 0; --j) {
+                    float y[19], hist[NH], cys[19], cz[6];
+#pragma unroll
+                    for (int r = 0; r < 19; ++r) { y[r] = s1[r * N + j]; cys[r] = P.ds * yb[r]; }
+#pragma unroll
+                    for (int s = 0; s < NH; ++s) hist[s] = P.c1 * s0[(13 + s) * N + j] + P.c2 * sm1[(13 + s) * N + j];
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) {
+                        float v = 0.f;
+                        if (k == 0) v = lam[(19 + c) * N + j] + P.c1 * Ha[(size_t)(j * NH + 6 + c) * WG] + P.c2 * Hb[(size_t)(j * NH + 6 + c) * WG];
+                        cz[c] = v;
+                    }
+                    // MLP part: x = [y; z_pre; tf], go = [cys; cz]
+                    float ys0[19], zp[6], x[28], go[25], gx[28];
+                    rod_ode<float, DIAG>(P, y, hist, hist + 3, hist + 6, hist + 9, tf, ys0, zp);
+#pragma unroll
+                    for (int i = 0; i < 19; ++i) { x[i] = y[i]; go[i] = cys[i]; }
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) { x[19 + i] = zp[i]; go[19 + i] = cz[i]; }
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) x[25 + i] = tf[i];
+                    if (k == 0 && valid) {
+                        float* xq = xs + (((size_t)b * (T_ - 1) + t) * Nm1 + j) * 28;
+#pragma unroll
+                        for (int i = 0; i < 28; i += 4) *reinterpret_cast<float4*>(xq + i) = make_float4(x[i], x[i + 1], x[i + 2], x[i + 3]);
+                    }
+                    float* rs = rowscr + (size_t)j * SV * 128;
+#pragma unroll
+                    for (int c = 0; c < 25; ++c) rs[(size_t)(NH + c) * 128] = go[c];
+                    mlp_input_vjp<float, 28>(M, x, go, gx);
+                    float czt[6], gy[19], gqh[3], gwh[3], gvh[3], guh[3], gtf[3];
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) czt[i] = cz[i] + gx[19 + i];
+                    rod_ode_vjp<float, DIAG>(P, y, hist, hist + 3, hist + 6, hist + 9, tf, cys, czt, gy, gqh, gwh, gvh, guh, gtf);
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        rs[(size_t)i * 128] = gqh[i]; rs[(size_t)(3 + i) * 128] = gwh[i];
+                        rs[(size_t)(6 + i) * 128] = gvh[i]; rs[(size_t)(9 + i) * 128] = guh[i];
+                        gtf_acc[i] += gtf[i] + gx[25 + i];
+                    }
+                    // cotangent of y_j: direct (loss + later histories) + pass-through of the Euler update + node Jacobian
+#pragma unroll
+                    for (int r = 0; r < 19; ++r) {
+                        float d = 0.f;
+                        if (k == 0) {
+                            d = lam[r * N + j];
+                            if (r >= 13) d += P.c1 * Ha[(size_t)(j * NH + r - 13) * WG] + P.c2 * Hb[(size_t)(j * NH + r - 13) * WG];
+                        }
+                        yb[r] = d + yb[r] + gy[r] + gx[r];
+                    }
+                }
+                // implicit function theorem: rows 1..6 hold d y_N[7+i] / d G at the base -> A mu = Gbar, A[kx][i] = yb_i[7+kx]
+                float A[36], mu[6];
+#pragma unroll
+                for (int kx = 0; kx < 6; ++kx) {
+                    mu[kx] = __shfl_sync(full, yb[7 + kx], lane & ~7);
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) A[kx * 6 + i] = __shfl_sync(full, yb[7 + kx], (lane & ~7) | (i + 1));
+                }
+#pragma unroll
+                for (int p = 0; p < 6; ++p) {      // Gaussian elimination, no pivoting (A = [[I, X^T], [0, I]] + small)
+                    const float ip = 1.f / A[p * 6 + p];
+#pragma unroll
+                    for (int r = p + 1; r < 6; ++r) {
+                        const float f = A[r * 6 + p] * ip;
+#pragma unroll
+                        for (int c = p + 1; c < 6; ++c) A[r * 6 + c] -= f * A[p * 6 + c];
+                        mu[r] -= f * mu[p];
+                    }
+                }
+#pragma unroll
+                for (int r = 5; r >= 0; --r) {
+                    float s = mu[r];
+#pragma unroll
+                    for (int c = r + 1; c < 6; ++c) s -= A[r * 6 + c] * mu[c];
+                    mu[r] = s / A[r * 6 + r];
+                }
+                // total cotangent = row 0 + sum_i (-mu_i) row_i: weight of this lane's row
+                float wk = k == 0 ? 1.f : 0.f;
+#pragma unroll
+                for (int i = 0; i < 6; ++i) if (k == i + 1) wk = -mu[i];
+                float* Hc = hscr + ic * harr;
+                __syncwarp();
+                for (int v0 = 0; v0 < Nm1 * SV; v0 += 8) {
+                    float tot[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const int v = v0 + q;
+                        float a = v < Nm1 * SV ? rowscr[(size_t)v * 128] * wk : 0.f;
+                        a += __shfl_xor_sync(full, a, 1);
+                        a += __shfl_xor_sync(full, a, 2);
+                        a += __shfl_xor_sync(full, a, 4);
+                        tot[q] = a;
+                    }
+                    float mine = 0.f;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) if (q == k) mine = tot[q];
+                    const int v = v0 + k;
+                    if (v < Nm1 * SV) {
+                        const int j = v / SV, s = v - j * SV;
+                        if (s < NH) Hc[(size_t)(j * NH + s) * WG] = mine;
+                        else if (valid) gos[(((size_t)b * (T_ - 1) + t) * Nm1 + j) * 25 + (s - NH)] = mine;
+                    }
+                }
+                if (gten) {
+                    float gt[3];
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        float a = gtf_acc[i] * wk;
+                        a += __shfl_xor_sync(full, a, 1);
+                        a += __shfl_xor_sync(full, a, 2);
+                        a += __shfl_xor_sync(full, a, 4);
+                        gt[i] = a;
+                    }
+                    if (k < 4 && valid)
+                        gten[((size_t)b * T_ + t) * 4 + k] = P.tdirs[k * 3] * gt[0] + P.tdirs[k * 3 + 1] * gt[1] + P.tdirs[k * 3 + 2] * gt[2];
+                }
+                __syncwarp();
+                const int tmp = ib; ib = ia; ia = ic; ic = tmp;   // Hb <- Ha, Ha <- Hc
+            }
+            if (gten && k < 4 && valid) gten[((size_t)b * T_ + (T_ - 1)) * 4 + k] = 0.f;   // the last control is never applied
+        }
+    }
+    ktc::cta_teardown(bars, tbase);
+}
+
+// ---- weight images ------------------------------------------------------------------------------------------------------
+// img: W1 hi|lo [512 units x 32] (column 28 = b1), W2 hi|lo [32 outs x 512 units], then for the backward W2^T hi|lo
+// [512 units x 32 outs] and W1^T hi|lo [32 inputs x 512 units] (columns >= 28 zero); all bf16, K-major, no swizzle.
+__global__ void kc_knode_tc_prep_kernel(const float* __restrict__ W1, const float* __restrict__ b1, const float* __restrict__ W2,
+                                        int hidden, unsigned char* __restrict__ img) {
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < 512 * 32; e += gridDim.x * blockDim.x) {
+        const int u = e >> 5, k = e & 31;
+        const float w1 = u < hidden ? (k < 28 ? W1[(size_t)u * 28 + k] : (k == 28 ? b1[u] : 0.f)) : 0.f;
+        const float w2 = (u < hidden && k < 25) ? W2[(size_t)k * hidden + u] : 0.f;
+        const float w1t = (u < hidden && k < 28) ? W1[(size_t)u * 28 + k] : 0.f;
+        auto put = [&](int image, uint32_t off, float w) {
+            const __nv_bfloat16 h = __float2bfloat16_rn(w);
+            const __nv_bfloat16 l = __float2bfloat16_rn(w - __bfloat162float(h));
+            *reinterpret_cast<__nv_bfloat16*>(img + (size_t)image * 2 * ktc::IMG + off) = h;
+            *reinterpret_cast<__nv_bfloat16*>(img + (size_t)image * 2 * ktc::IMG + ktc::IMG + off) = l;
+        };
+        put(0, umma::kmajor_off_b16(u, k, 32), w1);      // W1   : rows = units, k = inputs
+        put(1, umma::kmajor_off_b16(k, u, 512), w2);     // W2   : rows = outputs, k = units
+        put(2, umma::kmajor_off_b16(u, k, 32), w2);      // W2^T : rows = units, k = outputs
+        put(3, umma::kmajor_off_b16(k, u, 512), w1t);    // W1^T : rows = inputs, k = units
+    }
+}
+
+// ---- host side (called by kc_rollout.cu / kc_bptt.cu) ----------------------------------------------------------------
+bool kc_knode_tc_eligible(int dtype, const kc_mlp* mlp, int N, int method) {
+    if (!mlp || dtype != KC_F32 || mlp->in_dim != 28 || mlp->hidden > 512 || method != KC_MARCH_EULER) return false;
+    if ((size_t)ktc::F_HIST + (size_t)(N - 1) * 12 * ktc::RPC * 4 > 227 * 1024) return false;
+    const char* e = getenv("KC_ROLLOUT_TC");
+    if (e && e[0] == '0') return false;
+    return true;
+}
+size_t kc_knode_tc_img_bytes() { return (size_t)8 * ktc::IMG; }
+static int tc_bwd_grid(int64_t B) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t ng = (B + ktc::RPC - 1) / ktc::RPC;
+    return (int)(ng < sms ? (ng > 0 ? ng : 1) : sms);
+}
+size_t kc_knode_tc_bwd_scratch_bytes(int N, int64_t B) {
+    const size_t per_cta = ((size_t)(N - 1) * ktc::SV * 128 + (size_t)3 * (N - 1) * 12 * ktc::RPC) * sizeof(float);
+    return per_cta * (size_t)tc_bwd_grid(B) + 256;
+}
+static int tc_prep(const kc_mlp* mlp, unsigned char* img, cudaStream_t st) {
+    kc_knode_tc_prep_kernel<<<32, 256, 0, st>>>((const float*)mlp->W1, (const float*)mlp->b1, (const float*)mlp->W2, mlp->hidden, img);
+    KC_CHECK_LAUNCH("kc_knode_tc_prep_kernel");
+    return KC_OK;
+}
+int kc_knode_tc_fwd(const RodC<float>& P, const kc_mlp* mlp, int64_t B, int T_, const float* tensions, const float* y0,
+                    const float* z0, float* trajD, float tol, int max_iter, float fd_eps, float* Gout, int32_t* iters,
+                    unsigned char* img, cudaStream_t st) {
+    int rc = tc_prep(mlp, img, st);
+    if (rc) return rc;
+    const size_t smem = (size_t)ktc::F_HIST + (size_t)(P.N - 1) * 12 * ktc::RPC * sizeof(float);
+    const unsigned grid = (unsigned)((B + ktc::RPC - 1) / ktc::RPC);
+#define KC_GO(D)                                                                                                       \
+    do {                                                                                                               \
+        cudaFuncSetAttribute(kc_knode_tc_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
+        kc_knode_tc_fwd_kernel<D><<<grid, ktc::THREADS, smem, st>>>(P, img, (const float*)mlp->b2, mlp->hidden, B, T_, \
+            tensions, y0, z0, trajD, tol, max_iter, fd_eps, Gout, iters);                                              \
+    } while (0)
+    if (P.diag) KC_GO(true); else KC_GO(false);
+#undef KC_GO
+    KC_CHECK_LAUNCH("kc_knode_tc_fwd_kernel");
+    return KC_OK;
+}
+int kc_knode_tc_bwd(const RodC<float>& P, const kc_mlp* mlp, int64_t B, int T_, const float* tensions, const float* traj,
+                    const float* gtraj, float* gten, float* xs, float* gos, unsigned char* img, unsigned char* scratch,
+                    cudaStream_t st) {
+    int rc = tc_prep(mlp, img, st);
+    if (rc) return rc;
+    const int grid = tc_bwd_grid(B);
+    float* rowscr = reinterpret_cast<float*>(scratch);
+    float* hscr = rowscr + (size_t)grid * (P.N - 1) * ktc::SV * 128;
+#define KC_GO(D)                                                                                                       \
+    do {                                                                                                               \
+        cudaFuncSetAttribute(kc_knode_tc_bwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, ktc::B_BYTES);    \
+        kc_knode_tc_bwd_kernel<D><<<grid, ktc::THREADS, ktc::B_BYTES, st>>>(P, img, mlp->hidden, B, T_, tensions, traj,\
+            gtraj, gten, xs, gos, rowscr, hscr);                                                                       \
+    } while (0)
+    if (P.diag) KC_GO(true); else KC_GO(false);
+#undef KC_GO
+    KC_CHECK_LAUNCH("kc_knode_tc_bwd_kernel");
+    return KC_OK;
+}

@@ -16,6 +16,14 @@
 #include "kc_rollout_core.cuh"
 #include "kc_rollout_wide.cuh"
 #include "kc_mlp_coop.cuh"
+#include <type_traits>
+
+// kc_knode_tc.cu: KNODE march with the MLP on tcgen05 (fp32, 28 inputs, hidden <= 512, Euler march)
+bool kc_knode_tc_eligible(int dtype, const kc_mlp* mlp, int N, int method);
+size_t kc_knode_tc_img_bytes();
+int kc_knode_tc_fwd(const RodC<float>& P, const kc_mlp* mlp, int64_t B, int T_, const float* tensions, const float* y0,
+                    const float* z0, float* trajD, float tol, int max_iter, float fd_eps, float* Gout, int32_t* iters,
+                    unsigned char* img, cudaStream_t st);
 
 constexpr int KC_LS = 32;  // lane stride of every per-rod array (one warp-wide tile)
 
@@ -522,7 +530,7 @@ int kc_check_mlp(const kc_mlp* mlp) {
 static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct RolloutWs {
-    size_t trajD, wp, wc, state, total;
+    size_t trajD, wp, wc, state, tcimg, total;
     size_t Bpad;
 };
 static RolloutWs rollout_ws(int dtype, int N, const kc_mlp* mlp, int64_t B, int64_t T_) {
@@ -537,6 +545,8 @@ static RolloutWs rollout_ws(int dtype, int N, const kc_mlp* mlp, int64_t B, int6
     if (mlp) off += align256((size_t)kc_coop_row(mlp->in_dim) * (size_t)((mlp->hidden + 31) & ~31) * sz);
     w.state = off;
     off += align256((size_t)KC_SHOOT_SLOTS * w.Bpad * sz);
+    w.tcimg = off;
+    if (mlp) off += align256(kc_knode_tc_img_bytes());
     w.total = off;
     return w;
 }
@@ -629,13 +639,29 @@ static int rollout_typed(const kc_rod_params* Pp, const kc_mlp* mlp, int64_t B, 
         if (e && e[0] == '0') coop = false;
         if (e && e[0] == '1' && in_dim != 0 && !rk4) coop = true;
     }
+    // MLP of the march on the tensor cores (kc_knode_tc.cu): 16 rods x 8 shooting points per CTA.  Default for every KNODE
+    // rollout of the eligible shape; KC_ROLLOUT_TC=0 falls back to the SIMT kernels above, an explicit KC_ROLLOUT_COOP /
+    // KC_ROLLOUT_MODE request is honoured (the parity tests run every mode).
+    bool tc = kc_knode_tc_eligible(sizeof(T) == 4 ? KC_F32 : KC_F64, mlp, N, method) && !getenv("KC_ROLLOUT_COOP") &&
+              !getenv("KC_ROLLOUT_MODE");
+    {
+        const char* e = getenv("KC_ROLLOUT_TC");
+        if (e && e[0] == '1' && kc_knode_tc_eligible(sizeof(T) == 4 ? KC_F32 : KC_F64, mlp, N, method)) tc = true;
+    }
+    if (tc) { coop = false; wide = false; lin = false; }
     const bool full_range = t_begin == 0 && t_end == (int)T_ - 1;
-    const bool resumable = !coop && (!wide || lin);
+    const bool resumable = !tc && !coop && (!wide || lin);
     if (query_resumable) return resumable ? 1 : 0;
     KC_CHECK_ARG(full_range || resumable, "this rollout mode cannot be run in time ranges");
     const int t_first = t_begin == 0 ? 0 : t_begin + 1, n_idx = t_end - t_first + 1;   // time indices this call produces
     if (B > 0 && n_idx > 0) {
-        if (coop) {
+        if (tc) {
+            if constexpr (std::is_same<T, float>::value) {
+                int rc = kc_knode_tc_fwd(P, mlp, B, (int)T_, (const float*)tensions, (const float*)y0, (const float*)z0, trajD,
+                                         tl, max_iter, fd_eps, (float*)G_out, iters, ws + w.tcimg, st);
+                if (rc) return rc;
+            }
+        } else if (coop) {
         MlpCoop<T> MC;
         static_cast<MlpC<T>&>(MC) = M;
         MC.Hp = (mlp->hidden + 31) & ~31;

@@ -112,4 +112,36 @@ __device__ __forceinline__ float to_tf32_rn(float x) {  // round-to-nearest tf32
     return __uint_as_float(u);
 }
 
+
+// ---- A operand from TMEM (".ts" form) ------------------------------------------------------------------------------------
+// D[tmem] (+)= A[tmem] * B[smem]^T, kind::f16 (bf16 operands): A is M = 128 rows x 16 k-values per instruction, row r in
+// TMEM lane r, the k-values packed two per 32-bit column (even k in the low half), i.e. 8 columns per instruction
+// (CuTe: SM100_MMA_F16BF16_TS, A fragment = tmem_frg_1sm<bf16, bf16>).  The activation tile of the KNODE MLP is written
+// there by the epilogue threads with tcgen05.st and never touches shared memory.
+__device__ __forceinline__ void mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// registers -> TMEM: this warp's 32 lanes, 16 consecutive columns
+__device__ __forceinline__ void st16(uint32_t taddr, const uint32_t v[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+          "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+}
+__device__ __forceinline__ void wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// plain arrive (count 1) on a CTA-local mbarrier, release semantics
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// K-major, no swizzle, 2-byte elements: element (r, k) of a tile with KT k-values per row (8 x 16-byte core matrices:
+// LBO = 128 B to the next 8 k-values, SBO = (KT/8) * 128 B to the next 8 rows); one kind::f16 instruction consumes
+// K = 16 = two core matrices (256 B)
+__device__ __forceinline__ uint32_t kmajor_off_b16(int r, int k, int KT) {
+    return (uint32_t)(((r >> 3) * (KT >> 3) + (k >> 3)) * 128 + (r & 7) * 16 + (k & 7) * 2);
+}
+
 }  // namespace umma
