@@ -504,7 +504,7 @@ kc_knode_tc_bwd_kernel(const __grid_constant__ RodC<float> P, const unsigned cha
     extern __shared__ __align__(1024) unsigned char sm[];
     constexpr int NH = 12, WG = ktc::RPC, SV = ktc::SV;
     const int N = P.N, Nm1 = N - 1, tid = threadIdx.x, warp = tid >> 5;
-    ktc::Bars* bars = ktc::cta_setup(sm, ktc::B_MISC, img, 6 * ktc::IMG);
+    ktc::Bars* bars = ktc::cta_setup(sm, ktc::B_MISC, img + 4 * ktc::IMG, 6 * ktc::IMG);
     const uint32_t tbase = bars->tmem_slot;
     const uint32_t laneblk = (uint32_t)((warp & 3) * 32) << 16;
     const int nch = (hidden + 63) / 64;
@@ -675,7 +675,7 @@ kc_knode_tc_bwd_kernel(const __grid_constant__ RodC<float> P, const unsigned cha
 }
 
 // ---- weight images ------------------------------------------------------------------------------------------------------
-// img: W1 hi|lo [512 units x 32] (column 28 = b1), W2 hi|lo [32 outs x 512 units], then for the backward W2^T hi|lo
+// img: W1 hi|lo [512 units x 32] (column 28 = b1), W2 hi|lo [32 outs x 512 units], then for the backward W1 again, W2^T hi|lo
 // [512 units x 32 outs] and W1^T hi|lo [32 inputs x 512 units] (columns >= 28 zero); all bf16, K-major, no swizzle.
 __global__ void kc_knode_tc_prep_kernel(const float* __restrict__ W1, const float* __restrict__ b1, const float* __restrict__ W2,
                                         int hidden, unsigned char* __restrict__ img) {
@@ -690,10 +690,12 @@ __global__ void kc_knode_tc_prep_kernel(const float* __restrict__ W1, const floa
             *reinterpret_cast<__nv_bfloat16*>(img + (size_t)image * 2 * ktc::IMG + off) = h;
             *reinterpret_cast<__nv_bfloat16*>(img + (size_t)image * 2 * ktc::IMG + ktc::IMG + off) = l;
         };
+        // forward set (images 0, 1) and backward set (images 2, 3, 4): each is copied to shared memory as one block
         put(0, umma::kmajor_off_b16(u, k, 32), w1);      // W1   : rows = units, k = inputs
         put(1, umma::kmajor_off_b16(k, u, 512), w2);     // W2   : rows = outputs, k = units
-        put(2, umma::kmajor_off_b16(u, k, 32), w2);      // W2^T : rows = units, k = outputs
-        put(3, umma::kmajor_off_b16(k, u, 512), w1t);    // W1^T : rows = inputs, k = units
+        put(2, umma::kmajor_off_b16(u, k, 32), w1);      // W1 again
+        put(3, umma::kmajor_off_b16(u, k, 32), w2);      // W2^T : rows = units, k = outputs
+        put(4, umma::kmajor_off_b16(k, u, 512), w1t);    // W1^T : rows = inputs, k = units
     }
 }
 
@@ -705,7 +707,7 @@ bool kc_knode_tc_eligible(int dtype, const kc_mlp* mlp, int N, int method) {
     if (e && e[0] == '0') return false;
     return true;
 }
-size_t kc_knode_tc_img_bytes() { return (size_t)8 * ktc::IMG; }
+size_t kc_knode_tc_img_bytes() { return (size_t)10 * ktc::IMG; }
 static int tc_bwd_grid(int64_t B) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
