@@ -65,6 +65,17 @@ __device__ __forceinline__ void split_pair(float x0, float x1, uint32_t& hi, uin
     hi = __byte_perm(a, b, 0x7632);
     lo = pack_bf16x2(x0 - __uint_as_float(a), x1 - __uint_as_float(b));
 }
+// The same split for the epilogues, which are bound by the ALU pipe (64 lanes/clk: LOP3, VIADD, PRMT, F2FP, FSETP — measured
+// with tools/micro/pipe_bench.cu) while the FMA pipe (128 lanes/clk) idles: hi by Veltkamp's splitting on the FMA pipe
+// (t = x * (2^16 + 1); hi = t - (t - x): x rounded to nearest with 8 significant bits = exactly a bf16), lo = x - hi exactly,
+// stored truncated to bf16 (|lo| <= 2^-9 |x|, so the truncation is 2^-17 relative and its sign is random).  Two byte
+// permutes are all that is left on the ALU pipe.
+__device__ __forceinline__ void split_pair_fma(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    const float t0 = __fmul_rn(x0, 65537.f), t1 = __fmul_rn(x1, 65537.f);
+    const float h0 = __fsub_rn(t0, __fsub_rn(t0, x0)), h1 = __fsub_rn(t1, __fsub_rn(t1, x1));
+    hi = __byte_perm(__float_as_uint(h0), __float_as_uint(h1), 0x7632);
+    lo = __byte_perm(__float_as_uint(__fsub_rn(x0, h0)), __float_as_uint(__fsub_rn(x1, h1)), 0x7632);
+}
 // 32 values of one row -> the row's bf16 hi/lo entries of a [128 x 32] K-major tile (4 x 16-byte stores each)
 __device__ __forceinline__ void store_row32(unsigned char* tile_hi, int row, const float v[32]) {
 #pragma unroll
@@ -100,12 +111,12 @@ __device__ __forceinline__ void fwd_epilogue(uint32_t taddr) {   // taddr -> thi
     uint32_t hi[16], lo[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i)
-        split_pair(kc_elu(__uint_as_float(v0[2 * i])), kc_elu(__uint_as_float(v0[2 * i + 1])), hi[i], lo[i]);
+        split_pair_fma(kc_elu(__uint_as_float(v0[2 * i])), kc_elu(__uint_as_float(v0[2 * i + 1])), hi[i], lo[i]);
     umma::st16(taddr, hi);
     umma::st16(taddr + 16, lo);
 #pragma unroll
     for (int i = 0; i < 16; ++i)
-        split_pair(kc_elu(__uint_as_float(v1[2 * i])), kc_elu(__uint_as_float(v1[2 * i + 1])), hi[i], lo[i]);
+        split_pair_fma(kc_elu(__uint_as_float(v1[2 * i])), kc_elu(__uint_as_float(v1[2 * i + 1])), hi[i], lo[i]);
     umma::st16(taddr + 32, hi);
     umma::st16(taddr + 48, lo);
     umma::wait_st();
@@ -122,7 +133,7 @@ __device__ __forceinline__ void bwd_epilogue(uint32_t taddr) {   // taddr -> lan
     for (int i = 0; i < 16; ++i) {
         const float z0 = __uint_as_float(z[2 * i]), z1 = __uint_as_float(z[2 * i + 1]);
         const float e0 = z0 > 0.f ? 1.f : kc_exp_fast(z0), e1 = z1 > 0.f ? 1.f : kc_exp_fast(z1);
-        split_pair(__uint_as_float(d[2 * i]) * e0, __uint_as_float(d[2 * i + 1]) * e1, hi[i], lo[i]);
+        split_pair_fma(__uint_as_float(d[2 * i]) * e0, __uint_as_float(d[2 * i + 1]) * e1, hi[i], lo[i]);
     }
     umma::st16(taddr, hi);
     umma::st16(taddr + 16, lo);
@@ -229,32 +240,35 @@ __device__ __forceinline__ void helper_loop(Bars* bars, uint32_t tbase, uint32_t
     }
 }
 
-// ---- the MMA thread (warp 8, lane 0) -----------------------------------------------------------------------------------
-// forward: Z chunk c = 128 units.  X: [128 x 32] K-major (LBO 128, SBO 512); W1 image rows = units (chunk c at c*8192);
-// W2 image [32 outs x 512 units] K-major (LBO 128, SBO 8192), 16 units = 256 bytes.
+// ---- the MMA warp (warp 8): all 32 lanes run the loop, the instructions are issued by one elected lane ------------------
+// Descriptors: no swizzle, LBO 128 B; the 14-bit address field counts 16-byte units, so stepping through a tile is an add
+// on the low word.  X / GO tiles and the W1 / W2^T images: [rows x 32] K-major, SBO 512; W2 / W1^T images:
+// [32 x 512] K-major, SBO 8192.
+__device__ __forceinline__ uint64_t desc_step(uint64_t d, uint32_t bytes) { return d + (bytes >> 4); }
+
+// forward: Z chunk c = 128 units.  W1 image rows = units (chunk c at c*8192); in the W2 image 16 units = 256 bytes.
 __device__ __forceinline__ void mma_loop_fwd(unsigned char* sm, Bars* bars, uint32_t tbase, int nch) {
     const uint32_t idZ = umma::make_idesc_bf16(128, 128), idO = umma::make_idesc_bf16(128, 32);
-    const uint32_t aX = umma::smem_u32(sm + F_X), aW1 = umma::smem_u32(sm + F_W1), aW2 = umma::smem_u32(sm + F_W2);
+    const uint64_t dXh = umma::make_desc(umma::smem_u32(sm + F_X), 128, 512), dXl = desc_step(dXh, 8192);
+    const uint64_t dW1h = umma::make_desc(umma::smem_u32(sm + F_W1), 128, 512), dW1l = desc_step(dW1h, IMG);
+    const uint64_t dW2h = umma::make_desc(umma::smem_u32(sm + F_W2), 128, 8192), dW2l = desc_step(dW2h, IMG);
     uint32_t phX = 0, phA = 0;
     auto gemm1 = [&](int c) {
-        const uint32_t d = tbase + (c % NBUF) * 128, w = aW1 + c * 8192;
-        uint32_t acc = 0;
+        const uint32_t d = tbase + (c % NBUF) * 128, wo = c * 8192;
 #pragma unroll
         for (int p = 0; p < 3; ++p) {
-            const uint32_t a = p == 1 ? aX + 8192 : aX, b = p == 2 ? w + IMG : w;
+            const uint64_t a = p == 1 ? dXl : dXh, b = desc_step(p == 2 ? dW1l : dW1h, wo);
 #pragma unroll
-            for (int kk = 0; kk < 2; ++kk) {
-                umma::mma_bf16(d, umma::make_desc(a + kk * 256, 128, 512), umma::make_desc(b + kk * 256, 128, 512), idZ, acc);
-                acc = 1;
-            }
+            for (int kk = 0; kk < 2; ++kk)
+                umma::mma_bf16_w(d, desc_step(a, kk * 256), desc_step(b, kk * 256), idZ, (p | kk) ? 1u : 0u);
         }
-        umma::commit(&bars->Z[c % NBUF]);
+        umma::commit_w(&bars->Z[c % NBUF]);
     };
     while (true) {
         umma::mbar_wait(&bars->X, phX);
         phX ^= 1;
         if (*reinterpret_cast<volatile uint32_t*>(&bars->exit_flag)) {
-            umma::mbar_arrive(&bars->Z[0]);      // releases the helper warps, which then see the flag
+            umma::mbar_arrive_w(&bars->Z[0]);      // releases the helper warps, which then see the flag
             return;
         }
         umma::fence_after();
@@ -264,52 +278,51 @@ __device__ __forceinline__ void mma_loop_fwd(unsigned char* sm, Bars* bars, uint
             umma::mbar_wait(&bars->A[buf], (phA >> buf) & 1u);
             phA ^= 1u << buf;
             umma::fence_after();
-            uint32_t acc = c > 0 ? 1u : 0u;
+            const uint32_t ab = tbase + buf * 128;
 #pragma unroll
             for (int p = 0; p < 3; ++p) {
+                const uint64_t b = desc_step(p == 2 ? dW2l : dW2h, c * 2048);
 #pragma unroll
                 for (int kk = 0; kk < 8; ++kk) {
-                    const uint32_t a = tbase + buf * 128 + (kk >> 2) * 64 + ((kk >> 1) & 1) * 32 + (kk & 1) * 8 + (p == 1 ? 16 : 0);
-                    const uint32_t b = aW2 + (p == 2 ? IMG : 0) + (c * 8 + kk) * 256;
-                    umma::mma_bf16_ts(tbase + COL_O, a, umma::make_desc(b, 128, 8192), idO, acc);
-                    acc = 1;
+                    const uint32_t a = ab + (kk >> 2) * 64 + ((kk >> 1) & 1) * 32 + (kk & 1) * 8 + (p == 1 ? 16 : 0);
+                    umma::mma_bf16_ts_w(tbase + COL_O, a, desc_step(b, kk * 256), idO, (c | p | kk) ? 1u : 0u);
                 }
             }
             if (c + NBUF < nch) gemm1(c + NBUF);
         }
-        umma::commit(&bars->O);
+        umma::commit_w(&bars->O);
     }
 }
 // backward: chunk c = 64 units; buffer = Z (64 columns) | dA (64 columns).  W1 / W2^T images: rows = units (chunk c at
-// c*4096); GO tile as X; W1^T image [32 inputs x 512 units] K-major as the forward W2 image.
+// c*4096); in the W1^T image 16 units = 256 bytes.
 __device__ __forceinline__ void mma_loop_bwd(unsigned char* sm, Bars* bars, uint32_t tbase, int nch) {
     const uint32_t idZ = umma::make_idesc_bf16(128, 64), idO = umma::make_idesc_bf16(128, 32);
-    const uint32_t aX = umma::smem_u32(sm + B_X), aGO = umma::smem_u32(sm + B_GO), aW1 = umma::smem_u32(sm + B_W1),
-                   aW2T = umma::smem_u32(sm + B_W2T), aW1T = umma::smem_u32(sm + B_W1T);
+    const uint64_t dXh = umma::make_desc(umma::smem_u32(sm + B_X), 128, 512), dXl = desc_step(dXh, 8192);
+    const uint64_t dGh = umma::make_desc(umma::smem_u32(sm + B_GO), 128, 512), dGl = desc_step(dGh, 8192);
+    const uint64_t dW1h = umma::make_desc(umma::smem_u32(sm + B_W1), 128, 512), dW1l = desc_step(dW1h, IMG);
+    const uint64_t dW2Th = umma::make_desc(umma::smem_u32(sm + B_W2T), 128, 512), dW2Tl = desc_step(dW2Th, IMG);
+    const uint64_t dW1Th = umma::make_desc(umma::smem_u32(sm + B_W1T), 128, 8192), dW1Tl = desc_step(dW1Th, IMG);
     uint32_t phX = 0, phA = 0;
     auto gemm13 = [&](int c) {
-        const uint32_t d = tbase + (c % NBUF) * 128;
+        const uint32_t d = tbase + (c % NBUF) * 128, wo = c * 4096;
 #pragma unroll
         for (int which = 0; which < 2; ++which) {
-            const uint32_t at = which ? aGO : aX, w = (which ? aW2T : aW1) + c * 4096;
-            uint32_t acc = 0;
 #pragma unroll
             for (int p = 0; p < 3; ++p) {
-                const uint32_t a = p == 1 ? at + 8192 : at, b = p == 2 ? w + IMG : w;
+                const uint64_t a = which ? (p == 1 ? dGl : dGh) : (p == 1 ? dXl : dXh);
+                const uint64_t b = desc_step(which ? (p == 2 ? dW2Tl : dW2Th) : (p == 2 ? dW1l : dW1h), wo);
 #pragma unroll
-                for (int kk = 0; kk < 2; ++kk) {
-                    umma::mma_bf16(d + which * 64, umma::make_desc(a + kk * 256, 128, 512), umma::make_desc(b + kk * 256, 128, 512), idZ, acc);
-                    acc = 1;
-                }
+                for (int kk = 0; kk < 2; ++kk)
+                    umma::mma_bf16_w(d + which * 64, desc_step(a, kk * 256), desc_step(b, kk * 256), idZ, (p | kk) ? 1u : 0u);
             }
         }
-        umma::commit(&bars->Z[c % NBUF]);
+        umma::commit_w(&bars->Z[c % NBUF]);
     };
     while (true) {
         umma::mbar_wait(&bars->X, phX);
         phX ^= 1;
         if (*reinterpret_cast<volatile uint32_t*>(&bars->exit_flag)) {
-            umma::mbar_arrive(&bars->Z[0]);
+            umma::mbar_arrive_w(&bars->Z[0]);
             return;
         }
         umma::fence_after();
@@ -319,20 +332,19 @@ __device__ __forceinline__ void mma_loop_bwd(unsigned char* sm, Bars* bars, uint
             umma::mbar_wait(&bars->A[buf], (phA >> buf) & 1u);
             phA ^= 1u << buf;
             umma::fence_after();
-            uint32_t acc = c > 0 ? 1u : 0u;
+            const uint32_t ab = tbase + buf * 128;
 #pragma unroll
             for (int p = 0; p < 3; ++p) {
+                const uint64_t b = desc_step(p == 2 ? dW1Tl : dW1Th, c * 1024);
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk) {
-                    const uint32_t a = tbase + buf * 128 + (kk >> 1) * 32 + (kk & 1) * 8 + (p == 1 ? 16 : 0);
-                    const uint32_t b = aW1T + (p == 2 ? IMG : 0) + (c * 4 + kk) * 256;
-                    umma::mma_bf16_ts(tbase + COL_O, a, umma::make_desc(b, 128, 8192), idO, acc);
-                    acc = 1;
+                    const uint32_t a = ab + (kk >> 1) * 32 + (kk & 1) * 8 + (p == 1 ? 16 : 0);
+                    umma::mma_bf16_ts_w(tbase + COL_O, a, desc_step(b, kk * 256), idO, (c | p | kk) ? 1u : 0u);
                 }
             }
             if (c + NBUF < nch) gemm13(c + NBUF);
         }
-        umma::commit(&bars->O);
+        umma::commit_w(&bars->O);
     }
 }
 
@@ -388,14 +400,13 @@ kc_knode_tc_fwd_kernel(const __grid_constant__ RodC<float> P, const unsigned cha
                        int32_t* iters) {
     extern __shared__ __align__(1024) unsigned char sm[];
     constexpr int NH = 12, WG = ktc::RPC, LS = 32;
-    const int N = P.N, tid = threadIdx.x, warp = tid >> 5;
+    const int N = P.N, tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // (provably warp-uniform)
     ktc::Bars* bars = ktc::cta_setup(sm, ktc::F_MISC, img, 4 * ktc::IMG);
-    const uint32_t tbase = bars->tmem_slot;
+    const uint32_t tbase = __shfl_sync(0xffffffffu, bars->tmem_slot, 0);
     const uint32_t laneblk = (uint32_t)((warp & 3) * 32) << 16;
     const int nch = (hidden + 127) / 128;
     if (warp == 8) {
-        if ((tid & 31) == 0) ktc::mma_loop_fwd(sm, bars, tbase, nch);
-        __syncwarp();
+        ktc::mma_loop_fwd(sm, bars, tbase, nch);
     } else if (warp >= 4) {
         ktc::helper_loop<false>(bars, tbase, laneblk, nch);
     } else {
@@ -503,14 +514,13 @@ kc_knode_tc_bwd_kernel(const __grid_constant__ RodC<float> P, const unsigned cha
                        float* __restrict__ gos, float* __restrict__ rowscr_all, float* __restrict__ hscr_all) {
     extern __shared__ __align__(1024) unsigned char sm[];
     constexpr int NH = 12, WG = ktc::RPC, SV = ktc::SV;
-    const int N = P.N, Nm1 = N - 1, tid = threadIdx.x, warp = tid >> 5;
+    const int N = P.N, Nm1 = N - 1, tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     ktc::Bars* bars = ktc::cta_setup(sm, ktc::B_MISC, img + 4 * ktc::IMG, 6 * ktc::IMG);
-    const uint32_t tbase = bars->tmem_slot;
+    const uint32_t tbase = __shfl_sync(0xffffffffu, bars->tmem_slot, 0);
     const uint32_t laneblk = (uint32_t)((warp & 3) * 32) << 16;
     const int nch = (hidden + 63) / 64;
     if (warp == 8) {
-        if ((tid & 31) == 0) ktc::mma_loop_bwd(sm, bars, tbase, nch);
-        __syncwarp();
+        ktc::mma_loop_bwd(sm, bars, tbase, nch);
     } else if (warp >= 4) {
         ktc::helper_loop<true>(bars, tbase, laneblk, nch);
     } else {
