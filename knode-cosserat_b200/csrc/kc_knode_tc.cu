@@ -65,16 +65,14 @@ __device__ __forceinline__ void split_pair(float x0, float x1, uint32_t& hi, uin
     hi = __byte_perm(a, b, 0x7632);
     lo = pack_bf16x2(x0 - __uint_as_float(a), x1 - __uint_as_float(b));
 }
-// The same split for the epilogues, which are bound by the ALU pipe (64 lanes/clk: LOP3, VIADD, PRMT, F2FP, FSETP — measured
-// with tools/micro/pipe_bench.cu) while the FMA pipe (128 lanes/clk) idles: hi by Veltkamp's splitting on the FMA pipe
-// (t = x * (2^16 + 1); hi = t - (t - x): x rounded to nearest with 8 significant bits = exactly a bf16), lo = x - hi exactly,
-// stored truncated to bf16 (|lo| <= 2^-9 |x|, so the truncation is 2^-17 relative and its sign is random).  Two byte
-// permutes are all that is left on the ALU pipe.
-__device__ __forceinline__ void split_pair_fma(float x0, float x1, uint32_t& hi, uint32_t& lo) {
-    const float t0 = __fmul_rn(x0, 65537.f), t1 = __fmul_rn(x1, 65537.f);
-    const float h0 = __fsub_rn(t0, __fsub_rn(t0, x0)), h1 = __fsub_rn(t1, __fsub_rn(t1, x1));
-    hi = __byte_perm(__float_as_uint(h0), __float_as_uint(h1), 0x7632);
-    lo = __byte_perm(__float_as_uint(__fsub_rn(x0, h0)), __float_as_uint(__fsub_rn(x1, h1)), 0x7632);
+// The split as the epilogues use it (measured pipe rates, tools/micro/pipe_bench.cu: FMA 128, ALU 64, XU 16 lanes/clk/SM;
+// F2FP / PRMT / LOP3 / SHF / FSETP are ALU-pipe instructions): hi = one packed round-to-nearest conversion for the pair,
+// unpacked again with a shift / a mask, lo = x - hi exactly, stored truncated to bf16 (|lo| <= 2^-9 |x|, so the truncation
+// is 2^-17 relative and its sign is random).  3 instructions per value.
+__device__ __forceinline__ void split_pair_fast(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    hi = pack_bf16x2(x0, x1);
+    const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xffff0000u);
+    lo = __byte_perm(__float_as_uint(x0 - h0), __float_as_uint(x1 - h1), 0x7632);
 }
 // 32 values of one row -> the row's bf16 hi/lo entries of a [128 x 32] K-major tile (4 x 16-byte stores each)
 __device__ __forceinline__ void store_row32(unsigned char* tile_hi, int row, const float v[32]) {
@@ -111,12 +109,12 @@ __device__ __forceinline__ void fwd_epilogue(uint32_t taddr) {   // taddr -> thi
     uint32_t hi[16], lo[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i)
-        split_pair_fma(kc_elu(__uint_as_float(v0[2 * i])), kc_elu(__uint_as_float(v0[2 * i + 1])), hi[i], lo[i]);
+        split_pair_fast(kc_elu(__uint_as_float(v0[2 * i])), kc_elu(__uint_as_float(v0[2 * i + 1])), hi[i], lo[i]);
     umma::st16(taddr, hi);
     umma::st16(taddr + 16, lo);
 #pragma unroll
     for (int i = 0; i < 16; ++i)
-        split_pair_fma(kc_elu(__uint_as_float(v1[2 * i])), kc_elu(__uint_as_float(v1[2 * i + 1])), hi[i], lo[i]);
+        split_pair_fast(kc_elu(__uint_as_float(v1[2 * i])), kc_elu(__uint_as_float(v1[2 * i + 1])), hi[i], lo[i]);
     umma::st16(taddr + 32, hi);
     umma::st16(taddr + 48, lo);
     umma::wait_st();
@@ -133,7 +131,7 @@ __device__ __forceinline__ void bwd_epilogue(uint32_t taddr) {   // taddr -> lan
     for (int i = 0; i < 16; ++i) {
         const float z0 = __uint_as_float(z[2 * i]), z1 = __uint_as_float(z[2 * i + 1]);
         const float e0 = z0 > 0.f ? 1.f : kc_exp_fast(z0), e1 = z1 > 0.f ? 1.f : kc_exp_fast(z1);
-        split_pair_fma(__uint_as_float(d[2 * i]) * e0, __uint_as_float(d[2 * i + 1]) * e1, hi[i], lo[i]);
+        split_pair_fast(__uint_as_float(d[2 * i]) * e0, __uint_as_float(d[2 * i + 1]) * e1, hi[i], lo[i]);
     }
     umma::st16(taddr, hi);
     umma::st16(taddr + 16, lo);
@@ -390,14 +388,33 @@ template <typename T> __device__ __forceinline__ T* rod_base_tc(T* trajD, int64_
 }  // namespace ktc
 
 // =========================================================================================================================
-// Forward: KNODE rollout, 16 rods per CTA, Newton shooting solve with a per-march finite-difference Jacobian (the logic of
-// kc_rollout_wide_kernel), MLP on tcgen05.  Trajectory in the device layout [tile][T][N][25][32] (transposed afterwards).
+// Forward: KNODE rollout, persistent CTAs over groups of 16 rods, Newton shooting solve with a per-march finite-difference
+// Jacobian and the linearised final correction of kc_rollout_wide_lin_kernel (the marched states of the 7 shooting points
+// are kept — here in an L2-resident scratch, [25*N][128 rows] per CTA — and once the Newton step is so small that its
+// second-order remainder is below the tolerance, the state at G + dG is formed from them instead of marching again: about
+// 2.5 instead of 3.6 joint marches per step), MLP on tcgen05.  Trajectory in the device layout [tile][T][N][25][32].
+struct ScrSink {   // marched state of this row, "output order" e = r*N + j, element stride 128 (rows of the CTA)
+    float* p; int n; bool on;
+    __device__ __forceinline__ void put(int j, const float y[19]) {
+        if (on) {
+#pragma unroll
+            for (int r = 0; r < 19; ++r) p[(size_t)(r * n + j) * 128] = y[r];
+        }
+    }
+    __device__ __forceinline__ void putz(int j, const float z[6]) {
+        if (on) {
+#pragma unroll
+            for (int c = 0; c < 6; ++c) p[(size_t)((19 + c) * n + j) * 128] = z[c];
+        }
+    }
+};
+
 template <bool DIAG>
 __global__ void __launch_bounds__(ktc::THREADS, 1)
 kc_knode_tc_fwd_kernel(const __grid_constant__ RodC<float> P, const unsigned char* __restrict__ img, const float* __restrict__ b2,
                        int hidden, int64_t B, int T_, const float* __restrict__ tensions, const float* __restrict__ y0,
                        const float* __restrict__ z0, float* trajD, float tol, int max_iter, float fd_eps, float* Gout,
-                       int32_t* iters) {
+                       int32_t* iters, float* __restrict__ stscr_all) {
     extern __shared__ __align__(1024) unsigned char sm[];
     constexpr int NH = 12, WG = ktc::RPC, LS = 32;
     const int N = P.N, tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // (provably warp-uniform)
@@ -415,87 +432,116 @@ kc_knode_tc_fwd_kernel(const __grid_constant__ RodC<float> P, const unsigned cha
         M.hidden = hidden; M.in_dim = 28;
         const int lane = tid & 31, g = tid >> 3, k = tid & 7;
         const unsigned full = 0xffffffffu;
-        const int64_t b_raw = (int64_t)blockIdx.x * WG + g;
-        const bool valid = b_raw < B;
-        const int64_t b = valid ? b_raw : B - 1;   // surplus groups shadow the last rod and never store
+        const int NV = 25 * N;
         float* Hs = reinterpret_cast<float*>(sm + ktc::F_HIST) + g;
-        float* traj_b = ktc::rod_base_tc(trajD, b, T_, N);
+        float* stscr = stscr_all + (size_t)blockIdx.x * NV * 128;      // this CTA's marched states
         const size_t tstride = (size_t)25 * N * LS;
-        if (k == 0 && valid) {
-            rollout_init<float, LS>(P, y0 ? y0 + (size_t)b * 19 * N : nullptr, z0 ? z0 + (size_t)b * 6 * N : nullptr, traj_b);
-            if (Gout) {
-#pragma unroll
-                for (int i = 0; i < 6; ++i) Gout[(size_t)b * T_ * 6 + i] = 0.f;
-            }
-            if (iters) iters[(size_t)b * T_] = 0;
-        }
-        __threadfence_block();
-        ktc::sync128();   // (surplus groups read the last rod's initial state written by another warp)
-        auto build_hist = [&](const float* cur, const float* prev) {
-            for (int e = k; e < (N - 1) * NH; e += 8) {
-                const int j = e / NH, s = e - j * NH;
-                const size_t o = ((size_t)j * 25 + slot_row<NH>(s)) * LS;
-                Hs[(size_t)e * WG] = P.c1 * cur[o] + P.c2 * prev[o];
-            }
-        };
-        build_hist(traj_b, traj_b);
-        float zlast[6];   // z[:, N-1] is never written by the march (cosserat_ode.py:198-201)
-#pragma unroll
-        for (int c = 0; c < 6; ++c) zlast[c] = traj_b[((size_t)(N - 1) * 25 + 19 + c) * LS];
-        __syncwarp();
-        float G[6], Gm1[6];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) { G[i] = 0.f; Gm1[i] = 0.f; }
-        const float* ten = tensions + (size_t)b * T_ * 4;
-        for (int t = 0; t < T_ - 1; ++t) {
-            float tn[4], tf[3];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) tn[i] = ten[(size_t)t * 4 + i];
-            tendon_force(P, tn, tf);
-            float* nxt = traj_b + (size_t)(t + 1) * tstride;
-            float Gp[6];
-#pragma unroll
-            for (int i = 0; i < 6; ++i) { Gp[i] = G[i]; G[i] = G[i] + (G[i] - Gm1[i]); }   // linear predictor
-            bool done = false;
-            int status = 0, marches = 0;
-            HistView<float, NH, WG> H{Hs};
-            while (true) {
-                float eps[6], Ge[6], F[6];
-                wide_eps(G, fd_eps, eps);
-#pragma unroll
-                for (int i = 0; i < 6; ++i) Ge[i] = G[i] + ((k == i + 1) ? eps[i] : 0.f);
-                TrajSinkPred<float, LS, NH, WG> S{nxt, nullptr, k == 0 && !done && valid, N - 1};
-                rod_march<float, DIAG, 28, NH>(P, M, Ge, tf, H, S, F);
-                float Fall[7][6];
-#pragma unroll
-                for (int c = 0; c < 7; ++c) {
-#pragma unroll
-                    for (int i = 0; i < 6; ++i) Fall[c][i] = __shfl_sync(full, F[i], (lane & ~7) | c);
-                }
-                if (!done) {
-                    ++marches;
-                    const int r = wide_decide(Fall, G, eps, tol);
-                    if (r != 0) { done = true; status = r; }
-                    else if (marches >= max_iter) { done = true; status = -1; }
-                }
-                if (ktc::all128(done)) break;
-            }
-#pragma unroll
-            for (int i = 0; i < 6; ++i) Gm1[i] = Gp[i];
+        const int64_t ngroups = (B + WG - 1) / WG;
+        for (int64_t grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+            const int64_t b_raw = grp * WG + g;
+            const bool valid = b_raw < B;
+            const int64_t b = valid ? b_raw : B - 1;   // surplus groups shadow the last rod and never store
+            float* traj_b = ktc::rod_base_tc(trajD, b, T_, N);
             if (k == 0 && valid) {
-                const size_t o = (size_t)(N - 1) * 25 * LS;
-#pragma unroll
-                for (int c = 0; c < 6; ++c) nxt[o + (19 + c) * LS] = zlast[c];
+                rollout_init<float, LS>(P, y0 ? y0 + (size_t)b * 19 * N : nullptr, z0 ? z0 + (size_t)b * 6 * N : nullptr, traj_b);
                 if (Gout) {
 #pragma unroll
-                    for (int i = 0; i < 6; ++i) Gout[((size_t)b * T_ + t + 1) * 6 + i] = G[i];
+                    for (int i = 0; i < 6; ++i) Gout[(size_t)b * T_ * 6 + i] = 0.f;
                 }
-                if (iters) iters[(size_t)b * T_ + t + 1] = status > 0 ? marches : -marches;
+                if (iters) iters[(size_t)b * T_] = 0;
             }
             __threadfence_block();
-            ktc::sync128();   // the new state (written by the rod's base lane, maybe of another warp for shadow groups)
-            build_hist(nxt, nxt - tstride);
+            ktc::sync128();   // (surplus groups read the last rod's initial state written by another warp)
+            auto build_hist = [&](const float* cur, const float* prev) {
+                for (int e = k; e < (N - 1) * NH; e += 8) {
+                    const int j = e / NH, s = e - j * NH;
+                    const size_t o = ((size_t)j * 25 + slot_row<NH>(s)) * LS;
+                    Hs[(size_t)e * WG] = P.c1 * cur[o] + P.c2 * prev[o];
+                }
+            };
+            build_hist(traj_b, traj_b);
+            float zlast[6];   // z[:, N-1] is never written by the march (cosserat_ode.py:198-201)
+#pragma unroll
+            for (int c = 0; c < 6; ++c) zlast[c] = traj_b[((size_t)(N - 1) * 25 + 19 + c) * LS];
             __syncwarp();
+            float G[6], Gm1[6];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) { G[i] = 0.f; Gm1[i] = 0.f; }
+            const float* ten = tensions + (size_t)b * T_ * 4;
+            for (int t = 0; t < T_ - 1; ++t) {
+                float tn[4], tf[3];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) tn[i] = ten[(size_t)t * 4 + i];
+                tendon_force(P, tn, tf);
+                float* nxt = traj_b + (size_t)(t + 1) * tstride;
+                float Gp[6], w[6], Gm[6];
+#pragma unroll
+                for (int i = 0; i < 6; ++i) { Gp[i] = G[i]; G[i] = G[i] + (G[i] - Gm1[i]); w[i] = 0.f; Gm[i] = 0.f; }   // linear predictor
+                bool done = false, first = true;
+                int status = 0, marches = 0;
+                float Cest = 0.f, sprev = 0.f;   // curvature estimate: from THIS step's own iterations only
+                HistView<float, NH, WG> H{Hs};
+                while (true) {
+                    float eps[6], Ge[6], F[6];
+                    // the marched point is frozen once the rod is done: its re-marches (while other rods of the CTA still
+                    // iterate) reproduce the stored states bit for bit
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) Gm[i] = done ? Gm[i] : G[i];
+                    wide_eps(Gm, fd_eps, eps);
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) Ge[i] = Gm[i] + ((k == i + 1) ? eps[i] : 0.f);
+                    // the first joint march of a step is never the accepted one: it stores nothing
+                    ScrSink S{stscr + tid, N, !first && k < 7};
+                    rod_march<float, DIAG, 28, NH>(P, M, Ge, tf, H, S, F);
+                    float Fall[7][6];
+#pragma unroll
+                    for (int c = 0; c < 7; ++c) {
+#pragma unroll
+                        for (int i = 0; i < 6; ++i) Fall[c][i] = __shfl_sync(full, F[i], (lane & ~7) | c);
+                    }
+                    if (!done) {
+                        ++marches;
+                        const int r = wide_decide_lin(Fall, G, eps, tol, Cest, sprev, w);
+                        if (r != 0) { done = true; status = r; }
+                        else if (marches >= max_iter) { done = true; status = -1; }
+                    }
+                    // a rod that converged on the first march is re-marched once at its frozen point so that its state exists
+                    if (ktc::all128(done) && !first) break;
+                    first = false;
+                }
+#pragma unroll
+                for (int i = 0; i < 6; ++i) { Gm1[i] = Gp[i]; w[i] = (status == 2) ? w[i] : 0.f; }
+                __syncwarp();
+                // accepted state = base state + first-order correction (w = 0 unless status == 2); the 8 lanes of the rod
+                // split the elements of the time slice
+                {
+                    const float* sp0 = stscr + (tid & ~7);
+                    for (int e = k; e < NV; e += 8) {
+                        const int r = e / N, j = e - r * N;
+                        if (r >= 19 && j == N - 1) continue;          // never marched (zlast below)
+                        const float* sp = sp0 + (size_t)e * 128;
+                        const float s0 = sp[0];
+                        float va = (sp[1] - s0) * w[0], vb = (sp[2] - s0) * w[1];
+                        va += (sp[3] - s0) * w[2]; vb += (sp[4] - s0) * w[3];
+                        va += (sp[5] - s0) * w[4]; vb += (sp[6] - s0) * w[5];
+                        if (valid) nxt[((size_t)j * 25 + r) * LS] = s0 + (va + vb);
+                    }
+                }
+                if (k == 0 && valid) {
+                    const size_t o = (size_t)(N - 1) * 25 * LS;
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) nxt[o + (19 + c) * LS] = zlast[c];
+                    if (Gout) {
+#pragma unroll
+                        for (int i = 0; i < 6; ++i) Gout[((size_t)b * T_ + t + 1) * 6 + i] = G[i];
+                    }
+                    if (iters) iters[(size_t)b * T_ + t + 1] = status > 0 ? marches : -marches;
+                }
+                __threadfence_block();
+                ktc::sync128();   // the new state is complete (shadow groups read another warp's rod)
+                build_hist(nxt, nxt - tstride);
+                __syncwarp();
+            }
         }
     }
     ktc::cta_teardown(bars, tbase);
@@ -734,18 +780,21 @@ static int tc_prep(const kc_mlp* mlp, unsigned char* img, cudaStream_t st) {
     KC_CHECK_LAUNCH("kc_knode_tc_prep_kernel");
     return KC_OK;
 }
+size_t kc_knode_tc_fwd_scratch_bytes(int N, int64_t B) {
+    return (size_t)tc_bwd_grid(B) * 25 * N * 128 * sizeof(float) + 256;
+}
 int kc_knode_tc_fwd(const RodC<float>& P, const kc_mlp* mlp, int64_t B, int T_, const float* tensions, const float* y0,
                     const float* z0, float* trajD, float tol, int max_iter, float fd_eps, float* Gout, int32_t* iters,
-                    unsigned char* img, cudaStream_t st) {
+                    unsigned char* img, unsigned char* scratch, cudaStream_t st) {
     int rc = tc_prep(mlp, img, st);
     if (rc) return rc;
     const size_t smem = (size_t)ktc::F_HIST + (size_t)(P.N - 1) * 12 * ktc::RPC * sizeof(float);
-    const unsigned grid = (unsigned)((B + ktc::RPC - 1) / ktc::RPC);
+    const unsigned grid = (unsigned)tc_bwd_grid(B);
 #define KC_GO(D)                                                                                                       \
     do {                                                                                                               \
         cudaFuncSetAttribute(kc_knode_tc_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
         kc_knode_tc_fwd_kernel<D><<<grid, ktc::THREADS, smem, st>>>(P, img, (const float*)mlp->b2, mlp->hidden, B, T_, \
-            tensions, y0, z0, trajD, tol, max_iter, fd_eps, Gout, iters);                                              \
+            tensions, y0, z0, trajD, tol, max_iter, fd_eps, Gout, iters, reinterpret_cast<float*>(scratch));           \
     } while (0)
     if (P.diag) KC_GO(true); else KC_GO(false);
 #undef KC_GO

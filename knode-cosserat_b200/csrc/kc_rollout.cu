@@ -23,7 +23,8 @@ bool kc_knode_tc_eligible(int dtype, const kc_mlp* mlp, int N, int method);
 size_t kc_knode_tc_img_bytes();
 int kc_knode_tc_fwd(const RodC<float>& P, const kc_mlp* mlp, int64_t B, int T_, const float* tensions, const float* y0,
                     const float* z0, float* trajD, float tol, int max_iter, float fd_eps, float* Gout, int32_t* iters,
-                    unsigned char* img, cudaStream_t st);
+                    unsigned char* img, unsigned char* scratch, cudaStream_t st);
+size_t kc_knode_tc_fwd_scratch_bytes(int N, int64_t B);
 
 constexpr int KC_LS = 32;  // lane stride of every per-rod array (one warp-wide tile)
 
@@ -530,7 +531,7 @@ int kc_check_mlp(const kc_mlp* mlp) {
 static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct RolloutWs {
-    size_t trajD, wp, wc, state, tcimg, total;
+    size_t trajD, wp, wc, state, tcimg, tcscr, total;
     size_t Bpad;
 };
 static RolloutWs rollout_ws(int dtype, int N, const kc_mlp* mlp, int64_t B, int64_t T_) {
@@ -547,6 +548,8 @@ static RolloutWs rollout_ws(int dtype, int N, const kc_mlp* mlp, int64_t B, int6
     off += align256((size_t)KC_SHOOT_SLOTS * w.Bpad * sz);
     w.tcimg = off;
     if (mlp) off += align256(kc_knode_tc_img_bytes());
+    w.tcscr = off;
+    if (mlp && dtype == KC_F32) off += align256(kc_knode_tc_fwd_scratch_bytes(N, B));
     w.total = off;
     return w;
 }
@@ -658,7 +661,7 @@ static int rollout_typed(const kc_rod_params* Pp, const kc_mlp* mlp, int64_t B, 
         if (tc) {
             if constexpr (std::is_same<T, float>::value) {
                 int rc = kc_knode_tc_fwd(P, mlp, B, (int)T_, (const float*)tensions, (const float*)y0, (const float*)z0, trajD,
-                                         tl, max_iter, fd_eps, (float*)G_out, iters, ws + w.tcimg, st);
+                                         tl, max_iter, fd_eps, (float*)G_out, iters, ws + w.tcimg, ws + w.tcscr, st);
                 if (rc) return rc;
             }
         } else if (coop) {
