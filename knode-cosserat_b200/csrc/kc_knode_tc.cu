@@ -34,6 +34,19 @@
 #include "kc_adjoint.cuh"
 #include "kc_umma.cuh"
 
+// Development aid (make EXTRA=-DKC_TC_TRACE): clock64 time stamps of the three roles of CTA 0 for a few node evaluations,
+// read back by tools/trace_knode_tc.py.  Not compiled into the product build.
+#ifdef KC_TC_TRACE
+__device__ long long* g_ktc_trace = nullptr;   // [3 roles][8 evaluations][32 events]
+extern "C" int kc_knode_tc_set_trace(long long* p) { return (int)cudaMemcpyToSymbol(g_ktc_trace, &p, sizeof(p)); }
+#define KTC_TRACE(on, role, ev, id)                                                                                    \
+    do {                                                                                                               \
+        if ((on) && g_ktc_trace && (ev) >= 100 && (ev) < 108) g_ktc_trace[((role) * 8 + ((ev) - 100)) * 32 + (id)] = clock64(); \
+    } while (0)
+#else
+#define KTC_TRACE(on, role, ev, id) do {} while (0)
+#endif
+
 namespace ktc {
 constexpr int THREADS = 288;          // warps 0-3 physics + epilogue, 4-7 epilogue, 8 MMA issue
 constexpr int RPC = 16;               // rods per CTA (8 rows each)
@@ -74,6 +87,38 @@ __device__ __forceinline__ void split_pair_fast(float x0, float x1, uint32_t& hi
     const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xffff0000u);
     lo = __byte_perm(__float_as_uint(x0 - h0), __float_as_uint(x1 - h1), 0x7632);
 }
+// Packed FP32 (FMUL2 / FADD2 / FFMA2: two values per issue slot).  The epilogues are ISSUE bound (ncu: the two warps of
+// a scheduler alternate, "selected" + "not selected" = 60 % of their samples), so halving the issue slots of the plain
+// arithmetic is what shortens them.
+__device__ __forceinline__ uint64_t pk2(float a, float b) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void upk2(uint64_t r, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(r)); }
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) { uint64_t r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) { uint64_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) { uint64_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ float ex2f(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+// (x0, x1) -> packed bf16 hi pair, packed bf16 lo pair (as split_pair_fast), 5 issue slots per pair
+__device__ __forceinline__ void split_pair2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    hi = pack_bf16x2(x0, x1);
+    const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xffff0000u);
+    float l0, l1;
+    upk2(fma2(pk2(h0, h1), pk2(-1.f, -1.f), pk2(x0, x1)), l0, l1);      // x - hi, exact
+    lo = __byte_perm(__float_as_uint(l0), __float_as_uint(l1), 0x7632);
+}
+// ELU of a pair
+__device__ __forceinline__ void elu_pair(float z0, float z1, float& a0, float& a1) {
+    float t0, t1, e0, e1;
+    upk2(mul2(pk2(z0, z1), pk2(1.4426950408889634f, 1.4426950408889634f)), t0, t1);
+    upk2(add2(pk2(ex2f(t0), ex2f(t1)), pk2(-1.f, -1.f)), e0, e1);
+    a0 = z0 > 0.f ? z0 : e0;
+    a1 = z1 > 0.f ? z1 : e1;
+}
+// dA * ELU'(z) of a pair
+__device__ __forceinline__ void dz_pair(float z0, float z1, float d0, float d1, float& r0, float& r1) {
+    float t0, t1;
+    upk2(mul2(pk2(z0, z1), pk2(1.4426950408889634f, 1.4426950408889634f)), t0, t1);
+    const float e0 = z0 > 0.f ? 1.f : ex2f(t0), e1 = z1 > 0.f ? 1.f : ex2f(t1);
+    upk2(mul2(pk2(d0, d1), pk2(e0, e1)), r0, r1);
+}
 // 32 values of one row -> the row's bf16 hi/lo entries of a [128 x 32] K-major tile (4 x 16-byte stores each)
 __device__ __forceinline__ void store_row32(unsigned char* tile_hi, int row, const float v[32]) {
 #pragma unroll
@@ -108,13 +153,19 @@ __device__ __forceinline__ void fwd_epilogue(uint32_t taddr) {   // taddr -> thi
     umma::wait_ld();
     uint32_t hi[16], lo[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i)
-        split_pair_fast(kc_elu(__uint_as_float(v0[2 * i])), kc_elu(__uint_as_float(v0[2 * i + 1])), hi[i], lo[i]);
+    for (int i = 0; i < 16; ++i) {
+        float a0, a1;
+        elu_pair(__uint_as_float(v0[2 * i]), __uint_as_float(v0[2 * i + 1]), a0, a1);
+        split_pair2(a0, a1, hi[i], lo[i]);
+    }
     umma::st16(taddr, hi);
     umma::st16(taddr + 16, lo);
 #pragma unroll
-    for (int i = 0; i < 16; ++i)
-        split_pair_fast(kc_elu(__uint_as_float(v1[2 * i])), kc_elu(__uint_as_float(v1[2 * i + 1])), hi[i], lo[i]);
+    for (int i = 0; i < 16; ++i) {
+        float a0, a1;
+        elu_pair(__uint_as_float(v1[2 * i]), __uint_as_float(v1[2 * i + 1]), a0, a1);
+        split_pair2(a0, a1, hi[i], lo[i]);
+    }
     umma::st16(taddr + 32, hi);
     umma::st16(taddr + 48, lo);
     umma::wait_st();
@@ -129,9 +180,9 @@ __device__ __forceinline__ void bwd_epilogue(uint32_t taddr) {   // taddr -> lan
     uint32_t hi[16], lo[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-        const float z0 = __uint_as_float(z[2 * i]), z1 = __uint_as_float(z[2 * i + 1]);
-        const float e0 = z0 > 0.f ? 1.f : kc_exp_fast(z0), e1 = z1 > 0.f ? 1.f : kc_exp_fast(z1);
-        split_pair_fast(__uint_as_float(d[2 * i]) * e0, __uint_as_float(d[2 * i + 1]) * e1, hi[i], lo[i]);
+        float r0, r1;
+        dz_pair(__uint_as_float(z[2 * i]), __uint_as_float(z[2 * i + 1]), __uint_as_float(d[2 * i]), __uint_as_float(d[2 * i + 1]), r0, r1);
+        split_pair2(r0, r1, hi[i], lo[i]);
     }
     umma::st16(taddr, hi);
     umma::st16(taddr + 16, lo);
@@ -147,12 +198,18 @@ struct MlpTCF : MlpC<float> {
     uint32_t tbase, laneblk;
     int nch, row;
     mutable uint32_t ph;   // bit b: parity of barZ[b]; bit 3: parity of barO
+    mutable int ev;        // node evaluations so far (trace builds)
+    bool tr;
 };
 
 // forward: o[25] = W2 ELU(W1 x + b1) + b2 for this thread's row; called by all 128 physics threads together
 template <typename T, int IN>
 __device__ __forceinline__ void mlp_eval(const MlpTCF& M, const float* __restrict__ x, float* __restrict__ o) {
     static_assert(IN == 28, "tensor-core march: 28 inputs");
+    KTC_TRACE(M.tr, 0, M.ev, 0);
+#ifdef KC_TC_TRACE
+    if (M.tr && g_ktc_trace && M.ev >= 100 && M.ev < 228) g_ktc_trace[3 * 8 * 32 + (M.ev - 100)] = clock64();
+#endif
     float xv[32];
 #pragma unroll
     for (int i = 0; i < 28; ++i) xv[i] = x[i];
@@ -161,23 +218,29 @@ __device__ __forceinline__ void mlp_eval(const MlpTCF& M, const float* __restric
     umma::fence_async_smem();
     umma::fence_before();                                         // (orders this thread's last TMEM read of O before the next MMAs)
     umma::mbar_arrive(&M.bars->X);
+    KTC_TRACE(M.tr, 0, M.ev, 1);
     for (int c = 0; c < M.nch; ++c) {
         const int buf = c % ktc::NBUF;
         umma::mbar_wait(&M.bars->Z[buf], (M.ph >> buf) & 1u);
         M.ph ^= 1u << buf;
         umma::fence_after();
+        KTC_TRACE(M.tr, 0, M.ev, 2 + 2 * c);
         ktc::fwd_epilogue(M.tbase + M.laneblk + buf * 128);
         umma::fence_before();
         umma::mbar_arrive(&M.bars->A[buf]);
+        KTC_TRACE(M.tr, 0, M.ev, 3 + 2 * c);
     }
     umma::mbar_wait(&M.bars->O, (M.ph >> 3) & 1u);
     M.ph ^= 8u;
     umma::fence_after();
+    KTC_TRACE(M.tr, 0, M.ev, 20);
     uint32_t v[32];
     umma::ld32(M.tbase + M.laneblk + ktc::COL_O, v);
     umma::wait_ld();
 #pragma unroll
     for (int c = 0; c < 25; ++c) o[c] = __uint_as_float(v[c]) + M.b2[c];
+    KTC_TRACE(M.tr, 0, M.ev, 21);
+    ++M.ev;
 }
 
 struct MlpTCB : MlpTCF {};
@@ -223,6 +286,9 @@ namespace ktc {
 template <bool BWD>
 __device__ __forceinline__ void helper_loop(Bars* bars, uint32_t tbase, uint32_t laneblk, int nch) {
     uint32_t ph = 0;
+    int ev = 0;
+    const bool tr = threadIdx.x == 128 && blockIdx.x == 0;
+    (void)ev; (void)tr;
     while (true) {
         for (int c = 0; c < nch; ++c) {
             const int buf = c % NBUF;
@@ -230,11 +296,14 @@ __device__ __forceinline__ void helper_loop(Bars* bars, uint32_t tbase, uint32_t
             ph ^= 1u << buf;
             if (*reinterpret_cast<volatile uint32_t*>(&bars->exit_flag)) return;
             umma::fence_after();
+            KTC_TRACE(tr, 1, ev, 2 + 2 * c);
             if (BWD) bwd_epilogue(tbase + laneblk + buf * 128 + 32);
             else fwd_epilogue(tbase + laneblk + buf * 128 + 64);
             umma::fence_before();
             umma::mbar_arrive(&bars->A[buf]);
+            KTC_TRACE(tr, 1, ev, 3 + 2 * c);
         }
+        ++ev;
     }
 }
 
@@ -251,6 +320,9 @@ __device__ __forceinline__ void mma_loop_fwd(unsigned char* sm, Bars* bars, uint
     const uint64_t dW1h = umma::make_desc(umma::smem_u32(sm + F_W1), 128, 512), dW1l = desc_step(dW1h, IMG);
     const uint64_t dW2h = umma::make_desc(umma::smem_u32(sm + F_W2), 128, 8192), dW2l = desc_step(dW2h, IMG);
     uint32_t phX = 0, phA = 0;
+    int evm = 0;
+    const bool trm = (threadIdx.x & 31) == 0 && blockIdx.x == 0;
+    (void)evm; (void)trm;
     auto gemm1 = [&](int c) {
         const uint32_t d = tbase + (c % NBUF) * 128, wo = c * 8192;
 #pragma unroll
@@ -270,12 +342,15 @@ __device__ __forceinline__ void mma_loop_fwd(unsigned char* sm, Bars* bars, uint
             return;
         }
         umma::fence_after();
+        KTC_TRACE(trm, 2, evm, 0);
         for (int c = 0; c < nch && c < NBUF; ++c) gemm1(c);
+        KTC_TRACE(trm, 2, evm, 1);
         for (int c = 0; c < nch; ++c) {
             const int buf = c % NBUF;
             umma::mbar_wait(&bars->A[buf], (phA >> buf) & 1u);
             phA ^= 1u << buf;
             umma::fence_after();
+            KTC_TRACE(trm, 2, evm, 2 + 2 * c);
             const uint32_t ab = tbase + buf * 128;
 #pragma unroll
             for (int p = 0; p < 3; ++p) {
@@ -287,8 +362,11 @@ __device__ __forceinline__ void mma_loop_fwd(unsigned char* sm, Bars* bars, uint
                 }
             }
             if (c + NBUF < nch) gemm1(c + NBUF);
+            KTC_TRACE(trm, 2, evm, 3 + 2 * c);
         }
         umma::commit_w(&bars->O);
+        KTC_TRACE(trm, 2, evm, 20);
+        ++evm;
     }
 }
 // backward: chunk c = 64 units; buffer = Z (64 columns) | dA (64 columns).  W1 / W2^T images: rows = units (chunk c at
@@ -429,11 +507,13 @@ kc_knode_tc_fwd_kernel(const __grid_constant__ RodC<float> P, const unsigned cha
     } else {
         MlpTCF M{};
         M.sm = sm; M.bars = bars; M.tbase = tbase; M.laneblk = laneblk; M.nch = nch; M.row = tid; M.ph = 0; M.b2 = b2;
+        M.ev = 0; M.tr = tid == 0 && blockIdx.x == 0;
         M.hidden = hidden; M.in_dim = 28;
         const int lane = tid & 31, g = tid >> 3, k = tid & 7;
         const unsigned full = 0xffffffffu;
         const int NV = 25 * N;
-        float* Hs = reinterpret_cast<float*>(sm + ktc::F_HIST) + g;
+        float* Hs = reinterpret_cast<float*>(sm + ktc::F_HIST) + g;                 // history of the step being solved
+        float* As = Hs + (size_t)(N - 1) * NH * WG;                                  // previous accepted state (history rows)
         float* stscr = stscr_all + (size_t)blockIdx.x * NV * 128;      // this CTA's marched states
         const size_t tstride = (size_t)25 * N * LS;
         const int64_t ngroups = (B + WG - 1) / WG;
@@ -452,14 +532,13 @@ kc_knode_tc_fwd_kernel(const __grid_constant__ RodC<float> P, const unsigned cha
             }
             __threadfence_block();
             ktc::sync128();   // (surplus groups read the last rod's initial state written by another warp)
-            auto build_hist = [&](const float* cur, const float* prev) {
-                for (int e = k; e < (N - 1) * NH; e += 8) {
-                    const int j = e / NH, s = e - j * NH;
-                    const size_t o = ((size_t)j * 25 + slot_row<NH>(s)) * LS;
-                    Hs[(size_t)e * WG] = P.c1 * cur[o] + P.c2 * prev[o];
-                }
-            };
-            build_hist(traj_b, traj_b);
+            // history of step 0 and "previous accepted state" from the initial state: state[-1] := state[0] (knode.py:65-66)
+            for (int e = k; e < (N - 1) * NH; e += 8) {
+                const int j = e / NH, s = e - j * NH;
+                const float v = traj_b[((size_t)j * 25 + slot_row<NH>(s)) * LS];
+                As[(size_t)e * WG] = v;
+                Hs[(size_t)e * WG] = (P.c1 + P.c2) * v;
+            }
             float zlast[6];   // z[:, N-1] is never written by the march (cosserat_ode.py:198-201)
 #pragma unroll
             for (int c = 0; c < 6; ++c) zlast[c] = traj_b[((size_t)(N - 1) * 25 + 19 + c) * LS];
@@ -513,18 +592,39 @@ kc_knode_tc_fwd_kernel(const __grid_constant__ RodC<float> P, const unsigned cha
                 for (int i = 0; i < 6; ++i) { Gm1[i] = Gp[i]; w[i] = (status == 2) ? w[i] : 0.f; }
                 __syncwarp();
                 // accepted state = base state + first-order correction (w = 0 unless status == 2); the 8 lanes of the rod
-                // split the elements of the time slice
+                // split the elements of the time slice (e = r*N + j), four elements per lane in flight.  The next step's
+                // history is formed here from the accepted values and the previous accepted state kept in shared memory —
+                // nothing is read back from the trajectory, and a shadow group recomputes its rod's values itself, so the
+                // step needs no CTA-wide barrier.
                 {
-                    const float* sp0 = stscr + (tid & ~7);
-                    for (int e = k; e < NV; e += 8) {
-                        const int r = e / N, j = e - r * N;
-                        if (r >= 19 && j == N - 1) continue;          // never marched (zlast below)
-                        const float* sp = sp0 + (size_t)e * 128;
-                        const float s0 = sp[0];
-                        float va = (sp[1] - s0) * w[0], vb = (sp[2] - s0) * w[1];
-                        va += (sp[3] - s0) * w[2]; vb += (sp[4] - s0) * w[3];
-                        va += (sp[5] - s0) * w[4]; vb += (sp[6] - s0) * w[5];
-                        if (valid) nxt[((size_t)j * 25 + r) * LS] = s0 + (va + vb);
+                    const float* __restrict__ sp0 = stscr + (tid & ~7);
+                    float* __restrict__ out_t = nxt;
+                    for (int e0 = k; e0 < NV; e0 += 32) {
+                        float s0[4], sc[4][6];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int e = e0 + 8 * u < NV ? e0 + 8 * u : NV - 1;
+                            const float* sp = sp0 + (size_t)e * 128;
+                            s0[u] = sp[0];
+#pragma unroll
+                            for (int c = 0; c < 6; ++c) sc[u][c] = sp[c + 1];
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int e = e0 + 8 * u;
+                            const int r = e / N, j = e - r * N;
+                            if (e >= NV || (r >= 19 && j == N - 1)) continue;    // (tip z: never marched, zlast below)
+                            float va = (sc[u][0] - s0[u]) * w[0], vb = (sc[u][1] - s0[u]) * w[1];
+                            va += (sc[u][2] - s0[u]) * w[2]; vb += (sc[u][3] - s0[u]) * w[3];
+                            va += (sc[u][4] - s0[u]) * w[4]; vb += (sc[u][5] - s0[u]) * w[5];
+                            const float v = s0[u] + (va + vb);
+                            if (valid) out_t[((size_t)j * 25 + r) * LS] = v;
+                            if (r >= 13 && j < N - 1) {
+                                const size_t hi = (size_t)(j * NH + r - 13) * WG;
+                                Hs[hi] = P.c1 * v + P.c2 * As[hi];
+                                As[hi] = v;
+                            }
+                        }
                     }
                 }
                 if (k == 0 && valid) {
@@ -537,9 +637,6 @@ kc_knode_tc_fwd_kernel(const __grid_constant__ RodC<float> P, const unsigned cha
                     }
                     if (iters) iters[(size_t)b * T_ + t + 1] = status > 0 ? marches : -marches;
                 }
-                __threadfence_block();
-                ktc::sync128();   // the new state is complete (shadow groups read another warp's rod)
-                build_hist(nxt, nxt - tstride);
                 __syncwarp();
             }
         }
@@ -687,25 +784,30 @@ kc_knode_tc_bwd_kernel(const __grid_constant__ RodC<float> P, const unsigned cha
                 for (int i = 0; i < 6; ++i) if (k == i + 1) wk = -mu[i];
                 float* Hc = hscr + ic * harr;
                 __syncwarp();
-                for (int v0 = 0; v0 < Nm1 * SV; v0 += 8) {
-                    float tot[8];
+                for (int v0 = 0; v0 < Nm1 * SV; v0 += 32) {     // 32 loads in flight (the scratch sits in L2)
+                    float a[32];
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
+                    for (int q = 0; q < 32; ++q) {
                         const int v = v0 + q;
-                        float a = v < Nm1 * SV ? rowscr[(size_t)v * 128] * wk : 0.f;
-                        a += __shfl_xor_sync(full, a, 1);
-                        a += __shfl_xor_sync(full, a, 2);
-                        a += __shfl_xor_sync(full, a, 4);
-                        tot[q] = a;
+                        a[q] = v < Nm1 * SV ? rowscr[(size_t)v * 128] * wk : 0.f;
                     }
-                    float mine = 0.f;
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) if (q == k) mine = tot[q];
-                    const int v = v0 + k;
-                    if (v < Nm1 * SV) {
-                        const int j = v / SV, s = v - j * SV;
-                        if (s < NH) Hc[(size_t)(j * NH + s) * WG] = mine;
-                        else if (valid) gos[(((size_t)b * (T_ - 1) + t) * Nm1 + j) * 25 + (s - NH)] = mine;
+                    for (int q8 = 0; q8 < 4; ++q8) {
+                        float mine = 0.f;
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            float t = a[q8 * 8 + q];
+                            t += __shfl_xor_sync(full, t, 1);
+                            t += __shfl_xor_sync(full, t, 2);
+                            t += __shfl_xor_sync(full, t, 4);
+                            if (q == k) mine = t;
+                        }
+                        const int v = v0 + q8 * 8 + k;
+                        if (v < Nm1 * SV) {
+                            const int j = v / SV, s = v - j * SV;
+                            if (s < NH) Hc[(size_t)(j * NH + s) * WG] = mine;
+                            else if (valid) gos[(((size_t)b * (T_ - 1) + t) * Nm1 + j) * 25 + (s - NH)] = mine;
+                        }
                     }
                 }
                 if (gten) {
@@ -758,7 +860,7 @@ __global__ void kc_knode_tc_prep_kernel(const float* __restrict__ W1, const floa
 // ---- host side (called by kc_rollout.cu / kc_bptt.cu) ----------------------------------------------------------------
 bool kc_knode_tc_eligible(int dtype, const kc_mlp* mlp, int N, int method) {
     if (!mlp || dtype != KC_F32 || mlp->in_dim != 28 || mlp->hidden > 512 || method != KC_MARCH_EULER) return false;
-    if ((size_t)ktc::F_HIST + (size_t)(N - 1) * 12 * ktc::RPC * 4 > 227 * 1024) return false;
+    if ((size_t)ktc::F_HIST + (size_t)2 * (N - 1) * 12 * ktc::RPC * 4 > 227 * 1024) return false;
     const char* e = getenv("KC_ROLLOUT_TC");
     if (e && e[0] == '0') return false;
     return true;
@@ -788,7 +890,7 @@ int kc_knode_tc_fwd(const RodC<float>& P, const kc_mlp* mlp, int64_t B, int T_, 
                     unsigned char* img, unsigned char* scratch, cudaStream_t st) {
     int rc = tc_prep(mlp, img, st);
     if (rc) return rc;
-    const size_t smem = (size_t)ktc::F_HIST + (size_t)(P.N - 1) * 12 * ktc::RPC * sizeof(float);
+    const size_t smem = (size_t)ktc::F_HIST + (size_t)2 * (P.N - 1) * 12 * ktc::RPC * sizeof(float);
     const unsigned grid = (unsigned)tc_bwd_grid(B);
 #define KC_GO(D)                                                                                                       \
     do {                                                                                                               \
