@@ -345,68 +345,128 @@ def main():
                                    "graph) with every rank holding its own 1024 trajectories; compare trajectory_steps_per_s "
                                    "with 1024 x train.value at N = 1"}
 
-    # ---------------- KNODE rollout training step (C3 ii, north-star extension): rollout + loss + BPTT + Adam ----------
-    bptt = None
-    if not args.no_train:
-        from Utils.transformations import quaternion_to_euler
-        torch.manual_seed(1)
-        brobot = CosseratRodTorch(str(dev), TRAIN_H)
-        setup_robot(brobot, "youngs")
+    # ---------------- KNODE rollout + rollout training step (C3 ii, north-star subsystems 2 and 3) ----------------------
+    # MLP of the march on tcgen05 (csrc/kc_knode_tc.cu).  Executed tensor work per node evaluation of a 128-row CTA:
+    # forward 2 GEMMs x 128 x 32 x 512 MAC, backward 3 GEMMs, each in 3 bf16 hi/lo passes.
+    bf16_peak = float(peaks.get("bf16_tflops", 1590.0)) * 1e12
+    MMA_FWD = 2 * 128 * 32 * 512 * 2 * 3.0
+    MMA_BWD = 3 * 128 * 32 * 512 * 2 * 3.0
+    F_MLP = 106.0 * TRAIN_H
+    FLOP_PER_RNS_KNODE = E_REF * (N_NODES - 1) / N_NODES * (F_ODE + F_MLP)      # 738.7 kFLOP
+
+    def knode_model(seed):
+        torch.manual_seed(seed)
+        r_ = CosseratRodTorch(str(dev), TRAIN_H)
+        setup_robot(r_, "youngs")
         with torch.no_grad():   # a trained-size residual (the reference's random init is unstable inside a rollout)
-            brobot.nn_models[2].weight.mul_(0.02)
-            brobot.nn_models[2].bias.mul_(0.02)
-        nb = TRAIN_B // world
-        target = plan.traj[:nb, :TRAIN_T].contiguous()
-        btens = ctl[:nb, :TRAIN_T].contiguous()
-        key = torch.tensor(TRAIN_KEYS, device=dev)
-        BW = [p for p in brobot.nn_models.parameters()]
-        bm = [torch.zeros_like(w.data) for w in BW]
-        bv = [torch.zeros_like(w.data) for w in BW]
-        bstep = [0]
+            r_.nn_models[2].weight.mul_(0.02)
+            r_.nn_models[2].bias.mul_(0.02)
+        return r_
 
-        def bptt_step():
-            traj, its_b = brobot.rollout(btens, return_iters=True)
-            pk, tk = traj[:, 1:, :, key], target[:, 1:, :, key]
-            qp = pk[:, :, 3:7].permute(2, 0, 1, 3).reshape(4, -1)
-            qt = tk[:, :, 3:7].permute(2, 0, 1, 3).reshape(4, -1)
-            loss = ((pk[:, :, :3] - tk[:, :, :3]) ** 2).mean() + ((pk[:, :, 7:19] - tk[:, :, 7:19]) ** 2).mean() + \
-                ((quaternion_to_euler(qp) - quaternion_to_euler(qt)) ** 2).mean() + \
-                ((traj[:, 1:, 19:, key - 1] - target[:, 1:, 19:, key - 1]) ** 2).mean()
-            for w in BW:
-                w.grad = None
-            loss.backward()
-            grads = [w.grad for w in BW]
-            if world > 1:
-                flat = torch.cat([g.reshape(-1) for g in grads])
-                dist.all_reduce(flat)
-                off = 0
-                new = []
-                for g in grads:
-                    new.append(flat[off:off + g.numel()].view_as(g) / world)
-                    off += g.numel()
-                grads = new
-            bstep[0] += 1
-            for i, (w, g) in enumerate(zip(BW, grads)):
-                _ops.adam_clamp(w.data, g, bm[i], bv[i], bstep[0], lr=1e-4, clamp=(i % 2 == 0))
-            return loss, its_b
+    def group_marches(iters_bt, rods_per_cta=16):
+        """Joint marches the tensor-core kernel executes: a CTA's 16 rods march until the slowest one has converged."""
+        a = iters_bt[:, 1:].abs().float()
+        pad = (-a.shape[0]) % rods_per_cta
+        if pad:
+            a = torch.cat([a, a[-1:].expand(pad, -1)])
+        return float(a.view(-1, rods_per_cta, a.shape[1]).amax(1).clamp(min=2).sum().item())
 
-        nsteps_b = max(2, min(args.steps, 5))
+    knode = None
+    bptt = None
+    bptt_weak = None
+    if not args.no_train:
+        # (a) forward KNODE rollout at a batch that fills the chip: 148 CTAs x 128 rows = 18 944 rods per GPU
+        KB, KT = 148 * 128, TRAIN_T
+        krobot = knode_model(1)
+        ksd = krobot.nn_models.state_dict()
+        kmlp = _ops.Mlp(ksd["0.weight"], ksd["0.bias"], ksd["2.weight"], ksd["2.bias"])
+        ktens = torch.tensor(synthetic_tensions(KB, KT, krobot.del_t, seed=100 + rank), device=dev)
+        kplan = _ops.RolloutPlan(krobot._params(), kmlp, KB, KT, torch.float32, dev, rows=25)
         for _ in range(2):
-            bptt_step()
+            kplan.run(ktens)
         barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(nsteps_b):
-            bl, its_b = bptt_step()
-        e1.record()
-        barrier()
-        bms = max_over_ranks(e0.elapsed_time(e1)) / nsteps_b
-        bptt = {"metric": "KNODE rollout-BPTT train steps/sec", "value": 1e3 / bms, "unit": "steps/s", "ms_per_step": bms,
-                "global_batch_trajectories": TRAIN_B, "rollout_steps": TRAIN_T - 1, "hidden": TRAIN_H, "steps": nsteps_b,
-                "semantics": "29-step KNODE rollout from the straight rod + 4-term loss at key nodes + BPTT "
-                             "(kc_rollout_bwd) + all-reduce + Adam + clamp; MLP inside the march on the FP32 SIMT path",
-                "loss": float(bl.item()), "all_converged": bool(int(its_b.min()) >= 0),
-                "rod_node_steps_per_s_fwd_bwd": TRAIN_B * N_NODES * (TRAIN_T - 1) / (bms * 1e-3)}
+        kms = []
+        for _ in range(max(3, min(args.steps, 5))):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            kplan.run(ktens)
+            e1.record()
+            e1.synchronize()
+            kms.append(e0.elapsed_time(e1))
+        kms_med = max_over_ranks(float(np.median(kms)))
+        k_rns = KB * N_NODES * (KT - 1)
+        k_exec = group_marches(kplan.iters) * (N_NODES - 1) * MMA_FWD
+        knode = {"metric": "KNODE rod-node-steps/sec (forward rollout, MLP in the march)", "value": world * k_rns / (kms_med * 1e-3),
+                 "unit": "rod-node-steps/s", "ms_per_rollout": kms_med, "rods_per_gpu": KB, "time_indices": KT, "hidden": TRAIN_H,
+                 "dtype": "f32", "all_converged": bool(int(kplan.iters.min()) >= 0),
+                 "marches_per_step_mean": float(kplan.iters[:, 1:].abs().float().mean().item()),
+                 "roofline": {"bound": "tensor", "kernel": "kc_knode_tc_fwd_kernel (tcgen05 kind::f16, activation tile in TMEM, "
+                              ".ts MMA; 16 rods x 8 shooting points per CTA)",
+                              "achieved": k_exec / (kms_med * 1e-3) / 1e12, "peak": bf16_peak / 1e12, "unit": "TFLOP/s",
+                              "frac": k_exec / (kms_med * 1e-3) / bf16_peak,
+                              "peak_source": "MEASURED_PEAKS.json bf16_tflops (cuBLAS burst; the kernel is timed alone)",
+                              "what": "EXECUTED tensor FLOP/s: every joint march evaluates the MLP for 128 rows per CTA "
+                                      "(8 shooting points per rod: base + 6 finite-difference points + 1 spare) in 3 bf16 "
+                                      "hi/lo passes (fp32-grade products); rows padded to K = 32 inputs / N = 32 outputs",
+                              "useful_tflops": k_rns * FLOP_PER_RNS_KNODE / (kms_med * 1e-3) / 1e12,
+                              "useful_frac": k_rns * FLOP_PER_RNS_KNODE / (kms_med * 1e-3) / bf16_peak,
+                              "useful_normalisation": "738.7 kFLOP per rod-node-step = 15 nominal evaluations x 9/10 x (449 + "
+                                                      "106 H) FLOP (SURVEY 8d)"}}
+        del kplan, ktens
+
+        # (b) rollout training: 29-step KNODE rollout from the straight rod + fused 4-term loss + BPTT + all-reduce + Adam
+        from _train import BpttTrainer
+
+        def bptt_leg(presharded):
+            brobot = knode_model(1)
+            nb = TRAIN_B if presharded else TRAIN_B // world
+            lo = 0 if presharded else rank * nb
+            tr = BpttTrainer(brobot, plan.traj[lo:lo + nb, :TRAIN_T].contiguous(), ctl[lo:lo + nb, :TRAIN_T].contiguous(),
+                             TRAIN_KEYS, lr=1e-4, presharded=True)
+            for _ in range(3):
+                tr.step(sync=False)
+            barrier()
+            n_ = max(3, min(args.steps, 10))
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(n_):
+                tr.step(sync=True)       # the loss is read every step: the plateau scheduler runs as in physics_train.py
+            e1.record()
+            barrier()
+            ms = max_over_ranks(e0.elapsed_time(e1)) / n_
+            its_ = tr.plan.fwd.iters
+            exec_flop = group_marches(its_) * (N_NODES - 1) * MMA_FWD + \
+                ((nb + 15) // 16) * (TRAIN_T - 1) * (N_NODES - 1) * MMA_BWD
+            identical = None
+            if world > 1:
+                wflat = torch.cat([p_.data.reshape(-1) for p_ in brobot.nn_models.parameters()])
+                wlo, whi = wflat.clone(), wflat.clone()
+                dist.all_reduce(wlo, op=dist.ReduceOp.MIN)
+                dist.all_reduce(whi, op=dist.ReduceOp.MAX)
+                identical = bool(torch.equal(wlo, whi))
+            gb = nb * world
+            return {"metric": "KNODE rollout-BPTT train steps/sec", "value": 1e3 / ms, "unit": "steps/s", "ms_per_step": ms,
+                    "global_batch_trajectories": gb, "trajectories_per_gpu": nb, "rollout_steps": TRAIN_T - 1,
+                    "hidden": TRAIN_H, "steps": n_, "scaling": "weak" if presharded else "strong",
+                    "trajectory_steps_per_s": gb * 1e3 / ms,
+                    "semantics": "29-step KNODE rollout from the straight rod (kc_rollout_fwd, MLP on tcgen05) + fused 4-term "
+                                 "loss and cotangent at the key nodes (kc_rollout_loss) + BPTT (kc_rollout_bwd: joint adjoint "
+                                 "march, MLP input-VJP on tcgen05, weight gradients by the tensor-core sample reduction) + "
+                                 "one all-reduce of [gradients | loss] + kc_adam_clamp_multi; loss read every step",
+                    "loss": tr.loss_arr[-1], "all_converged": tr.converged(),
+                    "rod_node_steps_per_s_fwd_bwd": gb * N_NODES * (TRAIN_T - 1) / (ms * 1e-3),
+                    "weights_bitwise_identical_across_ranks": identical,
+                    "roofline": {"bound": "tensor", "kernel": "kc_knode_tc_fwd_kernel + kc_knode_tc_bwd_kernel",
+                                 "achieved": exec_flop / (ms * 1e-3) / 1e12, "peak": bf16_peak / 1e12, "unit": "TFLOP/s",
+                                 "frac": exec_flop / (ms * 1e-3) / bf16_peak,
+                                 "what": "executed tensor FLOP/s per GPU of the WHOLE step (3 bf16 hi/lo passes, 8 rows per "
+                                         "rod); at %d rods per GPU only %d of 148 SMs hold a CTA — the step is bound by the "
+                                         "dependent chain of node evaluations, not by the tensor pipe" % (nb, (nb + 15) // 16)}}
+
+        bptt = bptt_leg(False)
+        if world > 1:
+            bptt_weak = bptt_leg(True)
 
     # ---------------- state estimation (SURVEY 8f rank 2): estimate_state on recordings resident in HBM ----------------
     estimate = None
@@ -511,7 +571,8 @@ def main():
                          "profiles/r01_ncu_prof_rollout_lin_r1h.csv (algorithmic 416 MB: 410 MB trajectory written once + "
                          "6.5 MB tensions read; the tail of the trajectory is still in L2 when the kernel ends)",
                          "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak}},
-            "cpu_baseline": cpu, "train": train, "train_weak": train_weak, "train_bptt": bptt, "estimate_state": estimate}
+            "cpu_baseline": cpu, "train": train, "train_weak": train_weak, "knode_rollout": knode, "train_bptt": bptt,
+            "train_bptt_weak": bptt_weak, "estimate_state": estimate}
         print(json.dumps(out))
     sys.stdout.flush()
     if world > 1:

@@ -167,6 +167,15 @@ int kc_rollout_bwd(int dtype, const kc_rod_params *P, const kc_mlp *mlp, int64_t
                    const void *traj, const void *g_traj, void *g_tensions, void *gW1, void *gb1, void *gW2, void *gb2,
                    void *workspace, int64_t workspace_bytes, void *stream);
 
+/* The training loss of physics_train.py:345-352 (p | n,m,q,w | euler(h) at the key nodes k, z at node k-1; every block a
+ * mean over its entries, the K key nodes and the T-1 steps, Utils/transformations.py:3-31 for the Euler angles) applied to a
+ * ROLLOUT against a target trajectory, fused with its cotangent — the loss of the north-star rollout training step (C3 ii;
+ * the reference only ever applies it to teacher-forced one-step predictions).  traj, target: [B][T][25][N];
+ * key_idx_host[K]: distinct node indices in [1, N-1] -> *loss (device, float64 always) = scale * sum over trajectories, and
+ * g_traj[B][T][25][N] = d loss / d traj (OVERWRITTEN, dense), ready for kc_rollout_bwd. */
+int kc_rollout_loss(int dtype, int64_t B, int64_t T, int32_t N, int32_t K, const int32_t *key_idx_host, const void *traj,
+                    const void *target, double scale, double *loss, void *g_traj, void *stream);
+
 /* One teacher-forced training step of physics_train.py's fast path (:313-368) == slow path (:215-267) restricted
  * to its key nodes == train_segment.py:140-185: for every trajectory b, step t in [0, T-2] and key node k:
  * ODE+MLP at node k-1 of the NEXT ground-truth state, Euler step, 4-term MSE loss (p | n,m,q,w | euler(h) | z,

@@ -326,6 +326,67 @@ def rollout_bwd(P, mlp, tensions, traj, g_traj, want_g_tensions=True, want_param
     return (gt, *gp)
 
 
+def rollout_loss(traj, target, key_idx, scale=1.0, g_traj=None, loss=None):
+    """kc_rollout_loss: the 4-term training loss (physics_train.py:345-352) of a rollout against a target trajectory,
+    fused with its cotangent.  traj, target [B,T,25,N] -> (loss float64[1] tensor, g_traj [B,T,25,N])."""
+    _require_cuda(traj, target)
+    traj, target = _c(traj), _c(target, traj.dtype)
+    B, T, rows, N = traj.shape
+    if rows != 25 or tuple(target.shape) != tuple(traj.shape):
+        raise ValueError("rollout_loss needs traj and target of shape [B,T,25,N]")
+    ki = np.ascontiguousarray(np.asarray(key_idx).reshape(-1), dtype=np.int32)
+    if g_traj is None:
+        g_traj = torch.empty_like(traj)
+    if loss is None:
+        loss = torch.zeros(1, dtype=torch.float64, device=traj.device)
+    with torch.cuda.device(traj.device):
+        rc = _kc.lib().kc_rollout_loss(_dtype_code(traj), B, T, N, int(ki.size), ki.ctypes.data_as(C.POINTER(C.c_int32)),
+                                       _ptr(traj), _ptr(target), float(scale), _ptr(loss), _ptr(g_traj), _stream(traj.device))
+    _kc.check(rc, "kc_rollout_loss")
+    return loss, g_traj
+
+
+class BpttStepPlan:
+    """One rollout-training step with nothing but kernel launches: kc_rollout_fwd -> kc_rollout_loss -> kc_rollout_bwd,
+    every buffer allocated once.  As in TrainStepPlan the four gradients are views of ONE flat buffer whose last element
+    receives the loss, so a single all-reduce covers gradients and loss."""
+
+    def __init__(self, P, weights, tensions, target, key_idx, scale=1.0):
+        _require_cuda(tensions, target, *weights)
+        self.P = P
+        self.dt, self.dev = target.dtype, target.device
+        self.tensions, self.target = _c(tensions, self.dt), _c(target)
+        self.B, self.T, rows, self.N = self.target.shape
+        if rows != 25:
+            raise ValueError("target must be [B,T,25,N]")
+        self.key, self.scale = np.asarray(key_idx).reshape(-1), float(scale)
+        self.mlp = Mlp(*weights)
+        sizes = [t.numel() for t in (self.mlp.W1, self.mlp.b1, self.mlp.W2, self.mlp.b2)]
+        self.flat = torch.zeros(sum(sizes) + 1, dtype=self.dt, device=self.dev)
+        self.grads, off = [], 0
+        for t, n in zip((self.mlp.W1, self.mlp.b1, self.mlp.W2, self.mlp.b2), sizes):
+            self.grads.append(self.flat[off:off + n].view_as(t))
+            off += n
+        self.loss64 = torch.zeros(1, dtype=torch.float64, device=self.dev)
+        self.fwd = RolloutPlan(P, self.mlp, self.B, self.T, self.dt, self.dev, rows=25)
+        self.g_traj = torch.empty_like(self.target)
+        with torch.cuda.device(self.dev):
+            self.nbytes = int(_kc.lib().kc_rollout_bwd_workspace_bytes(_DT[self.dt], C.byref(P), self.mlp.ref(), self.B, self.T))
+        self.ws = torch.empty(max(self.nbytes, 1), dtype=torch.uint8, device=self.dev)
+
+    def run(self):
+        self.fwd.P = self.P
+        traj = self.fwd.run(self.tensions)
+        rollout_loss(traj, self.target, self.key, self.scale, g_traj=self.g_traj, loss=self.loss64)
+        with torch.cuda.device(self.dev):
+            rc = _kc.lib().kc_rollout_bwd(_DT[self.dt], C.byref(self.P), self.mlp.ref(), self.B, self.T, _ptr(self.tensions),
+                                          _ptr(traj), _ptr(self.g_traj), None, *[_ptr(g) for g in self.grads], _ptr(self.ws),
+                                          self.nbytes, _stream(self.dev))
+        _kc.check(rc, "kc_rollout_bwd")
+        self.flat[-1:].copy_(self.loss64)
+        return self.flat
+
+
 def train_step(P, mlp, traj, controls, key_idx, want_pred=False):
     """kc_train_step: traj[B,T,25,N], controls[B,T,4] -> (loss float64[1] tensor, (gW1,gb1,gW2,gb2), pred|None)."""
     _require_cuda(traj, controls)

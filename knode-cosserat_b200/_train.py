@@ -184,6 +184,64 @@ class TeacherForcedTrainer:
                                   "weight_decay": self.weight_decay, "params": list(range(len(self.params)))}]}
 
 
+class BpttTrainer:
+    """Rollout training (north-star C3 ii): every step rolls the KNODE model out from the straight rod under the recorded
+    tensions, compares the rollout with the target trajectories at the key nodes (the reference's 4-term loss), and
+    back-propagates THROUGH the rollout (kc_rollout_bwd) into the MLP weights; then the same all-reduce / Adam / clamp as
+    the teacher-forced trainer.  The reference has no such loop (it never differentiates a rollout); the
+    optimiser settings are physics_train.py's (:198-207,289-304).
+
+    targets [B,T,25,N], tensions [B,T,4]; under torch.distributed every rank keeps its shard (presharded=True: the tensors
+    passed ARE the shard).  The loss is the mean over the GLOBAL batch, so the all-reduced gradient is the single-GPU one."""
+
+    def __init__(self, robot, targets, tensions, key_pt_idx, lr=1e-3, weight_decay=0.0, clamp_weight=True, patience=80,
+                 factor=0.5, presharded=False):
+        self.robot = robot
+        self.rank, self.world = _dist.world_info()
+        n = targets.shape[0]
+        if presharded:
+            self.n_total, lo, hi = n * self.world, 0, n
+        else:
+            self.n_total = n
+            lo, hi = _dist.shard_range(n, self.rank, self.world)
+        self.params = [p for p in robot.nn_models.parameters()]
+        weights = [p.data for p in self.params]
+        self.is_weight = ['weight' in nm and 'layer1' not in nm for nm, _ in robot.nn_models.named_parameters()]
+        self.sched = PlateauLR(lr, patience, factor)
+        self.plan = _ops.BpttStepPlan(robot._params(), weights, tensions[lo:hi].detach(), targets[lo:hi].detach(),
+                                      key_pt_idx, scale=1.0 / max(self.n_total, 1))
+        self.adam = _ops.AdamClampMulti(weights, self.plan.grads, [clamp_weight and w for w in self.is_weight],
+                                        lr=lr, weight_decay=weight_decay)
+        self._lr_on_device = lr
+        self.step_no = 0
+        self.loss_arr = []
+
+    def step(self, train=True, sync=True):
+        self.plan.P = self.robot._params()
+        lr = self.sched.get_last_lr()[0]
+        if lr != self._lr_on_device:
+            self.adam.set_lr(lr)
+            self._lr_on_device = lr
+        self.plan.run()
+        if self.world > 1:
+            dist.all_reduce(self.plan.flat)
+        if train:
+            self.adam.run()
+            self.step_no += 1
+            for p, g in zip(self.params, self.plan.grads):
+                p.grad = g
+        if not sync:
+            return None
+        loss_val = float(self.plan.flat[-1].item())
+        self.loss_arr.append(loss_val)
+        if train:
+            self.sched.step(loss_val)
+        return loss_val
+
+    def converged(self):
+        return bool(int(self.plan.fwd.iters.min()) >= 0)
+
+
 def dtw_l1(a, b):
     """Exact dynamic-time-warping distance with the L1 point distance — what fastdtw(a, b)[0] approximates with its
     default radius=1 (physics_train.py:159, physics_multitrain.py:211).  a[Ta,d], b[Tb,d].

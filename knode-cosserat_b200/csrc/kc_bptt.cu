@@ -205,3 +205,101 @@ extern "C" int kc_rollout_bwd(int dtype, const kc_rod_params* P, const kc_mlp* m
         return bwd_typed<float>(P, mlp, B, T_, tensions, traj, g_traj, g_tensions, gW1, gb1, gW2, gb2, workspace, st);
     return bwd_typed<double>(P, mlp, B, T_, tensions, traj, g_traj, g_tensions, gW1, gb1, gW2, gb2, workspace, st);
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Loss of a rollout against a target trajectory and its cotangent, fused (north-star C3(ii): the training loss of
+// physics_train.py:345-352 applied to a ROLLOUT instead of a teacher-forced step): for every trajectory b, time index
+// t = 1..T-1 and key node k:  MSE(p) + MSE(n,m,q,w) + MSE(euler(h)) at node k and MSE(z) at node k-1, every block
+// averaged over its own entries, the key nodes and the T-1 steps, times `scale`.
+// -> *loss (double) and g_traj[B][T][25][N] = d loss / d traj (dense; zero where the loss does not look).
+struct KeyIdx { int32_t k[64]; };
+constexpr int KC_LOSS_BLOCKS = 1024;
+__device__ double kc_loss_partials[KC_LOSS_BLOCKS];
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+kc_rollout_loss_kernel(int64_t B, int T_, int N, int K, KeyIdx key, const T* __restrict__ traj, const T* __restrict__ target,
+                       double scale, T* __restrict__ g_traj) {
+    __shared__ double red[8];
+    const int64_t total = B * (T_ - 1) * K;
+    const T S = T(T_ - 1);
+    const T wp = T(scale) / (T(3 * K) * S), wf = T(scale) / (T(12 * K) * S), wz = T(scale) / (T(6 * K) * S);
+    double acc = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int kk = (int)(i % K);
+        const int64_t bt = i / K;
+        const int t = 1 + (int)(bt % (T_ - 1));
+        const int64_t b = bt / (T_ - 1);
+        const int node = key.k[kk];
+        const size_t base = ((size_t)b * T_ + t) * 25 * N;
+        const T* pr = traj + base;
+        const T* tg = target + base;
+        T* g = g_traj + base;
+        T a = T(0);
+#pragma unroll
+        for (int r = 0; r < 3; ++r) { const T e = pr[r * N + node] - tg[r * N + node]; a += wp * e * e; g[r * N + node] = T(2) * wp * e; }
+#pragma unroll
+        for (int r = 7; r < 19; ++r) { const T e = pr[r * N + node] - tg[r * N + node]; a += wf * e * e; g[r * N + node] = T(2) * wf * e; }
+#pragma unroll
+        for (int c = 19; c < 25; ++c) { const T e = pr[c * N + node - 1] - tg[c * N + node - 1]; a += wz * e * e; g[c * N + node - 1] = T(2) * wz * e; }
+        T qp[4], qt[4], ep[3], et[3], ge[3], gq[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) { qp[r] = pr[(3 + r) * N + node]; qt[r] = tg[(3 + r) * N + node]; }
+        quat_to_euler(qp, ep);
+        quat_to_euler(qt, et);
+#pragma unroll
+        for (int r = 0; r < 3; ++r) { const T e = ep[r] - et[r]; a += wp * e * e; ge[r] = T(2) * wp * e; }
+        quat_to_euler_vjp(qp, ge, gq);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) g[(3 + r) * N + node] = gq[r];
+        acc += (double)a;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < 8; ++w) s += red[w];
+        kc_loss_partials[blockIdx.x] = s;
+    }
+}
+__global__ void kc_loss_sum_kernel(int n, double* __restrict__ loss) {   // fixed order: bitwise reproducible
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double s = 0.0;
+        for (int i = 0; i < n; ++i) s += kc_loss_partials[i];
+        *loss = s;
+    }
+}
+
+extern "C" int kc_rollout_loss(int dtype, int64_t B, int64_t T_, int32_t N, int32_t K, const int32_t* key_idx_host,
+                               const void* traj, const void* target, double scale, double* loss, void* g_traj, void* stream) {
+    KC_CHECK_ARG(dtype == KC_F32 || dtype == KC_F64, "dtype must be KC_F32 or KC_F64");
+    KC_CHECK_ARG(B >= 0 && T_ >= 2 && N >= 2, "need B >= 0, T >= 2, N >= 2");
+    KC_CHECK_ARG(K >= 1 && K <= 64 && key_idx_host, "1 <= K <= 64 and key_idx_host non-NULL");
+    KC_CHECK_ARG(loss && (B == 0 || (traj && target && g_traj)), "NULL pointer");
+    KeyIdx key{};
+    for (int i = 0; i < K; ++i) {
+        KC_CHECK_ARG(key_idx_host[i] >= 1 && key_idx_host[i] < N, "key node indices must lie in [1, N-1]");
+        for (int j = 0; j < i; ++j) KC_CHECK_ARG(key_idx_host[j] != key_idx_host[i], "key node indices must be distinct");
+        key.k[i] = key_idx_host[i];
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t sz = dtype == KC_F32 ? 4 : 8;
+    const int64_t total = B * (T_ - 1) * K;
+    int grid = (int)((total + 255) / 256);
+    if (grid > KC_LOSS_BLOCKS) grid = KC_LOSS_BLOCKS;
+    if (grid < 1) grid = 1;
+    if (B > 0) {
+        cudaError_t e = cudaMemsetAsync(g_traj, 0, (size_t)B * T_ * 25 * N * sz, st);
+        if (e != cudaSuccess) { kc_set_error("cudaMemsetAsync: %s", cudaGetErrorString(e)); return KC_ECUDA; }
+    }
+    if (dtype == KC_F32)
+        kc_rollout_loss_kernel<float><<<grid, 256, 0, st>>>(B, (int)T_, N, K, key, (const float*)traj, (const float*)target, scale, (float*)g_traj);
+    else
+        kc_rollout_loss_kernel<double><<<grid, 256, 0, st>>>(B, (int)T_, N, K, key, (const double*)traj, (const double*)target, scale, (double*)g_traj);
+    KC_CHECK_LAUNCH("kc_rollout_loss_kernel");
+    kc_loss_sum_kernel<<<1, 32, 0, st>>>(grid, loss);
+    KC_CHECK_LAUNCH("kc_loss_sum_kernel");
+    return KC_OK;
+}

@@ -164,3 +164,66 @@ def test_differentiable_rollout_trains_on_tensor_cores(tc):
         opt.step()
         losses.append(loss.item())
     assert losses[-1] < losses[0]
+
+
+@pytest.mark.parametrize("dt", [torch.float64, torch.float32])
+def test_rollout_loss_matches_torch_autograd(dt):
+    """kc_rollout_loss (fused 4-term loss of a rollout + its cotangent) against the same loss written with torch ops and
+    differentiated by autograd (the loss lines of physics_train.py:345-352 with Utils/transformations.quaternion_to_euler)."""
+    import _ops
+    from Utils.transformations import quaternion_to_euler
+    torch.manual_seed(4)
+    B, T, N = 5, 7, 10
+    key = [3, 5, 7, 9]
+    traj = torch.randn(B, T, 25, N, device="cuda", dtype=dt)
+    target = traj + 0.1 * torch.randn_like(traj)
+    loss, g = _ops.rollout_loss(traj, target, key, scale=0.25)
+    x = traj.clone().double().requires_grad_(True)
+    tg = target.double()
+    k = torch.tensor(key, device="cuda")
+    pk, tk = x[:, 1:, :, k], tg[:, 1:, :, k]
+    # (quaternion_to_euler force-casts to fp32, Utils/transformations.py:14: restate it in the tensor's own precision)
+    def euler(q):
+        q = q / q.norm(dim=2, keepdim=True)
+        w_, x_, y_, z_ = q[:, :, 0], q[:, :, 1], q[:, :, 2], q[:, :, 3]
+        roll = torch.atan2(2 * (w_ * y_ + x_ * z_), 1 - 2 * (y_ * y_ + z_ * z_))
+        pitch = torch.asin(torch.clamp(2 * (w_ * z_ - x_ * y_), -1, 1))
+        yaw = torch.atan2(2 * (w_ * x_ + y_ * z_), 1 - 2 * (x_ * x_ + z_ * z_))
+        return torch.stack([roll, pitch, yaw], dim=2)
+    per_traj = ((pk[:, :, :3] - tk[:, :, :3]) ** 2).mean(dim=(2, 3)).sum(1) + \
+               ((pk[:, :, 7:19] - tk[:, :, 7:19]) ** 2).mean(dim=(2, 3)).sum(1) + \
+               ((euler(pk[:, :, 3:7]) - euler(tk[:, :, 3:7])) ** 2).mean(dim=(2, 3)).sum(1) + \
+               ((x[:, 1:, 19:, k - 1] - tg[:, 1:, 19:, k - 1]) ** 2).mean(dim=(2, 3)).sum(1)
+    ref = 0.25 * per_traj.sum() / (T - 1)
+    ref.backward()
+    tol = 1e-12 if dt == torch.float64 else 2e-5
+    assert abs(loss.item() - ref.item()) < tol * abs(ref.item()) * 10
+    assert (g.double() - x.grad).abs().max().item() < tol * x.grad.abs().max().item() * 10
+    # the euler restatement above is the reference's function
+    q = torch.randn(4, 9, device="cuda")
+    assert torch.allclose(euler(q.T[None, :, :, None].double())[0, :, :, 0].T.float(), quaternion_to_euler(q), atol=1e-5)
+
+
+def test_bptt_trainer_reduces_the_rollout_loss(tc):
+    """_train.BpttTrainer: rollout -> fused loss -> BPTT -> Adam + clamp, all library kernels."""
+    from cosserat_ode_torch import CosseratRodTorch
+    from knode import setup_robot
+    from physics_controls import synthetic_tensions
+    from _train import BpttTrainer
+    torch.manual_seed(0)
+    truth = CosseratRodTorch("cuda", 32)
+    setup_robot(truth)
+    truth.use_nn = False
+    model = CosseratRodTorch("cuda", 256)
+    setup_robot(model, "youngs")
+    with torch.no_grad():
+        model.nn_models[2].weight.mul_(0.05)
+        model.nn_models[2].bias.mul_(0.1)
+    tens = torch.tensor(synthetic_tensions(48, 12, truth.del_t, seed=3), device="cuda")
+    with torch.no_grad():
+        target = truth.rollout(tens)
+    tr = BpttTrainer(model, target, tens, [3, 5, 7, 9], lr=1e-3)
+    losses = [tr.step() for _ in range(8)]
+    assert tr.converged()
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0]
+    assert all((p.data >= 0).all() for n, p in model.nn_models.named_parameters() if "weight" in n)
