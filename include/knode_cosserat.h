@@ -209,6 +209,16 @@ int kc_adam_clamp_multi(int dtype, int32_t n_tensors, const kc_adam_tensor *tens
                         const double *lr_dev, double beta1, double beta2, double eps, double weight_decay,
                         int32_t *ticket_dev, void *stream);
 
+/* Evaluation metrics of the training drivers for E (prediction, reference) pairs of rollouts, on the device:
+ * dtw[E] = exact dynamic-time-warping distance with the L1 point distance between pred[e][:, 0:3, node] (Ta points) and
+ * ref[e][:, 0:3, node] (Tb points) — what fastdtw(trajectory[:, :3, 9], tip_pos)[0] approximates (physics_train.py:159,
+ * physics_multitrain.py:211; fastdtw is a third-party package the reference does not pin); and, if mse != NULL,
+ * mse[E] = 1000 * mean of the squared position errors and squared 'zyx' Euler-angle differences over all nodes and time
+ * indices (physics_multitrain.py:213-222, scipy Rotation.from_quat(q, scalar_first=True).as_euler('zyx')); NaN if Ta != Tb.
+ * pred[E][Ta][rows][N], ref[E][Tb][rows][N] (rows >= 7: 25 or 50); outputs are float64 on the device. */
+int kc_eval_metrics(int dtype, int64_t E, int64_t Ta, int64_t Tb, int32_t rows, int32_t N, int32_t node, const void *pred,
+                    const void *ref, double *dtw, double *mse, void *stream);
+
 /* State estimation from measurements (replaces estimate_state(data, tensions, robot),
  * knode_cosserat_realworld/estimate_state.py:158-242 with its helpers :11-156): data[B][T][7][N] (positions 0:3 and
  * quaternions 3:7 (w,x,y,z) on the full grid), tensions[B][T][4] -> est[B][T][25][N] in the state layout of the path.

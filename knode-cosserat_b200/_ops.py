@@ -500,6 +500,30 @@ class AdamClampMulti:
         _kc.check(rc, "kc_adam_clamp_multi")
 
 
+def eval_metrics(pred, ref, node=None, want_mse=True):
+    """kc_eval_metrics: pred [E,Ta,rows,N], ref [E,Tb,rows,N] (or one pair without the leading axis) on the device ->
+    (dtw float64[E], mse float64[E] | None): exact L1 DTW of the tip positions and the pos + Euler-'zyx' MSE x 1000."""
+    _require_cuda(pred, ref)
+    single = pred.ndim == 3
+    if single:
+        pred, ref = pred[None], ref[None]
+    pred, ref = _c(pred), _c(ref, pred.dtype)
+    E, Ta, rows, N = pred.shape
+    Tb = ref.shape[1]
+    if ref.shape[0] != E or ref.shape[2] != rows or ref.shape[3] != N:
+        raise ValueError("pred and ref must share E, rows and N")
+    node = N - 1 if node is None else int(node)
+    dtw = torch.empty(E, dtype=torch.float64, device=pred.device)
+    mse = torch.empty(E, dtype=torch.float64, device=pred.device) if want_mse else None
+    with torch.cuda.device(pred.device):
+        rc = _kc.lib().kc_eval_metrics(_dtype_code(pred), E, Ta, Tb, rows, N, node, _ptr(pred), _ptr(ref), _ptr(dtw),
+                                       _ptr(mse), _stream(pred.device))
+    _kc.check(rc, "kc_eval_metrics")
+    if single:
+        return dtw[0], (mse[0] if want_mse else None)
+    return dtw, mse
+
+
 def fma_peak(dtype, iters, device):
     """Measured FP32/FP64 FMA-pipe throughput in FLOP/s (CUDA-event timed), used as the rollout's roofline peak."""
     code = _DT[dtype]

@@ -161,8 +161,8 @@ class TeacherForcedTrainer:
 
     def step(self, train=True):
         """One epoch of the reference loop: loss -> backward -> Adam -> scheduler -> clamp (physics_train.py:266-304)."""
-        if self.fused and self.traj.shape[0] > 0:
-            return self.fused_step(train)
+        if self.fused:   # also on a rank whose shard is empty: kc_train_step returns zero gradients for B = 0, and every rank
+            return self.fused_step(train)   # must apply the SAME Adam kernel for the weights to stay bitwise identical
         loss, grads = self.loss_and_grads()
         loss_val = float(loss.item())
         self.loss_arr.append(loss_val)

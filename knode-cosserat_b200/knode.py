@@ -77,14 +77,23 @@ def _robot_mlp(robot, dtype):
 
 
 def simulate(robot, ctl, robot_reference=None, *, dtype=np.float64, rows=50, tol=0.0, max_iter=0, return_info=False,
-             pinned_out=None, method="euler"):
+             pinned_out=None, method="euler", device_out=False):
     """Roll the rod out under the tendon tensions `ctl` ([T,4] -> [T,rows,N]; [B,T,4] -> [B,T,rows,N]).
 
     Keyword-only extensions (not in the reference): dtype (np.float64 | np.float32 arithmetic and output), rows (50 =
     reference layout, 25 = [y;z] only), tol / max_iter of the shooting solve, return_info -> (traj, G[..,T,6],
     marches[..,T]), pinned_out = a pinned host torch tensor to receive the result (avoids an allocation per call),
     method = "euler" (getResidualEuler, what the reference's loop calls, knode.py:89) or "rk4" (the reference's
-    getResidualRK4, cosserat_ode.py:215-255, as the residual of the same loop).
+    getResidualRK4, cosserat_ode.py:215-255, as the residual of the same loop), device_out = True with CUDA tensions:
+    return the trajectory as a CUDA tensor (no device-to-host copy; for callers that reduce it on the GPU, e.g. the
+    evaluation metrics of physics_train / physics_multitrain).
+
+    Shooting solve: Newton / Broyden on the 6 base reactions to `tol` (default 1e-11 fp64, 2e-6 fp32, relative to
+    max(1, |G|)) instead of MINPACK hybrd.  In the kernels with the linearised final correction (small batches) the LAST
+    Newton step of a time step is not re-marched: once the step dG is so small that its estimated second-order remainder
+    4 C |dG|^2 is below tol, the state at G + dG is formed from the finite-difference marches of the same iteration.  Such
+    steps are reported in `marches` like any converged step; KC_ROLLOUT_LIN=0 in the environment switches the correction
+    off (every accepted state is then a marched one) — the parity tests run both.
     """
     if robot_reference is None:
         robot_reference = robot
@@ -140,6 +149,13 @@ def simulate(robot, ctl, robot_reference=None, *, dtype=np.float64, rows=50, tol
     if on_device:
         plan.run(tens, y0, z0, tol=tol, max_iter=max_iter)
         traj, G, iters = plan.traj, plan.G, plan.iters
+        if device_out:
+            out_t = traj.clone()
+            if single:
+                out_t = out_t[0]
+            if return_info:
+                return (out_t, G[0].clone(), iters[0].clone()) if single else (out_t, G.clone(), iters.clone())
+            return out_t
         if pinned_out is not None:
             pinned_out.copy_(traj, non_blocking=True)
             torch.cuda.current_stream().synchronize()

@@ -4,7 +4,10 @@ The reference fans {dataset} x {mod} x {seed} out as physics_train.py subprocess
 stdout (physics_multitrain.py:85-157); then rolls every saved model out with numpy + fsolve and prints a DTW / pos+Euler
 MSE table against the physics-only baseline (:169-233).  Here the jobs are independent replicas: under torchrun each
 rank takes every world-th job on its own GPU (no collective); a plain run executes them in-process one after the other.
-The evaluation rollouts of one job (all eval sets) are one batched GPU launch.
+The evaluation rollouts of one job (all eval sets) are one batched GPU launch and stay on the device: the DTW and the
+pos + Euler MSE columns come from kc_eval_metrics (exact L1 DTW — fastdtw, which the reference uses, approximates it — and
+scipy's as_euler('zyx') in closed form); only the two scalars per cell and the evals/*.npy dumps cross to the host.
+All ranks synchronise before the evaluation (the reference joins its training subprocesses first, :152-157).
 """
 import argparse
 import os
@@ -13,8 +16,8 @@ import numpy as np
 import torch
 
 import _dist
+import _ops
 import physics_train
-from _train import dtw_l1
 from cosserat_ode import CosseratRod
 from knode import setup_robot, simulate
 from physics_controls import calc_controls
@@ -47,10 +50,29 @@ def pct_error(new, old):
     return (new - old) / old * 100
 
 
-def quat_to_euler_zyx(q):
-    """scipy Rotation.from_quat(q, scalar_first=True).as_euler('zyx') (physics_multitrain.py:216-217), q[n,4] wxyz."""
-    from scipy.spatial.transform import Rotation
-    return Rotation.from_quat(q[:, [1, 2, 3, 0]]).as_euler('zyx')
+def wait_for_all_ranks(rank, world, paths, timeout_s=24 * 3600):
+    """The reference evaluates only after every training subprocess has been joined (physics_multitrain.py:152-157).
+    Under torchrun the jobs of other ranks may still be running when rank 0 finishes its own: barrier through
+    torch.distributed when a process group can be made, and in any case wait until every expected checkpoint exists
+    (checkpoints are written atomically, physics_train.save_checkpoint)."""
+    import time
+    if world > 1:
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            dist.init_process_group("nccl" if torch.cuda.is_available() else "gloo")
+        dist.barrier()
+    t0 = time.time()
+    missing = [p for p in paths if not os.path.exists(p)]
+    while missing and time.time() - t0 < timeout_s:
+        time.sleep(1.0)
+        missing = [p for p in missing if not os.path.exists(p)]
+    if missing:
+        raise FileNotFoundError(f"checkpoints never appeared: {missing}")
+
+
+def model_path(args, data, mod, seed):
+    filename = '_'.join('-'.join(s).replace('.', '_') for s in split_list(data.split(' ')))
+    return f'{args.save_dir}/physics_{filename}_{mod}_trainlen_30_{args.epochs}_epoch_{seed}.pth'
 
 
 def main(argv=None):
@@ -64,8 +86,9 @@ def main(argv=None):
     datas = ['sine sine 0.5 1.0', 'sine sine random 0.5 1.0 0.0']   # physics_multitrain.py:43-46
     eval_set = ['sine 1.5', 'step 1.5']                                # :62-65
 
+    jobs = [(d, m, s) for d in datas for m in MODS for s in range(args.n_seeds)]
     if args.train:
-        jobs = [(d, m, s) for d in datas for m in MODS for s in range(args.n_seeds)]
+        t_start = __import__("time").time()
         for i, (data, mod, seed) in enumerate(jobs):
             if i % world != rank:
                 continue
@@ -77,12 +100,22 @@ def main(argv=None):
             print(f'[rank {rank}] training {data};{mod};{seed}')
             physics_train.main(argv_job + [*control_type, *control_arg], distributed=False)
 
+    if args.eval:
+        wait_for_all_ranks(rank, world, [model_path(args, *j) for j in jobs],
+                           timeout_s=24 * 3600 if (world > 1 and args.train) else 0)
+        if args.train and rank == 0:   # a checkpoint older than this run would be a stale model from an earlier run
+            stale = [p for p in (model_path(args, *j) for j in jobs) if os.path.getmtime(p) < t_start - 1.0]
+            if stale:
+                raise RuntimeError(f"stale checkpoints (not written by this run): {stale}")
     if args.eval and rank == 0:
+        dev = torch.device("cuda", torch.cuda.current_device())
         robot_reference = CosseratRod(use_fsolve=True)
         setup_robot(robot_reference)
         ctl_eval = np.array([calc_controls(e.split(' ')[0], float(e.split(' ')[1]), robot_reference.del_t, 100)
                              for e in eval_set])
-        ref = simulate(robot_reference, ctl_eval)[:, :, :25]  # one batched launch for all eval sets
+        ctl_eval_dev = torch.tensor(ctl_eval, device=dev)
+        ref_dev = simulate(robot_reference, ctl_eval_dev, device_out=True)[:, :, :25].contiguous()  # one batched launch
+        ref = ref_dev.cpu().numpy()
         print(' ' * SPACE, end='')
         for e in eval_set:
             print((';' + e + ' DTW').ljust(20), end='')
@@ -98,23 +131,18 @@ def main(argv=None):
                         robot = CosseratRod(use_fsolve=True, nn_path=None)
                     else:
                         data_short = f'{data} {mod} {seed}'
-                        filename = '_'.join('-'.join(s).replace('.', '_') for s in split_list(data.split(' ')))
-                        nn_path = f'{args.save_dir}/physics_{filename}_{mod}_trainlen_30_{args.epochs}_epoch_{seed}.pth'
-                        robot = CosseratRod(use_fsolve=True, nn_path=nn_path)
+                        robot = CosseratRod(use_fsolve=True, nn_path=model_path(args, data, mod, seed))
                     setup_robot(robot, mod)
                     print(data_short.ljust(SPACE), end='')
-                    trajs = simulate(robot, ctl_eval)
+                    trajs_dev = simulate(robot, ctl_eval_dev, device_out=True)
+                    dtws, mses = _ops.eval_metrics(trajs_dev[:, :, :25].contiguous(), ref_dev, node=9)   # (:211-222) on the GPU
+                    dtws, mses, trajs = dtws.cpu().numpy(), mses.cpu().numpy(), trajs_dev.cpu().numpy()
                     for k, evall in enumerate(eval_set):
                         trajectory, interp = trajs[k], ref[k]
                         fn = evall.replace(' ', '_') + '+' + data_short.replace(' ', '_')
                         np.save(f'evals/physics_{fn}_trainlen_30_{args.epochs}_epochs.npy',
                                 {"tensions": ctl_eval[k], "reference": interp, "predicted": trajectory})
-                        dtw = dtw_l1(trajectory[:, :3, 9], interp[:, :3, 9])
-                        se_pos = (trajectory[:, :3] - interp[:, :3]).reshape((-1, 3)) ** 2
-                        eq = trajectory[:, 3:7].transpose((0, 2, 1)).reshape((-1, 4))
-                        rq = interp[:, 3:7].transpose((0, 2, 1)).reshape((-1, 4))
-                        se_euler = (quat_to_euler_zyx(eq) - quat_to_euler_zyx(rq)) ** 2
-                        mse = np.mean(np.concatenate([se_euler, se_pos])) * 1000
+                        dtw, mse = float(dtws[k]), float(mses[k])
                         if data is None:
                             baselines[(evall, mod)] = {'dtw': dtw, 'mse': mse}
                             print(';{0:.2f}'.format(dtw).ljust(20), end='')

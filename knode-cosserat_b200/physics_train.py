@@ -17,7 +17,8 @@ import numpy as np
 import torch
 
 import _dist
-from _train import TeacherForcedTrainer, dtw_l1, transplant
+import _ops
+from _train import TeacherForcedTrainer, transplant
 from cosserat_ode import CosseratRod
 from cosserat_ode_torch import CosseratRodTorch
 from knode import setup_robot, simulate
@@ -89,7 +90,8 @@ def main(argv=None, distributed=True):
     ctl_train = np.array([calc_controls(t, a, robot_reference.del_t, train_len) for t, a in zip(control_type, control_arg)])
     np_traj_ls = list(simulate(robot_reference, ctl_train)[:, :, :25])
     ctl_val = np.array(calc_controls(validation_type, validation_arg, robot_reference.del_t, eval_len))
-    validation_reference = simulate(robot_reference, ctl_val)[:, :25]
+    ctl_val_dev = torch.tensor(ctl_val, device=device)
+    validation_reference_dev = simulate(robot_reference, ctl_val_dev, device_out=True)[:, :25].contiguous()
 
     torch_traj_ls, torch_controls_ls = [], []
     for traj_np, controls_np in zip(np_traj_ls, ctl_train):  # noise exactly as :126-127
@@ -116,12 +118,20 @@ def main(argv=None, distributed=True):
                                    weight_decay=args.weight_decay, clamp_weight=CLAMP_WEIGHT)
     loss_arr, dtw_arr, saves = trainer.loss_arr, [], {}
 
+    def save_checkpoint(obj):
+        """torch.save through a temporary file + rename: a reader (physics_multitrain's evaluation, another rank) never
+        sees a half-written checkpoint."""
+        tmp = f"{MODEL_SAVE_PATH}.tmp{os.getpid()}"
+        torch.save(obj, tmp)
+        os.replace(tmp, MODEL_SAVE_PATH)
+
     def evaluate(torch_robot=None):
         """(:136-167) KNODE rollout of the validation controls on the GPU, DTW of the tip position vs the reference."""
         if torch_robot is not None:
             transplant(robot_eval, torch_robot)
-        traj_np = simulate(robot_eval, ctl_val[:eval_len])[:eval_len, :25]
-        dtw_metric = dtw_l1(traj_np[:, :3, 9], validation_reference[:, :3, 9])
+        # rollout and metric stay on the device: only the DTW scalar comes back (kc_rollout_fwd -> kc_eval_metrics)
+        traj_dev = simulate(robot_eval, ctl_val_dev[:eval_len], device_out=True)[:eval_len]
+        dtw_metric = float(_ops.eval_metrics(traj_dev, validation_reference_dev, node=9, want_mse=False)[0].item())
         print('Validation DTW Distance XYZ', dtw_metric)
         dtw_arr.append([dtw_metric])
         buff = io.BytesIO()
@@ -135,8 +145,7 @@ def main(argv=None, distributed=True):
             evaluate(robot if epoch != 0 else None)
         if TRAIN and epoch % save_every == 0 and epoch != 0 and rank == 0:
             print("saving model")
-            torch.save({'robot': robot, 'dtw': dtw_arr, 'loss': loss_arr, 'optim': trainer.optim_state_dict()},
-                       MODEL_SAVE_PATH)
+            save_checkpoint({'robot': robot, 'dtw': dtw_arr, 'loss': loss_arr, 'optim': trainer.optim_state_dict()})
         total_loss = trainer.step(train=TRAIN)
         if epoch % 10 == 0 and (args.verbose or not args.fast) and rank == 0:
             print(f"Epoch {epoch} of {args.epochs}")
@@ -147,11 +156,10 @@ def main(argv=None, distributed=True):
         if args.fast and args.eval and saves:  # (:410-417) keep the best-by-validation model
             best_dtw = min(saves.keys())
             print('Saving model with dtw', best_dtw)
-            torch.save({**torch.load(saves[best_dtw], weights_only=False), 'dtw': dtw_arr, 'loss': loss_arr,
-                        'optim': trainer.optim_state_dict()}, MODEL_SAVE_PATH)
+            save_checkpoint({**torch.load(saves[best_dtw], weights_only=False), 'dtw': dtw_arr, 'loss': loss_arr,
+                             'optim': trainer.optim_state_dict()})
         else:
-            torch.save({'robot': robot, 'dtw': dtw_arr, 'loss': loss_arr, 'optim': trainer.optim_state_dict()},
-                       MODEL_SAVE_PATH)
+            save_checkpoint({'robot': robot, 'dtw': dtw_arr, 'loss': loss_arr, 'optim': trainer.optim_state_dict()})
     trainer.close()
     return robot, loss_arr
 

@@ -557,3 +557,42 @@ def adam_clamp_step(params, grads, state, lr=1e-2, betas=(0.9, 0.999), eps=1e-8,
             p = np.maximum(p, 0)
         new[k] = p
     return new
+
+
+# ---- evaluation metrics (physics_train.py:159, physics_multitrain.py:211-222) ---------------------------------------------
+def dtw_l1(a, b):
+    """Exact dynamic-time-warping distance with the L1 point distance, a[Ta,d], b[Tb,d] — the quantity
+    fastdtw(a, b)[0] (physics_train.py:159, physics_multitrain.py:211) approximates with radius 1.  fastdtw is a
+    third-party package the reference neither vendors nor pins; its published algorithm (Salvador & Chan, "FastDTW", 2007)
+    is a multi-resolution approximation of exactly this recurrence, plain cell-by-cell loops here:
+        acc[i,j] = |a_i - b_j|_1 + min(acc[i-1,j], acc[i,j-1], acc[i-1,j-1])."""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    Ta, Tb = len(a), len(b)
+    acc = np.full((Ta + 1, Tb + 1), np.inf)
+    acc[0, 0] = 0.0
+    for i in range(1, Ta + 1):
+        for j in range(1, Tb + 1):
+            d = a[i - 1] - b[j - 1]
+            cost = (abs(d[0]) + abs(d[1])) + abs(d[2]) if d.shape[0] == 3 else np.abs(d).sum()
+            acc[i, j] = cost + min(min(acc[i - 1, j], acc[i, j - 1]), acc[i - 1, j - 1])
+    return float(acc[Ta, Tb])
+
+
+def euler_zyx(q):
+    """scipy Rotation.from_quat(q, scalar_first=True).as_euler('zyx') (physics_multitrain.py:216-217) in closed form,
+    q[n,4] = (w,x,y,z): extrinsic rotations about z, y, x, i.e. R = Rx(c) Ry(b) Rz(a) -> [a, b, c]."""
+    q = np.asarray(q, dtype=np.float64)
+    q = q / np.linalg.norm(q, axis=1, keepdims=True)
+    w, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+    r00, r01, r02 = 1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)
+    r12, r22 = 2 * (y * z - w * x), 1 - 2 * (x * x + y * y)
+    return np.stack([np.arctan2(-r01, r00), np.arcsin(np.clip(r02, -1, 1)), np.arctan2(-r12, r22)], axis=1)
+
+
+def pos_euler_mse(trajectory, interpolated):
+    """physics_multitrain.py:213-222: 1000 * mean over [squared Euler-angle differences ; squared position errors]."""
+    se_pos = (trajectory[:, :3] - interpolated[:, :3]).reshape((-1, 3)) ** 2
+    eq = trajectory[:, 3:7].transpose((0, 2, 1)).reshape((-1, 4))
+    rq = interpolated[:, 3:7].transpose((0, 2, 1)).reshape((-1, 4))
+    se_euler = (euler_zyx(eq) - euler_zyx(rq)) ** 2
+    return float(np.mean(np.concatenate([se_euler, se_pos])) * 1000)

@@ -251,3 +251,54 @@ def test_physics_multitrain_script_trains_and_writes_evals(tmp_path, monkeypatch
     assert np.isfinite(d["predicted"]).all()
     base = np.load(tmp_path / "evals" / "physics_sine_1.5+baseline_youngs_trainlen_30_2_epochs.npy", allow_pickle=True).item()
     assert np.abs(base["predicted"][:, :3, 9] - base["reference"][:, :3, 9]).max() > 1e-4   # a modified rod differs
+    # the printed table VALUES: every cell recomputed from the saved rollouts with the oracle metrics (exact L1 DTW;
+    # pos + Euler MSE pinned to scipy's Rotation.as_euler('zyx'), tests/test_oracle_golden.py) — physics_multitrain.py:211-222
+    from oracle import rod_oracle as O
+    rows = {l.split(';')[0].strip(): l.split(';')[1:] for l in out.splitlines() if ';' in l and not l.startswith(' ')}
+    assert len(rows) == 12
+    for name in ("baseline youngs", "sine sine 0.5 1.0 nsw 0", "sine sine random 0.5 1.0 0.0 short 0"):
+        for k, ev in enumerate(("sine_1.5", "step_1.5")):
+            dd = np.load(tmp_path / "evals" / f"physics_{ev}+{name.replace(' ', '_')}_trainlen_30_2_epochs.npy", allow_pickle=True).item()
+            dtw = O.dtw_l1(dd["predicted"][:, :3, 9], dd["reference"][:, :3, 9])
+            mse = O.pos_euler_mse(dd["predicted"][:, :25], dd["reference"])
+            assert float(rows[name][2 * k].split()[0]) == float(f"{dtw:.2f}"), (name, ev, rows[name], dtw)
+            assert float(rows[name][2 * k + 1].split()[0]) == float(f"{mse:.2f}"), (name, ev, rows[name], mse)
+
+
+def test_reference_pickled_checkpoint_rollout(golden):
+    """The evaluation path of physics_train.py:136-158 from a checkpoint the reference itself pickled: CosseratRod(nn_path=
+    tests/golden/ref_checkpoint.pth) + simulate against the rollout the reference computes from the same weights."""
+    import os
+    from conftest import GOLDEN
+    from cosserat_ode import CosseratRod
+    from knode import setup_robot, simulate
+    d = golden["ref_checkpoint"]
+    r = CosseratRod(nn_path=os.path.join(GOLDEN, "ref_checkpoint.pth"), use_fsolve=True)
+    setup_robot(r, "youngs")
+    got = simulate(r, d["ctl"])
+    assert got.shape == d["traj"].shape
+    for lo, hi in [(0, 3), (3, 7), (7, 10), (10, 13), (13, 16), (16, 19), (19, 22), (22, 25)]:
+        s_ = np.abs(d["traj"][:, lo:hi]).max()
+        assert np.abs(got[:, lo:hi] - d["traj"][:, lo:hi]).max() < 1e-9 * max(s_, 1e-30)
+
+
+@pytest.mark.parametrize("dt", [torch.float64, torch.float32])
+def test_eval_metrics_kernel_vs_oracle(golden, dt):
+    """kc_eval_metrics (GPU DTW wavefront + pos/Euler-'zyx' MSE) against the oracle (pinned to scipy's as_euler and to the
+    exact DTW recurrence): DTW bit for bit in fp64, the MSE column to rounding; unequal lengths; rows = 25 and 50."""
+    import _ops
+    from oracle import rod_oracle as O
+    d = golden["rollouts"]
+    a, b = d["setup_sine_traj"][:60], d["setup_random_traj"][:60]            # [T,50,N]
+    pred = torch.tensor(np.stack([a, b, a]), dtype=dt, device="cuda")
+    ref = torch.tensor(np.stack([b, a, a]), dtype=dt, device="cuda")
+    dtw, mse = _ops.eval_metrics(pred, ref)
+    pa, pb = pred.cpu().numpy().astype(np.float64), ref.cpu().numpy().astype(np.float64)
+    for e in range(3):
+        assert dtw[e].item() == O.dtw_l1(pa[e][:, :3, 9], pb[e][:, :3, 9])
+        want = O.pos_euler_mse(pa[e], pb[e])
+        assert abs(mse[e].item() - want) <= 1e-12 * max(want, 1e-30) + 1e-300
+    d2, m2 = _ops.eval_metrics(pred[0, :, :25], ref[0, :37, :25])           # one pair, 25 rows, unequal lengths
+    assert d2.item() == O.dtw_l1(pa[0][:, :3, 9], pb[0][:37, :3, 9]) and np.isnan(m2.item())
+    d3, _ = _ops.eval_metrics(pred[:, :1], ref[:, :1], want_mse=False)       # a single time index
+    assert d3[0].item() == float(np.abs(pa[0][0, :3, 9] - pb[0][0, :3, 9]).sum())

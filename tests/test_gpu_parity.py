@@ -219,6 +219,48 @@ def test_rollout_full_size_properties(ops, mode):
 
 
 @pytest.mark.parametrize("dt", [torch.float64, torch.float32])
+@pytest.mark.parametrize("name,kind,mod", [ROLLS[0], ROLLS[2], ROLLS[4], ROLLS[-1]])
+def test_rollout_plain_wide_kernel_vs_reference(ops, golden, monkeypatch, dt, name, kind, mod):
+    """kc_rollout_wide_kernel itself (8 lanes per rod, Newton, NO linearised final correction): the launcher upgrades every
+    small batch to wide-lin, so it is forced here with KC_ROLLOUT_LIN=0 — it is the kernel an fp64 rollout of 1 777 - 4 736
+    rods gets (next test)."""
+    monkeypatch.setenv("KC_ROLLOUT_MODE", "wide")
+    monkeypatch.setenv("KC_ROLLOUT_LIN", "0")
+    d = golden["rollouts"]
+    P = O.RodParams() if kind == "default" else P_setup(mod)
+    traj, G, iters = ops.rollout(params(P), None, dev(d[name + "_ctl"][None], dt), rows=50, want_G=True)
+    assert int(iters.min()) >= 0
+    got = traj.cpu().numpy()[0].astype(np.float64)
+    assert field_err(got[:, :25], d[name + "_traj"][:, :25]) < TOL[dt]
+    assert field_err(got[:, 25:], d[name + "_traj"][:, 25:]) < TOL[dt] * 10
+
+
+def test_rollout_fp64_4096_rods_selects_plain_wide_kernel(ops, monkeypatch):
+    """fp64 at BASELINE config 2's batch (4096 rods): the launcher's own choice here is the plain wide kernel (wide-lin's
+    fp64 state only fits one wave up to 1 776 rods).  Properties at full batch + sampled rods against the fp64 oracle at
+    the fp64 bar, and bitwise agreement with the same kernel forced explicitly (proves which kernel ran)."""
+    for k in ("KC_ROLLOUT_MODE", "KC_ROLLOUT_LIN", "KC_ROLLOUT_COOP"):
+        monkeypatch.delenv(k, raising=False)
+    rng = np.random.default_rng(2)
+    P = P_setup()
+    B, T = 4096, 24
+    ctl = np.stack([np.array(O.calc_controls("sine", 0.5 + 2.5 * rng.random(), P.del_t, T)) if b % 2 == 0
+                    else 5 + 5 * rng.random((T, 4)) for b in range(B)])
+    ctl[1] = ctl[0]
+    traj, _, iters = ops.rollout(params(P), None, dev(ctl, torch.float64))
+    assert int(iters.min()) >= 0
+    tr = traj.cpu().numpy()
+    assert np.isfinite(tr).all() and np.array_equal(tr[0], tr[1])
+    assert np.abs(tr[:, 1:, 7:13, -1]).max() < 1e-9
+    sel = [0, 7, 2048, 4095]
+    assert field_err(tr[sel], O.rollout_newton(P, ctl[sel], rows=25)) < 1e-9
+    monkeypatch.setenv("KC_ROLLOUT_MODE", "wide")
+    monkeypatch.setenv("KC_ROLLOUT_LIN", "0")
+    forced, _, _ = ops.rollout(params(P), None, dev(ctl, torch.float64))
+    assert torch.equal(traj, forced)
+
+
+@pytest.mark.parametrize("dt", [torch.float64, torch.float32])
 @pytest.mark.parametrize("N,B", [(20, 40), (7, 19), (13, 33)])
 def test_rollout_other_node_counts(ops, mode, dt, N, B):
     """BASELINE config 5 at reduced size: 2x the default node count (and two odd counts) — the kernels take N at run time;

@@ -79,6 +79,29 @@ def test_torch_class_constructs_and_pickles_on_cpu(tmp_path):
     assert CosseratRodTorch("cpu", 8, nn_input_history=True).nn_models[0].weight.shape == (8, 53)
 
 
+def test_reference_pickled_checkpoint_loads_into_the_drop_in(golden):
+    """tests/golden/ref_checkpoint.pth was written by the UNMODIFIED reference (make_checkpoint.py: torch.save of the whole
+    CosseratRodTorch object + dtw/loss lists + Adam state, physics_train.py:284-288).  Unpickling resolves the class by
+    module name, i.e. to the drop-in; CosseratRod(nn_path=...) (cosserat_ode.py:81-88) must hand back the reference's
+    weights in state-dict order, and the resumed object must still be a usable CosseratRodTorch."""
+    import os
+    from conftest import GOLDEN
+    from cosserat_ode import CosseratRod
+    from cosserat_ode_torch import CosseratRodTorch
+    d = golden["ref_checkpoint"]
+    path = os.path.join(GOLDEN, "ref_checkpoint.pth")
+    r = CosseratRod(nn_path=path, use_fsolve=True)
+    assert [p.shape for p in r.param_ls] == [(64, 28), (64,), (25, 64), (25,)]
+    for got, k in zip(r.param_ls, ("W1", "b1", "W2", "b2")):
+        assert np.array_equal(got, d[k])
+    ck = torch.load(path, map_location="cpu", weights_only=False)
+    assert isinstance(ck["robot"], CosseratRodTorch) and ck["dtw"] == [1.25, 0.75] and ck["loss"] == [0.5, 0.25, 0.125]
+    assert ck["robot"].E == 10e9 and ck["robot"].del_t == 0.05            # setup_robot(..., "youngs") state travelled
+    assert set(ck["optim"].keys()) == {"state", "param_groups"}
+    ck["robot"].compute_intermediate_terms()                             # the drop-in's methods work on the unpickled object
+    assert ck["robot"]._params().N == 10
+
+
 def test_plateau_lr_matches_torch():
     from _train import PlateauLR
     rng = np.random.default_rng(0)
@@ -160,3 +183,21 @@ def test_gradient_allreduce_world2_gloo():
     for rank, g, cnt in res:
         assert g == want                      # identical (bitwise) on every rank == single-process sum
         assert cnt == [[5.0] * 3] * 2
+
+
+def test_data_processing_matches_reference_behaviour():
+    """Utils/data_processing.py (knode_cosserat_realworld/Utils/data_processing.py:3-50): axis choice by rank, range clipped
+    to 1e-10, squeezed statistics, and the reference's denormalize formula."""
+    from Utils.data_processing import denormalize_data, normalize_data
+    rng = np.random.default_rng(0)
+    d3 = rng.standard_normal((7, 4, 5))
+    d3[:, 2] = 3.0                                   # a constant channel: range clipped, not replaced by 1
+    n, lo, span = normalize_data(d3)
+    assert lo.shape == (4,) and span.shape == (4,)
+    np.testing.assert_array_equal(lo, d3.min(axis=(0, 2)))
+    np.testing.assert_array_equal(span, np.clip(d3.max(axis=(0, 2)) - d3.min(axis=(0, 2)), 1e-10, np.inf))
+    assert span[2] == 1e-10 and n.min() == 0.0 and abs(n[:, [0, 1, 3]].max() - 1.0) < 1e-15
+    d2 = rng.standard_normal((9, 3))
+    n2, lo2, span2 = normalize_data(d2)
+    np.testing.assert_array_equal(lo2, d2.min(axis=0))
+    np.testing.assert_allclose(denormalize_data(n2, lo2, lo2 + span2), d2, rtol=0, atol=1e-15)

@@ -288,3 +288,57 @@ def test_rollout_rk4_residual(golden, name):
     if name == "default_sine":
         euler = O.rollout_newton(P_default(), d[name + "_ctl"][None])[0]
         assert rel_field_err(euler[:, :25], d[name + "_traj"][:, :25]) > 0.1
+
+
+# ---- gradients through a rollout: autograd through the reference's ODE_parallel composition (make_bptt_golden.py) ----------
+@pytest.mark.parametrize("tag", ["h16", "h48"])
+def test_bptt_golden_rollout_and_a_gradient_entry(golden, tag):
+    """The composed, differentiable rollout the golden gradients come from IS the oracle's rollout (which is pinned to
+    knode.simulate), and a finite difference of the oracle reproduces golden gradient entries."""
+    d = golden["bptt"]
+    P = O.setup_params(O.RodParams(), "youngs")
+    mlp = {k: d[f"{tag}_{k}"] for k in ("W1", "b1", "W2", "b2")}
+    ctl, Cw = d[tag + "_ctl"], d[tag + "_Cw"]
+    got = O.rollout_newton(P, ctl, mlp, rows=25, tol=1e-13)
+    np.testing.assert_allclose(got, d[tag + "_traj"], rtol=0, atol=1e-10)
+
+    def loss(m, c=ctl):
+        return float(np.sum(Cw * O.rollout_newton(P, c, m, rows=25, tol=1e-13)))
+    e = 1e-6
+    for name, idx in [("W2", (20, 3)), ("b1", (5,))]:
+        mp = {k: v.copy() for k, v in mlp.items()}
+        mm = {k: v.copy() for k, v in mlp.items()}
+        mp[name][idx] += e
+        mm[name][idx] -= e
+        fd = (loss(mp) - loss(mm)) / (2 * e)
+        an = d[f"{tag}_g{name}"][idx]
+        assert abs(fd - an) < 2e-6 * max(1.0, abs(an)), (name, fd, an)
+    cp, cm = ctl.copy(), ctl.copy()
+    cp[0, 1, 2] += e
+    cm[0, 1, 2] -= e
+    fd = (loss(mlp, cp) - loss(mlp, cm)) / (2 * e)
+    assert abs(fd - d[tag + "_gctl"][0, 1, 2]) < 2e-6 * max(1.0, abs(fd))
+
+
+# ---- evaluation metrics --------------------------------------------------------------------------------------------------
+def test_eval_metric_oracle_pinned_to_scipy_and_to_the_vectorised_dtw(golden):
+    """The 'PQ MSE' column of physics_multitrain.py:213-222 is defined through scipy's Rotation.as_euler('zyx'): the closed
+    form of the oracle is pinned to scipy itself on random quaternions and on the reference's golden rollouts; the
+    cell-by-cell DTW agrees bit for bit with the anti-diagonal host version the drivers used so far."""
+    from scipy.spatial.transform import Rotation
+    import sys as _s, os as _o
+    _s.path.insert(0, _o.path.join(_o.path.dirname(_o.path.dirname(_o.path.abspath(__file__))), "knode-cosserat_b200"))
+    rng = np.random.default_rng(3)
+    q = rng.standard_normal((500, 4))
+    want = Rotation.from_quat(q[:, [1, 2, 3, 0]]).as_euler('zyx')
+    np.testing.assert_allclose(O.euler_zyx(q), want, rtol=0, atol=1e-12)
+    d = golden["rollouts"]
+    a, b = d["setup_sine_traj"][:60, :25], d["setup_random_traj"][:60, :25]
+    se_pos = (a[:, :3] - b[:, :3]).reshape((-1, 3)) ** 2
+    e1 = Rotation.from_quat(a[:, 3:7].transpose((0, 2, 1)).reshape((-1, 4))[:, [1, 2, 3, 0]]).as_euler('zyx')
+    e2 = Rotation.from_quat(b[:, 3:7].transpose((0, 2, 1)).reshape((-1, 4))[:, [1, 2, 3, 0]]).as_euler('zyx')
+    ref_mse = np.mean(np.concatenate([(e1 - e2) ** 2, se_pos])) * 1000
+    assert abs(O.pos_euler_mse(a, b) - ref_mse) < 1e-12 * ref_mse
+    from _train import dtw_l1 as dtw_vec
+    assert O.dtw_l1(a[:, :3, 9], b[:40, :3, 9]) == dtw_vec(a[:, :3, 9], b[:40, :3, 9])
+    assert O.dtw_l1(a[:, :3, 9], a[:, :3, 9]) == 0.0
