@@ -146,6 +146,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true")
+    ap.add_argument("--config", default="c2", choices=["c2", "c5"],
+                    help="c2 (default): BASELINE configs[1], the headline; c5: configs[4], 8192 rods/GPU x 20 nodes x 500 time "
+                         "indices, class-default rod (train_segment.py's configuration), physics-only and KNODE")
     ap.add_argument("--cpu-sample", type=int, nargs=2, default=None, help=argparse.SUPPRESS)  # T_sample cores
     args = ap.parse_args()
     if args.cpu_sample is not None:  # child process of the cpu_baseline leg (keeps fork() away from the CUDA context)
@@ -209,6 +212,11 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    if args.config == "c5":
+        run_c5(args, rank, world, dev, barrier, max_over_ranks)
+        finish(world, None, args)
+        return
+
     # ---------------- workload ----------------
     robot = CosseratRod(use_fsolve=True)
     setup_robot(robot)
@@ -271,6 +279,70 @@ def main():
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = world * rns_per_step * args.steps / e2e_s
 
+    # ---------------- the same API under the REFERENCE's contract: float64 host list/array in -> fresh float64 [B,T,50,N] ----
+    e2e_ref = None
+    if not args.no_train:
+        ctl64 = ctl_host.astype(np.float64)
+        simulate(robot, ctl64)
+        barrier()
+        t0 = time.perf_counter()
+        n_rc = max(2, min(args.steps, 3))
+        for _ in range(n_rc):
+            out64 = simulate(robot, ctl64)
+        barrier()
+        rc_s = max_over_ranks(time.perf_counter() - t0) / n_rc
+        e2e_ref = {"value": world * rns_per_step / rc_s, "unit": "rod-node-steps/s", "ms_per_step": rc_s * 1e3,
+                   "api": "knode.simulate(robot, ctl[B,T,4] float64) -> fresh float64 ndarray [B,T,50,N] (the reference's own "
+                          "contract, knode.py:55-102: fp64 arithmetic, rows 25:50 = yh, zh, pageable output)",
+                   "h2d_bytes_per_step": int(ctl64.nbytes), "d2h_bytes_per_step": int(out64.nbytes), "dtype": "f64"}
+        del out64
+
+    # ---------------- fp64 rollout (the reference's only rollout arithmetic is fp64: knode.py:55-102, cosserat_ode.py) ------
+    f64 = None
+    if not args.no_train:
+        plan64 = _ops.RolloutPlan(P, None, B, T, torch.float64, dev, rows=25)
+        ctl64_dev = ctl.double()
+        for _ in range(2):
+            plan64.run(ctl64_dev)
+        barrier()
+        ms64 = []
+        for _ in range(max(3, min(args.steps, 5))):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            plan64.run(ctl64_dev)
+            e1.record()
+            e1.synchronize()
+            ms64.append(e0.elapsed_time(e1))
+        ms64_med = max_over_ranks(float(np.median(ms64)))
+        fp64_peak = _ops.fma_peak(torch.float64, 20000, dev)
+        f64 = {"metric": "rod-node-steps/sec, fp64", "value": world * rns_per_step / (ms64_med * 1e-3), "unit": "rod-node-steps/s",
+               "ms_per_step": ms64_med, "dtype": "f64", "all_converged": bool(int(plan64.iters.min()) >= 0),
+               "marches_per_step_mean": float(plan64.iters[:, 1:].abs().float().mean().item()), "tol": 1e-11,
+               "roofline": {"bound": "fp64", "kernel": "kc_rollout_wide_kernel<double> (8 lanes per rod, Newton) + layout transpose",
+                            "achieved": rns_per_step * FLOP_PER_RNS / (ms64_med * 1e-3) / 1e12, "peak": fp64_peak / 1e12,
+                            "unit": "TFLOP/s", "frac": rns_per_step * FLOP_PER_RNS / (ms64_med * 1e-3) / fp64_peak,
+                            "peak_source": "kc_fma_peak(fp64) micro-benchmark measured live in this run",
+                            "normalisation": "6.06 kFLOP per rod-node-step (as the fp32 line)"}}
+        del plan64, ctl64_dev
+
+    # ---------------- C1 (BASELINE configs[0]): ONE class-default rod, 200 steps, through knode.simulate itself ------------
+    c1 = None
+    if not args.no_train and rank == 0:
+        from physics_controls import calc_controls
+        r1 = CosseratRod(use_fsolve=True)                      # class-default parameters, no setup_robot
+        ctl1 = np.array(calc_controls('sine', 1.0, r1.del_t, 200))
+        simulate(r1, ctl1)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            tr1 = simulate(r1, ctl1)
+        c1_s = (time.perf_counter() - t0) / 5
+        c1 = {"metric": "rod-node-steps/sec, single rod", "value": 199 * N_NODES / c1_s, "unit": "rod-node-steps/s",
+              "ms_per_call": c1_s * 1e3, "dtype": "f64", "tip_xyz_index_29": [float(v) for v in tr1[29, :3, -1]],
+              "api": "knode.simulate(CosseratRod(use_fsolve=True), calc_controls('sine', 1.0, 0.005, 200)) -> float64 [200,50,10]; "
+                     "one rod is one dependent chain of 199 shooting solves: latency, not throughput",
+              "cpu_reference_published": "361 rod-node-steps/s (the reference itself, one core, SURVEY 6)"}
+
     # ---------------- KNODE training step (C3/C4): teacher-forced fwd + loss + bwd + allreduce + Adam + clamp -----------
     train = None
     if not args.no_train:
@@ -282,21 +354,26 @@ def main():
         trainer = TeacherForcedTrainer(trobot, plan.traj[:TRAIN_B, :TRAIN_T].contiguous(),
                                        ctl[:TRAIN_B, :TRAIN_T].contiguous(), TRAIN_KEYS, lr=1e-2)
 
-        def train_step():
+        def train_step(sync):
             # kc_train_step -> all-reduce of [gradients | loss] -> kc_adam_clamp_multi; one CUDA-graph launch per step
-            # from the third call on; no host read of the loss inside the timed region
-            trainer.fused_step(train=True, sync=False)
+            # from the third call on.  sync=True is the epoch of physics_train.py (:266-297): the loss is read back and
+            # ReduceLROnPlateau steps on it, every epoch; sync=False leaves the loss on the device (no scheduler).
+            trainer.fused_step(train=True, sync=sync)
 
-        for _ in range(args.warmup):
-            train_step()
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(args.steps):
-            train_step()
-        e1.record()
-        barrier()
-        tms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+        def time_train(sync):
+            for _ in range(args.warmup):
+                train_step(sync)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(args.steps):
+                train_step(sync)
+            e1.record()
+            barrier()
+            return max_over_ranks(e0.elapsed_time(e1)) / args.steps
+
+        tms_nosync = time_train(False)
+        tms = time_train(True)
         q = TRAIN_B * (TRAIN_T - 1) * len(TRAIN_KEYS)
         identical = None
         if world > 1:   # C4: every rank applied the same all-reduced gradient -> weights bitwise identical on all ranks
@@ -317,6 +394,9 @@ def main():
                                       "fp32 accuracy, so the executed tensor FLOP/s are 3x this",
                               "frac_of_fp32_fma_peak": None, "frac_of_bf16_tensor_peak_executed": None},
                  "loss": float(trainer.plan.flat[-1].item()), "kernels_per_step": 4 + 1 + 1,
+                 "scheduler": "ReduceLROnPlateau stepped on the loss read back every step (physics_train.py:206,297)",
+                 "train_nosync": {"value": 1e3 / tms_nosync, "unit": "steps/s", "ms_per_step": tms_nosync,
+                                  "note": "same step without the host read of the loss (no scheduler step)"},
                  "weights_bitwise_identical_across_ranks": identical}
 
     # ---------------- the same training step, weak scaling: 1024 trajectories PER GPU (global batch grows with N) -------
@@ -572,15 +652,22 @@ def main():
                          "6.5 MB tensions read; the tail of the trajectory is still in L2 when the kernel ends)",
                          "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak}},
             "cpu_baseline": cpu, "train": train, "train_weak": train_weak, "knode_rollout": knode, "train_bptt": bptt,
+            "rollout_f64": f64, "c1_single_rod": c1, "e2e_reference_contract": e2e_ref,
             "train_bptt_weak": bptt_weak, "estimate_state": estimate}
         print(json.dumps(out))
     sys.stdout.flush()
+    finish(world, None if args.no_train else trainer, args)
+
+
+def finish(world, trainer, args):
+    import torch
+    import torch.distributed as dist
     if world > 1:
         # a CUDA graph that captured NCCL kernels must be released before its communicator is torn down (otherwise
         # destroy_process_group can block forever); a watchdog turns any remaining teardown hang into a clean exit
         import gc
         import threading
-        if not args.no_train:
+        if trainer is not None:
             trainer.close()
         gc.collect()
         torch.cuda.synchronize()
@@ -590,6 +677,105 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
         wd.cancel()
+
+
+def run_c5(args, rank, world, dev, barrier, max_over_ranks):
+    """BASELINE configs[4]: 65 536 rods x 20 nodes x 500 time indices over 8 GPUs = 8 192 rods per GPU, the
+    configuration of train_segment.py (class-default physical parameters: it never calls setup_robot; dt = 0.005; H = 512).
+    Physics-only rollout (the contract line's value) and the KNODE rollout (MLP in the march on tcgen05)."""
+    import torch
+    import _kc
+    import _ops
+    from cosserat_ode import CosseratRod
+    from cosserat_ode_torch import CosseratRodTorch
+    from physics_controls import synthetic_tensions
+    B, T, N = 8192, 500, 20
+    robot = CosseratRod(use_fsolve=True)
+    robot.N = N
+    robot.compute_intermediate_terms()
+    P = _kc.rod_params(robot)
+    ctl = torch.tensor(synthetic_tensions(B, T, robot.del_t, seed=rank, dtype=np.float32), device=dev)
+    flop_rns = E_REF * (N - 1) / N * F_ODE
+    sampler = ClockSampler(dev.index)
+    plan = _ops.RolloutPlan(P, None, B, T, torch.float32, dev, rows=25)
+    for _ in range(2):
+        plan.run(ctl)
+    barrier()
+    sampler.start()
+    steps = max(2, min(args.steps, 5))
+    ev = []
+    for _ in range(steps):     # 8.2 GB written per step: far beyond L2, no flush needed
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        plan.run(ctl)
+        e1.record()
+        ev.append((e0, e1))
+    barrier()
+    sampler.stop_flag = True
+    ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in ev)) / steps
+    its = plan.iters
+    ok = bool(int(its.min()) >= 0)
+    marches = float(its[:, 1:].abs().float().mean().item())
+    rns = B * N * (T - 1)
+    fp32_peak = _ops.fma_peak(torch.float32, 40000, dev)
+    del plan
+    torch.cuda.empty_cache()
+    # KNODE on: H = 512 (train_segment.py:13), a trained-size residual
+    torch.manual_seed(1)
+    kr = CosseratRodTorch(str(dev), 512)
+    kr.N = N
+    kr.compute_intermediate_terms()
+    with torch.no_grad():
+        kr.nn_models[2].weight.mul_(0.02)
+        kr.nn_models[2].bias.mul_(0.02)
+    sd = kr.nn_models.state_dict()
+    mlp = _ops.Mlp(sd["0.weight"], sd["0.bias"], sd["2.weight"], sd["2.bias"])
+    kplan = _ops.RolloutPlan(kr._params(), mlp, B, T, torch.float32, dev, rows=25)
+    kplan.run(ctl)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    kplan.run(ctl)
+    e1.record()
+    barrier()
+    kms = max_over_ranks(e0.elapsed_time(e1))
+    kits = kplan.iters
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    bf16_peak = float(peaks.get("bf16_tflops", 1590.0)) * 1e12
+    a = kits[:, 1:].abs().float()
+    joint = float(a.view(-1, 16, a.shape[1]).amax(1).clamp(min=2).sum().item())
+    k_exec = joint * (N - 1) * 2 * 128 * 32 * 512 * 2 * 3.0
+    if rank == 0:
+        print(json.dumps({
+            "metric": "rod-node-steps/sec", "value": world * rns / (ms * 1e-3), "unit": "rod-node-steps/s", "n_gpus": world,
+            "steps": steps, "warmup": 2, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C5 large sweep (BASELINE configs[4]): 8192 rods/GPU x 20 nodes x 500 time indices (65 536 "
+                                   "rods on 8 GPUs), class-default rod of train_segment.py, physics-only, half sine / half "
+                                   "random tensions", "rods_per_gpu": B, "nodes": N, "time_indices": T,
+                       "l2": "8.2 GB of trajectory written per step (>> 126 MB L2)",
+                       "parallelism": f"rods sharded over {world} rank(s), no collective",
+                       "solver": {"marches_per_step_mean": marches, "all_converged": ok}},
+            "clocks": sampler.summary(), "gpu_launches": 2 * steps,
+            "roofline": {"bound": "fp32", "kernel": "kc_rollout_kernel<float,diag,physics> (one rod per lane, Broyden) + layout "
+                         "transpose", "achieved": rns * flop_rns / (ms * 1e-3) / 1e12, "peak": fp32_peak / 1e12,
+                         "unit": "TFLOP/s", "frac": rns * flop_rns / (ms * 1e-3) / fp32_peak,
+                         "peak_source": "kc_fma_peak micro-benchmark measured live in this run",
+                         "normalisation": "6.40 kFLOP per rod-node-step = 15 nominal evaluations x 19/20 x 449 FLOP (SURVEY 8d)",
+                         "traffic": None},
+            "e2e": None, "cpu_baseline": None,
+            "knode": {"metric": "KNODE rod-node-steps/sec", "value": world * rns / (kms * 1e-3), "unit": "rod-node-steps/s",
+                      "ms_per_rollout": kms, "hidden": 512, "all_converged": bool(int(kits.min()) >= 0),
+                      "marches_per_step_mean": float(a.mean().item()),
+                      "roofline": {"bound": "tensor", "kernel": "kc_knode_tc_fwd_kernel", "achieved": k_exec / (kms * 1e-3) / 1e12,
+                                   "peak": bf16_peak / 1e12, "unit": "TFLOP/s", "frac": k_exec / (kms * 1e-3) / bf16_peak,
+                                   "what": "executed tensor FLOP/s (8 rows per rod, 3 bf16 hi/lo passes)",
+                                   "useful_tflops": rns * E_REF * (N - 1) / N * (F_ODE + 106 * 512) / (kms * 1e-3) / 1e12}}}))
+    sys.stdout.flush()
 
 
 if __name__ == "__main__":

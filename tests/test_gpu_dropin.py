@@ -254,7 +254,7 @@ def test_physics_multitrain_script_trains_and_writes_evals(tmp_path, monkeypatch
     # the printed table VALUES: every cell recomputed from the saved rollouts with the oracle metrics (exact L1 DTW;
     # pos + Euler MSE pinned to scipy's Rotation.as_euler('zyx'), tests/test_oracle_golden.py) — physics_multitrain.py:211-222
     from oracle import rod_oracle as O
-    rows = {l.split(';')[0].strip(): l.split(';')[1:] for l in out.splitlines() if ';' in l and not l.startswith(' ')}
+    rows = {l.split(';')[0].strip(): l.split(';')[1:] for l in out.splitlines() if ';' in l and not l.startswith((' ', '['))}
     assert len(rows) == 12
     for name in ("baseline youngs", "sine sine 0.5 1.0 nsw 0", "sine sine random 0.5 1.0 0.0 short 0"):
         for k, ev in enumerate(("sine_1.5", "step_1.5")):
