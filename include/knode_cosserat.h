@@ -209,6 +209,23 @@ int kc_adam_clamp_multi(int dtype, int32_t n_tensors, const kc_adam_tensor *tens
                         const double *lr_dev, double beta1, double beta2, double eps, double weight_decay,
                         int32_t *ticket_dev, void *stream);
 
+/* The gradient all-reduce of the training step (an all-reduce(sum) of the flat [gW1|gb1|gW2|gb2|loss] buffer, the
+ * only collective of the path) fused with the optimiser, over NVLink peer memory instead of a collective library call:
+ * regions_host[world] = device-visible pointers to every rank's region of kc_peer_region_bytes() bytes of symmetric
+ * (peer-mapped) memory, zero-initialised once (torch.distributed._symmetric_memory in the Python host).
+ *   kc_peer_publish     copies flat[n_flat] into the own region and signals every peer;
+ *   kc_peer_gather_adam waits for all ranks' signals of this step, sums the ranks' copies in rank order (bitwise identical
+ *                       on every rank), stores the sums back into flat and applies kc_adam_clamp_multi's update; the
+ *                       tensors' gradients must be the consecutive leading views of `flat`; it advances *step_dev.
+ * Both take *step_dev (updates applied so far) as the step number of the exchange, so the pair can be replayed from a CUDA
+ * graph.  ticket_dev: two zero-initialised int32 (one per call).  world <= 8; world == 1 degenerates to Adam alone. */
+int64_t kc_peer_region_bytes(int dtype, int64_t n_flat);
+int kc_peer_publish(int dtype, int32_t world, int32_t rank, void *const *regions_host, int64_t n_flat, const void *flat,
+                    const int64_t *step_dev, int32_t *ticket_dev, void *stream);
+int kc_peer_gather_adam(int dtype, int32_t world, int32_t rank, void *const *regions_host, int64_t n_flat, void *flat,
+                        int32_t n_tensors, const kc_adam_tensor *tensors_host, int64_t *step_dev, const double *lr_dev,
+                        double beta1, double beta2, double eps, double weight_decay, int32_t *ticket_dev, void *stream);
+
 /* Evaluation metrics of the training drivers for E (prediction, reference) pairs of rollouts, on the device:
  * dtw[E] = exact dynamic-time-warping distance with the L1 point distance between pred[e][:, 0:3, node] (Ta points) and
  * ref[e][:, 0:3, node] (Tb points) — what fastdtw(trajectory[:, :3, 9], tip_pos)[0] approximates (physics_train.py:159,

@@ -491,6 +491,50 @@ class AdamClampMulti:
     def set_lr(self, lr):
         self.lr_dev.fill_(float(lr))
 
+    # -- gradient all-reduce fused with the update, over NVLink peer memory (kc_peer_publish / kc_peer_gather_adam) ------
+    def enable_peer_allreduce(self, flat, regions=None, rank=None, world=None):
+        """`flat` = the [gradients | loss] buffer whose leading views are this optimiser's gradients.  regions: list of
+        device pointers to every rank's symmetric region (tests); default: one torch.distributed._symmetric_memory
+        allocation, rendezvoused over the world group.  Returns False (and leaves the NCCL path in place) if symmetric memory
+        cannot be set up on this system."""
+        n = flat.numel()
+        nbytes = int(_kc.lib().kc_peer_region_bytes(_DT[self.dt], n))
+        if regions is None:
+            import torch.distributed as dist
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                self._sym = symm_mem.empty(nbytes, dtype=torch.uint8, device=self.dev)
+                self._sym.zero_()
+                self._sym_hdl = symm_mem.rendezvous(self._sym, dist.group.WORLD)
+                regions = [int(p) for p in self._sym_hdl.buffer_ptrs]
+                rank, world = dist.get_rank(), dist.get_world_size()
+                torch.cuda.synchronize(self.dev)
+                dist.barrier()            # every region is zeroed before anybody publishes
+            except Exception as e:        # no peer access / no symmetric-memory support: keep the collective-library path
+                self._peer_error = repr(e)
+                return False
+        if world > 8:
+            return False
+        self._peer_flat, self._peer_n = flat, n
+        self._peer_rank, self._peer_world = int(rank), int(world)
+        self._peer_regions = (C.c_void_p * world)(*[C.c_void_p(int(p)) for p in regions])
+        self._peer_tickets = torch.zeros(2, dtype=torch.int32, device=self.dev)
+        return True
+
+    def run_peer(self):
+        """publish -> gather + Adam + clamp (two launches; replaces all_reduce(flat) + run())."""
+        L = _kc.lib()
+        with torch.cuda.device(self.dev):
+            st = _stream(self.dev)
+            rc = L.kc_peer_publish(_DT[self.dt], self._peer_world, self._peer_rank, C.cast(self._peer_regions, C.c_void_p),
+                                   self._peer_n, _ptr(self._peer_flat), _ptr(self.step_dev), _ptr(self._peer_tickets), st)
+            _kc.check(rc, "kc_peer_publish")
+            rc = L.kc_peer_gather_adam(_DT[self.dt], self._peer_world, self._peer_rank, C.cast(self._peer_regions, C.c_void_p),
+                                       self._peer_n, _ptr(self._peer_flat), len(self.params), C.cast(self.arr, C.c_void_p),
+                                       _ptr(self.step_dev), _ptr(self.lr_dev), float(self.betas[0]), float(self.betas[1]),
+                                       float(self.eps), float(self.weight_decay), self._peer_tickets[1:].data_ptr(), st)
+            _kc.check(rc, "kc_peer_gather_adam")
+
     def run(self):
         with torch.cuda.device(self.dev):
             rc = _kc.lib().kc_adam_clamp_multi(_DT[self.dt], len(self.params), C.cast(self.arr, C.c_void_p),

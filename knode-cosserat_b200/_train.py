@@ -6,6 +6,8 @@ loss over all (trajectory, step, key node) samples, so here an epoch is: kc_trai
 reverse mode to the MLP weights) -> all-reduce of dW across ranks (only if torch.distributed is initialised) ->
 kc_adam_clamp per parameter tensor.  ReduceLROnPlateau and the bookkeeping stay on the host exactly as in the reference.
 """
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -84,9 +86,17 @@ class TeacherForcedTrainer:
         self._lr_on_device = self.sched.get_last_lr()[0]
         self.graph = None
         self._eager_fused_steps = 0
+        # the all-reduce fused with the update over NVLink peer memory (kc_peer_publish / kc_peer_gather_adam);
+        # KC_PEER_ALLREDUCE=0 keeps the NCCL all-reduce + kc_adam_clamp_multi
+        self.peer = False
+        if self.world > 1 and os.environ.get("KC_PEER_ALLREDUCE", "1") != "0":
+            self.peer = self.adam.enable_peer_allreduce(self.plan.flat)
 
     def _fused_body(self, train):
         self.plan.run()
+        if train and self.peer:
+            self.adam.run_peer()                     # publish -> wait for all ranks -> sum in rank order -> Adam + clamp
+            return
         if self.world > 1:
             dist.all_reduce(self.plan.flat)          # the only collective: gradients + loss, one launch
         if train:
@@ -215,6 +225,9 @@ class BpttTrainer:
         self._lr_on_device = lr
         self.step_no = 0
         self.loss_arr = []
+        self.peer = False
+        if self.world > 1 and os.environ.get("KC_PEER_ALLREDUCE", "1") != "0":
+            self.peer = self.adam.enable_peer_allreduce(self.plan.flat)
 
     def step(self, train=True, sync=True):
         self.plan.P = self.robot._params()
@@ -223,10 +236,13 @@ class BpttTrainer:
             self.adam.set_lr(lr)
             self._lr_on_device = lr
         self.plan.run()
-        if self.world > 1:
+        if train and self.peer:
+            self.adam.run_peer()
+        elif self.world > 1:
             dist.all_reduce(self.plan.flat)
-        if train:
+        if train and not self.peer:
             self.adam.run()
+        if train:
             self.step_no += 1
             for p, g in zip(self.params, self.plan.grads):
                 p.grad = g

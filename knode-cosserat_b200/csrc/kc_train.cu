@@ -644,4 +644,186 @@ extern "C" int kc_adam_clamp_multi(int dtype, int32_t n_tensors, const kc_adam_t
     return KC_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Gradient all-reduce + Adam as TWO kernels over NVLink peer memory (replaces kc_train_reduce's output -> ncclAllReduce ->
+// kc_adam_clamp_multi for the 110 KB [gradients | loss] buffer of the training step, SURVEY §8e: the only collective of the
+// path is latency bound).  Every rank owns a region of symmetric (peer-mapped) memory:
+//     float data[2][n_pad]   two slots, used alternately by consecutive optimiser steps
+//     uint32 flags[8]        flags[p] = number of the last step whose data rank p has published HERE
+//   kc_peer_publish     : copy the local flat buffer into the own region's slot (step & 1), fence, then store the step
+//                         number into flags[rank] of EVERY rank's region (st.release.sys over NVLink);
+//   kc_peer_gather_adam : wait until all flags of the own region have reached this step (ld.acquire.sys), then every
+//                         thread sums its element over the ranks' slots IN RANK ORDER — all ranks add the same numbers in
+//                         the same order, so the result (and therefore the weights) are bitwise identical everywhere —
+//                         writes the sum back to the local flat buffer and applies Adam + clamp to its parameter.
+// A slot is rewritten two steps later; by then every peer has passed the gather of the step in between, which waited for
+// this rank's publish of that step, i.e. for the end of this rank's previous gather: no reader can still be in the slot.
+struct PeerRegions { void* r[8]; int32_t world, rank; };
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+static inline int64_t peer_npad(int64_t n) { return (n + 31) / 32 * 32; }
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+kc_peer_publish_kernel(const __grid_constant__ PeerRegions R, int64_t n, int64_t n_pad, const T* __restrict__ flat,
+                       const int64_t* __restrict__ step_dev, int32_t* ticket) {
+    const uint32_t e = (uint32_t)(*step_dev + 1);
+    T* slot = reinterpret_cast<T*>(R.r[R.rank]) + (size_t)(e & 1u) * n_pad;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) slot[i] = flat[i];
+    __threadfence_system();
+    __syncthreads();
+    __shared__ int last;
+    if (threadIdx.x == 0) last = atomicAdd(ticket, 1) == (int)gridDim.x - 1;
+    __syncthreads();
+    if (last) {
+        if (threadIdx.x == 0) *ticket = 0;
+        __threadfence_system();
+        if ((int)threadIdx.x < R.world) {
+            uint32_t* flags = reinterpret_cast<uint32_t*>(reinterpret_cast<T*>(R.r[threadIdx.x]) + 2 * n_pad);
+            st_release_sys(flags + R.rank, e);
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+kc_peer_gather_adam_kernel(const __grid_constant__ PeerRegions R, const __grid_constant__ AdamTensors A, int64_t n, int64_t n_pad,
+                           T* __restrict__ flat, int64_t* step_dev, const double* lr_dev, double b1d, double b2d, T eps, T wd,
+                           int32_t* ticket, int adam_blocks) {
+    __shared__ T s_lr1, s_bc2s;
+    const uint32_t e = (uint32_t)(*step_dev + 1);
+    if ((int)threadIdx.x < R.world) {
+        const uint32_t* flags = reinterpret_cast<const uint32_t*>(reinterpret_cast<const T*>(R.r[R.rank]) + 2 * n_pad);
+        while ((int32_t)(ld_acquire_sys(flags + threadIdx.x) - e) < 0) __nanosleep(20);
+    }
+    if (threadIdx.x == 32) {
+        const double step = (double)(*step_dev + 1);
+        s_lr1 = (T)(*lr_dev / (1.0 - pow(b1d, step)));
+        s_bc2s = (T)sqrt(1.0 - pow(b2d, step));
+    }
+    __syncthreads();
+    const size_t so = (size_t)(e & 1u) * n_pad;
+    auto gather = [&](int64_t fi) {
+        T s = T(0);
+        for (int p = 0; p < R.world; ++p) s += *reinterpret_cast<const volatile T*>(reinterpret_cast<const T*>(R.r[p]) + so + fi);
+        flat[fi] = s;
+        return s;
+    };
+    if ((int)blockIdx.x < adam_blocks) {
+        int k = 0;
+#pragma unroll
+        for (int i = 1; i < 8; ++i) if (i < A.count && (int)blockIdx.x >= A.first_block[i]) k = i;
+        const int64_t i = (int64_t)((int)blockIdx.x - A.first_block[k]) * 256 + threadIdx.x;
+        if (i < A.n[k]) {
+            T* p = (T*)A.p[k]; T* m = (T*)A.m[k]; T* v = (T*)A.v[k];
+            const int64_t fi = (const T*)A.g[k] - flat + i;
+            const T b1 = (T)b1d, b2 = (T)b2d;
+            const T gi = gather(fi) + wd * p[i];
+            const T mi = b1 * m[i] + (T(1) - b1) * gi;
+            const T vi = b2 * v[i] + (T(1) - b2) * gi * gi;
+            m[i] = mi;
+            v[i] = vi;
+            const T denom = sqrt(vi) / s_bc2s + eps;
+            T pi = p[i] - s_lr1 * (mi / denom);
+            if (A.clamp[k] && pi < T(0)) pi = T(0);
+            p[i] = pi;
+        }
+    } else {   // elements of the flat buffer that belong to no parameter tensor (the loss): sum only
+        int64_t covered = 0;
+        for (int i = 0; i < A.count; ++i) covered += A.n[i];
+        const int64_t fi = covered + (int64_t)((int)blockIdx.x - adam_blocks) * 256 + threadIdx.x;
+        if (fi < n) gather(fi);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(ticket, 1) == (int)gridDim.x - 1) {
+            *step_dev += 1;
+            *ticket = 0;
+        }
+    }
+}
+
+extern "C" int64_t kc_peer_region_bytes(int dtype, int64_t n_flat) {
+    if ((dtype != KC_F32 && dtype != KC_F64) || n_flat < 1) return KC_EINVAL;
+    return 2 * peer_npad(n_flat) * (dtype == KC_F32 ? 4 : 8) + 128;
+}
+
+static int peer_regions(int32_t world, int32_t rank, void* const* regions_host, PeerRegions& R) {
+    KC_CHECK_ARG(world >= 1 && world <= 8 && rank >= 0 && rank < world && regions_host, "need 1 <= world <= 8, 0 <= rank < world");
+    for (int i = 0; i < world; ++i) {
+        KC_CHECK_ARG(regions_host[i], "peer region %d is NULL", i);
+        R.r[i] = regions_host[i];
+    }
+    R.world = world; R.rank = rank;
+    return KC_OK;
+}
+
+extern "C" int kc_peer_publish(int dtype, int32_t world, int32_t rank, void* const* regions_host, int64_t n_flat,
+                               const void* flat, const int64_t* step_dev, int32_t* ticket_dev, void* stream) {
+    KC_CHECK_ARG(dtype == KC_F32 || dtype == KC_F64, "dtype must be KC_F32 or KC_F64");
+    KC_CHECK_ARG(n_flat >= 1 && flat && step_dev && ticket_dev, "NULL pointer or empty buffer");
+    PeerRegions R{};
+    int rc = peer_regions(world, rank, regions_host, R);
+    if (rc) return rc;
+    const int blocks = (int)((n_flat + 1023) / 1024);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == KC_F32)
+        kc_peer_publish_kernel<float><<<blocks, 256, 0, st>>>(R, n_flat, peer_npad(n_flat), (const float*)flat, step_dev, ticket_dev);
+    else
+        kc_peer_publish_kernel<double><<<blocks, 256, 0, st>>>(R, n_flat, peer_npad(n_flat), (const double*)flat, step_dev, ticket_dev);
+    KC_CHECK_LAUNCH("kc_peer_publish_kernel");
+    return KC_OK;
+}
+
+extern "C" int kc_peer_gather_adam(int dtype, int32_t world, int32_t rank, void* const* regions_host, int64_t n_flat, void* flat,
+                                   int32_t n_tensors, const kc_adam_tensor* t, int64_t* step_dev, const double* lr_dev,
+                                   double beta1, double beta2, double eps, double weight_decay, int32_t* ticket_dev,
+                                   void* stream) {
+    KC_CHECK_ARG(dtype == KC_F32 || dtype == KC_F64, "dtype must be KC_F32 or KC_F64");
+    KC_CHECK_ARG(n_tensors >= 1 && n_tensors <= 8 && t, "1..8 tensors");
+    KC_CHECK_ARG(n_flat >= 1 && flat && step_dev && lr_dev && ticket_dev, "NULL pointer or empty buffer");
+    PeerRegions R{};
+    int rc = peer_regions(world, rank, regions_host, R);
+    if (rc) return rc;
+    const size_t sz = dtype == KC_F32 ? 4 : 8;
+    AdamTensors A{};
+    A.count = n_tensors;
+    int blocks = 0;
+    int64_t covered = 0;
+    for (int i = 0; i < n_tensors; ++i) {
+        KC_CHECK_ARG(t[i].n >= 0 && (t[i].n == 0 || (t[i].param && t[i].grad && t[i].exp_avg && t[i].exp_avg_sq)),
+                     "tensor %d: NULL data pointer or negative size", i);
+        // the gradients must be the consecutive leading views of the flat buffer ([g0 | g1 | ... | rest])
+        KC_CHECK_ARG((const char*)t[i].grad == (const char*)flat + (size_t)covered * sz,
+                     "tensor %d: its gradient must be the view of the flat buffer that follows the previous tensor's", i);
+        A.p[i] = t[i].param; A.g[i] = t[i].grad; A.m[i] = t[i].exp_avg; A.v[i] = t[i].exp_avg_sq;
+        A.n[i] = t[i].n; A.clamp[i] = t[i].clamp_min_zero;
+        A.first_block[i] = blocks;
+        blocks += (int)((t[i].n + 255) / 256);
+        covered += t[i].n;
+    }
+    A.first_block[n_tensors] = blocks;
+    KC_CHECK_ARG(covered <= n_flat, "the tensors are larger than the flat buffer");
+    const int adam_blocks = blocks;
+    blocks += (int)((n_flat - covered + 255) / 256);
+    if (blocks == 0) blocks = 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == KC_F32)
+        kc_peer_gather_adam_kernel<float><<<blocks, 256, 0, st>>>(R, A, n_flat, peer_npad(n_flat), (float*)flat, step_dev, lr_dev,
+                                                                 beta1, beta2, (float)eps, (float)weight_decay, ticket_dev, adam_blocks);
+    else
+        kc_peer_gather_adam_kernel<double><<<blocks, 256, 0, st>>>(R, A, n_flat, peer_npad(n_flat), (double*)flat, step_dev, lr_dev,
+                                                                  beta1, beta2, eps, weight_decay, ticket_dev, adam_blocks);
+    KC_CHECK_LAUNCH("kc_peer_gather_adam_kernel");
+    return KC_OK;
+}
+
 #include "kc_ode_bwd.inl"

@@ -148,7 +148,7 @@ kc_train_tc_kernel(int hidden, int nch, const float* __restrict__ W1hl, const un
     float* redb = reinterpret_cast<float*>(sm + tc::OFF_MISC + 128);     // [4][25]
     float* sO = reinterpret_cast<float*>(sm + tc::OFF_MISC + 640);       // unused now (kept for layout stability)
     (void)sO;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;   // (warp: provably uniform)
     const int row = tid & 127, half = tid >> 7;
     const uint32_t laneblk = (uint32_t)((warp & 3) * 32) << 16;
     if (warp == 0) umma::tmem_alloc(tmem_slot, 512);
@@ -164,7 +164,9 @@ kc_train_tc_kernel(int hidden, int nch, const float* __restrict__ W1hl, const un
     umma::fence_before();
     __syncthreads();
     umma::fence_after();
-    const uint32_t tbase = *tmem_slot;
+    // MMAs are issued by ALL lanes of warp 0 (descriptors in uniform registers, the instruction predicated on elect.sync):
+    // issuing from the single-thread region `if (tid == 0)` made the compiler wrap every tcgen05.mma in an R2UR / ELECT loop
+    const uint32_t tbase = __shfl_sync(0xffffffffu, *tmem_slot, 0);
     uint32_t phZ = 0, phG = 0, phO = 0, phW = 0, phL = 0;
     const uint32_t idescZ = umma::make_idesc_tf32(128, 128);
     const uint32_t idescG = umma::make_idesc_bf16(128, 32, 1, 1);   // gradient GEMMs: both operands MN-major
@@ -199,7 +201,7 @@ kc_train_tc_kernel(int hidden, int nch, const float* __restrict__ W1hl, const un
             const uint32_t a = (p == 1) ? aXl : aXh, b = (p == 2) ? aW1l : aW1h;
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
-                umma::mma_tf32(tbase + tc::COL_Z, umma::make_desc(a + kk * 256, 128, 1024), umma::make_desc(b + kk * 256, 128, 1024), idescZ, acc);
+                umma::mma_tf32_w(tbase + tc::COL_Z, umma::make_desc(a + kk * 256, 128, 1024), umma::make_desc(b + kk * 256, 128, 1024), idescZ, acc);
                 acc = 1;
             }
         }
@@ -212,11 +214,11 @@ kc_train_tc_kernel(int hidden, int nch, const float* __restrict__ W1hl, const un
         for (int p = 0; p < 3; ++p) {
             const uint32_t a = (p == 1) ? aAl : aAh, b = (p == 2) ? aWB + 8192 : aWB;
             for (int kk = 0; kk < 8; ++kk) {
-                umma::mma_bf16(tbase + tc::COL_O, umma::make_desc(a + kk * 4096, 2048, 128), umma::make_desc(b + kk * 256, 128, 2048), idescO, acc);
+                umma::mma_bf16_w(tbase + tc::COL_O, umma::make_desc(a + kk * 4096, 2048, 128), umma::make_desc(b + kk * 256, 128, 2048), idescO, acc);
                 acc = 1;
             }
         }
-        umma::commit(barO);
+        umma::commit_w(barO);
     };
     // dA[128 samples x 128 units] = dO[samples x 32 outs] W2c: A = the dO tile viewed K-major (LBO 2048, SBO 128),
     // B = W2^T image [128 units x 32 outs] K-major (LBO 128, SBO 512); K = 32 = 2 x K16
@@ -227,7 +229,7 @@ kc_train_tc_kernel(int hidden, int nch, const float* __restrict__ W1hl, const un
             const uint32_t a = (p == 1) ? aDOl : aDOh, b = (p == 2) ? aWB + 8192 : aWB;
 #pragma unroll
             for (int kk = 0; kk < 2; ++kk) {
-                umma::mma_bf16(tbase + tc::COL_O, umma::make_desc(a + kk * 4096, 2048, 128), umma::make_desc(b + kk * 256, 128, 512), idescD, acc);
+                umma::mma_bf16_w(tbase + tc::COL_O, umma::make_desc(a + kk * 4096, 2048, 128), umma::make_desc(b + kk * 256, 128, 512), idescD, acc);
                 acc = 1;
             }
         }
@@ -238,26 +240,26 @@ kc_train_tc_kernel(int hidden, int nch, const float* __restrict__ W1hl, const un
         const uint32_t d1 = tbase + tc::COL_GW1 + 32 * c, d2 = tbase + tc::COL_GW2 + 32 * c;
         uint32_t acc = first_tile ? 0u : 1u;
         for (int kk = 0; kk < 8; ++kk) {   // dZ lo * X hi
-            umma::mma_bf16(d1, umma::make_desc(aDZl + kk * 256, 128, 2048), umma::make_desc(aXth + kk * 256, 128, 2048), idescG, acc);
+            umma::mma_bf16_w(d1, umma::make_desc(aDZl + kk * 256, 128, 2048), umma::make_desc(aXth + kk * 256, 128, 2048), idescG, acc);
             acc = 1;
         }
-        umma::commit(barL);
+        umma::commit_w(barL);
 #pragma unroll
         for (int p = 0; p < 2; ++p) {      // dZ hi * X hi, dZ hi * X lo
             const uint32_t b = p == 0 ? aXth : aXtl;
             for (int kk = 0; kk < 8; ++kk)
-                umma::mma_bf16(d1, umma::make_desc(aDZh + kk * 256, 128, 2048), umma::make_desc(b + kk * 256, 128, 2048), idescG, 1u);
+                umma::mma_bf16_w(d1, umma::make_desc(aDZh + kk * 256, 128, 2048), umma::make_desc(b + kk * 256, 128, 2048), idescG, 1u);
         }
         acc = first_tile ? 0u : 1u;
 #pragma unroll
         for (int p = 0; p < 3; ++p) {
             const uint32_t a = (p == 1) ? aAl : aAh, b = (p == 2) ? aDOl : aDOh;
             for (int kk = 0; kk < 8; ++kk) {
-                umma::mma_bf16(d2, umma::make_desc(a + kk * 256, 128, 2048), umma::make_desc(b + kk * 256, 128, 2048), idescG, acc);
+                umma::mma_bf16_w(d2, umma::make_desc(a + kk * 256, 128, 2048), umma::make_desc(b + kk * 256, 128, 2048), idescG, acc);
                 acc = 1;
             }
         }
-        umma::commit(barG);
+        umma::commit_w(barG);
     };
 
     // MODE 3: gX[128 samples x 32 inputs] += dZ[samples x 128 units] W1c: A = the dZ tile viewed K-major (as the activation
@@ -265,17 +267,17 @@ kc_train_tc_kernel(int hidden, int nch, const float* __restrict__ W1hl, const un
     auto issue_gemm4 = [&](bool first_chunk, uint32_t aW1T) {
         uint32_t acc = first_chunk ? 0u : 1u;
         for (int kk = 0; kk < 8; ++kk) {
-            umma::mma_bf16(tbase + tc::COL_GW1, umma::make_desc(aDZl + kk * 4096, 2048, 128), umma::make_desc(aW1T + kk * 256, 128, 2048), idescO, acc);
+            umma::mma_bf16_w(tbase + tc::COL_GW1, umma::make_desc(aDZl + kk * 4096, 2048, 128), umma::make_desc(aW1T + kk * 256, 128, 2048), idescO, acc);
             acc = 1;
         }
-        umma::commit(barL);
+        umma::commit_w(barL);
 #pragma unroll
         for (int p = 0; p < 2; ++p) {
             const uint32_t b = p == 0 ? aW1T : aW1T + 8192;
             for (int kk = 0; kk < 8; ++kk)
-                umma::mma_bf16(tbase + tc::COL_GW1, umma::make_desc(aDZh + kk * 4096, 2048, 128), umma::make_desc(b + kk * 256, 128, 2048), idescO, 1u);
+                umma::mma_bf16_w(tbase + tc::COL_GW1, umma::make_desc(aDZh + kk * 4096, 2048, 128), umma::make_desc(b + kk * 256, 128, 2048), idescO, 1u);
         }
-        umma::commit(barG);
+        umma::commit_w(barG);
     };
     float gb2acc[25];
 #pragma unroll
@@ -336,7 +338,7 @@ kc_train_tc_kernel(int hidden, int nch, const float* __restrict__ W1hl, const un
         for (int c = 0; c < nch; ++c, ++gs) {
             const int stage = gs;
             umma::mbar_wait(barW, phW); phW ^= 1;                     // W1(c), W2 fwd image(c) have landed
-            if (tid == 0) { umma::fence_after(); issue_gemm1(); umma::commit(barZ); }
+            if (warp == 0) { umma::fence_after(); issue_gemm1(); umma::commit_w(barZ); }
             if (c > 0) { umma::mbar_wait(barO, phO); phO ^= 1; }      // chunk c-1's O GEMM done: A tile and its W2 buffer free
             umma::mbar_wait(barZ, phZ); phZ ^= 1;
             umma::fence_after();
@@ -366,7 +368,7 @@ kc_train_tc_kernel(int hidden, int nch, const float* __restrict__ W1hl, const un
             umma::fence_async_smem();
             umma::fence_before();
             __syncthreads();
-            if (tid == 0) { umma::fence_after(); issue_gemm2(c == 0, (stage & 1) ? aWB1 : aWB0); }
+            if (warp == 0) { umma::fence_after(); issue_gemm2(c == 0, (stage & 1) ? aWB1 : aWB0); }
         }
         umma::mbar_wait(barO, phO); phO ^= 1;
         umma::fence_after();
@@ -462,7 +464,7 @@ kc_train_tc_kernel(int hidden, int nch, const float* __restrict__ W1hl, const un
             const int stage = gs;
             const uint32_t aWB = (stage & 1) ? aWB1 : aWB0;
             umma::mbar_wait(barW, phW); phW ^= 1;                     // W1(c), W2 bwd image(c) have landed
-            if (tid == 0) { umma::fence_after(); issue_gemm1(); issue_gemm3(aWB); umma::commit(barZ); }
+            if (warp == 0) { umma::fence_after(); issue_gemm1(); issue_gemm3(aWB); umma::commit_w(barZ); }
             umma::mbar_wait(barZ, phZ); phZ ^= 1;                     // (in-order pipe: chunk c-1's gradient MMAs are done too)
             if (c > 0) { umma::mbar_wait(barG, phG); phG ^= 1; }      // A and dZ tiles free
             umma::fence_after();
@@ -505,12 +507,12 @@ kc_train_tc_kernel(int hidden, int nch, const float* __restrict__ W1hl, const un
             umma::fence_async_smem();
             umma::fence_before();
             __syncthreads();
-            if (tid == 0) {
+            if (warp == 0) {
                 umma::fence_after();
                 if (MODE == 3) issue_gemm4(c == 0, aAh + ((stage & 1) ? 16384u : 0u));
                 else issue_grads(c, first_tile);
                 umma::mbar_wait(barL, phL);                           // dZ lo consumed: its bytes may take the next W1 chunk
-                if (prefetch) fetch_w1(c + 1 < nch ? c + 1 : 0);
+                if (lane == 0 && prefetch) fetch_w1(c + 1 < nch ? c + 1 : 0);
             }
             phL ^= 1;
         }

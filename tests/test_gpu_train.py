@@ -1,5 +1,7 @@
 """GPU parity of the training-step kernels (kc_train_step, kc_adam_clamp, kc_ode_bwd) through the C ABI, against the
 reference's own autograd results (tests/golden/train.npz, ode.npz) and the numpy oracle."""
+import ctypes as C
+
 import numpy as np
 import pytest
 import torch
@@ -374,3 +376,64 @@ def test_train_step_config3_full_size_properties(ops, monkeypatch):
     assert abs(ls - o_loss) < 1e-4 * abs(o_loss)
     for k, a in zip(PK, gs):
         assert np.abs(a - o_grads[k]).max() < 1e-4 * np.abs(o_grads[k]).max(), k
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.float64])
+def test_peer_allreduce_adam_emulated_ranks(dt):
+    """kc_peer_publish / kc_peer_gather_adam (all-reduce over peer memory fused with Adam + clamp) with 3 emulated ranks on
+    one GPU: the three regions are ordinary device buffers, all ranks publish first and gather afterwards (so nothing
+    waits), two consecutive steps (both slots).  Against: sum of the ranks' flat buffers in rank order, then
+    kc_adam_clamp_multi on that sum — bitwise."""
+    import _kc
+    import _ops
+    torch.manual_seed(0)
+    W, sizes = 3, [(7, 5), (7,), (4, 7), (4,)]
+    n = sum(int(np.prod(s)) for s in sizes) + 1
+    nbytes = int(_kc.lib().kc_peer_region_bytes(_ops._DT[dt], n))
+    regions = [torch.zeros(nbytes, dtype=torch.uint8, device="cuda") for _ in range(W)]
+    ranks = []
+    for r in range(W):
+        flat = torch.zeros(n, dtype=dt, device="cuda")
+        grads, off = [], 0
+        for s in sizes:
+            k = int(np.prod(s))
+            grads.append(flat[off:off + k].view(s))
+            off += k
+        torch.manual_seed(1)
+        params = [torch.rand(s, dtype=dt, device="cuda") * 0.1 for s in sizes]      # same weights on every rank
+        adam = _ops.AdamClampMulti(params, grads, [True, False, True, False], lr=1e-2)
+        assert adam.enable_peer_allreduce(flat, regions=[t.data_ptr() for t in regions], rank=r, world=W)
+        ranks.append((flat, params, adam))
+    torch.manual_seed(2)
+    ref_params = [p.clone() for p in ranks[0][1]]
+    ref_flat = torch.zeros(n, dtype=dt, device="cuda")
+    ref_grads, off = [], 0
+    for s in sizes:
+        k = int(np.prod(s))
+        ref_grads.append(ref_flat[off:off + k].view(s))
+        off += k
+    ref_adam = _ops.AdamClampMulti(ref_params, ref_grads, [True, False, True, False], lr=1e-2)
+    L = _kc.lib()
+    for step in range(3):
+        locals_ = [torch.randn(n, dtype=dt, device="cuda") for _ in range(W)]
+        tot = locals_[0].clone()
+        for r in range(1, W):
+            tot = tot + locals_[r]                                   # rank order, as the kernel adds
+        for r, (flat, _, adam) in enumerate(ranks):
+            flat.copy_(locals_[r])
+            st = _ops._stream(flat.device)
+            _kc.check(L.kc_peer_publish(_ops._DT[dt], W, r, C.cast(adam._peer_regions, C.c_void_p), n, _ops._ptr(flat),
+                                        _ops._ptr(adam.step_dev), _ops._ptr(adam._peer_tickets), st), "publish")
+        for r, (flat, _, adam) in enumerate(ranks):
+            st = _ops._stream(flat.device)
+            _kc.check(L.kc_peer_gather_adam(_ops._DT[dt], W, r, C.cast(adam._peer_regions, C.c_void_p), n, _ops._ptr(flat),
+                                            4, C.cast(adam.arr, C.c_void_p), _ops._ptr(adam.step_dev), _ops._ptr(adam.lr_dev),
+                                            0.9, 0.999, 1e-8, 0.0, adam._peer_tickets[1:].data_ptr(), st), "gather")
+        ref_flat.copy_(tot)
+        ref_adam.run()
+        torch.cuda.synchronize()
+        for flat, params, adam in ranks:
+            assert torch.equal(flat, tot)
+            assert int(adam.step_dev.item()) == step + 1
+            for p, q in zip(params, ref_params):
+                assert torch.equal(p, q)
