@@ -279,6 +279,21 @@ def main():
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = world * rns_per_step * args.steps / e2e_s
 
+    # ---------------- end to end for a caller that only reads the tip positions (physics_train.py:159) ----------------------
+    tip_pinned = torch.empty((B, T, 3, 1), dtype=torch.float32).pin_memory()
+    tip_sel = ([0, 1, 2], [N_NODES - 1])
+    for _ in range(2):
+        simulate(robot, ctl_pinned, dtype=np.float32, rows=25, pinned_out=tip_pinned, select=tip_sel)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        simulate(robot, ctl_pinned, dtype=np.float32, rows=25, pinned_out=tip_pinned, select=tip_sel)
+    barrier()
+    tip_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_tip = {"value": world * rns_per_step * args.steps / tip_s, "unit": "rod-node-steps/s", "ms_per_step": tip_s / args.steps * 1e3,
+               "api": "knode.simulate(..., select=([0,1,2],[N-1])): same rollout, only the tip positions cross PCIe",
+               "h2d_bytes_per_step": int(ctl_host.nbytes), "d2h_bytes_per_step": int(tip_pinned.numel() * 4)}
+
     # ---------------- the same API under the REFERENCE's contract: float64 host list/array in -> fresh float64 [B,T,50,N] ----
     e2e_ref = None
     if not args.no_train:
@@ -584,9 +599,10 @@ def main():
                                  "peak": hbm, "unit": "GB/s", "frac": ebytes / (ems_med * 1e-3) / 1e9 / hbm,
                                  "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy bandwidth)",
                                  "algorithmic_bytes_per_rod_node_step": (32 * N_NODES + 4) * 8 / N_NODES,
-                                 "algorithmic_bytes": ebytes, "traffic": 4.042e9 * EB / 256,
-                                 "traffic_source": "ncu dram__bytes_read+write of one launch at 256 recordings (1.03 GB + 3.01 "
-                                                   "GB, profiles/r01_ncu_prof_est64_r1t.csv), scaled to this batch"}}
+                                 "algorithmic_bytes": ebytes, "traffic": 4.048e9 * EB / 256,
+                                 "traffic_source": "ncu dram__bytes_read+write of one launch at 256 recordings in the round-2 "
+                                                   "build (1.032 GB + 3.015 GB, profiles/r02_ncu_prof_estimate.csv), scaled "
+                                                   "to this batch"}}
 
     # ---------------- CPU baseline (rank 0, bounded sample, the reference's algorithm on the host cores) -----------
     cpu = None
@@ -647,12 +663,12 @@ def main():
                                         "no FP32-pipe figure)", "normalisation": "6.06 kFLOP per rod-node-step = 15 "
                          "nominal residual evaluations x 9/10 x 449 FLOP (SURVEY 8d)",
                          "kernel_ms": kern_ms, "executed_tflops": executed_flop / (kern_ms * 1e-3) / 1e12,
-                         "traffic": 364.1e6, "traffic_source": "ncu dram__bytes_read+write per launch, "
-                         "profiles/r01_ncu_prof_rollout_lin_r1h.csv (algorithmic 416 MB: 410 MB trajectory written once + "
+                         "traffic": 364.9e6, "traffic_source": "ncu --set full of this kernel in the round-2 build (7.5 MB read + 357.4 MB "
+                         "written per launch), profiles/r02_ncu_prof_rollout_lin.csv (algorithmic 416 MB: 410 MB trajectory written once + "
                          "6.5 MB tensions read; the tail of the trajectory is still in L2 when the kernel ends)",
                          "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak}},
             "cpu_baseline": cpu, "train": train, "train_weak": train_weak, "knode_rollout": knode, "train_bptt": bptt,
-            "rollout_f64": f64, "c1_single_rod": c1, "e2e_reference_contract": e2e_ref,
+            "rollout_f64": f64, "c1_single_rod": c1, "e2e_reference_contract": e2e_ref, "e2e_tip_only": e2e_tip,
             "train_bptt_weak": bptt_weak, "estimate_state": estimate}
         print(json.dumps(out))
     sys.stdout.flush()

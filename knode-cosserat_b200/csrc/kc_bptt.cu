@@ -264,12 +264,17 @@ kc_rollout_loss_kernel(int64_t B, int T_, int N, int K, KeyIdx key, const T* __r
         kc_loss_partials[blockIdx.x] = s;
     }
 }
-__global__ void kc_loss_sum_kernel(int n, double* __restrict__ loss) {   // fixed order: bitwise reproducible
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        double s = 0.0;
-        for (int i = 0; i < n; ++i) s += kc_loss_partials[i];
-        *loss = s;
+__global__ void __launch_bounds__(256) kc_loss_sum_kernel(int n, double* __restrict__ loss) {   // fixed tree: bitwise reproducible
+    __shared__ double s[256];
+    double a = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) a += kc_loss_partials[i];
+    s[threadIdx.x] = a;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if ((int)threadIdx.x < w) s[threadIdx.x] += s[threadIdx.x + w];
+        __syncthreads();
     }
+    if (threadIdx.x == 0) *loss = s[0];
 }
 
 extern "C" int kc_rollout_loss(int dtype, int64_t B, int64_t T_, int32_t N, int32_t K, const int32_t* key_idx_host,
@@ -299,7 +304,7 @@ extern "C" int kc_rollout_loss(int dtype, int64_t B, int64_t T_, int32_t N, int3
     else
         kc_rollout_loss_kernel<double><<<grid, 256, 0, st>>>(B, (int)T_, N, K, key, (const double*)traj, (const double*)target, scale, (double*)g_traj);
     KC_CHECK_LAUNCH("kc_rollout_loss_kernel");
-    kc_loss_sum_kernel<<<1, 32, 0, st>>>(grid, loss);
+    kc_loss_sum_kernel<<<1, 256, 0, st>>>(grid, loss);
     KC_CHECK_LAUNCH("kc_loss_sum_kernel");
     return KC_OK;
 }

@@ -77,7 +77,7 @@ def _robot_mlp(robot, dtype):
 
 
 def simulate(robot, ctl, robot_reference=None, *, dtype=np.float64, rows=50, tol=0.0, max_iter=0, return_info=False,
-             pinned_out=None, method="euler", device_out=False):
+             pinned_out=None, method="euler", device_out=False, select=None):
     """Roll the rod out under the tendon tensions `ctl` ([T,4] -> [T,rows,N]; [B,T,4] -> [B,T,rows,N]).
 
     Keyword-only extensions (not in the reference): dtype (np.float64 | np.float32 arithmetic and output), rows (50 =
@@ -87,6 +87,11 @@ def simulate(robot, ctl, robot_reference=None, *, dtype=np.float64, rows=50, tol
     getResidualRK4, cosserat_ode.py:215-255, as the residual of the same loop), device_out = True with CUDA tensions:
     return the trajectory as a CUDA tensor (no device-to-host copy; for callers that reduce it on the GPU, e.g. the
     evaluation metrics of physics_train / physics_multitrain).
+
+    select = (row_indices, node_indices): return only traj[..., rows, :][..., nodes] — e.g. ([0, 1, 2], [N-1]) for the tip
+    positions that physics_train.py:159 / physics_multitrain.py:211 actually read.  The rollout is unchanged; the selection
+    happens on the device, so the device-to-host copy (the bulk of an end-to-end call: 410 MB at BASELINE config 2) shrinks
+    to the selected entries.
 
     Shooting solve: Newton / Broyden on the 6 base reactions to `tol` (default 1e-11 fp64, 2e-6 fp32, relative to
     max(1, |G|)) instead of MINPACK hybrd.  In the kernels with the linearised final correction (small batches) the LAST
@@ -100,6 +105,26 @@ def simulate(robot, ctl, robot_reference=None, *, dtype=np.float64, rows=50, tol
     if not torch.cuda.is_available():
         raise RuntimeError("knode-cosserat_b200 has no CPU fallback: simulate() needs a CUDA device")
     dev = torch.device("cuda", torch.cuda.current_device())
+    if select is not None:
+        # solve on the device, gather the selected rows / nodes there, copy only those back
+        rows_sel, nodes_sel = select
+        if torch.is_tensor(ctl):
+            ctl_dev = ctl.to(dev, non_blocking=True)
+        else:
+            ctl_np_ = np.asarray(ctl)
+            ctl_dev = torch.as_tensor(ctl_np_ if ctl_np_.dtype.kind == 'f' else ctl_np_.astype(np.float64)).to(dev, non_blocking=True)
+        full = simulate(robot, ctl_dev, robot_reference, dtype=dtype, rows=rows, tol=tol, max_iter=max_iter, method=method,
+                        device_out=True)
+        ri = torch.as_tensor(np.asarray(rows_sel).reshape(-1), device=dev, dtype=torch.long)
+        ni = torch.as_tensor(np.asarray(nodes_sel).reshape(-1), device=dev, dtype=torch.long)
+        sel = full.index_select(-2, ri).index_select(-1, ni)
+        if device_out:
+            return sel
+        if pinned_out is not None:
+            pinned_out.copy_(sel, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return pinned_out.numpy()
+        return sel.cpu().numpy()
     tdt = torch.float64 if np.dtype(dtype) == np.float64 else torch.float32
     on_device = torch.is_tensor(ctl) and ctl.is_cuda
     if method != "euler" and not on_device:     # the pipelined host entry point runs the Euler march only

@@ -302,3 +302,19 @@ def test_eval_metrics_kernel_vs_oracle(golden, dt):
     assert d2.item() == O.dtw_l1(pa[0][:, :3, 9], pb[0][:37, :3, 9]) and np.isnan(m2.item())
     d3, _ = _ops.eval_metrics(pred[:, :1], ref[:, :1], want_mse=False)       # a single time index
     assert d3[0].item() == float(np.abs(pa[0][0, :3, 9] - pb[0][0, :3, 9]).sum())
+
+
+def test_simulate_select_returns_the_selected_entries():
+    """simulate(..., select=(rows, nodes)): the same rollout, only the selected entries copied back (what
+    physics_train.py:159 reads is the tip position)."""
+    from cosserat_ode import CosseratRod
+    from knode import setup_robot, simulate
+    from physics_controls import synthetic_tensions
+    r = CosseratRod(use_fsolve=True)
+    setup_robot(r)
+    ctl = synthetic_tensions(9, 12, r.del_t, seed=4, dtype=np.float64)
+    full = simulate(r, ctl)
+    tip = simulate(r, ctl, select=([0, 1, 2], [9]))
+    assert tip.shape == (9, 12, 3, 1) and np.array_equal(tip[..., 0], full[:, :, :3, 9])
+    one = simulate(r, ctl[0], rows=25, dtype=np.float32, select=([7, 8, 9, 10, 11, 12], [0, 9]))
+    assert one.shape == (12, 6, 2) and one.dtype == np.float32
