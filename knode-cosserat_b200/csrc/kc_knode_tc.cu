@@ -645,6 +645,178 @@ kc_knode_tc_fwd_kernel(const __grid_constant__ RodC<float> P, const unsigned cha
 }
 
 // =========================================================================================================================
+// Forward, LARGE batches: one row per rod (up to 128 rods per CTA), quasi-Newton shooting solve of the one-rod-per-lane kernel
+// (shoot_step, kc_rod.cuh: linear predictor, Broyden-updated inverse Jacobian kept across time steps, finite-difference
+// rebuild on the first step or after two stalled iterations) run in LOCK STEP over the CTA — every march is one MLP per node
+// for all rods, so a rod that has converged keeps marching its frozen point (without storing) until the slowest rod of the
+// CTA is done.  Per rod-step this evaluates the MLP ~7 times instead of 8 rows x ~3 joint marches: 3-4x the throughput of
+// the 8-rows-per-rod kernel once the batch fills the chip with 128-row CTAs; the per-march latency is the same, so small
+// batches (training, <= 8k rods) stay with the Newton kernel above.
+struct LsState {   // per-rod state of the lock-step solve (registers)
+    float G[6], F[6], dG[6], fprev, eps_k;
+    int phase, k, marches, stalled;
+    bool fin, converged, failed;
+};
+
+template <bool DIAG>
+__global__ void __launch_bounds__(ktc::THREADS, 1)
+kc_knode_tc_fwd1_kernel(const __grid_constant__ RodC<float> P, const unsigned char* __restrict__ img, const float* __restrict__ b2,
+                        int hidden, int64_t B, int T_, int rpc, const float* __restrict__ tensions, const float* __restrict__ y0,
+                        const float* __restrict__ z0, float* trajD, float tol, int max_iter, float fd_eps, float* Gout,
+                        int32_t* iters, float* __restrict__ hist_all, int hist_in_smem) {
+    extern __shared__ __align__(1024) unsigned char sm[];
+    constexpr int NH = 12, LS = 32, CS = 128;
+    enum { PRED = 0, FD = 1, BROY = 2 };
+    const int N = P.N, tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    ktc::Bars* bars = ktc::cta_setup(sm, ktc::F_MISC, img, 4 * ktc::IMG);
+    const uint32_t tbase = __shfl_sync(0xffffffffu, bars->tmem_slot, 0);
+    const uint32_t laneblk = (uint32_t)((warp & 3) * 32) << 16;
+    const int nch = (hidden + 127) / 128;
+    if (warp == 8) {
+        ktc::mma_loop_fwd(sm, bars, tbase, nch);
+    } else if (warp >= 4) {
+        ktc::helper_loop<false>(bars, tbase, laneblk, nch);
+    } else {
+        MlpTCF M{};
+        M.sm = sm; M.bars = bars; M.tbase = tbase; M.laneblk = laneblk; M.nch = nch; M.row = tid; M.ph = 0; M.b2 = b2;
+        M.ev = 0; M.tr = false;
+        M.hidden = hidden; M.in_dim = 28;
+        float* stm = reinterpret_cast<float*>(sm + ktc::F_HIST) + tid;                       // ShootMem [49][128]
+        float* Hs = hist_in_smem ? stm - tid + (size_t)KC_SHOOT_SLOTS * CS + tid             // history [N-1][12][128]
+                                 : hist_all + (size_t)blockIdx.x * (N - 1) * NH * CS + tid;
+        const ShootMem<float, CS> st{stm};
+        const size_t tstride = (size_t)25 * N * LS;
+        const int64_t ngroups = (B + rpc - 1) / rpc;
+        for (int64_t grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+            // rows beyond the group's rods shadow one of them (same values, no stores): every row takes part in every MLP
+            const int64_t b_raw = grp * rpc + (tid % rpc);
+            const bool valid = tid < rpc && b_raw < B;
+            const int64_t b = b_raw < B ? b_raw : B - 1;
+            float* traj_b = ktc::rod_base_tc(trajD, b, T_, N);
+            st.reset();
+            if (valid) {
+                rollout_init<float, LS>(P, y0 ? y0 + (size_t)b * 19 * N : nullptr, z0 ? z0 + (size_t)b * 6 * N : nullptr, traj_b);
+                if (Gout) {
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) Gout[(size_t)b * T_ * 6 + i] = 0.f;
+                }
+                if (iters) iters[(size_t)b * T_] = 0;
+            }
+            __threadfence_block();
+            ktc::sync128();
+            build_history<float, NH, LS, CS>(P, traj_b, traj_b, Hs);
+            const float* ten = tensions + (size_t)b * T_ * 4;
+            for (int t = 0; t < T_ - 1; ++t) {
+                float tn[4], tf[3];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) tn[i] = ten[(size_t)t * 4 + i];
+                tendon_force(P, tn, tf);
+                float* cur = traj_b + (size_t)t * tstride;
+                float* nxt = cur + tstride;
+                HistView<float, NH, CS> H{Hs};
+                // ---- shoot_step (kc_rod.cuh) in lock step ----
+                LsState q;
+#pragma unroll
+                for (int i = 0; i < 6; ++i) { q.G[i] = st.G(i) + (st.G(i) - st.Gm1(i)); q.F[i] = 0.f; q.dG[i] = 0.f; }
+                q.phase = PRED; q.k = 0; q.marches = 0; q.stalled = 0; q.fprev = 0.f; q.eps_k = 0.f;
+                q.fin = false; q.converged = false; q.failed = false;
+                while (true) {
+                    float Ge[6], Fn[6];
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) Ge[i] = q.G[i];
+                    if (!q.fin && q.phase == FD) {
+                        float gk = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 6; ++i) if (i == q.k) gk = q.G[i];
+                        q.eps_k = fd_eps * kc_max(1.f, kc_abs(gk));
+#pragma unroll
+                        for (int i = 0; i < 6; ++i) if (i == q.k) Ge[i] += q.eps_k;
+                    }
+                    TrajSinkPred<float, LS, NH, CS> S{nxt, nullptr, valid && !q.fin, N - 1};
+                    rod_march<float, DIAG, 28, NH>(P, M, Ge, tf, H, S, Fn);
+                    if (!q.fin) {
+                        ++q.marches;
+                        bool take_step = false;
+                        if (q.phase == FD) {
+                            const float ie = 1.f / q.eps_k;
+#pragma unroll
+                            for (int i = 0; i < 6; ++i) {
+                                const float d = (Fn[i] - q.F[i]) * ie;
+#pragma unroll
+                                for (int c = 0; c < 6; ++c) if (c == q.k) st.J(i, c) = d;
+                            }
+                            if (++q.k == 6) {
+                                float A[36];
+#pragma unroll
+                                for (int i = 0; i < 36; ++i) A[i] = st.J(i / 6, i % 6);
+                                if (!inv6(A)) { q.failed = true; q.fin = true; }
+                                else {
+#pragma unroll
+                                    for (int i = 0; i < 36; ++i) st.J(i / 6, i % 6) = A[i];
+                                    st.haveJ() = 1.f;
+                                    q.stalled = 0;
+                                    take_step = true;
+                                }
+                            }
+                        } else {
+                            if (q.phase == BROY) {
+                                float yv[6];
+#pragma unroll
+                                for (int i = 0; i < 6; ++i) yv[i] = Fn[i] - q.F[i];
+                                broyden_update(st, q.dG, yv);
+                            }
+#pragma unroll
+                            for (int i = 0; i < 6; ++i) q.F[i] = Fn[i];
+                            const float fn = norm_inf6(q.F);
+                            if (!(fn == fn)) { q.failed = true; q.fin = true; }
+                            else {
+                                if (q.phase == BROY) q.stalled = (fn > 0.5f * q.fprev) ? q.stalled + 1 : 0;
+                                q.fprev = fn;
+                                q.converged = fn <= tol * kc_max(1.f, norm_inf6(q.G));
+                                if (q.converged || q.marches >= max_iter) q.fin = true;
+                                else if (st.haveJ() == 0.f || q.stalled >= 2) { q.phase = FD; q.k = 0; }
+                                else take_step = true;
+                            }
+                        }
+                        if (take_step) {
+#pragma unroll
+                            for (int i = 0; i < 6; ++i) {
+                                float a = 0.f;
+#pragma unroll
+                                for (int j = 0; j < 6; ++j) a += st.J(i, j) * q.F[j];
+                                q.dG[i] = -a;
+                            }
+#pragma unroll
+                            for (int i = 0; i < 6; ++i) q.G[i] += q.dG[i];
+                            q.phase = BROY;
+                        }
+                    }
+                    if (ktc::all128(q.fin)) break;
+                }
+                if (!q.failed) {
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) { st.Gm1(i) = st.G(i); st.G(i) = q.G[i]; }
+                }
+                if (valid) {
+                    const size_t o = (size_t)(N - 1) * 25 * LS;
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) nxt[o + (19 + c) * LS] = cur[o + (19 + c) * LS];   // z[:, N-1] never changes
+                    if (Gout) {
+#pragma unroll
+                        for (int i = 0; i < 6; ++i) Gout[((size_t)b * T_ + t + 1) * 6 + i] = st.G(i);
+                    }
+                    if (iters) iters[(size_t)b * T_ + t + 1] = (q.converged && !q.failed) ? q.marches : -q.marches;
+                }
+                __threadfence_block();
+                ktc::sync128();       // shadow rows read the state their rod's owner has just stored
+                build_history<float, NH, LS, CS>(P, nxt, cur, Hs);
+            }
+        }
+    }
+    ktc::cta_teardown(bars, tbase);
+}
+
+// =========================================================================================================================
 // Backward through the rollout for the same shape: persistent CTAs over groups of 16 rods, steps in reverse, ONE joint
 // adjoint march per step (see the header).  traj / gtraj in the reference layout [B][T][25][N].
 //   rowscr : per CTA [(N-1)*SV][128] floats — per node and row: 12 history cotangents, 25 output cotangents
@@ -882,14 +1054,60 @@ static int tc_prep(const kc_mlp* mlp, unsigned char* img, cudaStream_t st) {
     KC_CHECK_LAUNCH("kc_knode_tc_prep_kernel");
     return KC_OK;
 }
+static int tc_sms() {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms;
+}
+// rods per CTA of the one-row-per-rod kernel: a round of CTAs costs the same whether they hold 32 or 128 rods, so use the
+// fewest rounds and spread the rods evenly over them (multiples of a warp)
+static int tc_fwd1_rpc(int64_t B) {
+    const int64_t sms = tc_sms();
+    const int64_t rounds = (B + 128 * sms - 1) / (128 * sms);
+    int64_t rpc = (B + rounds * sms - 1) / (rounds * sms);
+    rpc = (rpc + 31) / 32 * 32;
+    return (int)(rpc < 32 ? 32 : (rpc > 128 ? 128 : rpc));
+}
+static bool tc_fwd_one_row(int64_t B) {
+    // 8 rows per rod (Newton, ~3 joint marches per step, 16 rods per CTA) for small batches; one row per rod (Broyden in
+    // lock step, ~8 marches per step, 128 rods per CTA) once the 8-row kernel would need more than 3 rounds of CTAs.
+    // Measured (H = 512, T = 30): 4096 rods 8.2 vs 12.0 ms, 8192 rods 16.0 vs 12.6 ms, 18 944 rods 31.5 vs 12.6 ms
+    bool one = B > (int64_t)3 * tc_sms() * ktc::RPC;
+    if (const char* e = getenv("KC_ROLLOUT_TC_ROWS")) { if (e[0] == '1') one = true; if (e[0] == '8') one = false; }
+    return one;
+}
 size_t kc_knode_tc_fwd_scratch_bytes(int N, int64_t B) {
-    return (size_t)tc_bwd_grid(B) * 25 * N * 128 * sizeof(float) + 256;
+    const size_t states = (size_t)tc_bwd_grid(B) * 25 * N * 128 * sizeof(float);             // 8-row kernel: marched states
+    const size_t hist = (size_t)148 * 2 * (N - 1) * 12 * 128 * sizeof(float);                // 1-row kernel: history, if not in smem
+    return (states > hist ? states : hist) + 256;
 }
 int kc_knode_tc_fwd(const RodC<float>& P, const kc_mlp* mlp, int64_t B, int T_, const float* tensions, const float* y0,
                     const float* z0, float* trajD, float tol, int max_iter, float fd_eps, float* Gout, int32_t* iters,
                     unsigned char* img, unsigned char* scratch, cudaStream_t st) {
     int rc = tc_prep(mlp, img, st);
     if (rc) return rc;
+    if (tc_fwd_one_row(B)) {
+        const int rpc = tc_fwd1_rpc(B);
+        const int64_t ngroups = (B + rpc - 1) / rpc;
+        const int sms = tc_sms();
+        const unsigned grid = (unsigned)(ngroups < sms ? ngroups : sms);
+        const size_t hist_b = (size_t)(P.N - 1) * 12 * 128 * sizeof(float);
+        const size_t base = (size_t)ktc::F_HIST + (size_t)KC_SHOOT_SLOTS * 128 * sizeof(float);
+        const int hist_in_smem = base + hist_b <= 227 * 1024 ? 1 : 0;
+        const size_t smem = base + (hist_in_smem ? hist_b : 0);
+#define KC_GO1(D)                                                                                                      \
+    do {                                                                                                               \
+        cudaFuncSetAttribute(kc_knode_tc_fwd1_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
+        kc_knode_tc_fwd1_kernel<D><<<grid, ktc::THREADS, smem, st>>>(P, img, (const float*)mlp->b2, mlp->hidden, B, T_,\
+            rpc, tensions, y0, z0, trajD, tol, max_iter, fd_eps, Gout, iters, reinterpret_cast<float*>(scratch),       \
+            hist_in_smem);                                                                                             \
+    } while (0)
+        if (P.diag) KC_GO1(true); else KC_GO1(false);
+#undef KC_GO1
+        KC_CHECK_LAUNCH("kc_knode_tc_fwd1_kernel");
+        return KC_OK;
+    }
     const size_t smem = (size_t)ktc::F_HIST + (size_t)2 * (P.N - 1) * 12 * ktc::RPC * sizeof(float);
     const unsigned grid = (unsigned)tc_bwd_grid(B);
 #define KC_GO(D)                                                                                                       \

@@ -32,6 +32,14 @@ def tc(monkeypatch):
     monkeypatch.setenv("KC_ROLLOUT_TC", "1")
 
 
+@pytest.fixture(params=["8", "1"])
+def rows(request, monkeypatch):
+    """Both forward kernels: 8 rows per rod (Newton with a finite-difference Jacobian per joint march; small batches) and
+    one row per rod (Broyden in lock step over the CTA; the launcher's choice from 8192 rods on)."""
+    monkeypatch.setenv("KC_ROLLOUT_TC_ROWS", request.param)
+    return request.param
+
+
 @pytest.fixture
 def simt(monkeypatch):
     monkeypatch.setenv("KC_ROLLOUT_TC", "0")
@@ -64,7 +72,7 @@ def _dev(a, dt=torch.float32):
 
 
 @pytest.mark.parametrize("tag", ["h64", "h512"])
-def test_knode_rollout_tc_vs_reference(golden, tc, tag):
+def test_knode_rollout_tc_vs_reference(golden, tc, rows, tag):
     import _ops
     d = golden["knode_rollouts"]
     P = O.setup_params(O.RodParams(), "youngs")
@@ -84,8 +92,8 @@ def _case(H, B, T, seed):
     return P, ctl, mlp
 
 
-@pytest.mark.parametrize("H,B,T", [(16, 37, 9), (200, 16, 6), (512, 19, 8), (384, 1, 5)])
-def test_knode_rollout_tc_ragged_batches_vs_oracle(tc, H, B, T):
+@pytest.mark.parametrize("H,B,T", [(16, 37, 9), (200, 16, 6), (512, 19, 8), (384, 1, 5), (64, 150, 5)])
+def test_knode_rollout_tc_ragged_batches_vs_oracle(tc, rows, H, B, T):
     """Batches that do not fill a CTA (16 rods), hidden sizes that do not fill a chunk (128), one chunk / several chunks."""
     import _ops
     P, ctl, mlp = _case(H, B, T, seed=H + B)
