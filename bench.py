@@ -458,13 +458,22 @@ def main():
             r_.nn_models[2].bias.mul_(0.02)
         return r_
 
-    def group_marches(iters_bt, rods_per_cta=16):
-        """Joint marches the tensor-core kernel executes: a CTA's 16 rods march until the slowest one has converged."""
+    def group_marches(iters_bt):
+        """Marches the tensor-core forward kernel executes (each is one 128-row MLP per node and CTA): a CTA's rods march
+        until the slowest one has converged.  Mirrors the launcher's choice (csrc/kc_knode_tc.cu): 16 rods x 8 rows per CTA,
+        or — beyond 3 rounds of such CTAs — one row per rod."""
         a = iters_bt[:, 1:].abs().float()
-        pad = (-a.shape[0]) % rods_per_cta
+        nb = a.shape[0]
+        if nb > 3 * 148 * 16:
+            rounds = -(-nb // (128 * 148))
+            rpc = min(128, max(32, -(-(-(-nb // (rounds * 148))) // 32) * 32))
+            lo = 1
+        else:
+            rpc, lo = 16, 2
+        pad = (-nb) % rpc
         if pad:
             a = torch.cat([a, a[-1:].expand(pad, -1)])
-        return float(a.view(-1, rods_per_cta, a.shape[1]).amax(1).clamp(min=2).sum().item())
+        return float(a.view(-1, rpc, a.shape[1]).amax(1).clamp(min=lo).sum().item()), rpc
 
     knode = None
     bptt = None
@@ -491,19 +500,20 @@ def main():
             kms.append(e0.elapsed_time(e1))
         kms_med = max_over_ranks(float(np.median(kms)))
         k_rns = KB * N_NODES * (KT - 1)
-        k_exec = group_marches(kplan.iters) * (N_NODES - 1) * MMA_FWD
+        k_marches, k_rpc = group_marches(kplan.iters)
+        k_exec = k_marches * (N_NODES - 1) * MMA_FWD
         knode = {"metric": "KNODE rod-node-steps/sec (forward rollout, MLP in the march)", "value": world * k_rns / (kms_med * 1e-3),
                  "unit": "rod-node-steps/s", "ms_per_rollout": kms_med, "rods_per_gpu": KB, "time_indices": KT, "hidden": TRAIN_H,
                  "dtype": "f32", "all_converged": bool(int(kplan.iters.min()) >= 0),
                  "marches_per_step_mean": float(kplan.iters[:, 1:].abs().float().mean().item()),
-                 "roofline": {"bound": "tensor", "kernel": "kc_knode_tc_fwd_kernel (tcgen05 kind::f16, activation tile in TMEM, "
-                              ".ts MMA; 16 rods x 8 shooting points per CTA)",
+                 "roofline": {"bound": "tensor", "kernel": "kc_knode_tc_fwd1_kernel (tcgen05 kind::f16, activation tile in TMEM, "
+                              ".ts MMA; one row per rod, %d rods per CTA, Broyden in lock step)" % k_rpc,
                               "achieved": k_exec / (kms_med * 1e-3) / 1e12, "peak": bf16_peak / 1e12, "unit": "TFLOP/s",
                               "frac": k_exec / (kms_med * 1e-3) / bf16_peak,
                               "peak_source": "MEASURED_PEAKS.json bf16_tflops (cuBLAS burst; the kernel is timed alone)",
-                              "what": "EXECUTED tensor FLOP/s: every joint march evaluates the MLP for 128 rows per CTA "
-                                      "(8 shooting points per rod: base + 6 finite-difference points + 1 spare) in 3 bf16 "
-                                      "hi/lo passes (fp32-grade products); rows padded to K = 32 inputs / N = 32 outputs",
+                              "what": "EXECUTED tensor FLOP/s: every march evaluates the MLP for a 128-row tile per CTA in 3 bf16 "
+                                      "hi/lo passes (fp32-grade products), K = 32 inputs / N = 32 outputs padded; a CTA "
+                                      "marches until its slowest rod has converged",
                               "useful_tflops": k_rns * FLOP_PER_RNS_KNODE / (kms_med * 1e-3) / 1e12,
                               "useful_frac": k_rns * FLOP_PER_RNS_KNODE / (kms_med * 1e-3) / bf16_peak,
                               "useful_normalisation": "738.7 kFLOP per rod-node-step = 15 nominal evaluations x 9/10 x (449 + "
@@ -531,7 +541,7 @@ def main():
             barrier()
             ms = max_over_ranks(e0.elapsed_time(e1)) / n_
             its_ = tr.plan.fwd.iters
-            exec_flop = group_marches(its_) * (N_NODES - 1) * MMA_FWD + \
+            exec_flop = group_marches(its_)[0] * (N_NODES - 1) * MMA_FWD + \
                 ((nb + 15) // 16) * (TRAIN_T - 1) * (N_NODES - 1) * MMA_BWD
             identical = None
             if world > 1:
@@ -604,6 +614,17 @@ def main():
                                                    "build (1.032 GB + 3.015 GB, profiles/r02_ncu_prof_estimate.csv), scaled "
                                                    "to this batch"}}
 
+    # ---------------- config 5 (BASELINE configs[4]): this rank's 8192-rod shard of the 65 536-rod sweep -----------------------
+    config5 = None
+    if not args.no_train:
+        del plan
+        torch.cuda.empty_cache()
+        config5 = measure_c5(args, rank, world, dev, barrier, max_over_ranks, 2)
+        config5.pop("e2e", None)
+        config5.pop("cpu_baseline", None)
+        config5["note"] = ("every rank rolls its own 8192-rod shard out (no collective): at --gpus 8 this IS configuration 5 "
+                           "(65 536 rods x 20 nodes x 500 time indices); `python bench.py --config c5` prints it as a contract line")
+
     # ---------------- CPU baseline (rank 0, bounded sample, the reference's algorithm on the host cores) -----------
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
@@ -668,7 +689,7 @@ def main():
                          "6.5 MB tensions read; the tail of the trajectory is still in L2 when the kernel ends)",
                          "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak}},
             "cpu_baseline": cpu, "train": train, "train_weak": train_weak, "knode_rollout": knode, "train_bptt": bptt,
-            "rollout_f64": f64, "c1_single_rod": c1, "e2e_reference_contract": e2e_ref, "e2e_tip_only": e2e_tip,
+            "config5": config5, "rollout_f64": f64, "c1_single_rod": c1, "e2e_reference_contract": e2e_ref, "e2e_tip_only": e2e_tip,
             "train_bptt_weak": bptt_weak, "estimate_state": estimate}
         print(json.dumps(out))
     sys.stdout.flush()
@@ -696,6 +717,13 @@ def finish(world, trainer, args):
 
 
 def run_c5(args, rank, world, dev, barrier, max_over_ranks):
+    out = measure_c5(args, rank, world, dev, barrier, max_over_ranks, max(2, min(args.steps, 5)))
+    if rank == 0:
+        print(json.dumps(out))
+    sys.stdout.flush()
+
+
+def measure_c5(args, rank, world, dev, barrier, max_over_ranks, steps):
     """BASELINE configs[4]: 65 536 rods x 20 nodes x 500 time indices over 8 GPUs = 8 192 rods per GPU, the
     configuration of train_segment.py (class-default physical parameters: it never calls setup_robot; dt = 0.005; H = 512).
     Physics-only rollout (the contract line's value) and the KNODE rollout (MLP in the march on tcgen05)."""
@@ -718,7 +746,6 @@ def run_c5(args, rank, world, dev, barrier, max_over_ranks):
         plan.run(ctl)
     barrier()
     sampler.start()
-    steps = max(2, min(args.steps, 5))
     ev = []
     for _ in range(steps):     # 8.2 GB written per step: far beyond L2, no flush needed
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -763,10 +790,13 @@ def run_c5(args, rank, world, dev, barrier, max_over_ranks):
         pass
     bf16_peak = float(peaks.get("bf16_tflops", 1590.0)) * 1e12
     a = kits[:, 1:].abs().float()
-    joint = float(a.view(-1, 16, a.shape[1]).amax(1).clamp(min=2).sum().item())
+    rounds = -(-B // (128 * 148))
+    rpc = min(128, max(32, -(-(-(-B // (rounds * 148))) // 32) * 32))      # one row per rod (csrc/kc_knode_tc.cu: tc_fwd1_rpc)
+    joint = float(a.view(-1, rpc, a.shape[1]).amax(1).sum().item())
     k_exec = joint * (N - 1) * 2 * 128 * 32 * 512 * 2 * 3.0
-    if rank == 0:
-        print(json.dumps({
+    del kplan
+    torch.cuda.empty_cache()
+    return ({
             "metric": "rod-node-steps/sec", "value": world * rns / (ms * 1e-3), "unit": "rod-node-steps/s", "n_gpus": world,
             "steps": steps, "warmup": 2, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
@@ -787,11 +817,11 @@ def run_c5(args, rank, world, dev, barrier, max_over_ranks):
             "knode": {"metric": "KNODE rod-node-steps/sec", "value": world * rns / (kms * 1e-3), "unit": "rod-node-steps/s",
                       "ms_per_rollout": kms, "hidden": 512, "all_converged": bool(int(kits.min()) >= 0),
                       "marches_per_step_mean": float(a.mean().item()),
-                      "roofline": {"bound": "tensor", "kernel": "kc_knode_tc_fwd_kernel", "achieved": k_exec / (kms * 1e-3) / 1e12,
+                      "roofline": {"bound": "tensor", "kernel": "kc_knode_tc_fwd1_kernel (one row per rod, %d rods per CTA)" % rpc,
+                                   "achieved": k_exec / (kms * 1e-3) / 1e12,
                                    "peak": bf16_peak / 1e12, "unit": "TFLOP/s", "frac": k_exec / (kms * 1e-3) / bf16_peak,
-                                   "what": "executed tensor FLOP/s (8 rows per rod, 3 bf16 hi/lo passes)",
-                                   "useful_tflops": rns * E_REF * (N - 1) / N * (F_ODE + 106 * 512) / (kms * 1e-3) / 1e12}}}))
-    sys.stdout.flush()
+                                   "what": "executed tensor FLOP/s (128-row tiles, 3 bf16 hi/lo passes)",
+                                   "useful_tflops": rns * E_REF * (N - 1) / N * (F_ODE + 106 * 512) / (kms * 1e-3) / 1e12}}})
 
 
 if __name__ == "__main__":
