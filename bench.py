@@ -371,8 +371,9 @@ def main():
 
         def train_step(sync):
             # kc_train_step -> all-reduce of [gradients | loss] -> kc_adam_clamp_multi; one CUDA-graph launch per step
-            # from the third call on.  sync=True is the epoch of physics_train.py (:266-297): the loss is read back and
-            # ReduceLROnPlateau steps on it, every epoch; sync=False leaves the loss on the device (no scheduler).
+            # from the third call on.  ReduceLROnPlateau (physics_train.py:206,297) is stepped on every epoch's loss by a
+            # device kernel inside the same graph (kc_plateau_step); sync=True additionally reads the loss back to the
+            # host every step (what a caller that logs every epoch pays), sync=False leaves it on the device.
             trainer.fused_step(train=True, sync=sync)
 
         def time_train(sync):
@@ -387,8 +388,8 @@ def main():
             barrier()
             return max_over_ranks(e0.elapsed_time(e1)) / args.steps
 
-        tms_nosync = time_train(False)
-        tms = time_train(True)
+        tms = time_train(False)
+        tms_hostread = time_train(True)
         q = TRAIN_B * (TRAIN_T - 1) * len(TRAIN_KEYS)
         identical = None
         if world > 1:   # C4: every rank applied the same all-reduced gradient -> weights bitwise identical on all ranks
@@ -399,8 +400,10 @@ def main():
             identical = bool(torch.equal(wlo, whi))
         train = {"metric": "KNODE train steps/sec", "value": 1e3 / tms, "unit": "steps/s", "ms_per_step": tms,
                  "global_batch_trajectories": TRAIN_B, "samples_per_step": q, "scaling": "strong",
-                 "semantics": "teacher-forced (physics_train.py), fwd+loss+bwd+allreduce+Adam+clamp through "
-                              "_train.TeacherForcedTrainer.fused_step (CUDA graph: %s)" % (trainer.graph is not None),
+                 "semantics": "teacher-forced (physics_train.py), fwd+loss+bwd+allreduce+Adam+clamp+plateau scheduler through "
+                              "_train.TeacherForcedTrainer.fused_step (CUDA graph: %s; all-reduce: %s)"
+                              % (trainer.graph is not None, "peer memory, fused with Adam" if trainer.peer else
+                                 ("NCCL" if world > 1 else "none (1 GPU)")),
                  "useful_tflops": q * FLOP_PER_TRAIN_SAMPLE / (tms * 1e-3) / 1e12, "hidden": TRAIN_H,
                  "roofline": {"bound": "tensor", "kernel": "kc_train_tc_kernel (tcgen05 + TMEM; 80 % of the step)",
                               "achieved": q * FLOP_PER_TRAIN_SAMPLE / world / (tms * 1e-3) / 1e12, "unit": "TFLOP/s",
@@ -408,10 +411,11 @@ def main():
                                       "8d); every contraction runs 3 tensor-core passes (tf32 / bf16 hi-lo split) to keep "
                                       "fp32 accuracy, so the executed tensor FLOP/s are 3x this",
                               "frac_of_fp32_fma_peak": None, "frac_of_bf16_tensor_peak_executed": None},
-                 "loss": float(trainer.plan.flat[-1].item()), "kernels_per_step": 4 + 1 + 1,
-                 "scheduler": "ReduceLROnPlateau stepped on the loss read back every step (physics_train.py:206,297)",
-                 "train_nosync": {"value": 1e3 / tms_nosync, "unit": "steps/s", "ms_per_step": tms_nosync,
-                                  "note": "same step without the host read of the loss (no scheduler step)"},
+                 "loss": float(trainer.plan.flat[-1].item()), "kernels_per_step": 4 + (2 if trainer.peer else 1) + 1,
+                 "scheduler": "ReduceLROnPlateau(patience 80, factor 0.5) stepped on every epoch's loss by kc_plateau_step inside "
+                              "the captured step (physics_train.py:206,297); learning rate now %g" % trainer.sched.get_last_lr()[0],
+                 "train_hostread": {"value": 1e3 / tms_hostread, "unit": "steps/s", "ms_per_step": tms_hostread,
+                                    "note": "same step plus a host read of the loss after every step (loss logging every epoch)"},
                  "weights_bitwise_identical_across_ranks": identical}
 
     # ---------------- the same training step, weak scaling: 1024 trajectories PER GPU (global batch grows with N) -------

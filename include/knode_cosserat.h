@@ -209,6 +209,12 @@ int kc_adam_clamp_multi(int dtype, int32_t n_tensors, const kc_adam_tensor *tens
                         const double *lr_dev, double beta1, double beta2, double eps, double weight_decay,
                         int32_t *ticket_dev, void *stream);
 
+/* torch.optim.lr_scheduler.ReduceLROnPlateau('min', patience, factor) (physics_train.py:206,297) on the device:
+ * *loss_dev (dtype of the call) is this epoch's loss; state_dev[6] = {best (init +inf), bad epochs (init 0), patience, factor,
+ * relative threshold (1e-4), eps (1e-8)}; *lr_dev is the learning rate the optimiser kernels read.  Launch it after the
+ * optimiser; it needs no host synchronisation, so a captured training step keeps its scheduler. */
+int kc_plateau_step(int dtype, const void *loss_dev, double *state_dev, double *lr_dev, void *stream);
+
 /* The gradient all-reduce of the training step (an all-reduce(sum) of the flat [gW1|gb1|gW2|gb2|loss] buffer, the
  * only collective of the path) fused with the optimiser, over NVLink peer memory instead of a collective library call:
  * regions_host[world] = device-visible pointers to every rank's region of kc_peer_region_bytes() bytes of symmetric

@@ -81,6 +81,7 @@ _SIGNATURES = {
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "kc_rollout_loss": (C.c_int, [C.c_int, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.c_void_p,
                                   C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "kc_plateau_step": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "kc_peer_region_bytes": (C.c_int64, [C.c_int, C.c_int64]),
     "kc_peer_publish": (C.c_int, [C.c_int, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_void_p]),

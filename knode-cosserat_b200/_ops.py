@@ -568,6 +568,41 @@ def eval_metrics(pred, ref, node=None, want_mse=True):
     return dtw, mse
 
 
+class PlateauDevice:
+    """kc_plateau_step: ReduceLROnPlateau('min', patience, factor) with its state and the learning rate on the device."""
+
+    def __init__(self, lr_dev, patience=80, factor=0.5, threshold=1e-4, eps=1e-8):
+        self.lr_dev = lr_dev
+        self.state = torch.tensor([float("inf"), 0.0, float(patience), float(factor), float(threshold), float(eps)],
+                                  dtype=torch.float64, device=lr_dev.device)
+
+    def run(self, loss_elem):
+        """loss_elem: a one-element device tensor (fp32 or fp64) holding this epoch's loss."""
+        with torch.cuda.device(self.lr_dev.device):
+            rc = _kc.lib().kc_plateau_step(_DT[loss_elem.dtype], loss_elem.data_ptr(), _ptr(self.state), _ptr(self.lr_dev),
+                                           _stream(self.lr_dev.device))
+        _kc.check(rc, "kc_plateau_step")
+
+    def get_last_lr(self):
+        return [float(self.lr_dev.item())]
+
+    @property
+    def lr(self):
+        return float(self.lr_dev.item())
+
+    @lr.setter
+    def lr(self, value):               # a manual change of the learning rate reaches the (captured) optimiser kernels
+        self.lr_dev.fill_(float(value))
+
+    @property
+    def best(self):
+        return float(self.state[0].item())
+
+    @property
+    def bad(self):
+        return int(self.state[1].item())
+
+
 def fma_peak(dtype, iters, device):
     """Measured FP32/FP64 FMA-pipe throughput in FLOP/s (CUDA-event timed), used as the rollout's roofline peak."""
     code = _DT[dtype]

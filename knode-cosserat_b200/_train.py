@@ -86,6 +86,12 @@ class TeacherForcedTrainer:
         self._lr_on_device = self.sched.get_last_lr()[0]
         self.graph = None
         self._eager_fused_steps = 0
+        # ReduceLROnPlateau on the device (kc_plateau_step), stepped inside the graph on every epoch's loss: the host
+        # scheduler object is replaced by a view of the device state
+        self.device_sched = _ops.PlateauDevice(self.adam.lr_dev, patience=self.sched.patience, factor=self.sched.factor)
+        self.device_sched.state[0] = self.sched.best
+        self.device_sched.state[1] = float(self.sched.bad)
+        self.sched = self.device_sched
         # the all-reduce fused with the update over NVLink peer memory (kc_peer_publish / kc_peer_gather_adam);
         # KC_PEER_ALLREDUCE=0 keeps the NCCL all-reduce + kc_adam_clamp_multi
         self.peer = False
@@ -96,17 +102,20 @@ class TeacherForcedTrainer:
         self.plan.run()
         if train and self.peer:
             self.adam.run_peer()                     # publish -> wait for all ranks -> sum in rank order -> Adam + clamp
-            return
-        if self.world > 1:
-            dist.all_reduce(self.plan.flat)          # the only collective: gradients + loss, one launch
+        else:
+            if self.world > 1:
+                dist.all_reduce(self.plan.flat)      # the only collective: gradients + loss, one launch
+            if train:
+                self.adam.run()
         if train:
-            self.adam.run()
+            self.device_sched.run(self.plan.flat[-1:])   # scheduler.step(loss) (physics_train.py:297), on the device
 
     def fused_step(self, train=True, sync=True):
         """The same epoch as `step` with nothing but kernel launches on the critical path: outputs and workspace are
-        allocated once, Adam runs as one launch with its step count / learning rate on the device, and from the third
-        call on the whole step (kernels + NCCL all-reduce + Adam) is ONE CUDA-graph launch.  sync=False skips the host
-        read of the loss (the plateau scheduler then sees no new value for this epoch)."""
+        allocated once, Adam runs as one launch with its step count / learning rate on the device, ReduceLROnPlateau is a
+        device kernel too (kc_plateau_step), and from the third call on the whole step (kernels + all-reduce + Adam +
+        scheduler) is ONE CUDA-graph launch.  sync=False skips the host read of the loss (loss_arr then misses this epoch;
+        the scheduler has seen it all the same)."""
         if not hasattr(self, "plan"):
             self._fused_setup()
         P = self.robot._params()
@@ -114,10 +123,6 @@ class TeacherForcedTrainer:
             self.plan.P = P
             self.graph = None
             self._eager_fused_steps = 0
-        lr = self.sched.get_last_lr()[0]
-        if lr != self._lr_on_device:
-            self.adam.set_lr(lr)
-            self._lr_on_device = lr
         if not train:
             self._fused_body(False)
         elif self.graph is not None:
@@ -147,8 +152,6 @@ class TeacherForcedTrainer:
             return None
         loss_val = float(self.plan.flat[-1].item())
         self.loss_arr.append(loss_val)
-        if train:
-            self.sched.step(loss_val)
         return loss_val
 
     def close(self):

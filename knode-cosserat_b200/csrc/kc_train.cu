@@ -826,4 +826,34 @@ extern "C" int kc_peer_gather_adam(int dtype, int32_t world, int32_t rank, void*
     return KC_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// torch.optim.lr_scheduler.ReduceLROnPlateau('min', patience, factor) with its defaults (relative threshold, cooldown 0,
+// min_lr 0) on the DEVICE — physics_train.py:206,297 steps it on the epoch loss every epoch.  state[6] = {best, bad epochs,
+// patience, factor, threshold, eps}; *lr_dev is the learning rate kc_adam_clamp_multi / kc_peer_gather_adam read at their
+// next launch.  One thread; launched after the optimiser inside the training step's CUDA graph, so the scheduler runs
+// every step without a host read of the loss.
+template <typename T>
+__global__ void kc_plateau_step_kernel(const T* __restrict__ loss, double* __restrict__ state, double* __restrict__ lr) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const double metric = (double)*loss;
+    double best = state[0], bad = state[1];
+    if (metric < best * (1.0 - state[4])) { best = metric; bad = 0.0; }
+    else bad += 1.0;
+    if (bad > state[2]) {
+        const double old_lr = *lr, new_lr = old_lr * state[3];
+        if (old_lr - new_lr > state[5]) *lr = new_lr;
+        bad = 0.0;
+    }
+    state[0] = best; state[1] = bad;
+}
+extern "C" int kc_plateau_step(int dtype, const void* loss_dev, double* state_dev, double* lr_dev, void* stream) {
+    KC_CHECK_ARG(dtype == KC_F32 || dtype == KC_F64, "dtype must be KC_F32 or KC_F64");
+    KC_CHECK_ARG(loss_dev && state_dev && lr_dev, "NULL pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == KC_F32) kc_plateau_step_kernel<float><<<1, 32, 0, st>>>((const float*)loss_dev, state_dev, lr_dev);
+    else kc_plateau_step_kernel<double><<<1, 32, 0, st>>>((const double*)loss_dev, state_dev, lr_dev);
+    KC_CHECK_LAUNCH("kc_plateau_step_kernel");
+    return KC_OK;
+}
+
 #include "kc_ode_bwd.inl"

@@ -437,3 +437,42 @@ def test_peer_allreduce_adam_emulated_ranks(dt):
             assert int(adam.step_dev.item()) == step + 1
             for p, q in zip(params, ref_params):
                 assert torch.equal(p, q)
+
+
+def test_device_plateau_scheduler_matches_torch():
+    """kc_plateau_step (ReduceLROnPlateau on the device, stepped inside the captured training step) against
+    torch.optim.lr_scheduler.ReduceLROnPlateau on a loss sequence with plateaus (physics_train.py:206,297)."""
+    import _ops
+    rng = np.random.default_rng(0)
+    losses = np.concatenate([np.linspace(1, 0.5, 20), 0.5 + 0.01 * rng.random(40), np.linspace(0.5, 0.4, 5),
+                             0.4 + 0.01 * rng.random(30)]).astype(np.float32)
+    p = torch.nn.Parameter(torch.zeros(1))
+    opt = torch.optim.Adam([p], lr=1e-2)
+    ref = torch.optim.lr_scheduler.ReduceLROnPlateau(opt, 'min', patience=7, factor=0.5)
+    lr_dev = torch.full((1,), 1e-2, dtype=torch.float64, device="cuda")
+    dev = _ops.PlateauDevice(lr_dev, patience=7, factor=0.5)
+    ld = torch.tensor(losses, device="cuda")
+    for i, l in enumerate(losses):
+        ref.step(float(l))
+        dev.run(ld[i:i + 1])
+        assert abs(dev.get_last_lr()[0] - opt.param_groups[0]["lr"]) < 1e-15, i
+    assert dev.get_last_lr()[0] < 1e-2
+
+
+def test_fused_trainer_runs_the_scheduler_on_the_device(golden):
+    """TeacherForcedTrainer.fused_step(sync=False) steps ReduceLROnPlateau inside the step: with patience 0 and a loss
+    that cannot improve every step, the learning rate on the device halves without any host read."""
+    from _train import TeacherForcedTrainer
+    from cosserat_ode_torch import CosseratRodTorch
+    from knode import setup_robot
+    d = golden["train"]
+    torch.manual_seed(0)
+    r = CosseratRodTorch("cuda", 32)
+    setup_robot(r)
+    traj = torch.tensor(d["traj"], dtype=torch.float32, device="cuda")
+    ctl = torch.tensor(d["controls"], dtype=torch.float32, device="cuda")
+    tr = TeacherForcedTrainer(r, traj, ctl, [3, 5, 7, 9], lr=0.5, patience=0, factor=0.5)   # a step size that overshoots
+    for _ in range(12):
+        tr.fused_step(train=True, sync=False)
+    assert tr.sched.get_last_lr()[0] < 0.5
+    assert tr.loss_arr == []
