@@ -456,10 +456,10 @@ static int train_typed(const kc_rod_params* Pp, const kc_mlp* mlp, int64_t B, in
         if (use_tc) {
             float* tcw = (float*)(ws + w.tcw);
             tc_slices = kc_train_tc_grid(Q);
-            // KC_TRAIN_TC=2 selects the second-generation kernel (warp-specialised pipeline, kc_train_tc2.cu)
+            // second-generation kernel (warp-specialised pipeline, kc_train_tc2.cu) unless KC_TRAIN_TC=1
             const char* gen = getenv("KC_TRAIN_TC");
             int rc2;
-            if (!(gen && gen[0] == '2'))
+            if (gen && gen[0] == '1')
                 rc2 = kc_train_tc_launch(mlp, (float)P.ds, Q, (int)T_, K, (const float*)X, (const float*)PHYS, (const float*)TGT,
                                          tcw, tcw + 4 * 2 * 128 * 32, (float*)part, w.NP, lossp, (float*)pred, tc_slices, st);
             else
