@@ -3,10 +3,11 @@
 // warp-specialised pipeline so that the tensor pipe and the SIMT epilogues overlap (in kc_train_tc_kernel every stage was
 // MMA -> wait -> epilogue -> barrier -> MMA: 45 % of its warp samples sat in mbarrier waits, profiles/r02_ncu_prof_train_tc.csv).
 //
-// One persistent CTA per SM, tiles of 128 samples, hidden units in SUB-CHUNKS of 64.  320 threads:
-//   warps 0-7  epilogue: thread = sample row (tid & 127), half = tid >> 7 owns 32 of a sub-chunk's 64 units
-//   warp 8     MMA issue, warp-uniform (all lanes run the loop, the instruction is predicated on elect.sync)
-//   warp 9     weight loader: TMA bulk copies of the next sub-chunks' operand images into two 4-slot rings (W1 | W2 images:
+// One persistent CTA per SM, tiles of 128 samples, hidden units in SUB-CHUNKS of 64.  NG x 128 + 64 threads (NG = 4):
+//   warps 0..4NG-1  epilogue: thread = sample row (tid & 127), group = tid >> 7 owns 64/NG of a sub-chunk's 64 units (the
+//              epilogues are issue / latency bound: 16 warps instead of 8 hide the LDTM, MUFU and shared-store latencies)
+//   next warp  MMA issue, warp-uniform (all lanes run the loop, the instruction is predicated on elect.sync)
+//   last warp  weight loader: TMA bulk copies of the next sub-chunks' operand images into two 4-slot rings (W1 | W2 images:
 //              they are released at different times - W1 right after the Z GEMM, issued three sub-chunks ahead)
 // TMEM (512 columns): gW1 accumulators 0..127 (32 per 128-unit chunk), gW2^T 128..255, working area 256..511:
 //   forward : ring of three 64-column Z buffers (256, 320, 384) and O at 448..479
@@ -24,10 +25,11 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include "kc_rod.cuh"
+#include <cstdlib>
 #include "kc_umma.cuh"
 
 namespace tc2 {
-constexpr int THREADS = 320, STAGES = 4;
+constexpr int STAGES = 4;
 constexpr int OFF_X = 0;            // X^T hi | lo, bf16 MN-major [32 inputs x 128 samples]   2 x 8192
 constexpr int OFF_DO = 16384;       // dO^T hi | lo, bf16 MN-major [32 outputs x 128 samples] 2 x 8192
 constexpr int OFF_DZ = 32768;       // dZ^T hi | lo, bf16 MN-major [128 units x 128 samples]  2 x 32768
@@ -98,7 +100,9 @@ __global__ void kc_tc2_prep_weights_kernel(const float* __restrict__ W1, const f
     }
 }
 
-__global__ void __launch_bounds__(tc2::THREADS, 1)
+// NG = epilogue warp groups (each = 4 warps covering the 128 rows); a thread owns 64 / NG units of every sub-chunk.
+template <int NG>
+__global__ void __launch_bounds__(NG * 128 + 64, 1)
 kc_train_tc2_kernel(int hidden, int nsub, const unsigned char* __restrict__ img, const float* __restrict__ b2, float ds, int64_t Q,
                     int T_, int K, const float* __restrict__ X, const float* __restrict__ PHYS, const float* __restrict__ TGT,
                     float* __restrict__ partial, int64_t NP, double* __restrict__ loss_part, float* __restrict__ pred_out) {
@@ -112,11 +116,12 @@ kc_train_tc2_kernel(int hidden, int nsub, const unsigned char* __restrict__ img,
             umma::mbar_init(&bars->w1full[i], 1); umma::mbar_init(&bars->w1free[i], 1);
             umma::mbar_init(&bars->w2full[i], 1); umma::mbar_init(&bars->w2free[i], 1);
         }
-        umma::mbar_init(&bars->xrdy, 256); umma::mbar_init(&bars->ordy, 1); umma::mbar_init(&bars->dordy, 256);
+        constexpr int NE = NG * 128;   // epilogue threads
+        umma::mbar_init(&bars->xrdy, NE); umma::mbar_init(&bars->ordy, 1); umma::mbar_init(&bars->dordy, NE);
         umma::mbar_init(&bars->gdone, 1);
-        for (int i = 0; i < 4; ++i) umma::mbar_init(&bars->tile_rdy[i], 256);
-        for (int i = 0; i < 3; ++i) { umma::mbar_init(&bars->zf_rdy[i], 1); umma::mbar_init(&bars->zf_used[i], 256); }
-        for (int i = 0; i < 2; ++i) { umma::mbar_init(&bars->zb_rdy[i], 1); umma::mbar_init(&bars->zb_used[i], 256); }
+        for (int i = 0; i < 4; ++i) umma::mbar_init(&bars->tile_rdy[i], NE);
+        for (int i = 0; i < 3; ++i) { umma::mbar_init(&bars->zf_rdy[i], 1); umma::mbar_init(&bars->zf_used[i], NE); }
+        for (int i = 0; i < 2; ++i) { umma::mbar_init(&bars->zb_rdy[i], 1); umma::mbar_init(&bars->zb_used[i], NE); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     umma::fence_async_smem();
@@ -128,7 +133,8 @@ kc_train_tc2_kernel(int hidden, int nsub, const unsigned char* __restrict__ img,
     const int64_t my_tiles = ntiles > blockIdx.x ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const int npair = nsub / 2;
 
-    if (warp == 9) {
+    constexpr int CPT = 64 / NG;          // units (TMEM columns) of a sub-chunk per epilogue thread
+    if (warp == NG * 4 + 1) {
         // ---- weight loader: unit u of a ring = sub-chunk-stage u (per tile: nsub forward stages, then nsub backward stages);
         // lane 0 feeds the W1 ring (the same image in both phases), lane 1 the W2 ring (forward image / W2^T) ----
         const int64_t total = my_tiles * 2 * nsub;
@@ -145,7 +151,7 @@ kc_train_tc2_kernel(int hidden, int nsub, const unsigned char* __restrict__ img,
                 bulk_g2s(umma::smem_u32(sm + ring + slot * 8192), src, 8192, &full[slot]);
             }
         }
-    } else if (warp == 8) {
+    } else if (warp == NG * 4) {
         // ---- MMA issue ----
         const uint32_t idZ = umma::make_idesc_bf16(128, 64), idO = umma::make_idesc_bf16(128, 32);
         const uint32_t idG = umma::make_idesc_bf16(128, 32, 1, 1);
@@ -193,7 +199,8 @@ kc_train_tc2_kernel(int hidden, int nsub, const unsigned char* __restrict__ img,
                 for (int p = 0; p < 3; ++p) {
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk) {
-                        const uint32_t a = ab + (kk >> 1) * 32 + (kk & 1) * 8 + (p == 1 ? 16 : 0);
+                        // 16-unit group kk lives in the column block of the thread group that owns it: hi | lo halves
+                        const uint32_t a = ab + (kk / (CPT / 16)) * CPT + (kk % (CPT / 16)) * 8 + (p == 1 ? CPT / 2 : 0);
                         umma::mma_bf16_ts_w(tbase + COL_O, a, dstep(p == 2 ? wl : wh, kk * 256), idO, (s | p | kk) ? 1u : 0u);
                     }
                 }
@@ -247,7 +254,7 @@ kc_train_tc2_kernel(int hidden, int nsub, const unsigned char* __restrict__ img,
         }
     } else {
         // ---- epilogue warps ----
-        const int row = tid & 127, half = tid >> 7;
+        const int row = tid & 127, grp = tid >> 7;     // grp: which CPT-wide column block of every sub-chunk this thread owns
         const uint32_t laneblk = (uint32_t)((warp & 3) * 32) << 16;
         uint32_t phzf = 0, phzb = 0, pho = 0, phg = 0;
         float gb2acc[25];
@@ -265,19 +272,21 @@ kc_train_tc2_kernel(int hidden, int nsub, const unsigned char* __restrict__ img,
             }
             // ---- X tile: bf16 hi/lo, MN-major [32 inputs x 128 samples]; column 28 = 1 carries b1 / yields gb1 ----
             {
-                float xv[16];
-                const float4* xs = reinterpret_cast<const float4*>(X + (size_t)(valid ? qrow : 0) * 32 + half * 16);
+                constexpr int IPT = 32 / NG;            // inputs per thread (16 or 8)
+                float xv[IPT];
+                const float4* xs = reinterpret_cast<const float4*>(X + (size_t)(valid ? qrow : 0) * 32 + grp * IPT);
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    const float4 v4 = (valid && !(half == 1 && g == 3)) ? xs[g] : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int g = 0; g < IPT / 4; ++g) {
+                    const int k0 = grp * IPT + 4 * g;   // columns 28..31 of X are never read from memory
+                    const float4 v4 = (valid && k0 < 28) ? xs[g] : make_float4(0.f, 0.f, 0.f, 0.f);
                     xv[4 * g] = v4.x; xv[4 * g + 1] = v4.y; xv[4 * g + 2] = v4.z; xv[4 * g + 3] = v4.w;
                 }
-                if (half == 1) { xv[12] = valid ? 1.f : 0.f; xv[13] = 0.f; xv[14] = 0.f; xv[15] = 0.f; }
+                if (grp == NG - 1) { xv[IPT - 4] = valid ? 1.f : 0.f; xv[IPT - 3] = 0.f; xv[IPT - 2] = 0.f; xv[IPT - 1] = 0.f; }
 #pragma unroll
-                for (int g = 0; g < 2; ++g) {
+                for (int g = 0; g < IPT / 8; ++g) {
                     uint4 hi, lo;
                     split8(xv + 8 * g, hi, lo);
-                    const uint32_t o = umma::mnmajor_off_b16(half * 16 + 8 * g, row, 128);
+                    const uint32_t o = umma::mnmajor_off_b16(grp * IPT + 8 * g, row, 128);
                     *reinterpret_cast<uint4*>(sm + OFF_X + o) = hi;
                     *reinterpret_cast<uint4*>(sm + OFF_X + 8192 + o) = lo;
                 }
@@ -289,22 +298,22 @@ kc_train_tc2_kernel(int hidden, int nsub, const unsigned char* __restrict__ img,
                 const int b = s % 3;
                 umma::mbar_wait(&bars->zf_rdy[b], (phzf >> b) & 1u); phzf ^= 1u << b;
                 umma::fence_after();
-                const uint32_t ta = tbase + laneblk + COL_W + b * 64 + half * 32;
-                uint32_t z[32], hi[16], lo[16];
-                umma::ld32(ta, z);
+                const uint32_t ta = tbase + laneblk + COL_W + b * 64 + grp * CPT;
+                uint32_t z[CPT], hi[CPT / 2], lo[CPT / 2];
+                if (CPT == 32) umma::ld32(ta, z); else umma::ld16(ta, z);
                 umma::wait_ld();
 #pragma unroll
-                for (int i = 0; i < 16; ++i) split_pair(kc_elu(__uint_as_float(z[2 * i])), kc_elu(__uint_as_float(z[2 * i + 1])), hi[i], lo[i]);
-                umma::st16(ta, hi);
-                umma::st16(ta + 16, lo);
+                for (int i = 0; i < CPT / 2; ++i) split_pair(kc_elu(__uint_as_float(z[2 * i])), kc_elu(__uint_as_float(z[2 * i + 1])), hi[i], lo[i]);
+                if (CPT == 32) { umma::st16(ta, hi); umma::st16(ta + 16, lo); }
+                else { umma::st8(ta, hi); umma::st8(ta + 8, lo); }
                 umma::wait_st();
                 umma::fence_before();
                 umma::mbar_arrive(&bars->zf_used[b]);
             }
-            // ---- loss and dL/do (rows of half 0) ----
+            // ---- loss and dL/do (the threads of group 0 own the sample) ----
             umma::mbar_wait(&bars->ordy, pho); pho ^= 1;
             umma::fence_after();
-            if (half == 0) {
+            if (grp == 0) {
                 float o[25], g[25];
                 {
                     uint32_t v[32];
@@ -369,10 +378,10 @@ kc_train_tc2_kernel(int hidden, int nsub, const unsigned char* __restrict__ img,
                 const int b = s & 1;
                 umma::mbar_wait(&bars->zb_rdy[b], (phzb >> b) & 1u); phzb ^= 1u << b;
                 umma::fence_after();
-                const uint32_t ta = tbase + laneblk + COL_W + b * 128 + half * 32;
-                uint32_t z[32], d[32];
-                umma::ld32(ta, z);
-                umma::ld32(ta + 64, d);
+                const uint32_t ta = tbase + laneblk + COL_W + b * 128 + grp * CPT;
+                uint32_t z[CPT], d[CPT];
+                if (CPT == 32) { umma::ld32(ta, z); umma::ld32(ta + 64, d); }
+                else { umma::ld16(ta, z); umma::ld16(ta + 64, d); }
                 umma::wait_ld();
                 umma::fence_before();
                 umma::mbar_arrive(&bars->zb_used[b]);                  // the buffer may be refilled while this thread computes
@@ -381,9 +390,9 @@ kc_train_tc2_kernel(int hidden, int nsub, const unsigned char* __restrict__ img,
                     umma::mbar_wait(&bars->gdone, phg); phg ^= 1;
                     ++pairs_done;
                 }
-                const int u0 = (s & 1) * 64 + half * 32;
+                const int u0 = (s & 1) * 64 + grp * CPT;
 #pragma unroll
-                for (int g8 = 0; g8 < 4; ++g8) {
+                for (int g8 = 0; g8 < CPT / 8; ++g8) {
                     float a8[8], d8[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
@@ -415,8 +424,8 @@ kc_train_tc2_kernel(int hidden, int nsub, const unsigned char* __restrict__ img,
         float* out = partial + (size_t)blockIdx.x * NP;
         const int64_t ob1 = (int64_t)hidden * 28, oW2 = ob1 + hidden, ob2 = oW2 + (int64_t)25 * hidden;
         if (my_tiles == 0) {   // (grid <= ntiles, so this does not happen; keep the slice defined anyway)
-            for (int64_t i = tid; i < NP; i += 256) out[i] = 0.f;
-        } else if (half == 0) {
+            for (int64_t i = tid; i < NP; i += NG * 128) out[i] = 0.f;
+        } else if (grp == 0) {
             for (int c = 0; c < npair; ++c) {
                 const int u = c * 128 + row;
                 uint32_t v[32];
@@ -448,7 +457,7 @@ kc_train_tc2_kernel(int hidden, int nsub, const unsigned char* __restrict__ img,
             for (int o2 = 16; o2 > 0; o2 >>= 1) s += __shfl_down_sync(0xffffffffu, s, o2);
             if (lane == 0) bars->redd[warp] = s;
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(NG * 128) : "memory");
         if (tid < 25) out[ob2 + tid] = bars->redb[tid] + bars->redb[25 + tid] + bars->redb[50 + tid] + bars->redb[75 + tid];
         if (tid == 0) loss_part[blockIdx.x] = bars->redd[0] + bars->redd[1] + bars->redd[2] + bars->redd[3];
     }
@@ -465,9 +474,11 @@ int kc_train_tc2_launch(const kc_mlp* mlp, float ds, int64_t Q, int T_, int K, c
     kc_tc2_prep_weights_kernel<<<32, 256, 0, st>>>((const float*)mlp->W1, (const float*)mlp->b1, (const float*)mlp->W2,
                                                    mlp->hidden, img);
     KC_CHECK_LAUNCH("kc_tc2_prep_weights_kernel");
-    cudaFuncSetAttribute(kc_train_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES);
-    kc_train_tc2_kernel<<<grid, tc2::THREADS, tc2::SMEM_BYTES, st>>>(mlp->hidden, nsub, img, (const float*)mlp->b2, ds, Q, T_, K,
-                                                                    X, PHYS, TGT, partial, NP, loss_part, pred_out);
+    // two epilogue warp groups (8 epilogue warps, 32 units per thread).  The kernel is written over NG, but only NG = 2 is
+    // instantiated: a 16-warp variant (96 registers, spills) measured slower (0.254 vs 0.240 ms per kc_train_step at 1024x29).
+    cudaFuncSetAttribute(kc_train_tc2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES);
+    kc_train_tc2_kernel<2><<<grid, 2 * 128 + 64, tc2::SMEM_BYTES, st>>>(mlp->hidden, nsub, img, (const float*)mlp->b2, ds, Q, T_, K,
+                                                                      X, PHYS, TGT, partial, NP, loss_part, pred_out);
     KC_CHECK_LAUNCH("kc_train_tc2_kernel");
     return KC_OK;
 }
