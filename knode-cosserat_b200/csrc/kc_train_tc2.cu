@@ -3,9 +3,8 @@
 // warp-specialised pipeline so that the tensor pipe and the SIMT epilogues overlap (in kc_train_tc_kernel every stage was
 // MMA -> wait -> epilogue -> barrier -> MMA: 45 % of its warp samples sat in mbarrier waits, profiles/r02_ncu_prof_train_tc.csv).
 //
-// One persistent CTA per SM, tiles of 128 samples, hidden units in SUB-CHUNKS of 64.  NG x 128 + 64 threads (NG = 4):
-//   warps 0..4NG-1  epilogue: thread = sample row (tid & 127), group = tid >> 7 owns 64/NG of a sub-chunk's 64 units (the
-//              epilogues are issue / latency bound: 16 warps instead of 8 hide the LDTM, MUFU and shared-store latencies)
+// One persistent CTA per SM, tiles of 128 samples, hidden units in SUB-CHUNKS of 64.  NG x 128 + 64 threads (NG = 2 is built):
+//   warps 0..4NG-1  epilogue: thread = sample row (tid & 127), group = tid >> 7 owns 64/NG of a sub-chunk's 64 units
 //   next warp  MMA issue, warp-uniform (all lanes run the loop, the instruction is predicated on elect.sync)
 //   last warp  weight loader: TMA bulk copies of the next sub-chunks' operand images into two 4-slot rings (W1 | W2 images:
 //              they are released at different times - W1 right after the Z GEMM, issued three sub-chunks ahead)
@@ -27,6 +26,16 @@
 #include "kc_rod.cuh"
 #include <cstdlib>
 #include "kc_umma.cuh"
+
+// Development aid (make EXTRA=-DKC_TC2_TRACE): clock64 stamps of CTA 0's epilogue warps 0 / 4 and MMA warp, tools/trace_train_tc2.py.
+#ifdef KC_TC2_TRACE
+__device__ long long* g_tc2_trace = nullptr;
+extern "C" int kc_train_tc2_set_trace(long long* p) { return (int)cudaMemcpyToSymbol(g_tc2_trace, &p, sizeof(p)); }
+#define TC2_TR(id) do { if (tr_role >= 0 && lane == 0 && g_tc2_trace && tr_n < 2048)                                         \
+        g_tc2_trace[tr_role * 2048 + tr_n++] = ((long long)(id) << 48) | (clock64() & 0xffffffffffffll); } while (0)
+#else
+#define TC2_TR(id) do {} while (0)
+#endif
 
 namespace tc2 {
 constexpr int STAGES = 4;
@@ -132,6 +141,10 @@ kc_train_tc2_kernel(int hidden, int nsub, const unsigned char* __restrict__ img,
     const int64_t ntiles = (Q + 127) / 128;
     const int64_t my_tiles = ntiles > blockIdx.x ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const int npair = nsub / 2;
+#ifdef KC_TC2_TRACE
+    const int tr_role = blockIdx.x != 0 ? -1 : (warp == 0 ? 0 : (warp == 4 ? 1 : (warp == NG * 4 ? 2 : -1)));
+    int tr_n = 0;
+#endif
 
     constexpr int CPT = 64 / NG;          // units (TMEM columns) of a sub-chunk per epilogue thread
     if (warp == NG * 4 + 1) {
@@ -179,6 +192,7 @@ kc_train_tc2_kernel(int hidden, int nsub, const unsigned char* __restrict__ img,
             const bool first_tile = t == 0;
             umma::mbar_wait(&bars->xrdy, phx); phx ^= 1;
             umma::fence_after();
+            TC2_TR(100);
             // ---------------- forward ----------------
             auto fwd_gemm1 = [&](int s) {
                 const int slot = (int)((q + s) % STAGES);
@@ -192,6 +206,7 @@ kc_train_tc2_kernel(int hidden, int nsub, const unsigned char* __restrict__ img,
                 const int b = s % 3, slot = (int)((q + s) % STAGES);
                 umma::mbar_wait(&bars->zf_used[b], (phzfu >> b) & 1u); phzfu ^= 1u << b;
                 umma::fence_after();
+                TC2_TR(120 + s);
                 wait_w2(slot);
                 const uint64_t wh = umma::make_desc(umma::smem_u32(sm + OFF_W2 + slot * 8192), 128, 1024), wl = dstep(wh, 4096);
                 const uint32_t ab = tbase + COL_W + b * 64;
@@ -206,12 +221,14 @@ kc_train_tc2_kernel(int hidden, int nsub, const unsigned char* __restrict__ img,
                 }
                 umma::commit_w(&bars->w2free[slot]);
                 if (s + 3 < nsub) fwd_gemm1(s + 3);
+                TC2_TR(130 + s);
             }
             umma::commit_w(&bars->ordy);
             q += nsub;
             // ---------------- backward ----------------
             umma::mbar_wait(&bars->dordy, phdo); phdo ^= 1;
             umma::fence_after();
+            TC2_TR(140);
             auto bwd_gemm13 = [&](int s) {
                 const int slot = (int)((q + s) % STAGES);
                 wait_w1(slot);
@@ -228,9 +245,12 @@ kc_train_tc2_kernel(int hidden, int nsub, const unsigned char* __restrict__ img,
                 const int b = s & 1;
                 umma::mbar_wait(&bars->zb_used[b], (phzbu >> b) & 1u); phzbu ^= 1u << b;   // both Z and dA are in registers
                 umma::fence_after();
+                TC2_TR(150 + s);
                 if (s + 2 < nsub) bwd_gemm13(s + 2);
+                TC2_TR(160 + s);
                 umma::mbar_wait(&bars->tile_rdy[s & 3], (phtile >> (s & 3)) & 1u); phtile ^= 1u << (s & 3);   // a, dz of sub-chunk s are in shared memory
                 umma::fence_after();
+                TC2_TR(170 + s);
                 if (s & 1) {
                     const int c = s >> 1;
                     const uint32_t d1 = tbase + COL_GW1 + 32 * c, d2 = tbase + COL_GW2 + 32 * c;
@@ -248,6 +268,7 @@ kc_train_tc2_kernel(int hidden, int nsub, const unsigned char* __restrict__ img,
                         for (int kk = 0; kk < 8; ++kk) umma::mma_bf16_w(d2, dstep(a, kk * 256), dstep(bb, kk * 256), idG, (p | kk) ? 1u : acc0);
                     }
                     umma::commit_w(&bars->gdone);
+                    TC2_TR(180 + s);
                 }
             }
             q += nsub;
@@ -262,42 +283,46 @@ kc_train_tc2_kernel(int hidden, int nsub, const unsigned char* __restrict__ img,
         for (int c = 0; c < 25; ++c) gb2acc[c] = 0.f;
         double lossacc = 0.0;
         int64_t pairs_done = 0;      // gradient-GEMM completions consumed so far
+        constexpr int IPT = 32 / NG;            // inputs per thread (16 or 8)
+        float xv[IPT];
+        // this thread's slice of a sample's inputs (columns 28..31 of X are never read from memory; column 28 := 1)
+        auto load_x = [&](int64_t tile_) {
+            const int64_t qr = tile_ * 128 + row;
+            const bool ok = qr < Q;
+            const float4* xs = reinterpret_cast<const float4*>(X + (size_t)(ok ? qr : 0) * 32 + grp * IPT);
+#pragma unroll
+            for (int g = 0; g < IPT / 4; ++g) {
+                const int k0 = grp * IPT + 4 * g;
+                const float4 v4 = (ok && k0 < 28) ? xs[g] : make_float4(0.f, 0.f, 0.f, 0.f);
+                xv[4 * g] = v4.x; xv[4 * g + 1] = v4.y; xv[4 * g + 2] = v4.z; xv[4 * g + 3] = v4.w;
+            }
+            if (grp == NG - 1) { xv[IPT - 4] = ok ? 1.f : 0.f; xv[IPT - 3] = 0.f; xv[IPT - 2] = 0.f; xv[IPT - 1] = 0.f; }
+        };
+        if (my_tiles > 0) load_x(blockIdx.x);
         for (int64_t t = 0; t < my_tiles; ++t) {
             const int64_t tile = blockIdx.x + t * gridDim.x;
             const int64_t qrow = tile * 128 + row;
             const bool valid = qrow < Q;
-            // X and dO tiles are read by the gradient MMAs of the previous tile's last pair
-            if (t > 0 && npair > 0) {
-                // (the completion of the last pair has been consumed below only if npair > 1; wait for the outstanding one)
-            }
-            // ---- X tile: bf16 hi/lo, MN-major [32 inputs x 128 samples]; column 28 = 1 carries b1 / yields gb1 ----
-            {
-                constexpr int IPT = 32 / NG;            // inputs per thread (16 or 8)
-                float xv[IPT];
-                const float4* xs = reinterpret_cast<const float4*>(X + (size_t)(valid ? qrow : 0) * 32 + grp * IPT);
+            TC2_TR(0);
+            // ---- X tile: bf16 hi/lo, MN-major [32 inputs x 128 samples]; column 28 = 1 carries b1 / yields gb1 (xv was loaded
+            // before the previous tile's last gradient wait) ----
 #pragma unroll
-                for (int g = 0; g < IPT / 4; ++g) {
-                    const int k0 = grp * IPT + 4 * g;   // columns 28..31 of X are never read from memory
-                    const float4 v4 = (valid && k0 < 28) ? xs[g] : make_float4(0.f, 0.f, 0.f, 0.f);
-                    xv[4 * g] = v4.x; xv[4 * g + 1] = v4.y; xv[4 * g + 2] = v4.z; xv[4 * g + 3] = v4.w;
-                }
-                if (grp == NG - 1) { xv[IPT - 4] = valid ? 1.f : 0.f; xv[IPT - 3] = 0.f; xv[IPT - 2] = 0.f; xv[IPT - 1] = 0.f; }
-#pragma unroll
-                for (int g = 0; g < IPT / 8; ++g) {
-                    uint4 hi, lo;
-                    split8(xv + 8 * g, hi, lo);
-                    const uint32_t o = umma::mnmajor_off_b16(grp * IPT + 8 * g, row, 128);
-                    *reinterpret_cast<uint4*>(sm + OFF_X + o) = hi;
-                    *reinterpret_cast<uint4*>(sm + OFF_X + 8192 + o) = lo;
-                }
+            for (int g = 0; g < IPT / 8; ++g) {
+                uint4 hi, lo;
+                split8(xv + 8 * g, hi, lo);
+                const uint32_t o = umma::mnmajor_off_b16(grp * IPT + 8 * g, row, 128);
+                *reinterpret_cast<uint4*>(sm + OFF_X + o) = hi;
+                *reinterpret_cast<uint4*>(sm + OFF_X + 8192 + o) = lo;
             }
             umma::fence_async_smem();
             umma::mbar_arrive(&bars->xrdy);
+            TC2_TR(1);
             // ---- forward epilogues ----
             for (int s = 0; s < nsub; ++s) {
                 const int b = s % 3;
                 umma::mbar_wait(&bars->zf_rdy[b], (phzf >> b) & 1u); phzf ^= 1u << b;
                 umma::fence_after();
+                TC2_TR(10 + s);
                 const uint32_t ta = tbase + laneblk + COL_W + b * 64 + grp * CPT;
                 uint32_t z[CPT], hi[CPT / 2], lo[CPT / 2];
                 if (CPT == 32) umma::ld32(ta, z); else umma::ld16(ta, z);
@@ -309,10 +334,17 @@ kc_train_tc2_kernel(int hidden, int nsub, const unsigned char* __restrict__ img,
                 umma::wait_st();
                 umma::fence_before();
                 umma::mbar_arrive(&bars->zf_used[b]);
+                TC2_TR(20 + s);
             }
             // ---- loss and dL/do (the threads of group 0 own the sample) ----
+            float ph[25], tg[25];    // physics prediction and target of this sample: in flight while the last GEMM2 drains
+            if (grp == 0 && valid) {
+#pragma unroll
+                for (int r = 0; r < 25; ++r) { ph[r] = PHYS[(size_t)qrow * 25 + r]; tg[r] = TGT[(size_t)qrow * 25 + r]; }
+            }
             umma::mbar_wait(&bars->ordy, pho); pho ^= 1;
             umma::fence_after();
+            TC2_TR(30);
             if (grp == 0) {
                 float o[25], g[25];
                 {
@@ -323,13 +355,11 @@ kc_train_tc2_kernel(int hidden, int nsub, const unsigned char* __restrict__ img,
                     for (int c = 0; c < 25; ++c) { o[c] = __uint_as_float(v[c]) + b2[c]; g[c] = 0.f; }
                 }
                 if (valid) {
-                    float pred[25], tg[25];
+                    float pred[25];
 #pragma unroll
-                    for (int r = 0; r < 19; ++r) pred[r] = PHYS[(size_t)qrow * 25 + r] + ds * o[r];
+                    for (int r = 0; r < 19; ++r) pred[r] = ph[r] + ds * o[r];
 #pragma unroll
-                    for (int c = 19; c < 25; ++c) pred[c] = PHYS[(size_t)qrow * 25 + c] + o[c];
-#pragma unroll
-                    for (int r = 0; r < 25; ++r) tg[r] = TGT[(size_t)qrow * 25 + r];
+                    for (int c = 19; c < 25; ++c) pred[c] = ph[c] + o[c];
                     const float S = float(T_ - 1);
                     const float wp = 1.f / (float(3 * K) * S), wf = 1.f / (float(12 * K) * S), wz = 1.f / (float(6 * K) * S);
                     float acc = 0.f;
@@ -373,11 +403,13 @@ kc_train_tc2_kernel(int hidden, int nsub, const unsigned char* __restrict__ img,
             umma::fence_async_smem();
             umma::fence_before();
             umma::mbar_arrive(&bars->dordy);
+            TC2_TR(31);
             // ---- backward epilogues ----
             for (int s = 0; s < nsub; ++s) {
                 const int b = s & 1;
                 umma::mbar_wait(&bars->zb_rdy[b], (phzb >> b) & 1u); phzb ^= 1u << b;
                 umma::fence_after();
+                TC2_TR(40 + s);
                 const uint32_t ta = tbase + laneblk + COL_W + b * 128 + grp * CPT;
                 uint32_t z[CPT], d[CPT];
                 if (CPT == 32) { umma::ld32(ta, z); umma::ld32(ta + 64, d); }
@@ -385,12 +417,9 @@ kc_train_tc2_kernel(int hidden, int nsub, const unsigned char* __restrict__ img,
                 umma::wait_ld();
                 umma::fence_before();
                 umma::mbar_arrive(&bars->zb_used[b]);                  // the buffer may be refilled while this thread computes
-                // the shared tiles of this pair must be free: the gradient MMAs of the previous pair are done
-                if ((s & 1) == 0 && pairs_done < t * npair + (s >> 1)) {
-                    umma::mbar_wait(&bars->gdone, phg); phg ^= 1;
-                    ++pairs_done;
-                }
-                const int u0 = (s & 1) * 64 + grp * CPT;
+                TC2_TR(50 + s);
+                // a = ELU(z), dz = dA ELU'(z) as bf16 hi/lo, held in registers ...
+                uint4 ah[CPT / 8], al[CPT / 8], dh[CPT / 8], dl[CPT / 8];
 #pragma unroll
                 for (int g8 = 0; g8 < CPT / 8; ++g8) {
                     float a8[8], d8[8];
@@ -401,24 +430,39 @@ kc_train_tc2_kernel(int hidden, int nsub, const unsigned char* __restrict__ img,
                         a8[j] = a;
                         d8[j] = __uint_as_float(d[g8 * 8 + j]) * (zz > 0.f ? 1.f : a + 1.f);   // ELU'(z) = e^z = ELU(z) + 1
                     }
-                    uint4 ah, al, dh, dl;
-                    split8(a8, ah, al);
-                    split8(d8, dh, dl);
+                    split8(a8, ah[g8], al[g8]);
+                    split8(d8, dh[g8], dl[g8]);
+                }
+                TC2_TR(60 + s);
+                // ... until the shared tiles of this pair are free: the gradient MMAs of the previous pair are done (they were
+                // issued when the previous sub-chunk was stored; the arithmetic above ran while they executed)
+                if ((s & 1) == 0 && pairs_done < t * npair + (s >> 1)) {
+                    umma::mbar_wait(&bars->gdone, phg); phg ^= 1;
+                    ++pairs_done;
+                }
+                TC2_TR(70 + s);
+                const int u0 = (s & 1) * 64 + grp * CPT;
+#pragma unroll
+                for (int g8 = 0; g8 < CPT / 8; ++g8) {
                     const uint32_t off = umma::mnmajor_off_b16(u0 + g8 * 8, row, 128);
-                    *reinterpret_cast<uint4*>(sm + OFF_A + off) = ah;
-                    *reinterpret_cast<uint4*>(sm + OFF_A + 32768 + off) = al;
-                    *reinterpret_cast<uint4*>(sm + OFF_DZ + off) = dh;
-                    *reinterpret_cast<uint4*>(sm + OFF_DZ + 32768 + off) = dl;
+                    *reinterpret_cast<uint4*>(sm + OFF_A + off) = ah[g8];
+                    *reinterpret_cast<uint4*>(sm + OFF_A + 32768 + off) = al[g8];
+                    *reinterpret_cast<uint4*>(sm + OFF_DZ + off) = dh[g8];
+                    *reinterpret_cast<uint4*>(sm + OFF_DZ + 32768 + off) = dl[g8];
                 }
                 umma::fence_async_smem();
                 umma::mbar_arrive(&bars->tile_rdy[s & 3]);
+                TC2_TR(80 + s);
             }
-            // X / dO of the next tile overwrite what the last pair's gradient MMAs read: consume its completion now
+            // X / dO of the next tile overwrite what the last pair's gradient MMAs read: consume its completion now (the next
+            // tile's inputs are fetched into registers first: their latency hides behind this wait)
+            if (t + 1 < my_tiles) load_x(tile + gridDim.x);
             while (pairs_done < (t + 1) * npair) {
                 umma::mbar_wait(&bars->gdone, phg); phg ^= 1;
                 ++pairs_done;
             }
             umma::fence_after();
+            TC2_TR(90);
         }
         // ---- this CTA's partial gradients ----
         float* out = partial + (size_t)blockIdx.x * NP;
