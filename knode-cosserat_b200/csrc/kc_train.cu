@@ -24,6 +24,9 @@ int kc_train_tc_grid(int64_t Q);
 int kc_train_tc2_launch(const kc_mlp* mlp, float ds, int64_t Q, int T_, int K, const float* X, const float* PHYS, const float* TGT,
                         unsigned char* img, float* partial, int64_t NP, double* loss_part, float* pred_out, int grid,
                         cudaStream_t st);
+int kc_train_tc3_launch(const kc_mlp* mlp, float ds, int64_t Q, int T_, int K, const float* X, const float* PHYS, const float* TGT,
+                        unsigned char* img, float* partial, int64_t NP, double* loss_part, float* pred_out, int grid,
+                        cudaStream_t st);
 int kc_train_tc_launch(const kc_mlp* mlp, float ds, int64_t Q, int T_, int K, const float* X, const float* PHYS,
                        const float* TGT, float* W1hl, float* W2c, float* partial, int64_t NP, double* loss_part,
                        float* pred_out, int grid, cudaStream_t st);
@@ -456,14 +459,18 @@ static int train_typed(const kc_rod_params* Pp, const kc_mlp* mlp, int64_t B, in
         if (use_tc) {
             float* tcw = (float*)(ws + w.tcw);
             tc_slices = kc_train_tc_grid(Q);
-            // second-generation kernel (warp-specialised pipeline, kc_train_tc2.cu) unless KC_TRAIN_TC=1
+            // third-generation kernel (kc_train_tc3.cu: transposed backward, activations stay in TMEM) unless KC_TRAIN_TC=2
+            // (warp-specialised pipeline with shared-memory activation tiles, kc_train_tc2.cu) or =1 (kc_train_tc.cu)
             const char* gen = getenv("KC_TRAIN_TC");
             int rc2;
             if (gen && gen[0] == '1')
                 rc2 = kc_train_tc_launch(mlp, (float)P.ds, Q, (int)T_, K, (const float*)X, (const float*)PHYS, (const float*)TGT,
                                          tcw, tcw + 4 * 2 * 128 * 32, (float*)part, w.NP, lossp, (float*)pred, tc_slices, st);
-            else
+            else if (gen && gen[0] == '2')
                 rc2 = kc_train_tc2_launch(mlp, (float)P.ds, Q, (int)T_, K, (const float*)X, (const float*)PHYS, (const float*)TGT,
+                                          (unsigned char*)tcw, (float*)part, w.NP, lossp, (float*)pred, tc_slices, st);
+            else
+                rc2 = kc_train_tc3_launch(mlp, (float)P.ds, Q, (int)T_, K, (const float*)X, (const float*)PHYS, (const float*)TGT,
                                           (unsigned char*)tcw, (float*)part, w.NP, lossp, (float*)pred, tc_slices, st);
             if (rc2) return rc2;
         } else {
