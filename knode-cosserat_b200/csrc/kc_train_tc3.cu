@@ -156,12 +156,7 @@ kc_train_tc3_kernel(int hidden, int nsub, const unsigned char* __restrict__ img,
         uint32_t phx = 0, phdo = 0, phzfu = 0, phzbd = 0;
         // D[128 x 64] = A[128 x 32] * B[64 x 32]^T, both K-major with 16 inputs per instruction, 3 passes (hi hi, lo hi, hi lo)
         auto gemm_k32 = [&](uint32_t d, uint64_t ah, uint64_t al, uint32_t astep, uint64_t bh, uint64_t bl, uint32_t bstep) {
-#pragma unroll
-            for (int p = 0; p < 3; ++p) {
-                const uint64_t a = p == 1 ? al : ah, b = p == 2 ? bl : bh;
-#pragma unroll
-                for (int kk = 0; kk < 2; ++kk) umma::mma_bf16_w(d, dstep(a, kk * astep), dstep(b, kk * bstep), idZ, (p | kk) ? 1u : 0u);
-            }
+            umma::mma_bf16_ss_3x2_w(d, ah, al, astep >> 4, bh, bl, bstep >> 4, idZ);
         };
         if (my_tiles > 0) { umma::mbar_wait(&bars->wfull, 0); umma::fence_after(); }
         for (int64_t t = 0; t < my_tiles; ++t) {
@@ -184,15 +179,8 @@ kc_train_tc3_kernel(int hidden, int nsub, const unsigned char* __restrict__ img,
                 TC3_TR(120 + s);
                 const uint64_t wh = umma::make_desc(umma::smem_u32(sm + OFF_W2F + s * 8192), 128, 1024), wl = dstep(wh, 4096);
                 const uint32_t ab = tbase + COL_W + b * 64;
-#pragma unroll
-                for (int p = 0; p < 3; ++p) {
-#pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {
-                        // 16-unit group kk lives in the 32-column block of the thread group that owns it: hi | lo halves
-                        const uint32_t a = ab + (kk >> 1) * 32 + (kk & 1) * 8 + (p == 1 ? 16 : 0);
-                        umma::mma_bf16_ts_w(tbase + COL_O, a, dstep(p == 2 ? wl : wh, kk * 256), idO, (s | p | kk) ? 1u : 0u);
-                    }
-                }
+                // 16-unit group kk lives in the 32-column block of the thread group that owns it: [hi 16 | lo 16] columns
+                umma::mma_bf16_ts_3x4_w(tbase + COL_O, ab, wh, wl, idO, s ? 1u : 0u);
                 if (s + 3 < nsub) fwd_gemm1(s + 3);
                 TC3_TR(130 + s);
             }
@@ -225,24 +213,9 @@ kc_train_tc3_kernel(int hidden, int nsub, const unsigned char* __restrict__ img,
                 const uint32_t d1 = tbase + COL_GW1 + 32 * c, d2 = tbase + COL_GW2 + 32 * c;
                 const uint32_t acc0 = (first_tile && h == 0) ? 0u : 1u;
                 const uint32_t za = tbase + COL_W + b * 128, da = za + 64;
-#pragma unroll
-                for (int p = 0; p < 3; ++p) {      // gW1_c += dZ^T X  (hi*hi, lo*hi, hi*lo) over this step's 64 samples
-                    const uint64_t bb = p == 2 ? mXl : mXh;
-#pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {
-                        const uint32_t a = da + (kk >> 1) * 32 + (kk & 1) * 8 + (p == 1 ? 16 : 0);
-                        umma::mma_bf16_ts_w(d1, a, dstep(bb, (4 * h + kk) * 256), idG, (p | kk) ? 1u : acc0);
-                    }
-                }
-#pragma unroll
-                for (int p = 0; p < 3; ++p) {      // gW2_c^T += A^T dO
-                    const uint64_t bb = p == 2 ? mOl : mOh;
-#pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {
-                        const uint32_t a = za + (kk >> 1) * 32 + (kk & 1) * 8 + (p == 1 ? 16 : 0);
-                        umma::mma_bf16_ts_w(d2, a, dstep(bb, (4 * h + kk) * 256), idG, (p | kk) ? 1u : acc0);
-                    }
-                }
+                // gW1_c += dZ^T X, gW2_c^T += A^T dO (hi*hi, lo*hi, hi*lo) over this step's 64 samples
+                umma::mma_bf16_ts_3x4_w<16, 32, 48, 8>(d1, da, dstep(mXh, h * 1024), dstep(mXl, h * 1024), idG, acc0);
+                umma::mma_bf16_ts_3x4_w<16, 32, 48, 8>(d2, za, dstep(mOh, h * 1024), dstep(mOl, h * 1024), idG, acc0);
                 TC3_TR(160 + j);
                 if (j + 2 < nsub) { bwd_z(j + 2); bwd_da(j + 2); }   // same buffer: executes after the MMAs above (issue order)
                 TC3_TR(170 + j);
@@ -254,10 +227,8 @@ kc_train_tc3_kernel(int hidden, int nsub, const unsigned char* __restrict__ img,
         const int row = tid & 127, grp = tid >> 7;     // grp: which 32-column block of every 64-column buffer this thread owns
         const uint32_t laneblk = (uint32_t)((warp & 3) * 32) << 16;
         uint32_t phzf = 0, phzb = 0, pho = 0, phg = 0;
-        float gb2acc[25];
-#pragma unroll
-        for (int c = 0; c < 25; ++c) gb2acc[c] = 0.f;
         double lossacc = 0.0;
+        if (tid < 100) bars->redb[tid] = 0.f;     // gb2 partial sums, one row of 25 per warp of group 0 (only that warp touches it)
         float xv[16];
         // this thread's 16 inputs of a sample (columns 28..31 of X are never read from memory; column 28 := 1)
         auto load_x = [&](int64_t tile_) {
@@ -290,30 +261,43 @@ kc_train_tc3_kernel(int hidden, int nsub, const unsigned char* __restrict__ img,
             umma::fence_async_smem();
             umma::mbar_arrive(&bars->xrdy);
             TC3_TR(1);
-            // ---- forward epilogues: a = ELU(z) back into the Z columns as packed bf16 hi | lo ----
-            for (int s = 0; s < nsub; ++s) {
+            // ---- forward epilogues: a = ELU(z) back into the Z columns as packed bf16 hi | lo.  The Z of the NEXT sub-chunk is
+            // loaded (it was produced two sub-chunks ago) before this one is processed: its TMEM latency and the barrier round
+            // trip hide behind the arithmetic ----
+            auto fwd_step = [&](int s, uint32_t (&zc)[32], uint32_t (&zn)[32]) {
                 const int b = s % 3;
-                umma::mbar_wait(&bars->zf_rdy[b], (phzf >> b) & 1u); phzf ^= 1u << b;
-                umma::fence_after();
+                umma::wait_ld();                                   // zc holds sub-chunk s
+                if (s + 1 < nsub) {
+                    const int bn = (s + 1) % 3;
+                    umma::mbar_wait(&bars->zf_rdy[bn], (phzf >> bn) & 1u); phzf ^= 1u << bn;
+                    umma::fence_after();
+                    umma::ld32(tbase + laneblk + COL_W + bn * 64 + grp * 32, zn);
+                }
                 TC3_TR(10 + s);
                 const uint32_t ta = tbase + laneblk + COL_W + b * 64 + grp * 32;
-                uint32_t z[32], hi[16], lo[16];
-                umma::ld32(ta, z);
-                umma::wait_ld();
+                uint32_t hi[16], lo[16];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) split_pair(kc_elu(__uint_as_float(z[2 * i])), kc_elu(__uint_as_float(z[2 * i + 1])), hi[i], lo[i]);
+                for (int i = 0; i < 16; ++i) split_pair(kc_elu(__uint_as_float(zc[2 * i])), kc_elu(__uint_as_float(zc[2 * i + 1])), hi[i], lo[i]);
                 umma::st16(ta, hi);
                 umma::st16(ta + 16, lo);
                 umma::wait_st();
                 umma::fence_before();
                 umma::mbar_arrive(&bars->zf_used[b]);
                 TC3_TR(20 + s);
+            };
+            {
+                uint32_t zA[32], zB[32];
+                umma::mbar_wait(&bars->zf_rdy[0], phzf & 1u); phzf ^= 1u;
+                umma::fence_after();
+                umma::ld32(tbase + laneblk + COL_W + grp * 32, zA);
+                for (int s = 0; s < nsub; s += 2) { fwd_step(s, zA, zB); fwd_step(s + 1, zB, zA); }
             }
-            // ---- loss and dL/do (the threads of group 0 own the sample) ----
-            float ph[25], tg[25];    // physics prediction and target of this sample: in flight while the last GEMM2 drains
+            // physics prediction and target of this sample, and the target's Euler angles: formed while the last GEMM2 drains
+            float ph[25], tg[25], et[3];
             if (grp == 0 && valid) {
 #pragma unroll
                 for (int r = 0; r < 25; ++r) { ph[r] = PHYS[(size_t)qrow * 25 + r]; tg[r] = TGT[(size_t)qrow * 25 + r]; }
+                quat_to_euler(tg + 3, et);
             }
             umma::mbar_wait(&bars->ordy, pho); pho ^= 1;
             umma::fence_after();
@@ -342,9 +326,8 @@ kc_train_tc3_kernel(int hidden, int nsub, const unsigned char* __restrict__ img,
                     for (int r = 7; r < 19; ++r) { const float e = pred[r] - tg[r]; acc += wf * e * e; g[r] = 2.f * wf * e * ds; }
 #pragma unroll
                     for (int r = 19; r < 25; ++r) { const float e = pred[r] - tg[r]; acc += wz * e * e; g[r] = 2.f * wz * e; }
-                    float ep[3], et[3], ge[3], gq[4];
+                    float ep[3], ge[3], gq[4];
                     quat_to_euler(pred + 3, ep);
-                    quat_to_euler(tg + 3, et);
 #pragma unroll
                     for (int i = 0; i < 3; ++i) { const float e = ep[i] - et[i]; acc += wp * e * e; ge[i] = 2.f * wp * e; }
                     quat_to_euler_vjp(pred + 3, ge, gq);
@@ -359,8 +342,14 @@ kc_train_tc3_kernel(int hidden, int nsub, const unsigned char* __restrict__ img,
                         for (int r = 0; r < 25; ++r) po[r * K] = pred[r];
                     }
                 }
+                // gb2 += sum over the warp's 32 samples (kept in shared memory: 25 live registers less in the epilogue loops)
 #pragma unroll
-                for (int c = 0; c < 25; ++c) gb2acc[c] += g[c];
+                for (int c = 0; c < 25; ++c) {
+                    float sg = g[c];
+#pragma unroll
+                    for (int o2 = 16; o2 > 0; o2 >>= 1) sg += __shfl_xor_sync(0xffffffffu, sg, o2);
+                    if (lane == 0) bars->redb[warp * 25 + c] += sg;
+                }
 #pragma unroll
                 for (int gi = 0; gi < 4; ++gi) {
                     float g8[8];
@@ -401,10 +390,10 @@ kc_train_tc3_kernel(int hidden, int nsub, const unsigned char* __restrict__ img,
                     split_pair(a0, a1, ah[i], al[i]);
                     split_pair(g0, g1, dh[i], dl[i]);
                 }
-                umma::st16(ta, ah);
-                umma::st16(ta + 16, al);
-                umma::st16(ta + 64, dh);
-                umma::st16(ta + 80, dl);
+                // packed layout per thread group: [hi 8 | lo 8] columns per 16 samples (8-column stores: measured faster than
+                // [hi 16 | lo 16] with 16-column stores, 0.186 vs 0.201 ms per step)
+                umma::st8(ta, ah); umma::st8(ta + 8, al); umma::st8(ta + 16, ah + 8); umma::st8(ta + 24, al + 8);
+                umma::st8(ta + 64, dh); umma::st8(ta + 72, dl); umma::st8(ta + 80, dh + 8); umma::st8(ta + 88, dl + 8);
                 umma::wait_st();
                 umma::fence_before();
                 umma::mbar_arrive(&bars->zb_done[b]);
@@ -440,13 +429,6 @@ kc_train_tc3_kernel(int hidden, int nsub, const unsigned char* __restrict__ img,
                     for (int co = 0; co < 25; ++co) out[oW2 + (size_t)co * hidden + u] = __uint_as_float(v[co]);
                 }
             }
-        }
-#pragma unroll
-        for (int c = 0; c < 25; ++c) {
-            float s = gb2acc[c];
-#pragma unroll
-            for (int o2 = 16; o2 > 0; o2 >>= 1) s += __shfl_down_sync(0xffffffffu, s, o2);
-            if (lane == 0 && warp < 4) bars->redb[warp * 25 + c] = s;
         }
         {
             double s = lossacc;

@@ -75,6 +75,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
+// non-blocking phase test: true once the phase with this parity has completed
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+
 // D[tmem] (+)= A[smem] * B[smem]^T, issued by ONE thread
 __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -184,6 +194,58 @@ __device__ __forceinline__ void mbar_arrive_w(uint64_t* bar) {
         "{\n\t.reg .pred e;\n\t"
         "elect.sync _|e, 0xffffffff;\n\t"
         "@e mbarrier.arrive.shared::cta.b64 _, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+// ---- batched warp-uniform issue: ONE elect.sync for a whole 3-pass (hi*hi, lo*hi, hi*lo) product, so the per-instruction
+// ELECT / VOTEU / R2UR chain (~11 instructions, 40-60 cycles per MMA when issued one by one) is paid once per batch ----
+// TS form, 3 passes x 4 k-steps of 16: A in TMEM as packed bf16 pairs, laid out as two 32-column blocks (one per epilogue
+// thread group), each block = [hi 16 columns | lo 16 columns]; k-step kk reads 8 columns at block (kk >> 1), offset (kk & 1) * 8.
+// B: shared-memory descriptors of the hi and lo images, advancing 256 B (16 descriptor units) per k-step.
+// O1..O3: column offsets of k-steps 1..3, LO: offset of the lo half (defaults: the layout described above; the transposed
+// backward of kc_train_tc3.cu uses [hi 8 | lo 8] per k-step: O = 16, 32, 48, LO = 8).
+template <int O1 = 8, int O2 = 32, int O3 = 40, int LO = 16>
+__device__ __forceinline__ void mma_bf16_ts_3x4_w(uint32_t d_tmem, uint32_t a_tmem, uint64_t bh, uint64_t bl, uint32_t idesc,
+                                                  uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, e, t;\n\t.reg .b32 a<4>, l<4>;\n\t.reg .b64 h<4>, g<4>;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "setp.eq.u32 t, 0, 0;\n\t"
+        "mov.b32 a0, %1;\n\tadd.u32 a1, %1, %6;\n\tadd.u32 a2, %1, %7;\n\tadd.u32 a3, %1, %8;\n\t"
+        "add.u32 l0, %1, %9;\n\tadd.u32 l1, %1, %10;\n\tadd.u32 l2, %1, %11;\n\tadd.u32 l3, %1, %12;\n\t"
+        "mov.b64 h0, %2;\n\tadd.u64 h1, %2, 16;\n\tadd.u64 h2, %2, 32;\n\tadd.u64 h3, %2, 48;\n\t"
+        "mov.b64 g0, %3;\n\tadd.u64 g1, %3, 16;\n\tadd.u64 g2, %3, 32;\n\tadd.u64 g3, %3, 48;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a0], h0, %4, p;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a1], h1, %4, t;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a2], h2, %4, t;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a3], h3, %4, t;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [l0], h0, %4, t;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [l1], h1, %4, t;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [l2], h2, %4, t;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [l3], h3, %4, t;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a0], g0, %4, t;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a1], g1, %4, t;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a2], g2, %4, t;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a3], g3, %4, t;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(bh), "l"(bl), "r"(idesc), "r"(accumulate), "n"(O1), "n"(O2), "n"(O3), "n"(LO), "n"(O1 + LO),
+          "n"(O2 + LO), "n"(O3 + LO) : "memory");
+}
+// SS form, 3 passes x 2 k-steps (K = 32): D = A B^T from scratch (the first instruction overwrites D); astep / bstep are the
+// descriptor increments (bytes >> 4) of one k-step of 16.
+__device__ __forceinline__ void mma_bf16_ss_3x2_w(uint32_t d_tmem, uint64_t ah, uint64_t al, uint32_t astep, uint64_t bh, uint64_t bl,
+                                                  uint32_t bstep, uint32_t idesc) {
+    asm volatile(
+        "{\n\t.reg .pred e, t, f;\n\t.reg .b64 ah1, al1, bh1, bl1, sa, sb;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.eq.u32 t, 0, 0;\n\tsetp.ne.u32 f, 0, 0;\n\t"
+        "cvt.u64.u32 sa, %3;\n\tcvt.u64.u32 sb, %6;\n\t"
+        "add.u64 ah1, %1, sa;\n\tadd.u64 al1, %2, sa;\n\tadd.u64 bh1, %4, sb;\n\tadd.u64 bl1, %5, sb;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %4, %7, f;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], ah1, bh1, %7, t;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %2, %4, %7, t;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], al1, bh1, %7, t;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %5, %7, t;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], ah1, bl1, %7, t;\n\t}"
+        ::"r"(d_tmem), "l"(ah), "l"(al), "r"(astep), "l"(bh), "l"(bl), "r"(bstep), "r"(idesc) : "memory");
 }
 // K-major, no swizzle, 2-byte elements: element (r, k) of a tile with KT k-values per row (8 x 16-byte core matrices:
 // LBO = 128 B to the next 8 k-values, SBO = (KT/8) * 128 B to the next 8 rows); one kind::f16 instruction consumes
