@@ -102,7 +102,9 @@ kc_train_prep_kernel(const __grid_constant__ RodC<T> P, const __grid_constant__ 
 // by three consecutive steps and the per-sample accesses are column gathers), the samples are computed from there,
 // staged in shared memory and written out as contiguous runs.  (56 -> ~25 us at C3; the thread-per-sample kernel moves
 // 4-byte elements at a 40-byte stride in both directions.)
-constexpr int PREP_ROW = 56 + 50;   // staging row: x (<= 56) | phys 25 | tgt 25
+// x goes straight from registers to its 128 / 224-byte row as 16-byte stores; phys | tgt (100-byte rows) are staged.  Shared
+// memory per CTA: the trajectory + 128 x 50 values (4 CTAs per SM at C3 instead of 2 with x staged as well: 31 -> ~20 us).
+constexpr int PREP_ROW = 50;   // staging row: phys 25 | tgt 25
 template <typename T, bool DIAG, int IN>
 __global__ void __launch_bounds__(128)
 kc_train_prep_traj_kernel(const __grid_constant__ RodC<T> P, const __grid_constant__ KeyIdx64 key, int64_t B, int T_, int K,
@@ -116,25 +118,39 @@ kc_train_prep_traj_kernel(const __grid_constant__ RodC<T> P, const __grid_consta
     const int64_t b = blockIdx.x;
     const int tid = threadIdx.x;
     const T* src = traj + (size_t)b * total;
-    for (int e = tid; e < total; e += 128) s_traj[e] = src[e];
+    if (((size_t)total * sizeof(T)) % 16 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {     // 128-bit loads
+        const int nv = (int)((size_t)total * sizeof(T) / 16);
+        const uint4* s4 = reinterpret_cast<const uint4*>(src);
+        uint4* d4 = reinterpret_cast<uint4*>(s_traj);
+        for (int e = tid; e < nv; e += 128) d4[e] = s4[e];
+    } else {
+        for (int e = tid; e < total; e += 128) s_traj[e] = src[e];
+    }
     __syncthreads();
     const int S = (T_ - 1) * K;
     for (int s0 = 0; s0 < S; s0 += 128) {
         const int s = s0 + tid, n = S - s0 < 128 ? S - s0 : 128;
+        const size_t q0 = (size_t)b * S + s0;
         if (s < S) {
             const int t = s / K, kk = s - t * K;
             T* row = s_out + (size_t)tid * PREP_ROW;
+            T x[XPG];
             prep_sample<T, DIAG, IN>(P, key.k[kk], s_traj + (size_t)(t + 1) * slab, s_traj + (size_t)t * slab,
                                      s_traj + (size_t)(t > 0 ? t - 1 : 0) * slab, controls + (size_t)(b * T_ + t) * 4,
-                                     row, row + 56, row + 81);
+                                     x, row, row + 25);
+            T* xr = X + (q0 + tid) * XPG;            // rows are 16-byte aligned (XPG * sizeof(T) is a multiple of 16)
+            constexpr int V = 16 / sizeof(T);
+#pragma unroll
+            for (int i = 0; i < XPG; i += V) {
+                if (sizeof(T) == 4) *reinterpret_cast<float4*>(xr + i) = make_float4((float)x[i], (float)x[i + 1], (float)x[i + 2], (float)x[i + 3]);
+                else *reinterpret_cast<double2*>(xr + i) = make_double2((double)x[i], (double)x[i + 1]);
+            }
         }
         __syncthreads();
-        const size_t q0 = (size_t)b * S + s0;
-        for (int e = tid; e < n * XPG; e += 128) X[q0 * XPG + e] = s_out[(size_t)(e / XPG) * PREP_ROW + (e % XPG)];
         for (int e = tid; e < n * 25; e += 128) {
             const int r = e / 25, c = e - r * 25;
-            PHYS[q0 * 25 + e] = s_out[(size_t)r * PREP_ROW + 56 + c];
-            TGT[q0 * 25 + e] = s_out[(size_t)r * PREP_ROW + 81 + c];
+            PHYS[q0 * 25 + e] = s_out[(size_t)r * PREP_ROW + c];
+            TGT[q0 * 25 + e] = s_out[(size_t)r * PREP_ROW + 25 + c];
         }
         __syncthreads();
     }
