@@ -405,10 +405,10 @@ def main():
                               % (trainer.graph is not None, "peer memory, fused with Adam" if trainer.peer else
                                  ("NCCL" if world > 1 else "none (1 GPU)")),
                  "useful_tflops": q * FLOP_PER_TRAIN_SAMPLE / (tms * 1e-3) / 1e12, "hidden": TRAIN_H,
-                 "roofline": {"bound": "tensor", "kernel": "kc_train_tc_kernel (tcgen05 + TMEM; 80 % of the step)",
+                 "roofline": {"bound": "tensor", "kernel": "kc_train_tc3_kernel (tcgen05 + TMEM, transposed backward: activations stay in TMEM; ~78 % of the step)",
                               "achieved": q * FLOP_PER_TRAIN_SAMPLE / world / (tms * 1e-3) / 1e12, "unit": "TFLOP/s",
                               "note": "useful fp32-accurate FLOP/s per GPU of the WHOLE step (134.6 kFLOP per sample, SURVEY "
-                                      "8d); every contraction runs 3 tensor-core passes (tf32 / bf16 hi-lo split) to keep "
+                                      "8d); every contraction runs 3 tensor-core passes (bf16 hi-lo split) to keep "
                                       "fp32 accuracy, so the executed tensor FLOP/s are 3x this",
                               "frac_of_fp32_fma_peak": None, "frac_of_bf16_tensor_peak_executed": None},
                  "loss": float(trainer.plan.flat[-1].item()), "kernels_per_step": 4 + (2 if trainer.peer else 1) + 1,
