@@ -27,9 +27,6 @@ int kc_train_tc2_launch(const kc_mlp* mlp, float ds, int64_t Q, int T_, int K, c
 int kc_train_tc3_launch(const kc_mlp* mlp, float ds, int64_t Q, int T_, int K, const float* X, const float* PHYS, const float* TGT,
                         unsigned char* img, float* partial, int64_t NP, double* loss_part, float* pred_out, int grid,
                         cudaStream_t st);
-int kc_train_tc4_launch(const kc_mlp* mlp, float ds, int64_t Q, int T_, int K, const float* X, const float* PHYS, const float* TGT,
-                        unsigned char* img, float* partial, int64_t NP, double* loss_part, float* pred_out, int grid,
-                        cudaStream_t st);
 int kc_train_tc_launch(const kc_mlp* mlp, float ds, int64_t Q, int T_, int K, const float* X, const float* PHYS,
                        const float* TGT, float* W1hl, float* W2c, float* partial, int64_t NP, double* loss_part,
                        float* pred_out, int grid, cudaStream_t st);
@@ -482,10 +479,7 @@ static int train_typed(const kc_rod_params* Pp, const kc_mlp* mlp, int64_t B, in
             // (warp-specialised pipeline with shared-memory activation tiles, kc_train_tc2.cu) or =1 (kc_train_tc.cu)
             const char* gen = getenv("KC_TRAIN_TC");
             int rc2;
-            if (gen && gen[0] == '4')
-                rc2 = kc_train_tc4_launch(mlp, (float)P.ds, Q, (int)T_, K, (const float*)X, (const float*)PHYS, (const float*)TGT,
-                                          (unsigned char*)tcw, (float*)part, w.NP, lossp, (float*)pred, tc_slices, st);
-            else if (gen && gen[0] == '1')
+            if (gen && gen[0] == '1')
                 rc2 = kc_train_tc_launch(mlp, (float)P.ds, Q, (int)T_, K, (const float*)X, (const float*)PHYS, (const float*)TGT,
                                          tcw, tcw + 4 * 2 * 128 * 32, (float*)part, w.NP, lossp, (float*)pred, tc_slices, st);
             else if (gen && gen[0] == '2')

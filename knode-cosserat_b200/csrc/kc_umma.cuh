@@ -229,25 +229,6 @@ __device__ __forceinline__ void mma_bf16_ts_3x4_w(uint32_t d_tmem, uint32_t a_tm
         ::"r"(d_tmem), "r"(a_tmem), "l"(bh), "l"(bl), "r"(idesc), "r"(accumulate), "n"(O1), "n"(O2), "n"(O3), "n"(LO), "n"(O1 + LO),
           "n"(O2 + LO), "n"(O3 + LO) : "memory");
 }
-// TS form, 3 passes x 2 k-steps (K = 32): A = one 32-column block; O1 = column offset of k-step 1, LO = offset of the lo half
-template <int O1 = 8, int LO = 16>
-__device__ __forceinline__ void mma_bf16_ts_3x2_w(uint32_t d_tmem, uint32_t a_tmem, uint64_t bh, uint64_t bl, uint32_t idesc,
-                                                  uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p, e, t;\n\t.reg .b32 a1, l0, l1;\n\t.reg .b64 h1, g1;\n\t"
-        "elect.sync _|e, 0xffffffff;\n\t"
-        "setp.ne.b32 p, %5, 0;\n\t"
-        "setp.eq.u32 t, 0, 0;\n\t"
-        "add.u32 a1, %1, %6;\n\tadd.u32 l0, %1, %7;\n\tadd.u32 l1, %1, %8;\n\t"
-        "add.u64 h1, %2, 16;\n\tadd.u64 g1, %3, 16;\n\t"
-        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %4, p;\n\t"
-        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a1], h1, %4, t;\n\t"
-        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [l0], %2, %4, t;\n\t"
-        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [l1], h1, %4, t;\n\t"
-        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %3, %4, t;\n\t"
-        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a1], g1, %4, t;\n\t}"
-        ::"r"(d_tmem), "r"(a_tmem), "l"(bh), "l"(bl), "r"(idesc), "r"(accumulate), "n"(O1), "n"(LO), "n"(O1 + LO) : "memory");
-}
 // SS form, 3 passes x 2 k-steps (K = 32): D = A B^T from scratch (the first instruction overwrites D); astep / bstep are the
 // descriptor increments (bytes >> 4) of one k-step of 16.
 __device__ __forceinline__ void mma_bf16_ss_3x2_w(uint32_t d_tmem, uint64_t ah, uint64_t al, uint32_t astep, uint64_t bh, uint64_t bl,

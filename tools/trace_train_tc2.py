@@ -37,7 +37,7 @@ tiles = [c for i, c in ev[0] if i == 0]
 print("tile starts (epilogue warp 0):", [c - t0 for c in tiles], "diffs", np.diff(tiles).tolist())
 lo = tiles[want]; hi = tiles[want + 1] if want + 1 < len(tiles) else 1 << 62
 rows = []
-for r, nm in enumerate(["epi0", "epi4", "mma "]):   # gen 4: epi0 = team 0, epi4 = team 1
+for r, nm in enumerate(["epi0", "epi4", "mma "]):
     for i, c in ev[r]:
         if lo - 3000 <= c < hi:
             rows.append((c - lo, nm, i))
@@ -50,13 +50,6 @@ def name(i):
     tab3 = [(10, "fwd zf_rdy got s="), (20, "fwd done s="), (40, "bwd zb_rdy got j="), (50, "bwd loaded j="), (60, "bwd done j="),
             (120, "mma: zf_used got s="), (130, "mma: gemm2+gemm1 issued s="), (150, "mma: zb_done got j="),
             (160, "mma: grads issued j="), (170, "mma: refill issued j=")]
-    tab4 = [(10, "fwd got i="), (30, "fwd done i="), (60, "bwd zb_rdy got j="), (80, "bwd done j="),
-            (110, "mma: zf_used got i="), (150, "mma: zb_done got j="), (170, "mma: grads+refill issued j=")]
-    if GEN == "4":
-        names.update({50: "O ready", 51: "dO stored", 99: "tile end"})
-        for b, n in tab4:
-            if b <= i < b + 16: return n + str(i - b)
-        return str(i)
     for b, n in (tab3 if GEN == "3" else tab2):
         if b <= i < b + 10: return n + str(i - b)
     return str(i)
