@@ -7,7 +7,9 @@
 #pragma once
 #include "kc_common.cuh"
 
-template <typename T> KC_HD T kc_abs(T x) { return x < T(0) ? -x : x; }
+// |x| as fabs: an operand modifier on the device (the compare + select form cost two instructions, 2.8 % of the rollout kernel)
+KC_HD float kc_abs(float x) { return fabsf(x); }
+KC_HD double kc_abs(double x) { return fabs(x); }
 template <typename T> KC_HD T kc_max(T a, T b) { return a > b ? a : b; }
 
 // e^x on the device: ONE multiply and ONE MUFU.EX2 (ex2.approx.ftz, rel. error 2^-22).  __expf without -use_fast_math
