@@ -6,6 +6,12 @@
 // narrow and wide-lin kernels resume from the trajectory plus a few words of solver state) and every finished range is
 // copied back on a second stream while the next one is being solved.
 #include <cuda_runtime.h>
+#include <atomic>
+#include <condition_variable>
+#include <cstring>
+#include <mutex>
+#include <thread>
+#include <vector>
 #include "kc_common.cuh"
 
 #define KC_CHECK_CUDA(call)                                                                  \
@@ -44,6 +50,83 @@ extern "C" int64_t kc_rollout_host_device_bytes(int dtype, const kc_rod_params* 
 
 // one copy stream per device, created on first use (never destroyed: lives as long as the library)
 static cudaStream_t g_copy_stream[64] = {};
+
+// ---- pageable destinations (the reference's own contract: knode.simulate returns a FRESH ndarray, knode.py:102) ----------
+// A device-to-host copy into pageable memory is staged by the driver at a fraction of the PCIe rate, and a fresh array
+// takes a page fault per 4 KB on first touch (1.6 GB at BASELINE config 2 in fp64 x 50 rows: 0.75 s, almost all of it
+// faults on one thread).  Instead: the finished time ranges are copied in chunks of <= 32 MB into a pinned ring at the full
+// PCIe rate, and a pool of host threads moves each landed chunk to its rows of the destination (the page faults are taken
+// by all threads in parallel) while the next chunk is in flight.
+constexpr size_t KC_STAGE_CHUNK = (size_t)32 << 20;
+constexpr int KC_STAGE_SLOTS = 4;
+static unsigned char* g_stage[64] = {};
+
+static bool host_ptr_is_pinned(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+struct StageChunk { int slot; int64_t b0, nb; size_t dst_off, row_bytes; };   // rows b0 .. b0+nb-1, each row_bytes long
+struct Stager {
+    int dev = 0;
+    unsigned char* ring = nullptr;
+    unsigned char* dst = nullptr;
+    size_t dst_pitch = 0;                    // bytes between consecutive rods in the destination
+    cudaEvent_t ev[KC_STAGE_SLOTS] = {};
+    bool busy[KC_STAGE_SLOTS] = {};
+    std::mutex mu;
+    std::condition_variable cv;
+    std::vector<StageChunk> queue;
+    size_t head = 0;
+    bool closed = false, failed = false;
+    int nthreads = 1;
+    std::thread consumer;
+
+    void run() {
+        cudaSetDevice(dev);
+        for (;;) {
+            StageChunk c;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return head < queue.size() || closed; });
+                if (head >= queue.size()) return;
+                c = queue[head++];
+            }
+            if (cudaEventSynchronize(ev[c.slot]) != cudaSuccess) failed = true;
+            const unsigned char* src = ring + (size_t)c.slot * KC_STAGE_CHUNK;
+            const int nt = (int)std::min<int64_t>(nthreads, c.nb);
+            auto work = [&](int w) {
+                for (int64_t r = w; r < c.nb; r += nt)
+                    std::memcpy(dst + (size_t)(c.b0 + r) * dst_pitch + c.dst_off, src + (size_t)r * c.row_bytes, c.row_bytes);
+            };
+            std::vector<std::thread> pool;
+            for (int w = 1; w < nt; ++w) pool.emplace_back(work, w);
+            work(0);
+            for (auto& t : pool) t.join();
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                busy[c.slot] = false;
+            }
+            cv.notify_all();
+        }
+    }
+    void wait_slot(int slot) {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return !busy[slot]; });
+        busy[slot] = true;
+    }
+    void push(const StageChunk& c) {
+        { std::lock_guard<std::mutex> lk(mu); queue.push_back(c); }
+        cv.notify_all();
+    }
+    void close() {
+        { std::lock_guard<std::mutex> lk(mu); closed = true; }
+        cv.notify_all();
+        if (consumer.joinable()) consumer.join();
+    }
+    ~Stager() { close(); }
+};
 
 extern "C" int kc_rollout_host(int dtype, const kc_rod_params* P, const kc_mlp* mlp, int64_t B, int64_t T_,
                                const void* tensions_host, const void* y0, const void* z0, double tol, int32_t max_iter,
@@ -89,6 +172,25 @@ extern "C" int kc_rollout_host(int dtype, const kc_rod_params* P, const kc_mlp* 
     KC_CHECK_CUDA(cudaMemcpyAsync(tens_d, tensions_host, (size_t)B * T_ * 4 * sz, cudaMemcpyHostToDevice, st));
     cudaEvent_t ev[8] = {};
     int rc = KC_OK;
+    // pageable destination -> pinned ring + host copy threads (see above); pinned destination -> direct copies
+    Stager stg;
+    bool staged = !host_ptr_is_pinned(traj_host);
+    if (staged) {
+        if (!g_stage[dev] && cudaHostAlloc((void**)&g_stage[dev], KC_STAGE_CHUNK * KC_STAGE_SLOTS, cudaHostAllocDefault) != cudaSuccess) {
+            cudaGetLastError();
+            g_stage[dev] = nullptr;
+            staged = false;                 // no pinned memory to be had: the driver's own staging still works
+        }
+    }
+    if (staged) {
+        stg.dev = dev; stg.ring = g_stage[dev]; stg.dst = (unsigned char*)traj_host; stg.dst_pitch = (size_t)T_ * slice;
+        const unsigned hc = std::thread::hardware_concurrency();
+        stg.nthreads = hc ? (int)std::min(16u, hc) : 4;
+        for (int i = 0; i < KC_STAGE_SLOTS; ++i)
+            if (cudaEventCreateWithFlags(&stg.ev[i], cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); staged = false; }
+        if (staged) stg.consumer = std::thread([&stg] { stg.run(); });
+    }
+    int64_t chunk_no = 0;
     for (int s = 0; s < nseg && rc == KC_OK; ++s) {
         // steps [t0, t1): the copy engine is ~6x slower than the solve, so only the FIRST range's solve is exposed — it is
         // kept short (a quarter of an even share); the other ranges share the rest evenly
@@ -102,7 +204,20 @@ extern "C" int kc_rollout_host(int dtype, const kc_rod_params* P, const kc_mlp* 
         if (e == cudaSuccess) e = cudaEventRecord(ev[s], st);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(cs, ev[s], 0);
         const int64_t i0 = s == 0 ? 0 : t0 + 1, ni = t1 - i0 + 1;             // time indices this range produced
-        if (e == cudaSuccess && ni > 0) {
+        if (e == cudaSuccess && ni > 0 && staged && (size_t)ni * slice <= KC_STAGE_CHUNK) {
+            const size_t row_bytes = (size_t)ni * slice;
+            const int64_t per = (int64_t)(KC_STAGE_CHUNK / row_bytes);
+            for (int64_t b0 = 0; b0 < B && e == cudaSuccess; b0 += per, ++chunk_no) {
+                const int64_t nb = std::min<int64_t>(per, B - b0);
+                const int slot = (int)(chunk_no % KC_STAGE_SLOTS);
+                stg.wait_slot(slot);          // its previous contents have reached the destination
+                e = cudaMemcpy2DAsync(stg.ring + (size_t)slot * KC_STAGE_CHUNK, row_bytes,
+                                      traj_d + ((size_t)b0 * T_ + (size_t)i0) * slice, (size_t)T_ * slice, row_bytes, (size_t)nb,
+                                      cudaMemcpyDeviceToHost, cs);
+                if (e == cudaSuccess) e = cudaEventRecord(stg.ev[slot], cs);
+                stg.push(StageChunk{slot, b0, nb, (size_t)i0 * slice, row_bytes});
+            }
+        } else if (e == cudaSuccess && ni > 0) {
             if (nseg == 1)
                 e = cudaMemcpyAsync(traj_host, traj_d, total_bytes, cudaMemcpyDeviceToHost, cs);
             else
@@ -126,6 +241,10 @@ extern "C" int kc_rollout_host(int dtype, const kc_rod_params* P, const kc_mlp* 
         }
     }
     // a host API: the result is in host memory when the call returns
+    if (stg.consumer.joinable()) stg.close();
+    for (int i = 0; i < KC_STAGE_SLOTS; ++i)
+        if (stg.ev[i]) cudaEventDestroy(stg.ev[i]);
+    if (stg.failed && rc == KC_OK) { kc_set_error("kc_rollout_host: staged device-to-host copy failed"); rc = KC_ECUDA; }
     cudaError_t e1 = cudaStreamSynchronize(cs), e2 = cudaStreamSynchronize(st);
     for (int s = 0; s < 8; ++s)
         if (ev[s]) cudaEventDestroy(ev[s]);
