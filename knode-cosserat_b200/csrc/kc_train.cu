@@ -18,15 +18,17 @@
 #include <cstdlib>
 #include "kc_rod.cuh"
 #include "kc_adjoint.cuh"
+#include "kc_train_prep.cuh"
 
 template <typename T> int kc_pack_mlp(const kc_mlp* mlp, T* Wp, MlpC<T>& M, cudaStream_t st);
 int kc_train_tc_grid(int64_t Q);
 int kc_train_tc2_launch(const kc_mlp* mlp, float ds, int64_t Q, int T_, int K, const float* X, const float* PHYS, const float* TGT,
                         unsigned char* img, float* partial, int64_t NP, double* loss_part, float* pred_out, int grid,
                         cudaStream_t st);
-int kc_train_tc3_launch(const kc_mlp* mlp, float ds, int64_t Q, int T_, int K, const float* X, const float* PHYS, const float* TGT,
+int kc_train_tc3_launch(const kc_mlp* mlp, float ds, int64_t Q, int T_, int K, float* X, float* PHYS, float* TGT,
                         unsigned char* img, float* partial, int64_t NP, double* loss_part, float* pred_out, int grid,
-                        cudaStream_t st);
+                        cudaStream_t st, const RodC<float>* RP, const KeyIdx64* key, const float* traj, const float* controls,
+                        int64_t B);
 int kc_train_tc_launch(const kc_mlp* mlp, float ds, int64_t Q, int T_, int K, const float* X, const float* PHYS,
                        const float* TGT, float* W1hl, float* W2c, float* partial, int64_t NP, double* loss_part,
                        float* pred_out, int grid, cudaStream_t st);
@@ -34,51 +36,11 @@ template <typename T> struct kc_is_float { static constexpr bool value = false; 
 template <> struct kc_is_float<float> { static constexpr bool value = true; };
 int kc_check_mlp(const kc_mlp* mlp);
 
-struct KeyIdx64 { int32_t k[64]; };
 static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 // ---------------------------------------------------------------------------------------------------------------
 // 1. prep
 // ---------------------------------------------------------------------------------------------------------------
-// One (b, t, key) sample: ODE at node kn-1 of the NEXT ground-truth state -> x[XPG], phys[25], tgt[25] (unit stride).
-// nxt / cur / prv: the [25][N] states t+1, t, t-1 of the trajectory (global or shared memory).
-template <typename T, bool DIAG, int IN>
-KC_D void prep_sample(const RodC<T>& P, int kn, const T* nxt, const T* cur, const T* prv, const T* tn4, T* x, T* ph, T* tg) {
-    const int N = P.N, j = kn - 1;
-    T y[19], hist[25], tn[4], tf[3], ys[19], z[6];
-#pragma unroll
-    for (int r = 0; r < 19; ++r) y[r] = nxt[r * N + j];
-#pragma unroll
-    for (int r = 0; r < 25; ++r) hist[r] = P.c1 * cur[r * N + j] + P.c2 * prv[r * N + j];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) tn[i] = tn4[i];
-    tendon_force(P, tn, tf);
-    rod_ode<T, DIAG>(P, y, hist + 13, hist + 16, hist + 19, hist + 22, tf, ys, z);
-    if (IN == 28) {
-#pragma unroll
-        for (int i = 0; i < 19; ++i) x[i] = y[i];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) x[19 + i] = z[i];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) x[25 + i] = tf[i];
-#pragma unroll
-        for (int i = 28; i < 32; ++i) x[i] = T(0);
-    } else {
-#pragma unroll
-        for (int i = 0; i < 19; ++i) { x[i] = y[i]; x[19 + i] = hist[i]; }
-#pragma unroll
-        for (int i = 0; i < 6; ++i) { x[38 + i] = z[i]; x[44 + i] = hist[19 + i]; }
-#pragma unroll
-        for (int i = 0; i < 3; ++i) x[50 + i] = tf[i];
-#pragma unroll
-        for (int i = 53; i < 56; ++i) x[i] = T(0);
-    }
-#pragma unroll
-    for (int r = 0; r < 19; ++r) { ph[r] = y[r] + P.ds * ys[r]; tg[r] = nxt[r * N + kn]; }
-#pragma unroll
-    for (int c = 0; c < 6; ++c) { ph[19 + c] = z[c]; tg[19 + c] = nxt[(19 + c) * N + kn - 1]; }
-}
-
 // thread per sample, straight from global memory (any T): the fallback when a trajectory does not fit shared memory
 template <typename T, bool DIAG, int IN>
 __global__ void __launch_bounds__(128)
@@ -462,16 +424,29 @@ static int train_typed(const kc_rod_params* Pp, const kc_mlp* mlp, int64_t B, in
                                                               (const T*)controls, X, w.XPG, PHYS, TGT);                \
         }                                                                                                              \
     } while (0)
-        if (P.diag) { if (in_dim == 28) PREP(true, 28); else PREP(true, 53); }
-        else { if (in_dim == 28) PREP(false, 28); else PREP(false, 53); }
-#undef PREP
-        KC_CHECK_LAUNCH("kc_train_prep_kernel");
         // tensor-core path (tcgen05): fp32 model, 28 inputs, hidden <= 512; KC_TRAIN_MODE=simt forces the SIMT kernels
         bool use_tc = kc_is_float<T>::value && in_dim == 28 && mlp->hidden <= 512;
         {
             const char* e = getenv("KC_TRAIN_MODE");
             if (e && e[0] == 's') use_tc = false;
         }
+        // Small batches (at most one tile per CTA: the strong-scaling regime): the third-generation kernel forms its own samples
+        // in its prologue and the prep launch is skipped (0.073 -> 0.069 ms at 128 trajectories).  With several tiles per CTA the
+        // in-kernel gathers (4-byte, 40-byte stride) lose against the coalescing prep kernel (0.192 vs 0.179 ms at 1024), so the
+        // stand-alone kernel stays.  KC_TRAIN_FUSE_PREP=0|1 forces either.
+        bool fuse_prep = false;
+        if (use_tc) {
+            const char* gen = getenv("KC_TRAIN_TC");
+            const char* fe = getenv("KC_TRAIN_FUSE_PREP");
+            fuse_prep = !(gen && (gen[0] == '1' || gen[0] == '2')) && (Q + 127) / 128 <= kc_train_tc_grid(Q);
+            if (fe && (fe[0] == '0' || fe[0] == '1')) fuse_prep = fe[0] == '1' && !(gen && (gen[0] == '1' || gen[0] == '2'));
+        }
+        if (!fuse_prep) {
+            if (P.diag) { if (in_dim == 28) PREP(true, 28); else PREP(true, 53); }
+            else { if (in_dim == 28) PREP(false, 28); else PREP(false, 53); }
+            KC_CHECK_LAUNCH("kc_train_prep_kernel");
+        }
+#undef PREP
         if (use_tc) {
             float* tcw = (float*)(ws + w.tcw);
             tc_slices = kc_train_tc_grid(Q);
@@ -486,8 +461,14 @@ static int train_typed(const kc_rod_params* Pp, const kc_mlp* mlp, int64_t B, in
                 rc2 = kc_train_tc2_launch(mlp, (float)P.ds, Q, (int)T_, K, (const float*)X, (const float*)PHYS, (const float*)TGT,
                                           (unsigned char*)tcw, (float*)part, w.NP, lossp, (float*)pred, tc_slices, st);
             else
-                rc2 = kc_train_tc3_launch(mlp, (float)P.ds, Q, (int)T_, K, (const float*)X, (const float*)PHYS, (const float*)TGT,
-                                          (unsigned char*)tcw, (float*)part, w.NP, lossp, (float*)pred, tc_slices, st);
+{
+                if constexpr (kc_is_float<T>::value)
+                    rc2 = kc_train_tc3_launch(mlp, (float)P.ds, Q, (int)T_, K, (float*)X, (float*)PHYS, (float*)TGT, (unsigned char*)tcw,
+                                              (float*)part, w.NP, lossp, (float*)pred, tc_slices, st, fuse_prep ? &P : nullptr, &key,
+                                              (const float*)traj, (const float*)controls, B);
+                else
+                    rc2 = KC_EINVAL;
+            }
             if (rc2) return rc2;
         } else {
         {

@@ -27,6 +27,7 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include "kc_rod.cuh"
+#include "kc_train_prep.cuh"
 #include <cstdlib>
 #include "kc_umma.cuh"
 
@@ -105,10 +106,17 @@ __global__ void kc_tc3_prep_weights_kernel(const float* __restrict__ W1, const f
     }
 }
 
+// FUSE: the kernel forms its own samples.  The thread group that has nothing to do while the loss of a tile is being formed
+// (group 1; the tensor pipe idles there too) computes X | phys | tgt of the CTA's NEXT tile from the trajectory (prep_sample:
+// gathers + the rod ODE at the key node) and leaves them in the L2-resident sample arrays, from where all threads read them
+// a phase later, as they would read the output of the stand-alone prep kernel (26 us, its own launch) otherwise.
+struct Tc3Src { const float* traj; const float* controls; int64_t B; };
+template <bool FUSE>
 __global__ void __launch_bounds__(288, 1)
 kc_train_tc3_kernel(int hidden, int nsub, const unsigned char* __restrict__ img, const float* __restrict__ b2, float ds, int64_t Q,
-                    int T_, int K, const float* __restrict__ X, const float* __restrict__ PHYS, const float* __restrict__ TGT,
-                    float* __restrict__ partial, int64_t NP, double* __restrict__ loss_part, float* __restrict__ pred_out) {
+                    int T_, int K, float* X, float* PHYS, float* TGT,
+                    float* __restrict__ partial, int64_t NP, double* __restrict__ loss_part, float* __restrict__ pred_out,
+                    const __grid_constant__ RodC<float> RP, const __grid_constant__ KeyIdx64 key, const Tc3Src src) {
     extern __shared__ __align__(1024) unsigned char sm[];
     using namespace tc3;
     Bars* bars = reinterpret_cast<Bars*>(sm + OFF_MISC);
@@ -243,6 +251,32 @@ kc_train_tc3_kernel(int hidden, int nsub, const unsigned char* __restrict__ img,
             }
             if (grp == 1) { xv[12] = ok ? 1.f : 0.f; xv[13] = 0.f; xv[14] = 0.f; xv[15] = 0.f; }
         };
+        // sample `row` of a tile straight from the trajectory -> its rows of X | PHYS | TGT (FUSE only)
+        auto prep_tile = [&](int64_t tile_) {
+            const int64_t qr = tile_ * 128 + row;
+            if (qr >= Q) return;
+            const int N = RP.N, kk = (int)(qr % K);
+            const int64_t bt = qr / K;
+            const int tt = (int)(bt % (T_ - 1));
+            const int64_t bb = bt / (T_ - 1);
+            const float* tb = src.traj + (size_t)bb * T_ * 25 * N;
+            float x[32];
+            float* ph = PHYS + (size_t)qr * 25;
+            float* tg = TGT + (size_t)qr * 25;
+            if (RP.diag)
+                prep_sample<float, true, 28>(RP, key.k[kk], tb + (size_t)(tt + 1) * 25 * N, tb + (size_t)tt * 25 * N,
+                                             tb + (size_t)(tt > 0 ? tt - 1 : 0) * 25 * N, src.controls + (size_t)(bb * T_ + tt) * 4, x, ph, tg);
+            else
+                prep_sample<float, false, 28>(RP, key.k[kk], tb + (size_t)(tt + 1) * 25 * N, tb + (size_t)tt * 25 * N,
+                                              tb + (size_t)(tt > 0 ? tt - 1 : 0) * 25 * N, src.controls + (size_t)(bb * T_ + tt) * 4, x, ph, tg);
+            float4* xr = reinterpret_cast<float4*>(X + (size_t)qr * 32);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) xr[i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+        };
+        if (FUSE && my_tiles > 0) {
+            if (grp == 1) prep_tile(blockIdx.x);
+            asm volatile("bar.sync 1, 256;" ::: "memory");      // the samples of the first tile are visible to the whole CTA
+        }
         if (my_tiles > 0) load_x(blockIdx.x);
         for (int64_t t = 0; t < my_tiles; ++t) {
             const int64_t tile = blockIdx.x + t * gridDim.x;
@@ -366,6 +400,7 @@ kc_train_tc3_kernel(int hidden, int nsub, const unsigned char* __restrict__ img,
             umma::fence_before();
             umma::mbar_arrive(&bars->dordy);
             TC3_TR(31);
+            if (FUSE && grp == 1 && t + 1 < my_tiles) prep_tile(tile + gridDim.x);   // off the critical path: dO does not wait for it
             // ---- backward epilogues: thread = unit `row` of chunk j >> 1, columns = samples 64 (j & 1) + 32 grp + i.  a = ELU(z),
             // dz = dA ELU'(z) go back in place as packed bf16 hi | lo (the A operands of the gradient MMAs).  Samples beyond Q
             // and units beyond H carry z = dA = 0 (zero X rows / zero weight rows): they contribute nothing ----
@@ -401,6 +436,7 @@ kc_train_tc3_kernel(int hidden, int nsub, const unsigned char* __restrict__ img,
             }
             // X / dO of the next tile overwrite what this tile's gradient MMAs read (the next tile's inputs are fetched into
             // registers first: their latency hides behind this wait)
+            if (FUSE) asm volatile("bar.sync 1, 256;" ::: "memory");   // group 1's samples of the next tile are visible
             if (t + 1 < my_tiles) load_x(tile + gridDim.x);
             umma::mbar_wait(&bars->gdone, phg); phg ^= 1;
             umma::fence_after();
@@ -445,17 +481,29 @@ kc_train_tc3_kernel(int hidden, int nsub, const unsigned char* __restrict__ img,
     if (warp == 0) umma::tmem_dealloc(tbase, 512);
 }
 
-// Host side: same contract as kc_train_tc_launch (kc_train_tc.cu); `img`: 192 KB of workspace.
-int kc_train_tc3_launch(const kc_mlp* mlp, float ds, int64_t Q, int T_, int K, const float* X, const float* PHYS, const float* TGT,
+// Host side: same contract as kc_train_tc_launch (kc_train_tc.cu); `img`: 192 KB of workspace.  With `src` (trajectory,
+// controls, rod constants, key nodes) the kernel forms its own samples and the caller skips the prep kernel.
+int kc_train_tc3_launch(const kc_mlp* mlp, float ds, int64_t Q, int T_, int K, float* X, float* PHYS, float* TGT,
                         unsigned char* img, float* partial, int64_t NP, double* loss_part, float* pred_out, int grid,
-                        cudaStream_t st) {
+                        cudaStream_t st, const RodC<float>* RP, const KeyIdx64* key, const float* traj, const float* controls,
+                        int64_t B) {
     const int nsub = 2 * ((mlp->hidden + 127) / 128);
     kc_tc3_prep_weights_kernel<<<32, 256, 0, st>>>((const float*)mlp->W1, (const float*)mlp->b1, (const float*)mlp->W2,
                                                    mlp->hidden, img);
     KC_CHECK_LAUNCH("kc_tc3_prep_weights_kernel");
-    cudaFuncSetAttribute(kc_train_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc3::SMEM_BYTES);
-    kc_train_tc3_kernel<<<grid, 288, tc3::SMEM_BYTES, st>>>(mlp->hidden, nsub, img, (const float*)mlp->b2, ds, Q, T_, K, X, PHYS, TGT,
-                                                            partial, NP, loss_part, pred_out);
+    if (RP) {
+        const Tc3Src src{traj, controls, B};
+        cudaFuncSetAttribute(kc_train_tc3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc3::SMEM_BYTES);
+        kc_train_tc3_kernel<true><<<grid, 288, tc3::SMEM_BYTES, st>>>(mlp->hidden, nsub, img, (const float*)mlp->b2, ds, Q, T_, K, X, PHYS,
+                                                                      TGT, partial, NP, loss_part, pred_out, *RP, *key, src);
+    } else {
+        const RodC<float> none{};
+        const KeyIdx64 nokey{};
+        const Tc3Src src{nullptr, nullptr, 0};
+        cudaFuncSetAttribute(kc_train_tc3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc3::SMEM_BYTES);
+        kc_train_tc3_kernel<false><<<grid, 288, tc3::SMEM_BYTES, st>>>(mlp->hidden, nsub, img, (const float*)mlp->b2, ds, Q, T_, K, X, PHYS,
+                                                                       TGT, partial, NP, loss_part, pred_out, none, nokey, src);
+    }
     KC_CHECK_LAUNCH("kc_train_tc3_kernel");
     return KC_OK;
 }

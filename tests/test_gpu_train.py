@@ -358,6 +358,18 @@ def test_train_step_config3_full_size_properties(ops, monkeypatch):
             assert np.abs(a - r).max() < 1e-4 * np.abs(r).max(), (name, k)
     for a, b in zip(raw1, raw2):
         assert torch.equal(a, b)                                             # deterministic reduction
+    # (5) the kernel that forms its own samples (default only below one tile per SM) and the stand-alone prep kernel feed
+    # the same values to the same arithmetic: bitwise identical, at the full size and at a one-tile-per-CTA size
+    for sl_ in (slice(None), slice(0, 100)):
+        res = []
+        for fuse in ("1", "0"):
+            monkeypatch.setenv("KC_TRAIN_FUSE_PREP", fuse)
+            lf, _, rawf = run(torch.float32, None, sl_)
+            res.append((lf, rawf))
+        monkeypatch.delenv("KC_TRAIN_FUSE_PREP", raising=False)
+        assert res[0][0] == res[1][0]
+        for a, b in zip(res[0][1], res[1][1]):
+            assert torch.equal(a, b)
     la, ga, _ = run(torch.float64, None, slice(0, 300))
     lb, gb, _ = run(torch.float64, None, slice(300, B))
     assert abs(la + lb - l64) < 1e-11 * l64
