@@ -58,6 +58,7 @@ struct Bars {
     uint32_t tmem_slot;
     double redd[8];
     float redb[4 * 25];
+    float b2s[32];
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
@@ -236,7 +237,9 @@ kc_train_tc3_kernel(int hidden, int nsub, const unsigned char* __restrict__ img,
         const uint32_t laneblk = (uint32_t)((warp & 3) * 32) << 16;
         uint32_t phzf = 0, phzb = 0, pho = 0, phg = 0;
         double lossacc = 0.0;
-        if (tid < 100) bars->redb[tid] = 0.f;     // gb2 partial sums, one row of 25 per warp of group 0 (only that warp touches it)
+        if (tid < 100) bars->redb[tid] = 0.f;     // gb2 partial sums: row (warp & 3), columns 0..7 by group 0, 8..24 by group 1
+        if (tid >= 128 && tid < 160) bars->b2s[tid - 128] = tid - 128 < 25 ? b2[tid - 128] : 0.f;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         float xv[16];
         // this thread's 16 inputs of a sample (columns 28..31 of X are never read from memory; column 28 := 1)
         auto load_x = [&](int64_t tile_) {
@@ -326,75 +329,102 @@ kc_train_tc3_kernel(int hidden, int nsub, const unsigned char* __restrict__ img,
                 umma::ld32(tbase + laneblk + COL_W + grp * 32, zA);
                 for (int s = 0; s < nsub; s += 2) { fwd_step(s, zA, zB); fwd_step(s + 1, zB, zA); }
             }
-            // physics prediction and target of this sample, and the target's Euler angles: formed while the last GEMM2 drains
-            float ph[25], tg[25], et[3];
-            if (grp == 0 && valid) {
+            // ---- loss and dL/do, split over the two thread groups of a sample row: group 0 takes outputs 0..7 (position,
+            // quaternion -> Euler angles, n_x), group 1 outputs 8..24 (n_y, n_z, m, q, w, v, u).  The physics prediction, the
+            // target and the target's Euler angles are fetched / formed while the last GEMM2 drains ----
+            float ph[17], tg[17], et[3];
+            if (valid) {
+                if (grp == 0) {
 #pragma unroll
-                for (int r = 0; r < 25; ++r) { ph[r] = PHYS[(size_t)qrow * 25 + r]; tg[r] = TGT[(size_t)qrow * 25 + r]; }
-                quat_to_euler(tg + 3, et);
+                    for (int r = 0; r < 8; ++r) { ph[r] = PHYS[(size_t)qrow * 25 + r]; tg[r] = TGT[(size_t)qrow * 25 + r]; }
+                    quat_to_euler(tg + 3, et);
+                } else {
+#pragma unroll
+                    for (int r = 0; r < 17; ++r) { ph[r] = PHYS[(size_t)qrow * 25 + 8 + r]; tg[r] = TGT[(size_t)qrow * 25 + 8 + r]; }
+                }
             }
             umma::mbar_wait(&bars->ordy, pho); pho ^= 1;
             umma::fence_after();
             TC3_TR(30);
-            if (grp == 0) {
-                float o[25], g[25];
-                {
-                    uint32_t v[32];
-                    umma::ld32(tbase + laneblk + COL_O, v);
-                    umma::wait_ld();
+            {
+                const float S = float(T_ - 1);
+                const float wp = 1.f / (float(3 * K) * S), wf = 1.f / (float(12 * K) * S), wz = 1.f / (float(6 * K) * S);
+                uint32_t v[32];
+                umma::ld32(tbase + laneblk + COL_O, v);
+                umma::wait_ld();
+                float acc = 0.f;
+                float* po = nullptr;
+                if (pred_out && valid) po = pred_out + (size_t)(qrow / K) * 25 * K + (int)(qrow % K);
+                if (grp == 0) {
+                    float g[8];
 #pragma unroll
-                    for (int c = 0; c < 25; ++c) { o[c] = __uint_as_float(v[c]) + b2[c]; g[c] = 0.f; }
-                }
-                if (valid) {
-                    float pred[25];
+                    for (int c = 0; c < 8; ++c) g[c] = 0.f;
+                    if (valid) {
+                        float pred[8];
 #pragma unroll
-                    for (int r = 0; r < 19; ++r) pred[r] = ph[r] + ds * o[r];
+                        for (int r = 0; r < 8; ++r) pred[r] = ph[r] + ds * (__uint_as_float(v[r]) + bars->b2s[r]);
 #pragma unroll
-                    for (int c = 19; c < 25; ++c) pred[c] = ph[c] + o[c];
-                    const float S = float(T_ - 1);
-                    const float wp = 1.f / (float(3 * K) * S), wf = 1.f / (float(12 * K) * S), wz = 1.f / (float(6 * K) * S);
-                    float acc = 0.f;
+                        for (int r = 0; r < 3; ++r) { const float e = pred[r] - tg[r]; acc += wp * e * e; g[r] = 2.f * wp * e * ds; }
+                        { const float e = pred[7] - tg[7]; acc += wf * e * e; g[7] = 2.f * wf * e * ds; }
+                        float ep[3], ge[3], gq[4];
+                        quat_to_euler(pred + 3, ep);
 #pragma unroll
-                    for (int r = 0; r < 3; ++r) { const float e = pred[r] - tg[r]; acc += wp * e * e; g[r] = 2.f * wp * e * ds; }
+                        for (int i = 0; i < 3; ++i) { const float e = ep[i] - et[i]; acc += wp * e * e; ge[i] = 2.f * wp * e; }
+                        quat_to_euler_vjp(pred + 3, ge, gq);
 #pragma unroll
-                    for (int r = 7; r < 19; ++r) { const float e = pred[r] - tg[r]; acc += wf * e * e; g[r] = 2.f * wf * e * ds; }
+                        for (int i = 0; i < 4; ++i) g[3 + i] = gq[i] * ds;
+                        if (po) {
 #pragma unroll
-                    for (int r = 19; r < 25; ++r) { const float e = pred[r] - tg[r]; acc += wz * e * e; g[r] = 2.f * wz * e; }
-                    float ep[3], ge[3], gq[4];
-                    quat_to_euler(pred + 3, ep);
-#pragma unroll
-                    for (int i = 0; i < 3; ++i) { const float e = ep[i] - et[i]; acc += wp * e * e; ge[i] = 2.f * wp * e; }
-                    quat_to_euler_vjp(pred + 3, ge, gq);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) g[3 + i] = gq[i] * ds;
-                    lossacc += (double)acc;
-                    if (pred_out) {
-                        const int kk = (int)(qrow % K);
-                        const int64_t bt = qrow / K;
-                        float* po = pred_out + (size_t)bt * 25 * K + kk;
-#pragma unroll
-                        for (int r = 0; r < 25; ++r) po[r * K] = pred[r];
+                            for (int r = 0; r < 8; ++r) po[r * K] = pred[r];
+                        }
                     }
-                }
-                // gb2 += sum over the warp's 32 samples (kept in shared memory: 25 live registers less in the epilogue loops)
+                    // gb2 += sum over the warp's 32 samples (kept in shared memory: 25 live registers less in the epilogue loops)
 #pragma unroll
-                for (int c = 0; c < 25; ++c) {
-                    float sg = g[c];
+                    for (int c = 0; c < 8; ++c) {
+                        float sg = g[c];
 #pragma unroll
-                    for (int o2 = 16; o2 > 0; o2 >>= 1) sg += __shfl_xor_sync(0xffffffffu, sg, o2);
-                    if (lane == 0) bars->redb[warp * 25 + c] += sg;
-                }
-#pragma unroll
-                for (int gi = 0; gi < 4; ++gi) {
-                    float g8[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) { const int c = gi * 8 + j; g8[j] = c < 25 ? g[c < 25 ? c : 0] : 0.f; }
+                        for (int o2 = 16; o2 > 0; o2 >>= 1) sg += __shfl_xor_sync(0xffffffffu, sg, o2);
+                        if (lane == 0) bars->redb[(warp & 3) * 25 + c] += sg;
+                    }
                     uint4 hi, lo;
-                    split8(g8, hi, lo);
-                    const uint32_t off = umma::mnmajor_off_b16(gi * 8, row, 128);
+                    split8(g, hi, lo);
+                    const uint32_t off = umma::mnmajor_off_b16(0, row, 128);
                     *reinterpret_cast<uint4*>(sm + OFF_DO + off) = hi;
                     *reinterpret_cast<uint4*>(sm + OFF_DO + 8192 + off) = lo;
+                } else {
+                    float g[24];     // outputs 8..31 (25..31 are padding)
+#pragma unroll
+                    for (int c = 0; c < 24; ++c) g[c] = 0.f;
+                    if (valid) {
+#pragma unroll
+                        for (int r = 0; r < 17; ++r) {
+                            const int c = 8 + r;
+                            const float o = __uint_as_float(v[c]) + bars->b2s[c];
+                            const float pred = ph[r] + (c < 19 ? ds * o : o);
+                            const float e = pred - tg[r];
+                            const float wgt = c < 19 ? wf : wz;
+                            acc += wgt * e * e;
+                            g[r] = c < 19 ? 2.f * wgt * e * ds : 2.f * wgt * e;
+                            if (po) po[c * K] = pred;
+                        }
+                    }
+#pragma unroll
+                    for (int r = 0; r < 17; ++r) {
+                        float sg = g[r];
+#pragma unroll
+                        for (int o2 = 16; o2 > 0; o2 >>= 1) sg += __shfl_xor_sync(0xffffffffu, sg, o2);
+                        if (lane == 0) bars->redb[(warp & 3) * 25 + 8 + r] += sg;
+                    }
+#pragma unroll
+                    for (int gi = 0; gi < 3; ++gi) {
+                        uint4 hi, lo;
+                        split8(g + 8 * gi, hi, lo);
+                        const uint32_t off = umma::mnmajor_off_b16(8 + gi * 8, row, 128);
+                        *reinterpret_cast<uint4*>(sm + OFF_DO + off) = hi;
+                        *reinterpret_cast<uint4*>(sm + OFF_DO + 8192 + off) = lo;
+                    }
                 }
+                if (valid) lossacc += (double)acc;
             }
             umma::fence_async_smem();
             umma::fence_before();
@@ -474,7 +504,9 @@ kc_train_tc3_kernel(int hidden, int nsub, const unsigned char* __restrict__ img,
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (tid < 25) out[ob2 + tid] = bars->redb[tid] + bars->redb[25 + tid] + bars->redb[50 + tid] + bars->redb[75 + tid];
-        if (tid == 0) loss_part[blockIdx.x] = bars->redd[0] + bars->redd[1] + bars->redd[2] + bars->redd[3];
+        if (tid == 0)
+            loss_part[blockIdx.x] = ((bars->redd[0] + bars->redd[1]) + (bars->redd[2] + bars->redd[3])) +
+                                    ((bars->redd[4] + bars->redd[5]) + (bars->redd[6] + bars->redd[7]));
     }
     umma::fence_before();
     __syncthreads();
