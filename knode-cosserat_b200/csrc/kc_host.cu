@@ -60,6 +60,7 @@ static cudaStream_t g_copy_stream[64] = {};
 constexpr size_t KC_STAGE_CHUNK = (size_t)32 << 20;
 constexpr int KC_STAGE_SLOTS = 4;
 static unsigned char* g_stage[64] = {};
+static std::mutex g_stage_mu[64];     // the ring of a device serves one call at a time (concurrent callers queue here)
 
 static bool host_ptr_is_pinned(const void* p) {
     cudaPointerAttributes a;
@@ -175,6 +176,8 @@ extern "C" int kc_rollout_host(int dtype, const kc_rod_params* P, const kc_mlp* 
     // pageable destination -> pinned ring + host copy threads (see above); pinned destination -> direct copies
     Stager stg;
     bool staged = !host_ptr_is_pinned(traj_host);
+    std::unique_lock<std::mutex> ring_lock(g_stage_mu[dev], std::defer_lock);
+    if (staged) ring_lock.lock();
     if (staged) {
         if (!g_stage[dev] && cudaHostAlloc((void**)&g_stage[dev], KC_STAGE_CHUNK * KC_STAGE_SLOTS, cudaHostAllocDefault) != cudaSuccess) {
             cudaGetLastError();

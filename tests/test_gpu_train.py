@@ -228,6 +228,41 @@ def test_adam_clamp_multi_matches_single_tensor_kernels(ops):
     assert int(multi.step_dev.item()) == 3 and int(multi.ticket.item()) == 0
 
 
+@pytest.mark.parametrize("H", [512, 200])
+def test_train_step_kernel_generations_agree(ops, monkeypatch, H):
+    """The three generations of the tensor-core training kernel (KC_TRAIN_TC = 1 | 2 | default 3; kc_train_tc.cu,
+    kc_train_tc2.cu, kc_train_tc3.cu) and the fused-prep variant of the third compute the same step: loss and gradients agree
+    with the fp64 kernels at the fp32 tolerance, on a batch with several tiles per CTA and a ragged last tile."""
+    import physics_controls
+    P = P_setup()
+    B, T, key = 200, 30, [3, 5, 7, 9]              # 23 200 samples: 182 tiles, the last one partly filled
+    ctl = physics_controls.synthetic_tensions(B, T, P.del_t, seed=5, dtype=np.float32)
+    traj32, _, iters = ops.rollout(params(P), None, dev(ctl, torch.float32))
+    assert int(iters.min()) >= 0
+    g = torch.Generator().manual_seed(H)
+    W = [torch.normal(0.01, 0.02, (H, 28), generator=g), torch.normal(0.0, 0.01, (H,), generator=g),
+         torch.normal(0.01, 0.02, (25, H), generator=g), torch.normal(0.0, 0.01, (25,), generator=g)]
+
+    def run(dt, gen, fuse=None):
+        for k, v in (("KC_TRAIN_TC", gen), ("KC_TRAIN_FUSE_PREP", fuse)):
+            if v is None:
+                monkeypatch.delenv(k, raising=False)
+            else:
+                monkeypatch.setenv(k, v)
+        mlp = ops.Mlp(*[w.to("cuda", dt) for w in W])
+        loss, grads, _ = ops.train_step(params(P), mlp, traj32.to(dt), dev(ctl, dt), key)
+        return float(loss.item()), [x.cpu().numpy().astype(np.float64) for x in grads]
+
+    l64, g64 = run(torch.float64, None)
+    for gen, fuse in (("1", None), ("2", None), (None, "0"), (None, "1")):
+        l, gr = run(torch.float32, gen, fuse)
+        assert abs(l - l64) < 1e-5 * abs(l64), (gen, fuse)
+        for k, a, r in zip(PK, gr, g64):
+            assert np.abs(a - r).max() < 1e-4 * np.abs(r).max(), (gen, fuse, k)
+    monkeypatch.delenv("KC_TRAIN_TC", raising=False)
+    monkeypatch.delenv("KC_TRAIN_FUSE_PREP", raising=False)
+
+
 @pytest.mark.parametrize("H", [512, 200, 64])
 def test_param_grads_tensor_core_vs_simt_and_fp64(ops, monkeypatch, H):
     """kc_mlp_bwd with enough samples takes the tcgen05 gradient kernel (kc_train_tc_kernel<2>); same numbers as the SIMT
