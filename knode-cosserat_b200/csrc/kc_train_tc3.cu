@@ -2,8 +2,8 @@
 // formats as kc_train_tc2.cu (physics_train.py:313-368; fp32 model, 28 inputs, hidden <= 512; bf16 hi/lo in 3 passes =
 // fp32-grade), with the BACKWARD half transposed so that no activation ever goes through shared memory:
 //
-// The clock64 timeline of kc_train_tc3_kernel (tools/trace_train_tc2.py (KC_TRACE_GEN=3)) showed a tile of 128 samples taking 46.8k cycles of
-// which 24k were the backward epilogues (3.0k per 64-unit sub-chunk: 1.4k of issue, 0.7k of shared-memory stores of the a / dz
+// The clock64 timeline of kc_train_tc2_kernel (tools/trace_train_tc2.py, KC_TRACE_GEN=2) showed a tile of 128 samples taking 46.8k
+// cycles of which 24k were the backward epilogues (3.0k per 64-unit sub-chunk: 1.4k of issue, 0.7k of shared-memory stores of the a / dz
 // tiles - 64 KB per sub-chunk, bandwidth bound - and the rest barrier / fence latency), while the gradient MMAs re-read those
 // tiles three times (240 KB per 128 units: 40 cycles per N = 32 MMA, shared-memory bound).
 //
@@ -23,7 +23,11 @@
 //   backward: two buffers of [Z^T 64 | dA^T 64] (256, 384); step j = (chunk j >> 1, sample half j & 1) uses buffer j & 1
 // Backward per step: Z^T and dA^T (one commit) -> epilogue in place -> 24 gradient MMAs from TMEM, then the refill of the same
 // buffer for step j + 2 (the tensor pipe executes in issue order, so no barrier is needed between the two).
-// At the end every CTA writes one partial-gradient slice in the layout kc_train_reduce_kernel sums.
+// Packed layouts inside a thread group's 32 columns: forward [hi 16 | lo 16] (two 16-column stores), backward [hi 8 | lo 8] per
+// 16 samples (8-column stores: measured faster).  A 3-pass product is ONE issue batch (one elect.sync per 6 / 12 MMAs).
+// The loss of a sample row is split over the two groups (outputs 0..7 with the Euler angles | outputs 8..24).
+// At the end every CTA writes one partial-gradient slice in the layout kc_train_reduce_kernel sums.  A tile now takes 34.5k
+// cycles (DESIGN.md section 5 has the timeline and the measured history 199 -> 148 us).
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include "kc_rod.cuh"
