@@ -15,20 +15,21 @@ kc_umma_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B
     float* sB = reinterpret_cast<float*>(smem + (size_t)128 * K * 4);  // N x K
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint32_t ncols = 32;
-    while ((int)ncols < N + (mn_major == 3 ? K / 2 : 0)) ncols <<= 1;
+    while ((int)ncols < N + (mn_major >= 3 ? K / 2 : 0)) ncols <<= 1;
     if (warp == 0) umma::tmem_alloc(&tmem_slot, ncols);
     if (tid == 0) umma::mbar_init(&bar, 1);
     unsigned char* bA = reinterpret_cast<unsigned char*>(sA);
     unsigned char* bB = bA + (mn_major == 2 ? (size_t)128 * K * 2 : (size_t)128 * K * 4);
-    if (mn_major == 3) bB = bA;   // mode 3: A goes to TMEM, only B is staged in shared memory (K-major bf16)
-    for (int e = tid; e < 128 * K && mn_major != 3; e += 128) {
+    if (mn_major >= 3) bB = bA;   // modes 3, 4: A goes to TMEM, only B is staged in shared memory (bf16)
+    for (int e = tid; e < 128 * K && mn_major < 3; e += 128) {
         const int r = e / K, k = e - r * K;
         if (mn_major == 2) *reinterpret_cast<__nv_bfloat16*>(bA + umma::mnmajor_off_b16(r, k, K)) = __float2bfloat16(A[e]);
         else *reinterpret_cast<float*>(bA + (mn_major ? umma::mnmajor_off(r, k, K) : umma::kmajor_off(r, k, K))) = A[e];
     }
     for (int e = tid; e < N * K; e += 128) {
         const int r = e / K, k = e - r * K;
-        if (mn_major == 3) *reinterpret_cast<__nv_bfloat16*>(bB + umma::kmajor_off_b16(r, k, K)) = __float2bfloat16(B[e]);
+        if (mn_major == 4) *reinterpret_cast<__nv_bfloat16*>(bB + umma::kmajor_off_b16(k, r, N)) = __float2bfloat16(B[e]);   // B^T [K][N], K-major image
+        else if (mn_major == 3) *reinterpret_cast<__nv_bfloat16*>(bB + umma::kmajor_off_b16(r, k, K)) = __float2bfloat16(B[e]);
         else if (mn_major == 2) *reinterpret_cast<__nv_bfloat16*>(bB + umma::mnmajor_off_b16(r, k, K)) = __float2bfloat16(B[e]);
         else *reinterpret_cast<float*>(bB + (mn_major ? umma::mnmajor_off(r, k, K) : umma::kmajor_off(r, k, K))) = B[e];
     }
@@ -37,7 +38,7 @@ kc_umma_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B
     __syncthreads();
     umma::fence_after();
     const uint32_t tbase = tmem_slot;
-    if (mn_major == 3) {
+    if (mn_major >= 3) {
         // A[row][k] as packed bf16 pairs in TMEM columns N .. N + K/2 of this thread's lane (row = warp*32 + lane)
         const int row = warp * 32 + lane;
         for (int c0 = 0; c0 < K / 2; c0 += 16) {
@@ -55,7 +56,15 @@ kc_umma_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B
         umma::fence_after();
     }
     if (tid == 0) {
-        if (mn_major == 3) {  // bf16, A from TMEM (8 packed columns per K = 16), B K-major in shared memory
+        if (mn_major == 4) {  // as mode 3, but B is the K-major image of B^T ([K rows][N]): read as an MN-major B operand whose
+                              // k-groups are (N/8)*128 bytes apart (LBO) and whose n-groups are 128 bytes apart (SBO)
+            const uint32_t idesc = umma::make_idesc_bf16(128, N, 0, 1);
+            const uint32_t lbo = (uint32_t)(N / 8) * 128;
+            for (int kk = 0; kk < K / 16; ++kk) {
+                const uint64_t db = umma::make_desc(umma::smem_u32(bB) + kk * 2 * lbo, lbo, 128);
+                umma::mma_bf16_ts(tbase, tbase + N + kk * 8, db, idesc, kk > 0 ? 1u : 0u);
+            }
+        } else if (mn_major == 3) {  // bf16, A from TMEM (8 packed columns per K = 16), B K-major in shared memory
             const uint32_t idesc = umma::make_idesc_bf16(128, N, 0, 0);
             const uint32_t sbo = (uint32_t)(K / 8) * 128;
             for (int kk = 0; kk < K / 16; ++kk) {
@@ -100,7 +109,7 @@ kc_umma_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B
 // D[128][N] = A[128][K] B[N][K]^T on the tensor cores; N % 16 == 0, 16 <= N <= 256, K % 8 == 0, (128+N)*K*4 <= 200 KB.
 extern "C" int kc_umma_selftest(const void* A, const void* B, void* D, int32_t N, int32_t K, int32_t mn_major, void* stream) {
     KC_CHECK_ARG(A && B && D, "NULL pointer");
-    KC_CHECK_ARG(N % 16 == 0 && N >= 16 && N <= 256 && K % 8 == 0 && K >= 8 && (mn_major < 2 || K % 32 == 0 || (mn_major == 2 && K % 16 == 0)), "need N %% 16 == 0 in [16,256], K %% 8 == 0 (16 for bf16)");
+    KC_CHECK_ARG(N % 16 == 0 && N >= 16 && N <= 256 && K % 8 == 0 && K >= 8 && (mn_major < 2 || K % 32 == 0 || (mn_major == 2 && K % 16 == 0)) && mn_major <= 4, "need N %% 16 == 0 in [16,256], K %% 8 == 0 (16 for bf16)");
     const size_t smem = (size_t)(128 + N) * K * 4;
     KC_CHECK_ARG(smem <= 200 * 1024, "tile too large for shared memory");
     cudaFuncSetAttribute(kc_umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

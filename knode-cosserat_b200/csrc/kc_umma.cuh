@@ -202,7 +202,8 @@ __device__ __forceinline__ void mbar_arrive_w(uint64_t* bar) {
 // B: shared-memory descriptors of the hi and lo images, advancing 256 B (16 descriptor units) per k-step.
 // O1..O3: column offsets of k-steps 1..3, LO: offset of the lo half (defaults: the layout described above; the transposed
 // backward of kc_train_tc3.cu uses [hi 8 | lo 8] per k-step: O = 16, 32, 48, LO = 8).
-template <int O1 = 8, int O2 = 32, int O3 = 40, int LO = 16>
+// BSTEP: descriptor increment (bytes >> 4) of one k-step of the B images.
+template <int O1 = 8, int O2 = 32, int O3 = 40, int LO = 16, int BSTEP = 16>
 __device__ __forceinline__ void mma_bf16_ts_3x4_w(uint32_t d_tmem, uint32_t a_tmem, uint64_t bh, uint64_t bl, uint32_t idesc,
                                                   uint32_t accumulate) {
     asm volatile(
@@ -212,8 +213,8 @@ __device__ __forceinline__ void mma_bf16_ts_3x4_w(uint32_t d_tmem, uint32_t a_tm
         "setp.eq.u32 t, 0, 0;\n\t"
         "mov.b32 a0, %1;\n\tadd.u32 a1, %1, %6;\n\tadd.u32 a2, %1, %7;\n\tadd.u32 a3, %1, %8;\n\t"
         "add.u32 l0, %1, %9;\n\tadd.u32 l1, %1, %10;\n\tadd.u32 l2, %1, %11;\n\tadd.u32 l3, %1, %12;\n\t"
-        "mov.b64 h0, %2;\n\tadd.u64 h1, %2, 16;\n\tadd.u64 h2, %2, 32;\n\tadd.u64 h3, %2, 48;\n\t"
-        "mov.b64 g0, %3;\n\tadd.u64 g1, %3, 16;\n\tadd.u64 g2, %3, 32;\n\tadd.u64 g3, %3, 48;\n\t"
+        "mov.b64 h0, %2;\n\tadd.u64 h1, %2, %13;\n\tadd.u64 h2, %2, %14;\n\tadd.u64 h3, %2, %15;\n\t"
+        "mov.b64 g0, %3;\n\tadd.u64 g1, %3, %13;\n\tadd.u64 g2, %3, %14;\n\tadd.u64 g3, %3, %15;\n\t"
         "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a0], h0, %4, p;\n\t"
         "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a1], h1, %4, t;\n\t"
         "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a2], h2, %4, t;\n\t"
@@ -227,7 +228,7 @@ __device__ __forceinline__ void mma_bf16_ts_3x4_w(uint32_t d_tmem, uint32_t a_tm
         "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a2], g2, %4, t;\n\t"
         "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a3], g3, %4, t;\n\t}"
         ::"r"(d_tmem), "r"(a_tmem), "l"(bh), "l"(bl), "r"(idesc), "r"(accumulate), "n"(O1), "n"(O2), "n"(O3), "n"(LO), "n"(O1 + LO),
-          "n"(O2 + LO), "n"(O3 + LO) : "memory");
+          "n"(O2 + LO), "n"(O3 + LO), "n"(BSTEP), "n"(2 * BSTEP), "n"(3 * BSTEP) : "memory");
 }
 // SS form, 3 passes x 2 k-steps (K = 32): D = A B^T from scratch (the first instruction overwrites D); astep / bstep are the
 // descriptor increments (bytes >> 4) of one k-step of 16.

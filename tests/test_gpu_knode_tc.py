@@ -62,6 +62,22 @@ def test_umma_selftest_a_operand_in_tmem(N, K):
     assert torch.equal(D, A @ B.T)     # small integers: exact in bf16 operands and fp32 accumulation
 
 
+@pytest.mark.parametrize("N,K", [(32, 64), (32, 128), (64, 32)])
+def test_umma_selftest_b_operand_from_transposed_image(N, K):
+    """mode 4: as mode 3, but B is staged as the K-major image of B^T ([K rows][N]) and read as an MN-major operand with
+    LBO = (N/8)*128 (next 8 k) and SBO = 128 (next 8 n): one weight image then serves the GEMM that contracts over its rows
+    and the GEMM that contracts over its columns."""
+    import _kc
+    A = torch.randint(-8, 9, (128, K), device="cuda").float()
+    B = torch.randint(-8, 9, (N, K), device="cuda").float()
+    D = torch.full((128, N), float("nan"), device="cuda")
+    rc = _kc.lib().kc_umma_selftest(C.c_void_p(A.data_ptr()), C.c_void_p(B.data_ptr()), C.c_void_p(D.data_ptr()), N, K, 4,
+                                    C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    _kc.check(rc, "kc_umma_selftest")
+    torch.cuda.synchronize()
+    assert torch.equal(D, A @ B.T)
+
+
 def _params(P):
     import _kc
     return _kc.rod_params(P)
