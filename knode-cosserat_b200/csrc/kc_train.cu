@@ -724,9 +724,16 @@ kc_peer_gather_adam_kernel(const __grid_constant__ PeerRegions R, const __grid_c
     }
     __syncthreads();
     const size_t so = (size_t)(e & 1u) * n_pad;
+    // all peers' values are requested before any is used (a loop of load -> add would pay one NVLink round trip per rank);
+    // the sum is then formed in rank order, so every rank adds the same numbers in the same order
     auto gather = [&](int64_t fi) {
+        T v[8];
+#pragma unroll
+        for (int p = 0; p < 8; ++p)
+            v[p] = p < R.world ? *reinterpret_cast<const volatile T*>(reinterpret_cast<const T*>(R.r[p]) + so + fi) : T(0);
         T s = T(0);
-        for (int p = 0; p < R.world; ++p) s += *reinterpret_cast<const volatile T*>(reinterpret_cast<const T*>(R.r[p]) + so + fi);
+#pragma unroll
+        for (int p = 0; p < 8; ++p) if (p < R.world) s += v[p];
         flat[fi] = s;
         return s;
     };
