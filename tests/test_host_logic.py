@@ -201,3 +201,34 @@ def test_data_processing_matches_reference_behaviour():
     n2, lo2, span2 = normalize_data(d2)
     np.testing.assert_array_equal(lo2, d2.min(axis=0))
     np.testing.assert_allclose(denormalize_data(n2, lo2, lo2 + span2), d2, rtol=0, atol=1e-15)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs next to ours) prints ONE JSON line with the contract keys and
+    needs no GPU: it times the oracle port of knode.simulate on the host cores on a bounded sample."""
+    import json, subprocess, sys, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.strip().splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "rod-node-steps/sec" and d["unit"] == "rod-node-steps/s"
+    assert d["value"] > 0 and d["higher_is_better"] is True and d["n_gpus"] == 1
+    assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+
+
+def test_product_path_fails_loudly_without_cuda():
+    """No CPU fallback: on a machine without a CUDA device the drop-in raises instead of computing on the host."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("needs a machine without CUDA")
+    import numpy as np
+    from cosserat_ode import CosseratRod
+    from knode import setup_robot, simulate
+    robot = CosseratRod(use_fsolve=True)
+    setup_robot(robot)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        simulate(robot, np.zeros((3, 4)))
