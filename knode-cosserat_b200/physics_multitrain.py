@@ -152,6 +152,11 @@ def main(argv=None):
                             print(f';{dtw:.2f} ({pct_error(dtw, base["dtw"]):+.1f}%)'.ljust(20), end='')
                             print(f';{mse:.2f} ({pct_error(mse, base["mse"]):+.1f}%)'.ljust(20), end='')
                     print()
+    if world > 1:
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.barrier()                 # the other ranks leave only after rank 0 has read every checkpoint
+            dist.destroy_process_group()
 
 
 if __name__ == "__main__":
