@@ -130,7 +130,7 @@ def main(argv=None, distributed=True):
         if torch_robot is not None:
             transplant(robot_eval, torch_robot)
         # rollout and metric stay on the device: only the DTW scalar comes back (kc_rollout_fwd -> kc_eval_metrics)
-        traj_dev = simulate(robot_eval, ctl_val_dev[:eval_len], device_out=True)[:eval_len]
+        traj_dev = simulate(robot_eval, ctl_val_dev[:eval_len], device_out=True)[:eval_len, :25].contiguous()
         dtw_metric = float(_ops.eval_metrics(traj_dev, validation_reference_dev, node=9, want_mse=False)[0].item())
         print('Validation DTW Distance XYZ', dtw_metric)
         dtw_arr.append([dtw_metric])

@@ -220,6 +220,32 @@ def test_physics_train_script_reproduces_reference_losses(golden, tmp_path, monk
     assert saved["robot"].nn_models[0].weight.min() >= 0          # clamp applied
 
 
+def test_physics_train_script_with_its_evaluation(tmp_path, monkeypatch, capsys):
+    """python physics_train.py --fast --epochs 2 sine 1.0 with the evaluation ON (the default, physics_train.py:136-167 at epochs
+    0, 200, ...): the validation rollout and its DTW run on the device; the value printed at epoch 0 is the DTW of the
+    untrained KNODE rod against the reference rod, recomputed here with the oracle's DTW from two host rollouts."""
+    import physics_train
+    from knode import simulate, setup_robot
+    from cosserat_ode import CosseratRod
+    from physics_controls import calc_controls
+    from oracle import rod_oracle as O
+    monkeypatch.chdir(tmp_path)
+    robot, loss_arr = physics_train.main(["--fast", "--epochs", "2", "--seed", "0", "--mod", "youngs", "sine", "1.0"],
+                                         distributed=False)
+    out = capsys.readouterr().out
+    vals = [float(l.split()[-1]) for l in out.splitlines() if l.startswith("Validation DTW Distance XYZ")]
+    assert len(vals) == 1 and np.isfinite(vals[0]) and vals[0] > 0
+    saved = torch.load(tmp_path / "saved_models" / "physics_sine_1_0_youngs_trainlen_30_2_epoch_0.pth", weights_only=False)
+    assert saved["dtw"] == [[vals[0]]] and len(saved["loss"]) == 3
+    # epoch 0 evaluates robot_eval WITHOUT the network (physics_train.py:145 passes None): physics-only 'youngs' rod vs reference
+    ref_rod, mod_rod = CosseratRod(use_fsolve=True), CosseratRod(use_fsolve=True)
+    setup_robot(ref_rod); setup_robot(mod_rod, "youngs")
+    ctl = np.array(calc_controls("sine", 1.25, ref_rod.del_t, 100))
+    a = simulate(mod_rod, ctl)[:, :3, 9]
+    b = simulate(ref_rod, ctl)[:, :3, 9]
+    assert abs(vals[0] - O.dtw_l1(a, b)) < 1e-9 * max(1.0, vals[0])
+
+
 def test_train_segment_script_synthetic(tmp_path, monkeypatch):
     import train_segment
     monkeypatch.chdir(tmp_path)
