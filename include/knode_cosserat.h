@@ -259,8 +259,10 @@ int kc_fma_peak(int dtype, int64_t iters, double *flops_host, void *scratch, voi
 /* Tensor-core self-test (tcgen05.mma kind::tf32, accumulators in TMEM): D[128][N] = A[128][K] * B[N][K]^T in fp32 storage,
  * one CTA.  Pins the operand layout / descriptor / TMEM read-back conventions that the fused KNODE MLP kernels rely on.
  * N % 16 == 0 in [16, 256], K % 8 == 0.  mode (mn_major) 0: tf32 operands, K-major; 1: tf32, MN-major (not a legal
- * no-swizzle layout for tf32 - kept to document the failure); 2: bf16 operands, MN-major, K % 16 == 0.  Modes 0 and 2 are
- * the two shared-memory layouts the fused kernels use. */
+ * no-swizzle layout for tf32 - kept to document the failure); 2: bf16 operands, MN-major, K % 16 == 0; 3: bf16, A written to
+ * TMEM with tcgen05.st as packed pairs (".ts" MMA, the activation operand of the march and training kernels), B K-major,
+ * K % 32 == 0; 4: as 3 with B staged as the K-major image of B^T and read as an MN-major operand (LBO = (N/8)*128, SBO = 128).
+ * Modes 0, 2 and 3 are the layouts the fused kernels use. */
 int kc_umma_selftest(const void *A, const void *B, void *D, int32_t N, int32_t K, int32_t mn_major, void *stream);
 
 #ifdef __cplusplus
