@@ -15,7 +15,7 @@ F=$(cuobjdump -sass kc_knode_tc.o | grep "Function : _Z22kc_knode_tc_fwd_kernelI
 cuobjdump -sass -fun "$F" kc_knode_tc.o | grep -E "UTCHMMA|UTCBAR|LDTM|STTM" | sed 's#/\* 0x[0-9a-f]* \*/##' | awk '{$1=$1};1' | head -24
 echo "==== excerpt: kc_train_tc3_kernel, batched issue of a 3-pass gradient product (A operand in TMEM, one ELECT per 12 UTCHMMA)"
 F=$(cuobjdump -sass kc_train_tc3.o | grep "Function : _Z19kc_train_tc3_kernelILb0" | head -1 | sed "s/.*Function : //")
-cuobjdump -sass -fun "$F" kc_train_tc3.o | grep -E "UTCHMMA|UTCBAR|LDTM|STTM|ELECT|UBLKCP" | sed 's#/\* 0x[0-9a-f]* \*/##' | awk '{$1=$1};1' | sed -n 20,60p
+cuobjdump -sass -fun "$F" kc_train_tc3.o | grep -E "UTCHMMA|UTCBAR|LDTM|STTM|ELECT|UBLKCP" | sed 's#/\* 0x[0-9a-f]* \*/##' | awk '{$1=$1};1' | awk '/UTCHMMA/{f=1} f' | sed -n 1,44p
 echo "==== ptxas -v (registers / spills) of the tensor-core march kernels"
 nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a --expt-relaxed-constexpr --extended-lambda -Xptxas -v -c kc_knode_tc.cu -o /tmp/_k.o 2>&1 | grep -E "Compiling entry|Used|spill" | grep -A2 "kc_knode_tc_[fb]wd" | sed 's/ptxas info    : //'
 echo "==== ptxas -v of the training kernel"
